@@ -1,0 +1,209 @@
+"""Generate golden vectors by running the LIVE reference (mwydmuch/xCOLUMNs 0.0.3).
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the reference unmodified, with two environment shims that do not touch its
+arithmetic:
+  * ``np.product = np.prod``        (numpy >= 2 removed the alias used at block_coordinate.py:663)
+  * a stub ``autograd`` package     (absent here; grad() is served by torch float64 autograd)
+and stores inputs + outputs as small .npz files next to this script.  tests/test_oracle_golden.py
+replays them against oracle/ (bit-exact where the path is deterministic), and the -m gpu tests
+replay them against the CUDA path.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+from scipy.sparse import csr_matrix
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+REF = os.environ.get("XC_REFERENCE", "/root/reference")
+
+
+def _install_shims():
+    np.product = np.prod
+    stub = tempfile.mkdtemp(prefix="autograd_stub_")
+    os.makedirs(os.path.join(stub, "autograd"))
+    with open(os.path.join(stub, "autograd", "__init__.py"), "w") as f:
+        f.write(
+            "import numpy as _np\n"
+            "import torch as _torch\n"
+            "def grad(fun, argnum=0):\n"
+            "    argnums = list(argnum) if isinstance(argnum, (list, tuple)) else [argnum]\n"
+            "    def g(*args):\n"
+            "        ts = [_torch.tensor(_np.asarray(a, dtype=_np.float64), requires_grad=(i in argnums)) for i, a in enumerate(args)]\n"
+            "        val = fun(*ts)\n"
+            "        gs = _torch.autograd.grad(val, [ts[i] for i in argnums], allow_unused=True, materialize_grads=True)\n"
+            "        return tuple(x.detach().numpy() for x in gs)\n"
+            "    return g\n")
+    with open(os.path.join(stub, "autograd", "numpy.py"), "w") as f:
+        f.write("from numpy import *\nimport numpy as _np\nrandom = _np.random\n")
+    sys.path.insert(0, stub)
+    sys.path.insert(0, REF)
+
+
+def pred_to_idx(y_pred, k):
+    """(n, k) ascending label ids of a 0/1 prediction matrix with exactly k ones per row."""
+    if isinstance(y_pred, csr_matrix):
+        n = y_pred.shape[0]
+        return np.asarray(y_pred.indices, dtype=np.int32).reshape(n, k).copy()
+    n = y_pred.shape[0]
+    r, c = np.nonzero(y_pred)
+    assert (np.bincount(r, minlength=n) == k).all()
+    return c.reshape(n, k).astype(np.int32)
+
+
+def main():
+    _install_shims()
+    from xcolumns import block_coordinate as bc
+    from xcolumns import confusion_matrix as cm
+    from xcolumns import frank_wolfe as fw
+    from xcolumns import metrics as mt
+    from xcolumns import weighted_prediction as wp
+
+    from xcolumns_b200.synth import csr_probs, dense_probs
+
+    def save(name, **kw):
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **kw)
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+    rng = np.random.default_rng(7)
+
+    # ---------------- weighted top-k, dense ----------------
+    eta = dense_probs(96, 333, seed=11)
+    a32 = (0.5 + rng.random(333)).astype(np.float32)
+    b32 = (0.01 * rng.standard_normal(333)).astype(np.float32)
+    a64 = 1.0 / (eta.mean(0).astype(np.float64) + 1e-6)
+    out = {"eta": eta, "a32": a32, "b32": b32, "a64": a64}
+    out["top5"] = pred_to_idx(wp.predict_top_k(eta, 5), 5)
+    out["top1"] = pred_to_idx(wp.predict_top_k(eta, 1), 1)
+    out["w5_ab32"] = pred_to_idx(wp.predict_weighted_per_instance(eta, 5, a=a32, b=b32), 5)
+    out["w3_a64"] = pred_to_idx(wp.predict_weighted_per_instance(eta, 3, a=a64), 3)
+    ks = wp.predict_weighted_per_instance(eta, 4, a=a32, b=b32, keep_scores=True)
+    out["w4_scores"] = ks
+    eta64 = eta.astype(np.float64)
+    out["w5_f64"] = pred_to_idx(wp.predict_weighted_per_instance(eta64, 5, a=a64, b=b32.astype(np.float64)), 5)
+    out["th0"] = wp.predict_weighted_per_instance(eta, 0, th=0.3, a=a32, b=b32)
+    save("topk_dense", **out)
+
+    # ---------------- weighted top-k, CSR (ragged rows, some with nnz <= k) ----------------
+    ycsr = csr_probs(80, 1500, 24, seed=12, ragged=True)
+    ac = (0.5 + rng.random(1500)).astype(np.float64)
+    bcf = (0.01 * rng.standard_normal(1500)).astype(np.float64)
+    out = {"data": ycsr.data, "indices": ycsr.indices, "indptr": ycsr.indptr, "shape": np.array(ycsr.shape),
+           "a": ac, "b": bcf}
+    for name, kw, k in (("top5", {}, 5), ("top8", {}, 8), ("w5", {"a": ac, "b": bcf}, 5),
+                        ("w5s", {"a": ac, "b": bcf, "keep_scores": True}, 5)):
+        r = wp.predict_weighted_per_instance(ycsr, k, **kw)
+        out[name + "_data"], out[name + "_indices"], out[name + "_indptr"] = r.data, r.indices, r.indptr
+    save("topk_csr", **out)
+
+    # ---------------- confusion matrix ----------------
+    eta = dense_probs(200, 150, seed=13)
+    pred = wp.predict_top_k(eta, 4)
+    lab = (rng.random(eta.shape) < eta).astype(np.float32)
+    out = {"eta": eta, "pred": pred_to_idx(pred, 4), "lab": lab}
+    for name, yt, kw in (("probs_f64", eta, dict(dtype=np.float64, skip_tn=True)),
+                         ("probs_none", eta, dict()),
+                         ("lab_norm", lab, dict(normalize=True)),
+                         ("lab_f64_norm_skip", lab, dict(normalize=True, skip_tn=True, dtype=np.float64)),
+                         ("lab_axis1", lab, dict(axis=1, dtype=np.float64))):
+        c = cm.calculate_confusion_matrix(yt, pred, **kw)
+        out[name] = np.stack([np.asarray(v, dtype=np.float64) for v in c])
+    ycsr = csr_probs(150, 900, 20, seed=14)
+    pcsr = wp.predict_top_k(ycsr, 4)
+    out.update({"c_data": ycsr.data, "c_indices": ycsr.indices, "c_indptr": ycsr.indptr,
+                "c_shape": np.array(ycsr.shape), "c_pred": pred_to_idx(pcsr, 4)})
+    for name, kw in (("csr_f64", dict(dtype=np.float64, skip_tn=True)), ("csr_none", dict()),
+                     ("csr_norm", dict(normalize=True, dtype=np.float64))):
+        c = cm.calculate_confusion_matrix(ycsr, pcsr, **kw)
+        out[name] = np.stack([np.asarray(v, dtype=np.float64) for v in c])
+    save("confmat", **out)
+
+    # ---------------- BCA dense ----------------
+    eta = dense_probs(300, 200, seed=1001)
+    out = {"eta": eta}
+
+    def run_bc(name, y, metric, k, **kw):
+        yp, meta = bc.predict_using_bc_with_0approx(y, metric, k, return_meta=True, **kw)
+        if k > 0:
+            out[name + "_pred"] = pred_to_idx(yp, k)
+        else:
+            out[name + "_pred"] = np.asarray(yp != 0, dtype=np.uint8)
+        out[name + "_util"] = np.array(meta["utilities"], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} util={meta['utilities'][-1]:.6f} time={meta['time']:.2f}s")
+
+    run_bc("f1", eta, mt.binary_f1_score_on_conf_matrix, 5, seed=0, skip_tn=True)
+    run_bc("f1_f64", eta.astype(np.float64), mt.binary_f1_score_on_conf_matrix, 5, seed=0, skip_tn=True)
+    run_bc("recall", eta, mt.binary_recall_on_conf_matrix, 5, seed=3, skip_tn=True)
+    run_bc("precision", eta, mt.binary_precision_on_conf_matrix, 3, seed=4, skip_tn=True)
+    run_bc("jaccard", eta, mt.binary_jaccard_score_on_conf_matrix, 5, seed=5, skip_tn=True)
+    run_bc("fbeta2", eta, mt.binary_fbeta_score_on_conf_matrix, 5, seed=6, skip_tn=True,
+           metric_kwargs={"beta": 2.0, "epsilon": 1e-6})
+    run_bc("balacc", eta, mt.binary_balanced_accuracy_on_conf_matrix, 5, seed=7, skip_tn=False)
+    run_bc("gmean", eta, mt.binary_gmean_on_conf_matrix, 5, seed=8, skip_tn=False)
+    run_bc("hmean", eta, mt.binary_hmean_on_conf_matrix, 5, seed=9, skip_tn=False)
+    run_bc("f1_noshuffle", eta, mt.binary_f1_score_on_conf_matrix, 5, seed=0, skip_tn=True, shuffle_order=False)
+    run_bc("f1_random", eta, mt.binary_f1_score_on_conf_matrix, 5, seed=10, skip_tn=True, init_y_pred="random")
+    run_bc("f1_greedy", eta, mt.binary_f1_score_on_conf_matrix, 5, seed=11, skip_tn=True, init_y_pred="greedy")
+    run_bc("f1_sum", eta, mt.binary_f1_score_on_conf_matrix, 5, seed=12, skip_tn=True, metric_aggregation="sum",
+           tolerance=1e-4)
+    run_bc("f1_k0", eta, mt.binary_f1_score_on_conf_matrix, 0, seed=13, skip_tn=True, init_y_pred=wp.predict_top_k(eta, 3))
+    yp, meta = bc.predict_optimizing_macro_f1_score_using_bc(eta, 5, seed=0, return_meta=True)
+    assert (pred_to_idx(yp, 5) == out["f1_pred"]).all()
+    save("bca_dense", **out)
+
+    # ---------------- BCA CSR ----------------
+    ycsr = csr_probs(300, 3000, 40, seed=1004)
+    out = {"data": ycsr.data, "indices": ycsr.indices, "indptr": ycsr.indptr, "shape": np.array(ycsr.shape)}
+    run_bc("f1", ycsr, mt.binary_f1_score_on_conf_matrix, 5, seed=0, skip_tn=True)
+    run_bc("recall", ycsr, mt.binary_recall_on_conf_matrix, 5, seed=1, skip_tn=True)
+    run_bc("jaccard", ycsr, mt.binary_jaccard_score_on_conf_matrix, 3, seed=2, skip_tn=True)
+    y64 = csr_matrix((ycsr.data.astype(np.float64), ycsr.indices, ycsr.indptr), shape=ycsr.shape)
+    run_bc("f1_f64", y64, mt.binary_f1_score_on_conf_matrix, 5, seed=0, skip_tn=True)
+    save("bca_csr", **out)
+
+    # ---------------- coverage BCA (CSR) ----------------
+    ycsr = csr_probs(400, 600, 30, seed=1005)
+    out = {"data": ycsr.data, "indices": ycsr.indices, "indptr": ycsr.indptr, "shape": np.array(ycsr.shape)}
+    for name, kw in (("cov", dict(seed=0)), ("cov_a07", dict(seed=1, alpha=0.7))):
+        yp, meta = bc.predict_optimizing_coverage_using_bc(ycsr, 5, return_meta=True, **kw)
+        out[name + "_pred"] = pred_to_idx(yp, 5)
+        out[name + "_util"] = np.array(meta["utilities"], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} util={meta['utilities']}")
+    save("coverage_csr", **out)
+
+    # ---------------- Frank-Wolfe ----------------
+    eta = dense_probs(400, 300, seed=1005)
+    out = {"eta": eta}
+
+    def run_fw(name, yt, yp, metric, **kw):
+        clf, meta = fw.find_classifier_using_fw(yt, yp, metric, 5, return_meta=True, **kw)
+        out[name + "_a"], out[name + "_b"], out[name + "_p"] = clf.a, clf.b, clf.p
+        out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        out[name + "_cutil"] = np.array([float(u) for u in meta["classifiers_utilities"]], dtype=np.float64)
+        out[name + "_iters"] = np.array(meta["iters"])
+        print(f"  {name}: iters={meta['iters']} util={out[name + '_util']}")
+
+    run_fw("f1_proba", eta, eta, mt.macro_f1_score_on_conf_matrix, max_iters=10, skip_tn=True, seed=0)
+    lab = (np.random.default_rng(5).random(eta.shape) < eta).astype(np.float32)
+    out["lab"] = lab
+    run_fw("f1_lab", lab, eta, mt.macro_f1_score_on_conf_matrix, max_iters=10, skip_tn=True, seed=0,
+           metric_kwargs={"epsilon": 1e-4})
+    run_fw("recall_lab", lab, eta, mt.macro_recall_on_conf_matrix, max_iters=6, skip_tn=True, seed=0,
+           metric_kwargs={"epsilon": 1e-4})
+    run_fw("balacc_lab", lab, eta, mt.macro_balanced_accuracy_on_conf_matrix, max_iters=6, seed=0,
+           metric_kwargs={"epsilon": 1e-4})
+    save("fw_dense", **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+"""The CPU oracle (oracle/) replayed against outputs of the LIVE reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py).  Bit-exact on label ids,
+float64 state and per-sweep utilities; Frank-Wolfe within 1e-6 (the reference differentiates
+with autograd and keeps float32 confusion vectors; contract tolerance is 1e-4)."""
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+
+def _idx(pred, k):
+    n = pred.shape[0]
+    r, c = np.nonzero(pred)
+    return c.reshape(n, k).astype(np.int32)
+
+
+def test_topk_dense(golden, oracle):
+    g = golden("topk_dense")
+    eta = g["eta"]
+    assert (oracle.topk_indices_dense(eta, 5)[0] == g["top5"]).all()
+    assert (oracle.topk_indices_dense(eta, 1)[0] == g["top1"]).all()
+    assert (oracle.topk_indices_dense(eta, 5, g["a32"], g["b32"])[0] == g["w5_ab32"]).all()
+    assert (oracle.topk_indices_dense(eta, 3, g["a64"])[0] == g["w3_a64"]).all()
+    assert (oracle.topk_indices_dense(eta.astype(np.float64), 5, g["a64"], g["b32"].astype(np.float64))[0]
+            == g["w5_f64"]).all()
+    ks = oracle.predict_weighted_per_instance(eta, 4, a=g["a32"], b=g["b32"], keep_scores=True)
+    assert ks.dtype == g["w4_scores"].dtype and (ks == g["w4_scores"]).all()
+    th = oracle.predict_weighted_per_instance(eta, 0, th=0.3, a=g["a32"], b=g["b32"])
+    assert (th == g["th0"]).all()
+
+
+def test_topk_csr(golden, oracle):
+    g = golden("topk_csr")
+    y = csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    for name, kw, k in (("top5", {}, 5), ("top8", {}, 8), ("w5", {"a": g["a"], "b": g["b"]}, 5),
+                        ("w5s", {"a": g["a"], "b": g["b"], "keep_scores": True}, 5)):
+        r = oracle.predict_weighted_per_instance(y, k, **kw)
+        assert (r.indices == g[name + "_indices"]).all(), name
+        assert (r.indptr == g[name + "_indptr"]).all(), name
+        assert r.data.dtype == g[name + "_data"].dtype and (r.data == g[name + "_data"]).all(), name
+
+
+def test_confmat(golden, oracle):
+    g = golden("confmat")
+    eta, lab = g["eta"], g["lab"]
+    n, m = eta.shape
+    pred = np.zeros_like(eta)
+    pred[np.arange(n)[:, None], g["pred"]] = 1
+    for name, yt, kw in (("probs_f64", eta, dict(dtype=np.float64, skip_tn=True)),
+                         ("probs_none", eta, dict()),
+                         ("lab_norm", lab, dict(normalize=True)),
+                         ("lab_f64_norm_skip", lab, dict(normalize=True, skip_tn=True, dtype=np.float64))):
+        c = np.stack([np.asarray(v, dtype=np.float64) for v in oracle.calculate_confusion_matrix(yt, pred, **kw)])
+        assert (c == g[name]).all(), name
+    c = np.stack(oracle.calculate_confusion_matrix(lab, pred, axis=1, dtype=np.float64))
+    assert np.allclose(c, g["lab_axis1"], rtol=0, atol=1e-9)
+    y = csr_matrix((g["c_data"], g["c_indices"], g["c_indptr"]), shape=tuple(g["c_shape"]))
+    nn = y.shape[0]
+    p = csr_matrix((np.ones(nn * 4, dtype=np.float32), g["c_pred"].reshape(-1), np.arange(nn + 1) * 4), shape=y.shape)
+    for name, kw in (("csr_f64", dict(dtype=np.float64, skip_tn=True)), ("csr_none", dict()),
+                     ("csr_norm", dict(normalize=True, dtype=np.float64))):
+        c = np.stack([np.asarray(v, dtype=np.float64) for v in oracle.calculate_confusion_matrix(y, p, **kw)])
+        assert (c == g[name]).all(), name
+
+
+BCA_DENSE = [
+    ("f1", "f1", 5, dict(seed=0, skip_tn=True)),
+    ("f1_f64", "f1", 5, dict(seed=0, skip_tn=True)),
+    ("recall", "recall", 5, dict(seed=3, skip_tn=True)),
+    ("precision", "precision", 3, dict(seed=4, skip_tn=True)),
+    ("jaccard", "jaccard", 5, dict(seed=5, skip_tn=True)),
+    ("fbeta2", "fbeta", 5, dict(seed=6, skip_tn=True, beta=2.0, epsilon=1e-6)),
+    ("balacc", "balanced_accuracy", 5, dict(seed=7, skip_tn=False)),
+    ("gmean", "gmean", 5, dict(seed=8, skip_tn=False)),
+    ("hmean", "hmean", 5, dict(seed=9, skip_tn=False)),
+    ("f1_noshuffle", "f1", 5, dict(seed=0, skip_tn=True, shuffle_order=False)),
+    ("f1_random", "f1", 5, dict(seed=10, skip_tn=True, init_y_pred="random")),
+    ("f1_greedy", "f1", 5, dict(seed=11, skip_tn=True, init_y_pred="greedy")),
+    ("f1_sum", "f1", 5, dict(seed=12, skip_tn=True, metric_aggregation="sum", tolerance=1e-4)),
+]
+
+
+@pytest.mark.parametrize("name,metric,k,kw", BCA_DENSE, ids=[c[0] for c in BCA_DENSE])
+def test_bca_dense(golden, oracle, name, metric, k, kw):
+    g = golden("bca_dense")
+    eta = g["eta"].astype(np.float64) if name.endswith("f64") else g["eta"]
+    pred, meta = oracle.predict_using_bc_with_0approx(eta, metric, k, **kw)
+    assert (_idx(pred, k) == g[name + "_pred"]).all()
+    assert meta["iters"] == len(g[name + "_util"])
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+def test_bca_dense_k0(golden, oracle):
+    g = golden("bca_dense")
+    eta = g["eta"]
+    init = np.zeros(eta.shape, dtype=np.uint8)
+    init[np.arange(eta.shape[0])[:, None], oracle.topk_indices_dense(eta, 3)[0]] = 1
+    pred, meta = oracle.predict_using_bc_with_0approx(eta, "f1", 0, seed=13, skip_tn=True, init_y_pred=init)
+    assert (pred == g["f1_k0_pred"]).all()
+    assert (np.array(meta["utilities"]) == g["f1_k0_util"]).all()
+
+
+BCA_CSR = [("f1", "f1", 5, 0), ("recall", "recall", 5, 1), ("jaccard", "jaccard", 3, 2), ("f1_f64", "f1", 5, 0)]
+
+
+@pytest.mark.parametrize("name,metric,k,seed", BCA_CSR, ids=[c[0] for c in BCA_CSR])
+def test_bca_csr(golden, oracle, name, metric, k, seed):
+    g = golden("bca_csr")
+    data = g["data"].astype(np.float64) if name.endswith("f64") else g["data"]
+    y = csr_matrix((data, g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    pidx, meta = oracle.predict_using_bc_with_0approx(y, metric, k, seed=seed, skip_tn=True)
+    assert (pidx == g[name + "_pred"]).all()
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+@pytest.mark.parametrize("name,kw", [("cov", dict(seed=0)), ("cov_a07", dict(seed=1, alpha=0.7))])
+def test_coverage_csr(golden, oracle, name, kw):
+    g = golden("coverage_csr")
+    y = csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    pidx, meta = oracle.predict_optimizing_coverage_using_bc(y, 5, **kw)
+    assert (pidx == g[name + "_pred"]).all()
+    if name == "cov":
+        assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+    else:  # the precision@k mix is summed in float32 by the reference
+        assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-6)
+
+
+FW = [("f1_proba", "f1", "eta", dict(max_iters=10, skip_tn=True)),
+      ("f1_lab", "f1", "lab", dict(max_iters=10, skip_tn=True, epsilon=1e-4)),
+      ("recall_lab", "recall", "lab", dict(max_iters=6, skip_tn=True, epsilon=1e-4)),
+      ("balacc_lab", "balanced_accuracy", "lab", dict(max_iters=6, epsilon=1e-4))]
+
+
+@pytest.mark.parametrize("name,metric,yt,kw", FW, ids=[c[0] for c in FW])
+def test_fw_dense(golden, oracle, name, metric, yt, kw):
+    g = golden("fw_dense")
+    A, B, P, meta = oracle.find_classifier_using_fw(g[yt], g["eta"], metric, 5, seed=0, **kw)
+    assert meta["iters"] == int(g[name + "_iters"])
+    assert A.shape == g[name + "_a"].shape
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=2e-3)
+    assert np.allclose(P, g[name + "_p"], rtol=0, atol=2e-3)
