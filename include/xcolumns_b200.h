@@ -1,0 +1,247 @@
+/*
+ * xcolumns_b200 -- C ABI of the B200-native prediction-optimisation path.
+ *
+ * Drop-in boundary for the hot path of mwydmuch/xCOLUMNs 0.0.3.
+ * The reference has no FFI of its own (pure Python + numba); each entry point below names
+ * the reference function(s) it replaces ("ref:", paths relative to the reference repo).
+ * INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all calls are asynchronous on `stream` unless documented otherwise;
+ *   - return value: 0 on success, negative XC_ERR_* otherwise (never throws);
+ *   - matrices are row-major with leading dimension `ld` (elements); the 128-bit fast path
+ *     needs ld % 4 == 0 (f32) / ld % 2 == 0 (f64) and a 16-byte aligned base, otherwise a
+ *     scalar path is used;
+ *   - label ids are int32, CSR indptr is int64, accumulators ("state") are float64;
+ *   - a compact prediction is an [n, k] int32 matrix of label ids, ascending inside a row,
+ *     -1 marks an unused slot (CSR rows with fewer than k stored labels).
+ */
+#ifndef XCOLUMNS_B200_H
+#define XCOLUMNS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XC_API __attribute__((visibility("default")))
+
+#define XC_ABI_VERSION 1
+
+/* element types of probability matrices / weight vectors */
+enum { XC_F32 = 0, XC_F64 = 1 };
+
+/* binary metrics, ref: xcolumns/metrics.py:585-944 */
+enum {
+    XC_METRIC_PRECISION = 0,    /* tp / (tp + fp + eps)                               :603 */
+    XC_METRIC_RECALL = 1,       /* tp / (tp + fn + eps)                               :652 */
+    XC_METRIC_FBETA = 2,        /* (1+b^2) tp / (b^2 (tp+fp) + tp + fn + eps)         :703 */
+    XC_METRIC_JACCARD = 3,      /* tp / (tp + fp + fn + eps)                          :797 */
+    XC_METRIC_BALANCED_ACC = 4, /* (tpr + tnr) / 2                                    :843 */
+    XC_METRIC_GMEAN = 5,        /* sqrt(tpr * tnr)                                    :890 */
+    XC_METRIC_HMEAN = 6         /* 2 tpr tnr / (tpr + tnr)                            :939 */
+};
+
+/* summation order of label-wise reductions */
+enum {
+    XC_SUM_FAST = 0,   /* float64 atomics, any order (value parity ~1e-12 relative)           */
+    XC_SUM_ORDERED = 1 /* one running sum per label, rows in order: bit-identical to numpy's  */
+                       /* axis-0 reduction / numba's row loop (sequential-exact BCA)          */
+};
+
+enum {
+    XC_OK = 0,
+    XC_ERR_INVALID = -1,     /* bad argument (shape, k, dtype, metric id, NULL pointer)   */
+    XC_ERR_UNSUPPORTED = -2, /* valid request this build has no kernel for                */
+    XC_ERR_CUDA = -3,        /* a CUDA runtime call failed; see xc_last_cuda_error        */
+    XC_ERR_NOMEM = -4
+};
+
+typedef struct xc_ctx xc_ctx;
+
+typedef struct {
+    int32_t metric;    /* XC_METRIC_*                                                          */
+    int32_t maximize;  /* 1: ascend, 0: descend (ref: block_coordinate.py:187-188)             */
+    int32_t skip_tn;   /* 1: tn is a constant -1 vector (ref: confusion_matrix.py:391-393)     */
+    int32_t reserved;
+    double c1;         /* 1 + beta**2, computed by the host exactly like python does           */
+    double beta2;      /* beta**2                                                              */
+    double eps;        /* epsilon of the metric (metric_kwargs["epsilon"], default 1e-9)       */
+    double n_div;      /* n if normalize_conf_matrix else 1 (ref: block_coordinate.py:149-151) */
+} xc_metric_params;
+
+/* ---- context -------------------------------------------------------------------------- */
+XC_API int xc_abi_version(void);
+XC_API const char *xc_strerror(int code);
+/* one context per device and host thread: scratch buffers, SM count, launch counter */
+XC_API int xc_ctx_create(int device, xc_ctx **out);
+XC_API void xc_ctx_destroy(xc_ctx *ctx);
+XC_API const char *xc_last_cuda_error(xc_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py: gpu_launches) */
+XC_API int64_t xc_launch_count(xc_ctx *ctx);
+XC_API int xc_sm_count(xc_ctx *ctx);
+
+/* ---- weighted per-instance top-k ------------------------------------------------------ */
+/* ref: weighted_prediction.py:25-60 (_predict_weighted_per_instance_dense), :91-220.
+ * gains = eta [* a] [+ b] evaluated in `g_dtype` (separate multiply and add, no FMA, so the
+ * selection is bit-comparable with numpy); per row the k largest gains, ties -> lowest label.
+ * rows: optional list of n_rows row ids to process (NULL = rows 0..n_rows-1); output row r
+ * belongs to rows[r].  out_val (optional) receives the gains in g_dtype.  1 <= k <= 32.    */
+XC_API int xc_topk_dense(xc_ctx *ctx, const void *eta, int eta_dtype, int64_t n_rows, int64_t m,
+                         int64_t ld, const int32_t *rows, const void *a, const void *b,
+                         int g_dtype, int k, int32_t *out_idx, void *out_val, void *stream);
+/* ref: numba_csr_functions.py:586-629 (numba_predict_weighted_per_instance_csr), :456-484.
+ * Rows with nnz <= k keep all their labels; unused slots get id -1 in out_idx and (when
+ * out_val != NULL) value 1 -- the host shim turns them into the reference's (0, 1) filler.  */
+XC_API int xc_topk_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                       const int64_t *indptr, int64_t n_rows, const void *a, const void *b, int k,
+                       int32_t *out_idx, void *out_val, void *stream);
+/* k == 0 branch of weighted_prediction.py:57-58: out[i][j] = (gain >= th) in out dtype=eta dtype */
+XC_API int xc_threshold_dense(xc_ctx *ctx, const void *eta, int eta_dtype, int64_t n_rows,
+                              int64_t m, int64_t ld, const void *a, const void *b, int g_dtype,
+                              double th, void *out, int64_t ld_out, void *stream);
+/* scatter a compact prediction into a dense 0/1 (or gain-valued) matrix that was zeroed */
+XC_API int xc_scatter_pred_dense(xc_ctx *ctx, const int32_t *pred_idx, const void *val,
+                                 int val_dtype, int k, int64_t n_rows, void *out, int out_dtype,
+                                 int64_t ld_out, void *stream);
+
+/* ---- label-wise confusion sums -------------------------------------------------------- */
+/* ref: confusion_matrix.py:160-202, :364-399 (calculate_confusion_matrix), dense x dense.
+ * axis 0: tp/fp/fn have m entries; axis 1: n entries.  Products are formed in the input
+ * dtype, sums in float64 (acc_f32 = 1 with XC_SUM_ORDERED keeps float32 running sums like
+ * dtype=None does).  normalize / tn are m-vector epilogues left to the host shim.           */
+XC_API int xc_confmat_dense(xc_ctx *ctx, const void *y_true, int64_t ldt, const void *y_pred,
+                            int64_t ldp, int dtype, int64_t n, int64_t m, int axis, int order,
+                            int acc_f32, double *tp, double *fp, double *fn, void *stream);
+/* same sums with a compact prediction (k ids per row); colsum (optional, fast order only) is
+ * sum_i y_true[i][j] so that fn = colsum - tp without a second pass over y_true.            */
+XC_API int xc_confmat_dense_compact(xc_ctx *ctx, const void *y_true, int dtype, int64_t ld,
+                                    const int32_t *pred_idx, int k, int64_t n, int64_t m,
+                                    int order, const double *colsum, double *tp, double *fp,
+                                    double *fn, void *stream);
+/* ref: numba_csr_functions.py:144-182, 217-258 via confusion_matrix.py:174-228 (both CSR) */
+XC_API int xc_confmat_csr(xc_ctx *ctx, const void *t_data, const int32_t *t_idx,
+                          const int64_t *t_ptr, const void *p_data, const int32_t *p_idx,
+                          const int64_t *p_ptr, int dtype, int64_t n, int64_t m, int order,
+                          int acc_f32, double *tp, double *fp, double *fn, void *stream);
+/* CSR truth, compact prediction of ones */
+XC_API int xc_confmat_csr_compact(xc_ctx *ctx, const void *t_data, const int32_t *t_idx,
+                                  const int64_t *t_ptr, int dtype, const int32_t *pred_idx, int k,
+                                  int64_t n, int64_t m, int order, double *tp, double *fp,
+                                  double *fn, void *stream);
+/* column sums of a dense / CSR matrix in float64 (fast order) */
+XC_API int xc_colsum_dense(xc_ctx *ctx, const void *x, int dtype, int64_t n, int64_t m, int64_t ld,
+                           double *out, void *stream);
+XC_API int xc_colsum_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                         int64_t nnz, int64_t m, double *out, void *stream);
+/* ref: block_coordinate.py:54-90 (_calculate_utility): mean (agg=0) or sum (agg=1) over labels
+ * of the binary metric on (tp,fp,fn,tn)/n_div; result written to *out_dev (device double).   */
+XC_API int xc_utility(xc_ctx *ctx, const xc_metric_params *p, int agg, const double *tp,
+                      const double *fp, const double *fn, const double *tn, int64_t m,
+                      double *out_dev, void *stream);
+
+/* ---- BCA, sequential-exact mode ("Gauss-Seidel", reference instance order) -------------- */
+/* ref: block_coordinate.py:132-209 (_bc_with_0approx_step_dense) for i in order (:448-463).
+ * One cooperative launch per sweep; float64 arithmetic in the reference's operation order
+ * (compiled without FMA contraction).  tp/fp/fn/tn are the un-normalised running sums,
+ * updated in place; pred_idx [n, k] is updated in place.  greedy: skip the removal step.    */
+XC_API int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m,
+                                    int64_t ld, const int32_t *order, int64_t n_order, int k,
+                                    const xc_metric_params *p, int greedy, int32_t *pred_idx,
+                                    double *tp, double *fp, double *fn, double *tn, void *stream);
+/* ref: block_coordinate.py:212-293 (_bc_with_0approx_step_csr) + numba_csr_functions.py
+ * :386-452, :456-466, :500-546.  skip_tn metrics only.                                       */
+XC_API int xc_bca_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                                  const int64_t *indptr, int64_t n, int64_t m,
+                                  const int32_t *order, int64_t n_order, int k,
+                                  const xc_metric_params *p, int greedy, int32_t *pred_idx,
+                                  double *tp, double *fp, double *fn, void *stream);
+/* ref: block_coordinate.py:539-580 (_bc_for_coverage_step_csr); Ef updated in place */
+XC_API int xc_cov_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                                  const int64_t *indptr, int64_t n, int64_t m,
+                                  const int32_t *order, int64_t n_order, int k, double alpha,
+                                  int greedy, int32_t *pred_idx, double *Ef, void *stream);
+/* ref: numba_csr_functions.py:325-382 as called at block_coordinate.py:665/676 */
+XC_API int xc_cov_state_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                            const int64_t *indptr, int64_t n, int64_t m, const int32_t *pred_idx,
+                            int k, int order, double *Ef, void *stream);
+
+/* ---- BCA, batched block-Jacobi mode ----------------------------------------------------- */
+/* Per-label gain coefficients from the frozen state: for the metrics
+ * whose gain is affine in eta (precision, recall, F-beta)
+ *     gain_ij = A_j + B_j * eta_ij          label j not selected in row i   -> coef_n[j] = (B, A)
+ *     gain_ij = A'_j + B'_j * eta_ij        label j currently selected      -> coef_s[j] = (B', A')
+ * Before computing them the pending deltas are folded into the state and cleared:
+ *     tp += dtp; fp += dfp; fn += dfn; d* = 0     (d* may be NULL).
+ * ref: block_coordinate.py:158-185 evaluated against a frozen state.                        */
+XC_API int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
+                       double *dtp, double *dfp, double *dfn, int64_t m, float *coef_n,
+                       float *coef_s, void *stream);
+/* One batch: rows[0..n_rows) stream past the frozen coefficients, every row re-selects its k
+ * best labels (own contribution removed via coef_s), pred_idx rows are rewritten and the
+ * confusion deltas of all changed rows are accumulated into dtp/dfp/dfn (float64 atomics). */
+XC_API int xc_bca_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld,
+                              const int32_t *rows, int64_t n_rows, int k, const float *coef_n,
+                              const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
+                              double *dfn, void *stream);
+XC_API int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                            const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k,
+                            const float *coef_n, const float *coef_s, int32_t *pred_idx,
+                            double *dtp, double *dfp, double *dfn, void *stream);
+/* coverage: gain = Ef_j * eta (not selected) or Ef_j / (1 - eta) * eta (selected); the batch
+ * accumulates multiplicative factors into dEf (init 1), folded by xc_cov_fold.               */
+XC_API int xc_cov_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                            const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k,
+                            double alpha, const double *Ef, int32_t *pred_idx, double *dEf,
+                            void *stream);
+XC_API int xc_cov_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld,
+                              const int32_t *rows, int64_t n_rows, int k, double alpha,
+                              const double *Ef, int32_t *pred_idx, double *dEf, void *stream);
+XC_API int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void *stream);
+
+/* ---- Frank-Wolfe iterate ----------------------------------------------------------------- */
+/* ref: frank_wolfe.py:601-606: weighted top-k of every row with the linear classifier (a, b)
+ * fused with the accumulation of tp_j = sum_i y_true[i][j] * yhat[i][j] and
+ * cnt_j = sum_i yhat[i][j] (float64).  a, b and y_true have eta's dtype (numpy promotes the
+ * float32 classifier rows to it); gains = eta * a + b with separate IEEE multiply and add.
+ * y_true may alias eta.  tp/cnt are zeroed by the call.  pred_idx [n, k] is optional.         */
+XC_API int xc_fw_iterate_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m,
+                               int64_t ld, const void *y_true, int64_t ld_true, const void *a,
+                               const void *b, int k, double *tp, double *cnt, int32_t *pred_idx,
+                               void *stream);
+XC_API int xc_fw_iterate_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                             const int64_t *indptr, int64_t n, int64_t m, const void *t_data,
+                             const int32_t *t_idx, const int64_t *t_ptr, const void *a,
+                             const void *b, int k, double *tp, double *cnt, int32_t *pred_idx,
+                             void *stream);
+/* ref: confusion_matrix.py:386-399 on the iterate: Ci = [tp, fp, fn, tn] (4 stacked m-vectors)
+ * with fp = cnt - tp, fn = colsum(y_true) - tp, optional / n, tn = -tp - fp - fn + (1 | n) or
+ * the constant -1 when skip_tn.                                                               */
+XC_API int xc_fw_make_conf(xc_ctx *ctx, const double *tp_raw, const double *cnt,
+                           const double *colsum, int64_t m, double n, int normalize, int skip_tn,
+                           double *Ci, void *stream);
+/* ref: frank_wolfe.py:591-596 (+ :368-376): value of the macro-averaged metric on the stacked
+ * confusion vectors C and the next linear classifier a = dtp - dfp - dfn + dtn, b = dfp - dtn
+ * (negated when minimising), closed-form gradients, stored as float32 like :503-504.
+ * a_out/b_out may both be NULL (value only).                                                  */
+XC_API int xc_fw_metric_grad(xc_ctx *ctx, const xc_metric_params *p, const double *C, int64_t m,
+                             float *a_out, float *b_out, double *value_dev, void *stream);
+/* ref: frank_wolfe.py:379-404 + utils.py:174-184 (uniform_search): evaluates the metric of
+ * (1-alpha) C + alpha Ci at alpha = 0 and at alphas_dev[0..n_alphas) (the host builds the grid
+ * with numpy.arange so the grid points are bit-identical), keeps the FIRST strict maximum.
+ * vals_dev: scratch of n_alphas + 1 doubles; result_dev[0] = alpha, result_dev[1] = value.    */
+XC_API int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const double *C,
+                              const double *Ci, int64_t m, const double *alphas_dev,
+                              int64_t n_alphas, double *vals_dev, double *result_dev,
+                              void *stream);
+/* C = (1 - alpha) C + alpha Ci on the 4 stacked m-vectors, alpha read from device memory */
+XC_API int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4,
+                         const double *alpha_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XCOLUMNS_B200_H */

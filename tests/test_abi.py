@@ -1,0 +1,87 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/xcolumns_b200.h
+declares; the ctypes prototypes in xcolumns_b200/_lib.py agree with the header, argument by
+argument (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "xcolumns_b200.h")
+
+
+def _declarations():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = {}
+    for mobj in re.finditer(r"XC_API\s+([\w\s\*]+?)\s*\b(xc_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        ret, name, args = mobj.group(1).strip(), mobj.group(2), mobj.group(3)
+        params = [a.strip() for a in args.replace("\n", " ").split(",")] if args.strip() != "void" else []
+        decls[name] = (ret, params)
+    return decls
+
+
+def _ctype_of(param: str):
+    if "*" in param:
+        return "ptr"
+    if param.startswith("int64_t"):
+        return C.c_int64
+    if param.startswith("double"):
+        return C.c_double
+    if param.startswith("int"):
+        return C.c_int
+    raise AssertionError(f"unparsed parameter {param!r}")
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as entry
+    entry.build()
+    from xcolumns_b200 import _lib
+    lib = _lib.load()
+    decls = _declarations()
+    assert len(decls) >= 30
+    for name in decls:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert lib.xc_abi_version() == 1
+    assert lib.xc_strerror(-1) == b"invalid argument"
+
+
+def test_ctypes_prototypes_match_header():
+    from xcolumns_b200 import _lib
+    decls = _declarations()
+    for name, argtypes in _lib._SIGNATURES.items():
+        assert name in decls, f"{name} bound in _lib.py but not declared"
+        ret, params = decls[name]
+        assert ret == "int"
+        assert params[0].startswith("xc_ctx")
+        params = params[1:]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} args after ctx, binding {len(argtypes)}"
+        for p, t in zip(params, argtypes):
+            want = _ctype_of(p)
+            if want == "ptr":
+                assert t in (C.c_void_p, _lib._MP), f"{name}: {p!r} bound as {t}"
+                if "xc_metric_params" in p:
+                    assert t is _lib._MP, f"{name}: {p!r} must be the params struct pointer"
+            else:
+                assert t is want, f"{name}: {p!r} bound as {t}"
+    bound = set(_lib._SIGNATURES) | {"xc_abi_version", "xc_strerror", "xc_ctx_create", "xc_ctx_destroy",
+                                     "xc_last_cuda_error", "xc_launch_count", "xc_sm_count"}
+    assert set(decls) == bound, f"unbound: {set(decls) - bound}, undeclared: {bound - set(decls)}"
+
+
+def test_metric_params_layout():
+    from xcolumns_b200 import _lib
+    assert C.sizeof(_lib.MetricParams) == 48
+    assert _lib.MetricParams.c1.offset == 16 and _lib.MetricParams.n_div.offset == 40
+
+
+def test_no_gpu_fails_loudly():
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import xcolumns_b200 as xb
+    from xcolumns_b200._lib import XColumnsB200Error
+    with pytest.raises(XColumnsB200Error):
+        xb.predict_top_k(np.random.rand(4, 8).astype(np.float32), 2)

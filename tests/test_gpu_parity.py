@@ -1,0 +1,357 @@
+"""Parity of the CUDA path (through the Python boundary -> C ABI) with the CPU oracle and with the
+golden vectors recorded from the live reference.  Bit-exact for label ids (top-k, weighted
+prediction, sequential-exact BCA) and float64 state; 1e-4 absolute on batched-BCA and Frank-Wolfe
+metric values (the tolerance BASELINE.json's north_star states)."""
+import numpy as np
+import pytest
+import torch
+from scipy.sparse import csr_matrix
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north_star: batched-BCA and FW metric values within 1e-4 absolute
+
+
+@pytest.fixture(scope="module")
+def xb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import xcolumns_b200
+    return xcolumns_b200
+
+
+def _idx(pred, k):
+    if isinstance(pred, torch.Tensor):
+        pred = pred.cpu().numpy()
+    n = pred.shape[0]
+    r, c = np.nonzero(pred)
+    assert (np.bincount(r, minlength=n) == k).all()
+    return c.reshape(n, k).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------
+# weighted top-k
+# ------------------------------------------------------------------------------------------
+
+def test_topk_dense_golden(xb, golden):
+    g = golden("topk_dense")
+    eta = g["eta"]
+    assert (_idx(xb.predict_top_k(eta, 5), 5) == g["top5"]).all()
+    assert (_idx(xb.predict_top_k(eta, 1), 1) == g["top1"]).all()
+    assert (_idx(xb.predict_weighted_per_instance(eta, 5, a=g["a32"], b=g["b32"]), 5) == g["w5_ab32"]).all()
+    assert (_idx(xb.predict_weighted_per_instance(eta, 3, a=g["a64"]), 3) == g["w3_a64"]).all()
+    p64 = xb.predict_weighted_per_instance(eta.astype(np.float64), 5, a=g["a64"], b=g["b32"].astype(np.float64))
+    assert p64.dtype == np.float64 and (_idx(p64, 5) == g["w5_f64"]).all()
+    ks = xb.predict_weighted_per_instance(eta, 4, a=g["a32"], b=g["b32"], keep_scores=True)
+    assert ks.dtype == g["w4_scores"].dtype and (ks == g["w4_scores"]).all()
+    th = xb.predict_weighted_per_instance(eta, 0, th=0.3, a=g["a32"], b=g["b32"])
+    assert (th == g["th0"]).all()
+
+
+@pytest.mark.parametrize("n,m,k,dtype", [(1, 7, 3, np.float32), (37, 1001, 5, np.float32), (500, 4096, 5, np.float32),
+                                         (64, 333, 32, np.float32), (129, 2050, 7, np.float64),
+                                         (3000, 777, 5, np.float32), (20000, 130, 3, np.float32)])
+def test_topk_dense_vs_oracle(xb, oracle, n, m, k, dtype):
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(n, m, seed=n + m, dtype=dtype)
+    rng = np.random.default_rng(1)
+    a = (0.5 + rng.random(m)).astype(dtype)
+    b = (0.05 * rng.standard_normal(m)).astype(dtype)
+    for kw in ({}, {"a": a}, {"a": a, "b": b}):
+        got = xb.predict_weighted_per_instance(eta, k, **kw)
+        assert type(got) is np.ndarray and got.dtype == eta.dtype and got.shape == eta.shape
+        assert (got.sum(1) == k).all()
+        assert (_idx(got, k) == oracle.topk_indices_dense(eta, k, kw.get("a"), kw.get("b"))[0]).all()
+
+
+def test_topk_ties_lowest_index(xb):
+    eta = np.zeros((3, 40), dtype=np.float32)
+    eta[1, 5:] = 0.5
+    eta[2, ::2] = 0.25
+    got = _idx(xb.predict_top_k(eta, 4), 4)
+    assert (got[0] == [0, 1, 2, 3]).all() and (got[1] == [5, 6, 7, 8]).all() and (got[2] == [0, 2, 4, 6]).all()
+
+
+def test_topk_torch_cuda(xb, oracle):
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(200, 515, seed=3)
+    t = torch.from_numpy(eta).cuda()
+    got = xb.predict_top_k(t, 5)
+    assert isinstance(got, torch.Tensor) and got.is_cuda and got.dtype == t.dtype
+    assert (_idx(got, 5) == oracle.topk_indices_dense(eta, 5)[0]).all()
+    got_cpu = xb.predict_top_k(torch.from_numpy(eta), 5)
+    assert isinstance(got_cpu, torch.Tensor) and not got_cpu.is_cuda
+
+
+def test_topk_csr_golden(xb, golden):
+    g = golden("topk_csr")
+    y = csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    for name, kw, k in (("top5", {}, 5), ("top8", {}, 8), ("w5", {"a": g["a"], "b": g["b"]}, 5),
+                        ("w5s", {"a": g["a"], "b": g["b"], "keep_scores": True}, 5)):
+        r = xb.predict_weighted_per_instance(y, k, **kw)
+        assert isinstance(r, csr_matrix)
+        assert (r.indices == g[name + "_indices"]).all(), name
+        assert (r.indptr == g[name + "_indptr"]).all(), name
+        assert r.data.dtype == g[name + "_data"].dtype and (r.data == g[name + "_data"]).all(), name
+
+
+def test_topk_errors(xb):
+    eta = np.random.rand(4, 10).astype(np.float32)
+    with pytest.raises(ValueError):
+        xb.predict_top_k(eta, 2.0)
+    with pytest.raises(ValueError):
+        xb.predict_weighted_per_instance(eta, 2, a=np.ones(9, dtype=np.float32))
+    with pytest.raises(ValueError):
+        xb.predict_weighted_per_instance([[0.1, 0.2]], 1)
+
+
+# ------------------------------------------------------------------------------------------
+# confusion matrix
+# ------------------------------------------------------------------------------------------
+
+def test_confmat_golden(xb, golden):
+    g = golden("confmat")
+    eta, lab = g["eta"], g["lab"]
+    n, m = eta.shape
+    pred = np.zeros_like(eta)
+    pred[np.arange(n)[:, None], g["pred"]] = 1
+    for name, yt, kw in (("probs_f64", eta, dict(dtype=np.float64, skip_tn=True)),
+                         ("probs_none", eta, dict()),
+                         ("lab_norm", lab, dict(normalize=True)),
+                         ("lab_f64_norm_skip", lab, dict(normalize=True, skip_tn=True, dtype=np.float64))):
+        exact = np.stack([np.asarray(v, np.float64) for v in xb.calculate_confusion_matrix(yt, pred, order="ordered", **kw)])
+        assert (exact == g[name]).all(), name
+        fast = np.stack([np.asarray(v, np.float64) for v in xb.calculate_confusion_matrix(yt, pred, **kw)])
+        assert np.allclose(fast, g[name], rtol=1e-6, atol=1e-9), name
+    c = xb.calculate_confusion_matrix(lab, pred, axis=1, dtype=np.float64)
+    assert np.allclose(np.stack(list(c)), g["lab_axis1"], rtol=0, atol=1e-9)
+    y = csr_matrix((g["c_data"], g["c_indices"], g["c_indptr"]), shape=tuple(g["c_shape"]))
+    nn = y.shape[0]
+    p = csr_matrix((np.ones(nn * 4, dtype=np.float32), g["c_pred"].reshape(-1), np.arange(nn + 1) * 4), shape=y.shape)
+    for name, kw in (("csr_f64", dict(dtype=np.float64, skip_tn=True)), ("csr_none", dict()),
+                     ("csr_norm", dict(normalize=True, dtype=np.float64))):
+        exact = np.stack([np.asarray(v, np.float64) for v in xb.calculate_confusion_matrix(y, p, order="ordered", **kw)])
+        assert (exact == g[name]).all(), name
+        fast = np.stack([np.asarray(v, np.float64) for v in xb.calculate_confusion_matrix(y, p, **kw)])
+        assert np.allclose(fast, g[name], rtol=1e-6, atol=1e-9), name
+
+
+def test_confmat_types_and_errors(xb):
+    yt = (np.random.rand(50, 20) < 0.2).astype(np.int64)
+    yp = (np.random.rand(50, 20) < 0.2).astype(np.float32)
+    c = xb.calculate_confusion_matrix(yt, yp)
+    assert isinstance(c, xb.ConfusionMatrix)
+    tp, fp, fn, tn = c
+    assert np.allclose(tp, (yt * yp).sum(0)) and np.allclose(tn, ((1 - yt) * (1 - yp)).sum(0))
+    ct = xb.calculate_confusion_matrix(torch.from_numpy(yp).cuda(), torch.from_numpy(yp).cuda())
+    assert isinstance(ct.tp, torch.Tensor) and ct.tp.is_cuda
+    with pytest.raises(ValueError):
+        xb.calculate_confusion_matrix(yp, csr_matrix(yp))
+    with pytest.raises(ValueError):
+        xb.calculate_confusion_matrix(yp, yp[:, :5])
+    s = c + c
+    assert (s.tp == 2 * c.tp).all() and (c * 2 == s)
+
+
+# ------------------------------------------------------------------------------------------
+# BCA, sequential-exact mode: bit parity with the reference's golden runs
+# ------------------------------------------------------------------------------------------
+
+def _metric(xb, name):
+    from xcolumns_b200 import metrics as M
+    return {"f1": M.binary_f1_score_on_conf_matrix, "recall": M.binary_recall_on_conf_matrix,
+            "precision": M.binary_precision_on_conf_matrix, "jaccard": M.binary_jaccard_score_on_conf_matrix,
+            "fbeta": M.binary_fbeta_score_on_conf_matrix, "balanced_accuracy": M.binary_balanced_accuracy_on_conf_matrix,
+            "gmean": M.binary_gmean_on_conf_matrix, "hmean": M.binary_hmean_on_conf_matrix}[name]
+
+
+BCA_DENSE = [
+    ("f1", "f1", 5, dict(seed=0, skip_tn=True)),
+    ("f1_f64", "f1", 5, dict(seed=0, skip_tn=True)),
+    ("recall", "recall", 5, dict(seed=3, skip_tn=True)),
+    ("precision", "precision", 3, dict(seed=4, skip_tn=True)),
+    ("jaccard", "jaccard", 5, dict(seed=5, skip_tn=True)),
+    ("fbeta2", "fbeta", 5, dict(seed=6, skip_tn=True, metric_kwargs={"beta": 2.0, "epsilon": 1e-6})),
+    ("balacc", "balanced_accuracy", 5, dict(seed=7, skip_tn=False)),
+    ("gmean", "gmean", 5, dict(seed=8, skip_tn=False)),
+    ("hmean", "hmean", 5, dict(seed=9, skip_tn=False)),
+    ("f1_noshuffle", "f1", 5, dict(seed=0, skip_tn=True, shuffle_order=False)),
+    ("f1_random", "f1", 5, dict(seed=10, skip_tn=True, init_y_pred="random")),
+    ("f1_greedy", "f1", 5, dict(seed=11, skip_tn=True, init_y_pred="greedy")),
+    ("f1_sum", "f1", 5, dict(seed=12, skip_tn=True, metric_aggregation="sum", tolerance=1e-4)),
+]
+
+
+@pytest.mark.parametrize("name,metric,k,kw", BCA_DENSE, ids=[c[0] for c in BCA_DENSE])
+def test_bca_exact_dense_golden(xb, golden, name, metric, k, kw):
+    g = golden("bca_dense")
+    eta = g["eta"].astype(np.float64) if name.endswith("f64") else g["eta"]
+    pred, meta = xb.predict_using_bc_with_0approx(eta, _metric(xb, metric), k, return_meta=True, mode="exact", **kw)
+    assert type(pred) is np.ndarray and pred.dtype == eta.dtype and pred.shape == eta.shape
+    assert (_idx(pred, k) == g[name + "_pred"]).all()
+    assert meta["iters"] == len(g[name + "_util"])
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+@pytest.mark.parametrize("n,m,k", [(700, 513, 5), (257, 4100, 3), (2000, 1000, 5)])
+def test_bca_exact_dense_vs_oracle(xb, oracle, n, m, k):
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(n, m, seed=77 + n)
+    pred, meta = xb.predict_optimizing_macro_f1_score_using_bc(eta, k, seed=1, return_meta=True, mode="exact")
+    opred, ometa = oracle.predict_using_bc_with_0approx(eta, "f1", k, seed=1, skip_tn=True)
+    assert (pred.astype(np.uint8) == opred).all()
+    assert meta["utilities"] == ometa["utilities"]
+
+
+BCA_CSR = [("f1", "f1", 5, 0), ("recall", "recall", 5, 1), ("jaccard", "jaccard", 3, 2), ("f1_f64", "f1", 5, 0)]
+
+
+@pytest.mark.parametrize("name,metric,k,seed", BCA_CSR, ids=[c[0] for c in BCA_CSR])
+def test_bca_exact_csr_golden(xb, golden, name, metric, k, seed):
+    g = golden("bca_csr")
+    data = g["data"].astype(np.float64) if name.endswith("f64") else g["data"]
+    y = csr_matrix((data, g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    pred, meta = xb.predict_using_bc_with_0approx(y, _metric(xb, metric), k, seed=seed, skip_tn=True,
+                                                  return_meta=True, mode="exact")
+    assert isinstance(pred, csr_matrix) and pred.dtype == y.dtype and pred.shape == y.shape
+    assert pred.indices.dtype == y.indices.dtype and pred.indptr.dtype == y.indptr.dtype
+    assert (pred.indices.reshape(-1, k) == g[name + "_pred"]).all()
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+@pytest.mark.parametrize("name,kw", [("cov", dict(seed=0)), ("cov_a07", dict(seed=1, alpha=0.7))])
+def test_coverage_exact_csr_golden(xb, golden, name, kw):
+    g = golden("coverage_csr")
+    y = csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    pred, meta = xb.predict_optimizing_coverage_using_bc(y, 5, return_meta=True, mode="exact", **kw)
+    assert (pred.indices.reshape(-1, 5) == g[name + "_pred"]).all()
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-12 if name == "cov" else 1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# BCA, batched block-Jacobi mode: utilities within 1e-4 of the sequential reference
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("metric", ["f1", "recall", "precision"])
+def test_bca_batched_dense_vs_oracle(xb, oracle, metric):
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(6000, 2000, seed=1002)
+    opred, ometa = oracle.predict_using_bc_with_0approx(eta, metric, 5, seed=0, skip_tn=True)
+    pred, meta = xb.predict_using_bc_with_0approx(eta, _metric(xb, metric), 5, seed=0, skip_tn=True,
+                                                  return_meta=True, mode="batched")
+    assert pred.shape == eta.shape and (pred.sum(1) == 5).all() and pred.dtype == eta.dtype
+    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < TOL
+    # the returned prediction really has the reported utility (recomputed by the oracle)
+    tp, fp, fn, tn = oracle.calculate_confusion_matrix(eta, pred, skip_tn=True, dtype=np.float64)
+    mid, c1, b2, eps = oracle.metric_params(metric)
+    u = oracle._utility(mid, c1, b2, eps, tp, fp, fn, tn, eta.shape[0], "mean")
+    assert abs(u - meta["utilities"][-1]) < 1e-9
+
+
+def test_bca_batched_csr_vs_oracle(xb, oracle):
+    from xcolumns_b200.synth import csr_probs
+    y = csr_probs(4000, 20000, 60, seed=1004)
+    opred, ometa = oracle.predict_using_bc_with_0approx(y, "f1", 5, seed=0, skip_tn=True)
+    pred, meta = xb.predict_optimizing_macro_f1_score_using_bc(y, 5, seed=0, return_meta=True, mode="batched")
+    assert isinstance(pred, csr_matrix) and (np.diff(pred.indptr) == 5).all()
+    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < TOL
+
+
+def test_coverage_batched_vs_oracle(xb, oracle):
+    from xcolumns_b200.synth import csr_probs
+    y = csr_probs(3000, 2000, 40, seed=1006)
+    opred, ometa = oracle.predict_optimizing_coverage_using_bc(y, 5, seed=0)
+    pred, meta = xb.predict_optimizing_coverage_using_bc(y, 5, seed=0, return_meta=True, mode="batched")
+    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < TOL
+    dense = np.asarray(y.todense())
+    predd, metad = xb.predict_optimizing_coverage_using_bc(dense, 5, seed=0, return_meta=True, mode="batched")
+    assert type(predd) is np.ndarray and (predd.sum(1) == 5).all()
+    assert abs(metad["utilities"][-1] - ometa["utilities"][-1]) < TOL
+
+
+def test_bca_torch_cuda_input(xb, oracle):
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(512, 256, seed=9)
+    t = torch.from_numpy(eta).cuda()
+    pred = xb.predict_optimizing_macro_f1_score_using_bc(t, 5, seed=0, mode="exact")
+    assert isinstance(pred, torch.Tensor) and pred.is_cuda and pred.dtype == t.dtype
+    opred, _ = oracle.predict_using_bc_with_0approx(eta, "f1", 5, seed=0, skip_tn=True)
+    assert (pred.cpu().numpy().astype(np.uint8) == opred).all()
+
+
+def test_bca_reference_properties(xb):
+    """The reference's own test assertions (tests/test_block_coordinate.py:27-30, :95-96)."""
+    from xcolumns_b200 import metrics as M
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(3000, 25, seed=2024, spread=1.0)
+    rng = np.random.default_rng(0)
+    y_true = (rng.random(eta.shape) < eta).astype(np.float32)
+    k = 3
+    for mode in ("exact", "batched"):
+        pred = xb.predict_optimizing_macro_recall_using_bc(eta, k, seed=2024, mode=mode)
+        assert type(pred) == type(eta) and pred.dtype == eta.dtype and (pred.sum(axis=1) == k).all()
+        top = xb.predict_top_k(eta, k)
+        rec = lambda p: float(M.macro_recall_on_conf_matrix(*xb.calculate_confusion_matrix(y_true, p)))
+        assert rec(pred) >= rec(top)
+
+
+def test_unsupported_metric_is_loud(xb):
+    eta = np.random.rand(10, 20).astype(np.float32)
+    with pytest.raises(NotImplementedError):
+        xb.predict_using_bc_with_0approx(eta, lambda tp, fp, fn, tn: tp, 3)
+
+
+# ------------------------------------------------------------------------------------------
+# Frank-Wolfe
+# ------------------------------------------------------------------------------------------
+
+FW = [("f1_proba", "f1", "eta", dict(max_iters=10, skip_tn=True)),
+      ("f1_lab", "f1", "lab", dict(max_iters=10, skip_tn=True, metric_kwargs={"epsilon": 1e-4})),
+      ("recall_lab", "recall", "lab", dict(max_iters=6, skip_tn=True, metric_kwargs={"epsilon": 1e-4})),
+      ("balacc_lab", "balanced_accuracy", "lab", dict(max_iters=6, metric_kwargs={"epsilon": 1e-4}))]
+
+
+@pytest.mark.parametrize("name,metric,yt,kw", FW, ids=[c[0] for c in FW])
+def test_fw_dense_golden(xb, golden, name, metric, yt, kw):
+    from xcolumns_b200 import metrics as M
+    g = golden("fw_dense")
+    mf = {"f1": M.macro_f1_score_on_conf_matrix, "recall": M.macro_recall_on_conf_matrix,
+          "balanced_accuracy": M.macro_balanced_accuracy_on_conf_matrix}[metric]
+    clf, meta = xb.find_classifier_using_fw(g[yt], g["eta"], mf, 5, seed=0, return_meta=True, **kw)
+    assert meta["iters"] == int(g[name + "_iters"])
+    assert clf.a.shape == g[name + "_a"].shape and clf.a.dtype == np.float32 and clf.p.dtype == np.float32
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=TOL)
+    assert np.allclose(meta["classifiers_utilities"], g[name + "_cutil"], rtol=0, atol=TOL)
+    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=5e-3)
+    assert np.allclose(clf.p, g[name + "_p"], rtol=0, atol=5e-3)
+
+
+def test_fw_vs_oracle_and_predict(xb, oracle):
+    from xcolumns_b200 import metrics as M
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(1500, 800, seed=1005)
+    clf, meta = xb.find_classifier_using_fw(eta, eta, M.macro_f1_score_on_conf_matrix, 5, max_iters=8, skip_tn=True,
+                                            seed=0, return_meta=True)
+    A, B, P, ometa = oracle.find_classifier_using_fw(eta, eta, "f1", 5, max_iters=8, skip_tn=True, seed=0)
+    assert meta["iters"] == ometa["iters"]
+    assert np.allclose(meta["utilities"], ometa["utilities"], rtol=0, atol=TOL)
+    assert abs(float(clf.p.sum()) - 1.0) < 1e-5
+    pred = clf.predict(eta, seed=3)
+    assert pred.shape == eta.shape and (pred.sum(1) == 5).all()
+    # same draws as the reference's per-row rng.choice, then the oracle's weighted top-k per row
+    rng = np.random.default_rng(3)
+    choice = np.array([rng.choice(np.arange(len(clf.p)), p=clf.p) for _ in range(eta.shape[0])])
+    for c in np.unique(choice):
+        rows = np.nonzero(choice == c)[0]
+        want = oracle.topk_indices_dense(eta[rows], 5, clf.a[c], clf.b[c])[0]
+        assert (_idx(pred[rows], 5) == want).all()
+
+
+def test_fw_csr(xb, oracle):
+    from xcolumns_b200.synth import csr_probs
+    y = csr_probs(2000, 5000, 50, seed=5)
+    clf, meta = xb.find_classifier_optimizing_macro_f1_score_using_fw(y, y, 5, max_iters=5, seed=0, return_meta=True)
+    A, B, P, ometa = oracle.find_classifier_using_fw(y, y, "f1", 5, max_iters=5, skip_tn=True, seed=0)
+    assert meta["iters"] == ometa["iters"]
+    assert np.allclose(meta["utilities"], ometa["utilities"], rtol=0, atol=TOL)
+    assert meta["utilities"][-1] > meta["utilities"][0]

@@ -1,0 +1,531 @@
+"""Block Coordinate Ascent on the GPU (drop-in for xcolumns/block_coordinate.py:296-801).
+
+Two execution modes behind the reference's signature (selected with the ``mode`` keyword or
+$XCOLUMNS_B200_MODE; the reference's ``**kwargs`` swallows the extra keyword):
+
+``exact``    sequential Gauss-Seidel sweep in the reference's instance order and float64 operation
+             order (csrc/bca_exact.cu).  Predictions, running state and per-sweep utilities are
+             bit-comparable with the reference on tie-free inputs.  Latency bound by construction.
+``batched``  block-Jacobi: the (shuffled) instance order is cut into batches; all rows of a batch
+             see the same frozen state and their confusion deltas are committed together
+             (csrc/bca_batched.cu).  One streaming pass over y_proba per sweep at HBM speed; final
+             utilities agree with the reference within 1e-4 when batch <= n/8.
+             With torch.distributed initialised and ``distributed=True`` every rank holds a row
+             shard and the per-batch deltas are all-reduced (NCCL over NVLink).
+``auto``     (default) exact for n <= 20000 rows, batched above.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from time import time
+from typing import Any, Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix
+
+from . import _device as dev
+from . import metrics as M
+from ._lib import XC_SUM_FAST, XC_SUM_ORDERED, MetricParams
+from .distributed import Comm, make_comm
+from .types import DefaultAccDataDType, Matrix
+from .utils import add_kwargs_to_signature, log_info, log_warning
+from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
+
+_AUTO_EXACT_MAX_ROWS = 20000
+
+
+def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div) -> MetricParams:
+    return MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)), reserved=0,
+                        c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=float(n_div))
+
+
+def _resolve_mode(mode: Optional[str], n: int, greedy: bool) -> str:
+    mode = mode or os.environ.get("XCOLUMNS_B200_MODE", "auto")
+    if mode not in ("auto", "exact", "batched"):
+        raise ValueError("mode must be 'auto', 'exact' or 'batched'")
+    if mode == "auto":
+        mode = "exact" if (n <= _AUTO_EXACT_MAX_ROWS or greedy) else "batched"
+    return mode
+
+
+# ------------------------------------------------------------------------------------------
+# initial prediction (block_coordinate.py:28-51)
+# ------------------------------------------------------------------------------------------
+
+def _initial_pred(y_proba, data, init_y_pred, k: int, seed, device) -> torch.Tensor:
+    n, m = data.n, data.m
+    if isinstance(init_y_pred, str) and init_y_pred == "top":
+        if isinstance(data, dev.CsrDev):
+            return topk_csr_device(data, k, None, None)[0]
+        return topk_dense_device(data, k, None, None, data.code)[0]
+    if isinstance(init_y_pred, str) and init_y_pred in ("random", "greedy"):
+        # dense: utils.py:104-116 (numpy Generator, bit-identical).  CSR: the reference draws with
+        # numba's private Mersenne state (numba_csr_functions.py:93-112), which cannot be
+        # reproduced without numba; the same numpy recipe is used (documented deviation).
+        rng = np.random.default_rng(seed)
+        labels = np.arange(m)
+        idx = np.empty((n, k), dtype=np.int32)
+        for i in range(n):
+            idx[i] = np.sort(rng.choice(labels, k, replace=False, shuffle=False))
+        return torch.from_numpy(idx).to(device)
+    if isinstance(init_y_pred, (np.ndarray, torch.Tensor, csr_matrix)):
+        if tuple(init_y_pred.shape) != (n, m):
+            raise ValueError(f"init_y_pred must have shape (n, m) = ({n}, {m}), but has shape {init_y_pred.shape}")
+        return dev.dense_pred_to_compact(init_y_pred, k, device)
+    raise ValueError(
+        f"init_y_pred must be np.ndarray, Torch.tensor, csr_matrix or str in ['random', 'greedy', 'top'], but has type {type(init_y_pred)}")
+
+
+# ------------------------------------------------------------------------------------------
+# device session
+# ------------------------------------------------------------------------------------------
+
+class BcaSession:
+    """State of one BCA run on one device: probability matrix (dense or CSR), compact prediction,
+    float64 confusion state, coefficient / delta workspaces.  Used by the public functions below
+    and driven directly by bench.py on HBM-resident inputs."""
+
+    def __init__(self, data, k: int, params: MetricParams, util_params: MetricParams, aggregation: str,
+                 comm: Optional[Comm] = None):
+        self.data = data
+        self.is_csr = isinstance(data, dev.CsrDev)
+        self.device = (data.data if self.is_csr else data.t).device
+        self.ctx = dev.ctx_for(self.device)
+        self.k = k
+        self.p = params
+        self.up = util_params
+        self.agg = 0 if aggregation == "mean" else 1
+        self.comm = comm or Comm(None)
+        self.n, self.m = data.n, data.m
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.state = torch.zeros((4, self.m), **f64)           # tp, fp, fn, tn
+        self.state[3].fill_(-1.0)
+        self.delta = torch.zeros((3, self.m), **f64)           # pending batch deltas
+        self.colsum: Optional[torch.Tensor] = None
+        self.coef_n = torch.empty((self.m, 2), dtype=torch.float32, device=self.device)
+        self.coef_s = torch.empty((self.m, 2), dtype=torch.float32, device=self.device)
+        self.util_buf = torch.zeros(8, **f64)
+        self.pred: Optional[torch.Tensor] = None
+
+    # -- small helpers ---------------------------------------------------------------------
+    def _s(self):
+        return dev.stream_ptr(self.device)
+
+    def _sp(self, i):
+        return C.c_void_p(self.state[i].data_ptr())
+
+    def _dp(self, i):
+        return C.c_void_p(self.delta[i].data_ptr())
+
+    # -- state from the current prediction ---------------------------------------------------
+    def recompute(self, order: int) -> None:
+        """tp / fp / fn (and tn) from scratch (block_coordinate.py:430-436, :465-467)."""
+        d, k = self.data, self.k
+        if order == XC_SUM_ORDERED:
+            if self.comm.world > 1:
+                raise NotImplementedError("sequential-exact BCA runs on one GPU (replicas only)")
+            if self.is_csr:
+                self.ctx.call("xc_confmat_csr_compact", dev.ptr(d.data), dev.ptr(d.indices), dev.ptr(d.indptr), d.code,
+                              dev.ptr(self.pred), k, d.n, d.m, order, self._sp(0), self._sp(1), self._sp(2), self._s())
+            else:
+                self.ctx.call("xc_confmat_dense_compact", dev.ptr(d.t), d.code, d.ld, dev.ptr(self.pred), k, d.n, d.m,
+                              order, None, self._sp(0), self._sp(1), self._sp(2), self._s())
+        elif self.is_csr:
+            self.ctx.call("xc_confmat_csr_compact", dev.ptr(d.data), dev.ptr(d.indices), dev.ptr(d.indptr), d.code,
+                          dev.ptr(self.pred), k, d.n, d.m, order, self._sp(0), self._sp(1), self._sp(2), self._s())
+            if self.comm.world > 1:
+                self.comm.allreduce_sum_(self.state[0:3])
+        else:
+            if self.colsum is None:  # sum_i eta_ij never changes: one extra pass per call, not per sweep
+                self.colsum = torch.empty(self.m, dtype=torch.float64, device=self.device)
+                self.ctx.call("xc_colsum_dense", dev.ptr(d.t), d.code, d.n, d.m, d.ld, dev.ptr(self.colsum), self._s())
+                self.comm.allreduce_sum_(self.colsum)
+            self.ctx.call("xc_confmat_dense_compact", dev.ptr(d.t), d.code, d.ld, dev.ptr(self.pred), k, d.n, d.m,
+                          order, dev.ptr(self.colsum), self._sp(0), self._sp(1), self._sp(2), self._s())
+            if self.comm.world > 1:
+                self.comm.allreduce_sum_(self.state[0:2])
+                torch.sub(self.colsum, self.state[0], out=self.state[2])
+        if self.p.skip_tn:
+            self.state[3].fill_(-1.0)
+        else:  # -tp - fp - fn + n   (confusion_matrix.py:397, n = number of rows)
+            n_total = self.comm.n_global(self.n)
+            self.state[3] = -self.state[0] - self.state[1] - self.state[2] + n_total
+
+    def utility_device(self, slot: int) -> None:
+        """block_coordinate.py:54-90 on the device; result lands in util_buf[slot]."""
+        self.ctx.call("xc_utility", C.byref(self.up), self.agg, self._sp(0), self._sp(1), self._sp(2), self._sp(3),
+                      self.m, C.c_void_p(self.util_buf[slot:].data_ptr()), self._s())
+
+    # -- sweeps -------------------------------------------------------------------------------
+    def sweep_exact(self, order_dev: torch.Tensor, greedy: bool) -> None:
+        d, k = self.data, self.k
+        if self.is_csr:
+            self.ctx.call("xc_bca_exact_sweep_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
+                          d.n, d.m, dev.ptr(order_dev), int(order_dev.numel()), k, C.byref(self.p), int(greedy),
+                          dev.ptr(self.pred), self._sp(0), self._sp(1), self._sp(2), self._s())
+        else:
+            self.ctx.call("xc_bca_exact_sweep_dense", dev.ptr(d.t), d.code, d.n, d.m, d.ld, dev.ptr(order_dev),
+                          int(order_dev.numel()), k, C.byref(self.p), int(greedy), dev.ptr(self.pred), self._sp(0),
+                          self._sp(1), self._sp(2), self._sp(3), self._s())
+
+    def sweep_batched(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int] = None) -> None:
+        """One block-Jacobi sweep over the (local) rows in order_dev, `batch` rows per commit.
+        n_batches (distributed): common number of commits so every rank joins every all-reduce."""
+        d, k = self.data, self.k
+        n_loc = int(order_dev.numel())
+        nb = n_batches if n_batches is not None else (n_loc + batch - 1) // batch
+        for b in range(nb):
+            lo = min(b * batch, n_loc)
+            hi = min(lo + batch, n_loc)
+            # fold the pending deltas into the state, refresh the gain coefficients
+            self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
+                          self._dp(1), self._dp(2), self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
+            if hi > lo:
+                rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
+                if self.is_csr:
+                    self.ctx.call("xc_bca_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
+                                  rows, hi - lo, k, dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
+                                  self._dp(0), self._dp(1), self._dp(2), self._s())
+                else:
+                    self.ctx.call("xc_bca_batch_dense", dev.ptr(d.t), d.code, d.m, d.ld, rows, hi - lo, k,
+                                  dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._dp(0),
+                                  self._dp(1), self._dp(2), self._s())
+            if self.comm.world > 1:
+                self.comm.allreduce_sum_(self.delta)
+
+
+def _host_utility(binary_metric_func, aggregation: str, state: torch.Tensor, n_div) -> float:
+    """The reference's own utility expression on the float64 state copied to the host
+    (block_coordinate.py:54-90; note that it does NOT forward metric_kwargs)."""
+    tp, fp, fn, tn = state.cpu().numpy()
+    if callable(binary_metric_func):
+        vals = binary_metric_func(tp / n_div, fp / n_div, fn / n_div, tn / n_div)
+    else:
+        vals = np.array([f(tp[i] / n_div, fp[i] / n_div, fn[i] / n_div, tn[i] / n_div)
+                         for i, f in enumerate(binary_metric_func)])
+    if not isinstance(vals, np.ndarray):
+        raise ValueError(f"binary_metric_func must return np.ndarray, but returned {type(vals)}")
+    if vals.shape != (tp.shape[0],):
+        raise ValueError(f"binary_metric_func must return np.ndarray of shape {tp.shape[0]}, but returned {vals.shape}")
+    if aggregation == "sum":
+        return vals.sum()
+    if aggregation == "mean":
+        return vals.mean()
+    raise ValueError(f"Unsupported utility aggregation function: {aggregation}, must be either 'mean' or 'sum'")
+
+
+def default_batch_rows(n: int, world: int = 1) -> int:
+    """Rows committed together by one rank: global batch <= n_global / 16 (SURVEY.md App. C:
+    <= n/6 keeps the reference's fixed point within 3e-7), at most 16384."""
+    return max(1, min(16384, n // 16 if n >= 16 else 1))
+
+
+def predict_using_bc_with_0approx(
+    y_proba: Matrix,
+    binary_metric_func: Union[Callable, List[Callable]],
+    k: int,
+    metric_aggregation: str = "mean",  # "mean" or "sum"
+    normalize_conf_matrix: bool = True,
+    metric_kwargs: Optional[Dict[str, Any]] = None,
+    maximize: bool = True,
+    tolerance: float = 1e-6,
+    init_y_pred: Union[str, Matrix] = "top",  # "random", "top", "greedy", Matrix
+    max_iters: int = 100,
+    shuffle_order: bool = True,
+    skip_tn: bool = False,
+    return_meta: bool = False,
+    seed: Optional[int] = None,
+    verbose: bool = False,
+    **kwargs,
+) -> Union[Matrix, Tuple[Matrix, Dict[str, Any]]]:
+    """Block coordinate ascent/descent on the 0-th order approximation of the Expected Test Utility
+    for a metric that decomposes into per-label binary metrics.  Arguments, defaults, return value
+    and ``meta`` keys follow the reference (xcolumns/block_coordinate.py:296-499).
+
+    Extra keywords (absorbed by the reference's ``**kwargs``): ``mode`` ("auto" | "exact" |
+    "batched"), ``batch_size`` (rows per commit in batched mode), ``distributed`` (bool: y_proba is
+    this rank's row shard of a torch.distributed job), ``y_pred_format`` ("same" | "indices": return
+    the compact (n, k) int32 label ids instead of materialising a dense matrix)."""
+    mode = kwargs.pop("mode", None)
+    batch_size = kwargs.pop("batch_size", None)
+    distributed = kwargs.pop("distributed", False)
+    y_pred_format = kwargs.pop("y_pred_format", "same")
+
+    log_info(f"Starting optimization of ETU metric using block coordinate "
+             f"{'ascent (maximization)' if maximize else 'descent (minimization)'} algorithm ...", verbose)
+    meta: Dict[str, Any] = {"utilities": [], "iters": 0, "time": time()}
+
+    _check_k(k)
+    if not isinstance(y_proba, (np.ndarray, torch.Tensor, csr_matrix)):
+        raise ValueError("y_proba must be either np.ndarray, torch.Tensor, or csr_matrix")
+    if metric_aggregation not in ("mean", "sum"):
+        raise ValueError(f"Unsupported utility aggregation function: {metric_aggregation}, must be either 'mean' or 'sum'")
+    if k <= 0:
+        raise NotImplementedError("xcolumns_b200: BCA without a budget (k=0) is not implemented on the GPU path yet")
+    metric_id, beta, eps = M.resolve_binary_metric(binary_metric_func, metric_kwargs)
+    if metric_id in M.TN_METRICS and skip_tn:
+        log_warning("skip_tn=True with a metric that uses true negatives: tn is the constant -1 like in the reference")
+
+    n, m = y_proba.shape
+    if k > m:
+        raise ValueError(f"k={k} is larger than the number of labels m={m}")
+    greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
+    mode = _resolve_mode(mode, n, greedy)
+
+    device = dev.pick_device(y_proba)
+    comm = make_comm(distributed, device)
+    is_csr = isinstance(y_proba, csr_matrix)
+    data = dev.csr_to_device(y_proba, device) if is_csr else dev.dense_to_device(y_proba, device)
+
+    n_div = n if normalize_conf_matrix else 1            # block_coordinate.py:403-405
+    n_div_global = comm.n_global(n) if normalize_conf_matrix else 1
+    n_order = n if normalize_conf_matrix else 1          # order = arange(n) after the overwrite (:414)
+    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div_global)
+    util_params = _metric_params(metric_id, 1.0, 1e-9, maximize, skip_tn, n_div_global)  # no kwargs (:63)
+
+    sess = BcaSession(data, k, params, util_params, metric_aggregation, comm)
+    sess.pred = _initial_pred(y_proba, data, init_y_pred, k, seed, device)
+    meta["mode"] = mode
+    meta["h2d_bytes"] = data.h2d_bytes
+
+    if mode == "exact":
+        if comm.world > 1:
+            raise NotImplementedError("sequential-exact BCA does not shard (replicas only); use mode='batched'")
+        if is_csr and not skip_tn:
+            raise NotImplementedError("xcolumns_b200: sequential-exact CSR BCA carries tn only with skip_tn=True")
+        rng = np.random.default_rng(seed)                # :413
+        order = np.arange(n_order)                       # :414
+        new_u = None
+        for j in range(1, max_iters + 1):
+            log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+            if shuffle_order:
+                rng.shuffle(order)
+            if greedy:
+                sess.state.zero_()
+            elif new_u is None:
+                sess.recompute(XC_SUM_ORDERED)
+            # (from the 2nd sweep on the state recomputed after the previous sweep is reused:
+            #  the reference recomputes the identical sums again at :430)
+            old_u = _host_utility(binary_metric_func, metric_aggregation, sess.state, n_div) if (
+                new_u is None or greedy) else new_u
+            order_dev = torch.from_numpy(order.astype(np.int32)).to(device)
+            sess.sweep_exact(order_dev, greedy)
+            sess.recompute(XC_SUM_ORDERED)
+            new_u = _host_utility(binary_metric_func, metric_aggregation, sess.state, n_div)
+            greedy = False
+            meta["iters"] = j
+            meta["utilities"].append(new_u)
+            log_info(f"    Iteration {j}/{max_iters} finished, expected metric value: {old_u} -> {new_u}", verbose)
+            if (maximize and new_u - old_u < tolerance) or (not maximize and new_u - old_u > tolerance):
+                log_info(f"  Stopping because improvement of expected metric value is smaller than {tolerance}", verbose)
+                break
+    else:
+        if greedy:
+            raise NotImplementedError("init_y_pred='greedy' needs the sequential mode (mode='exact')")
+        if metric_id not in M.AFFINE_GAIN_METRICS:
+            raise NotImplementedError(
+                "xcolumns_b200 batched mode fuses the metrics whose marginal gain is affine in the probability "
+                "(precision, recall, F-beta/F1); use mode='exact' for Jaccard / balanced accuracy / G-mean / H-mean")
+        batch = int(batch_size) if batch_size else default_batch_rows(n_order, comm.world)
+        n_batches = comm.max_int((n_order + batch - 1) // batch)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(0 if seed is None else int(seed) + 7919 * comm.rank)
+        order_dev = torch.arange(n_order, dtype=torch.int32, device=device)
+        sess.recompute(XC_SUM_FAST)
+        sess.utility_device(0)
+        meta["batch_size"] = batch
+        for j in range(1, max_iters + 1):
+            log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+            if shuffle_order:
+                order_dev = torch.randperm(n_order, generator=gen, device=device, dtype=torch.int32)
+            sess.delta.zero_()
+            sess.sweep_batched(order_dev, batch, n_batches)
+            sess.recompute(XC_SUM_FAST)
+            sess.utility_device(1)
+            old_u, new_u = (float(v) for v in sess.util_buf[:2].cpu())
+            sess.util_buf[0] = sess.util_buf[1]
+            meta["iters"] = j
+            meta["utilities"].append(new_u)
+            log_info(f"    Iteration {j}/{max_iters} finished, expected metric value: {old_u} -> {new_u}", verbose)
+            if (maximize and new_u - old_u < tolerance) or (not maximize and new_u - old_u > tolerance):
+                log_info(f"  Stopping because improvement of expected metric value is smaller than {tolerance}", verbose)
+                break
+
+    meta["launches"] = sess.ctx.launches()
+    y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format)
+    if return_meta:
+        meta["time"] = time() - meta["time"]
+        return y_pred, meta
+    return y_pred
+
+
+def _finish_pred(y_proba, pred: torch.Tensor, m: int, y_pred_format: str):
+    if y_pred_format == "indices":
+        return pred if isinstance(y_proba, torch.Tensor) and y_proba.is_cuda else pred.cpu().numpy()
+    if isinstance(y_proba, csr_matrix):
+        return dev.compact_to_csr_like(y_proba, pred, reference_padding=False)
+    return dev.compact_to_dense_like(y_proba, pred, m)
+
+
+# ------------------------------------------------------------------------------------------
+# coverage (block_coordinate.py:600-701; CSR semantics for both layouts)
+# ------------------------------------------------------------------------------------------
+
+def predict_optimizing_coverage_using_bc(
+    y_proba: Matrix,
+    k: int,
+    alpha: float = 1,
+    tolerance: float = 1e-6,
+    init_y_pred: Union[str, Matrix] = "top",
+    max_iters: int = 100,
+    shuffle_order: bool = True,
+    return_meta: bool = False,
+    seed: Optional[int] = None,
+    verbose: bool = False,
+    **kwargs,
+) -> Union[Matrix, Tuple[Matrix, Dict[str, Any]]]:
+    """Block coordinate ascent for coverage@k (optionally mixed with precision@k through alpha).
+    State: Ef[j] = prod_i (1 - yhat_ij * eta_ij), the probability that label j is never covered.
+    Same arguments as the reference; ``mode`` / ``batch_size`` / ``y_pred_format`` as above."""
+    mode = kwargs.pop("mode", None)
+    batch_size = kwargs.pop("batch_size", None)
+    y_pred_format = kwargs.pop("y_pred_format", "same")
+    log_info(f"Starting optimization of ETU coverage@{k} metric using block coordinate ascent algorithm ...", verbose)
+    if not isinstance(k, int) or k <= 0:
+        raise ValueError("k must be an integer > 0")
+    _check_k(k)
+    if not isinstance(y_proba, (np.ndarray, torch.Tensor, csr_matrix)):
+        raise ValueError("y_proba must be either np.ndarray or csr_matrix")
+    n, m = y_proba.shape
+    meta: Dict[str, Any] = {"utilities": [], "iters": 0, "time": time()}
+    if seed is not None:
+        np.random.seed(seed)  # global side effect kept from the reference (:632-633)
+    greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
+    mode = _resolve_mode(mode, n, greedy)
+    device = dev.pick_device(y_proba)
+    ctx = dev.ctx_for(device)
+    is_csr = isinstance(y_proba, csr_matrix)
+    data = dev.csr_to_device(y_proba, device) if is_csr else dev.dense_to_device(y_proba, device)
+    csr_view = data if is_csr else _dense_as_csr(data)
+    pred = _initial_pred(y_proba, data, init_y_pred if not greedy else "random", k, seed, device)
+    Ef = torch.empty(m, dtype=torch.float64, device=device)
+    sp = lambda: dev.stream_ptr(device)
+
+    def state(order):
+        ctx.call("xc_cov_state_csr", dev.ptr(csr_view.data), csr_view.code, dev.ptr(csr_view.indices),
+                 dev.ptr(csr_view.indptr), n, m, dev.ptr(pred), k, order, dev.ptr(Ef), sp())
+
+    def utility() -> float:
+        cov = 1 - float(Ef.cpu().numpy().mean())       # :592 (numpy pairwise mean, like the reference)
+        if alpha < 1:                                   # :593-595
+            tp = torch.zeros(m, dtype=torch.float64, device=device)
+            fp, fn = torch.zeros_like(tp), torch.zeros_like(tp)
+            ctx.call("xc_confmat_csr_compact", dev.ptr(csr_view.data), dev.ptr(csr_view.indices),
+                     dev.ptr(csr_view.indptr), csr_view.code, dev.ptr(pred), k, n, m, XC_SUM_FAST, dev.ptr(tp),
+                     dev.ptr(fp), dev.ptr(fn), sp())
+            cov = alpha * cov + (1 - alpha) * float((tp / n / k).sum())
+        return cov
+
+    meta["mode"] = mode
+    rng = np.random.default_rng(seed)
+    order = np.arange(n)
+    sum_order = XC_SUM_ORDERED if mode == "exact" else XC_SUM_FAST
+    batch = int(batch_size) if batch_size else default_batch_rows(n)
+    dEf = torch.ones(m, dtype=torch.float64, device=device)
+    new_cov = None
+    for j in range(1, max_iters + 1):
+        log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+        if shuffle_order:
+            rng.shuffle(order)
+        if greedy:
+            Ef.fill_(1.0)
+            old_cov = utility()
+        elif new_cov is None:
+            state(sum_order)
+            old_cov = utility()
+        else:
+            old_cov = new_cov
+        order_dev = torch.from_numpy(order.astype(np.int32)).to(device)
+        if mode == "exact":
+            ctx.call("xc_cov_exact_sweep_csr", dev.ptr(csr_view.data), csr_view.code, dev.ptr(csr_view.indices),
+                     dev.ptr(csr_view.indptr), n, m, dev.ptr(order_dev), n, k, C.c_double(float(alpha)), int(greedy),
+                     dev.ptr(pred), dev.ptr(Ef), sp())
+        else:
+            for lo in range(0, n, batch):
+                hi = min(n, lo + batch)
+                rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
+                if is_csr:
+                    ctx.call("xc_cov_batch_csr", dev.ptr(data.data), data.code, dev.ptr(data.indices),
+                             dev.ptr(data.indptr), rows, hi - lo, k, C.c_double(float(alpha)), dev.ptr(Ef),
+                             dev.ptr(pred), dev.ptr(dEf), sp())
+                else:
+                    ctx.call("xc_cov_batch_dense", dev.ptr(data.t), data.code, m, data.ld, rows, hi - lo, k,
+                             C.c_double(float(alpha)), dev.ptr(Ef), dev.ptr(pred), dev.ptr(dEf), sp())
+                ctx.call("xc_cov_fold", dev.ptr(Ef), dev.ptr(dEf), m, sp())
+        state(sum_order)
+        new_cov = utility()
+        greedy = False
+        meta["iters"] = j
+        meta["utilities"].append(new_cov)
+        log_info(f"    Iteration {j}/{max_iters} finished, expected coverage: {old_cov} -> {new_cov}", verbose)
+        if new_cov <= old_cov + tolerance:              # :690
+            log_info(f"  Stopping because improvement of expected coverage is smaller than {tolerance}", verbose)
+            break
+    y_pred = _finish_pred(y_proba, pred, m, y_pred_format)
+    if return_meta:
+        meta["time"] = time() - meta["time"]
+        return y_pred, meta
+    return y_pred
+
+
+def _dense_as_csr(d: dev.DenseDev) -> dev.CsrDev:
+    """Dense rows seen as CSR rows that store every non-zero label (what csr_matrix(dense) holds);
+    used only by the coverage state/sequential kernels, which are defined on stored entries."""
+    x = d.t[:, :d.m]
+    nz = x != 0
+    counts = nz.sum(1)
+    indptr = torch.zeros(d.n + 1, dtype=torch.int64, device=x.device)
+    indptr[1:] = counts.cumsum(0)
+    indices = nz.nonzero()[:, 1].to(torch.int32).contiguous()
+    return dev.CsrDev(x[nz].contiguous(), indices, indptr, d.n, d.m, d.code, 0)
+
+
+# ------------------------------------------------------------------------------------------
+# wrappers (block_coordinate.py:709-801)
+# ------------------------------------------------------------------------------------------
+
+def make_bc_wrapper(binary_metric_func: Callable, metric_name: str, maximize: bool = True,
+                    metric_aggregation: str = "mean", skip_tn: bool = False, warn_k_eq_0: bool = False):
+    """Factory of ``predict_optimizing_<metric>_using_bc(y_proba, k, **kwargs)`` wrappers around
+    :func:`predict_using_bc_with_0approx`; the wrapper exposes the forwarded keyword arguments in
+    its ``__signature__`` so callers can filter kwargs by name."""
+
+    def predict_optimizing_metric_using_bc(y_proba: Matrix, k: int, **kwargs):
+        if warn_k_eq_0 and k == 0:
+            log_warning(f"Warning: k=0 results in degenerated solution for {metric_name}!")
+        return predict_using_bc_with_0approx(y_proba, binary_metric_func, k, metric_aggregation=metric_aggregation,
+                                             maximize=maximize, skip_tn=skip_tn, **kwargs)
+
+    predict_optimizing_metric_using_bc.__doc__ = (
+        f"Predict for a given test set optimizing {metric_name} with block coordinate "
+        f"{'ascent' if maximize else 'descent'}; equivalent to predict_using_bc_with_0approx(y_proba, "
+        f"{binary_metric_func.__name__}, k, metric_aggregation={metric_aggregation!r}, maximize={maximize}, "
+        f"skip_tn={skip_tn}, ...).")
+    return add_kwargs_to_signature(predict_optimizing_metric_using_bc, predict_using_bc_with_0approx,
+                                   skip=["metric_func", "metric_aggregation", "maximize", "skip_tn"])
+
+
+predict_optimizing_macro_precision_using_bc = make_bc_wrapper(
+    M.binary_precision_on_conf_matrix, "macro-averaged precision", skip_tn=True, warn_k_eq_0=True)
+predict_optimizing_macro_recall_using_bc = make_bc_wrapper(
+    M.binary_recall_on_conf_matrix, "macro-averaged recall", skip_tn=True, warn_k_eq_0=True)
+predict_optimizing_macro_f1_score_using_bc = make_bc_wrapper(
+    M.binary_f1_score_on_conf_matrix, "macro-averaged F1 score", skip_tn=True)
+predict_optimizing_macro_jaccard_score_using_bc = make_bc_wrapper(
+    M.binary_jaccard_score_on_conf_matrix, "macro-averaged Jaccard score", skip_tn=True)
+predict_optimizing_macro_balanced_accuracy_using_bc = make_bc_wrapper(
+    M.binary_balanced_accuracy_on_conf_matrix, "macro-averaged balanced accuracy")
+predict_optimizing_macro_hmean_using_bc = make_bc_wrapper(M.binary_hmean_on_conf_matrix, "macro-averaged H-mean")
+predict_optimizing_macro_gmean_using_bc = make_bc_wrapper(M.binary_gmean_on_conf_matrix, "macro-averaged G-mean")

@@ -1,0 +1,542 @@
+// Batched block-Jacobi BCA sweep: per-label coefficient kernel + streaming batch kernels.
+//
+// Replaces the per-instance step of xcolumns/block_coordinate.py:132-293 (dense + CSR) and
+// :539-580 (coverage) evaluated against a state frozen for one batch of rows.  For metrics whose
+// marginal gain is affine in eta (precision / recall / F-beta)
+//     unselected label:  gain = A_j  + B_j  * eta_ij
+//     selected label:    gain = A'_j + B'_j * eta_ij      (own contribution removed)
+// so the dense batch is ONE streaming pass: 16-byte loads of eta, one FMA per element, a
+// warp-distributed top-k list seeded with the row's current selection (which gives a tight
+// threshold from the first element on), then float64 atomic deltas for the rows that changed.
+#include "xc_scan.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---- coefficient kernel -------------------------------------------------------------------------
+// D = u*(tp+fp) + v*(tp+fn) + E with E = eps*n_div (eps is added AFTER dividing by n in the
+// reference, block_coordinate.py:176-183 + metrics.py), c = numerator factor:
+//   precision (c,u,v) = (1,1,0); recall (1,0,1); F-beta (1+b^2, b^2, 1).
+__global__ void __launch_bounds__(kThreads)
+bca_coef_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn,
+                int64_t m, float2 *coef_n, float2 *coef_s)
+{
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= m) return;
+    double t = tp[j], f = fp[j], g = fn[j];
+    if (dtp) {
+        t += dtp[j]; f += dfp[j]; g += dfn[j];
+        tp[j] = t; fp[j] = f; fn[j] = g;
+        dtp[j] = 0.0; dfp[j] = 0.0; dfn[j] = 0.0;
+    }
+    double c, u, v;
+    if (p.metric == XC_METRIC_PRECISION) { c = 1.0; u = 1.0; v = 0.0; }
+    else if (p.metric == XC_METRIC_RECALL) { c = 1.0; u = 0.0; v = 1.0; }
+    else { c = p.c1; u = p.beta2; v = 1.0; }
+    const double E = p.eps * p.n_div;
+    const double D = u * (t + f) + v * (t + g) + E;
+    const double sgn = p.maximize ? 1.0 : -1.0;
+    const double ct = c * t;
+    // unselected: predict j for this row -> D grows by u
+    double Bn = c / (D + u), An = ct / (D + u) - ct / D;
+    // selected: un-predicting j -> D shrinks by u
+    double Bs = c / (D - u), As = ct / D - ct / (D - u);
+    coef_n[j] = make_float2((float)(sgn * Bn), (float)(sgn * An));
+    coef_s[j] = make_float2((float)(sgn * Bs), (float)(sgn * As));
+}
+
+// ---- shared epilogue: compare new selection with the old one, emit deltas, store the row ----------
+// lanes < k hold: old label / old eta (sorted as stored) and the new list entry (tk.idx).
+template <typename TE>
+__device__ __forceinline__ void bca_commit_row(const TE *__restrict__ row_ptr, int k, int old_j, TE old_e,
+                                               int new_j_unsorted, int32_t *__restrict__ pred_row, double *dtp,
+                                               double *dfp, double *dfn)
+{
+    const int lane = lane_id();
+    // sort new labels ascending
+    int src = warp_rank_src(new_j_unsorted, k);
+    int new_j = __shfl_sync(XC_FULL, new_j_unsorted, src);
+    bool stays_old = false, stays_new = false;
+    for (int t = 0; t < k; ++t) {
+        int nj = __shfl_sync(XC_FULL, new_j, t);
+        int oj = __shfl_sync(XC_FULL, old_j, t);
+        stays_old |= (nj == old_j);
+        stays_new |= (oj == new_j);
+    }
+    if (lane < k) {
+        const TE one = (TE)1;
+        if (!stays_old && old_j >= 0) {  // label leaves the prediction
+            atomicAdd(dtp + old_j, -(double)old_e);
+            atomicAdd(dfp + old_j, -(double)(TE)(one - old_e));
+            atomicAdd(dfn + old_j, (double)old_e);
+        }
+        if (!stays_new && new_j != 0x7fffffff) {  // label enters
+            TE e = row_ptr[new_j];
+            atomicAdd(dtp + new_j, (double)e);
+            atomicAdd(dfp + new_j, (double)(TE)(one - e));
+            atomicAdd(dfn + new_j, -(double)e);
+        }
+        pred_row[lane] = new_j == 0x7fffffff ? -1 : new_j;
+    }
+}
+
+// seed a list with the row's current selection evaluated under the "selected" coefficients
+template <typename G>
+__device__ __forceinline__ void seed_list(WarpTopK<G> &tk, G g, int j, int k)
+{
+    // k sequential warp-uniform inserts (k <= 32, once per row)
+    tk.init();
+    for (int t = 0; t < k; ++t) {
+        G gt = __shfl_sync(XC_FULL, g, t);
+        int jt = __shfl_sync(XC_FULL, j, t);
+        if (jt >= 0) tk.insert(gt, jt, k);
+    }
+}
+
+template <typename TE, int R>
+__global__ void __launch_bounds__(kThreads)
+bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ rows,
+                       int64_t n_rows, int k, const float2 *__restrict__ coef_n, const float2 *__restrict__ coef_s,
+                       int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn, bool vec_ok)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    XfAffine xf{coef_n};
+    for (int64_t grp = warp; grp * R < n_rows; grp += nwarps) {
+        const TE *rp[R];
+        int64_t row_id[R];
+        int old_j[R];
+        TE old_e[R];
+        WarpTopK<float> tk[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t i = grp * R + r;
+            bool valid = i < n_rows;
+            if (!valid) i = grp * R;
+            int64_t row = rows ? (int64_t)rows[i] : i;
+            row_id[r] = valid ? row : -1;
+            rp[r] = eta + row * ld;
+            old_j[r] = -1;
+            old_e[r] = (TE)0;
+            float g = 0.f;
+            if (lane < k) {
+                old_j[r] = pred_idx[row * k + lane];
+                if (old_j[r] >= 0) {
+                    old_e[r] = rp[r][old_j[r]];
+                    float2 cs = __ldg(coef_s + old_j[r]);
+                    g = fmaf(cs.x, (float)old_e[r], cs.y);
+                }
+            }
+            seed_list(tk[r], g, old_j[r], k);
+        }
+        xc_scan_rows<TE, float, R, true>(rp, m, vec_ok, xf, tk, old_j, k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (row_id[r] >= 0)  // warp-uniform
+                bca_commit_row<TE>(rp[r], k, old_j[r], old_e[r], tk[r].idx, pred_idx + row_id[r] * k, dtp, dfp, dfn);
+        }
+    }
+}
+
+// ---- CSR batch: one warp per row, candidates = stored labels ----------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bca_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                     const int64_t *__restrict__ indptr, const int32_t *__restrict__ rows, int64_t n_rows, int k,
+                     const float2 *__restrict__ coef_n, const float2 *__restrict__ coef_s,
+                     int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const T one = (T)1;
+    for (int64_t w = warp; w < n_rows; w += nwarps) {
+        const int64_t row = rows ? (int64_t)rows[w] : w;
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        int32_t *pred_row = pred_idx + row * k;
+        int old_j = -1;
+        if (lane < k) old_j = pred_row[lane];
+        WarpTopK<float> tk;
+        tk.init();
+        // every stored label is a candidate; selected ones use coef_s
+        for (int64_t q0 = s; q0 < e; q0 += 32) {
+            int64_t q = q0 + lane;
+            float g[1];
+            g[0] = NAN;
+            const int j = q < e ? indices[q] : -2;
+            bool sel = false;
+            for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, old_j, t) == j);
+            if (q < e) {
+                float ev = (float)data[q];
+                float2 cf = __ldg((sel ? coef_s : coef_n) + j);
+                g[0] = fmaf(cf.x, ev, cf.y);
+            }
+            if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<float, 1, false>(tk, g, q0 - s, 1, k, -1);
+        }
+        // list holds positions inside the row; translate to labels (ascending pos == ascending label)
+        int src = warp_rank_src(tk.idx, k);
+        int pos = __shfl_sync(XC_FULL, tk.idx, src);
+        int new_j = pos == 0x7fffffff ? 0x7fffffff : indices[s + pos];
+        T new_e = pos == 0x7fffffff ? (T)0 : data[s + pos];
+        bool stays_old = false, stays_new = false;
+        for (int t = 0; t < k; ++t) {
+            int nj = __shfl_sync(XC_FULL, new_j, t);
+            int oj = __shfl_sync(XC_FULL, old_j, t);
+            stays_old |= (nj == old_j);
+            stays_new |= (oj == new_j);
+        }
+        if (lane < k) {
+            if (!stays_old && old_j >= 0) {
+                // eta of the leaving label (0 when the row does not store it)
+                int64_t y = s, z = e;
+                T oe = (T)0;
+                bool found = false;
+                while (y < z) {
+                    int64_t mid = (y + z) >> 1;
+                    int v = indices[mid];
+                    if (v == old_j) { oe = data[mid]; found = true; break; }
+                    if (v < old_j) y = mid + 1; else z = mid;
+                }
+                if (found) {
+                    atomicAdd(dtp + old_j, -(double)oe);
+                    atomicAdd(dfp + old_j, -(double)(T)(one - oe));
+                    atomicAdd(dfn + old_j, (double)oe);
+                } else {
+                    atomicAdd(dfp + old_j, -1.0);
+                }
+            }
+            if (!stays_new && new_j != 0x7fffffff) {
+                atomicAdd(dtp + new_j, (double)new_e);
+                atomicAdd(dfp + new_j, (double)(T)(one - new_e));
+                atomicAdd(dfn + new_j, -(double)new_e);
+            }
+            pred_row[lane] = new_j == 0x7fffffff ? -1 : new_j;
+        }
+    }
+}
+
+// ---- coverage ------------------------------------------------------------------------------------
+// gain = Ef_j * eta (unselected) | Ef_j / (1 - eta) * eta (selected), optionally mixed with
+// precision@k: alpha * gain + (1 - alpha) * eta / k   (block_coordinate.py:562-569)
+__device__ __forceinline__ void atomic_mul(double *addr, double f)
+{
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        old = atomicCAS(a, assumed, __double_as_longlong(__longlong_as_double(assumed) * f));
+    } while (assumed != old);
+}
+
+template <typename T>
+__device__ __forceinline__ double cov_gain(double Ef, T eta, bool sel, double alpha, int k)
+{
+    double ef = sel ? Ef / (double)(T)((T)1 - eta) : Ef;
+    double g = ef * (double)eta;
+    if (alpha < 1.0) g = alpha * g + (1.0 - alpha) * (double)eta / (double)k;
+    return g;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cov_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                     const int64_t *__restrict__ indptr, const int32_t *__restrict__ rows, int64_t n_rows, int k,
+                     double alpha, const double *__restrict__ Ef, int32_t *__restrict__ pred_idx, double *dEf)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const T one = (T)1;
+    for (int64_t w = warp; w < n_rows; w += nwarps) {
+        const int64_t row = rows ? (int64_t)rows[w] : w;
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        int32_t *pred_row = pred_idx + row * k;
+        int old_j = -1;
+        if (lane < k) old_j = pred_row[lane];
+        WarpTopK<double> tk;
+        tk.init();
+        for (int64_t q0 = s; q0 < e; q0 += 32) {
+            int64_t q = q0 + lane;
+            double g[1];
+            g[0] = NAN;
+            const int j = q < e ? indices[q] : -2;
+            bool sel = false;
+            for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, old_j, t) == j);
+            if (q < e) g[0] = cov_gain<T>(Ef[j], data[q], sel, alpha, k);
+            if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<double, 1, false>(tk, g, q0 - s, 1, k, -1);
+        }
+        int src = warp_rank_src(tk.idx, k);
+        int pos = __shfl_sync(XC_FULL, tk.idx, src);
+        int new_j = pos == 0x7fffffff ? 0x7fffffff : indices[s + pos];
+        T new_e = pos == 0x7fffffff ? (T)0 : data[s + pos];
+        bool stays_old = false, stays_new = false;
+        for (int t = 0; t < k; ++t) {
+            int nj = __shfl_sync(XC_FULL, new_j, t);
+            int oj = __shfl_sync(XC_FULL, old_j, t);
+            stays_old |= (nj == old_j);
+            stays_new |= (oj == new_j);
+        }
+        if (lane < k) {
+            if (!stays_old && old_j >= 0) {
+                int64_t y = s, z = e;
+                while (y < z) {
+                    int64_t mid = (y + z) >> 1;
+                    int v = indices[mid];
+                    if (v == old_j) { atomic_mul(dEf + old_j, 1.0 / (double)(T)(one - data[mid])); break; }
+                    if (v < old_j) y = mid + 1; else z = mid;
+                }
+            }
+            if (!stays_new && new_j != 0x7fffffff) atomic_mul(dEf + new_j, (double)(T)(one - new_e));
+            pred_row[lane] = new_j == 0x7fffffff ? -1 : new_j;
+        }
+    }
+}
+
+// dense coverage batch: gains need Ef_j in float64 per element -> a = Ef as float32 coefficient would
+// lose the 1e-4 contract only marginally, but coverage products span many decades; keep float64.
+template <typename T>
+struct XfCov {
+    const double *Ef;
+    double alpha;
+    double inv_k;
+    template <typename TE, int V>
+    __device__ __forceinline__ void apply_vec(int64_t c, const TE (&e)[V], double (&g)[V], double (&ca)[V],
+                                              double (&cb)[V], bool first) const
+    {
+        if (first) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) ca[v] = __ldg(Ef + c + v);
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            double x = ca[v] * (double)e[v];
+            if (alpha < 1.0) x = alpha * x + (1.0 - alpha) * (double)e[v] * inv_k;
+            g[v] = x;
+        }
+    }
+    template <typename TE>
+    __device__ __forceinline__ double apply_one(int64_t c, TE e) const
+    {
+        double x = __ldg(Ef + c) * (double)e;
+        if (alpha < 1.0) x = alpha * x + (1.0 - alpha) * (double)e * inv_k;
+        return x;
+    }
+};
+
+template <typename TE, int R>
+__global__ void __launch_bounds__(kThreads)
+cov_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ rows,
+                       int64_t n_rows, int k, double alpha, const double *__restrict__ Ef,
+                       int32_t *__restrict__ pred_idx, double *dEf, bool vec_ok)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    XfCov<TE> xf{Ef, alpha, 1.0 / (double)k};
+    const TE one = (TE)1;
+    for (int64_t grp = warp; grp * R < n_rows; grp += nwarps) {
+        const TE *rp[R];
+        int64_t row_id[R];
+        int old_j[R];
+        TE old_e[R];
+        WarpTopK<double> tk[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t i = grp * R + r;
+            bool valid = i < n_rows;
+            if (!valid) i = grp * R;
+            int64_t row = rows ? (int64_t)rows[i] : i;
+            row_id[r] = valid ? row : -1;
+            rp[r] = eta + row * ld;
+            old_j[r] = -1;
+            old_e[r] = (TE)0;
+            double g = 0.0;
+            if (lane < k) {
+                old_j[r] = pred_idx[row * k + lane];
+                if (old_j[r] >= 0) {
+                    old_e[r] = rp[r][old_j[r]];
+                    g = cov_gain<TE>(Ef[old_j[r]], old_e[r], true, alpha, k);
+                }
+            }
+            seed_list(tk[r], g, old_j[r], k);
+        }
+        xc_scan_rows<TE, double, R, true>(rp, m, vec_ok, xf, tk, old_j, k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (row_id[r] < 0) continue;
+            int src = warp_rank_src(tk[r].idx, k);
+            int new_j = __shfl_sync(XC_FULL, tk[r].idx, src);
+            bool stays_old = false, stays_new = false;
+            for (int t = 0; t < k; ++t) {
+                int nj = __shfl_sync(XC_FULL, new_j, t);
+                int oj = __shfl_sync(XC_FULL, old_j[r], t);
+                stays_old |= (nj == old_j[r]);
+                stays_new |= (oj == new_j);
+            }
+            if (lane < k) {
+                if (!stays_old && old_j[r] >= 0) atomic_mul(dEf + old_j[r], 1.0 / (double)(TE)(one - old_e[r]));
+                if (!stays_new && new_j != 0x7fffffff) atomic_mul(dEf + new_j, (double)(TE)(one - rp[r][new_j]));
+                pred_idx[row_id[r] * k + lane] = new_j == 0x7fffffff ? -1 : new_j;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) cov_fold_kernel(double *Ef, double *dEf, int64_t m)
+{
+    int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j < m) {
+        Ef[j] *= dEf[j];
+        dEf[j] = 1.0;
+    }
+}
+
+template <typename K>
+int grid_for(xc_ctx *ctx, K kernel, int64_t work_warps)
+{
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    int64_t full = (int64_t)ctx->sm_count * per_sm;
+    int64_t need = (work_warps + (kThreads / 32) - 1) / (kThreads / 32);
+    if (need < 1) need = 1;
+    return (int)(need < full ? need : full);
+}
+
+template <typename TE>
+int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, const int32_t *rows, int64_t n_rows, int k,
+                       const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
+                       double *dfn, cudaStream_t st)
+{
+    constexpr int V = 16 / sizeof(TE);
+    bool vec_ok = xc_aligned16(eta) && (ld % V == 0) && xc_aligned16(coef_n);
+    int64_t warps_full = (int64_t)ctx->sm_count * 16;
+#define XC_GO(R)                                                                                              \
+    {                                                                                                         \
+        auto kern = bca_batch_dense_kernel<TE, R>;                                                            \
+        int grid = grid_for(ctx, kern, (n_rows + R - 1) / R);                                                 \
+        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, m, ld, rows, n_rows, k, (const float2 *)coef_n,      \
+                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok);             \
+    }
+    if (n_rows >= warps_full * 4) XC_GO(4)
+    else if (n_rows >= warps_full * 2) XC_GO(2)
+    else XC_GO(1)
+#undef XC_GO
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+}  // namespace
+
+extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn, double *dtp,
+                           double *dfp, double *dfn, int64_t m, float *coef_n, float *coef_s, void *stream)
+{
+    if (!ctx || !p || !tp || !fp || !fn || !coef_n || !coef_s || m <= 0) return XC_ERR_INVALID;
+    if ((dtp || dfp || dfn) && !(dtp && dfp && dfn)) return XC_ERR_INVALID;
+    if (p->metric != XC_METRIC_PRECISION && p->metric != XC_METRIC_RECALL && p->metric != XC_METRIC_FBETA)
+        return XC_ERR_UNSUPPORTED;  // gain not affine in eta
+    bca_coef_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        *p, tp, fp, fn, dtp, dfp, dfn, m, (float2 *)coef_n, (float2 *)coef_s);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_bca_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld, const int32_t *rows,
+                                  int64_t n_rows, int k, const float *coef_n, const float *coef_s, int32_t *pred_idx,
+                                  double *dtp, double *dfp, double *dfn, void *stream)
+{
+    if (!ctx || !eta || !coef_n || !coef_s || !pred_idx || !dtp || !dfp || !dfn || m <= 0 || ld < m || n_rows < 0)
+        return XC_ERR_INVALID;
+    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32)
+        return launch_batch_dense<float>(ctx, eta, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx, dtp, dfp, dfn, st);
+    if (dtype == XC_F64)
+        return launch_batch_dense<double>(ctx, eta, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx, dtp, dfp, dfn, st);
+    return XC_ERR_UNSUPPORTED;
+}
+
+extern "C" int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                                const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k,
+                                const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
+                                double *dfn, void *stream)
+{
+    if (!ctx || !indptr || !coef_n || !coef_s || !pred_idx || !dtp || !dfp || !dfn || n_rows < 0) return XC_ERR_INVALID;
+    if (k < 1 || k > 32) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32) {
+        auto kern = bca_batch_csr_kernel<float>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const float *)data, indices, indptr, rows, n_rows, k, (const float2 *)coef_n,
+                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn);
+    } else if (dtype == XC_F64) {
+        auto kern = bca_batch_csr_kernel<double>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const double *)data, indices, indptr, rows, n_rows, k,
+                                        (const float2 *)coef_n, (const float2 *)coef_s, pred_idx, dtp, dfp, dfn);
+    } else {
+        return XC_ERR_UNSUPPORTED;
+    }
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_cov_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                                const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k, double alpha,
+                                const double *Ef, int32_t *pred_idx, double *dEf, void *stream)
+{
+    if (!ctx || !indptr || !Ef || !pred_idx || !dEf || n_rows < 0) return XC_ERR_INVALID;
+    if (k < 1 || k > 32) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32) {
+        auto kern = cov_batch_csr_kernel<float>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const float *)data, indices, indptr, rows, n_rows, k, alpha, Ef, pred_idx, dEf);
+    } else if (dtype == XC_F64) {
+        auto kern = cov_batch_csr_kernel<double>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const double *)data, indices, indptr, rows, n_rows, k, alpha, Ef, pred_idx, dEf);
+    } else {
+        return XC_ERR_UNSUPPORTED;
+    }
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_cov_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld, const int32_t *rows,
+                                  int64_t n_rows, int k, double alpha, const double *Ef, int32_t *pred_idx,
+                                  double *dEf, void *stream)
+{
+    if (!ctx || !eta || !Ef || !pred_idx || !dEf || m <= 0 || ld < m || n_rows < 0) return XC_ERR_INVALID;
+    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32) {
+        bool vec_ok = xc_aligned16(eta) && (ld % 4 == 0);
+        auto kern = cov_batch_dense_kernel<float, 1>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const float *)eta, m, ld, rows, n_rows, k, alpha, Ef, pred_idx, dEf, vec_ok);
+    } else if (dtype == XC_F64) {
+        bool vec_ok = xc_aligned16(eta) && (ld % 2 == 0);
+        auto kern = cov_batch_dense_kernel<double, 1>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const double *)eta, m, ld, rows, n_rows, k, alpha, Ef, pred_idx, dEf, vec_ok);
+    } else {
+        return XC_ERR_UNSUPPORTED;
+    }
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void *stream)
+{
+    if (!ctx || !Ef || !dEf || m <= 0) return XC_ERR_INVALID;
+    cov_fold_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(Ef, dEf, m);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}

@@ -1,0 +1,562 @@
+// Sequential-exact BCA sweeps: the reference's instance order and float64 operation order.
+//
+// Dense rows (xcolumns/block_coordinate.py:132-209): one cooperative launch per sweep.  The m
+// labels are spread over the whole grid, each thread keeps the float64 state (tp, fp, fn, tn)
+// of its labels in registers for the whole sweep, and every instance costs ONE grid barrier:
+//   1. remove the row's contribution, evaluate psi(+row) - psi(-row) per label   (registers)
+//   2. block-level top-k  -> k candidates per block in a double-buffered exchange array
+//   3. grid barrier
+//   4. every block merges all candidates (same deterministic result everywhere), re-adds the
+//      row with the new selection to its own labels; block 0 stores the new prediction row.
+// eta of the next instance is prefetched before the barrier.  The chain is latency bound
+// (~2-3 us per instance) by construction: instance i+1 needs instance i's commit.
+//
+// CSR rows (:212-293) and coverage (:539-580): the candidates of a step are only the row's
+// stored labels, so a single warp walks the order; the state lives in L2.
+//
+// This file must be compiled with -fmad=false: every + - * / below is a separate IEEE
+// operation, exactly like numpy/numba evaluate the reference expressions.
+#include <cooperative_groups.h>
+
+#include "xc_scan.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int EX_THREADS = 128;
+constexpr int EX_WARPS = EX_THREADS / 32;
+
+struct alignas(16) Cand {
+    double g;
+    int j;
+    int pad;
+};
+
+// candidates written by other blocks: read through L2 (L1 is not coherent across SMs)
+__device__ __forceinline__ Cand cand_load_cg(const Cand *p)
+{
+    double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
+    Cand c;
+    c.g = v.x;
+    c.j = __double2loint(v.y);
+    c.pad = 0;
+    return c;
+}
+
+__device__ __forceinline__ Cand cand_best(Cand a, Cand b) { return xc_better(b.g, b.j, a.g, a.j) ? b : a; }
+
+__device__ __forceinline__ Cand warp_argmax(Cand c)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Cand t;
+        t.g = __shfl_xor_sync(XC_FULL, c.g, o);
+        t.j = __shfl_xor_sync(XC_FULL, c.j, o);
+        t.pad = 0;
+        c = cand_best(c, t);
+    }
+    return c;
+}
+
+// best candidate of the block, returned to every thread; sm has EX_WARPS entries
+__device__ __forceinline__ Cand block_argmax(Cand c, Cand *sm)
+{
+    c = warp_argmax(c);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+    __syncthreads();
+    Cand r;
+    const int lane = threadIdx.x & 31;
+    if (lane < EX_WARPS) r = sm[lane];
+    else { r.g = -INFINITY; r.j = 0x7fffffff; }
+    r.pad = 0;
+    r = warp_argmax(r);
+    __syncthreads();
+    return r;
+}
+
+template <typename TE, int L>
+__global__ void __launch_bounds__(EX_THREADS)
+bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ order,
+                       int64_t n_order, int k, xc_metric_params p, int greedy, int32_t *pred_idx, double *tp,
+                       double *fp, double *fn, double *tn, Cand *cand)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ Cand sm[EX_WARPS];
+    __shared__ int s_sel[32];
+    const int64_t stride = (int64_t)gridDim.x * EX_THREADS;
+    const int64_t j0 = (int64_t)blockIdx.x * EX_THREADS + threadIdx.x;
+    const int nblk = gridDim.x;
+    const bool use_tn = !p.skip_tn;
+    const double nd = p.n_div;
+    const TE one = (TE)1;
+
+    double stp[L], sfp[L], sfn[L], stn[L];
+    TE pv[L], pnext[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        int64_t j = j0 + l * stride;
+        bool ok = j < m;
+        stp[l] = ok ? tp[j] : 0.0;
+        sfp[l] = ok ? fp[j] : 0.0;
+        sfn[l] = ok ? fn[j] : 0.0;
+        stn[l] = ok ? tn[j] : 0.0;
+        pnext[l] = (TE)0;
+    }
+    if (n_order > 0) {
+        const TE *rp = eta + (int64_t)order[0] * ld;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            int64_t j = j0 + l * stride;
+            if (j < m) pnext[l] = __ldg(rp + j);
+        }
+    }
+
+    for (int64_t s = 0; s < n_order; ++s) {
+        const int64_t row = order[s];
+        int32_t *prow = pred_idx + row * k;
+#pragma unroll
+        for (int l = 0; l < L; ++l) pv[l] = pnext[l];
+        if (s + 1 < n_order) {  // prefetch the next instance's probabilities
+            const TE *rn = eta + (int64_t)order[s + 1] * ld;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                int64_t j = j0 + l * stride;
+                if (j < m) pnext[l] = __ldg(rn + j);
+            }
+        }
+        // ---- 1. remove own contribution, gains -----------------------------------------------
+        double gain[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int64_t j = j0 + l * stride;
+            gain[l] = -INFINITY;
+            if (j < m) {
+                bool sel = false;
+                for (int t = 0; t < k; ++t) sel |= (prow[t] == (int)j);
+                const TE pe = pv[l];
+                const TE om = one - pe;           // (1 - y_proba_i) in TE          :159
+                const TE y = sel ? one : (TE)0;
+                if (!greedy) {                    //                                :157-163
+                    stp[l] = stp[l] - (double)(TE)(y * pe);
+                    sfp[l] = sfp[l] - (double)(TE)(y * om);
+                    sfn[l] = sfn[l] - (double)(TE)((one - y) * pe);
+                    if (use_tn) stn[l] = stn[l] - (double)(TE)((one - y) * om);
+                }
+                const double pos_tp = stp[l] + (double)pe;   //                     :166-172
+                const double pos_fp = sfp[l] + (double)om;
+                const double neg_fn = sfn[l] + (double)pe;
+                const double neg_tn = use_tn ? stn[l] + (double)om : stn[l];
+                const double up = xc_binary_metric(p.metric, pos_tp / nd, pos_fp / nd, sfn[l] / nd, stn[l] / nd,
+                                                   p.c1, p.beta2, p.eps);
+                const double un = xc_binary_metric(p.metric, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn / nd,
+                                                   p.c1, p.beta2, p.eps);
+                const double g = up - un;         //                                :129
+                gain[l] = p.maximize ? g : -g;
+            }
+        }
+        // ---- 2. block-level top-k ---------------------------------------------------------------
+        Cand *slot = cand + ((s & 1) * (int64_t)nblk + blockIdx.x) * k;
+        unsigned taken = 0;
+        for (int t = 0; t < k; ++t) {
+            Cand c;
+            c.g = -INFINITY;
+            c.j = 0x7fffffff;
+            c.pad = 0;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                int64_t j = j0 + l * stride;
+                if (j < m && !((taken >> l) & 1u)) {
+                    Cand d;
+                    d.g = gain[l];
+                    d.j = (int)j;
+                    d.pad = 0;
+                    c = cand_best(c, d);
+                }
+            }
+            Cand w = block_argmax(c, sm);
+#pragma unroll
+            for (int l = 0; l < L; ++l)
+                if ((int64_t)w.j == j0 + l * stride) taken |= 1u << l;
+            if (threadIdx.x == 0) slot[t] = w;
+        }
+        // ---- 3. exchange --------------------------------------------------------------------------
+        __threadfence();
+        grid.sync();
+        // ---- 4. merge all candidates (identical in every block) ----------------------------------
+        const Cand *all = cand + (s & 1) * (int64_t)nblk * k;
+        const int total = nblk * k;
+        // every thread scans a strided slice; "taken" by label id comparison
+        int picked[32];
+        for (int t = 0; t < k; ++t) {
+            Cand c;
+            c.g = -INFINITY;
+            c.j = 0x7fffffff;
+            c.pad = 0;
+            for (int q = threadIdx.x; q < total; q += EX_THREADS) {
+                Cand d = cand_load_cg(all + q);
+                bool used = false;
+                for (int u = 0; u < t; ++u) used |= (picked[u] == d.j);
+                if (!used) c = cand_best(c, d);
+            }
+            Cand w = block_argmax(c, sm);
+            picked[t] = w.j;
+        }
+        if (threadIdx.x < 32) s_sel[threadIdx.x] = threadIdx.x < k ? picked[threadIdx.x] : 0x7fffffff;
+        // ---- 5. re-add with the new selection -------------------------------------------------------
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int64_t j = j0 + l * stride;
+            if (j < m) {
+                bool sel = false;
+                for (int t = 0; t < k; ++t) sel |= (picked[t] == (int)j);
+                const TE pe = pv[l];
+                const TE om = one - pe;
+                const TE y = sel ? one : (TE)0;
+                stp[l] = stp[l] + (double)(TE)(y * pe);      //                     :203-209
+                sfp[l] = sfp[l] + (double)(TE)(y * om);
+                sfn[l] = sfn[l] + (double)(TE)((one - y) * pe);
+                if (use_tn) stn[l] = stn[l] + (double)(TE)((one - y) * om);
+            }
+        }
+        if (blockIdx.x == 0) {
+            __syncthreads();
+            if (threadIdx.x < 32) {  // store ascending by label
+                int mine = s_sel[threadIdx.x];
+                int src = warp_rank_src(mine, k);
+                int v = __shfl_sync(XC_FULL, mine, src);
+                if (threadIdx.x < k) prow[threadIdx.x] = v;
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        int64_t j = j0 + l * stride;
+        if (j < m) {
+            tp[j] = stp[l];
+            fp[j] = sfp[l];
+            fn[j] = sfn[l];
+            if (use_tn) tn[j] = stn[l];
+        }
+    }
+}
+
+// ---- CSR: one warp walks the order ------------------------------------------------------------------
+// products exactly as numba forms them (numba_csr_functions.py:133, :206)
+template <typename T> __device__ __forceinline__ T mul_round(T a, T b) { return (T)(a * b); }
+template <typename T> __device__ __forceinline__ T mul_om_round(T a, T b) { return (T)((double)a * (1.0 - (double)b)); }
+
+__device__ __forceinline__ int64_t csr_find(const int32_t *idx, int64_t s, int64_t e, int j)
+{
+    while (s < e) {
+        int64_t mid = (s + e) >> 1;
+        int v = idx[mid];
+        if (v == j) return mid;
+        if (v < j) s = mid + 1; else e = mid;
+    }
+    return -1;
+}
+
+// +-(row contribution) for one CSR row given its compact prediction (lane x < k holds label pj)
+template <typename T>
+__device__ __forceinline__ void csr_apply_row(const T *data, const int32_t *indices, int64_t ts, int64_t te, int pj,
+                                              int k, double sgn, double *tp, double *fp, double *fn)
+{
+    const int lane = lane_id();
+    const T one = (T)1;
+    if (lane < k && pj >= 0) {  // numba_csr_functions.py:400-407 / 435-442
+        int64_t y = csr_find(indices, ts, te, pj);
+        if (y >= 0) {
+            tp[pj] = tp[pj] + sgn * (double)mul_round(one, data[y]);
+            fp[pj] = fp[pj] + sgn * (double)mul_om_round(one, data[y]);
+        } else {
+            fp[pj] = fp[pj] + sgn * (double)one;
+        }
+    }
+    for (int64_t q0 = ts; q0 < te; q0 += 32) {  // :408-411 / 443-446
+        int64_t q = q0 + lane;
+        int j = q < te ? indices[q] : -2;
+        bool sel = false;
+        for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, pj, t) == j);
+        if (q < te) fn[j] = fn[j] + sgn * (sel ? (double)mul_om_round(data[q], one) : (double)data[q]);
+    }
+    __syncwarp();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32)
+bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                     const int64_t *__restrict__ indptr, const int32_t *__restrict__ order, int64_t n_order, int k,
+                     xc_metric_params p, int greedy, int32_t *pred_idx, double *tp, double *fp, double *fn)
+{
+    const int lane = lane_id();
+    const double nd = p.n_div;
+    const T one = (T)1;
+    for (int64_t s = 0; s < n_order; ++s) {
+        const int64_t row = order[s];
+        const int64_t ts = indptr[row], te = indptr[row + 1], nz = te - ts;
+        int32_t *prow = pred_idx + row * k;
+        int pj = lane < k ? prow[lane] : -1;
+        if (!greedy) csr_apply_row<T>(data, indices, ts, te, pj, k, -1.0, tp, fp, fn);
+        WarpTopK<double> tk;
+        tk.init();
+        for (int64_t q0 = ts; q0 < te; q0 += 32) {  // block_coordinate.py:248-282
+            int64_t q = q0 + lane;
+            double g[1];
+            g[0] = NAN;
+            if (q < te) {
+                const int j = indices[q];
+                const T t = data[q];
+                const T om = one - t;
+                double neg_tp = tp[j], neg_fp = fp[j], pos_fn = fn[j];
+                const double pos_tpp = (neg_tp + (double)t) / nd;
+                const double pos_fpp = (neg_fp + (double)om) / nd;
+                const double neg_fnn = (pos_fn + (double)t) / nd;
+                neg_tp = neg_tp / nd;
+                neg_fp = neg_fp / nd;
+                pos_fn = pos_fn / nd;
+                const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, -1.0, p.c1, p.beta2, p.eps);
+                const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, -1.0, p.c1, p.beta2, p.eps);
+                const double gg = up - un;
+                g[0] = p.maximize ? gg : -gg;
+            }
+            if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<double, 1, false>(tk, g, q0 - ts, 1, k, -1);
+        }
+        // nz > k: the k best (ascending label); else all stored labels (numba_csr_functions.py:456-466)
+        (void)nz;
+        int src = warp_rank_src(tk.idx, k);
+        int pos = __shfl_sync(XC_FULL, tk.idx, src);
+        pj = (lane < k && pos != 0x7fffffff) ? indices[ts + pos] : -1;
+        if (lane < k) prow[lane] = pj;
+        csr_apply_row<T>(data, indices, ts, te, pj, k, 1.0, tp, fp, fn);
+    }
+}
+
+// ---- coverage (block_coordinate.py:539-580) ---------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(32)
+cov_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                     const int64_t *__restrict__ indptr, const int32_t *__restrict__ order, int64_t n_order, int k,
+                     double alpha, int greedy, int32_t *pred_idx, double *Ef)
+{
+    const int lane = lane_id();
+    const T one = (T)1;
+    for (int64_t s = 0; s < n_order; ++s) {
+        const int64_t row = order[s];
+        const int64_t ts = indptr[row], te = indptr[row + 1];
+        int32_t *prow = pred_idx + row * k;
+        int pj = lane < k ? prow[lane] : -1;
+        if (!greedy && lane < k && pj >= 0) {  // :562-564
+            int64_t y = csr_find(indices, ts, te, pj);
+            if (y >= 0) Ef[pj] = Ef[pj] / (double)(T)(one - mul_round(one, data[y]));
+        }
+        __syncwarp();
+        WarpTopK<double> tk;
+        tk.init();
+        for (int64_t q0 = ts; q0 < te; q0 += 32) {  // :567-569
+            int64_t q = q0 + lane;
+            double g[1];
+            g[0] = NAN;
+            if (q < te) {
+                const T t = data[q];
+                double gg = Ef[indices[q]] * (double)t;
+                if (alpha < 1.0) {
+                    T w = (T)((T)(1.0 - alpha) * t);
+                    w = (T)(w / (T)k);
+                    gg = alpha * gg + (double)w;
+                }
+                g[0] = gg;
+            }
+            if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<double, 1, false>(tk, g, q0 - ts, 1, k, -1);
+        }
+        int src = warp_rank_src(tk.idx, k);
+        int pos = __shfl_sync(XC_FULL, tk.idx, src);
+        pj = (lane < k && pos != 0x7fffffff) ? indices[ts + pos] : -1;
+        if (lane < k) prow[lane] = pj;
+        if (lane < k && pj >= 0) {  // :579-580
+            T t = data[ts + pos];
+            Ef[pj] = Ef[pj] * (double)(T)(one - mul_round(one, t));
+        }
+        __syncwarp();
+    }
+}
+
+// Ef = prod_i (1 - yhat_ij eta_ij), rows in order (numba_csr_functions.py:325-382)
+template <typename T>
+__global__ void __launch_bounds__(32)
+cov_state_ordered_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                         const int64_t *__restrict__ indptr, int64_t n, const int32_t *__restrict__ pred_idx, int k,
+                         double *Ef)
+{
+    const int lane = lane_id();
+    const T one = (T)1;
+    for (int64_t i = 0; i < n; ++i) {
+        int pj = lane < k ? pred_idx[i * k + lane] : -1;
+        if (pj >= 0) {
+            int64_t y = csr_find(indices, indptr[i], indptr[i + 1], pj);
+            Ef[pj] = Ef[pj] * (y >= 0 ? (double)mul_om_round(one, data[y]) : (double)one);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void atomic_mul_d(double *addr, double f)
+{
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        old = atomicCAS(a, assumed, __double_as_longlong(__longlong_as_double(assumed) * f));
+    } while (assumed != old);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cov_state_fast_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                      const int64_t *__restrict__ indptr, int64_t n, const int32_t *__restrict__ pred_idx, int k,
+                      double *Ef)
+{
+    const T one = (T)1;
+    const int64_t total = n * k;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        int pj = pred_idx[t];
+        if (pj < 0) continue;
+        int64_t i = t / k;
+        int64_t y = csr_find(indices, indptr[i], indptr[i + 1], pj);
+        if (y >= 0) atomic_mul_d(Ef + pj, (double)mul_om_round(one, data[y]));
+    }
+}
+
+__global__ void fill_kernel(double *x, double v, int64_t m)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m) x[j] = v;
+}
+
+template <typename TE, int L>
+int launch_exact_dense(xc_ctx *ctx, int grid, const void *eta, int64_t m, int64_t ld, const int32_t *order,
+                       int64_t n_order, int k, const xc_metric_params *p, int greedy, int32_t *pred_idx, double *tp,
+                       double *fp, double *fn, double *tn, Cand *cand, cudaStream_t st)
+{
+    const TE *eta_t = (const TE *)eta;
+    xc_metric_params pp = *p;
+    void *args[] = {&eta_t, &m, &ld, &order, &n_order, &k, &pp, &greedy, &pred_idx, &tp, &fp, &fn, &tn, &cand};
+    XC_CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)bca_exact_dense_kernel<TE, L>, dim3(grid), dim3(EX_THREADS),
+                                                 args, 0, st));
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+template <typename TE>
+int dispatch_exact_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, const int32_t *order, int64_t n_order,
+                         int k, const xc_metric_params *p, int greedy, int32_t *pred_idx, double *tp, double *fp,
+                         double *fn, double *tn, cudaStream_t st)
+{
+    // co-resident capacity of the largest-register variant bounds the grid for all variants
+    int per_sm = 0;
+    XC_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bca_exact_dense_kernel<TE, 8>, EX_THREADS, 0));
+    if (per_sm < 1) return XC_ERR_UNSUPPORTED;
+    if (per_sm > 4) per_sm = 4;  // barrier cost grows with the grid; 4 x 148 x 128 x 8 labels = 606k labels
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    int64_t need = (m + EX_THREADS - 1) / EX_THREADS;
+    // prefer one wave of <= sm_count blocks when L stays small
+    int64_t grid = need < (int64_t)ctx->sm_count ? need : (int64_t)ctx->sm_count;
+    int64_t L = (m + grid * EX_THREADS - 1) / (grid * EX_THREADS);
+    if (L > 8) {
+        grid = need < cap ? need : cap;
+        L = (m + grid * EX_THREADS - 1) / (grid * EX_THREADS);
+    }
+    if (L > 8) return XC_ERR_UNSUPPORTED;
+    void *scratch = nullptr;
+    int rc = xc_ctx_scratch(ctx, sizeof(Cand) * 2 * (size_t)grid * (size_t)k, &scratch);
+    if (rc) return rc;
+    Cand *cand = (Cand *)scratch;
+#define XC_GO(LL) return launch_exact_dense<TE, LL>(ctx, (int)grid, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, cand, st)
+    if (L <= 1) XC_GO(1);
+    if (L <= 2) XC_GO(2);
+    if (L <= 4) XC_GO(4);
+    XC_GO(8);
+#undef XC_GO
+}
+
+}  // namespace
+
+extern "C" int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m, int64_t ld,
+                                        const int32_t *order, int64_t n_order, int k, const xc_metric_params *p,
+                                        int greedy, int32_t *pred_idx, double *tp, double *fp, double *fn, double *tn,
+                                        void *stream)
+{
+    if (!ctx || !eta || !order || !p || !pred_idx || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
+    if (n <= 0 || m <= 0 || ld < m || n_order < 0 || k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    if (n_order == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32)
+        return dispatch_exact_dense<float>(ctx, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, st);
+    if (dtype == XC_F64)
+        return dispatch_exact_dense<double>(ctx, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, st);
+    return XC_ERR_UNSUPPORTED;
+}
+
+extern "C" int xc_bca_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                                      const int64_t *indptr, int64_t n, int64_t m, const int32_t *order,
+                                      int64_t n_order, int k, const xc_metric_params *p, int greedy, int32_t *pred_idx,
+                                      double *tp, double *fp, double *fn, void *stream)
+{
+    if (!ctx || !indptr || !order || !p || !pred_idx || !tp || !fp || !fn) return XC_ERR_INVALID;
+    if (n <= 0 || m <= 0 || n_order < 0 || k < 1 || k > 32) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_JACCARD || !p->skip_tn) return XC_ERR_UNSUPPORTED;
+    if (n_order == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32)
+        bca_exact_csr_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn);
+    else if (dtype == XC_F64)
+        bca_exact_csr_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn);
+    else
+        return XC_ERR_UNSUPPORTED;
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_cov_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                                      const int64_t *indptr, int64_t n, int64_t m, const int32_t *order,
+                                      int64_t n_order, int k, double alpha, int greedy, int32_t *pred_idx, double *Ef,
+                                      void *stream)
+{
+    if (!ctx || !indptr || !order || !pred_idx || !Ef) return XC_ERR_INVALID;
+    if (n <= 0 || m <= 0 || n_order < 0 || k < 1 || k > 32) return XC_ERR_INVALID;
+    if (n_order == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32)
+        cov_exact_csr_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, order, n_order, k, alpha, greedy, pred_idx, Ef);
+    else if (dtype == XC_F64)
+        cov_exact_csr_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, order, n_order, k, alpha, greedy, pred_idx, Ef);
+    else
+        return XC_ERR_UNSUPPORTED;
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_cov_state_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                                const int64_t *indptr, int64_t n, int64_t m, const int32_t *pred_idx, int k, int order,
+                                double *Ef, void *stream)
+{
+    if (!ctx || !indptr || !pred_idx || !Ef || n <= 0 || m <= 0 || k < 1 || k > 32) return XC_ERR_INVALID;
+    if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(Ef, 1.0, m);
+    XC_LAUNCHED(ctx);
+    if (order == XC_SUM_ORDERED) {
+        if (dtype == XC_F32) cov_state_ordered_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, n, pred_idx, k, Ef);
+        else cov_state_ordered_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, n, pred_idx, k, Ef);
+    } else {
+        int64_t blocks = (n * k + 255) / 256;
+        int64_t cap = (int64_t)ctx->sm_count * 16;
+        int grid = (int)(blocks < cap ? blocks : cap);
+        if (dtype == XC_F32) cov_state_fast_kernel<float><<<grid, 256, 0, st>>>((const float *)data, indices, indptr, n, pred_idx, k, Ef);
+        else cov_state_fast_kernel<double><<<grid, 256, 0, st>>>((const double *)data, indices, indptr, n, pred_idx, k, Ef);
+    }
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}

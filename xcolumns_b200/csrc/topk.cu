@@ -1,0 +1,234 @@
+// Weighted per-instance top-k (dense + CSR), thresholding, dense scatter.
+// Replaces xcolumns/weighted_prediction.py:25-88 and numba_csr_functions.py:456-484, 586-629.
+#include "xc_scan.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename TE, typename G, int R>
+__global__ void __launch_bounds__(kThreads)
+topk_dense_kernel(const TE *__restrict__ eta, int64_t n_rows, int64_t m, int64_t ld,
+                  const int32_t *__restrict__ rows, XfMulAdd<G> xf, int k, int32_t *__restrict__ out_idx,
+                  G *__restrict__ out_val, bool vec_ok)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t grp = warp; grp * R < n_rows; grp += nwarps) {
+        const TE *rp[R];
+        int64_t oi[R];
+        int dummy[R];
+        WarpTopK<G> tk[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t i = grp * R + r;
+            oi[r] = i < n_rows ? i : -1;
+            if (i >= n_rows) i = grp * R;  // re-scan a valid row, result discarded
+            int64_t row = rows ? (int64_t)rows[i] : i;
+            rp[r] = eta + row * ld;
+            tk[r].init();
+            dummy[r] = -1;
+        }
+        xc_scan_rows<TE, G, R, false>(rp, m, vec_ok, xf, tk, dummy, k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int src = warp_rank_src(tk[r].idx, k);
+            int j = __shfl_sync(XC_FULL, tk[r].idx, src);
+            G v = __shfl_sync(XC_FULL, tk[r].val, src);
+            if (oi[r] >= 0 && lane < k) {
+                out_idx[oi[r] * k + lane] = j;
+                if (out_val) out_val[oi[r] * k + lane] = v;
+            }
+        }
+    }
+}
+
+// one warp per CSR row; stored entries only
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+topk_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                const int64_t *__restrict__ indptr, int64_t n_rows, const T *__restrict__ a,
+                const T *__restrict__ b, int k, int32_t *__restrict__ out_idx, T *__restrict__ out_val)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    XfMulAdd<T> xf{a, b};
+    for (int64_t i = warp; i < n_rows; i += nwarps) {
+        const int64_t s = indptr[i], e = indptr[i + 1];
+        WarpTopK<T> tk;
+        tk.init();
+        // list entries carry the POSITION inside the row (ascending position == ascending label)
+        for (int64_t q0 = s; q0 < e; q0 += 32) {
+            int64_t q = q0 + lane;
+            T g[1];
+            g[0] = (T)NAN;
+            if (q < e) g[0] = xf.template apply_one<T>(indices[q], data[q]);
+            if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<T, 1, false>(tk, g, q0 - s, 1, k, -1);
+        }
+        int src = warp_rank_src(tk.idx, k);
+        int pos = __shfl_sync(XC_FULL, tk.idx, src);
+        T v = __shfl_sync(XC_FULL, tk.val, src);
+        if (lane < k) {
+            bool ok = pos != 0x7fffffff;
+            out_idx[i * k + lane] = ok ? indices[s + pos] : -1;
+            if (out_val) out_val[i * k + lane] = ok ? v : (T)1;
+        }
+    }
+}
+
+template <typename TE, typename G>
+__global__ void __launch_bounds__(kThreads)
+threshold_dense_kernel(const TE *__restrict__ eta, int64_t n_rows, int64_t m, int64_t ld, XfMulAdd<G> xf, G th,
+                       TE *__restrict__ out, int64_t ld_out)
+{
+    const int64_t total = n_rows * m;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        int64_t i = t / m, j = t - i * m;
+        G g = xf.template apply_one<TE>(j, eta[i * ld + j]);
+        out[i * ld_out + j] = (g >= th) ? (TE)1 : (TE)0;
+    }
+}
+
+template <typename TO, typename TV>
+__global__ void __launch_bounds__(kThreads)
+scatter_pred_kernel(const int32_t *__restrict__ pred_idx, const TV *__restrict__ val, int k, int64_t n_rows,
+                    TO *__restrict__ out, int64_t ld_out)
+{
+    const int64_t total = n_rows * k;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        int j = pred_idx[t];
+        if (j >= 0) out[(t / k) * ld_out + j] = val ? (TO)val[t] : (TO)1;
+    }
+}
+
+template <typename K>
+int grid_for(xc_ctx *ctx, K kernel, int64_t work_warps)
+{
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    int64_t full = (int64_t)ctx->sm_count * per_sm;
+    int64_t need = (work_warps + (kThreads / 32) - 1) / (kThreads / 32);
+    if (need < 1) need = 1;
+    return (int)(need < full ? need : full);
+}
+
+template <typename TE, typename G>
+int launch_topk_dense(xc_ctx *ctx, const void *eta, int64_t n_rows, int64_t m, int64_t ld, const int32_t *rows,
+                      const void *a, const void *b, int k, int32_t *out_idx, void *out_val, cudaStream_t st)
+{
+    constexpr int V = 16 / sizeof(TE);
+    bool vec_ok = xc_aligned16(eta) && (ld % V == 0);
+    XfMulAdd<G> xf{(const G *)a, (const G *)b};
+    // R rows per warp amortise the coefficient loads; small problems use R = 1 to fill the GPU
+    int64_t warps_full = (int64_t)ctx->sm_count * 16;
+    if (n_rows >= warps_full * 4) {
+        auto kern = topk_dense_kernel<TE, G, 4>;
+        int grid = grid_for(ctx, kern, (n_rows + 3) / 4);
+        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows, xf, k, out_idx, (G *)out_val, vec_ok);
+    } else if (n_rows >= warps_full * 2) {
+        auto kern = topk_dense_kernel<TE, G, 2>;
+        int grid = grid_for(ctx, kern, (n_rows + 1) / 2);
+        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows, xf, k, out_idx, (G *)out_val, vec_ok);
+    } else {
+        auto kern = topk_dense_kernel<TE, G, 1>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows, xf, k, out_idx, (G *)out_val, vec_ok);
+    }
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+}  // namespace
+
+extern "C" int xc_topk_dense(xc_ctx *ctx, const void *eta, int eta_dtype, int64_t n_rows, int64_t m, int64_t ld,
+                             const int32_t *rows, const void *a, const void *b, int g_dtype, int k,
+                             int32_t *out_idx, void *out_val, void *stream)
+{
+    if (!ctx || !eta || !out_idx || n_rows < 0 || m <= 0 || ld < m) return XC_ERR_INVALID;
+    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (eta_dtype == XC_F32 && g_dtype == XC_F32)
+        return launch_topk_dense<float, float>(ctx, eta, n_rows, m, ld, rows, a, b, k, out_idx, out_val, st);
+    if (eta_dtype == XC_F32 && g_dtype == XC_F64)
+        return launch_topk_dense<float, double>(ctx, eta, n_rows, m, ld, rows, a, b, k, out_idx, out_val, st);
+    if (eta_dtype == XC_F64 && g_dtype == XC_F64)
+        return launch_topk_dense<double, double>(ctx, eta, n_rows, m, ld, rows, a, b, k, out_idx, out_val, st);
+    return XC_ERR_UNSUPPORTED;
+}
+
+extern "C" int xc_topk_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices, const int64_t *indptr,
+                           int64_t n_rows, const void *a, const void *b, int k, int32_t *out_idx, void *out_val,
+                           void *stream)
+{
+    if (!ctx || !indptr || !out_idx || n_rows < 0) return XC_ERR_INVALID;
+    if (k < 1 || k > 32) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32) {
+        auto kern = topk_csr_kernel<float>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const float *)data, indices, indptr, n_rows, (const float *)a,
+                                        (const float *)b, k, out_idx, (float *)out_val);
+    } else if (dtype == XC_F64) {
+        auto kern = topk_csr_kernel<double>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const double *)data, indices, indptr, n_rows, (const double *)a,
+                                        (const double *)b, k, out_idx, (double *)out_val);
+    } else {
+        return XC_ERR_UNSUPPORTED;
+    }
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_threshold_dense(xc_ctx *ctx, const void *eta, int eta_dtype, int64_t n_rows, int64_t m,
+                                  int64_t ld, const void *a, const void *b, int g_dtype, double th, void *out,
+                                  int64_t ld_out, void *stream)
+{
+    if (!ctx || !eta || !out || n_rows < 0 || m <= 0 || ld < m || ld_out < m) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks64 = (n_rows * m + kThreads - 1) / kThreads;
+    int grid = (int)(blocks64 < (int64_t)ctx->sm_count * 16 ? blocks64 : (int64_t)ctx->sm_count * 16);
+    if (eta_dtype == XC_F32 && g_dtype == XC_F32) {
+        XfMulAdd<float> xf{(const float *)a, (const float *)b};
+        threshold_dense_kernel<float, float><<<grid, kThreads, 0, st>>>((const float *)eta, n_rows, m, ld, xf,
+                                                                         (float)th, (float *)out, ld_out);
+    } else if (eta_dtype == XC_F32 && g_dtype == XC_F64) {
+        XfMulAdd<double> xf{(const double *)a, (const double *)b};
+        threshold_dense_kernel<float, double><<<grid, kThreads, 0, st>>>((const float *)eta, n_rows, m, ld, xf, th,
+                                                                          (float *)out, ld_out);
+    } else if (eta_dtype == XC_F64 && g_dtype == XC_F64) {
+        XfMulAdd<double> xf{(const double *)a, (const double *)b};
+        threshold_dense_kernel<double, double><<<grid, kThreads, 0, st>>>((const double *)eta, n_rows, m, ld, xf,
+                                                                           th, (double *)out, ld_out);
+    } else {
+        return XC_ERR_UNSUPPORTED;
+    }
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_scatter_pred_dense(xc_ctx *ctx, const int32_t *pred_idx, const void *val, int val_dtype, int k,
+                                     int64_t n_rows, void *out, int out_dtype, int64_t ld_out, void *stream)
+{
+    if (!ctx || !pred_idx || !out || k < 1 || n_rows < 0) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks64 = (n_rows * k + kThreads - 1) / kThreads;
+    int grid = (int)(blocks64 < (int64_t)ctx->sm_count * 16 ? blocks64 : (int64_t)ctx->sm_count * 16);
+#define XC_SC(TO, TV) \
+    scatter_pred_kernel<TO, TV><<<grid, kThreads, 0, st>>>(pred_idx, (const TV *)val, k, n_rows, (TO *)out, ld_out)
+    if (out_dtype == XC_F32 && (val == nullptr || val_dtype == XC_F32)) XC_SC(float, float);
+    else if (out_dtype == XC_F32 && val_dtype == XC_F64) XC_SC(float, double);
+    else if (out_dtype == XC_F64 && (val == nullptr || val_dtype == XC_F64)) XC_SC(double, double);
+    else if (out_dtype == XC_F64 && val_dtype == XC_F32) XC_SC(double, float);
+    else return XC_ERR_UNSUPPORTED;
+#undef XC_SC
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}

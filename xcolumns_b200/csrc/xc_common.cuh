@@ -1,0 +1,170 @@
+// Shared device/host helpers for the xcolumns_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/xcolumns_b200.h"
+
+struct xc_ctx {
+    int device;
+    int sm_count;
+    int64_t launches;
+    cudaError_t last_err;
+    // scratch for the cooperative sequential-exact sweep (candidate exchange + barrier)
+    void *scratch;
+    size_t scratch_bytes;
+    int coop_blocks_cache[8];
+};
+
+#define XC_FULL 0xffffffffu
+
+#define XC_CUDA_TRY(ctx, expr)                    \
+    do {                                          \
+        cudaError_t e__ = (expr);                 \
+        if (e__ != cudaSuccess) {                 \
+            (ctx)->last_err = e__;                \
+            return XC_ERR_CUDA;                   \
+        }                                         \
+    } while (0)
+
+// call after every kernel launch: counts it and catches launch-configuration errors
+#define XC_LAUNCHED(ctx)                          \
+    do {                                          \
+        (ctx)->launches++;                        \
+        cudaError_t e__ = cudaGetLastError();     \
+        if (e__ != cudaSuccess) {                 \
+            (ctx)->last_err = e__;                \
+            return XC_ERR_CUDA;                   \
+        }                                         \
+    } while (0)
+
+int xc_ctx_scratch(xc_ctx *ctx, size_t bytes, void **out);
+
+static inline bool xc_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// streaming loads: read-only path, do not allocate in L1 (each byte of eta is used once)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream_f4(const float *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ld_stream_d2(const double *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream(const float *p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// (gain, label) ordering used everywhere: larger gain first, ties -> lower label id
+template <typename G>
+__device__ __forceinline__ bool xc_better(G g1, int j1, G g2, int j2)
+{
+    return (g1 > g2) || (g1 == g2 && j1 < j2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-distributed top-k list (k <= 32): lane l holds the l-th best (gain, label).
+// Empty slots hold (-inf, INT_MAX).  thr / thr_j mirror slot k-1 in every lane.
+// ---------------------------------------------------------------------------------------------
+template <typename G>
+struct WarpTopK {
+    G val;
+    int idx;
+    G thr;
+    int thr_j;
+
+    __device__ __forceinline__ void init()
+    {
+        val = -INFINITY;
+        idx = 0x7fffffff;
+        thr = -INFINITY;
+        thr_j = 0x7fffffff;
+    }
+    // warp-uniform (g, j); all 32 lanes must call
+    __device__ __forceinline__ void insert(G g, int j, int k)
+    {
+        const int lane = lane_id();
+        bool ahead = (lane < k) && xc_better(val, idx, g, j);
+        int pos = __popc(__ballot_sync(XC_FULL, ahead));
+        if (pos < k) {  // warp-uniform
+            G pv = __shfl_up_sync(XC_FULL, val, 1);
+            int pi = __shfl_up_sync(XC_FULL, idx, 1);
+            if (lane == pos) {
+                val = g;
+                idx = j;
+            } else if (lane > pos && lane < k) {
+                val = pv;
+                idx = pi;
+            }
+            thr = __shfl_sync(XC_FULL, val, k - 1);
+            thr_j = __shfl_sync(XC_FULL, idx, k - 1);
+        }
+    }
+    // does (g, j) have a chance to enter?  (cheap per-lane filter)
+    __device__ __forceinline__ bool passes(G g) const { return g >= thr; }
+};
+
+// sort the first k lanes' labels ascending; returns in lane r (< k) the label with rank r.
+// Invalid labels (INT_MAX) sort last.
+__device__ __forceinline__ int warp_sort_labels(int idx, int k)
+{
+    const int lane = lane_id();
+    int rank = 0;
+    for (int t = 0; t < k; ++t) {
+        int o = __shfl_sync(XC_FULL, idx, t);
+        rank += (o < idx) || (o == idx && t < lane);
+    }
+    int out = 0x7fffffff;
+    for (int t = 0; t < k; ++t) {
+        unsigned bal = __ballot_sync(XC_FULL, lane < k && rank == t);
+        int src = __ffs(bal) - 1;
+        int v = __shfl_sync(XC_FULL, idx, src < 0 ? 0 : src);
+        if (lane == t) out = v;
+    }
+    return out;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(XC_FULL, v, o);
+    return v;
+}
+
+// binary metrics in float64, operation order of xcolumns/metrics.py (see include/xcolumns_b200.h)
+__device__ __forceinline__ double xc_binary_metric(int metric, double tp, double fp, double fn, double tn,
+                                                   double c1, double beta2, double eps)
+{
+    switch (metric) {
+    case XC_METRIC_PRECISION: return tp / ((tp + fp) + eps);
+    case XC_METRIC_RECALL: return tp / ((tp + fn) + eps);
+    case XC_METRIC_FBETA: return (c1 * tp) / ((((beta2 * (tp + fp)) + tp) + fn) + eps);
+    case XC_METRIC_JACCARD: return tp / (((tp + fp) + fn) + eps);
+    default: {
+        double tpr = tp / ((tp + fn) + eps);
+        double tnr = tn / ((tn + fp) + eps);
+        if (metric == XC_METRIC_BALANCED_ACC) return (tpr + tnr) / 2.0;
+        if (metric == XC_METRIC_GMEAN) return sqrt(tpr * tnr);
+        return ((2.0 * tpr) * tnr) / (tpr + tnr);
+    }
+    }
+}

@@ -1,0 +1,289 @@
+"""Frank-Wolfe search for a randomized weighted classifier on the GPU
+(drop-in for xcolumns/frank_wolfe.py:294-360, :407-690 and the macro wrappers :698-830).
+
+Per iteration the reference does: autograd gradient of the metric -> linear classifier (a, b) ->
+weighted top-k over all rows -> confusion matrix vs y_true -> 10^4-point line search.  Here the
+n x m work is ONE fused streaming kernel (top-k + tp/count accumulation), the gradient is a
+closed form, and the whole alpha grid is evaluated by one kernel; only four scalars per
+iteration travel to the host (for the stopping rules and ``meta``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from time import time
+from typing import Any, Callable, Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix
+
+from . import _device as dev
+from . import metrics as M
+from ._lib import MetricParams
+from .distributed import make_comm
+from .types import DefaultDataDType, DenseMatrix, DType, Matrix
+from .utils import add_kwargs_to_signature, log_info, log_warning
+from .weighted_prediction import _check_k, predict_weighted_per_instance
+
+
+class RandomizedWeightedClassifier:
+    """A set of weighted classifiers (rows of ``a`` and ``b``), one of which is drawn per instance
+    with probabilities ``p`` (xcolumns/frank_wolfe.py:294-360)."""
+
+    def __init__(self, k: int, a: DenseMatrix, b: DenseMatrix, p: DenseMatrix):
+        if not isinstance(k, int):
+            raise ValueError("k must be an integer")
+        if not all(isinstance(v, (np.ndarray, torch.Tensor)) for v in (a, b, p)):
+            raise ValueError("a, b, and p must be ndarray")
+        if a.shape != b.shape or a.shape[0] != p.shape[0]:
+            raise ValueError("a, b must have the same shape and the number of rows must be equal to the number of rows of p")
+        self.k, self.a, self.b, self.p = k, a, b, p
+
+    def predict(self, y_proba: Matrix, dtype: Optional[DType] = None, seed: Optional[int] = None) -> Matrix:
+        if y_proba.shape[1] != self.a.shape[1]:
+            raise ValueError(f"This classifier support the input matrix with {self.a.shape[1]} columns (labels), got {y_proba.shape[1]}")
+        return predict_using_randomized_weighted_classifier(y_proba, self.k, self.a, self.b, self.p, dtype=dtype, seed=seed)
+
+
+def predict_using_randomized_weighted_classifier(y_proba: Matrix, k: int, classifiers_a, classifiers_b,
+                                                 classifiers_proba, dtype=None, seed=None) -> Matrix:
+    """Prediction of a randomized weighted classifier (xcolumns/frank_wolfe.py:175-291): every row
+    draws one classifier c_i ~ p with numpy's Generator (same stream as the reference), rows are
+    grouped by classifier and each group runs through the weighted top-k kernel."""
+    if not isinstance(y_proba, (np.ndarray, torch.Tensor, csr_matrix)):
+        raise ValueError("y_proba must be either np.ndarray, torch.Tensor, or csr_matrix")
+    _check_k(k)
+    if k <= 0:
+        raise NotImplementedError("xcolumns_b200: randomized classifier prediction needs k > 0")
+    to_np = lambda v: v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    A, B, P = to_np(classifiers_a), to_np(classifiers_b), to_np(classifiers_proba)
+    n, m = y_proba.shape
+    if A.shape[1] != m or B.shape[1] != m:
+        raise ValueError("classifiers_a, classifier_b, and classifiers_proba must have the same number of columns as y_proba")
+    if A.shape[0] != B.shape[0] or A.shape[0] != P.shape[0]:
+        raise ValueError("classifiers_a, classifier_b, and classifiers_proba must have the same number of rows")
+    rng = np.random.default_rng(seed)
+    rng_range = np.arange(P.shape[0])
+    choice = np.array([rng.choice(rng_range, p=P) for _ in range(n)], dtype=np.int64)
+    device = dev.pick_device(y_proba)
+    pred = torch.full((n, k), -1, dtype=torch.int32, device=device)
+    if isinstance(y_proba, csr_matrix):
+        from .weighted_prediction import topk_csr_device
+        for c in np.unique(choice):
+            rows = np.nonzero(choice == c)[0]
+            sub = dev.csr_to_device(y_proba[rows], device)
+            a = dev.vec_to_device(A[c], device, sub.data.dtype, m, "a")
+            b = dev.vec_to_device(B[c], device, sub.data.dtype, m, "b")
+            pred[torch.from_numpy(rows).to(device)] = topk_csr_device(sub, k, a, b)[0]
+        return dev.compact_to_csr_like(y_proba, pred, out_dtype=dtype)
+    from .weighted_prediction import topk_dense_device
+    d = dev.dense_to_device(y_proba, device)
+    gdt = torch.promote_types(d.torch_dtype, torch.from_numpy(A[:0]).dtype)
+    g_code = 0 if gdt == torch.float32 else 1
+    for c in np.unique(choice):
+        rows = torch.from_numpy(np.nonzero(choice == c)[0].astype(np.int32)).to(device)
+        a = dev.vec_to_device(A[c], device, gdt, m, "a")
+        b = dev.vec_to_device(B[c], device, gdt, m, "b")
+        pred[rows.long()] = topk_dense_device(d, k, a, b, g_code, rows=rows)[0]
+    return dev.compact_to_dense_like(y_proba, pred, m, out_dtype=dtype)
+
+
+def find_classifier_using_fw(
+    y_true: Matrix,
+    y_proba: Matrix,
+    metric_func: Callable,
+    k: int,
+    max_iters: int = 100,
+    init_classifier: Union[str, Tuple[DenseMatrix, DenseMatrix]] = "top",
+    maximize: bool = True,
+    normalize_conf_matrix: bool = True,
+    metric_kwargs: Optional[Dict[str, Any]] = None,
+    tolerance: float = 1e-6,
+    search_for_best_alpha: bool = True,
+    alpha_search_algo: str = "uniform",
+    alpha_tolerance: float = 0.001,
+    alpha_uniform_search_step: float = 0.0001,
+    skip_tn: bool = False,
+    seed: Optional[int] = None,
+    verbose: bool = False,
+    return_meta: bool = False,
+    **kwargs,
+) -> Union[RandomizedWeightedClassifier, Tuple[RandomizedWeightedClassifier, Dict[str, Any]]]:
+    """Frank-Wolfe over the confusion-matrix polytope for a macro-averaged built-in metric; same
+    arguments / defaults / return value / ``meta`` keys as xcolumns/frank_wolfe.py:407-690.
+    ``distributed=True``: y_true / y_proba are this rank's row shard; the per-iterate confusion sums
+    are all-reduced and every rank ends with the same classifier."""
+    distributed = kwargs.pop("distributed", False)
+    log_info("Starting searching for optimal randomized classifier using Frank-Wolfe algorithm ...", verbose)
+    if type(y_true) != type(y_proba) and isinstance(y_true, (np.ndarray, torch.Tensor, csr_matrix)):
+        raise ValueError(
+            f"y_true and y_proba have unsupported combination of types {type(y_true)} and {type(y_proba)}, should be both np.ndarray, both torch.Tensor, or both csr_matrix")
+    if tuple(y_true.shape) != tuple(y_proba.shape):
+        raise ValueError(f"y_true and y_proba must have the same shape, got {y_true.shape} and {y_proba.shape}")
+    _check_k(k)
+    if k <= 0:
+        raise NotImplementedError("xcolumns_b200: Frank-Wolfe without a budget (k=0) is not implemented on the GPU path yet")
+    if alpha_search_algo not in ("uniform",) and search_for_best_alpha:
+        if alpha_search_algo == "ternary":
+            raise NotImplementedError("xcolumns_b200: alpha_search_algo='ternary' is not implemented; use 'uniform'")
+        raise ValueError(f"Unknown search algorithm {alpha_search_algo}")
+    metric_id, beta, eps = M.resolve_macro_metric(metric_func, metric_kwargs)
+    n, m = y_proba.shape
+    device = dev.pick_device(y_proba, y_true)
+    comm = make_comm(distributed, device)
+    ctx = dev.ctx_for(device)
+    sp = lambda: dev.stream_ptr(device)
+    n_global = comm.n_global(n)
+
+    # ---- classifiers (frank_wolfe.py:500-540), kept on the host as float32 like the reference
+    rng = np.random.default_rng(seed)
+    A = np.zeros((max_iters + 1, m), dtype=DefaultDataDType)
+    B = np.zeros((max_iters + 1, m), dtype=DefaultDataDType)
+    P = np.ones(max_iters + 1, dtype=DefaultDataDType)
+    if isinstance(init_classifier, str) and init_classifier == "top":
+        A[0] = 1.0
+        B[0] = -0.5
+    elif isinstance(init_classifier, str) and init_classifier == "random":
+        A[0] = rng.random(m)
+        B[0] = rng.random(m) - 0.5
+    elif isinstance(init_classifier, str) and init_classifier == "prior":
+        freq = np.asarray(y_true.sum(axis=0), dtype=DefaultDataDType).flatten() if not isinstance(
+            y_true, torch.Tensor) else y_true.sum(0).float().cpu().numpy()
+        A[0] = 1.0 / ((freq + 0.1) / y_true.shape[0])
+        B[0] = 0
+    elif (isinstance(init_classifier, (tuple, list)) and len(init_classifier) == 2
+          and all(isinstance(v, (np.ndarray, torch.Tensor)) and tuple(v.shape) == (m,) for v in init_classifier)):
+        A[0], B[0] = (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v for v in init_classifier)
+    else:
+        raise ValueError(
+            "Unsupported type of init_classifier, it should be in ['random', 'top'], or a tuple of two np.ndarray or torch.Tensor of shape (y_true.shape[1], )")
+
+    # ---- inputs on the device
+    is_csr = isinstance(y_proba, csr_matrix)
+    if is_csr:
+        pd_ = dev.csr_to_device(y_proba, device)
+        td_ = dev.csr_to_device(y_true, device, pd_.data.cpu().numpy().dtype if False else np.dtype(
+            np.float32 if pd_.code == 0 else np.float64))
+        wdt = pd_.data.dtype
+    else:
+        pd_ = dev.dense_to_device(y_proba, device)
+        same = y_true is y_proba
+        td_ = pd_ if same else dev.dense_to_device(
+            y_true if not isinstance(y_true, torch.Tensor) else y_true, device, pd_.torch_dtype)
+        wdt = pd_.torch_dtype
+    f64 = dict(dtype=torch.float64, device=device)
+    colsum = torch.empty(m, **f64)
+    if is_csr:
+        ctx.call("xc_colsum_csr", dev.ptr(td_.data), td_.code, dev.ptr(td_.indices), int(td_.data.numel()), m,
+                 dev.ptr(colsum), sp())
+    else:
+        ctx.call("xc_colsum_dense", dev.ptr(td_.t), td_.code, n, m, td_.ld, dev.ptr(colsum), sp())
+    comm.allreduce_sum_(colsum)
+
+    params = MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)), reserved=0,
+                          c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=1.0)
+    Cm = torch.empty(4 * m, **f64)       # running confusion vectors [tp, fp, fn, tn]
+    Ci = torch.empty(4 * m, **f64)       # confusion vectors of the newest classifier
+    raw = torch.empty((2, m), **f64)     # tp_raw, cnt of one iterate
+    a_dev = torch.empty(m, dtype=torch.float32, device=device)
+    b_dev = torch.empty(m, dtype=torch.float32, device=device)
+    scal = torch.zeros(8, **f64)         # [old_u, u_i, alpha, best_val, new_u]
+    alphas = np.arange(0 + alpha_uniform_search_step, 1, alpha_uniform_search_step)  # utils.py:179
+    alphas_dev = torch.from_numpy(alphas).to(device)
+    vals_dev = torch.empty(alphas.size + 1, **f64)
+    sptr = lambda i: C.c_void_p(scal[i:].data_ptr())
+
+    def iterate(out: torch.Tensor):
+        """confusion vectors of the classifier held in (a_dev, b_dev) -> out (4m)"""
+        aw, bw = a_dev.to(wdt), b_dev.to(wdt)
+        if is_csr:
+            ctx.call("xc_fw_iterate_csr", dev.ptr(pd_.data), pd_.code, dev.ptr(pd_.indices), dev.ptr(pd_.indptr), n, m,
+                     dev.ptr(td_.data), dev.ptr(td_.indices), dev.ptr(td_.indptr), dev.ptr(aw), dev.ptr(bw), k,
+                     C.c_void_p(raw[0].data_ptr()), C.c_void_p(raw[1].data_ptr()), None, sp())
+        else:
+            ctx.call("xc_fw_iterate_dense", dev.ptr(pd_.t), pd_.code, n, m, pd_.ld, dev.ptr(td_.t), td_.ld,
+                     dev.ptr(aw), dev.ptr(bw), k, C.c_void_p(raw[0].data_ptr()), C.c_void_p(raw[1].data_ptr()), None,
+                     sp())
+        comm.allreduce_sum_(raw)
+        ctx.call("xc_fw_make_conf", C.c_void_p(raw[0].data_ptr()), C.c_void_p(raw[1].data_ptr()), dev.ptr(colsum), m,
+                 C.c_double(float(n_global)), int(bool(normalize_conf_matrix)), int(bool(skip_tn)), dev.ptr(out), sp())
+
+    a_dev.copy_(torch.from_numpy(A[0]))
+    b_dev.copy_(torch.from_numpy(B[0]))
+    iterate(Cm)
+    ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, None, None, sptr(0), sp())
+    utility_i = float(scal[0].item())
+    meta: Dict[str, Any] = {"alphas": [], "classifiers_utilities": [utility_i], "utilities": [utility_i], "time": time()}
+    log_info(f"    Metric value of the first (sub)classifier 0: {utility_i}", verbose)
+
+    new_utility = utility_i
+    i = 0
+    for i in range(1, max_iters + 1):
+        log_info(f"  Starting iteration {i}/{max_iters} ...", verbose)
+        # value + gradient -> next classifier (frank_wolfe.py:591-599), float32 rows
+        ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, dev.ptr(a_dev), dev.ptr(b_dev), sptr(0), sp())
+        iterate(Ci)
+        ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Ci), m, None, None, sptr(1), sp())
+        if search_for_best_alpha:
+            ctx.call("xc_fw_alpha_search", C.byref(params), dev.ptr(Cm), dev.ptr(Ci), m, dev.ptr(alphas_dev),
+                     int(alphas.size), dev.ptr(vals_dev), sptr(2), sp())
+        else:
+            scal[2] = 2 / (i + 1)
+        ctx.call("xc_fw_combine", dev.ptr(Cm), dev.ptr(Ci), 4 * m, sptr(2), sp())
+        ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, None, None, sptr(4), sp())
+        host = scal.cpu().numpy()                       # the only sync of the iteration
+        old_utility, utility_i, alpha, new_utility = float(host[0]), float(host[1]), float(host[2]), float(host[4])
+        A[i] = a_dev.cpu().numpy()
+        B[i] = b_dev.cpu().numpy()
+        log_info(f"    Iteration {i}/{max_iters} finished, alpha: {alpha}, metric: {old_utility} -> {new_utility}", verbose)
+        if alpha < alpha_tolerance or (maximize and new_utility - old_utility < tolerance) or (
+                not maximize and old_utility - new_utility < tolerance):
+            A, B, P = A[:i], B[:i], P[:i]               # :659-661
+            break
+        meta["alphas"].append(alpha)
+        meta["classifiers_utilities"].append(utility_i)
+        meta["utilities"].append(new_utility)
+        P[:i] *= 1 - alpha
+        P[i] = alpha
+    log_info(f"  Final utility of the randomized classifier: {new_utility}, number of sub-classifiers: {len(A)}", verbose)
+
+    if isinstance(y_true, torch.Tensor):
+        A, B, P = (torch.tensor(v, dtype=y_proba.dtype, device=y_proba.device) for v in (A, B, P))
+    clf = RandomizedWeightedClassifier(k, A, B, P)
+    if return_meta:
+        meta["time"] = time() - meta["time"]
+        meta["iters"] = i
+        meta["launches"] = ctx.launches()
+        return clf, meta
+    return clf
+
+
+def make_frank_wolfe_wrapper(metric_func: Callable, metric_name: str, maximize: bool = True, skip_tn: bool = False,
+                             warn_k_eq_0: bool = False):
+    """Factory of ``find_classifier_optimizing_<metric>_using_fw(y_true, y_proba, k, **kwargs)``
+    (xcolumns/frank_wolfe.py:698-748)."""
+
+    def find_classifier_for_metric_using_fw(y_true: Matrix, y_proba: Matrix, k: int, **kwargs):
+        if warn_k_eq_0 and k == 0:
+            log_warning(f"Warning: k=0 results in degenerated solution for {metric_name}!")
+        return find_classifier_using_fw(y_true, y_proba, metric_func, k, maximize=maximize, skip_tn=skip_tn, **kwargs)
+
+    find_classifier_for_metric_using_fw.__doc__ = (
+        f"Find a randomized classifier that {'maximizes' if maximize else 'minimizes'} {metric_name} with the "
+        f"Frank-Wolfe algorithm; see find_classifier_using_fw.")
+    return add_kwargs_to_signature(find_classifier_for_metric_using_fw, find_classifier_using_fw,
+                                   skip=["metric_func", "maximize", "skip_tn"])
+
+
+find_classifier_optimizing_macro_precision_using_fw = make_frank_wolfe_wrapper(
+    M.macro_precision_on_conf_matrix, "macro-averaged precision", skip_tn=True, warn_k_eq_0=True)
+find_classifier_optimizing_macro_recall_using_fw = make_frank_wolfe_wrapper(
+    M.macro_recall_on_conf_matrix, "macro-averaged recall", skip_tn=True, warn_k_eq_0=True)
+find_classifier_optimizing_macro_f1_score_using_fw = make_frank_wolfe_wrapper(
+    M.macro_f1_score_on_conf_matrix, "macro-averaged F1 score", skip_tn=True)
+find_classifier_optimizing_macro_jaccard_score_using_fw = make_frank_wolfe_wrapper(
+    M.macro_jaccard_score_on_conf_matrix, "macro-averaged Jaccard score", skip_tn=True)
+find_classifier_optimizing_macro_balanced_accuracy_using_fw = make_frank_wolfe_wrapper(
+    M.macro_balanced_accuracy_on_conf_matrix, "macro-averaged balanced accuracy")
+find_classifier_optimizing_macro_hmean_using_fw = make_frank_wolfe_wrapper(M.macro_hmean_on_conf_matrix, "macro-averaged H-mean")
+find_classifier_optimizing_macro_gmean_using_fw = make_frank_wolfe_wrapper(M.macro_gmean_on_conf_matrix, "macro-averaged G-mean")

@@ -1,0 +1,141 @@
+"""Binary / macro metrics on confusion vectors -- the formulas the hot path evaluates
+(xcolumns/metrics.py:585-944) -- plus the resolver that maps a metric callable onto the fused
+kernels' metric id.
+
+The functions work on numpy arrays, torch tensors and scalars and keep the reference's operation
+order, so they are usable exactly like the reference's (``binary_f1_score_on_conf_matrix(tp, fp,
+fn, tn, epsilon=...)``).  Inside the CUDA path they are never called per element: the kernels
+carry the same expressions (csrc/xc_common.cuh: xc_binary_metric).
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, Optional, Tuple
+
+from .utils import add_kwargs_to_signature
+
+XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA, XC_METRIC_JACCARD = 0, 1, 2, 3
+XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN = 4, 5, 6
+AFFINE_GAIN_METRICS = (XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA)
+TN_METRICS = (XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN)
+
+
+def binary_precision_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
+    return tp / (tp + fp + epsilon)
+
+
+def binary_recall_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
+    return tp / (tp + fn + epsilon)
+
+
+def binary_fbeta_score_on_conf_matrix(tp, fp, fn, tn, beta: float = 1.0, epsilon: float = 1e-9):
+    return (1 + beta**2) * tp / ((beta**2 * (tp + fp)) + tp + fn + epsilon)
+
+
+def binary_f1_score_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
+    return binary_fbeta_score_on_conf_matrix(tp, fp, fn, tn, beta=1.0, epsilon=epsilon)
+
+
+def binary_jaccard_score_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
+    return tp / (tp + fp + fn + epsilon)
+
+
+def _rates(tp, fp, fn, tn, epsilon):
+    return tp / (tp + fn + epsilon), tn / (tn + fp + epsilon)
+
+
+def binary_balanced_accuracy_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
+    tpr, tnr = _rates(tp, fp, fn, tn, epsilon)
+    return (tpr + tnr) / 2
+
+
+def binary_gmean_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
+    tpr, tnr = _rates(tp, fp, fn, tn, epsilon)
+    return (tpr * tnr) ** 0.5
+
+
+def binary_hmean_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
+    tpr, tnr = _rates(tp, fp, fn, tn, epsilon)
+    return (2 * tpr * tnr) / (tpr + tnr)
+
+
+_BINARY_IDS = {
+    "binary_precision_on_conf_matrix": XC_METRIC_PRECISION,
+    "binary_recall_on_conf_matrix": XC_METRIC_RECALL,
+    "binary_fbeta_score_on_conf_matrix": XC_METRIC_FBETA,
+    "binary_f1_score_on_conf_matrix": XC_METRIC_FBETA,
+    "binary_jaccard_score_on_conf_matrix": XC_METRIC_JACCARD,
+    "binary_balanced_accuracy_on_conf_matrix": XC_METRIC_BALANCED_ACC,
+    "binary_gmean_on_conf_matrix": XC_METRIC_GMEAN,
+    "binary_hmean_on_conf_matrix": XC_METRIC_HMEAN,
+}
+_OWN_MODULES = ("xcolumns_b200.metrics", "xcolumns.metrics")
+
+
+def make_macro_metric_on_conf_matrix(binary_metric: Callable, name: str) -> Callable:
+    """Macro average of a binary metric (xcolumns/metrics.py:38-67)."""
+
+    def macro_metric_on_conf_matrix(tp, fp, fn, tn, **kwargs):
+        return binary_metric(tp, fp, fn, tn, **kwargs).mean()
+
+    macro_metric_on_conf_matrix.__doc__ = f"Macro-averaged {name} on the confusion vectors (tp, fp, fn, tn)."
+    macro_metric_on_conf_matrix._xc_binary_metric = binary_metric
+    return add_kwargs_to_signature(macro_metric_on_conf_matrix, binary_metric)
+
+
+macro_precision_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_precision_on_conf_matrix, "precision")
+macro_recall_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_recall_on_conf_matrix, "recall")
+macro_fbeta_score_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_fbeta_score_on_conf_matrix, "F-beta score")
+macro_f1_score_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_fbeta_score_on_conf_matrix, "F1 score")
+macro_jaccard_score_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_jaccard_score_on_conf_matrix, "Jaccard score")
+macro_balanced_accuracy_on_conf_matrix = make_macro_metric_on_conf_matrix(
+    binary_balanced_accuracy_on_conf_matrix, "balanced accuracy")
+macro_gmean_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_gmean_on_conf_matrix, "G-mean")
+macro_hmean_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_hmean_on_conf_matrix, "H-mean")
+
+
+def coverage_on_conf_matrix(tp, fp, fn, tn):
+    """Fraction of labels with at least one true positive (xcolumns/metrics.py:972-990)."""
+    return (tp > 0).mean()
+
+
+class UnsupportedMetricError(NotImplementedError):
+    pass
+
+
+def resolve_binary_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]] = None) -> Tuple[int, float, float]:
+    """(metric id, beta, epsilon) of a built-in binary metric callable -- ours or the reference's
+    own (matched by module + name).  Other callables cannot run inside the fused kernels."""
+    kw = dict(metric_kwargs or {})
+    name = getattr(func, "__name__", None)
+    mod = getattr(func, "__module__", None)
+    if name in _BINARY_IDS and mod in _OWN_MODULES:
+        beta = 1.0
+        if name == "binary_fbeta_score_on_conf_matrix":
+            beta = float(kw.pop("beta", 1.0))
+        eps = float(kw.pop("epsilon", 1e-9))
+        if kw:
+            raise ValueError(f"unknown metric_kwargs for {name}: {sorted(kw)}")
+        return _BINARY_IDS[name], beta, eps
+    raise UnsupportedMetricError(
+        f"binary_metric_func={func!r} is not one of the built-in binary metrics "
+        f"({', '.join(sorted(_BINARY_IDS))}); arbitrary Python callables cannot be evaluated inside "
+        f"the CUDA sweep and xcolumns_b200 has no CPU fallback")
+
+
+def resolve_macro_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]] = None) -> Tuple[int, float, float]:
+    """Same for a macro-averaged metric on the confusion matrix (Frank-Wolfe objective)."""
+    inner = getattr(func, "_xc_binary_metric", None)
+    if inner is None and getattr(func, "__name__", "") == "macro_metric_on_conf_matrix" and func.__closure__:
+        # the reference's factory closure (xcolumns/metrics.py:51-58) captures `binary_metric`
+        for cell in func.__closure__:
+            try:
+                v = cell.cell_contents
+            except ValueError:
+                continue
+            if callable(v) and getattr(v, "__name__", None) in _BINARY_IDS:
+                inner = v
+    if inner is None:
+        raise UnsupportedMetricError(
+            f"metric_func={func!r} is not a built-in macro-averaged metric; xcolumns_b200 fuses "
+            f"macro precision / recall / F-beta / Jaccard / balanced accuracy / G-mean / H-mean")
+    return resolve_binary_metric(inner, metric_kwargs)

@@ -1,0 +1,175 @@
+"""predict_weighted_per_instance / predict_top_k on the GPU
+(drop-in for xcolumns/weighted_prediction.py:91-220).
+
+gains = a * eta + b per row, then the k largest (k > 0) or all gains >= th (k == 0).  The CUDA
+kernel streams every row once with 128-bit loads and keeps a warp-level top-k list; ties go to
+the lowest label id.  Results come back in the caller's container: numpy -> numpy, torch ->
+torch on the same device, csr_matrix -> csr_matrix with k slots per row.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from time import time
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix
+
+from . import _device as dev
+from ._lib import XC_F32, XC_F64
+from .types import DenseMatrix, DType, Matrix
+
+_MAX_K = 32
+
+
+def _check_k(k):
+    if not isinstance(k, int) or isinstance(k, bool):
+        raise ValueError("k must be an integer")
+    if k > _MAX_K:
+        raise NotImplementedError(f"xcolumns_b200 kernels support k <= {_MAX_K}, got k={k}")
+
+
+def topk_dense_device(d: dev.DenseDev, k: int, a: Optional[torch.Tensor], b: Optional[torch.Tensor],
+                      g_code: int, want_vals: bool = False, rows: Optional[torch.Tensor] = None):
+    """Device-level entry: compact [n, k] label ids (+ gains) of a DenseDev."""
+    device = d.t.device
+    ctx = dev.ctx_for(device)
+    n_rows = d.n if rows is None else int(rows.numel())
+    out_idx = torch.empty((n_rows, k), dtype=torch.int32, device=device)
+    out_val = torch.empty((n_rows, k), dtype=torch.float32 if g_code == XC_F32 else torch.float64,
+                          device=device) if want_vals else None
+    ctx.call("xc_topk_dense", dev.ptr(d.t), d.code, n_rows, d.m, d.ld, dev.ptr(rows), dev.ptr(a), dev.ptr(b),
+             g_code, k, dev.ptr(out_idx), dev.ptr(out_val), dev.stream_ptr(device))
+    return out_idx, out_val
+
+
+def topk_csr_device(c: dev.CsrDev, k: int, a: Optional[torch.Tensor], b: Optional[torch.Tensor],
+                    want_vals: bool = False):
+    device = c.data.device
+    ctx = dev.ctx_for(device)
+    out_idx = torch.empty((c.n, k), dtype=torch.int32, device=device)
+    out_val = torch.empty((c.n, k), dtype=c.data.dtype, device=device) if want_vals else None
+    ctx.call("xc_topk_csr", dev.ptr(c.data), c.code, dev.ptr(c.indices), dev.ptr(c.indptr), c.n, dev.ptr(a),
+             dev.ptr(b), k, dev.ptr(out_idx), dev.ptr(out_val), dev.stream_ptr(device))
+    return out_idx, out_val
+
+
+def _gain_dtype(y_dtype: torch.dtype, a, b) -> torch.dtype:
+    """numpy/torch type promotion of eta * a + b (weighted_prediction.py:37-41)."""
+    out = y_dtype
+    for v in (a, b):
+        if v is None:
+            continue
+        vd = v.dtype if isinstance(v, torch.Tensor) else torch.from_numpy(np.empty(0, dtype=np.asarray(v).dtype)).dtype
+        if vd == torch.float64:
+            out = torch.float64
+    return out
+
+
+def predict_weighted_per_instance(
+    y_proba: Matrix,
+    k: int,
+    th: float = 0.0,
+    a: Optional[DenseMatrix] = None,
+    b: Optional[DenseMatrix] = None,
+    dtype: Optional[DType] = None,
+    keep_scores: bool = False,
+    return_meta: bool = False,
+    return_weights: bool = False,
+) -> Union[Matrix, Tuple[Matrix, dict]]:
+    """Weighted per-instance prediction: gains g = a * eta_i + b, top-k (k > 0) or g >= th (k = 0).
+
+    Same arguments, validation and return contract as the reference
+    (xcolumns/weighted_prediction.py:91-188)."""
+    if not isinstance(y_proba, (np.ndarray, torch.Tensor, csr_matrix)):
+        raise ValueError("y_proba must be either np.ndarray, torch.Tensor, or csr_matrix")
+    if len(y_proba.shape) == 1:
+        y_proba = y_proba.reshape(1, -1)
+    elif len(y_proba.shape) > 2:
+        raise ValueError("y_proba must be 1d or 2d")
+    _check_k(k)
+    n, m = y_proba.shape
+    for name, v in (("a", a), ("b", b)):
+        if v is not None:
+            if not isinstance(v, (np.ndarray, torch.Tensor)):
+                raise ValueError(f"{name} must be np.ndarray or torch.Tensor")
+            if tuple(v.shape) != (m,):
+                raise ValueError(f"{name} must be of shape (y_proba[1],)")
+    if return_meta:
+        meta = {"iters": 1, "time": time()}
+
+    device = dev.pick_device(y_proba)
+    if isinstance(y_proba, csr_matrix):
+        c = dev.csr_to_device(y_proba, device)
+        # the reference casts a and b to the data dtype (weighted_prediction.py:72-75)
+        ad = dev.vec_to_device(a, device, c.data.dtype, m, "a")
+        bd = dev.vec_to_device(b, device, c.data.dtype, m, "b")
+        if k > 0:
+            idx, vals = topk_csr_device(c, k, ad, bd, want_vals=keep_scores)
+            y_pred = dev.compact_to_csr_like(y_proba, idx, out_dtype=dtype, vals=vals)
+        else:
+            y_pred = _threshold_csr(y_proba, c, ad, bd, th, dtype)
+    else:
+        d = dev.dense_to_device(y_proba, device)
+        gdt = _gain_dtype(d.torch_dtype, a, b)
+        g_code = XC_F32 if gdt == torch.float32 else XC_F64
+        ad = dev.vec_to_device(a, device, gdt, m, "a")
+        bd = dev.vec_to_device(b, device, gdt, m, "b")
+        if k > 0:
+            if k > m:
+                raise ValueError(f"k={k} is larger than the number of labels m={m}")
+            idx, vals = topk_dense_device(d, k, ad, bd, g_code, want_vals=keep_scores)
+            y_pred = dev.compact_to_dense_like(y_proba, idx, m, out_dtype=dtype, vals=vals)
+        else:
+            y_pred = _threshold_dense(y_proba, d, ad, bd, g_code, th, dtype)
+
+    if return_meta:
+        meta["time"] = time() - meta["time"]
+        if return_weights:
+            meta["a"] = a
+            meta["b"] = b
+        return y_pred, meta
+    return y_pred
+
+
+def _threshold_dense(like, d: dev.DenseDev, ad, bd, g_code, th, dtype):
+    device = d.t.device
+    ctx = dev.ctx_for(device)
+    out = torch.empty((d.n, d.m), dtype=d.torch_dtype, device=device)
+    ctx.call("xc_threshold_dense", dev.ptr(d.t), d.code, d.n, d.m, d.ld, dev.ptr(ad), dev.ptr(bd), g_code,
+             C.c_double(float(th)), dev.ptr(out), d.m, dev.stream_ptr(device))
+    if isinstance(like, torch.Tensor):
+        return out.to(device=like.device, dtype=like.dtype if dtype is None else dtype)
+    res = out.cpu().numpy()
+    return res if dtype is None else res.astype(dtype)
+
+
+def _threshold_csr(like: csr_matrix, c: dev.CsrDev, ad, bd, th, dtype):
+    """k == 0 on CSR rows (numba_csr_functions.py:516-517, :631-653): keep stored labels whose
+    gain >= th.  Elementwise on the nnz entries, compaction with torch on the device."""
+    idx = c.indices.long()
+    g = c.data
+    if ad is not None:
+        g = g * ad[idx]
+    if bd is not None:
+        g = g + bd[idx]
+    keep = g >= th
+    row_of = torch.repeat_interleave(torch.arange(c.n, device=c.data.device), c.indptr[1:] - c.indptr[:-1])
+    counts = torch.zeros(c.n, dtype=torch.int64, device=c.data.device).index_add_(0, row_of[keep], torch.ones_like(row_of[keep]))
+    indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=c.data.device), counts.cumsum(0)])
+    new_idx = c.indices[keep].cpu().numpy().astype(like.indices.dtype)
+    data = np.ones(new_idx.shape[0], dtype=like.data.dtype)
+    return csr_matrix((data, new_idx, indptr.cpu().numpy().astype(like.indptr.dtype)), shape=like.shape, dtype=dtype)
+
+
+def predict_top_k(
+    y_proba: Matrix,
+    k: int,
+    dtype: Optional[DType] = None,
+    keep_scores: bool = False,
+    return_meta: bool = False,
+) -> Union[Matrix, Tuple[Matrix, dict]]:
+    """Top-k labels per row -- optimal for precision@k / nDCG@k
+    (xcolumns/weighted_prediction.py:196-220)."""
+    return predict_weighted_per_instance(y_proba, k=k, dtype=dtype, keep_scores=keep_scores, return_meta=return_meta)
