@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the BCA macro-F1@5 hot path (BASELINE.json metric: instances/sec per sweep).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows n] [--labels m]
+
+A "step" is one block-Jacobi BCA sweep (macro-F1@5) over the whole synthetic AmazonCat-13K-shape
+probability matrix (n=307000, m=13000, float32, 15.96 GB -- far larger than the 126 MB L2, so no
+L2 flush is needed between steps).  With N > 1 (torchrun, one rank per GPU) every rank holds its
+own n-row shard (weak scaling) and the per-batch confusion deltas are all-reduced over NCCL.
+
+Printed JSON (one line, rank 0):
+  value     : instances/sec/sweep with y_proba resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same metric through the public Python API with HOST (pinned) buffers: H2D of
+              y_proba, top-k init, K sweeps, D2H + host materialisation of the prediction
+  roofline  : the dominant kernel (bca_batch_dense_kernel): algorithmic bytes per launch
+              (rows * m * 4) / CUDA-event duration per launch vs the measured HBM copy peak
+  cpu_baseline : the CPU oracle (C port of the reference algorithm, 1 core) on a row subsample
+`--impl reference` times that same CPU port (the reference is pure Python + numba and cannot
+travel to the GPU box) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "amazoncat13k-shape dense f32 n=307000 m=13000 k=5 macro-F1 BCA (batched)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=307000)
+    ap.add_argument("--labels", type=int, default=13000)
+    ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=0, help="rows per commit per rank (0 = default)")
+    ap.add_argument("--cpu-rows", type=int, default=1500, help="row subsample of the CPU baseline")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# --------------------------------------------------------------------------------------------
+
+def cpu_port_sample(eta_sub: np.ndarray, k: int, sweeps: int):
+    """instances/sec/sweep of the sequential reference algorithm (C port, 1 core)."""
+    from oracle import oracle as orc
+    orc.build()
+    t0 = time.time()
+    _, meta = orc.predict_using_bc_with_0approx(eta_sub, "f1", k, seed=0, skip_tn=True, max_iters=sweeps,
+                                                tolerance=-np.inf)
+    dt = time.time() - t0
+    return eta_sub.shape[0] * meta["iters"] / dt, dt, meta["iters"]
+
+
+def run_reference(args):
+    """--impl reference: rank 0 times the CPU port, other ranks exit."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from xcolumns_b200.synth import dense_probs
+    n_sub = args.cpu_rows
+    eta = dense_probs(n_sub, args.labels, seed=1003, tie_free=False)
+    cpu_port_sample(eta[:64], args.k, 1)  # warm (page-in, build)
+    per_step = []
+    for _ in range(args.warmup):
+        cpu_port_sample(eta, args.k, 1)
+    t0 = time.time()
+    for _ in range(args.steps):
+        v, dt, _ = cpu_port_sample(eta, args.k, 1)
+        per_step.append(dt)
+    total = time.time() - t0
+    value = n_sub * args.steps / total
+    line = {
+        "impl": "reference", "metric": "BCA macro-F1@5 instances/sec per sweep", "value": value,
+        "unit": "instances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 scores, f64 state", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows": args.rows, "labels": args.labels, "k": args.k},
+        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": 1, "kind": "port",
+                         "sample": f"{n_sub} rows x {args.labels} labels of the same distribution, 1 sequential sweep per step "
+                                   f"(a sweep's per-instance cost does not depend on n)"},
+        "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+        self.active = False  # samples are kept only while the timed region runs
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self.stop_flag:
+                clk = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                if self.active:
+                    self.sm.append(clk)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                time.sleep(0.001)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from xcolumns_b200 import _device as dev
+    from xcolumns_b200 import metrics as M
+    from xcolumns_b200 import predict_optimizing_macro_f1_score_using_bc
+    from xcolumns_b200._lib import XC_F32, XC_SUM_FAST
+    from xcolumns_b200.block_coordinate import BcaSession, _metric_params, default_batch_rows
+    from xcolumns_b200.distributed import make_comm
+    from xcolumns_b200.synth import dense_probs_device
+    from xcolumns_b200.weighted_prediction import topk_dense_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    comm = make_comm(world > 1, device)
+
+    n, m, k = args.rows, args.labels, args.k
+    eta_t = dense_probs_device(n, m, seed=1003 + rank, device=device)
+    data = dev.DenseDev(eta_t, n, m, m, XC_F32, 0)
+    n_global = comm.n_global(n)
+    params = _metric_params(M.XC_METRIC_FBETA, 1.0, 1e-9, True, True, n_global)
+    sess = BcaSession(data, k, params, params, "mean", comm)
+    init_pred = topk_dense_device(data, k, None, None, XC_F32)[0]
+    batch = args.batch or default_batch_rows(n, sess.wave_rows())
+    n_batches = comm.max_int((n + batch - 1) // batch)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(17 + rank)
+
+    def one_sweep(events=None):
+        order = torch.randperm(n, generator=gen, device=device, dtype=torch.int32)
+        sess.delta.zero_()
+        sess.sweep_batched(order, batch, n_batches, events=events)
+        sess.recompute(XC_SUM_FAST)
+        sess.utility_device(1)
+
+    def reset():
+        sess.pred = init_pred.clone()
+        sess.recompute(XC_SUM_FAST)
+        sess.utility_device(0)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    reset()
+    for _ in range(args.warmup):
+        one_sweep()
+    reset()
+    torch.cuda.synchronize(device)
+    comm.barrier()
+    torch.cuda.synchronize(device)
+    sampler.active = True
+    launches0 = sess.ctx.launches()
+    events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_sweep(events)
+    e1.record()
+    torch.cuda.synchronize(device)
+    comm.barrier()
+    torch.cuda.synchronize(device)
+    sampler.active = False
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = sess.ctx.launches() - launches0
+    utilities = sess.util_buf[:2].cpu().tolist()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_global * args.steps / (ms / 1e3)
+
+    # per-launch roofline of the dominant kernel
+    kern_ms = [a.elapsed_time(b) for a, b, _ in events]
+    kern_rows = [r for _, _, r in events]
+    full = [(t_, r) for t_, r in zip(kern_ms, kern_rows) if r == batch] or list(zip(kern_ms, kern_rows))
+    avg_ms = float(np.mean([t_ for t_, _ in full]))
+    bytes_per_launch = full[0][1] * m * 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_per_launch / (avg_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("bca_batch_dense_kernel")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "bca_batch_dense_kernel<float,4>",
+                "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                "kernel_share_of_step": float(np.sum(kern_ms)) / ms,
+                "kernel_ms_per_sweep": [round(float(np.sum(kern_ms[i * len(kern_ms) // args.steps:(i + 1) * len(kern_ms) // args.steps])), 4)
+                                        for i in range(args.steps)],
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+
+    line = {
+        "metric": "BCA macro-F1@5 instances/sec per sweep", "value": value, "unit": "instances/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 scores, f64 state",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_gpu": n, "labels": m, "k": k, "mode": "batched",
+                   "batch_rows_per_gpu": batch, "commits_per_sweep": n_batches,
+                   "l2": "input 15.96 GB per GPU >> 126 MB L2, no flush needed",
+                   "collective": "NCCL all-reduce of 3*m float64 deltas per commit" if world > 1 else "none"},
+        "roofline": roofline, "gpu_launches": int(launches), "clocks": sampler.summary(),
+        "utility_after_timed_sweeps": utilities[1],
+    }
+
+    # ---- end-to-end through the public API with host buffers (rank-local shard) ----------------
+    if not args.no_e2e:
+        del sess, init_pred
+        host = torch.empty((n, m), dtype=torch.float32, pin_memory=True)
+        host.copy_(eta_t)
+        del eta_t, data
+        torch.cuda.empty_cache()
+        y_np = host.numpy()
+        comm.barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.time()
+        pred, meta = predict_optimizing_macro_f1_score_using_bc(
+            y_np, k, seed=0, mode="batched", max_iters=args.steps, tolerance=-np.inf, return_meta=True,
+            distributed=(world > 1), batch_size=batch)
+        torch.cuda.synchronize(device)
+        dt = time.time() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        line["e2e"] = {"value": n_global * meta["iters"] / dt, "unit": "instances/s",
+                       "h2d_bytes_per_step": n * m * 4 / meta["iters"],
+                       "d2h_bytes_per_step": n * k * 4 / meta["iters"],
+                       "seconds_per_call": dt, "sweeps_per_call": meta["iters"],
+                       "what": "predict_optimizing_macro_f1_score_using_bc(numpy pinned host array) -> dense numpy y_pred"}
+        assert pred.shape == (n, m)
+        del pred
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1) -------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from xcolumns_b200.synth import dense_probs
+        n_sub = args.cpu_rows
+        eta_sub = dense_probs(n_sub, m, seed=1003, tie_free=False)
+        v, dt, iters = cpu_port_sample(eta_sub, k, 3)
+        line["cpu_baseline"] = {"value": v, "unit": "instances/s", "cores": 1, "kind": "port",
+                                "sample": f"{n_sub} rows x {m} labels, {iters} sequential sweeps in {dt:.1f} s "
+                                          f"(C port of the reference algorithm; the Python reference itself runs "
+                                          f"~1.0k inst/s at this m, BASELINE.md table B)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -180,6 +180,9 @@ XC_API int xc_cov_state_csr(xc_ctx *ctx, const void *data, int dtype, const int3
 XC_API int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
                        double *dtp, double *dfp, double *dfn, int64_t m, float *coef_n,
                        float *coef_s, void *stream);
+/* Rows one full wave of the dense batch kernel covers (SMs x resident CTAs x warps x rows per
+ * warp): batches that are a multiple of it leave no partially filled last wave.               */
+XC_API int xc_bca_wave_rows(xc_ctx *ctx, int dtype);
 /* One batch: rows[0..n_rows) stream past the frozen coefficients, every row re-selects its k
  * best labels (own contribution removed via coef_s), pred_idx rows are rewritten and the
  * confusion deltas of all changed rows are accumulated into dtp/dfp/dfn (float64 atomics). */

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "xc_cov_exact_sweep_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _i64, _int, _dbl, _int, _vp, _vp, _vp],
     "xc_cov_state_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _int, _int, _vp, _vp],
     "xc_bca_coef": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "xc_bca_wave_rows": [_int],
     "xc_bca_batch_dense": [_vp, _int, _i64, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_cov_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _dbl, _vp, _vp, _vp, _vp],

@@ -153,6 +153,12 @@ class BcaSession:
             n_total = self.comm.n_global(self.n)
             self.state[3] = -self.state[0] - self.state[1] - self.state[2] + n_total
 
+    def wave_rows(self) -> int:
+        """rows of one full wave of the dense batch kernel (0 for CSR: one warp per row)"""
+        if self.is_csr:
+            return 0
+        return int(self.ctx.lib.xc_bca_wave_rows(self.ctx.handle, self.data.code))
+
     def utility_device(self, slot: int) -> None:
         """block_coordinate.py:54-90 on the device; result lands in util_buf[slot]."""
         self.ctx.call("xc_utility", C.byref(self.up), self.agg, self._sp(0), self._sp(1), self._sp(2), self._sp(3),
@@ -170,9 +176,12 @@ class BcaSession:
                           int(order_dev.numel()), k, C.byref(self.p), int(greedy), dev.ptr(self.pred), self._sp(0),
                           self._sp(1), self._sp(2), self._sp(3), self._s())
 
-    def sweep_batched(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int] = None) -> None:
+    def sweep_batched(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int] = None,
+                      events: Optional[list] = None) -> None:
         """One block-Jacobi sweep over the (local) rows in order_dev, `batch` rows per commit.
-        n_batches (distributed): common number of commits so every rank joins every all-reduce."""
+        n_batches (distributed): common number of commits so every rank joins every all-reduce.
+        events: if a list, (start, end, rows) CUDA-event triples around every batch kernel are
+        appended (bench.py's per-launch roofline measurement)."""
         d, k = self.data, self.k
         n_loc = int(order_dev.numel())
         nb = n_batches if n_batches is not None else (n_loc + batch - 1) // batch
@@ -184,6 +193,9 @@ class BcaSession:
                           self._dp(1), self._dp(2), self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
             if hi > lo:
                 rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
+                if events is not None:
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record(torch.cuda.current_stream(self.device))
                 if self.is_csr:
                     self.ctx.call("xc_bca_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
                                   rows, hi - lo, k, dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
@@ -192,6 +204,9 @@ class BcaSession:
                     self.ctx.call("xc_bca_batch_dense", dev.ptr(d.t), d.code, d.m, d.ld, rows, hi - lo, k,
                                   dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._dp(0),
                                   self._dp(1), self._dp(2), self._s())
+                if events is not None:
+                    ev1.record(torch.cuda.current_stream(self.device))
+                    events.append((ev0, ev1, hi - lo))
             if self.comm.world > 1:
                 self.comm.allreduce_sum_(self.delta)
 
@@ -216,10 +231,14 @@ def _host_utility(binary_metric_func, aggregation: str, state: torch.Tensor, n_d
     raise ValueError(f"Unsupported utility aggregation function: {aggregation}, must be either 'mean' or 'sum'")
 
 
-def default_batch_rows(n: int, world: int = 1) -> int:
-    """Rows committed together by one rank: global batch <= n_global / 16 (SURVEY.md App. C:
-    <= n/6 keeps the reference's fixed point within 3e-7), at most 16384."""
-    return max(1, min(16384, n // 16 if n >= 16 else 1))
+def default_batch_rows(n: int, wave_rows: int = 0) -> int:
+    """Rows one rank commits together: about n/8 (<= n/6 keeps the reference's
+    fixed point within 3e-7 for F-measures), rounded down to whole waves of the streaming kernel so
+    that no launch ends with a partially filled wave; tiny inputs use n/8 as is."""
+    b = max(1, n // 8)
+    if wave_rows > 0 and b >= wave_rows:
+        b = (b // wave_rows) * wave_rows
+    return b
 
 
 def predict_using_bc_with_0approx(
@@ -328,7 +347,7 @@ def predict_using_bc_with_0approx(
             raise NotImplementedError(
                 "xcolumns_b200 batched mode fuses the metrics whose marginal gain is affine in the probability "
                 "(precision, recall, F-beta/F1); use mode='exact' for Jaccard / balanced accuracy / G-mean / H-mean")
-        batch = int(batch_size) if batch_size else default_batch_rows(n_order, comm.world)
+        batch = int(batch_size) if batch_size else default_batch_rows(n_order, sess.wave_rows())
         n_batches = comm.max_int((n_order + batch - 1) // batch)
         gen = torch.Generator(device=device)
         gen.manual_seed(0 if seed is None else int(seed) + 7919 * comm.rank)
@@ -432,7 +451,10 @@ def predict_optimizing_coverage_using_bc(
     rng = np.random.default_rng(seed)
     order = np.arange(n)
     sum_order = XC_SUM_ORDERED if mode == "exact" else XC_SUM_FAST
-    batch = int(batch_size) if batch_size else default_batch_rows(n)
+    # coverage couples the rows of a batch much more strongly than the F-measures (every row of a
+    # batch rushes to the same uncovered label): n/32 keeps the block-Jacobi fixed point within
+    # 1e-4 of the sequential one, n/8 does not (measured, tests/test_gpu_parity.py)
+    batch = int(batch_size) if batch_size else max(1, min(4096, n // 32))
     dEf = torch.ones(m, dtype=torch.float64, device=device)
     new_cov = None
     for j in range(1, max_iters + 1):

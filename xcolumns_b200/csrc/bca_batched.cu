@@ -430,6 +430,17 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
 
 }  // namespace
 
+extern "C" int xc_bca_wave_rows(xc_ctx *ctx, int dtype)
+{
+    if (!ctx) return XC_ERR_INVALID;
+    int per_sm = 0;
+    if (dtype == XC_F32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bca_batch_dense_kernel<float, 4>, kThreads, 0);
+    else if (dtype == XC_F64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bca_batch_dense_kernel<double, 4>, kThreads, 0);
+    else return XC_ERR_UNSUPPORTED;
+    if (per_sm < 1) per_sm = 1;
+    return ctx->sm_count * per_sm * (kThreads / 32) * 4;
+}
+
 extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn, double *dtp,
                            double *dfp, double *dfn, int64_t m, float *coef_n, float *coef_s, void *stream)
 {

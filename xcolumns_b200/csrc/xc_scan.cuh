@@ -99,9 +99,11 @@ struct XfAffine {
 };
 
 // ---- slow path: some lane holds a candidate for row-list tk ---------------------------------
+// Inlined on purpose: taking references to the register-resident list / gains from a real call
+// would force them into local memory in the streaming loop (measured: 8 STL.128 per trip).
 template <typename G, int V, bool SKIP>
-__device__ __noinline__ void xc_scan_insert(WarpTopK<G> &tk, const G (&g)[V], int64_t cbase, int stride, int k,
-                                            int old_idx)
+__device__ __forceinline__ void xc_scan_insert(WarpTopK<G> &tk, const G (&g)[V], int64_t cbase, int stride, int k,
+                                               int old_idx)
 {
     const int lane = lane_id();
     bool hit = false;
@@ -125,6 +127,15 @@ __device__ __noinline__ void xc_scan_insert(WarpTopK<G> &tk, const G (&g)[V], in
     }
 }
 
+template <typename G, int V>
+__device__ __forceinline__ G xc_vmax(const G (&g)[V])
+{
+    G mx = g[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) mx = fmax(mx, g[v]);  // FMNMX drops NaN operands; all-NaN stays NaN
+    return mx;
+}
+
 // ---- the scan ---------------------------------------------------------------------------------
 // rp[r]: start of row r; vec_ok: rows are 16-byte aligned (base aligned and ld % V == 0).
 // old_idx[r]: (SKIP) lanes < k hold the labels already seeded into tk[r]; candidates equal to
@@ -134,53 +145,66 @@ __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m
                                              WarpTopK<G> (&tk)[R], const int (&old_idx)[R], int k)
 {
     constexpr int V = XcVec<TE>::V;
+    constexpr int STEP = 32 * V;  // columns one warp covers per 16-byte load
     const int lane = lane_id();
     const int64_t mv = vec_ok ? (m / V) * V : 0;
+    const int64_t m2 = (mv / (2 * STEP)) * (2 * STEP);  // part covered by full, unguarded double steps
     const G qnan = (G)NAN;
 
-    for (int64_t c0 = 0; c0 < mv; c0 += 2 * 32 * V) {  // two chunks per trip for MLP
+    // ---- main loop: two 16-byte chunks per row in flight, no bounds checks, no local memory ----
+    for (int64_t c0 = 0; c0 < m2; c0 += 2 * STEP) {
         const int64_t cA = c0 + (int64_t)lane * V;
-        const int64_t cB = cA + 32 * V;
-        const bool inA = cA < mv, inB = cB < mv;
+        const int64_t cB = cA + STEP;
         TE eA[R][V], eB[R][V];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (inA) XcVec<TE>::load(rp[r] + cA, eA[r]);
-            if (inB) XcVec<TE>::load(rp[r] + cB, eB[r]);
+            XcVec<TE>::load(rp[r] + cA, eA[r]);
+            XcVec<TE>::load(rp[r] + cB, eB[r]);
         }
         G gA[R][V], gB[R][V], ca[V], cb[V];
         bool hit = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (inA) {
-                xf.template apply_vec<TE, V>(cA, eA[r], gA[r], ca, cb, r == 0);
-            } else {
-#pragma unroll
-                for (int v = 0; v < V; ++v) gA[r][v] = qnan;
-            }
-#pragma unroll
-            for (int v = 0; v < V; ++v) hit |= tk[r].passes(gA[r][v]);
+            xf.template apply_vec<TE, V>(cA, eA[r], gA[r], ca, cb, r == 0);
+            hit |= tk[r].passes(xc_vmax<G, V>(gA[r]));
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (inB) {
-                xf.template apply_vec<TE, V>(cB, eB[r], gB[r], ca, cb, r == 0);
-            } else {
-#pragma unroll
-                for (int v = 0; v < V; ++v) gB[r][v] = qnan;
-            }
-#pragma unroll
-            for (int v = 0; v < V; ++v) hit |= tk[r].passes(gB[r][v]);
+            xf.template apply_vec<TE, V>(cB, eB[r], gB[r], ca, cb, r == 0);
+            hit |= tk[r].passes(xc_vmax<G, V>(gB[r]));
         }
         if (__any_sync(XC_FULL, hit)) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 xc_scan_insert<G, V, SKIP>(tk[r], gA[r], c0, V, k, old_idx[r]);
-                xc_scan_insert<G, V, SKIP>(tk[r], gB[r], c0 + 32 * V, V, k, old_idx[r]);
+                xc_scan_insert<G, V, SKIP>(tk[r], gB[r], c0 + STEP, V, k, old_idx[r]);
             }
         }
     }
-    // scalar tail (and the whole row when it is not 16-byte aligned): one column per lane
+    // ---- guarded single steps for the rest of the vectorisable part ------------------------------
+    for (int64_t c0 = m2; c0 < mv; c0 += STEP) {
+        const int64_t c = c0 + (int64_t)lane * V;
+        const bool in = c < mv;
+        G g[R][V], ca[V], cb[V];
+        bool hit = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (in) {
+                TE e[V];
+                XcVec<TE>::load(rp[r] + c, e);
+                xf.template apply_vec<TE, V>(c, e, g[r], ca, cb, r == 0);
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) g[r][v] = qnan;
+            }
+            hit |= tk[r].passes(xc_vmax<G, V>(g[r]));
+        }
+        if (__any_sync(XC_FULL, hit)) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) xc_scan_insert<G, V, SKIP>(tk[r], g[r], c0, V, k, old_idx[r]);
+        }
+    }
+    // ---- scalar tail (and the whole row when it is not 16-byte aligned): one column per lane ----
     for (int64_t c0 = mv; c0 < m; c0 += 32) {
         const int64_t c = c0 + lane;
         G g1[R][1];
