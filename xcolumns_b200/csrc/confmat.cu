@@ -136,19 +136,51 @@ colsum_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indice
 }
 
 // ---- dense truth, compact prediction ------------------------------------------------------------
+// Warp w handles 32 consecutive rows of ONE prediction slot.  Frequent labels repeat inside such a
+// warp (head labels are predicted for a large share of the rows), so equal labels are combined
+// with __match_any_sync and only the group leader issues the float64 atomics: the hot addresses
+// see up to 32x fewer atomics (measured 244 us -> see profiles/ for n*k = 1.5M entries).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 confmat_compact_fast_kernel(const T *__restrict__ yt, int64_t ld, const int32_t *__restrict__ pred, int k,
                             int64_t n, double *tp, double *fp)
 {
-    const int64_t total = n * k;
+    const int lane = lane_id();
     const T one = (T)1;
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
-        int j = pred[t];
-        if (j < 0) continue;
-        T y = yt[(t / k) * ld + j];
-        atomicAdd(tp + j, (double)y);
-        atomicAdd(fp + j, (double)(T)(one - y));
+    const int64_t n32 = (n + 31) / 32;           // warps per slot
+    const int64_t total_warps = n32 * k;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    for (int64_t w = warp0; w < total_warps; w += (int64_t)gridDim.x * (kThreads / 32)) {
+        const int slot = (int)(w / n32);
+        const int64_t i = (w - (int64_t)slot * n32) * 32 + lane;
+        int j = -1;
+        double vt = 0.0, vf = 0.0;
+        if (i < n) {
+            j = pred[i * k + slot];
+            if (j >= 0) {
+                T y = yt[i * ld + j];
+                vt = (double)y;
+                vf = (double)(T)(one - y);
+            }
+        }
+        unsigned grp = __match_any_sync(XC_FULL, j);
+        const bool leader = (__ffs(grp) - 1) == lane;
+        double st = 0.0, sf = 0.0;
+        unsigned rest = grp;
+        while (__any_sync(XC_FULL, rest != 0)) {
+            int src = rest ? __ffs(rest) - 1 : lane;
+            double ot = __shfl_sync(XC_FULL, vt, src);
+            double of = __shfl_sync(XC_FULL, vf, src);
+            if (rest) {
+                st += ot;
+                sf += of;
+                rest &= rest - 1;
+            }
+        }
+        if (leader && j >= 0) {
+            atomicAdd(tp + j, st);
+            atomicAdd(fp + j, sf);
+        }
     }
 }
 
@@ -455,7 +487,7 @@ extern "C" int xc_confmat_dense_compact(xc_ctx *ctx, const void *y_true, int dty
     }
     XC_CUDA_TRY(ctx, cudaMemsetAsync(tp, 0, sizeof(double) * m, st));
     XC_CUDA_TRY(ctx, cudaMemsetAsync(fp, 0, sizeof(double) * m, st));
-    int grid = cap_grid(ctx, (n * k + kThreads - 1) / kThreads);
+    int grid = cap_grid(ctx, (((n + 31) / 32) * k + (kThreads / 32) - 1) / (kThreads / 32));
     if (dtype == XC_F32)
         confmat_compact_fast_kernel<float><<<grid, kThreads, 0, st>>>((const float *)y_true, ld, pred_idx, k, n, tp, fp);
     else
