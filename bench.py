@@ -270,6 +270,7 @@ def main():
         y_np = host.numpy()
         comm.barrier()
         torch.cuda.synchronize(device)
+        os.environ["XCOLUMNS_B200_TIMING"] = "1" if os.environ.get("BENCH_E2E_PHASES") else "0"
         t0 = time.time()
         pred, meta = predict_optimizing_macro_f1_score_using_bc(
             y_np, k, seed=0, mode="batched", max_iters=args.steps, tolerance=-np.inf, return_meta=True,
@@ -283,7 +284,7 @@ def main():
         line["e2e"] = {"value": n_global * meta["iters"] / dt, "unit": "instances/s",
                        "h2d_bytes_per_step": n * m * 4 / meta["iters"],
                        "d2h_bytes_per_step": n * k * 4 / meta["iters"],
-                       "seconds_per_call": dt, "sweeps_per_call": meta["iters"],
+                       "seconds_per_call": dt, "sweeps_per_call": meta["iters"], "phases_s": meta.get("timings"),
                        "what": "predict_optimizing_macro_f1_score_using_bc(numpy pinned host array) -> dense numpy y_pred"}
         assert pred.shape == (n, m)
         del pred

@@ -108,6 +108,14 @@ XC_API int xc_scatter_pred_dense(xc_ctx *ctx, const int32_t *pred_idx, const voi
                                  int val_dtype, int k, int64_t n_rows, void *out, int out_dtype,
                                  int64_t ld_out, void *stream);
 
+/* HOST helper (all pointers are host pointers): writes the dense n x m prediction matrix the
+ * reference returns for dense inputs (weighted_prediction.py:35,47; block_coordinate.py:191-198)
+ * from a compact prediction, zero-filling and scattering with `nthreads` host threads
+ * (0 = hardware concurrency, at most 32).  val_host may be NULL (ones).                       */
+XC_API int xc_fill_pred_dense_host(void *out_host, int out_dtype, int64_t n, int64_t m, int64_t ld,
+                                   const int32_t *idx_host, const void *val_host, int val_dtype,
+                                   int k, int nthreads);
+
 /* ---- label-wise confusion sums -------------------------------------------------------- */
 /* ref: confusion_matrix.py:160-202, :364-399 (calculate_confusion_matrix), dense x dense.
  * axis 0: tp/fp/fn have m entries; axis 1: n entries.  Products are formed in the input
@@ -179,10 +187,13 @@ XC_API int xc_cov_state_csr(xc_ctx *ctx, const void *data, int dtype, const int3
  * ref: block_coordinate.py:158-185 evaluated against a frozen state.                        */
 XC_API int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
                        double *dtp, double *dfp, double *dfn, int64_t m, float *coef_n,
-                       float *coef_s, void *stream);
+                       float *coef_s, void *stream);   /* coef_*: xc_bca_coef_len(m) float2 each */
+/* Number of float2 entries coef_n / coef_s must provide for m labels (m rounded up to whole
+ * coefficient tiles of the TMA-pipelined kernel; entries past m are never used for a gain).    */
+XC_API int64_t xc_bca_coef_len(int64_t m);
 /* Rows one full wave of the dense batch kernel covers (SMs x resident CTAs x warps x rows per
  * warp): batches that are a multiple of it leave no partially filled last wave.               */
-XC_API int xc_bca_wave_rows(xc_ctx *ctx, int dtype);
+XC_API int xc_bca_wave_rows(xc_ctx *ctx, int dtype, int64_t m);
 /* One batch: rows[0..n_rows) stream past the frozen coefficients, every row re-selects its k
  * best labels (own contribution removed via coef_s), pred_idx rows are rewritten and the
  * confusion deltas of all changed rows are accumulated into dtp/dfp/dfn (float64 atomics). */

@@ -17,6 +17,7 @@ def _declarations():
     decls = {}
     for mobj in re.finditer(r"XC_API\s+([\w\s\*]+?)\s*\b(xc_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         ret, name, args = mobj.group(1).strip(), mobj.group(2), mobj.group(3)
+        ret = ret.replace("XC_API", "").strip()
         params = [a.strip() for a in args.replace("\n", " ").split(",")] if args.strip() != "void" else []
         decls[name] = (ret, params)
     return decls
@@ -66,7 +67,7 @@ def test_ctypes_prototypes_match_header():
             else:
                 assert t is want, f"{name}: {p!r} bound as {t}"
     bound = set(_lib._SIGNATURES) | {"xc_abi_version", "xc_strerror", "xc_ctx_create", "xc_ctx_destroy",
-                                     "xc_last_cuda_error", "xc_launch_count", "xc_sm_count"}
+                                     "xc_last_cuda_error", "xc_launch_count", "xc_sm_count", "xc_fill_pred_dense_host", "xc_bca_coef_len"}
     assert set(decls) == bound, f"unbound: {set(decls) - bound}, undeclared: {bound - set(decls)}"
 
 

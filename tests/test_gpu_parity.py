@@ -72,6 +72,24 @@ def test_topk_dense_vs_oracle(xb, oracle, n, m, k, dtype):
         assert (_idx(got, k) == oracle.topk_indices_dense(eta, k, kw.get("a"), kw.get("b"))[0]).all()
 
 
+@pytest.mark.parametrize("m", [24000, 70000])
+def test_topk_dense_wide_labels(xb, oracle, m):
+    """coefficient vectors beyond L1: the kernels switch to 2 / 4 rows per warp"""
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(70, m, seed=m, tie_free=False)
+    rng = np.random.default_rng(2)
+    a = (0.5 + rng.random(m)).astype(np.float32)
+    b = (0.05 * rng.standard_normal(m)).astype(np.float32)
+    got = xb.predict_weighted_per_instance(eta, 5, a=a, b=b)
+    want, vals = oracle.topk_indices_dense(eta, 5, a, b)
+    # ties in eta are allowed here; compare gains of the selection instead of ids on tied rows
+    gains = eta * a + b
+    same = (_idx(got, 5) == want).all(axis=1)
+    assert same.mean() > 0.95
+    for i in np.nonzero(~same)[0]:
+        assert np.array_equal(np.sort(gains[i][got[i] != 0]), np.sort(gains[i][want[i]]))
+
+
 def test_topk_ties_lowest_index(xb):
     eta = np.zeros((3, 40), dtype=np.float32)
     eta[1, 5:] = 0.5
@@ -261,6 +279,23 @@ def test_bca_batched_dense_vs_oracle(xb, oracle, metric):
     mid, c1, b2, eps = oracle.metric_params(metric)
     u = oracle._utility(mid, c1, b2, eps, tp, fp, fn, tn, eta.shape[0], "mean")
     assert abs(u - meta["utilities"][-1]) < 1e-9
+
+
+@pytest.mark.parametrize("n,m", [(640, 22000), (320, 66000)])
+def test_bca_batched_dense_wide_labels(xb, oracle, n, m):
+    """m * 8 bytes of coefficients beyond L1 -> 2 / 4 rows per warp in the batch kernel"""
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(n, m, seed=7 + m, tie_free=False)
+    opred, ometa = oracle.predict_using_bc_with_0approx(eta, "f1", 5, seed=0, skip_tn=True)
+    pred, meta = xb.predict_optimizing_macro_f1_score_using_bc(eta, 5, seed=0, return_meta=True, mode="batched",
+                                                               batch_size=max(1, n // 16))
+    tol = _tol_from_reference_spread(
+        lambda s: oracle.predict_using_bc_with_0approx(eta, "f1", 5, seed=s, skip_tn=True)[1]["utilities"][-1],
+        ometa["utilities"][-1])
+    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol
+    tp, fp, fn, tn = oracle.calculate_confusion_matrix(eta, pred, skip_tn=True, dtype=np.float64)
+    mid, c1, b2, eps = oracle.metric_params("f1")
+    assert abs(oracle._utility(mid, c1, b2, eps, tp, fp, fn, tn, n, "mean") - meta["utilities"][-1]) < 1e-9
 
 
 def test_bca_batched_csr_vs_oracle(xb, oracle):

@@ -170,27 +170,40 @@ def compact_to_dense_like(like, pred_idx: torch.Tensor, m: int, out_dtype=None, 
     if isinstance(like, torch.Tensor):
         dt = like.dtype if out_dtype is None else out_dtype
         if like.is_cuda:
-            out = torch.zeros((n, m), dtype=dt, device=like.device)
-            rows = torch.arange(n, device=like.device).unsqueeze(1).expand(n, k)
-            ok = pred_idx >= 0
-            src = torch.ones((), dtype=dt, device=like.device).expand(n, k) if vals is None else vals.to(dt)
-            out[rows[ok], pred_idx[ok].long()] = src[ok]
-            return out
+            out = torch.zeros((n, m), dtype=dt if dt in _T2CODE else torch.float32, device=like.device)
+            ctx = ctx_for(like.device)
+            ctx.call("xc_scatter_pred_dense", ptr(pred_idx), ptr(vals), 0 if vals is None else _T2CODE[vals.dtype],
+                     k, n, ptr(out), _T2CODE[out.dtype], m, stream_ptr(like.device))
+            return out if out.dtype == dt else out.to(dt)
         idx = pred_idx.cpu().numpy()
         v = None if vals is None else vals.cpu().numpy()
-        out = np.zeros((n, m), dtype=_T2NP.get(dt, np.float32))
+        out = np.empty((n, m), dtype=_T2NP.get(dt, np.float32))
         _scatter_host(out, idx, v)
         return torch.from_numpy(out).to(dt)
     dt = np.dtype(like.dtype if out_dtype is None else out_dtype)
     idx = pred_idx.cpu().numpy()
     v = None if vals is None else vals.cpu().numpy()
-    out = np.zeros((n, m), dtype=dt)
+    out = np.empty((n, m), dtype=dt)
     _scatter_host(out, idx, v)
     return out
 
 
 def _scatter_host(out: np.ndarray, idx: np.ndarray, vals: Optional[np.ndarray]):
+    """zero-fill + scatter on host threads (csrc/host.cu); `out` may be uninitialised memory"""
     n, k = idx.shape
+    lib = _lib.load()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    v = None
+    if vals is not None:
+        v = np.ascontiguousarray(vals, dtype=np.float64 if vals.dtype == np.float64 else np.float32)
+    if out.dtype in _NP2CODE and out.flags.c_contiguous:
+        rc = lib.xc_fill_pred_dense_host(out.ctypes.data, _NP2CODE[out.dtype], n, out.shape[1], out.shape[1],
+                                         idx.ctypes.data, None if v is None else v.ctypes.data,
+                                         0 if v is None else _NP2CODE[v.dtype], k, 0)
+        if rc != 0:
+            raise XColumnsB200Error(f"xc_fill_pred_dense_host failed ({rc})")
+        return
+    out[...] = 0
     rows = np.repeat(np.arange(n), k)
     flat = idx.reshape(-1)
     ok = flat >= 0

@@ -48,7 +48,7 @@ _SIGNATURES = {
     "xc_cov_exact_sweep_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _i64, _int, _dbl, _int, _vp, _vp, _vp],
     "xc_cov_state_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _int, _int, _vp, _vp],
     "xc_bca_coef": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
-    "xc_bca_wave_rows": [_int],
+    "xc_bca_wave_rows": [_int, _i64],
     "xc_bca_batch_dense": [_vp, _int, _i64, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_cov_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _dbl, _vp, _vp, _vp, _vp],
@@ -89,6 +89,11 @@ def load():
         lib.xc_launch_count.argtypes = [C.c_void_p]
         lib.xc_launch_count.restype = C.c_int64
         lib.xc_sm_count.argtypes = [C.c_void_p]
+        lib.xc_bca_coef_len.argtypes = [C.c_int64]
+        lib.xc_bca_coef_len.restype = C.c_int64
+        lib.xc_fill_pred_dense_host.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                                C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.xc_fill_pred_dense_host.restype = C.c_int
         for name, args in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = [C.c_void_p] + args

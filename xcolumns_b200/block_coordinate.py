@@ -104,8 +104,9 @@ class BcaSession:
         self.state[3].fill_(-1.0)
         self.delta = torch.zeros((3, self.m), **f64)           # pending batch deltas
         self.colsum: Optional[torch.Tensor] = None
-        self.coef_n = torch.empty((self.m, 2), dtype=torch.float32, device=self.device)
-        self.coef_s = torch.empty((self.m, 2), dtype=torch.float32, device=self.device)
+        clen = int(self.ctx.lib.xc_bca_coef_len(self.m))       # padded to whole coefficient tiles
+        self.coef_n = torch.zeros((clen, 2), dtype=torch.float32, device=self.device)
+        self.coef_s = torch.zeros((clen, 2), dtype=torch.float32, device=self.device)
         self.util_buf = torch.zeros(8, **f64)
         self.pred: Optional[torch.Tensor] = None
 
@@ -157,7 +158,7 @@ class BcaSession:
         """rows of one full wave of the dense batch kernel (0 for CSR: one warp per row)"""
         if self.is_csr:
             return 0
-        return int(self.ctx.lib.xc_bca_wave_rows(self.ctx.handle, self.data.code))
+        return int(self.ctx.lib.xc_bca_wave_rows(self.ctx.handle, self.data.code, self.m))
 
     def utility_device(self, slot: int) -> None:
         """block_coordinate.py:54-90 on the device; result lands in util_buf[slot]."""
@@ -304,10 +305,19 @@ def predict_using_bc_with_0approx(
     params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div_global)
     util_params = _metric_params(metric_id, 1.0, 1e-9, maximize, skip_tn, n_div_global)  # no kwargs (:63)
 
+    timing = os.environ.get("XCOLUMNS_B200_TIMING") == "1"
+
+    def _mark(name):
+        if timing:  # phase wall-clock (synchronising; diagnostics only)
+            torch.cuda.synchronize(device)
+            meta.setdefault("timings", {})[name] = time() - meta["time"]
+
+    _mark("h2d")
     sess = BcaSession(data, k, params, util_params, metric_aggregation, comm)
     sess.pred = _initial_pred(y_proba, data, init_y_pred, k, seed, device)
     meta["mode"] = mode
     meta["h2d_bytes"] = data.h2d_bytes
+    _mark("init")
 
     if mode == "exact":
         if comm.world > 1:
@@ -373,7 +383,9 @@ def predict_using_bc_with_0approx(
                 break
 
     meta["launches"] = sess.ctx.launches()
+    _mark("sweeps")
     y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format)
+    _mark("output")
     if return_meta:
         meta["time"] = time() - meta["time"]
         return y_pred, meta

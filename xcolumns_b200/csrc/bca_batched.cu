@@ -8,7 +8,10 @@
 // so the dense batch is ONE streaming pass: 16-byte loads of eta, one FMA per element, a
 // warp-distributed top-k list seeded with the row's current selection (which gives a tight
 // threshold from the first element on), then float64 atomic deltas for the rows that changed.
+#include <cstdlib>
+
 #include "xc_scan.cuh"
+#include "xc_tma.cuh"
 
 namespace {
 
@@ -384,6 +387,191 @@ cov_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
     }
 }
 
+// =================================================================================================
+// TMA-pipelined dense batch kernel (float32, 16-byte aligned rows).
+//
+// One CTA per SM, persistent over groups of 32 rows.  A producer warp streams the group's rows tile
+// by tile (512 columns = 2 KB per row, plus the 4 KB coefficient tile from L2) into a 3-stage
+// shared-memory ring with cp.async.bulk (TMA, 1-D) and mbarrier transaction counts; lane l of the
+// producer owns row l of the group.  Eight consumer warps own 4 rows each: they read the tile with
+// conflict-free LDS.128, reuse the coefficient chunk for their 4 rows, run the same
+// FMA / max / compare common path as the LDG kernel and touch the top-k lists only on a hit.
+// Up to 3 x 68 KB per SM are in flight regardless of what the consumer warps are doing, so a warp
+// that sits in the list-update slow path no longer stops the HBM stream.
+// =================================================================================================
+constexpr int TMA_NCW = 8;                      // consumer warps
+constexpr int TMA_RW = 4;                       // rows per consumer warp
+constexpr int TMA_ROWS = TMA_NCW * TMA_RW;      // rows per CTA pass (= producer lanes)
+constexpr int TMA_TC = 512;                     // columns per tile
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_ETA_BYTES = TMA_ROWS * TMA_TC * 4;
+constexpr int TMA_COEF_BYTES = TMA_TC * 8;
+constexpr int TMA_STAGE_BYTES = TMA_ETA_BYTES + TMA_COEF_BYTES;
+constexpr int TMA_SMEM_BYTES = TMA_STAGES * TMA_STAGE_BYTES + 2 * TMA_STAGES * 8;
+constexpr int TMA_NPW = 4;                      // producer warps (bulk-copy issue is serialised per warp)
+constexpr int TMA_PROWS = TMA_ROWS / TMA_NPW;   // rows each producer warp feeds
+constexpr int TMA_THREADS = (TMA_NCW + TMA_NPW) * 32;
+static_assert(TMA_PROWS <= 32, "one producer lane per row");
+
+// list update for one row: only elements that pass the threshold are broadcast
+template <bool SKIP>
+__device__ __forceinline__ void tma_insert4(WarpTopK<float> &tk, float g0, float g1, float g2, float g3, int cbase,
+                                            int k, int old_idx)
+{
+    const int lane = lane_id();
+    unsigned pm = (tk.passes(g0) ? 1u : 0u) | (tk.passes(g1) ? 2u : 0u) | (tk.passes(g2) ? 4u : 0u) |
+                  (tk.passes(g3) ? 8u : 0u);
+    unsigned bal = __ballot_sync(XC_FULL, pm != 0);
+    while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        unsigned em = __shfl_sync(XC_FULL, pm, src);
+        while (em) {
+            const int i = __ffs(em) - 1;
+            em &= em - 1;
+            const float mine = i == 0 ? g0 : (i == 1 ? g1 : (i == 2 ? g2 : g3));
+            const float gv = __shfl_sync(XC_FULL, mine, src);
+            const int j = cbase + src * 4 + i;
+            if (xc_better(gv, j, tk.thr, tk.thr_j)) {
+                if (SKIP) {
+                    if (__any_sync(XC_FULL, lane < k && old_idx == j)) continue;
+                }
+                tk.insert(gv, j, k);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+bca_batch_dense_tma_kernel(const float *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ rows,
+                           int64_t n_rows, int k, const float2 *__restrict__ coef_n,
+                           const float2 *__restrict__ coef_s, int32_t *__restrict__ pred_idx, double *dtp,
+                           double *dfp, double *dfn)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TMA_STAGES * TMA_STAGE_BYTES);
+    uint64_t *empty = full + TMA_STAGES;
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TMA_STAGES; ++s) {
+            mbar_init(full + s, TMA_NPW);
+            mbar_init(empty + s, TMA_NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t n_groups = (n_rows + TMA_ROWS - 1) / TMA_ROWS;
+    const int64_t mcopy = ((m + 3) / 4) * 4;  // <= ld (ld % 4 == 0): whole 16-byte units
+    const int n_tiles = (int)((mcopy + TMA_TC - 1) / TMA_TC);
+    uint32_t it = 0;  // running tile counter -> stage / phase
+
+    if (warp >= TMA_NCW) {
+        // ------------------------------ producers -----------------------------
+        const int pw = warp - TMA_NCW;
+        for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+            const int64_t i = g * TMA_ROWS + pw * TMA_PROWS + lane;
+            const bool valid = lane < TMA_PROWS && i < n_rows;
+            const int64_t row = valid ? (rows ? (int64_t)rows[i] : i) : 0;
+            const float *src_row = eta + row * ld;
+            const int nvalid = __popc(__ballot_sync(XC_FULL, valid));
+            for (int t = 0; t < n_tiles; ++t, ++it) {
+                const int s = it % TMA_STAGES;
+                const uint32_t ph = (it / TMA_STAGES) & 1u;
+                mbar_wait(empty + s, ph ^ 1u);  // slot free (first TMA_STAGES waits pass immediately)
+                const int64_t c0 = (int64_t)t * TMA_TC;
+                const int cols = (int)(mcopy - c0 < TMA_TC ? mcopy - c0 : TMA_TC);
+                uint8_t *st = smem + s * TMA_STAGE_BYTES;
+                if (lane == 0)
+                    mbar_arrive_expect_tx(full + s, (uint32_t)(nvalid * cols * 4 + (pw == 0 ? TMA_COEF_BYTES : 0)));
+                __syncwarp();
+                if (valid)
+                    bulk_g2s(st + (pw * TMA_PROWS + lane) * (TMA_TC * 4), src_row + c0, (uint32_t)(cols * 4), full + s);
+                if (pw == 0 && lane == 0) bulk_g2s(st + TMA_ETA_BYTES, coef_n + c0, TMA_COEF_BYTES, full + s);
+            }
+        }
+    } else {
+        // ------------------------------ consumers -----------------------------
+        const int w = warp;
+        for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+            int64_t row_id[TMA_RW];
+            const float *rp[TMA_RW];
+            int old_j[TMA_RW];
+            float old_e[TMA_RW];
+            WarpTopK<float> tk[TMA_RW];
+#pragma unroll
+            for (int r = 0; r < TMA_RW; ++r) {
+                const int64_t i = g * TMA_ROWS + w * TMA_RW + r;
+                const bool valid = i < n_rows;
+                const int64_t row = valid ? (rows ? (int64_t)rows[i] : i) : 0;
+                row_id[r] = valid ? row : -1;
+                rp[r] = eta + row * ld;
+                old_j[r] = -1;
+                old_e[r] = 0.f;
+                float gs = 0.f;
+                if (valid && lane < k) {
+                    old_j[r] = pred_idx[row * k + lane];
+                    if (old_j[r] >= 0) {
+                        old_e[r] = rp[r][old_j[r]];
+                        float2 cs = __ldg(coef_s + old_j[r]);
+                        gs = fmaf(cs.x, old_e[r], cs.y);
+                    }
+                }
+                seed_list(tk[r], gs, old_j[r], k);
+                if (!valid) tk[r].thr = INFINITY;  // nothing passes: the smem row is never written
+            }
+            for (int t = 0; t < n_tiles; ++t, ++it) {
+                const int s = it % TMA_STAGES;
+                const uint32_t ph = (it / TMA_STAGES) & 1u;
+                mbar_wait(full + s, ph);
+                const uint8_t *st = smem + s * TMA_STAGE_BYTES;
+                const float *se = reinterpret_cast<const float *>(st) + (w * TMA_RW) * TMA_TC;
+                const float2 *sc = reinterpret_cast<const float2 *>(st + TMA_ETA_BYTES);
+                const int64_t c0 = (int64_t)t * TMA_TC;
+                const bool edge = c0 + TMA_TC > m;  // tile reaches past the last label
+#pragma unroll
+                for (int c = 0; c < TMA_TC / 128; ++c) {
+                    const int colw = c * 128 + lane * 4;
+                    const int col = (int)c0 + colw;
+                    const float4 u = *reinterpret_cast<const float4 *>(sc + colw);
+                    const float4 v = *reinterpret_cast<const float4 *>(sc + colw + 2);
+                    float gq[TMA_RW][4];
+                    bool hit = false;
+#pragma unroll
+                    for (int r = 0; r < TMA_RW; ++r) {
+                        const float4 e = *reinterpret_cast<const float4 *>(se + r * TMA_TC + colw);
+                        gq[r][0] = fmaf(u.x, e.x, u.y);
+                        gq[r][1] = fmaf(u.z, e.y, u.w);
+                        gq[r][2] = fmaf(v.x, e.z, v.y);
+                        gq[r][3] = fmaf(v.z, e.w, v.w);
+                        if (edge) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (col + q >= m) gq[r][q] = NAN;
+                        }
+                        hit |= tk[r].passes(fmaxf(fmaxf(gq[r][0], gq[r][1]), fmaxf(gq[r][2], gq[r][3])));
+                    }
+                    if (__any_sync(XC_FULL, hit)) {
+#pragma unroll
+                        for (int r = 0; r < TMA_RW; ++r)
+                            tma_insert4<true>(tk[r], gq[r][0], gq[r][1], gq[r][2], gq[r][3], (int)c0 + c * 128, k,
+                                              old_j[r]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);  // this warp is done with the slot
+            }
+#pragma unroll
+            for (int r = 0; r < TMA_RW; ++r) {
+                if (row_id[r] >= 0)
+                    bca_commit_row<float>(rp[r], k, old_j[r], old_e[r], tk[r].idx, pred_idx + row_id[r] * k, dtp, dfp,
+                                          dfn);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) cov_fold_kernel(double *Ef, double *dEf, int64_t m)
 {
     int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -405,6 +593,54 @@ int grid_for(xc_ctx *ctx, K kernel, int64_t work_warps)
     return (int)(need < full ? need : full);
 }
 
+// Rows one warp streams at a time in the LDG kernel.  Measured on B200 at m = 13 000 (profiles/
+// r01_notes.md): R = 1 -> 2.67 ms / sweep (0.91 of the measured HBM peak, 40 warps / SM), R = 2 ->
+// 2.91 ms, R = 4 -> 2.85 ms: with the 8 m-byte coefficient vector resident in L1, more independent
+// warps hide the list-update slow path and the per-row seed/commit latency better than register
+// reuse of the coefficients does.  Wider label spaces, whose coefficients no longer fit L1, reuse
+// them for 2 / 4 rows.  $XCOLUMNS_B200_DENSE_R overrides.
+int dense_rows_per_warp(int64_t m)
+{
+    static int force_r = -1;
+    if (force_r < 0) {
+        const char *e = getenv("XCOLUMNS_B200_DENSE_R");
+        force_r = e ? atoi(e) : 0;
+    }
+    if (force_r == 1 || force_r == 2 || force_r == 4) return force_r;
+    if (m * 8 <= 160 * 1024) return 1;
+    if (m * 8 <= 512 * 1024) return 2;
+    return 4;
+}
+
+// 0 = auto (LDG kernel), 1 = force the LDG kernel, 2 = force the TMA-ring kernel
+int dense_path_override()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("XCOLUMNS_B200_DENSE_PATH");
+        v = !e ? 0 : (e[0] == 'l' ? 1 : (e[0] == 't' ? 2 : 0));
+    }
+    return v;
+}
+
+int launch_batch_dense_tma(xc_ctx *ctx, const float *eta, int64_t m, int64_t ld, const int32_t *rows, int64_t n_rows,
+                           int k, const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp,
+                           double *dfp, double *dfn, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        XC_CUDA_TRY(ctx, cudaFuncSetAttribute(bca_batch_dense_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              TMA_SMEM_BYTES));
+        attr_set = true;
+    }
+    int64_t groups = (n_rows + TMA_ROWS - 1) / TMA_ROWS;
+    int grid = (int)(groups < ctx->sm_count ? groups : ctx->sm_count);
+    bca_batch_dense_tma_kernel<<<grid, TMA_THREADS, TMA_SMEM_BYTES, st>>>(
+        eta, m, ld, rows, n_rows, k, (const float2 *)coef_n, (const float2 *)coef_s, pred_idx, dtp, dfp, dfn);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
 template <typename TE>
 int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, const int32_t *rows, int64_t n_rows, int k,
                        const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
@@ -412,7 +648,16 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
 {
     constexpr int V = 16 / sizeof(TE);
     bool vec_ok = xc_aligned16(eta) && (ld % V == 0) && xc_aligned16(coef_n);
-    int64_t warps_full = (int64_t)ctx->sm_count * 16;
+    if (sizeof(TE) == 4 && vec_ok && dense_path_override() != 1) {
+        // the coefficient tile is copied in whole TMA_TC units: needs the padded coefficient
+        // arrays the host shim allocates (xc_bca_coef_len)
+        // Measured (profiles/r01_notes.md): the TMA ring keeps 200 KB / SM in flight but its 8
+        // lock-stepped consumer warps expose the per-group seed/commit latency: 3.05 ms / sweep vs
+        // 2.67 ms for the 40-warp LDG kernel.  It therefore stays opt-in.
+        if (dense_path_override() == 2)
+            return launch_batch_dense_tma(ctx, (const float *)eta, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx,
+                                          dtp, dfp, dfn, st);
+    }
 #define XC_GO(R)                                                                                              \
     {                                                                                                         \
         auto kern = bca_batch_dense_kernel<TE, R>;                                                            \
@@ -420,8 +665,9 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, m, ld, rows, n_rows, k, (const float2 *)coef_n,      \
                                         (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok);             \
     }
-    if (n_rows >= warps_full * 4) XC_GO(4)
-    else if (n_rows >= warps_full * 2) XC_GO(2)
+    const int rr = dense_rows_per_warp(m);
+    if (rr == 4) XC_GO(4)
+    else if (rr == 2) XC_GO(2)
     else XC_GO(1)
 #undef XC_GO
     XC_LAUNCHED(ctx);
@@ -430,15 +676,21 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
 
 }  // namespace
 
-extern "C" int xc_bca_wave_rows(xc_ctx *ctx, int dtype)
+extern "C" int64_t xc_bca_coef_len(int64_t m) { return ((m + TMA_TC - 1) / TMA_TC) * TMA_TC; }
+
+extern "C" int xc_bca_wave_rows(xc_ctx *ctx, int dtype, int64_t m)
 {
     if (!ctx) return XC_ERR_INVALID;
+    if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
+    if (dtype == XC_F32 && dense_path_override() == 2) return ctx->sm_count * TMA_ROWS;
+    const int rr = dense_rows_per_warp(m);
     int per_sm = 0;
-    if (dtype == XC_F32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bca_batch_dense_kernel<float, 4>, kThreads, 0);
-    else if (dtype == XC_F64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bca_batch_dense_kernel<double, 4>, kThreads, 0);
-    else return XC_ERR_UNSUPPORTED;
+#define XC_OCC(TE, R) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bca_batch_dense_kernel<TE, R>, kThreads, 0)
+    if (dtype == XC_F32) { if (rr == 4) XC_OCC(float, 4); else if (rr == 2) XC_OCC(float, 2); else XC_OCC(float, 1); }
+    else { if (rr == 4) XC_OCC(double, 4); else if (rr == 2) XC_OCC(double, 2); else XC_OCC(double, 1); }
+#undef XC_OCC
     if (per_sm < 1) per_sm = 1;
-    return ctx->sm_count * per_sm * (kThreads / 32) * 4;
+    return ctx->sm_count * per_sm * (kThreads / 32) * rr;
 }
 
 extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn, double *dtp,

@@ -305,7 +305,8 @@ int launch_fw_dense(xc_ctx *ctx, const void *eta, int64_t n, int64_t m, int64_t 
     constexpr int V = 16 / sizeof(TE);
     bool vec_ok = xc_aligned16(eta) && (ld % V == 0);
     XfMulAdd<TE> xf{(const TE *)a, (const TE *)b};
-    int64_t warps_full = (int64_t)ctx->sm_count * 16;
+    const int64_t coef_bytes = 2 * m * (int64_t)sizeof(TE);
+    const int rr = coef_bytes <= 160 * 1024 ? 1 : (coef_bytes <= 512 * 1024 ? 2 : 4);
 #define XC_GO(R)                                                                                             \
     {                                                                                                        \
         auto kern = fw_iterate_dense_kernel<TE, R>;                                                          \
@@ -313,8 +314,8 @@ int launch_fw_dense(xc_ctx *ctx, const void *eta, int64_t n, int64_t m, int64_t 
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true, xf, k, tp,   \
                                         cnt, pred_idx, vec_ok);                                              \
     }
-    if (n >= warps_full * 4) XC_GO(4)
-    else if (n >= warps_full * 2) XC_GO(2)
+    if (rr == 4) XC_GO(4)
+    else if (rr == 2) XC_GO(2)
     else XC_GO(1)
 #undef XC_GO
     XC_LAUNCHED(ctx);

@@ -123,12 +123,15 @@ int launch_topk_dense(xc_ctx *ctx, const void *eta, int64_t n_rows, int64_t m, i
     bool vec_ok = xc_aligned16(eta) && (ld % V == 0);
     XfMulAdd<G> xf{(const G *)a, (const G *)b};
     // R rows per warp amortise the coefficient loads; small problems use R = 1 to fill the GPU
-    int64_t warps_full = (int64_t)ctx->sm_count * 16;
-    if (n_rows >= warps_full * 4) {
+    // one row per warp unless wide coefficient vectors (a / b beyond L1) make register reuse pay;
+        // see dense_rows_per_warp in bca_batched.cu for the measurement
+    const int64_t coef_bytes = ((a ? 1 : 0) + (b ? 1 : 0)) * m * (int64_t)sizeof(G);
+    const int rr = coef_bytes <= 160 * 1024 ? 1 : (coef_bytes <= 512 * 1024 ? 2 : 4);
+    if (rr == 4) {
         auto kern = topk_dense_kernel<TE, G, 4>;
         int grid = grid_for(ctx, kern, (n_rows + 3) / 4);
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows, xf, k, out_idx, (G *)out_val, vec_ok);
-    } else if (n_rows >= warps_full * 2) {
+    } else if (rr == 2) {
         auto kern = topk_dense_kernel<TE, G, 2>;
         int grid = grid_for(ctx, kern, (n_rows + 1) / 2);
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows, xf, k, out_idx, (G *)out_val, vec_ok);
