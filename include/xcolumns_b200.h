@@ -246,14 +246,38 @@ XC_API int xc_fw_metric_grad(xc_ctx *ctx, const xc_metric_params *p, const doubl
 /* ref: frank_wolfe.py:379-404 + utils.py:174-184 (uniform_search): evaluates the metric of
  * (1-alpha) C + alpha Ci at alpha = 0 and at alphas_dev[0..n_alphas) (the host builds the grid
  * with numpy.arange so the grid points are bit-identical), keeps the FIRST strict maximum.
- * vals_dev: scratch of n_alphas + 1 doubles; result_dev[0] = alpha, result_dev[1] = value.    */
+ * For the c*tp/D metrics a float32 pass over the whole grid pre-selects the points that can be
+ * the float64 maximum; those are re-evaluated with the reference's float64 expression.
+ * scratch_dev: xc_fw_alpha_scratch_bytes(m, n_alphas) bytes; result_dev[0] = alpha, [1] = value. */
+XC_API int64_t xc_fw_alpha_scratch_bytes(int64_t m, int64_t n_alphas);
 XC_API int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const double *C,
                               const double *Ci, int64_t m, const double *alphas_dev,
-                              int64_t n_alphas, double *vals_dev, double *result_dev,
+                              int64_t n_alphas, double *scratch_dev, double *result_dev,
                               void *stream);
 /* C = (1 - alpha) C + alpha Ci on the 4 stacked m-vectors, alpha read from device memory */
 XC_API int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4,
                          const double *alpha_dev, void *stream);
+
+/* One dense Frank-Wolfe iteration as two calls (ref: frank_wolfe.py:589-637); between them the
+ * caller all-reduces raw[0..2m) when rows are sharded over ranks.
+ *   begin : have_grad != 0: scal[0] = metric(Cm) and (a_row, b_row) = next classifier from the
+ *           gradient (float32 rows, e.g. row i of the classifier matrices); then the fused
+ *           weighted top-k + accumulation of raw = [tp, cnt].  ab64: 2*m doubles, used when
+ *           dtype == XC_F64 (the float32 rows are widened like numpy promotes them).
+ *   finish: first != 0: Cm = confusion vectors of classifier 0, scal[0] = metric(Cm).  Otherwise
+ *           Ci = confusion vectors of classifier i, scal[1] = metric(Ci), scal[2..3] = line search
+ *           (alphas_dev != NULL) or the fixed step (alpha passed in fixed_alpha), Cm = (1-a) Cm + a Ci,
+ *           scal[4] = metric(Cm).  The fixed-step path copies from host memory synchronously
+ *           with respect to `stream` ordering only.                                              */
+XC_API int xc_fw_step_begin(xc_ctx *ctx, const xc_metric_params *p, int have_grad, const void *eta,
+                            int dtype, int64_t n, int64_t m, int64_t ld, const void *y_true,
+                            int64_t ld_true, const double *Cm, float *a_row, float *b_row,
+                            double *ab64, int k, double *raw, double *scal, void *stream);
+XC_API int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int first, const double *raw,
+                             const double *colsum, int64_t m, double n_global, int normalize,
+                             int skip_tn, double *Cm, double *Ci, const double *alphas_dev,
+                             int64_t n_alphas, double fixed_alpha, double *scratch_dev, double *scal,
+                             void *stream);
 
 #ifdef __cplusplus
 }

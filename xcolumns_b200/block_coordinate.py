@@ -365,21 +365,44 @@ def predict_using_bc_with_0approx(
         sess.recompute(XC_SUM_FAST)
         sess.utility_device(0)
         meta["batch_size"] = batch
-        for j in range(1, max_iters + 1):
-            log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+        # Sweep j+1 is enqueued before sweep j's utilities are read on the host, so the GPU queue
+        # never drains at the stopping test; if sweep j was the last one the prediction saved
+        # before the speculative sweep is restored.
+        util_dev = torch.zeros((max_iters + 2, 2), dtype=torch.float64, device=device)
+        util_host = torch.zeros((max_iters + 2, 2), dtype=torch.float64).pin_memory()
+        events, saved = {}, {}
+
+        def enqueue(j):
+            nonlocal order_dev
+            saved[j] = sess.pred.clone()
             if shuffle_order:
                 order_dev = torch.randperm(n_order, generator=gen, device=device, dtype=torch.int32)
             sess.delta.zero_()
             sess.sweep_batched(order_dev, batch, n_batches)
             sess.recompute(XC_SUM_FAST)
             sess.utility_device(1)
-            old_u, new_u = (float(v) for v in sess.util_buf[:2].cpu())
+            util_dev[j].copy_(sess.util_buf[:2])
             sess.util_buf[0] = sess.util_buf[1]
+            util_host[j].copy_(util_dev[j], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            events[j] = ev
+
+        enqueue(1)
+        for j in range(1, max_iters + 1):
+            log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+            if j + 1 <= max_iters:
+                enqueue(j + 1)
+            events[j].synchronize()
+            old_u, new_u = (float(v) for v in util_host[j])
+            saved.pop(j, None)
             meta["iters"] = j
             meta["utilities"].append(new_u)
             log_info(f"    Iteration {j}/{max_iters} finished, expected metric value: {old_u} -> {new_u}", verbose)
             if (maximize and new_u - old_u < tolerance) or (not maximize and new_u - old_u > tolerance):
                 log_info(f"  Stopping because improvement of expected metric value is smaller than {tolerance}", verbose)
+                if j + 1 in saved:
+                    sess.pred = saved[j + 1]      # undo the speculative sweep
                 break
 
     meta["launches"] = sess.ctx.launches()

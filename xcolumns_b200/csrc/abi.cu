@@ -39,6 +39,14 @@ extern "C" int xc_ctx_create(int device, xc_ctx **out)
         return XC_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->red_partials = nullptr;
+    ctx->red_counter = nullptr;
+    cudaSetDevice(device);
+    if (cudaMalloc(&ctx->red_partials, sizeof(double) * XC_RED_MAX_BLOCKS) != cudaSuccess ||
+        cudaMalloc(&ctx->red_counter, 64) != cudaSuccess || cudaMemset(ctx->red_counter, 0, 64) != cudaSuccess) {
+        delete ctx;
+        return XC_ERR_CUDA;
+    }
     *out = ctx;
     return XC_OK;
 }
@@ -47,6 +55,8 @@ extern "C" void xc_ctx_destroy(xc_ctx *ctx)
 {
     if (!ctx) return;
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->red_partials) cudaFree(ctx->red_partials);
+    if (ctx->red_counter) cudaFree(ctx->red_counter);
     delete ctx;
 }
 

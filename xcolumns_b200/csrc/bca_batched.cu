@@ -584,13 +584,21 @@ __global__ void __launch_bounds__(kThreads) cov_fold_kernel(double *Ef, double *
 template <typename K>
 int grid_for(xc_ctx *ctx, K kernel, int64_t work_warps)
 {
+    // Balanced persistent grid: every warp gets the same number of row tasks (+-1).  With W warps
+    // resident per full wave and T tasks, waves = ceil(T / W) and only ceil(T / waves) warps are
+    // launched, spread evenly over the SMs -- instead of a full first wave and a mostly empty last
+    // one (T = 1.48 W used to cost two full task times).
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (per_sm < 1) per_sm = 1;
-    int64_t full = (int64_t)ctx->sm_count * per_sm;
-    int64_t need = (work_warps + (kThreads / 32) - 1) / (kThreads / 32);
-    if (need < 1) need = 1;
-    return (int)(need < full ? need : full);
+    const int wpc = kThreads / 32;
+    const int64_t full_warps = (int64_t)ctx->sm_count * per_sm * wpc;
+    if (work_warps < 1) work_warps = 1;
+    const int64_t waves = (work_warps + full_warps - 1) / full_warps;
+    const int64_t warps = (work_warps + waves - 1) / waves;
+    int64_t grid = (warps + wpc - 1) / wpc;
+    const int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    return (int)(grid < cap ? grid : cap);
 }
 
 // Rows one warp streams at a time in the LDG kernel.  Measured on B200 at m = 13 000 (profiles/

@@ -348,13 +348,13 @@ confmat_csrc_ordered_kernel(const T *t_data, const int32_t *t_idx, const int64_t
 }
 
 // ---- utility: mean / sum over labels of the binary metric, fixed reduction order -----------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 utility_kernel(xc_metric_params p, int agg, const double *tp, const double *fp, const double *fn, const double *tn,
-               int64_t m, double *out)
+               int64_t m, double *out, double *partials, unsigned *counter)
 {
-    __shared__ double sm[32];
+    __shared__ double sm[8];
     double s = 0.0;
-    for (int64_t j = threadIdx.x; j < m; j += 1024) {
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += (int64_t)gridDim.x * 256) {
         double t4 = tn ? tn[j] : -1.0;
         s += xc_binary_metric(p.metric, tp[j] / p.n_div, fp[j] / p.n_div, fn[j] / p.n_div, t4 / p.n_div, p.c1,
                               p.beta2, p.eps);
@@ -362,11 +362,11 @@ utility_kernel(xc_metric_params p, int agg, const double *tp, const double *fp, 
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = sm[threadIdx.x];
-        v = warp_sum(v);
-        if (threadIdx.x == 0) *out = agg == 0 ? v / (double)m : v;
-    }
+    double bsum = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) bsum += sm[w];
+    double total;
+    if (xc_grid_sum_last(bsum, partials, counter, &total)) *out = agg == 0 ? total / (double)m : total;
 }
 
 inline int cap_grid(xc_ctx *ctx, int64_t blocks, int per_sm = 16)
@@ -550,7 +550,11 @@ extern "C" int xc_utility(xc_ctx *ctx, const xc_metric_params *p, int agg, const
 {
     if (!ctx || !p || !tp || !fp || !fn || !out_dev || m <= 0) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
-    utility_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*p, agg, tp, fp, fn, tn, m, out_dev);
+    int64_t blocks = (m + 255) / 256;
+    int grid = (int)(blocks < XC_RED_MAX_BLOCKS ? blocks : XC_RED_MAX_BLOCKS);
+    if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+    utility_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, agg, tp, fp, fn, tn, m, out_dev, ctx->red_partials,
+                                                            ctx->red_counter);
     XC_LAUNCHED(ctx);
     return XC_OK;
 }

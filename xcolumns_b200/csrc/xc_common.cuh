@@ -14,7 +14,12 @@ struct xc_ctx {
     void *scratch;
     size_t scratch_bytes;
     int coop_blocks_cache[8];
+    // scratch of the deterministic multi-block reductions (block partials + ticket counter)
+    double *red_partials;
+    unsigned *red_counter;
 };
+
+constexpr int XC_RED_MAX_BLOCKS = 1024;
 
 #define XC_FULL 0xffffffffu
 
@@ -141,6 +146,37 @@ __device__ __forceinline__ int warp_sort_labels(int idx, int k)
         if (lane == t) out = v;
     }
     return out;
+}
+
+// Deterministic grid-wide sum: every block stores its partial, the block that draws the last ticket
+// adds the partials in block order (fixed order -> bit-reproducible) and re-arms the counter.
+// Returns true in thread 0 of that last block with the total in *total.
+__device__ __forceinline__ bool xc_grid_sum_last(double block_partial, double *partials, unsigned *counter,
+                                                 double *total)
+{
+    __shared__ bool s_last;
+    __shared__ double s_total;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = block_partial;
+        __threadfence();
+        unsigned t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    if (threadIdx.x < 32) {
+        double v = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) v += __ldcg(partials + b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(XC_FULL, v, o);
+        if (threadIdx.x == 0) {
+            s_total = v;
+            *counter = 0;
+        }
+    }
+    __syncthreads();
+    *total = s_total;
+    return threadIdx.x == 0;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
