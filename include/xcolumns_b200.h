@@ -71,6 +71,7 @@ typedef struct {
     double beta2;      /* beta**2                                                              */
     double eps;        /* epsilon of the metric (metric_kwargs["epsilon"], default 1e-9)       */
     double n_div;      /* n if normalize_conf_matrix else 1 (ref: block_coordinate.py:149-151) */
+    double n_rows;     /* number of instances (all ranks), whatever the normalisation           */
 } xc_metric_params;
 
 /* ---- context -------------------------------------------------------------------------- */
@@ -160,13 +161,20 @@ XC_API int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype, int
                                     int64_t ld, const int32_t *order, int64_t n_order, int k,
                                     const xc_metric_params *p, int greedy, int32_t *pred_idx,
                                     double *tp, double *fp, double *fn, double *tn, void *stream);
+/* k == 0 (no budget, ref: block_coordinate.py:199-200): every label with gain >= 0 is predicted.
+ * pred is a dense [n, ld_pred] 0/1 matrix of eta's dtype, updated in place.                     */
+XC_API int xc_bca_exact_sweep_dense_k0(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m,
+                                       int64_t ld, const int32_t *order, int64_t n_order,
+                                       const xc_metric_params *p, int greedy, void *pred,
+                                       int64_t ld_pred, double *tp, double *fp, double *fn,
+                                       double *tn, void *stream);
 /* ref: block_coordinate.py:212-293 (_bc_with_0approx_step_csr) + numba_csr_functions.py
- * :386-452, :456-466, :500-546.  skip_tn metrics only.                                       */
+ * :386-452, :456-466, :500-546.  tn may be NULL when p->skip_tn.                              */
 XC_API int xc_bca_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
                                   const int64_t *indptr, int64_t n, int64_t m,
                                   const int32_t *order, int64_t n_order, int k,
                                   const xc_metric_params *p, int greedy, int32_t *pred_idx,
-                                  double *tp, double *fp, double *fn, void *stream);
+                                  double *tp, double *fp, double *fn, double *tn, void *stream);
 /* ref: block_coordinate.py:539-580 (_bc_for_coverage_step_csr); Ef updated in place */
 XC_API int xc_cov_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
                                   const int64_t *indptr, int64_t n, int64_t m,
@@ -188,6 +196,8 @@ XC_API int xc_cov_state_csr(xc_ctx *ctx, const void *data, int dtype, const int3
 XC_API int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
                        double *dtp, double *dfp, double *dfn, int64_t m, float *coef_n,
                        float *coef_s, void *stream);   /* coef_*: xc_bca_coef_len(m) float2 each */
+/* affine-gain metrics: precision, recall, F-beta and balanced accuracy (for the latter tp + fn and
+ * tn + fp are prediction-independent column sums, so the gain is state-free like recall's)      */
 /* Number of float2 entries coef_n / coef_s must provide for m labels (m rounded up to whole
  * coefficient tiles of the TMA-pipelined kernel; entries past m are never used for a gain).    */
 XC_API int64_t xc_bca_coef_len(int64_t m);

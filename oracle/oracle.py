@@ -263,8 +263,6 @@ def predict_using_bc_with_0approx(y_proba, metric: str, k: int, metric_aggregati
     if is_csr:
         if k <= 0:
             raise NotImplementedError("oracle: CSR BCA needs k > 0")
-        if not skip_tn and mid in USES_TN:
-            raise NotImplementedError("oracle: CSR BCA carries tn only with skip_tn")
         data = np.ascontiguousarray(y_proba.data)
         indices = np.ascontiguousarray(y_proba.indices, dtype=np.int32)
         indptr = y_proba.indptr.astype(np.int64)
@@ -337,7 +335,7 @@ def predict_using_bc_with_0approx(y_proba, metric: str, k: int, metric_aggregati
                 _p(plen), _p(order64), C.c_int64(order64.size), C.c_int(k), C.c_int(mid),
                 C.c_double(c1), C.c_double(b2), C.c_double(eps), C.c_double(n_div),
                 C.c_int(int(maximize)), C.c_int(int(greedy)), _p(tp), _p(fp), _p(fn),
-                C.c_double(-1.0))
+                None if skip_tn else _p(tn), C.c_double(-1.0))
         else:
             rc = getattr(lib(), "orc_bca_dense_sweep_" + sfx)(
                 _p(eta), C.c_int64(n), C.c_int64(m), C.c_int64(m), _p(pred), _p(order64),

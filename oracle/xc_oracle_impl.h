@@ -328,13 +328,15 @@ int FN(orc_bca_dense_sweep)(const T *eta, int64_t n, int64_t m, int64_t ld, uint
  * numba_csr_functions.py:386-452 (sub/add), :456-466 (top-k of the stored entries),
  * :500-546 (row replace).  pred is n x k label ids per row, ascending, with
  * pred_len[i] <= k valid entries (rows with nnz_i < k keep all nnz_i labels, :465-466).
- * Prediction values are all 1 (T).  skip_tn only (tn is carried untouched).
+ * Prediction values are all 1 (T).  tn == NULL means skip_tn (tn_const is passed to the metric);
+ * otherwise tn is updated literally like numba does: +-1 on ALL m labels, then the three products
+ * on the touched ones (numba_csr_functions.py:413-417, :448-452).
  * --------------------------------------------------------------------------------- */
 int FN(orc_bca_csr_sweep)(const T *data, const int32_t *indices, const int64_t *indptr,
                           int64_t n, int64_t m, int32_t *pred_idx, int32_t *pred_len,
                           const int64_t *order, int64_t n_order, int k, int metric, double c1,
                           double beta2, double eps, double n_div, int maximize, int greedy,
-                          double *tp, double *fp, double *fn, double tn_const)
+                          double *tp, double *fp, double *fn, double *tn, double tn_const)
 {
     (void)n; (void)m;
     int64_t cap = 0;
@@ -358,22 +360,35 @@ int FN(orc_bca_csr_sweep)(const T *data, const int32_t *indices, const int64_t *
                 double sgn = pass == 0 ? -1.0 : 1.0;
                 int np_ = pred_len[i];
                 int64_t x = 0, y = ts;
+                if (tn) for (int64_t j = 0; j < m; ++j) tn[j] += sgn;   /* tn -= 1 / tn += 1 on every label */
                 while (x < np_ && y < te) { /* tp on the intersection */
                     if (pi[x] < indices[y]) ++x;
-                    else if (pi[x] == indices[y]) { tp[pi[x]] += sgn * (double)FN(orc_mul_round)(one, data[y]); ++x; ++y; }
+                    else if (pi[x] == indices[y]) {
+                        double v = (double)FN(orc_mul_round)(one, data[y]);
+                        tp[pi[x]] += sgn * v;
+                        if (tn) tn[pi[x]] -= sgn * v;
+                        ++x; ++y;
+                    }
                     else ++y;
                 }
                 x = 0; y = ts;
                 while (x < np_) { /* fp over pred entries */
-                    if (y >= te || pi[x] < indices[y]) { fp[pi[x]] += sgn * (double)one; ++x; }
-                    else if (pi[x] == indices[y]) { fp[pi[x]] += sgn * (double)FN(orc_mul_om_round)(one, data[y]); ++x; ++y; }
+                    if (y >= te || pi[x] < indices[y]) { fp[pi[x]] += sgn * (double)one; if (tn) tn[pi[x]] -= sgn * (double)one; ++x; }
+                    else if (pi[x] == indices[y]) {
+                        double v = (double)FN(orc_mul_om_round)(one, data[y]);
+                        fp[pi[x]] += sgn * v;
+                        if (tn) tn[pi[x]] -= sgn * v;
+                        ++x; ++y;
+                    }
                     else ++y;
                 }
                 y = 0;
                 for (int64_t q = ts; q < te; ++q) { /* fn over true entries */
                     while (y < np_ && pi[y] < indices[q]) ++y;
-                    if (y < np_ && pi[y] == indices[q]) fn[indices[q]] += sgn * (double)FN(orc_mul_om_round)(data[q], one);
-                    else fn[indices[q]] += sgn * (double)data[q];
+                    double v = (y < np_ && pi[y] == indices[q]) ? (double)FN(orc_mul_om_round)(data[q], one)
+                                                                : (double)data[q];
+                    fn[indices[q]] += sgn * v;
+                    if (tn) tn[indices[q]] -= sgn * v;
                 }
             }
             if (pass == 1) break;
@@ -387,8 +402,14 @@ int FN(orc_bca_csr_sweep)(const T *data, const int32_t *indices, const int64_t *
                 double pos_fpp = (neg_fp + (double)om) / n_div;
                 double neg_fnn = (pos_fn + (double)t) / n_div;
                 neg_tp /= n_div; neg_fp /= n_div; pos_fn /= n_div;
-                double up = orc_binary_metric(metric, pos_tpp, pos_fpp, pos_fn, tn_const, c1, beta2, eps);
-                double un = orc_binary_metric(metric, neg_tp, neg_fp, neg_fnn, tn_const, c1, beta2, eps);
+                double pos_tn = tn_const, neg_tnn = tn_const;   /* block_coordinate.py:260-264 */
+                if (tn) {
+                    pos_tn = tn[j];
+                    neg_tnn = (pos_tn + (double)om) / n_div;
+                    pos_tn /= n_div;
+                }
+                double up = orc_binary_metric(metric, pos_tpp, pos_fpp, pos_fn, pos_tn, c1, beta2, eps);
+                double un = orc_binary_metric(metric, neg_tp, neg_fp, neg_fnn, neg_tnn, c1, beta2, eps);
                 double gain = up - un;
                 g[q] = maximize ? gain : -gain;
             }

@@ -168,6 +168,8 @@ def main():
     run_bc("jaccard", ycsr, mt.binary_jaccard_score_on_conf_matrix, 3, seed=2, skip_tn=True)
     y64 = csr_matrix((ycsr.data.astype(np.float64), ycsr.indices, ycsr.indptr), shape=ycsr.shape)
     run_bc("f1_f64", y64, mt.binary_f1_score_on_conf_matrix, 5, seed=0, skip_tn=True)
+    run_bc("balacc", ycsr, mt.binary_balanced_accuracy_on_conf_matrix, 5, seed=3, skip_tn=False)
+    run_bc("hmean", ycsr, mt.binary_hmean_on_conf_matrix, 5, seed=4, skip_tn=False)
     save("bca_csr", **out)
 
     # ---------------- coverage BCA (CSR) ----------------

@@ -73,7 +73,7 @@ def test_ctypes_prototypes_match_header():
 
 def test_metric_params_layout():
     from xcolumns_b200 import _lib
-    assert C.sizeof(_lib.MetricParams) == 48
+    assert C.sizeof(_lib.MetricParams) == 56
     assert _lib.MetricParams.c1.offset == 16 and _lib.MetricParams.n_div.offset == 40
 
 

@@ -219,6 +219,19 @@ def test_bca_exact_dense_golden(xb, golden, name, metric, k, kw):
     assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
 
 
+def test_bca_exact_dense_k0_golden(xb, golden, oracle):
+    """no budget (k = 0): every label with a non-negative gain is predicted"""
+    g = golden("bca_dense")
+    eta = g["eta"]
+    init = np.zeros_like(eta)
+    init[np.arange(eta.shape[0])[:, None], oracle.topk_indices_dense(eta, 3)[0]] = 1
+    pred, meta = xb.predict_using_bc_with_0approx(eta, _metric(xb, "f1"), 0, seed=13, skip_tn=True, init_y_pred=init,
+                                                  return_meta=True)
+    assert meta["mode"] == "exact" and type(pred) is np.ndarray and pred.dtype == eta.dtype
+    assert ((pred != 0).astype(np.uint8) == g["f1_k0_pred"]).all()
+    assert (np.array(meta["utilities"]) == g["f1_k0_util"]).all()
+
+
 @pytest.mark.parametrize("n,m,k", [(700, 513, 5), (257, 4100, 3), (2000, 1000, 5)])
 def test_bca_exact_dense_vs_oracle(xb, oracle, n, m, k):
     from xcolumns_b200.synth import dense_probs
@@ -229,15 +242,16 @@ def test_bca_exact_dense_vs_oracle(xb, oracle, n, m, k):
     assert meta["utilities"] == ometa["utilities"]
 
 
-BCA_CSR = [("f1", "f1", 5, 0), ("recall", "recall", 5, 1), ("jaccard", "jaccard", 3, 2), ("f1_f64", "f1", 5, 0)]
+BCA_CSR = [("f1", "f1", 5, 0, True), ("recall", "recall", 5, 1, True), ("jaccard", "jaccard", 3, 2, True),
+           ("f1_f64", "f1", 5, 0, True), ("balacc", "balanced_accuracy", 5, 3, False), ("hmean", "hmean", 5, 4, False)]
 
 
-@pytest.mark.parametrize("name,metric,k,seed", BCA_CSR, ids=[c[0] for c in BCA_CSR])
-def test_bca_exact_csr_golden(xb, golden, name, metric, k, seed):
+@pytest.mark.parametrize("name,metric,k,seed,skip_tn", BCA_CSR, ids=[c[0] for c in BCA_CSR])
+def test_bca_exact_csr_golden(xb, golden, name, metric, k, seed, skip_tn):
     g = golden("bca_csr")
     data = g["data"].astype(np.float64) if name.endswith("f64") else g["data"]
     y = csr_matrix((data, g["indices"], g["indptr"]), shape=tuple(g["shape"]))
-    pred, meta = xb.predict_using_bc_with_0approx(y, _metric(xb, metric), k, seed=seed, skip_tn=True,
+    pred, meta = xb.predict_using_bc_with_0approx(y, _metric(xb, metric), k, seed=seed, skip_tn=skip_tn,
                                                   return_meta=True, mode="exact")
     assert isinstance(pred, csr_matrix) and pred.dtype == y.dtype and pred.shape == y.shape
     assert pred.indices.dtype == y.indices.dtype and pred.indptr.dtype == y.indptr.dtype
@@ -258,24 +272,25 @@ def test_coverage_exact_csr_golden(xb, golden, name, kw):
 # BCA, batched block-Jacobi mode: utilities within 1e-4 of the sequential reference
 # ------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("metric", ["f1", "recall", "precision"])
+@pytest.mark.parametrize("metric", ["f1", "recall", "precision", "balanced_accuracy"])
 def test_bca_batched_dense_vs_oracle(xb, oracle, metric):
     from xcolumns_b200.synth import dense_probs
     eta = dense_probs(6000, 2000, seed=1002)
-    opred, ometa = oracle.predict_using_bc_with_0approx(eta, metric, 5, seed=0, skip_tn=True)
-    pred, meta = xb.predict_using_bc_with_0approx(eta, _metric(xb, metric), 5, seed=0, skip_tn=True,
+    skip = metric != "balanced_accuracy"
+    opred, ometa = oracle.predict_using_bc_with_0approx(eta, metric, 5, seed=0, skip_tn=skip)
+    pred, meta = xb.predict_using_bc_with_0approx(eta, _metric(xb, metric), 5, seed=0, skip_tn=skip,
                                                   return_meta=True, mode="batched")
     assert pred.shape == eta.shape and (pred.sum(1) == 5).all() and pred.dtype == eta.dtype
     # F1 / recall: the reference's seed-to-seed spread is < 1e-6 here, so tol = 1e-4;
     # macro-precision has many order-dependent fixed points (spread ~3e-4)
     tol = _tol_from_reference_spread(
-        lambda s: oracle.predict_using_bc_with_0approx(eta, metric, 5, seed=s, skip_tn=True)[1]["utilities"][-1],
+        lambda s: oracle.predict_using_bc_with_0approx(eta, metric, 5, seed=s, skip_tn=skip)[1]["utilities"][-1],
         ometa["utilities"][-1])
-    if metric in ("f1", "recall"):
+    if metric in ("f1", "recall", "balanced_accuracy"):
         assert tol == TOL
     assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol
     # the returned prediction really has the reported utility (recomputed by the oracle)
-    tp, fp, fn, tn = oracle.calculate_confusion_matrix(eta, pred, skip_tn=True, dtype=np.float64)
+    tp, fp, fn, tn = oracle.calculate_confusion_matrix(eta, pred, skip_tn=skip, dtype=np.float64)
     mid, c1, b2, eps = oracle.metric_params(metric)
     u = oracle._utility(mid, c1, b2, eps, tp, fp, fn, tn, eta.shape[0], "mean")
     assert abs(u - meta["utilities"][-1]) < 1e-9

@@ -99,15 +99,16 @@ def test_bca_dense_k0(golden, oracle):
     assert (np.array(meta["utilities"]) == g["f1_k0_util"]).all()
 
 
-BCA_CSR = [("f1", "f1", 5, 0), ("recall", "recall", 5, 1), ("jaccard", "jaccard", 3, 2), ("f1_f64", "f1", 5, 0)]
+BCA_CSR = [("f1", "f1", 5, 0, True), ("recall", "recall", 5, 1, True), ("jaccard", "jaccard", 3, 2, True),
+           ("f1_f64", "f1", 5, 0, True), ("balacc", "balanced_accuracy", 5, 3, False), ("hmean", "hmean", 5, 4, False)]
 
 
-@pytest.mark.parametrize("name,metric,k,seed", BCA_CSR, ids=[c[0] for c in BCA_CSR])
-def test_bca_csr(golden, oracle, name, metric, k, seed):
+@pytest.mark.parametrize("name,metric,k,seed,skip_tn", BCA_CSR, ids=[c[0] for c in BCA_CSR])
+def test_bca_csr(golden, oracle, name, metric, k, seed, skip_tn):
     g = golden("bca_csr")
     data = g["data"].astype(np.float64) if name.endswith("f64") else g["data"]
     y = csr_matrix((data, g["indices"], g["indptr"]), shape=tuple(g["shape"]))
-    pidx, meta = oracle.predict_using_bc_with_0approx(y, metric, k, seed=seed, skip_tn=True)
+    pidx, meta = oracle.predict_using_bc_with_0approx(y, metric, k, seed=seed, skip_tn=skip_tn)
     assert (pidx == g[name + "_pred"]).all()
     assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
 

@@ -24,7 +24,7 @@ class MetricParams(C.Structure):
     """Mirror of xc_metric_params."""
     _fields_ = [("metric", C.c_int32), ("maximize", C.c_int32), ("skip_tn", C.c_int32),
                 ("reserved", C.c_int32), ("c1", C.c_double), ("beta2", C.c_double),
-                ("eps", C.c_double), ("n_div", C.c_double)]
+                ("eps", C.c_double), ("n_div", C.c_double), ("n_rows", C.c_double)]
 
 
 _vp, _i32, _i64, _dbl, _int = C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int
@@ -44,7 +44,8 @@ _SIGNATURES = {
     "xc_colsum_csr": [_vp, _int, _vp, _i64, _i64, _vp, _vp],
     "xc_utility": [_MP, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "xc_bca_exact_sweep_dense": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _int, _MP, _int, _vp, _vp, _vp, _vp, _vp, _vp],
-    "xc_bca_exact_sweep_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _i64, _int, _MP, _int, _vp, _vp, _vp, _vp, _vp],
+    "xc_bca_exact_sweep_dense_k0": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _MP, _int, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "xc_bca_exact_sweep_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _i64, _int, _MP, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_cov_exact_sweep_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _i64, _int, _dbl, _int, _vp, _vp, _vp],
     "xc_cov_state_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _int, _int, _vp, _vp],
     "xc_bca_coef": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],

@@ -12,7 +12,8 @@ $XCOLUMNS_B200_MODE; the reference's ``**kwargs`` swallows the extra keyword):
              utilities agree with the reference within 1e-4 when batch <= n/8.
              With torch.distributed initialised and ``distributed=True`` every rank holds a row
              shard and the per-batch deltas are all-reduced (NCCL over NVLink).
-``auto``     (default) exact for n <= 20000 rows, batched above.
+``auto``     (default) exact for n <= 4096 rows (and whenever only the sequential kernels apply: greedy
+             init, k = 0, Jaccard / G-mean / H-mean), batched above.
 """
 from __future__ import annotations
 
@@ -33,20 +34,21 @@ from .types import DefaultAccDataDType, Matrix
 from .utils import add_kwargs_to_signature, log_info, log_warning
 from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
 
-_AUTO_EXACT_MAX_ROWS = 20000
+_AUTO_EXACT_MAX_ROWS = 4096
 
 
-def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div) -> MetricParams:
+def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n_rows=None) -> MetricParams:
+    n_rows = n_div if n_rows is None else n_rows
     return MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)), reserved=0,
-                        c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=float(n_div))
+                        c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=float(n_div), n_rows=float(n_rows))
 
 
-def _resolve_mode(mode: Optional[str], n: int, greedy: bool) -> str:
+def _resolve_mode(mode: Optional[str], n: int, needs_exact: bool) -> str:
     mode = mode or os.environ.get("XCOLUMNS_B200_MODE", "auto")
     if mode not in ("auto", "exact", "batched"):
         raise ValueError("mode must be 'auto', 'exact' or 'batched'")
     if mode == "auto":
-        mode = "exact" if (n <= _AUTO_EXACT_MAX_ROWS or greedy) else "batched"
+        mode = "exact" if (n <= _AUTO_EXACT_MAX_ROWS or needs_exact) else "batched"
     return mode
 
 
@@ -171,7 +173,7 @@ class BcaSession:
         if self.is_csr:
             self.ctx.call("xc_bca_exact_sweep_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
                           d.n, d.m, dev.ptr(order_dev), int(order_dev.numel()), k, C.byref(self.p), int(greedy),
-                          dev.ptr(self.pred), self._sp(0), self._sp(1), self._sp(2), self._s())
+                          dev.ptr(self.pred), self._sp(0), self._sp(1), self._sp(2), self._sp(3), self._s())
         else:
             self.ctx.call("xc_bca_exact_sweep_dense", dev.ptr(d.t), d.code, d.n, d.m, d.ld, dev.ptr(order_dev),
                           int(order_dev.numel()), k, C.byref(self.p), int(greedy), dev.ptr(self.pred), self._sp(0),
@@ -282,8 +284,10 @@ def predict_using_bc_with_0approx(
         raise ValueError("y_proba must be either np.ndarray, torch.Tensor, or csr_matrix")
     if metric_aggregation not in ("mean", "sum"):
         raise ValueError(f"Unsupported utility aggregation function: {metric_aggregation}, must be either 'mean' or 'sum'")
-    if k <= 0:
-        raise NotImplementedError("xcolumns_b200: BCA without a budget (k=0) is not implemented on the GPU path yet")
+    if k < 0:
+        raise ValueError("k must be >= 0")
+    if k == 0 and isinstance(y_proba, csr_matrix):
+        raise NotImplementedError("xcolumns_b200: BCA without a budget (k=0) is implemented for dense inputs only")
     metric_id, beta, eps = M.resolve_binary_metric(binary_metric_func, metric_kwargs)
     if metric_id in M.TN_METRICS and skip_tn:
         log_warning("skip_tn=True with a metric that uses true negatives: tn is the constant -1 like in the reference")
@@ -292,18 +296,24 @@ def predict_using_bc_with_0approx(
     if k > m:
         raise ValueError(f"k={k} is larger than the number of labels m={m}")
     greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
-    mode = _resolve_mode(mode, n, greedy)
+    mode = _resolve_mode(mode, n, greedy or k == 0 or metric_id not in M.AFFINE_GAIN_METRICS)
 
     device = dev.pick_device(y_proba)
     comm = make_comm(distributed, device)
+    if k == 0:
+        if mode != "exact" or comm.world > 1:
+            raise NotImplementedError("xcolumns_b200: k=0 runs in the sequential mode on one GPU (mode='exact')")
+        return _bca_k0_dense(y_proba, binary_metric_func, metric_id, beta, eps, metric_aggregation,
+                             normalize_conf_matrix, maximize, tolerance, init_y_pred, max_iters, shuffle_order,
+                             skip_tn, return_meta, seed, verbose, meta, device)
     is_csr = isinstance(y_proba, csr_matrix)
     data = dev.csr_to_device(y_proba, device) if is_csr else dev.dense_to_device(y_proba, device)
 
     n_div = n if normalize_conf_matrix else 1            # block_coordinate.py:403-405
     n_div_global = comm.n_global(n) if normalize_conf_matrix else 1
     n_order = n if normalize_conf_matrix else 1          # order = arange(n) after the overwrite (:414)
-    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div_global)
-    util_params = _metric_params(metric_id, 1.0, 1e-9, maximize, skip_tn, n_div_global)  # no kwargs (:63)
+    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div_global, comm.n_global(n))
+    util_params = _metric_params(metric_id, 1.0, 1e-9, maximize, skip_tn, n_div_global, comm.n_global(n))  # no kwargs (:63)
 
     timing = os.environ.get("XCOLUMNS_B200_TIMING") == "1"
 
@@ -322,8 +332,6 @@ def predict_using_bc_with_0approx(
     if mode == "exact":
         if comm.world > 1:
             raise NotImplementedError("sequential-exact BCA does not shard (replicas only); use mode='batched'")
-        if is_csr and not skip_tn:
-            raise NotImplementedError("xcolumns_b200: sequential-exact CSR BCA carries tn only with skip_tn=True")
         rng = np.random.default_rng(seed)                # :413
         order = np.arange(n_order)                       # :414
         new_u = None
@@ -356,7 +364,9 @@ def predict_using_bc_with_0approx(
         if metric_id not in M.AFFINE_GAIN_METRICS:
             raise NotImplementedError(
                 "xcolumns_b200 batched mode fuses the metrics whose marginal gain is affine in the probability "
-                "(precision, recall, F-beta/F1); use mode='exact' for Jaccard / balanced accuracy / G-mean / H-mean")
+                "(precision, recall, F-beta/F1, balanced accuracy); use mode='exact' for Jaccard / G-mean / H-mean")
+        if metric_id in M.TN_METRICS and skip_tn:
+            raise NotImplementedError("batched mode evaluates tn-based metrics with the real tn: pass skip_tn=False")
         batch = int(batch_size) if batch_size else default_batch_rows(n_order, sess.wave_rows())
         n_batches = comm.max_int((n_order + batch - 1) // batch)
         gen = torch.Generator(device=device)
@@ -409,6 +419,76 @@ def predict_using_bc_with_0approx(
     _mark("sweeps")
     y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format)
     _mark("output")
+    if return_meta:
+        meta["time"] = time() - meta["time"]
+        return y_pred, meta
+    return y_pred
+
+
+def _bca_k0_dense(y_proba, binary_metric_func, metric_id, beta, eps, aggregation, normalize_conf_matrix, maximize,
+                  tolerance, init_y_pred, max_iters, shuffle_order, skip_tn, return_meta, seed, verbose, meta, device):
+    """k = 0: no budget, a label is predicted whenever its gain is >= 0 (block_coordinate.py:199-200).
+    Labels are independent, so one thread per label walks the instance order (csrc/bca_exact.cu)."""
+    from .confusion_matrix import confusion_sums_device
+    ctx = dev.ctx_for(device)
+    data = dev.dense_to_device(y_proba, device)
+    n, m = data.n, data.m
+    n_div = n if normalize_conf_matrix else 1
+    n_order = n if normalize_conf_matrix else 1
+    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n)
+    tdt = data.torch_dtype
+    if isinstance(init_y_pred, str) and init_y_pred == "top":
+        pred = (data.t[:, :m] >= 0).to(tdt)                       # predict_top_k(k=0): gains >= th = 0
+    elif isinstance(init_y_pred, str) and init_y_pred in ("random", "greedy"):
+        pred = torch.zeros((n, m), dtype=tdt, device=device)      # random_at_k with k = 0 draws nothing
+    elif isinstance(init_y_pred, (np.ndarray, torch.Tensor)):
+        if tuple(init_y_pred.shape) != (n, m):
+            raise ValueError(f"init_y_pred must have shape (n, m) = ({n}, {m}), but has shape {init_y_pred.shape}")
+        pred = dev.dense_to_device(init_y_pred, device, tdt, pad=False).t.clone()
+    else:
+        raise ValueError("init_y_pred must be a dense matrix or one of 'random', 'greedy', 'top'")
+    pred = pred.contiguous()
+    greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
+    state = torch.zeros((4, m), dtype=torch.float64, device=device)
+    sp = lambda: dev.stream_ptr(device)
+
+    def recompute():
+        ctx.call("xc_confmat_dense", dev.ptr(data.t), data.ld, dev.ptr(pred), m, data.code, n, m, 0, XC_SUM_ORDERED, 0,
+                 C.c_void_p(state[0].data_ptr()), C.c_void_p(state[1].data_ptr()), C.c_void_p(state[2].data_ptr()), sp())
+        if skip_tn:
+            state[3].fill_(-1.0)
+        else:
+            state[3] = -state[0] - state[1] - state[2] + n
+
+    rng = np.random.default_rng(seed)
+    order = np.arange(n_order)
+    new_u = None
+    for j in range(1, max_iters + 1):
+        if shuffle_order:
+            rng.shuffle(order)
+        if greedy:
+            state.zero_()
+        elif new_u is None:
+            recompute()
+        old_u = _host_utility(binary_metric_func, aggregation, state, n_div) if (new_u is None or greedy) else new_u
+        order_dev = torch.from_numpy(order.astype(np.int32)).to(device)
+        ctx.call("xc_bca_exact_sweep_dense_k0", dev.ptr(data.t), data.code, n, m, data.ld, dev.ptr(order_dev),
+                 int(order_dev.numel()), C.byref(params), int(greedy), dev.ptr(pred), m,
+                 C.c_void_p(state[0].data_ptr()), C.c_void_p(state[1].data_ptr()), C.c_void_p(state[2].data_ptr()),
+                 C.c_void_p(state[3].data_ptr()), sp())
+        recompute()
+        new_u = _host_utility(binary_metric_func, aggregation, state, n_div)
+        greedy = False
+        meta["iters"] = j
+        meta["utilities"].append(new_u)
+        log_info(f"    Iteration {j}/{max_iters} finished, expected metric value: {old_u} -> {new_u}", verbose)
+        if (maximize and new_u - old_u < tolerance) or (not maximize and new_u - old_u > tolerance):
+            break
+    meta["mode"] = "exact"
+    if isinstance(y_proba, torch.Tensor):
+        y_pred = pred.to(device=y_proba.device, dtype=y_proba.dtype)
+    else:
+        y_pred = pred.cpu().numpy().astype(np.asarray(y_proba).dtype, copy=False)
     if return_meta:
         meta["time"] = time() - meta["time"]
         return y_pred, meta

@@ -242,6 +242,51 @@ bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
     }
 }
 
+// ---- k = 0 (no budget), dense: every label decides on its own (gain >= 0, block_coordinate.py:200),
+// so the sweep decomposes per label: thread j walks the whole order for label j -- no exchange at all,
+// still the reference's exact arithmetic.  pred is a dense [n, ldp] 0/1 matrix of the input dtype.
+template <typename TE>
+__global__ void __launch_bounds__(128)
+bca_exact_dense_k0_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ order,
+                          int64_t n_order, xc_metric_params p, int greedy, TE *pred, int64_t ldp, double *tp,
+                          double *fp, double *fn, double *tn)
+{
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= m) return;
+    const bool use_tn = !p.skip_tn;
+    const double nd = p.n_div;
+    const TE one = (TE)1;
+    double stp = tp[j], sfp = fp[j], sfn = fn[j], stn = tn[j];
+    for (int64_t s = 0; s < n_order; ++s) {
+        const int64_t row = order[s];
+        const TE pe = __ldg(eta + row * ld + j);
+        const TE om = one - pe;
+        TE y = pred[row * ldp + j];
+        if (!greedy) {
+            stp = stp - (double)(TE)(y * pe);
+            sfp = sfp - (double)(TE)(y * om);
+            sfn = sfn - (double)(TE)((one - y) * pe);
+            if (use_tn) stn = stn - (double)(TE)((one - y) * om);
+        }
+        const double pos_tp = stp + (double)pe, pos_fp = sfp + (double)om, neg_fn = sfn + (double)pe;
+        const double neg_tn = use_tn ? stn + (double)om : stn;
+        const double up = xc_binary_metric(p.metric, pos_tp / nd, pos_fp / nd, sfn / nd, stn / nd, p.c1, p.beta2, p.eps);
+        const double un = xc_binary_metric(p.metric, stp / nd, sfp / nd, neg_fn / nd, neg_tn / nd, p.c1, p.beta2, p.eps);
+        double g = up - un;
+        if (p.maximize) g = -g;           // :187-188
+        y = (g <= 0.0) ? one : (TE)0;     // :191, :200
+        pred[row * ldp + j] = y;
+        stp = stp + (double)(TE)(y * pe);
+        sfp = sfp + (double)(TE)(y * om);
+        sfn = sfn + (double)(TE)((one - y) * pe);
+        if (use_tn) stn = stn + (double)(TE)((one - y) * om);
+    }
+    tp[j] = stp;
+    fp[j] = sfp;
+    fn[j] = sfn;
+    if (use_tn) tn[j] = stn;
+}
+
 // ---- CSR: one warp walks the order ------------------------------------------------------------------
 // products exactly as numba forms them (numba_csr_functions.py:133, :206)
 template <typename T> __device__ __forceinline__ T mul_round(T a, T b) { return (T)(a * b); }
@@ -258,20 +303,31 @@ __device__ __forceinline__ int64_t csr_find(const int32_t *idx, int64_t s, int64
     return -1;
 }
 
-// +-(row contribution) for one CSR row given its compact prediction (lane x < k holds label pj)
+// +-(row contribution) for one CSR row given its compact prediction (lane x < k holds label pj).
+// tn (optional): numba subtracts 1 from EVERY label and adds the three products back on the touched
+// ones (numba_csr_functions.py:413-417 / :448-452).  For an untouched label (x - 1) + 1 == x exactly
+// in float64 (both steps are exact), so only the touched labels are rewritten, with numba's
+// operation order; each touched label is handled by exactly one lane.
 template <typename T>
 __device__ __forceinline__ void csr_apply_row(const T *data, const int32_t *indices, int64_t ts, int64_t te, int pj,
-                                              int k, double sgn, double *tp, double *fp, double *fn)
+                                              int k, double sgn, double *tp, double *fp, double *fn, double *tn)
 {
     const int lane = lane_id();
     const T one = (T)1;
     if (lane < k && pj >= 0) {  // numba_csr_functions.py:400-407 / 435-442
         int64_t y = csr_find(indices, ts, te, pj);
         if (y >= 0) {
-            tp[pj] = tp[pj] + sgn * (double)mul_round(one, data[y]);
-            fp[pj] = fp[pj] + sgn * (double)mul_om_round(one, data[y]);
+            const double vtp = (double)mul_round(one, data[y]);
+            const double vft = (double)mul_om_round(one, data[y]);
+            tp[pj] = tp[pj] + sgn * vtp;
+            fp[pj] = fp[pj] + sgn * vft;
+            if (tn) {  // label in pred and in the row: fn_data = t * (1 - 1) = 0
+                const double vfn = (double)mul_om_round(data[y], one);
+                tn[pj] = (((tn[pj] + sgn) - sgn * vtp) - sgn * vft) - sgn * vfn;
+            }
         } else {
             fp[pj] = fp[pj] + sgn * (double)one;
+            if (tn) tn[pj] = (tn[pj] + sgn) - sgn * (double)one;
         }
     }
     for (int64_t q0 = ts; q0 < te; q0 += 32) {  // :408-411 / 443-446
@@ -279,7 +335,11 @@ __device__ __forceinline__ void csr_apply_row(const T *data, const int32_t *indi
         int j = q < te ? indices[q] : -2;
         bool sel = false;
         for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, pj, t) == j);
-        if (q < te) fn[j] = fn[j] + sgn * (sel ? (double)mul_om_round(data[q], one) : (double)data[q]);
+        if (q < te) {
+            const double vfn = sel ? (double)mul_om_round(data[q], one) : (double)data[q];
+            fn[j] = fn[j] + sgn * vfn;
+            if (tn && !sel) tn[j] = (tn[j] + sgn) - sgn * vfn;
+        }
     }
     __syncwarp();
 }
@@ -288,7 +348,7 @@ template <typename T>
 __global__ void __launch_bounds__(32)
 bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
                      const int64_t *__restrict__ indptr, const int32_t *__restrict__ order, int64_t n_order, int k,
-                     xc_metric_params p, int greedy, int32_t *pred_idx, double *tp, double *fp, double *fn)
+                     xc_metric_params p, int greedy, int32_t *pred_idx, double *tp, double *fp, double *fn, double *tn)
 {
     const int lane = lane_id();
     const double nd = p.n_div;
@@ -298,7 +358,7 @@ bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
         const int64_t ts = indptr[row], te = indptr[row + 1], nz = te - ts;
         int32_t *prow = pred_idx + row * k;
         int pj = lane < k ? prow[lane] : -1;
-        if (!greedy) csr_apply_row<T>(data, indices, ts, te, pj, k, -1.0, tp, fp, fn);
+        if (!greedy) csr_apply_row<T>(data, indices, ts, te, pj, k, -1.0, tp, fp, fn, tn);
         WarpTopK<double> tk;
         tk.init();
         for (int64_t q0 = ts; q0 < te; q0 += 32) {  // block_coordinate.py:248-282
@@ -316,8 +376,14 @@ bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
                 neg_tp = neg_tp / nd;
                 neg_fp = neg_fp / nd;
                 pos_fn = pos_fn / nd;
-                const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, -1.0, p.c1, p.beta2, p.eps);
-                const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, -1.0, p.c1, p.beta2, p.eps);
+                double pos_tn = -1.0, neg_tnn = -1.0;       // block_coordinate.py:260-264
+                if (tn) {
+                    pos_tn = tn[j];
+                    neg_tnn = (pos_tn + (double)om) / nd;
+                    pos_tn = pos_tn / nd;
+                }
+                const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, pos_tn, p.c1, p.beta2, p.eps);
+                const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, neg_tnn, p.c1, p.beta2, p.eps);
                 const double gg = up - un;
                 g[0] = p.maximize ? gg : -gg;
             }
@@ -329,7 +395,7 @@ bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
         int pos = __shfl_sync(XC_FULL, tk.idx, src);
         pj = (lane < k && pos != 0x7fffffff) ? indices[ts + pos] : -1;
         if (lane < k) prow[lane] = pj;
-        csr_apply_row<T>(data, indices, ts, te, pj, k, 1.0, tp, fp, fn);
+        csr_apply_row<T>(data, indices, ts, te, pj, k, 1.0, tp, fp, fn, tn);
     }
 }
 
@@ -499,20 +565,43 @@ extern "C" int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype,
     return XC_ERR_UNSUPPORTED;
 }
 
+extern "C" int xc_bca_exact_sweep_dense_k0(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m, int64_t ld,
+                                           const int32_t *order, int64_t n_order, const xc_metric_params *p,
+                                           int greedy, void *pred, int64_t ld_pred, double *tp, double *fp, double *fn,
+                                           double *tn, void *stream)
+{
+    if (!ctx || !eta || !order || !p || !pred || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
+    if (n <= 0 || m <= 0 || ld < m || ld_pred < m || n_order < 0) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    if (n_order == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = (unsigned)((m + 127) / 128);
+    if (dtype == XC_F32)
+        bca_exact_dense_k0_kernel<float><<<grid, 128, 0, st>>>((const float *)eta, m, ld, order, n_order, *p, greedy, (float *)pred, ld_pred, tp, fp, fn, tn);
+    else if (dtype == XC_F64)
+        bca_exact_dense_k0_kernel<double><<<grid, 128, 0, st>>>((const double *)eta, m, ld, order, n_order, *p, greedy, (double *)pred, ld_pred, tp, fp, fn, tn);
+    else
+        return XC_ERR_UNSUPPORTED;
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
 extern "C" int xc_bca_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
                                       const int64_t *indptr, int64_t n, int64_t m, const int32_t *order,
                                       int64_t n_order, int k, const xc_metric_params *p, int greedy, int32_t *pred_idx,
-                                      double *tp, double *fp, double *fn, void *stream)
+                                      double *tp, double *fp, double *fn, double *tn, void *stream)
 {
     if (!ctx || !indptr || !order || !p || !pred_idx || !tp || !fp || !fn) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || n_order < 0 || k < 1 || k > 32) return XC_ERR_INVALID;
-    if (p->metric < 0 || p->metric > XC_METRIC_JACCARD || !p->skip_tn) return XC_ERR_UNSUPPORTED;
+    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    if (!p->skip_tn && !tn) return XC_ERR_INVALID;
     if (n_order == 0) return XC_OK;
+    double *tn_arg = p->skip_tn ? nullptr : tn;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == XC_F32)
-        bca_exact_csr_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn);
+        bca_exact_csr_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
     else if (dtype == XC_F64)
-        bca_exact_csr_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn);
+        bca_exact_csr_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
     else
         return XC_ERR_UNSUPPORTED;
     XC_LAUNCHED(ctx);

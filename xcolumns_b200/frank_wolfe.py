@@ -181,7 +181,7 @@ def find_classifier_using_fw(
     comm.allreduce_sum_(colsum)
 
     params = MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)), reserved=0,
-                          c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=1.0)
+                          c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=1.0, n_rows=float(n_global))
     Cm = torch.empty(4 * m, **f64)       # running confusion vectors [tp, fp, fn, tn]
     Ci = torch.empty(4 * m, **f64)       # confusion vectors of the newest classifier
     raw = torch.empty((2, m), **f64)     # tp_raw, cnt of one iterate

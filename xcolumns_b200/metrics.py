@@ -15,7 +15,7 @@ from .utils import add_kwargs_to_signature
 
 XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA, XC_METRIC_JACCARD = 0, 1, 2, 3
 XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN = 4, 5, 6
-AFFINE_GAIN_METRICS = (XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA)
+AFFINE_GAIN_METRICS = (XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA, XC_METRIC_BALANCED_ACC)
 TN_METRICS = (XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN)
 
 
