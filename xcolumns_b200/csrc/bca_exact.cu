@@ -17,6 +17,7 @@
 // This file must be compiled with -fmad=false: every + - * / below is a separate IEEE
 // operation, exactly like numpy/numba evaluate the reference expressions.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "xc_scan.cuh"
 
@@ -27,31 +28,42 @@ namespace {
 constexpr int EX_THREADS = 128;
 constexpr int EX_WARPS = EX_THREADS / 32;
 
+// Candidate = (gain, label).  The gain is carried as an order-preserving int64 key of the double
+// (FP64 compares and selects run on the scarce FP64 pipe of this chip -- ~16 lanes/clk/SM measured --
+// and every arg-max round is a chain of them; integer compares are 4x cheaper and 2-cycle issue).
 struct alignas(16) Cand {
-    double g;
+    long long g;   // sortable key of the float64 gain
     int j;
     int pad;
 };
 
+__device__ __forceinline__ long long gain_key(double x)
+{
+    if (!(x == x)) return (long long)0x8000000000000000ULL;          // NaN sorts below everything
+    long long b = __double_as_longlong(x + 0.0);                      // -0.0 -> +0.0
+    return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);                   // negative: reverse magnitude order
+}
+constexpr long long KEY_NEG_INF = (long long)0x8000000000000001ULL;   // below every real gain, above NaN key
+
 // candidates written by other blocks: read through L2 (L1 is not coherent across SMs)
 __device__ __forceinline__ Cand cand_load_cg(const Cand *p)
 {
-    double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
+    longlong2 v = __ldcg(reinterpret_cast<const longlong2 *>(p));
     Cand c;
     c.g = v.x;
-    c.j = __double2loint(v.y);
+    c.j = (int)(v.y & 0xffffffffLL);
     c.pad = 0;
     return c;
 }
 
-__device__ __forceinline__ Cand cand_best(Cand a, Cand b) { return xc_better(b.g, b.j, a.g, a.j) ? b : a; }
+__device__ __forceinline__ Cand cand_best(Cand a, Cand b) { return xc_better(b.g, b.j, a.g, a.j) ? b : a; }  // int64 keys
 
 __device__ __forceinline__ Cand warp_argmax(Cand c)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         Cand t;
-        t.g = __shfl_xor_sync(XC_FULL, c.g, o);
+        t.g = __shfl_xor_sync(XC_FULL, c.g, o);   // long long shuffle (2 x 32 bit)
         t.j = __shfl_xor_sync(XC_FULL, c.j, o);
         t.pad = 0;
         c = cand_best(c, t);
@@ -68,7 +80,7 @@ __device__ __forceinline__ Cand block_argmax(Cand c, Cand *sm)
     Cand r;
     const int lane = threadIdx.x & 31;
     if (lane < EX_WARPS) r = sm[lane];
-    else { r.g = -INFINITY; r.j = 0x7fffffff; }
+    else { r.g = KEY_NEG_INF; r.j = 0x7fffffff; }
     r.pad = 0;
     r = warp_argmax(r);
     __syncthreads();
@@ -160,7 +172,7 @@ bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
         unsigned taken = 0;
         for (int t = 0; t < k; ++t) {
             Cand c;
-            c.g = -INFINITY;
+            c.g = KEY_NEG_INF;
             c.j = 0x7fffffff;
             c.pad = 0;
 #pragma unroll
@@ -168,7 +180,7 @@ bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
                 int64_t j = j0 + l * stride;
                 if (j < m && !((taken >> l) & 1u)) {
                     Cand d;
-                    d.g = gain[l];
+                    d.g = gain_key(gain[l]);
                     d.j = (int)j;
                     d.pad = 0;
                     c = cand_best(c, d);
@@ -190,7 +202,7 @@ bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
         int picked[32];
         for (int t = 0; t < k; ++t) {
             Cand c;
-            c.g = -INFINITY;
+            c.g = KEY_NEG_INF;
             c.j = 0x7fffffff;
             c.pad = 0;
             for (int q = threadIdx.x; q < total; q += EX_THREADS) {
@@ -240,6 +252,264 @@ bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
             if (use_tn) tn[j] = stn[l];
         }
     }
+}
+
+// ---- dense, one thread-block cluster ---------------------------------------------------------------
+// Same arithmetic as bca_exact_dense_kernel, but the labels live in ONE cluster of up to 16 CTAs, so the
+// per-instance exchange goes through distributed shared memory and a cluster barrier (~0.2 us) instead
+// of global memory and a grid barrier (~3-5 us):
+//   warp top-k (k rounds of shuffle arg-max) -> block top-k in smem -> every CTA pushes its k candidates
+//   into all peers' smem (DSMEM stores) -> barrier.cluster -> every CTA merges the <= 16*k candidates.
+constexpr int CL_MAX = 16;
+
+// top-k of `cnt` candidates in smem by ranking: thread t < cnt counts the candidates that beat
+// candidate t (cnt broadcast-friendly smem reads, no shuffle chains, no serial rounds) and, if fewer
+// than k do, stores it at dst[rank].  All threads of the CTA call it; the caller synchronises.
+// Measured motivation (profiles/r01_notes.md): with k rounds of warp arg-max run by warp 0 alone, 47 %
+// of all warp samples of the sweep were other warps parked at the barriers behind those merges.
+__device__ __forceinline__ void rank_topk_smem(const Cand *src, int cnt, int k, Cand *dst)
+{
+    if (threadIdx.x < k) {   // slots no candidate claims (fewer than k real candidates) must read as empty
+        Cand e;
+        e.g = KEY_NEG_INF; e.j = 0x7fffffff; e.pad = 0;
+        dst[threadIdx.x] = e;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+        const Cand me = src[t];
+        int rank = 0;
+        for (int q = 0; q < cnt; ++q) {
+            const Cand o = src[q];
+            rank += xc_better(o.g, o.j, me.g, me.j) ? 1 : 0;   // strict order: labels are distinct
+        }
+        if (rank < k) dst[rank] = me;
+    }
+}
+
+// top-k of `cnt` candidates held in smem (cnt <= 32 * per), by one warp: lane l owns entries l, l+32, ...
+__device__ __forceinline__ void warp_topk_smem(const Cand *src, int cnt, int k, Cand *dst)
+{
+    const int lane = lane_id();
+    unsigned long long taken = 0ull;  // bit t: entry lane + 32*t already emitted
+    for (int r = 0; r < k; ++r) {
+        Cand c;
+        c.g = KEY_NEG_INF; c.j = 0x7fffffff; c.pad = -1;
+        for (int t = 0, q = lane; q < cnt; ++t, q += 32) {
+            if (!((taken >> t) & 1ull)) {
+                Cand d = src[q];
+                d.pad = t;
+                if (xc_better(d.g, d.j, c.g, c.j)) c = d;
+            }
+        }
+        // arg-max across lanes, remember the winning lane
+        Cand w = c;
+        int wl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            long long og = __shfl_xor_sync(XC_FULL, w.g, o);
+            int oj = __shfl_xor_sync(XC_FULL, w.j, o);
+            int ol = __shfl_xor_sync(XC_FULL, wl, o);
+            if (xc_better(og, oj, w.g, w.j)) { w.g = og; w.j = oj; wl = ol; }
+        }
+        if (lane == wl && c.pad >= 0) taken |= 1ull << c.pad;
+        if (lane == 0) { Cand o; o.g = w.g; o.j = w.j; o.pad = 0; dst[r] = o; }
+    }
+}
+
+template <typename TE, int L, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ order,
+                               int64_t n_order, int k, xc_metric_params p, int greedy, int32_t *pred_idx, double *tp,
+                               double *fp, double *fn, double *tn)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nc = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    constexpr int NW = THREADS / 32;
+    __shared__ Cand s_warp[NW * 32];          // per-warp top-k (k <= 32 each)
+    __shared__ Cand s_blk[32];                // block top-k
+    __shared__ Cand s_in[2][CL_MAX * 32];     // candidates pushed by every CTA of the cluster (double buffered)
+    __shared__ Cand s_fin[32];                // final top-k of the step
+    __shared__ Cand s_tmp[NW * 32];           // warp candidates, densely packed
+    __shared__ Cand s_keys[L == 1 ? NW * 32 : 1];   // per-warp key exchange (L == 1)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t stride = (int64_t)nc * THREADS;
+    const int64_t j0 = (int64_t)rank * THREADS + threadIdx.x;
+    const bool use_tn = !p.skip_tn;
+    const double nd = p.n_div;
+    const TE one = (TE)1;
+
+    double stp[L], sfp[L], sfn[L], stn[L];
+    TE pv[L], pnext[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        int64_t j = j0 + l * stride;
+        bool ok = j < m;
+        stp[l] = ok ? tp[j] : 0.0;
+        sfp[l] = ok ? fp[j] : 0.0;
+        sfn[l] = ok ? fn[j] : 0.0;
+        stn[l] = ok ? tn[j] : 0.0;
+        pnext[l] = (TE)0;
+    }
+    if (n_order > 0) {
+        const TE *rp = eta + (int64_t)order[0] * ld;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            int64_t j = j0 + l * stride;
+            if (j < m) pnext[l] = __ldg(rp + j);
+        }
+    }
+    cluster.sync();
+
+    for (int64_t s = 0; s < n_order; ++s) {
+        const int64_t row = order[s];
+        int32_t *prow = pred_idx + row * k;
+#pragma unroll
+        for (int l = 0; l < L; ++l) pv[l] = pnext[l];
+        if (s + 1 < n_order) {
+            const TE *rn = eta + (int64_t)order[s + 1] * ld;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                int64_t j = j0 + l * stride;
+                if (j < m) pnext[l] = __ldg(rn + j);
+            }
+        }
+        // ---- 1. remove own contribution, gains (block_coordinate.py:157-185) --------------------------
+        int myp = lane < k ? __ldg(prow + lane) : -1;   // the row's current selection, one label per lane
+        double gain[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int64_t j = j0 + l * stride;
+            gain[l] = -INFINITY;
+            bool sel = false;
+            for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, myp, t) == (int)j);
+            if (j < m) {
+                const TE pe = pv[l];
+                const TE om = one - pe;
+                const TE y = sel ? one : (TE)0;
+                if (!greedy) {
+                    stp[l] = stp[l] - (double)(TE)(y * pe);
+                    sfp[l] = sfp[l] - (double)(TE)(y * om);
+                    sfn[l] = sfn[l] - (double)(TE)((one - y) * pe);
+                    if (use_tn) stn[l] = stn[l] - (double)(TE)((one - y) * om);
+                }
+                const double pos_tp = stp[l] + (double)pe;
+                const double pos_fp = sfp[l] + (double)om;
+                const double neg_fn = sfn[l] + (double)pe;
+                const double neg_tn = use_tn ? stn[l] + (double)om : stn[l];
+                const double up = xc_binary_metric(p.metric, pos_tp / nd, pos_fp / nd, sfn[l] / nd, stn[l] / nd,
+                                                   p.c1, p.beta2, p.eps);
+                const double un = xc_binary_metric(p.metric, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn / nd,
+                                                   p.c1, p.beta2, p.eps);
+                const double g = up - un;
+                gain[l] = p.maximize ? g : -g;
+            }
+        }
+        // ---- 2a. warp top-k ---------------------------------------------------------------------------
+        if (L == 1) {
+            // one gain per lane: every lane ranks itself against the other 31 through smem
+            // (32 broadcast reads instead of k dependent 5-level shuffle arg-max rounds)
+            Cand me;
+            me.g = j0 < m ? gain_key(gain[0]) : KEY_NEG_INF;
+            me.j = j0 < m ? (int)j0 : 0x7fffffff;
+            me.pad = 0;
+            Cand *wk = s_keys + warp * 32;
+            wk[lane] = me;
+            if (lane < k) {   // fewer than k labels in this warp: the unused slots stay empty
+                Cand e;
+                e.g = KEY_NEG_INF; e.j = 0x7fffffff; e.pad = 0;
+                s_warp[warp * 32 + lane] = e;
+            }
+            __syncwarp();
+            int rank = 0;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) {
+                const Cand o = wk[q];
+                rank += xc_better(o.g, o.j, me.g, me.j) ? 1 : 0;
+            }
+            if (rank < k) s_warp[warp * 32 + rank] = me;
+        } else {
+            long long gkey[L];
+#pragma unroll
+            for (int l = 0; l < L; ++l) gkey[l] = gain_key(gain[l]);
+            unsigned taken = 0;
+            for (int r = 0; r < k; ++r) {
+                Cand c;
+                c.g = KEY_NEG_INF; c.j = 0x7fffffff; c.pad = -1;
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    int64_t j = j0 + l * stride;
+                    if (j < m && !((taken >> l) & 1u) && xc_better(gkey[l], (int)j, c.g, c.j)) {
+                        c.g = gkey[l]; c.j = (int)j; c.pad = l;
+                    }
+                }
+                Cand w = c;
+                int wl = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    long long og = __shfl_xor_sync(XC_FULL, w.g, o);
+                    int oj = __shfl_xor_sync(XC_FULL, w.j, o);
+                    int ol = __shfl_xor_sync(XC_FULL, wl, o);
+                    if (xc_better(og, oj, w.g, w.j)) { w.g = og; w.j = oj; wl = ol; }
+                }
+                if (lane == wl && c.pad >= 0) taken |= 1u << c.pad;
+                if (lane == 0) { Cand o; o.g = w.g; o.j = w.j; o.pad = 0; s_warp[warp * 32 + r] = o; }
+            }
+        }
+        __syncthreads();
+        // ---- 2b. block top-k by ranking the NW * k warp candidates, then push to every CTA ----------------
+        Cand *inbuf = s_in[s & 1];
+        {
+            const int cnt = NW * k;
+            for (int q = threadIdx.x; q < cnt; q += THREADS) s_tmp[q] = s_warp[(q / k) * 32 + (q % k)];
+            __syncthreads();
+            rank_topk_smem(s_tmp, cnt, k, s_blk);
+            __syncthreads();
+            // my block's k candidates go to slot `rank` of every CTA's input buffer (DSMEM stores)
+            for (int q = threadIdx.x; q < nc * k; q += THREADS) {
+                const int dst_rank = q / k, r = q % k;
+                Cand *remote = cluster.map_shared_rank(inbuf, dst_rank);
+                remote[rank * k + r] = s_blk[r];
+            }
+        }
+        cluster.sync();   // release/acquire: all pushes visible
+        // ---- 3. every CTA ranks the nc * k candidates (identical result everywhere) ---------------------
+        rank_topk_smem(inbuf, nc * k, k, s_fin);
+        __syncthreads();
+        // ---- 4. re-add with the new selection (block_coordinate.py:203-209) --------------------------------
+        const int fin = lane < k ? s_fin[lane].j : -1;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int64_t j = j0 + l * stride;
+            bool sel = false;
+            for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, fin, t) == (int)j);
+            if (j < m) {
+                const TE pe = pv[l];
+                const TE om = one - pe;
+                const TE y = sel ? one : (TE)0;
+                stp[l] = stp[l] + (double)(TE)(y * pe);
+                sfp[l] = sfp[l] + (double)(TE)(y * om);
+                sfn[l] = sfn[l] + (double)(TE)((one - y) * pe);
+                if (use_tn) stn[l] = stn[l] + (double)(TE)((one - y) * om);
+            }
+        }
+        if (rank == 0 && warp == 0) {   // store the new row ascending by label
+            int src = warp_rank_src(fin < 0 ? 0x7fffffff : fin, k);
+            int v = __shfl_sync(XC_FULL, fin, src);
+            if (lane < k) prow[lane] = v;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        int64_t j = j0 + l * stride;
+        if (j < m) {
+            tp[j] = stp[l];
+            fp[j] = sfp[l];
+            fn[j] = sfn[l];
+            if (use_tn) tn[j] = stn[l];
+        }
+    }
+    cluster.sync();   // nobody exits while peers may still address its shared memory
 }
 
 // ---- k = 0 (no budget), dense: every label decides on its own (gain >= 0, block_coordinate.py:200),
@@ -514,6 +784,60 @@ int launch_exact_dense(xc_ctx *ctx, int grid, const void *eta, int64_t m, int64_
     return XC_OK;
 }
 
+template <typename TE, int L, int THREADS>
+int launch_exact_cluster(xc_ctx *ctx, int nc, const void *eta, int64_t m, int64_t ld, const int32_t *order,
+                         int64_t n_order, int k, const xc_metric_params *p, int greedy, int32_t *pred_idx, double *tp,
+                         double *fp, double *fn, double *tn, cudaStream_t st)
+{
+    auto kern = bca_exact_dense_cluster_kernel<TE, L, THREADS>;
+    if (nc > 8) XC_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nc);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nc;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return XC_ERR_UNSUPPORTED;  // caller falls back to the grid-barrier kernel
+    }
+    XC_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, (const TE *)eta, m, ld, order, n_order, k, *p, greedy, pred_idx, tp,
+                                        fp, fn, tn));
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+// cluster shape for m labels: THREADS * L labels per CTA, at most 16 CTAs; prefers a portable (<= 8) cluster
+template <typename TE>
+int dispatch_exact_cluster(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, const int32_t *order, int64_t n_order,
+                           int k, const xc_metric_params *p, int greedy, int32_t *pred_idx, double *tp, double *fp,
+                           double *fn, double *tn, cudaStream_t st)
+{
+    auto ncta = [&](int64_t per_cta) { return (int)((m + per_cta - 1) / per_cta); };
+#define XC_TRY(LL, TH)                                                                                               \
+    {                                                                                                                \
+        int nc = ncta((int64_t)(TH) * (LL));                                                                         \
+        if (nc <= CL_MAX)                                                                                            \
+            return launch_exact_cluster<TE, LL, TH>(ctx, nc, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, \
+                                                    fp, fn, tn, st);                                                 \
+    }
+    if (ncta(512) <= 8) XC_TRY(1, 512)
+    if (ncta(1024) <= 8) XC_TRY(2, 512)
+    XC_TRY(1, 512)
+    XC_TRY(2, 512)
+    XC_TRY(4, 512)
+    XC_TRY(8, 256)
+#undef XC_TRY
+    return XC_ERR_UNSUPPORTED;
+}
+
 template <typename TE>
 int dispatch_exact_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, const int32_t *order, int64_t n_order,
                          int k, const xc_metric_params *p, int greedy, int32_t *pred_idx, double *tp, double *fp,
@@ -558,6 +882,17 @@ extern "C" int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype,
     if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
     if (n_order == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    static int grid_only = -1;   // $XCOLUMNS_B200_EXACT_PATH=grid forces the cooperative-grid kernel
+    if (grid_only < 0) {
+        const char *e = getenv("XCOLUMNS_B200_EXACT_PATH");
+        grid_only = (e && e[0] == 'g') ? 1 : 0;
+    }
+    if (!grid_only) {
+        int rc = XC_ERR_UNSUPPORTED;
+        if (dtype == XC_F32) rc = dispatch_exact_cluster<float>(ctx, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, st);
+        else if (dtype == XC_F64) rc = dispatch_exact_cluster<double>(ctx, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, st);
+        if (rc != XC_ERR_UNSUPPORTED) return rc;
+    }
     if (dtype == XC_F32)
         return dispatch_exact_dense<float>(ctx, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, st);
     if (dtype == XC_F64)
