@@ -166,11 +166,11 @@ def secondary(args):
         sess = BcaSession(data, k, params, params, "mean")
         init_pred = topk_csr_device(data, k, None, None)[0]
         batch = args.batch or max(1, n // 8)
-        gen = torch.Generator(device=device)
-        gen.manual_seed(3)
+        sweep_no = [0]
 
         def step():
-            order = torch.randperm(n, generator=gen, device=device, dtype=torch.int32)
+            sweep_no[0] += 1
+            order = sess.permutation(n, 3 + 7919 * sweep_no[0])
             sess.delta.zero_()
             sess.sweep_batched(order, batch)
             sess.recompute(XC_SUM_FAST)
@@ -292,11 +292,11 @@ def main():
     init_pred = topk_dense_device(data, k, None, None, XC_F32)[0]
     batch = args.batch or default_batch_rows(n, sess.wave_rows())
     n_batches = comm.max_int((n + batch - 1) // batch)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(17 + rank)
+    sweep_no = [0]
 
     def one_sweep(events=None):
-        order = torch.randperm(n, generator=gen, device=device, dtype=torch.int32)
+        sweep_no[0] += 1
+        order = sess.permutation(n, 17 + 1000003 * rank + 7919 * sweep_no[0])
         sess.delta.zero_()
         sess.sweep_batched(order, batch, n_batches, events=events)
         sess.recompute(XC_SUM_FAST)

@@ -85,6 +85,11 @@ XC_API const char *xc_last_cuda_error(xc_ctx *ctx);
 XC_API int64_t xc_launch_count(xc_ctx *ctx);
 XC_API int xc_sm_count(xc_ctx *ctx);
 
+/* Pseudo-random permutation of 0..n-1 (visiting order of one batched sweep), written to out[n].
+ * The sequential mode does not use it: there the order comes from numpy's Generator on the host,
+ * bit-identical to the reference (block_coordinate.py:413-419).                                */
+XC_API int xc_permutation(xc_ctx *ctx, int64_t n, uint64_t seed, int32_t *out, void *stream);
+
 /* ---- weighted per-instance top-k ------------------------------------------------------ */
 /* ref: weighted_prediction.py:25-60 (_predict_weighted_per_instance_dense), :91-220.
  * gains = eta [* a] [+ b] evaluated in `g_dtype` (separate multiply and add, no FMA, so the

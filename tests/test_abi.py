@@ -28,6 +28,8 @@ def _ctype_of(param: str):
         return "ptr"
     if param.startswith("int64_t"):
         return C.c_int64
+    if param.startswith("uint64_t"):
+        return C.c_uint64
     if param.startswith("double"):
         return C.c_double
     if param.startswith("int"):

@@ -364,6 +364,23 @@ def test_bca_reference_properties(xb):
         assert rec(pred) >= rec(top)
 
 
+def test_permutation_is_a_bijection(xb):
+    import ctypes as C
+    from xcolumns_b200 import _device as dev
+    device = torch.device("cuda", 0)
+    ctx = dev.ctx_for(device)
+    for n in (1, 2, 5, 1000, 4097, 307000):
+        outs = []
+        for seed in (1, 2):
+            out = torch.empty(n, dtype=torch.int32, device=device)
+            ctx.call("xc_permutation", n, C.c_uint64(seed), dev.ptr(out), dev.stream_ptr(device))
+            assert torch.equal(torch.sort(out).values, torch.arange(n, dtype=torch.int32, device=device))
+            outs.append(out)
+        if n > 100:
+            assert not torch.equal(outs[0], outs[1])
+            assert not torch.equal(outs[0], torch.arange(n, dtype=torch.int32, device=device))
+
+
 def test_unsupported_metric_is_loud(xb):
     eta = np.random.rand(10, 20).astype(np.float32)
     with pytest.raises(NotImplementedError):

@@ -32,6 +32,7 @@ _MP = C.POINTER(MetricParams)
 
 # name -> argtypes (after ctx); every function returns int unless listed in _RESTYPES
 _SIGNATURES = {
+    "xc_permutation": [_i64, C.c_uint64, _vp, _vp],
     "xc_topk_dense": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp],
     "xc_topk_csr": [_vp, _int, _vp, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp],
     "xc_threshold_dense": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _int, _dbl, _vp, _i64, _vp],

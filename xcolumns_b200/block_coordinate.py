@@ -162,6 +162,13 @@ class BcaSession:
             return 0
         return int(self.ctx.lib.xc_bca_wave_rows(self.ctx.handle, self.data.code, self.m))
 
+    def permutation(self, n: int, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pseudo-random visiting order of one batched sweep (int32 [n], device)"""
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=self.device)
+        self.ctx.call("xc_permutation", n, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), dev.ptr(out), self._s())
+        return out
+
     def utility_device(self, slot: int) -> None:
         """block_coordinate.py:54-90 on the device; result lands in util_buf[slot]."""
         self.ctx.call("xc_utility", C.byref(self.up), self.agg, self._sp(0), self._sp(1), self._sp(2), self._sp(3),
@@ -369,8 +376,7 @@ def predict_using_bc_with_0approx(
             raise NotImplementedError("batched mode evaluates tn-based metrics with the real tn: pass skip_tn=False")
         batch = int(batch_size) if batch_size else default_batch_rows(n_order, sess.wave_rows())
         n_batches = comm.max_int((n_order + batch - 1) // batch)
-        gen = torch.Generator(device=device)
-        gen.manual_seed(0 if seed is None else int(seed) + 7919 * comm.rank)
+        base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
         order_dev = torch.arange(n_order, dtype=torch.int32, device=device)
         sess.recompute(XC_SUM_FAST)
         sess.utility_device(0)
@@ -386,7 +392,7 @@ def predict_using_bc_with_0approx(
             nonlocal order_dev
             saved[j] = sess.pred.clone()
             if shuffle_order:
-                order_dev = torch.randperm(n_order, generator=gen, device=device, dtype=torch.int32)
+                order_dev = sess.permutation(n_order, base_seed + 0x632BE59BD9B4E019 * j)
             sess.delta.zero_()
             sess.sweep_batched(order_dev, batch, n_batches)
             sess.recompute(XC_SUM_FAST)

@@ -81,3 +81,47 @@ int xc_ctx_scratch(xc_ctx *ctx, size_t bytes, void **out)
     *out = ctx->scratch;
     return XC_OK;
 }
+
+// ---- pseudo-random permutation of 0..n-1 (visiting order of a batched sweep) ----------------------------
+// A 4-round balanced Feistel network on the smallest even-width power-of-two domain >= n, with cycle
+// walking (re-encrypt until the value falls below n): a bijection of [0, n) computed independently per
+// element, one 6 us kernel instead of a key-sort (torch.randperm: ~95 us at n = 307 k, measured).
+namespace {
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) permutation_kernel(int64_t n, uint64_t seed, int half_bits, int32_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint32_t k0 = mix32((uint32_t)seed), k1 = mix32((uint32_t)(seed >> 32) ^ 0x9e3779b9U);
+    uint64_t x = (uint64_t)i;
+    do {
+        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            uint32_t f = mix32(r ^ (round & 1 ? k1 : k0) ^ (0x85ebca6bU * (uint32_t)(round + 1))) & mask;
+            uint32_t t = l ^ f;
+            l = r;
+            r = t;
+        }
+        x = ((uint64_t)l << half_bits) | r;
+    } while (x >= (uint64_t)n);
+    out[i] = (int32_t)x;
+}
+}  // namespace
+
+extern "C" int xc_permutation(xc_ctx *ctx, int64_t n, uint64_t seed, int32_t *out, void *stream)
+{
+    if (!ctx || !out || n < 0 || n > 0x7fffffffLL) return XC_ERR_INVALID;
+    if (n == 0) return XC_OK;
+    int bits = 2;
+    while ((1ULL << bits) < (uint64_t)n) bits += 2;   // even width, domain < 4n -> < 4 walks expected
+    permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, seed, bits / 2, out);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}

@@ -286,36 +286,6 @@ __device__ __forceinline__ void rank_topk_smem(const Cand *src, int cnt, int k, 
     }
 }
 
-// top-k of `cnt` candidates held in smem (cnt <= 32 * per), by one warp: lane l owns entries l, l+32, ...
-__device__ __forceinline__ void warp_topk_smem(const Cand *src, int cnt, int k, Cand *dst)
-{
-    const int lane = lane_id();
-    unsigned long long taken = 0ull;  // bit t: entry lane + 32*t already emitted
-    for (int r = 0; r < k; ++r) {
-        Cand c;
-        c.g = KEY_NEG_INF; c.j = 0x7fffffff; c.pad = -1;
-        for (int t = 0, q = lane; q < cnt; ++t, q += 32) {
-            if (!((taken >> t) & 1ull)) {
-                Cand d = src[q];
-                d.pad = t;
-                if (xc_better(d.g, d.j, c.g, c.j)) c = d;
-            }
-        }
-        // arg-max across lanes, remember the winning lane
-        Cand w = c;
-        int wl = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            long long og = __shfl_xor_sync(XC_FULL, w.g, o);
-            int oj = __shfl_xor_sync(XC_FULL, w.j, o);
-            int ol = __shfl_xor_sync(XC_FULL, wl, o);
-            if (xc_better(og, oj, w.g, w.j)) { w.g = og; w.j = oj; wl = ol; }
-        }
-        if (lane == wl && c.pad >= 0) taken |= 1ull << c.pad;
-        if (lane == 0) { Cand o; o.g = w.g; o.j = w.j; o.pad = 0; dst[r] = o; }
-    }
-}
-
 template <typename TE, int L, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ order,
