@@ -146,6 +146,16 @@ XC_API int xc_confmat_csr_compact(xc_ctx *ctx, const void *t_data, const int32_t
                                   const int64_t *t_ptr, int dtype, const int32_t *pred_idx, int k,
                                   int64_t n, int64_t m, int order, double *tp, double *fp,
                                   double *fn, void *stream);
+/* XC_SUM_ORDERED sums for a CSR truth matrix through its column-major copy (c_data, c_rows, c_ptr:
+ * for every label its stored entries in row order -- a stable sort of the CSR by label, built once
+ * per call by the host shim).  One warp per label adds that label's contributions strictly in row
+ * order, bit-identical to xc_confmat_csr_compact(XC_SUM_ORDERED).  Only valid when every predicted
+ * label is stored in its row: *lone_flag_dev is set to 1 otherwise and the caller must use the
+ * row-walking entry point instead.                                                              */
+XC_API int xc_confmat_csc_ordered(xc_ctx *ctx, const void *c_data, int dtype, const int32_t *c_rows,
+                                  const int64_t *c_ptr, const int32_t *t_idx, const int64_t *t_ptr,
+                                  const int32_t *pred_idx, int k, int64_t n, int64_t m, double *tp,
+                                  double *fp, double *fn, int *lone_flag_dev, void *stream);
 /* column sums of a dense / CSR matrix in float64 (fast order) */
 XC_API int xc_colsum_dense(xc_ctx *ctx, const void *x, int dtype, int64_t n, int64_t m, int64_t ld,
                            double *out, void *stream);

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "xc_confmat_dense_compact": [_vp, _int, _i64, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp],
     "xc_confmat_csr": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp],
     "xc_confmat_csr_compact": [_vp, _vp, _vp, _int, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp],
+    "xc_confmat_csc_ordered": [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     "xc_colsum_dense": [_vp, _int, _i64, _i64, _i64, _vp, _vp],
     "xc_colsum_csr": [_vp, _int, _vp, _i64, _i64, _vp, _vp],
     "xc_utility": [_MP, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp],

@@ -130,8 +130,7 @@ class BcaSession:
             if self.comm.world > 1:
                 raise NotImplementedError("sequential-exact BCA runs on one GPU (replicas only)")
             if self.is_csr:
-                self.ctx.call("xc_confmat_csr_compact", dev.ptr(d.data), dev.ptr(d.indices), dev.ptr(d.indptr), d.code,
-                              dev.ptr(self.pred), k, d.n, d.m, order, self._sp(0), self._sp(1), self._sp(2), self._s())
+                self._recompute_csr_ordered()
             else:
                 self.ctx.call("xc_confmat_dense_compact", dev.ptr(d.t), d.code, d.ld, dev.ptr(self.pred), k, d.n, d.m,
                               order, None, self._sp(0), self._sp(1), self._sp(2), self._s())
@@ -155,6 +154,28 @@ class BcaSession:
         else:  # -tp - fp - fn + n   (confusion_matrix.py:397, n = number of rows)
             n_total = self.comm.n_global(self.n)
             self.state[3] = -self.state[0] - self.state[1] - self.state[2] + n_total
+
+    def _recompute_csr_ordered(self) -> None:
+        """Row-ordered per-label sums for CSR rows.  The probabilities never change, so their
+        column-major copy (stable sort by label = every label's entries in row order) is built once;
+        one warp per label then adds its column strictly in row order."""
+        d, k = self.data, self.k
+        if getattr(self, "_csc", None) is None:
+            counts = (d.indptr[1:] - d.indptr[:-1])
+            row_of = torch.repeat_interleave(torch.arange(d.n, device=self.device, dtype=torch.int32), counts)
+            perm = torch.sort(d.indices, stable=True).indices
+            c_ptr = torch.zeros(d.m + 1, dtype=torch.int64, device=self.device)
+            c_ptr[1:] = torch.bincount(d.indices, minlength=d.m).cumsum(0)
+            self._csc = (d.data[perm].contiguous(), row_of[perm].contiguous(), c_ptr)
+            self._lone = torch.zeros(1, dtype=torch.int32, device=self.device)
+        c_data, c_rows, c_ptr = self._csc
+        self.ctx.call("xc_confmat_csc_ordered", dev.ptr(c_data), d.code, dev.ptr(c_rows), dev.ptr(c_ptr),
+                      dev.ptr(d.indices), dev.ptr(d.indptr), dev.ptr(self.pred), k, d.n, d.m, self._sp(0), self._sp(1),
+                      self._sp(2), dev.ptr(self._lone), self._s())
+        if int(self._lone.item()):   # a predicted label that its row does not store: row-walking kernel
+            self.ctx.call("xc_confmat_csr_compact", dev.ptr(d.data), dev.ptr(d.indices), dev.ptr(d.indptr), d.code,
+                          dev.ptr(self.pred), k, d.n, d.m, XC_SUM_ORDERED, self._sp(0), self._sp(1), self._sp(2),
+                          self._s())
 
     def wave_rows(self) -> int:
         """rows of one full wave of the dense batch kernel (0 for CSR: one warp per row)"""

@@ -639,6 +639,268 @@ bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
     }
 }
 
+// ---- CSR, register-staged fast path ------------------------------------------------------------------
+// The generic kernel above walks every step through ~30 dependent L2 round trips (order -> indptr ->
+// row -> binary searches -> state ...): 26 us per instance.  Here a parallel prologue resolves all
+// order-dependent indirections for the whole sweep (row start, row length, the row's current
+// prediction -- a row is visited once per sweep, so its prediction cannot change before its turn), the
+// walking warp prefetches the next row's entries into registers one step ahead, matches prediction and
+// row by shuffles instead of searches, keeps the touched state in registers from "remove" to "re-add"
+// and stores it once.  What remains per step is one L2 gather of the state, the float64 gains and the
+// warp top-k.  Rows with more than 32 * CSR_RMAX stored labels take the generic per-row routine.
+constexpr int CSR_RMAX = 4;
+
+__global__ void __launch_bounds__(256)
+csr_step_meta_kernel(const int32_t *__restrict__ order, const int64_t *__restrict__ indptr,
+                     const int32_t *__restrict__ pred_idx, int k, int64_t n_order, int64_t *__restrict__ step_ts,
+                     int32_t *__restrict__ step_nz, int32_t *__restrict__ step_pred)
+{
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (s >= n_order) return;
+    const int64_t row = order[s];
+    const int64_t ts = indptr[row];
+    step_ts[s] = ts;
+    step_nz[s] = (int32_t)(indptr[row + 1] - ts);
+    for (int t = 0; t < k; ++t) step_pred[s * k + t] = pred_idx[row * k + t];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32)
+bca_exact_csr_fast_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                          const int32_t *__restrict__ order, const int64_t *__restrict__ step_ts,
+                          const int32_t *__restrict__ step_nz, const int32_t *__restrict__ step_pred, int64_t n_order,
+                          int k, xc_metric_params p, int greedy, int32_t *pred_idx, double *tp, double *fp, double *fn,
+                          double *tn)
+{
+    const int lane = lane_id();
+    const double nd = p.n_div;
+    const T one = (T)1;
+    // software pipeline: entries of step s+1 and metadata of step s+2 are in flight during step s
+    int64_t ts_c = 0, ts_n = 0;
+    int nz_c = 0, nz_n = 0, pj_c = -1, pj_n = -1;
+    int idx_c[CSR_RMAX], idx_n[CSR_RMAX];
+    T val_c[CSR_RMAX], val_n[CSR_RMAX];
+#pragma unroll
+    for (int t = 0; t < CSR_RMAX; ++t) { idx_c[t] = idx_n[t] = -2; val_c[t] = val_n[t] = (T)0; }
+    if (n_order > 0) {
+        ts_c = step_ts[0];
+        nz_c = step_nz[0];
+        pj_c = lane < k ? step_pred[lane] : -1;
+#pragma unroll
+        for (int t = 0; t < CSR_RMAX; ++t) {
+            int q = lane + 32 * t;
+            if (q < nz_c && nz_c <= 32 * CSR_RMAX) { idx_c[t] = indices[ts_c + q]; val_c[t] = data[ts_c + q]; }
+        }
+    }
+    if (n_order > 1) {
+        ts_n = step_ts[1];
+        nz_n = step_nz[1];
+        pj_n = lane < k ? step_pred[k + lane] : -1;
+    }
+    for (int64_t s = 0; s < n_order; ++s) {
+        // ---- prefetch: entries of step s+1 (its row start is already known), metadata of step s+2
+#pragma unroll
+        for (int t = 0; t < CSR_RMAX; ++t) {
+            int q = lane + 32 * t;
+            idx_n[t] = -2;
+            val_n[t] = (T)0;
+            if (s + 1 < n_order && q < nz_n && nz_n <= 32 * CSR_RMAX) {
+                idx_n[t] = indices[ts_n + q];
+                val_n[t] = data[ts_n + q];
+            }
+        }
+        int64_t ts_nn = 0;
+        int nz_nn = 0, pj_nn = -1;
+        if (s + 2 < n_order) {
+            ts_nn = step_ts[s + 2];
+            nz_nn = step_nz[s + 2];
+            pj_nn = lane < k ? step_pred[(s + 2) * k + lane] : -1;
+        }
+        const int64_t row = order[s];
+        int32_t *prow = pred_idx + row * k;
+
+        if (nz_c > 32 * CSR_RMAX) {
+            // ---- long row: generic per-row routine (global-memory searches) ------------------------------
+            const int64_t ts = ts_c, te = ts_c + nz_c;
+            int pj = pj_c;
+            if (!greedy) csr_apply_row<T>(data, indices, ts, te, pj, k, -1.0, tp, fp, fn, tn);
+            WarpTopK<double> tk;
+            tk.init();
+            for (int64_t q0 = ts; q0 < te; q0 += 32) {
+                int64_t q = q0 + lane;
+                double g[1];
+                g[0] = NAN;
+                if (q < te) {
+                    const int j = indices[q];
+                    const T tv = data[q];
+                    const T om = one - tv;
+                    double neg_tp = tp[j], neg_fp = fp[j], pos_fn = fn[j];
+                    const double pos_tpp = (neg_tp + (double)tv) / nd;
+                    const double pos_fpp = (neg_fp + (double)om) / nd;
+                    const double neg_fnn = (pos_fn + (double)tv) / nd;
+                    neg_tp = neg_tp / nd; neg_fp = neg_fp / nd; pos_fn = pos_fn / nd;
+                    double pos_tn = -1.0, neg_tnn = -1.0;
+                    if (tn) { pos_tn = tn[j]; neg_tnn = (pos_tn + (double)om) / nd; pos_tn = pos_tn / nd; }
+                    const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, pos_tn, p.c1, p.beta2, p.eps);
+                    const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, neg_tnn, p.c1, p.beta2, p.eps);
+                    const double gg = up - un;
+                    g[0] = p.maximize ? gg : -gg;
+                }
+                if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<double, 1, false>(tk, g, q0 - ts, 1, k, -1);
+            }
+            int src = warp_rank_src(tk.idx, k);
+            int pos = __shfl_sync(XC_FULL, tk.idx, src);
+            pj = (lane < k && pos != 0x7fffffff) ? indices[ts + pos] : -1;
+            if (lane < k) prow[lane] = pj;
+            csr_apply_row<T>(data, indices, ts, te, pj, k, 1.0, tp, fp, fn, tn);
+        } else {
+            // ---- register-staged row ---------------------------------------------------------------------
+            // which stored entries are currently predicted / which predicted labels are not stored
+            bool sel[CSR_RMAX];
+            bool pj_found = false;
+#pragma unroll
+            for (int t = 0; t < CSR_RMAX; ++t) sel[t] = false;
+            for (int x = 0; x < k; ++x) {
+                const int px = __shfl_sync(XC_FULL, pj_c, x);
+                bool any = false;
+#pragma unroll
+                for (int t = 0; t < CSR_RMAX; ++t) {
+                    const bool hit = px >= 0 && idx_c[t] == px;
+                    sel[t] |= hit;
+                    any |= hit;
+                }
+                const bool f = __any_sync(XC_FULL, any);
+                if (lane == x) pj_found = f;
+            }
+            // state of the touched labels -> registers
+            double stp[CSR_RMAX], sfp[CSR_RMAX], sfn[CSR_RMAX], stn[CSR_RMAX];
+#pragma unroll
+            for (int t = 0; t < CSR_RMAX; ++t) {
+                stp[t] = sfp[t] = sfn[t] = 0.0;
+                stn[t] = -1.0;
+                if (idx_c[t] >= 0) {
+                    stp[t] = tp[idx_c[t]];
+                    sfp[t] = fp[idx_c[t]];
+                    sfn[t] = fn[idx_c[t]];
+                    if (tn) stn[t] = tn[idx_c[t]];
+                }
+            }
+            // predicted label that the row does not store (lane x < k): fp / tn only
+            const bool lone = lane < k && pj_c >= 0 && !pj_found;
+            double lfp = 0.0, ltn = 0.0;
+            if (lone) {
+                lfp = fp[pj_c];
+                if (tn) ltn = tn[pj_c];
+            }
+            // ---- remove (numba_csr_functions.py:386-417)
+            if (!greedy) {
+#pragma unroll
+                for (int t = 0; t < CSR_RMAX; ++t) {
+                    if (idx_c[t] < 0) continue;
+                    if (sel[t]) {
+                        const double vtp = (double)mul_round(one, val_c[t]);
+                        const double vft = (double)mul_om_round(one, val_c[t]);
+                        const double vfn = (double)mul_om_round(val_c[t], one);
+                        stp[t] = stp[t] - vtp;
+                        sfp[t] = sfp[t] - vft;
+                        sfn[t] = sfn[t] - vfn;
+                        if (tn) stn[t] = (((stn[t] - 1.0) + vtp) + vft) + vfn;
+                    } else {
+                        const double vfn = (double)val_c[t];
+                        sfn[t] = sfn[t] - vfn;
+                        if (tn) stn[t] = (stn[t] - 1.0) + vfn;
+                    }
+                }
+                if (lone) {
+                    lfp = lfp - (double)one;
+                    if (tn) ltn = (ltn - 1.0) + (double)one;
+                }
+            }
+            // ---- gains (block_coordinate.py:248-282) and top-k of the stored entries
+            WarpTopK<double> tk;
+            tk.init();
+#pragma unroll
+            for (int t = 0; t < CSR_RMAX; ++t) {
+                double g[1];
+                g[0] = NAN;
+                if (idx_c[t] >= 0) {
+                    const T tv = val_c[t];
+                    const T om = one - tv;
+                    double neg_tp = stp[t], neg_fp = sfp[t], pos_fn = sfn[t];
+                    const double pos_tpp = (neg_tp + (double)tv) / nd;
+                    const double pos_fpp = (neg_fp + (double)om) / nd;
+                    const double neg_fnn = (pos_fn + (double)tv) / nd;
+                    neg_tp = neg_tp / nd; neg_fp = neg_fp / nd; pos_fn = pos_fn / nd;
+                    double pos_tn = -1.0, neg_tnn = -1.0;
+                    if (tn) { pos_tn = stn[t]; neg_tnn = (pos_tn + (double)om) / nd; pos_tn = pos_tn / nd; }
+                    const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, pos_tn, p.c1, p.beta2, p.eps);
+                    const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, neg_tnn, p.c1, p.beta2, p.eps);
+                    const double gg = up - un;
+                    g[0] = p.maximize ? gg : -gg;
+                }
+                if (32 * t < nz_c && __any_sync(XC_FULL, tk.passes(g[0])))
+                    xc_scan_insert<double, 1, false>(tk, g, 32 * t, 1, k, -1);
+            }
+            // new selection: positions inside the row, ascending (== ascending label)
+            const int src = warp_rank_src(tk.idx, k);
+            const int pos = __shfl_sync(XC_FULL, tk.idx, src);
+            // label of position `pos` lives in lane pos % 32, slot pos / 32
+            int newp = -1;
+            {
+                const int want_lane = pos == 0x7fffffff ? 0 : (pos & 31), want_t = pos == 0x7fffffff ? 0 : (pos >> 5);
+                int got = -1;
+#pragma unroll
+                for (int t = 0; t < CSR_RMAX; ++t) {
+                    const int v = __shfl_sync(XC_FULL, idx_c[t], want_lane);
+                    if (t == want_t) got = v;
+                }
+                if (lane < k && pos != 0x7fffffff) newp = got;
+            }
+            if (lane < k) prow[lane] = newp;
+            // ---- re-add with the new selection (numba_csr_functions.py:421-452), store once
+            bool nsel[CSR_RMAX];
+#pragma unroll
+            for (int t = 0; t < CSR_RMAX; ++t) nsel[t] = false;
+            for (int x = 0; x < k; ++x) {
+                const int px = __shfl_sync(XC_FULL, newp, x);
+#pragma unroll
+                for (int t = 0; t < CSR_RMAX; ++t) nsel[t] |= (px >= 0 && idx_c[t] == px);
+            }
+#pragma unroll
+            for (int t = 0; t < CSR_RMAX; ++t) {
+                if (idx_c[t] < 0) continue;
+                if (nsel[t]) {
+                    const double vtp = (double)mul_round(one, val_c[t]);
+                    const double vft = (double)mul_om_round(one, val_c[t]);
+                    const double vfn = (double)mul_om_round(val_c[t], one);
+                    stp[t] = stp[t] + vtp;
+                    sfp[t] = sfp[t] + vft;
+                    sfn[t] = sfn[t] + vfn;
+                    if (tn) stn[t] = (((stn[t] + 1.0) - vtp) - vft) - vfn;
+                } else {
+                    const double vfn = (double)val_c[t];
+                    sfn[t] = sfn[t] + vfn;
+                    if (tn) stn[t] = (stn[t] + 1.0) - vfn;
+                }
+                tp[idx_c[t]] = stp[t];
+                fp[idx_c[t]] = sfp[t];
+                fn[idx_c[t]] = sfn[t];
+                if (tn) tn[idx_c[t]] = stn[t];
+            }
+            if (lone && !greedy) {   // the new selection is a subset of the row: this label only left
+                fp[pj_c] = lfp;
+                if (tn) tn[pj_c] = ltn;
+            }
+            __syncwarp();
+        }
+        // ---- rotate the pipeline
+        ts_c = ts_n; nz_c = nz_n; pj_c = pj_n;
+#pragma unroll
+        for (int t = 0; t < CSR_RMAX; ++t) { idx_c[t] = idx_n[t]; val_c[t] = val_n[t]; }
+        ts_n = ts_nn; nz_n = nz_nn; pj_n = pj_nn;
+    }
+}
+
 // ---- coverage (block_coordinate.py:539-580) ---------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(32)
@@ -903,12 +1165,35 @@ extern "C" int xc_bca_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, 
     if (n_order == 0) return XC_OK;
     double *tn_arg = p->skip_tn ? nullptr : tn;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
+    static int generic_only = -1;   // $XCOLUMNS_B200_EXACT_CSR=generic forces the unstaged kernel
+    if (generic_only < 0) {
+        const char *e = getenv("XCOLUMNS_B200_EXACT_CSR");
+        generic_only = (e && e[0] == 'g') ? 1 : 0;
+    }
+    if (generic_only) {
+        if (dtype == XC_F32)
+            bca_exact_csr_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
+        else
+            bca_exact_csr_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
+        XC_LAUNCHED(ctx);
+        return XC_OK;
+    }
+    // per-step metadata resolved in parallel: row start (int64), row length (int32), current prediction
+    void *scratch = nullptr;
+    const size_t off_nz = (size_t)n_order * 8, off_pred = off_nz + (((size_t)n_order * 4 + 7) & ~(size_t)7);
+    int rc = xc_ctx_scratch(ctx, off_pred + (size_t)n_order * k * 4, &scratch);
+    if (rc) return rc;
+    int64_t *step_ts = (int64_t *)scratch;
+    int32_t *step_nz = (int32_t *)((uint8_t *)scratch + off_nz);
+    int32_t *step_pred = (int32_t *)((uint8_t *)scratch + off_pred);
+    csr_step_meta_kernel<<<(unsigned)((n_order + 255) / 256), 256, 0, st>>>(order, indptr, pred_idx, k, n_order, step_ts,
+                                                                            step_nz, step_pred);
+    XC_LAUNCHED(ctx);
     if (dtype == XC_F32)
-        bca_exact_csr_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
-    else if (dtype == XC_F64)
-        bca_exact_csr_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, order, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
+        bca_exact_csr_fast_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, order, step_ts, step_nz, step_pred, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
     else
-        return XC_ERR_UNSUPPORTED;
+        bca_exact_csr_fast_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, order, step_ts, step_nz, step_pred, n_order, k, *p, greedy, pred_idx, tp, fp, fn, tn_arg);
     XC_LAUNCHED(ctx);
     return XC_OK;
 }

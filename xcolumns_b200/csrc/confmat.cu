@@ -347,6 +347,71 @@ confmat_csrc_ordered_kernel(const T *t_data, const int32_t *t_idx, const int64_t
     }
 }
 
+// ---- CSR truth, compact prediction, ORDERED sums through a column-major copy -------------------------
+// The row-walking ordered kernel above is one CTA doing binary searches row after row (15 us per row).
+// The per-label sums only need each label's contributions in row order, which is exactly a CSC column
+// of y_proba (built once per call by the host shim with a stable sort; the probabilities never change).
+// One warp per label: 32 entries at a time are loaded / matched against their rows' predictions in
+// parallel, then added in lane order (a 32-step shuffle chain), i.e. strictly in row order.
+// Only valid when every predicted label is stored in its row (always true for predictions the sweeps
+// produce); confmat_lone_check_kernel verifies it and the host falls back to the row-walking kernel.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+confmat_csc_ordered_kernel(const T *__restrict__ c_data, const int32_t *__restrict__ c_rows,
+                           const int64_t *__restrict__ c_ptr, const int32_t *__restrict__ pred, int k, int64_t m,
+                           double *tp, double *fp, double *fn)
+{
+    const int lane = lane_id();
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const T one = (T)1;
+    for (int64_t j = warp0; j < m; j += (int64_t)gridDim.x * (kThreads / 32)) {
+        const int64_t s = c_ptr[j], e = c_ptr[j + 1];
+        double stp = 0.0, sfp = 0.0, sfn = 0.0;   // identical in every lane
+        for (int64_t q0 = s; q0 < e; q0 += 32) {
+            const int64_t q = q0 + lane;
+            double ctp = 0.0, cfp = 0.0, cfn = 0.0;
+            if (q < e) {
+                const int64_t i = c_rows[q];
+                const T v = c_data[q];
+                bool sel = false;
+                for (int t = 0; t < k; ++t) sel |= (__ldg(pred + i * k + t) == (int)j);
+                if (sel) {
+                    ctp = (double)mul_round(one, v);
+                    cfp = (double)mul_om_round(one, v);
+                    cfn = (double)mul_om_round(v, one);
+                } else {
+                    cfn = (double)v;
+                }
+            }
+            const int cnt = (int)min((int64_t)32, e - q0);
+            for (int l = 0; l < cnt; ++l) {   // strictly in row order; adding an exact 0.0 is a no-op
+                stp = stp + __shfl_sync(XC_FULL, ctp, l);
+                sfp = sfp + __shfl_sync(XC_FULL, cfp, l);
+                sfn = sfn + __shfl_sync(XC_FULL, cfn, l);
+            }
+        }
+        if (lane == 0) {
+            tp[j] = stp;
+            fp[j] = sfp;
+            fn[j] = sfn;
+        }
+    }
+}
+
+// flag = 1 if some predicted label is not stored in its row
+__global__ void __launch_bounds__(kThreads)
+confmat_lone_check_kernel(const int32_t *__restrict__ t_idx, const int64_t *__restrict__ t_ptr,
+                          const int32_t *__restrict__ pred, int k, int64_t n, int *flag)
+{
+    const int64_t total = n * k;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+        const int j = pred[t];
+        if (j < 0) continue;
+        const int64_t i = t / k;
+        if (csr_find(t_idx, t_ptr[i], t_ptr[i + 1], j) < 0) *flag = 1;
+    }
+}
+
 // ---- utility: mean / sum over labels of the binary metric, fixed reduction order -----------------
 __global__ void __launch_bounds__(256)
 utility_kernel(xc_metric_params p, int agg, const double *tp, const double *fp, const double *fn, const double *tn,
@@ -555,6 +620,28 @@ extern "C" int xc_utility(xc_ctx *ctx, const xc_metric_params *p, int agg, const
     if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
     utility_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, agg, tp, fp, fn, tn, m, out_dev, ctx->red_partials,
                                                             ctx->red_counter);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_confmat_csc_ordered(xc_ctx *ctx, const void *c_data, int dtype, const int32_t *c_rows,
+                                      const int64_t *c_ptr, const int32_t *t_idx, const int64_t *t_ptr,
+                                      const int32_t *pred_idx, int k, int64_t n, int64_t m, double *tp, double *fp,
+                                      double *fn, int *lone_flag_dev, void *stream)
+{
+    if (!ctx || !c_rows || !c_ptr || !t_ptr || !pred_idx || !tp || !fp || !fn || !lone_flag_dev) return XC_ERR_INVALID;
+    if (n <= 0 || m <= 0 || k < 1) return XC_ERR_INVALID;
+    if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    XC_CUDA_TRY(ctx, cudaMemsetAsync(lone_flag_dev, 0, sizeof(int), st));
+    confmat_lone_check_kernel<<<cap_grid(ctx, (n * k + kThreads - 1) / kThreads), kThreads, 0, st>>>(t_idx, t_ptr, pred_idx,
+                                                                                                  k, n, lone_flag_dev);
+    XC_LAUNCHED(ctx);
+    int grid = cap_grid(ctx, (m + 7) / 8);
+    if (dtype == XC_F32)
+        confmat_csc_ordered_kernel<float><<<grid, kThreads, 0, st>>>((const float *)c_data, c_rows, c_ptr, pred_idx, k, m, tp, fp, fn);
+    else
+        confmat_csc_ordered_kernel<double><<<grid, kThreads, 0, st>>>((const double *)c_data, c_rows, c_ptr, pred_idx, k, m, tp, fp, fn);
     XC_LAUNCHED(ctx);
     return XC_OK;
 }
