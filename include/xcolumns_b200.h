@@ -285,24 +285,32 @@ XC_API int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4,
 
 /* One dense Frank-Wolfe iteration as two calls (ref: frank_wolfe.py:589-637); between them the
  * caller all-reduces raw[0..2m) when rows are sharded over ranks.
- *   begin : have_grad != 0: scal[0] = metric(Cm) and (a_row, b_row) = next classifier from the
- *           gradient (float32 rows, e.g. row i of the classifier matrices); then the fused
- *           weighted top-k + accumulation of raw = [tp, cnt].  ab64: 2*m doubles, used when
- *           dtype == XC_F64 (the float32 rows are widened like numpy promotes them).
+ *   begin : fused weighted top-k + accumulation of raw = [tp, cnt] with the classifier held in the
+ *           float32 rows (a_row, b_row) (e.g. row i of the classifier matrices; written by the
+ *           previous finish call).  ab64: 2*m doubles, used when dtype == XC_F64 (the float32 rows
+ *           are widened like numpy promotes them).  raw_is_zero != 0: raw was already cleared by
+ *           the previous finish call (zero_raw), no memset is issued.
  *   finish: first != 0: Cm = confusion vectors of classifier 0, scal[0] = metric(Cm).  Otherwise
  *           Ci = confusion vectors of classifier i, scal[1] = metric(Ci), scal[2..3] = line search
  *           (alphas_dev != NULL) or the fixed step (alpha passed in fixed_alpha), Cm = (1-a) Cm + a Ci,
- *           scal[4] = metric(Cm).  The fixed-step path copies from host memory synchronously
- *           with respect to `stream` ordering only.                                              */
-XC_API int xc_fw_step_begin(xc_ctx *ctx, const xc_metric_params *p, int have_grad, const void *eta,
-                            int dtype, int64_t n, int64_t m, int64_t ld, const void *y_true,
-                            int64_t ld_true, const double *Cm, float *a_row, float *b_row,
-                            double *ab64, int k, double *raw, double *scal, void *stream);
-XC_API int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int first, const double *raw,
+ *           scal[4] = metric(Cm).  In both cases, when a_next/b_next are given, the NEXT classifier
+ *           (gradient of the metric at the new Cm, :591-596) is written to them and scal_next[0]
+ *           receives metric(Cm) (the next iteration's "old utility"); zero_raw != 0 clears raw.
+ *           The per-label work is fused into two kernels (confusion vectors + utility +
+ *           line-search linearisation; combine + utility + gradient).                           */
+XC_API int xc_fw_step_begin(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m, int64_t ld,
+                            const void *y_true, int64_t ld_true, const float *a_row,
+                            const float *b_row, double *ab64, int k, double *raw, int raw_is_zero,
+                            void *stream);
+XC_API int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int first, double *raw,
                              const double *colsum, int64_t m, double n_global, int normalize,
                              int skip_tn, double *Cm, double *Ci, const double *alphas_dev,
                              int64_t n_alphas, double fixed_alpha, double *scratch_dev, double *scal,
+                             float *a_next, float *b_next, double *scal_next, int zero_raw,
                              void *stream);
+/* byte offset, inside the line-search scratch, of the control block {int count, full, slices, tiles}
+ * the two-stage search leaves behind (diagnostics: number of float64 candidates)               */
+XC_API int64_t xc_fw_alpha_ctl_offset(int64_t m, int64_t n_alphas);
 
 #ifdef __cplusplus
 }

@@ -63,8 +63,9 @@ _SIGNATURES = {
     "xc_fw_metric_grad": [_MP, _vp, _i64, _vp, _vp, _vp, _vp],
     "xc_fw_alpha_search": [_MP, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp],
     "xc_fw_combine": [_vp, _vp, _i64, _vp, _vp],
-    "xc_fw_step_begin": [_MP, _int, _vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp],
-    "xc_fw_step_finish": [_MP, _int, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp],
+    "xc_fw_step_begin": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _int, _vp, _int, _vp],
+    "xc_fw_step_finish": [_MP, _int, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, _vp,
+                          _vp, _int, _vp],
 }
 
 _lib = None
@@ -96,6 +97,8 @@ def load():
         lib.xc_sm_count.argtypes = [C.c_void_p]
         lib.xc_fw_alpha_scratch_bytes.argtypes = [C.c_int64, C.c_int64]
         lib.xc_fw_alpha_scratch_bytes.restype = C.c_int64
+        lib.xc_fw_alpha_ctl_offset.argtypes = [C.c_int64, C.c_int64]
+        lib.xc_fw_alpha_ctl_offset.restype = C.c_int64
         lib.xc_bca_coef_len.argtypes = [C.c_int64]
         lib.xc_bca_coef_len.restype = C.c_int64
         lib.xc_fill_pred_dense_host.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,

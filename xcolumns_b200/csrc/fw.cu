@@ -55,6 +55,52 @@ fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_
     }
 }
 
+// Same iterate with the classifier staged through shared memory (xc_scan.cuh, "CTA-cooperative scan"):
+// one row per warp, kWarpsS warps per CTA walking the column chunks together.
+constexpr int kThreadsS = 256;
+
+template <typename TE, int OCC>
+__global__ void __launch_bounds__(kThreadsS, OCC)
+fw_iterate_dense_staged_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_t ld,
+                               const TE *__restrict__ y_true, int64_t ld_true, StageMulAdd<TE> st, int k, double *tp,
+                               double *cnt, int32_t *__restrict__ pred_idx)
+{
+    __shared__ __align__(16) char smem[2 * XC_STAGE_BYTES];
+    constexpr int W = kThreadsS / 32;
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int64_t ngroups = (n + W - 1) / W;
+    XcStagePipe<StageMulAdd<TE>> pipe(st, m, smem);
+    if ((int64_t)blockIdx.x >= ngroups) return;
+    pipe.prime();
+    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        int64_t i = grp * W + wid;
+        const bool valid = i < n;
+        if (!valid) i = grp * W;
+        const TE *rp = eta + i * ld;
+        WarpTopK<TE> tk;
+        tk.init();
+        const bool last_grp = grp + gridDim.x >= ngroups;
+        for (int c = 0; c < pipe.nch; ++c) {
+            // (a variant that issued the next double step's loads before the tile barrier was measured
+            // slower: 372 vs 351 us at 14 k x 31 k -- the extra live registers cost more than the bubbles)
+            const char *buf = pipe.acquire(!(last_grp && c + 1 == pipe.nch));
+            const int64_t cbeg = (int64_t)c * StageMulAdd<TE>::TC;
+            xc_scan_chunk_staged<TE, TE, false>(rp, cbeg, min(m, cbeg + StageMulAdd<TE>::TC), st, buf, tk, -1, k);
+        }
+        if (!valid) continue;
+        const int j = tk.idx;
+        if (lane < k && j != 0x7fffffff) {
+            atomicAdd(tp + j, (double)__ldg(y_true + i * ld_true + j));
+            atomicAdd(cnt + j, 1.0);
+        }
+        if (pred_idx) {
+            int src = warp_rank_src(j, k);
+            int v = __shfl_sync(XC_FULL, j, src);
+            if (lane < k) pred_idx[i * k + lane] = v == 0x7fffffff ? -1 : v;
+        }
+    }
+}
+
 __device__ __forceinline__ int64_t csr_find(const int32_t *idx, int64_t s, int64_t e, int j)
 {
     while (s < e) {
@@ -205,47 +251,75 @@ fw_metric_grad_kernel(xc_metric_params p, const double *tp, const double *fp, co
 // first strict maximum (utils.py:174-184): 10^4 x m IEEE float64 divisions per iteration (0.6-1.8 ms
 // at m = 31 k, several times the streaming pass).  For the metrics of the form c*tp/D with D linear
 // in the confusion entries (precision, recall, F-beta, Jaccard) the search runs in two stages:
-//   1. every grid point in float32 from a per-label linearisation (T0 + a dT) / (D0 + a dD)
-//      (2 FFMA + 1 MUFU.RCP + 1 FMUL + 1 FADD per term; measured 110 us.  A float64 variant with a
-//      Newton-refined reciprocal was measured at 394 us: vector FP64 is the scarce resource here);
-//   2. the grid points within 2e-5 (relative) of the float32 maximum -- a superset of every point
-//      that can be the exact maximum, the float32 pass is accurate to ~2e-6 -- are re-evaluated
-//      with the reference's exact float64 expression; the first strict maximum among them wins.
-// If more than ALPHA_MAX_CAND points qualify (objective flat in alpha to 2e-5) the whole grid is
-// evaluated exactly.  Metrics that use tn always take the exact path.
-constexpr int AT_FULL = 16;         // grid points per block, float64 kernel over the whole grid
-constexpr int AT_CAND = 4;          // ... over the candidate list (few points: spread them over the SMs)
+//   1. every grid point in float32 from a per-label linearisation T(a)/D(a) = (T0 + a dT) / (D0 + a dD).
+//      The reciprocal unit (MUFU, 16 lanes/clk/SM) is the scarce pipe, so two labels share one
+//      reciprocal: T1/D1 + T2/D2 = (T1 D2 + T2 D1) / (D1 D2), factors kept in product form so that no
+//      precision is lost to cancelling polynomial coefficients (9 FP32 + 1 MUFU per label pair;
+//      measured: 110 us for the one-label-per-reciprocal version at m = 31 k, 10^4 points);
+//   2. the grid points within 1e-5 (relative) of the float32 maximum -- the float32 pass is accurate to
+//      ~3e-6 in the worst case, so this is a superset of every point that can be the float64 maximum --
+//      are re-evaluated with the reference's float64 expression; the first strict maximum among them
+//      wins.  The candidates are spread over all SMs (label slices chosen on the device from the
+//      candidate count); partial sums are combined in a fixed order, so the result is reproducible.
+// If more than ALPHA_MAX_CAND points qualify (objective flat in alpha) the whole grid is evaluated in
+// float64.  Metrics that use tn always take that path.
+constexpr int AT64 = 4;             // grid points per block tile, float64 kernel
 constexpr int AT32 = 32;            // grid points per block, stage-1 kernel
+constexpr int ALPHA_LS = 8;         // label slices of the stage-1 kernel (blockIdx.y)
+constexpr int ALPHA_LS2_MAX = 32;   // max label slices of the float64 kernel
 constexpr int ALPHA_MAX_CAND = 2048;
+constexpr float ALPHA_WINDOW = 1e-5f;
+constexpr int ATR = 16;             // candidate slots per block, refinement kernel
+constexpr int ALPHA_LSR = 8;        // label slices of the refinement kernel (blockIdx.y)
+constexpr float ALPHA_REFINE_ULP = 2.5e-7f;  // error unit of the refinement's bound (~2 ulp of float32)
 
 struct AlphaCtl {
-    int count;   // number of candidate slots (or n_alphas + 1 when full)
-    int full;    // 1: evaluate the whole grid in float64
+    int count;   // number of slots to evaluate in float64 (candidates, or n_alphas + 1 when full)
+    int full;    // 1: slots are the grid points themselves
+    int slices;  // label slices per slot tile
+    int tiles;   // ceil(count / AT64)
+    int qstar;   // stage-1 arg-max (grid point index)
+    int pad[3];
 };
 
-__global__ void __launch_bounds__(kThreads)
-fw_alpha_prep_kernel(xc_metric_params p, const double *__restrict__ C, const double *__restrict__ Ci, int64_t m,
-                     float4 *__restrict__ lin)
+__device__ __forceinline__ float4 alpha_lin(const xc_metric_params &p, double tp, double fp, double fn, double tpi,
+                                            double fpi, double fni, float *E)
 {
-    int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (j >= m) return;
-    const double tp = C[j], fp = C[m + j], fn = C[2 * m + j];
-    const double tpi = Ci[j], fpi = Ci[m + j], fni = Ci[2 * m + j];
     double D0, D1;
     if (p.metric == XC_METRIC_PRECISION) { D0 = tp + fp + p.eps; D1 = tpi + fpi + p.eps; }
     else if (p.metric == XC_METRIC_RECALL) { D0 = tp + fn + p.eps; D1 = tpi + fni + p.eps; }
     else if (p.metric == XC_METRIC_JACCARD) { D0 = tp + fp + fn + p.eps; D1 = tpi + fpi + fni + p.eps; }
     else { D0 = p.beta2 * (tp + fp) + tp + fn + p.eps; D1 = p.beta2 * (tpi + fpi) + tpi + fni + p.eps; }
-    lin[j] = make_float4((float)tp, (float)(tpi - tp), (float)D0, (float)(D1 - D0));
+    if (E) *E = (float)((tpi - tp) * D0 - tp * (D1 - D0));  // dT D0 - T0 dD, formed in float64
+    return make_float4((float)tp, (float)(tpi - tp), (float)D0, (float)(D1 - D0));
 }
 
-constexpr int ALPHA_LSPLIT = 4;  // label slices per grid point tile (blockIdx.y)
-
 __global__ void __launch_bounds__(kThreads)
-fw_alpha_evalfast_kernel(const float4 *__restrict__ lin, int64_t m, const double *__restrict__ alphas,
-                         int64_t n_alphas, float scale, float *__restrict__ vals_fast)
+fw_alpha_prep_kernel(xc_metric_params p, const double *__restrict__ C, const double *__restrict__ Ci, int64_t m,
+                     float4 *__restrict__ lin, float *__restrict__ linE)
 {
-    __shared__ float sm[AT32][kThreads / 32];
+    int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j == m && (m & 1)) {  // pad to a whole label pair: term 0 / 1
+        lin[m] = make_float4(0.f, 0.f, 1.f, 0.f);
+        linE[m] = 0.f;
+    }
+    if (j >= m) return;
+    lin[j] = alpha_lin(p, C[j], C[m + j], C[2 * m + j], Ci[j], Ci[m + j], Ci[2 * m + j], linE + j);
+}
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// part[slice][q] = sum over the slice's label pairs of T/D at grid point q (q = 0 is alpha = 0)
+__global__ void __launch_bounds__(kThreads)
+fw_alpha_evalfast_kernel(const float4 *__restrict__ lin, int64_t npairs, const double *__restrict__ alphas,
+                         int64_t n_alphas, float *__restrict__ part)
+{
+    __shared__ float sm[AT32][kThreads];
     const int64_t q0 = (int64_t)blockIdx.x * AT32;
     float al[AT32], acc[AT32];
 #pragma unroll
@@ -254,133 +328,357 @@ fw_alpha_evalfast_kernel(const float4 *__restrict__ lin, int64_t m, const double
         al[t] = (q == 0 || q > n_alphas) ? 0.f : (float)alphas[q - 1];
         acc[t] = 0.f;
     }
-    // <= m / (256 * ALPHA_LSPLIT) terms per float32 accumulator (30 at m = 31 k): worst-case
-    // accumulation error ~2e-6 relative, well inside the 2e-5 candidate window of stage 2
-    for (int64_t j = (int64_t)blockIdx.y * kThreads + threadIdx.x; j < m; j += (int64_t)kThreads * ALPHA_LSPLIT) {
-        const float4 l = __ldg(lin + j);
+    // the linearisation comes from L2 (~1 us away under load) and one pair only feeds ~300 instructions:
+    // the next pair is fetched while the current one is evaluated
+    int64_t pr = (int64_t)blockIdx.y * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)kThreads * ALPHA_LS;
+    float4 u = make_float4(0.f, 0.f, 1.f, 0.f), w = u;
+    if (pr < npairs) { u = __ldg(lin + 2 * pr); w = __ldg(lin + 2 * pr + 1); }
+    for (; pr < npairs; pr += stride) {
+        float4 un = u, wn = w;
+        if (pr + stride < npairs) { un = __ldg(lin + 2 * (pr + stride)); wn = __ldg(lin + 2 * (pr + stride) + 1); }
 #pragma unroll
-        for (int t = 0; t < AT32; ++t)
-            acc[t] += __fdividef(fmaf(al[t], l.y, l.x), fmaf(al[t], l.w, l.z));
+        for (int t = 0; t < AT32; ++t) {
+            const float Ta = fmaf(al[t], u.y, u.x), Da = fmaf(al[t], u.w, u.z);
+            const float Tb = fmaf(al[t], w.y, w.x), Db = fmaf(al[t], w.w, w.z);
+            const float N = fmaf(Ta, Db, Tb * Da);
+            acc[t] = fmaf(N, rcp_approx(Da * Db), acc[t]);
+        }
+        u = un;
+        w = wn;
     }
+    // block reduction through shared memory in a fixed order: thread (t, s) adds the 32 values
+    // sm[t][32 s .. 32 s + 32) (rotated by the lane so that the 32 lanes hit 32 different banks)
 #pragma unroll
-    for (int t = 0; t < AT32; ++t) {
-        float v = acc[t];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(XC_FULL, v, o);
-        if ((threadIdx.x & 31) == 0) sm[t][threadIdx.x >> 5] = v;
-    }
+    for (int t = 0; t < AT32; ++t) sm[t][threadIdx.x] = acc[t];
     __syncthreads();
-    if (threadIdx.x < AT32) {
-        float v = 0.f;
-        for (int w = 0; w < kThreads / 32; ++w) v += sm[threadIdx.x][w];
-        int64_t q = q0 + threadIdx.x;
-        if (q <= n_alphas) atomicAdd(vals_fast + q, v * scale);
-    }
+    const int t = threadIdx.x >> 3, s = threadIdx.x & 7, lane = threadIdx.x & 31;
+    float v = 0.f;
+    for (int i = 0; i < 32; ++i) v += sm[t][s * 32 + ((i + lane) & 31)];
+    v += __shfl_xor_sync(XC_FULL, v, 1);
+    v += __shfl_xor_sync(XC_FULL, v, 2);
+    v += __shfl_xor_sync(XC_FULL, v, 4);
+    const int64_t q = q0 + t;
+    if (s == 0 && q <= n_alphas) part[(int64_t)blockIdx.y * (n_alphas + 1) + q] = v;
 }
 
-// candidates = grid points within 2e-5 (relative) of the stage-1 maximum, in grid order
+// candidates = grid points within ALPHA_WINDOW (relative) of the stage-1 maximum, in grid order
 __global__ void __launch_bounds__(1024)
-fw_alpha_cand_kernel(const float *__restrict__ vf, int64_t n_alphas, int *__restrict__ cand_q, AlphaCtl *ctl)
+fw_alpha_cand_kernel(const float *__restrict__ part, int64_t n_alphas, float scale, float *__restrict__ vfast,
+                     int *__restrict__ cand_q, AlphaCtl *ctl, int eval_ctas)
 {
     __shared__ float s_max[32];
-    __shared__ int s_cnt[1024];
-    __shared__ int s_base;
+    __shared__ int s_arg[32];
+    __shared__ int s_warp[32];
     const int64_t total = n_alphas + 1;
-    float mx = -INFINITY;
-    for (int64_t q = threadIdx.x; q < total; q += 1024) mx = fmaxf(mx, vf[q]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(XC_FULL, mx, o));
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = s_max[0];
-    for (int w = 1; w < 32; ++w) mx = fmaxf(mx, s_max[w]);
-    const float thr = mx - 2e-5f * fabsf(mx) - 1e-37f;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // contiguous slice per thread so that the compacted list stays in grid order
     const int64_t per = (total + 1023) / 1024;
     const int64_t b = threadIdx.x * per, e = min(total, b + per);
-    int cnt = 0;
-    for (int64_t q = b; q < e; ++q) cnt += (vf[q] >= thr) || !(vf[q] == vf[q]);  // NaN: keep
-    s_cnt[threadIdx.x] = cnt;
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+    bool nan = false;
+    // pass 1, coalesced: combine the label-slice partials in a fixed order, first maximum
+#pragma unroll 4
+    for (int64_t q = threadIdx.x; q < total; q += 1024) {
+        float v = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < ALPHA_LS; ++sl) v += __ldg(part + (int64_t)sl * total + q);
+        v *= scale;
+        vfast[q] = v;
+        nan |= !(v == v);
+        if (v > mx) { mx = v; arg = (int)q; }  // q ascending per thread: first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(XC_FULL, mx, o);
+        const int oa = __shfl_xor_sync(XC_FULL, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+    }
+    if (lane == 0) { s_max[wid] = mx; s_arg[wid] = arg; }
+    const int any_nan = __syncthreads_or(nan);
+    mx = s_max[0];
+    arg = s_arg[0];
+    for (int w = 1; w < 32; ++w)
+        if (s_max[w] > mx || (s_max[w] == mx && s_arg[w] < arg)) { mx = s_max[w]; arg = s_arg[w]; }
+    const float thr = mx - ALPHA_WINDOW * fabsf(mx) - 1e-37f;
+    int cnt = 0;   // (the barrier above also published vfast to the whole block)
+    for (int64_t q = b; q < e; ++q) cnt += vfast[q] >= thr;
+    // exclusive scan over the 1024 per-thread counts
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(XC_FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int t = 0; t < 1024; ++t) { int c = s_cnt[t]; s_cnt[t] = run; run += c; }
-        s_base = run;
-        const bool full = run > ALPHA_MAX_CAND || !(mx == mx);
-        ctl->full = full ? 1 : 0;
-        ctl->count = full ? (int)total : run;
+    if (wid == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(XC_FULL, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+        if (lane == 31) s_arg[0] = wi;
     }
     __syncthreads();
-    if (s_base <= ALPHA_MAX_CAND) {
-        int o = s_cnt[threadIdx.x];
+    const int run = s_arg[0];
+    const bool full = run > ALPHA_MAX_CAND || any_nan || arg == 0x7fffffff;
+    if (!full) {
+        int o = s_warp[wid] + incl - cnt;
         for (int64_t q = b; q < e; ++q)
-            if ((vf[q] >= thr) || !(vf[q] == vf[q])) cand_q[o++] = (int)q;
+            if (vfast[q] >= thr) cand_q[o++] = (int)q;
+    }
+    if (threadIdx.x == 0) {
+        const int count = full ? (int)total : run;
+        const int tiles = (count + AT64 - 1) / AT64;
+        int slices = full ? 1 : eval_ctas / (tiles > 0 ? tiles : 1);
+        slices = slices < 1 ? 1 : (slices > ALPHA_LS2_MAX ? ALPHA_LS2_MAX : slices);
+        ctl->count = count;
+        ctl->full = full ? 1 : 0;
+        ctl->slices = slices;
+        ctl->tiles = tiles;
+        ctl->qstar = full ? 0 : arg;
+    }
+}
+
+// Stage 1.5: with alpha* the stage-1 arg-max, the difference of one label's term between a candidate
+// and alpha* has the closed form
+//     T(a)/D(a) - T(a*)/D(a*) = (a - a*) E / (D(a) D(a*)),   E = dT D0 - T0 dD  (formed in float64)
+// which float32 evaluates to a relative accuracy of a few ulp OF THE DIFFERENCE (the direct float32
+// values only resolve ~1e-6 of the objective itself, which on a flat objective leaves hundreds of
+// candidates).  Per candidate the kernel accumulates d = sum_j t_j and a bound on its rounding error
+// err = ulp * sum_j |t_j| (amp_j(a) + amp_j(a*) + 10), amp = (|D0| + a |dD|) / D(a) being the
+// cancellation amplification of the float32 denominator (the constant covers the reciprocal, the
+// products and the worst-case rounding of the ~36-deep float32 summation).  A candidate survives iff
+// d + err >= max_s (d_s - err_s): only those can be the float64 maximum.
+__global__ void __launch_bounds__(kThreads)
+fw_alpha_refine_kernel(const float4 *__restrict__ lin, const float *__restrict__ linE, int64_t m,
+                       const double *__restrict__ alphas, const int *__restrict__ cand_q,
+                       const AlphaCtl *__restrict__ ctl, float *__restrict__ part_d, float *__restrict__ part_e)
+{
+    __shared__ float sm[2][ATR][kThreads / 32];
+    if (ctl->full) return;
+    const int count = ctl->count;
+    const int s0 = blockIdx.x * ATR;
+    if (s0 >= count) return;
+    const int qs = ctl->qstar;
+    const float astar = qs == 0 ? 0.f : (float)alphas[qs - 1];
+    float al[ATR], accd[ATR], acce[ATR];
+#pragma unroll
+    for (int t = 0; t < ATR; ++t) {
+        const int slot = s0 + t;
+        const int q = slot < count ? cand_q[slot] : qs;
+        al[t] = q == 0 ? 0.f : (float)alphas[q - 1];
+        accd[t] = 0.f;
+        acce[t] = 0.f;
+    }
+    int64_t j = (int64_t)blockIdx.y * kThreads + threadIdx.x;
+    const int64_t stride = (int64_t)kThreads * ALPHA_LSR;
+    float4 l = make_float4(0.f, 0.f, 1.f, 0.f);
+    float le = 0.f;
+    if (j < m) { l = __ldg(lin + j); le = __ldg(linE + j); }
+    for (; j < m; j += stride) {
+        float4 ln = l;
+        float len = le;
+        if (j + stride < m) { ln = __ldg(lin + j + stride); len = __ldg(linE + j + stride); }
+        const float aD0 = fabsf(l.z), adD = fabsf(l.w);
+        const float rstar = rcp_approx(fmaf(astar, l.w, l.z));
+        const float ampstar = fmaf(astar, adD, aD0) * rstar + 10.f;
+        const float er = le * rstar;
+#pragma unroll
+        for (int t = 0; t < ATR; ++t) {
+            const float rs = rcp_approx(fmaf(al[t], l.w, l.z));
+            const float tt = er * rs;
+            accd[t] += tt;
+            acce[t] = fmaf(fabsf(tt), fmaf(fmaf(al[t], adD, aD0), rs, ampstar), acce[t]);
+        }
+        l = ln;
+        le = len;
+    }
+#pragma unroll
+    for (int t = 0; t < ATR; ++t) {
+        float v = accd[t], w = acce[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v += __shfl_xor_sync(XC_FULL, v, o);
+            w += __shfl_xor_sync(XC_FULL, w, o);
+        }
+        if ((threadIdx.x & 31) == 0) { sm[0][t][threadIdx.x >> 5] = v; sm[1][t][threadIdx.x >> 5] = w; }
+    }
+    __syncthreads();
+    if (threadIdx.x < ATR) {
+        float v = 0.f, w = 0.f;
+        for (int x = 0; x < kThreads / 32; ++x) { v += sm[0][threadIdx.x][x]; w += sm[1][threadIdx.x][x]; }
+        const int slot = s0 + threadIdx.x;
+        if (slot < count) {
+            part_d[blockIdx.y * ALPHA_MAX_CAND + slot] = v;
+            part_e[blockIdx.y * ALPHA_MAX_CAND + slot] = w;
+        }
+    }
+}
+
+// prune the candidate list with the refined differences; writes the final list + control block
+__global__ void __launch_bounds__(1024)
+fw_alpha_cand2_kernel(const float *__restrict__ part_d, const float *__restrict__ part_e,
+                      const double *__restrict__ alphas, const int *__restrict__ cand_q,
+                      const AlphaCtl *__restrict__ ctl, int *__restrict__ cand_q2, AlphaCtl *ctl2, int eval_ctas)
+{
+    __shared__ float s_lo[32];
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    if (ctl->full) {
+        if (threadIdx.x == 0) *ctl2 = *ctl;
+        return;
+    }
+    const int count = ctl->count, qs = ctl->qstar;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double astar = qs == 0 ? 0.0 : alphas[qs - 1];
+    // two slots per thread (ALPHA_MAX_CAND = 2 * 1024), contiguous so the list stays in grid order
+    float hi[2], lo = -INFINITY;
+    int qq[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int slot = threadIdx.x * 2 + u;
+        hi[u] = -INFINITY;
+        qq[u] = -1;
+        if (slot < count) {
+            const int q = cand_q[slot];
+            float d = 0.f, er = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < ALPHA_LSR; ++sl) {
+                d += part_d[sl * ALPHA_MAX_CAND + slot];
+                er += part_e[sl * ALPHA_MAX_CAND + slot];
+            }
+            const float delta = (float)((q == 0 ? 0.0 : alphas[q - 1]) - astar);
+            d *= delta;
+            er = er * fabsf(delta) * ALPHA_REFINE_ULP;
+            if (q == qs) { d = 0.f; er = 0.f; }
+            if (!(d == d) || !(er == er)) { d = 0.f; er = INFINITY; }  // not a number: keep, bound nothing
+            hi[u] = d + er;
+            qq[u] = q;
+            lo = fmaxf(lo, d - er);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo = fmaxf(lo, __shfl_xor_sync(XC_FULL, lo, o));
+    if (lane == 0) s_lo[wid] = lo;
+    __syncthreads();
+    lo = s_lo[0];
+    for (int w = 1; w < 32; ++w) lo = fmaxf(lo, s_lo[w]);
+    const int cnt = (hi[0] >= lo) + (hi[1] >= lo);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(XC_FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(XC_FULL, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_run = wi;
+    }
+    __syncthreads();
+    int o = s_warp[wid] + incl - cnt;
+    if (hi[0] >= lo) cand_q2[o++] = qq[0];
+    if (hi[1] >= lo) cand_q2[o++] = qq[1];
+    if (threadIdx.x == 0) {
+        const int run = s_run;
+        const int tiles = (run + AT64 - 1) / AT64;
+        int slices = eval_ctas / (tiles > 0 ? tiles : 1);
+        slices = slices < 1 ? 1 : (slices > ALPHA_LS2_MAX ? ALPHA_LS2_MAX : slices);
+        ctl2->count = run;
+        ctl2->full = 0;
+        ctl2->slices = slices;
+        ctl2->tiles = tiles;
+        ctl2->qstar = qs;
     }
 }
 
 // float64 evaluation with the reference's expression (frank_wolfe.py:393-398).  Slot t evaluates grid
 // point q = cand_q[t] (candidate mode) or q = t (full mode / ctl == nullptr); q = 0 is alpha = 0.
-template <int AT>
+// Work item = (slot tile of AT64 slots, label slice); partial sums go to vals[slice * vstride + slot].
 __global__ void __launch_bounds__(kThreads)
 fw_alpha_eval_kernel(xc_metric_params p, const double *__restrict__ C, const double *__restrict__ Ci, int64_t m,
                      const double *__restrict__ alphas, int64_t n_alphas, const int *__restrict__ cand_q,
-                     const AlphaCtl *__restrict__ ctl, double *__restrict__ vals, int want_full)
+                     const AlphaCtl *__restrict__ ctl, double *__restrict__ vals, int64_t vstride)
 {
-    __shared__ double sm[AT][kThreads / 32];
-    const int64_t s0 = (int64_t)blockIdx.x * AT;
+    __shared__ double sm[AT64][kThreads / 32];
     const bool full = ctl == nullptr || ctl->full;
     const int64_t count = ctl == nullptr ? n_alphas + 1 : ctl->count;
-    if ((int)full != want_full || s0 >= count) return;  // the other launch handles this mode
-    double al[AT], acc[AT];
-#pragma unroll
-    for (int t = 0; t < AT; ++t) {
-        int64_t slot = s0 + t;
-        int64_t q = slot < count ? (full ? slot : (int64_t)cand_q[slot]) : 0;
-        al[t] = (q == 0) ? 0.0 : alphas[q - 1];
-        acc[t] = 0.0;
-    }
+    const int slices = ctl == nullptr ? 1 : ctl->slices;
+    const int64_t tiles = (count + AT64 - 1) / AT64;
     const bool use_tn = p.metric >= XC_METRIC_BALANCED_ACC;
-    // gridDim.y label slices (candidate mode): partial sums are combined with float64 atomics
-    for (int64_t j = (int64_t)blockIdx.y * kThreads + threadIdx.x; j < m; j += (int64_t)kThreads * gridDim.y) {
-        const double tp = C[j], fp = C[m + j], fn = C[2 * m + j], tn = use_tn ? C[3 * m + j] : 0.0;
-        const double tpi = Ci[j], fpi = Ci[m + j], fni = Ci[2 * m + j], tni = use_tn ? Ci[3 * m + j] : 0.0;
+    const int64_t per_slice = (m + slices - 1) / slices;
+    for (int64_t item = blockIdx.x; item < tiles * slices; item += gridDim.x) {
+        const int64_t tile = item / slices;
+        const int slice = (int)(item - tile * slices);
+        const int64_t s0 = tile * AT64;
+        double al[AT64], acc[AT64];
 #pragma unroll
-        for (int t = 0; t < AT; ++t) {
-            const double a1 = al[t], a0 = 1.0 - a1;
-            acc[t] += xc_binary_metric(p.metric, a0 * tp + a1 * tpi, a0 * fp + a1 * fpi, a0 * fn + a1 * fni,
-                                       a0 * tn + a1 * tni, p.c1, p.beta2, p.eps);
+        for (int t = 0; t < AT64; ++t) {
+            int64_t slot = s0 + t;
+            int64_t q = slot < count ? (full ? slot : (int64_t)cand_q[slot]) : 0;
+            al[t] = (q == 0) ? 0.0 : alphas[q - 1];
+            acc[t] = 0.0;
         }
-    }
+        const int64_t jb = slice * per_slice, je = min(m, jb + per_slice);
+        for (int64_t j = jb + threadIdx.x; j < je; j += kThreads) {
+            const double tp = C[j], fp = C[m + j], fn = C[2 * m + j], tn = use_tn ? C[3 * m + j] : 0.0;
+            const double tpi = Ci[j], fpi = Ci[m + j], fni = Ci[2 * m + j], tni = use_tn ? Ci[3 * m + j] : 0.0;
 #pragma unroll
-    for (int t = 0; t < AT; ++t) {
-        double v = warp_sum(acc[t]);
-        if ((threadIdx.x & 31) == 0) sm[t][threadIdx.x >> 5] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < AT) {
-        double v = 0.0;
-        for (int w = 0; w < kThreads / 32; ++w) v += sm[threadIdx.x][w];
-        int64_t slot = s0 + threadIdx.x;
-        if (slot < count) {
-            if (gridDim.y > 1) atomicAdd(vals + slot, v / (double)m);
-            else vals[slot] = v / (double)m;
+            for (int t = 0; t < AT64; ++t) {
+                const double a1 = al[t], a0 = 1.0 - a1;
+                acc[t] += xc_binary_metric(p.metric, a0 * tp + a1 * tpi, a0 * fp + a1 * fpi, a0 * fn + a1 * fni,
+                                           a0 * tn + a1 * tni, p.c1, p.beta2, p.eps);
+            }
         }
+#pragma unroll
+        for (int t = 0; t < AT64; ++t) {
+            double v = warp_sum(acc[t]);
+            if ((threadIdx.x & 31) == 0) sm[t][threadIdx.x >> 5] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < AT64) {
+            double v = 0.0;
+            for (int w = 0; w < kThreads / 32; ++w) v += sm[threadIdx.x][w];
+            int64_t slot = s0 + threadIdx.x;
+            if (slot < count) vals[(int64_t)slice * vstride + slot] = v;
+        }
+        __syncthreads();
     }
 }
 
-// first strict maximum over the evaluated slots (slots are in grid order; utils.py:177-184)
+// first strict maximum over the evaluated slots (slots are in grid order; utils.py:177-184); the
+// label-slice partials of a slot are added in slice order, then divided by m
 __global__ void __launch_bounds__(1024)
-fw_alpha_pick_kernel(const double *__restrict__ vals, const double *__restrict__ alphas, int64_t n_alphas,
-                     const int *__restrict__ cand_q, const AlphaCtl *__restrict__ ctl, double *result)
+fw_alpha_pick_kernel(const double *__restrict__ vals, int64_t vstride, int64_t m, const double *__restrict__ alphas,
+                     int64_t n_alphas, const int *__restrict__ cand_q, const AlphaCtl *__restrict__ ctl,
+                     double *result)
 {
     __shared__ double sv[32];
     __shared__ long long sq[32];
     const bool full = ctl == nullptr || ctl->full;
     const int64_t count = ctl == nullptr ? n_alphas + 1 : ctl->count;
+    const int slices = ctl == nullptr ? 1 : ctl->slices;
     double bv = -INFINITY;
     long long bq = 0x7fffffffffffffffLL;
-    for (int64_t q = threadIdx.x; q < count; q += 1024) {
-        double v = vals[q];
+    // one warp per slot: lane l fetches slice l's partial, fixed shuffle tree (reproducible)
+    for (int64_t q = threadIdx.x >> 5; q < count; q += 32) {
+        const int l = threadIdx.x & 31;
+        double v = l < slices ? vals[(int64_t)l * vstride + q] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(XC_FULL, v, o);
+        v = v / (double)m;
         if (v > bv || (v == bv && q < bq)) { bv = v; bq = q; }
     }
 #pragma unroll
@@ -401,7 +699,10 @@ fw_alpha_pick_kernel(const double *__restrict__ vals, const double *__restrict__
         }
         if (threadIdx.x == 0) {
             // NaN everywhere -> keep alpha = 0 like the reference (no score > best_val)
-            if (bq == 0x7fffffffffffffffLL) { bq = 0; bv = vals[0]; }
+            if (bq == 0x7fffffffffffffffLL) {
+                bq = 0;
+                bv = NAN;
+            }
             const long long q = full ? bq : (long long)cand_q[bq];
             result[0] = q == 0 ? 0.0 : alphas[q - 1];
             result[1] = bv;
@@ -415,6 +716,87 @@ fw_combine_kernel(double *C, const double *Ci, int64_t m4, const double *alpha_d
     const double a1 = *alpha_dev;
     int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (j < m4) C[j] = (1.0 - a1) * C[j] + a1 * Ci[j];  // frank_wolfe.py:633-636
+}
+
+// ---- fused per-label stages of one dense iteration ---------------------------------------------------
+// (1) confusion vectors of the newest classifier from the raw sums (fw_make_conf_kernel), its
+//     utility (deterministic grid sum) and, for the two-stage search, the per-label linearisation.
+__global__ void __launch_bounds__(256)
+fw_conf_prep_kernel(xc_metric_params p, const double *__restrict__ tp_raw, const double *__restrict__ cnt,
+                    const double *__restrict__ colsum, int64_t m, double n, int normalize, int skip_tn,
+                    const double *__restrict__ Cm, double *__restrict__ out, float4 *__restrict__ lin,
+                    float *__restrict__ linE, double *value, double *partials, unsigned *counter)
+{
+    __shared__ double sm[8];
+    double s = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += (int64_t)gridDim.x * 256) {
+        double t = tp_raw[j], f = cnt[j] - t, g = colsum[j] - t;
+        if (normalize) { t = t / n; f = f / n; g = g / n; }
+        const double tn = skip_tn ? -1.0 : ((-t - f) - g) + (normalize ? 1.0 : n);
+        out[j] = t;
+        out[m + j] = f;
+        out[2 * m + j] = g;
+        out[3 * m + j] = tn;
+        s += metric_grad(p.metric, t, f, g, tn, p.c1, p.beta2, p.eps).v;
+        if (lin) lin[j] = alpha_lin(p, Cm[j], Cm[m + j], Cm[2 * m + j], t, f, g, linE + j);
+    }
+    if (lin && (m & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        lin[m] = make_float4(0.f, 0.f, 1.f, 0.f);
+        linE[m] = 0.f;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double bsum = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) bsum += sm[w];
+    double total;
+    if (xc_grid_sum_last(bsum, partials, counter, &total) && value) *value = total * (1.0 / (double)m);
+}
+
+// (2) C = (1 - alpha) C + alpha Ci (skipped when alpha_dev == nullptr), utility of the new C, the next
+//     classifier from its gradient (frank_wolfe.py:591-596) and re-zeroing of the raw sums
+__global__ void __launch_bounds__(256)
+fw_finish_kernel(xc_metric_params p, double *__restrict__ C, const double *__restrict__ Ci, int64_t m,
+                 const double *__restrict__ alpha_dev, float *__restrict__ a_next, float *__restrict__ b_next,
+                 double *__restrict__ raw_zero, double *value, double *value_next, double *partials,
+                 unsigned *counter)
+{
+    __shared__ double sm[8];
+    double s = 0.0;
+    const double sgn = p.maximize ? 1.0 : -1.0;
+    const double inv_m = 1.0 / (double)m;
+    const double a1 = alpha_dev ? *alpha_dev : 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += (int64_t)gridDim.x * 256) {
+        double c[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            c[t] = C[t * m + j];
+            if (alpha_dev) {
+                c[t] = (1.0 - a1) * c[t] + a1 * Ci[t * m + j];
+                C[t * m + j] = c[t];
+            }
+        }
+        Grad4 g = metric_grad(p.metric, c[0], c[1], c[2], c[3], p.c1, p.beta2, p.eps);
+        s += g.v;
+        if (a_next) {
+            double gtp = g.gtp * inv_m, gfp = g.gfp * inv_m, gfn = g.gfn * inv_m, gtn = g.gtn * inv_m;
+            a_next[j] = (float)(sgn * (((gtp - gfp) - gfn) + gtn));
+            b_next[j] = (float)(sgn * (gfp - gtn));
+        }
+        if (raw_zero) { raw_zero[j] = 0.0; raw_zero[m + j] = 0.0; }
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double bsum = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) bsum += sm[w];
+    double total;
+    if (xc_grid_sum_last(bsum, partials, counter, &total)) {
+        if (value) *value = total * inv_m;
+        if (value_next) *value_next = total * inv_m;
+    }
 }
 
 template <typename K>
@@ -446,6 +828,33 @@ int launch_fw_dense(xc_ctx *ctx, const void *eta, int64_t n, int64_t m, int64_t 
     bool vec_ok = xc_aligned16(eta) && (ld % V == 0);
     XfMulAdd<TE> xf{(const TE *)a, (const TE *)b};
     const int64_t coef_bytes = 2 * m * (int64_t)sizeof(TE);
+    // classifier larger than L1: stage it through shared memory ($XCOLUMNS_B200_FW_PATH=plain|staged)
+    static int force_path = -1;
+    if (force_path < 0) {
+        const char *e = getenv("XCOLUMNS_B200_FW_PATH");
+        force_path = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'p' ? 2 : 0));
+    }
+    if (vec_ok && (force_path == 1 || (force_path == 0 && coef_bytes > 160 * 1024 && n >= 65536))) {
+        static int occ = -1;  // CTAs per SM the kernel is compiled for: $XCOLUMNS_B200_FW_OCC=4|5|6 (64 / 48 / 40 registers)
+        if (occ < 0) {
+            const char *e = getenv("XCOLUMNS_B200_FW_OCC");
+            occ = (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 5;
+        }
+        auto kern = occ == 4 ? fw_iterate_dense_staged_kernel<TE, 4>
+                             : (occ == 6 ? fw_iterate_dense_staged_kernel<TE, 6> : fw_iterate_dense_staged_kernel<TE, 5>);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreadsS, 0);
+        if (per_sm < 1) per_sm = 1;
+        const int64_t ngroups = (n + kThreadsS / 32 - 1) / (kThreadsS / 32);
+        const int64_t resident = (int64_t)ctx->sm_count * per_sm;
+        const int64_t waves = (ngroups + resident - 1) / resident;
+        const int grid = (int)((ngroups + waves - 1) / waves);
+        StageMulAdd<TE> stage{(const TE *)a, (const TE *)b, (!a || xc_aligned16(a)) && (!b || xc_aligned16(b))};
+        kern<<<grid, kThreadsS, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true, stage, k, tp, cnt,
+                                         pred_idx);
+        XC_LAUNCHED(ctx);
+        return XC_OK;
+    }
     int rr = coef_bytes <= 160 * 1024 ? 1 : (coef_bytes <= 512 * 1024 ? 2 : 4);
     if (const char *e = getenv("XCOLUMNS_B200_DENSE_R")) {
         int v = atoi(e);
@@ -536,63 +945,163 @@ extern "C" int xc_fw_metric_grad(xc_ctx *ctx, const xc_metric_params *p, const d
     return XC_OK;
 }
 
-extern "C" int64_t xc_fw_alpha_scratch_bytes(int64_t m, int64_t n_alphas)
+namespace {
+// scratch layout of the line search (all offsets 32-byte aligned)
+struct AlphaScratch {
+    double *vals;      // float64 partial sums: [slice][vstride]
+    int64_t vstride;
+    float *part;       // stage-1 partial sums: [ALPHA_LS][n_alphas + 1]
+    float *vfast;      // stage-1 values [n_alphas + 1]
+    int *cand_q;       // [ALPHA_MAX_CAND] stage-1 candidates
+    int *cand_q2;      // [ALPHA_MAX_CAND] candidates that survive the refinement
+    float *part_d;     // refinement partial sums [ALPHA_LSR][ALPHA_MAX_CAND]
+    float *part_e;
+    AlphaCtl *ctl;     // final control block (diagnostics: xc_fw_alpha_ctl_offset)
+    AlphaCtl *ctl1;    // stage-1 control block
+    float4 *lin;       // [m + 1]
+    float *linE;       // [m + 1]
+    size_t bytes;
+};
+
+AlphaScratch alpha_scratch(void *base_, int64_t m, int64_t n_alphas)
 {
-    // exact values | stage-1 values | candidate list | control | per-label linearisation
-    return (n_alphas + 1) * 8 + (n_alphas + 1) * 8 + ALPHA_MAX_CAND * 4 + 64 + m * 16 + 256;
+    auto up = [](size_t v) { return (v + 31) & ~(size_t)31; };
+    uint8_t *base = reinterpret_cast<uint8_t *>(base_);
+    AlphaScratch s;
+    const int64_t total = n_alphas + 1;
+    s.vstride = ALPHA_MAX_CAND;
+    const int64_t nvals = total > (int64_t)ALPHA_MAX_CAND * ALPHA_LS2_MAX ? total : (int64_t)ALPHA_MAX_CAND * ALPHA_LS2_MAX;
+    size_t off = 0;
+    s.vals = reinterpret_cast<double *>(base + off);
+    off = up(off + (size_t)nvals * 8);
+    s.part = reinterpret_cast<float *>(base + off);
+    off = up(off + (size_t)total * 4 * ALPHA_LS);
+    s.vfast = reinterpret_cast<float *>(base + off);
+    off = up(off + (size_t)total * 4);
+    s.cand_q = reinterpret_cast<int *>(base + off);
+    off = up(off + (size_t)ALPHA_MAX_CAND * 4);
+    s.cand_q2 = reinterpret_cast<int *>(base + off);
+    off = up(off + (size_t)ALPHA_MAX_CAND * 4);
+    s.part_d = reinterpret_cast<float *>(base + off);
+    off = up(off + (size_t)ALPHA_MAX_CAND * 4 * ALPHA_LSR);
+    s.part_e = reinterpret_cast<float *>(base + off);
+    off = up(off + (size_t)ALPHA_MAX_CAND * 4 * ALPHA_LSR);
+    s.ctl = reinterpret_cast<AlphaCtl *>(base + off);
+    off = up(off + 64);
+    s.ctl1 = reinterpret_cast<AlphaCtl *>(base + off);
+    off = up(off + 64);
+    s.lin = reinterpret_cast<float4 *>(base + off);
+    off = up(off + (size_t)(m + 1) * 16);
+    s.linE = reinterpret_cast<float *>(base + off);
+    off = up(off + (size_t)(m + 1) * 4);
+    s.bytes = off + 256;
+    return s;
 }
 
-extern "C" int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const double *C, const double *Ci,
-                                  int64_t m, const double *alphas_dev, int64_t n_alphas, double *vals_dev,
-                                  double *result_dev, void *stream)
+int eval_grid(xc_ctx *ctx)
 {
-    if (!ctx || !p || !C || !Ci || !vals_dev || !result_dev || m <= 0 || n_alphas < 0) return XC_ERR_INVALID;
-    if (n_alphas > 0 && !alphas_dev) return XC_ERR_INVALID;
-    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    // carve the caller's scratch (xc_fw_alpha_scratch_bytes)
-    uint8_t *base = reinterpret_cast<uint8_t *>(vals_dev);
-    double *vals = vals_dev;
-    size_t off = (size_t)(n_alphas + 1) * 8;
-    float *vals_fast = reinterpret_cast<float *>(base + off);
-    off += (size_t)(n_alphas + 1) * 8;
-    int *cand_q = reinterpret_cast<int *>(base + off);
-    off += ALPHA_MAX_CAND * 4;
-    AlphaCtl *ctl = reinterpret_cast<AlphaCtl *>(base + off);
-    off += 64;
-    off = (off + 31) & ~(size_t)31;
-    float4 *lin = reinterpret_cast<float4 *>(base + off);
-    const unsigned grid_full = (unsigned)((n_alphas + 1 + AT_FULL - 1) / AT_FULL);
-    const bool two_stage = p->metric <= XC_METRIC_JACCARD && n_alphas >= 256;
-    if (two_stage) {
-        fw_alpha_prep_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, st>>>(*p, C, Ci, m, lin);
-        XC_LAUNCHED(ctx);
-        XC_CUDA_TRY(ctx, cudaMemsetAsync(vals_fast, 0, sizeof(float) * (size_t)(n_alphas + 1), st));
-        XC_CUDA_TRY(ctx, cudaMemsetAsync(vals, 0, sizeof(double) * (size_t)ALPHA_MAX_CAND, st));
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fw_alpha_eval_kernel, kThreads, 0);
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+    }
+    return ctx->sm_count * per_sm;
+}
+
+bool alpha_two_stage(const xc_metric_params *p, int64_t n_alphas)
+{
+    static int force_full = -1;  // $XCOLUMNS_B200_FW_SEARCH=full: float64 over the whole grid
+    if (force_full < 0) {
+        const char *e = getenv("XCOLUMNS_B200_FW_SEARCH");
+        force_full = (e && e[0] == 'f') ? 1 : 0;
+    }
+    return !force_full && p->metric <= XC_METRIC_JACCARD && n_alphas >= 256;
+}
+
+bool alpha_refine()
+{
+    static int off = -1;  // $XCOLUMNS_B200_FW_REFINE=0: skip the stage-1.5 pruning
+    if (off < 0) {
+        const char *e = getenv("XCOLUMNS_B200_FW_REFINE");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    return !off;
+}
+
+// line search proper; `lin` must already hold the linearisation when the two-stage path applies
+int alpha_search_launch(xc_ctx *ctx, const xc_metric_params *p, const double *C, const double *Ci, int64_t m,
+                        const double *alphas_dev, int64_t n_alphas, const AlphaScratch &s, double *result_dev,
+                        cudaStream_t st)
+{
+    const int grid64 = eval_grid(ctx);
+    if (alpha_two_stage(p, n_alphas)) {
         const float scale = (float)((p->metric == XC_METRIC_FBETA ? p->c1 : 1.0) / (double)m);
-        dim3 g32((unsigned)((n_alphas + 1 + AT32 - 1) / AT32), ALPHA_LSPLIT);
-        fw_alpha_evalfast_kernel<<<g32, kThreads, 0, st>>>(lin, m, alphas_dev, n_alphas, scale, vals_fast);
+        dim3 g32((unsigned)((n_alphas + 1 + AT32 - 1) / AT32), ALPHA_LS);
+        fw_alpha_evalfast_kernel<<<g32, kThreads, 0, st>>>(s.lin, (m + 1) / 2, alphas_dev, n_alphas, s.part);
         XC_LAUNCHED(ctx);
-        fw_alpha_cand_kernel<<<1, 1024, 0, st>>>(vals_fast, n_alphas, cand_q, ctl);
+        fw_alpha_cand_kernel<<<1, 1024, 0, st>>>(s.part, n_alphas, scale, s.vfast, s.cand_q, s.ctl1, grid64);
         XC_LAUNCHED(ctx);
-        // candidate mode: <= ALPHA_MAX_CAND slots, 2 per block; blocks past the count exit at once
-        fw_alpha_eval_kernel<AT_CAND><<<dim3(ALPHA_MAX_CAND / AT_CAND, ALPHA_LSPLIT), kThreads, 0, st>>>(
-            *p, C, Ci, m, alphas_dev, n_alphas, cand_q, ctl, vals, 0);
+        const int *cq = s.cand_q;
+        const AlphaCtl *cc = s.ctl1;
+        if (alpha_refine()) {
+            fw_alpha_refine_kernel<<<dim3(ALPHA_MAX_CAND / ATR, ALPHA_LSR), kThreads, 0, st>>>(
+                s.lin, s.linE, m, alphas_dev, s.cand_q, s.ctl1, s.part_d, s.part_e);
+            XC_LAUNCHED(ctx);
+            fw_alpha_cand2_kernel<<<1, 1024, 0, st>>>(s.part_d, s.part_e, alphas_dev, s.cand_q, s.ctl1, s.cand_q2, s.ctl,
+                                                      grid64);
+            XC_LAUNCHED(ctx);
+            cq = s.cand_q2;
+            cc = s.ctl;
+        }
+        fw_alpha_eval_kernel<<<grid64, kThreads, 0, st>>>(*p, C, Ci, m, alphas_dev, n_alphas, cq, cc, s.vals, s.vstride);
         XC_LAUNCHED(ctx);
-        // fallback over the whole grid: every block exits unless the candidate kernel asked for it
-        fw_alpha_eval_kernel<AT_FULL><<<grid_full, kThreads, 0, st>>>(*p, C, Ci, m, alphas_dev, n_alphas, cand_q, ctl,
-                                                                      vals, 1);
-        XC_LAUNCHED(ctx);
-        fw_alpha_pick_kernel<<<1, 1024, 0, st>>>(vals, alphas_dev, n_alphas, cand_q, ctl, result_dev);
+        fw_alpha_pick_kernel<<<1, 1024, 0, st>>>(s.vals, s.vstride, m, alphas_dev, n_alphas, cq, cc, result_dev);
         XC_LAUNCHED(ctx);
     } else {
-        fw_alpha_eval_kernel<AT_FULL><<<grid_full, kThreads, 0, st>>>(*p, C, Ci, m, alphas_dev, n_alphas, nullptr,
-                                                                      nullptr, vals, 1);
+        fw_alpha_eval_kernel<<<grid64, kThreads, 0, st>>>(*p, C, Ci, m, alphas_dev, n_alphas, nullptr, nullptr, s.vals,
+                                                          s.vstride);
         XC_LAUNCHED(ctx);
-        fw_alpha_pick_kernel<<<1, 1024, 0, st>>>(vals, alphas_dev, n_alphas, nullptr, nullptr, result_dev);
+        fw_alpha_pick_kernel<<<1, 1024, 0, st>>>(s.vals, s.vstride, m, alphas_dev, n_alphas, nullptr, nullptr, result_dev);
         XC_LAUNCHED(ctx);
     }
     return XC_OK;
+}
+
+int reduce_grid(xc_ctx *ctx, int64_t m)
+{
+    int64_t blocks = (m + 255) / 256;
+    int grid = (int)(blocks < XC_RED_MAX_BLOCKS ? blocks : XC_RED_MAX_BLOCKS);
+    if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+    return grid;
+}
+}  // namespace
+
+extern "C" int64_t xc_fw_alpha_scratch_bytes(int64_t m, int64_t n_alphas)
+{
+    return (int64_t)alpha_scratch(nullptr, m, n_alphas).bytes;
+}
+
+extern "C" int64_t xc_fw_alpha_ctl_offset(int64_t m, int64_t n_alphas)
+{
+    AlphaScratch s = alpha_scratch(nullptr, m, n_alphas);
+    return (int64_t)(reinterpret_cast<uint8_t *>(s.ctl) - reinterpret_cast<uint8_t *>(s.vals));
+}
+
+extern "C" int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const double *C, const double *Ci,
+                                  int64_t m, const double *alphas_dev, int64_t n_alphas, double *scratch_dev,
+                                  double *result_dev, void *stream)
+{
+    if (!ctx || !p || !C || !Ci || !scratch_dev || !result_dev || m <= 0 || n_alphas < 0) return XC_ERR_INVALID;
+    if (n_alphas > 0 && !alphas_dev) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    AlphaScratch s = alpha_scratch(scratch_dev, m, n_alphas);
+    if (alpha_two_stage(p, n_alphas)) {
+        fw_alpha_prep_kernel<<<(unsigned)((m + 1 + kThreads - 1) / kThreads), kThreads, 0, st>>>(*p, C, Ci, m, s.lin, s.linE);
+        XC_LAUNCHED(ctx);
+    }
+    return alpha_search_launch(ctx, p, C, Ci, m, alphas_dev, n_alphas, s, result_dev, st);
 }
 
 extern "C" int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4, const double *alpha_dev,
@@ -605,66 +1114,81 @@ extern "C" int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m
     return XC_OK;
 }
 
-// ---- one Frank-Wolfe iteration as two host calls (the all-reduce of the iterate's raw sums, if
+// ---- one dense Frank-Wolfe iteration as two host calls (the all-reduce of the iterate's raw sums, if
 // any, happens between them) -----------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(kThreads) f32_to_f64_kernel(const float *a, double *o, int64_t m)
+__global__ void __launch_bounds__(kThreads) f32_to_f64_kernel(const float *a, const float *b, double *o, int64_t m)
 {
     int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (j < m) o[j] = (double)a[j];
+    if (j < m) {
+        o[j] = (double)a[j];
+        o[m + j] = (double)b[j];
+    }
 }
 }  // namespace
 
-extern "C" int xc_fw_step_begin(xc_ctx *ctx, const xc_metric_params *p, int have_grad, const void *eta, int dtype,
-                                int64_t n, int64_t m, int64_t ld, const void *y_true, int64_t ld_true,
-                                const double *Cm, float *a_row, float *b_row, double *ab64, int k, double *raw,
-                                double *scal, void *stream)
+extern "C" int xc_fw_step_begin(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m, int64_t ld,
+                                const void *y_true, int64_t ld_true, const float *a_row, const float *b_row,
+                                double *ab64, int k, double *raw, int raw_is_zero, void *stream)
 {
-    if (!ctx || !p || !eta || !y_true || !a_row || !b_row || !raw || !scal) return XC_ERR_INVALID;
-    int rc;
-    if (have_grad) {  // value of the running confusion vectors + next classifier -> (a_row, b_row)
-        if (!Cm) return XC_ERR_INVALID;
-        rc = xc_fw_metric_grad(ctx, p, Cm, m, a_row, b_row, scal + 0, stream);
-        if (rc) return rc;
-    }
+    if (!ctx || !eta || !y_true || !a_row || !b_row || !raw) return XC_ERR_INVALID;
+    if (n <= 0 || m <= 0 || ld < m || ld_true < m || k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
     const void *a = a_row, *b = b_row;
     if (dtype == XC_F64) {  // numpy promotes the float32 classifier rows to float64 gains
         if (!ab64) return XC_ERR_INVALID;
-        unsigned g = (unsigned)((m + kThreads - 1) / kThreads);
-        f32_to_f64_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(a_row, ab64, m);
-        XC_LAUNCHED(ctx);
-        f32_to_f64_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(b_row, ab64 + m, m);
+        f32_to_f64_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, st>>>(a_row, b_row, ab64, m);
         XC_LAUNCHED(ctx);
         a = ab64;
         b = ab64 + m;
+    } else if (dtype != XC_F32) {
+        return XC_ERR_UNSUPPORTED;
     }
-    return xc_fw_iterate_dense(ctx, eta, dtype, n, m, ld, y_true, ld_true, a, b, k, raw, raw + m, nullptr, stream);
+    if (!raw_is_zero) XC_CUDA_TRY(ctx, cudaMemsetAsync(raw, 0, sizeof(double) * 2 * m, st));
+    if (dtype == XC_F32)
+        return launch_fw_dense<float>(ctx, eta, n, m, ld, y_true, ld_true, a, b, k, raw, raw + m, nullptr, st);
+    return launch_fw_dense<double>(ctx, eta, n, m, ld, y_true, ld_true, a, b, k, raw, raw + m, nullptr, st);
 }
 
-extern "C" int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int first, const double *raw,
+extern "C" int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int first, double *raw,
                                  const double *colsum, int64_t m, double n_global, int normalize, int skip_tn,
                                  double *Cm, double *Ci, const double *alphas_dev, int64_t n_alphas,
-                                 double fixed_alpha, double *scratch_dev, double *scal, void *stream)
+                                 double fixed_alpha, double *scratch_dev, double *scal, float *a_next, float *b_next,
+                                 double *scal_next, int zero_raw, void *stream)
 {
-    if (!ctx || !p || !raw || !colsum || !Cm || !Ci || !scal) return XC_ERR_INVALID;
-    int rc;
+    if (!ctx || !p || !raw || !colsum || !Cm || !Ci || !scal || m <= 0) return XC_ERR_INVALID;
+    if ((a_next == nullptr) != (b_next == nullptr)) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = reduce_grid(ctx, m);
+    double *zr = zero_raw ? raw : nullptr;
     if (first) {  // classifier 0: its confusion vectors ARE the running ones (frank_wolfe.py:564-572)
-        rc = xc_fw_make_conf(ctx, raw, raw + m, colsum, m, n_global, normalize, skip_tn, Cm, stream);
-        if (rc) return rc;
-        return xc_fw_metric_grad(ctx, p, Cm, m, nullptr, nullptr, scal + 0, stream);
+        fw_conf_prep_kernel<<<grid, 256, 0, st>>>(*p, raw, raw + m, colsum, m, n_global, normalize, skip_tn, nullptr, Cm,
+                                                  nullptr, nullptr, scal + 0, ctx->red_partials, ctx->red_counter);
+        XC_LAUNCHED(ctx);
+        if (a_next || zr) {
+            fw_finish_kernel<<<grid, 256, 0, st>>>(*p, Cm, nullptr, m, nullptr, a_next, b_next, zr, nullptr,
+                                                   scal_next, ctx->red_partials, ctx->red_counter);
+            XC_LAUNCHED(ctx);
+        }
+        return XC_OK;
     }
-    rc = xc_fw_make_conf(ctx, raw, raw + m, colsum, m, n_global, normalize, skip_tn, Ci, stream);
-    if (rc) return rc;
-    rc = xc_fw_metric_grad(ctx, p, Ci, m, nullptr, nullptr, scal + 1, stream);  // utility of classifier i
-    if (rc) return rc;
-    if (alphas_dev) {
-        rc = xc_fw_alpha_search(ctx, p, Cm, Ci, m, alphas_dev, n_alphas, scratch_dev, scal + 2, stream);
+    const bool search = alphas_dev != nullptr;
+    if (search && !scratch_dev) return XC_ERR_INVALID;
+    AlphaScratch s = alpha_scratch(scratch_dev, m, n_alphas);
+    const bool two_stage = search && alpha_two_stage(p, n_alphas);
+    fw_conf_prep_kernel<<<grid, 256, 0, st>>>(*p, raw, raw + m, colsum, m, n_global, normalize, skip_tn, Cm, Ci,
+                                              two_stage ? s.lin : nullptr, s.linE, scal + 1, ctx->red_partials,
+                                              ctx->red_counter);
+    XC_LAUNCHED(ctx);
+    if (search) {
+        int rc = alpha_search_launch(ctx, p, Cm, Ci, m, alphas_dev, n_alphas, s, scal + 2, st);
         if (rc) return rc;
     } else {
-        XC_CUDA_TRY(ctx, cudaMemcpyAsync(scal + 2, &fixed_alpha, sizeof(double), cudaMemcpyHostToDevice,
-                                         (cudaStream_t)stream));
+        XC_CUDA_TRY(ctx, cudaMemcpyAsync(scal + 2, &fixed_alpha, sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    rc = xc_fw_combine(ctx, Cm, Ci, 4 * m, scal + 2, stream);
-    if (rc) return rc;
-    return xc_fw_metric_grad(ctx, p, Cm, m, nullptr, nullptr, scal + 4, stream);  // new utility
+    fw_finish_kernel<<<grid, 256, 0, st>>>(*p, Cm, Ci, m, scal + 2, a_next, b_next, zr, scal + 4, scal_next,
+                                           ctx->red_partials, ctx->red_counter);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
 }

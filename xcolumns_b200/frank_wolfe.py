@@ -10,6 +10,7 @@ iteration travel to the host (for the stopping rules and ``meta``).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from time import time
 from typing import Any, Callable, Dict, Optional, Tuple, Union
 
@@ -195,6 +196,10 @@ def find_classifier_using_fw(
     alphas_dev = torch.from_numpy(alphas).to(device)
     vals_dev = torch.empty((int(ctx.lib.xc_fw_alpha_scratch_bytes(m, int(alphas.size))) + 7) // 8, **f64)
     sptr = lambda i: C.c_void_p(scal[i:].data_ptr())
+    debug = bool(os.environ.get("XCOLUMNS_B200_FW_DEBUG"))   # diagnostics: meta["alpha_search_ctl"] (syncs!)
+    debug_ctl = os.environ.get("XCOLUMNS_B200_FW_DEBUG") == "2"   # also read the search control block per step
+    dbg_ctl = []
+    ctl_off = int(ctx.lib.xc_fw_alpha_ctl_offset(m, int(alphas.size)))
 
     def iterate(out: torch.Tensor):
         """confusion vectors of the classifier held in (a_dev, b_dev) -> out (4m)"""
@@ -231,18 +236,25 @@ def find_classifier_using_fw(
         n_alphas = int(alphas.size)
 
         def step(i, first):
-            """enqueue iteration i (no host sync); its scalars land in scal_all[i] / host_all[i]"""
+            """enqueue iteration i (no host sync); its scalars land in scal_all[i] / host_all[i].  The
+            finish call also writes classifier row i + 1 (gradient at the new running matrix) and
+            the next iteration's "old utility" into scal_all[i + 1][0]."""
             sc = C.c_void_p(scal_all[i].data_ptr())
-            ctx.call("xc_fw_step_begin", C.byref(params), 0 if first else 1, dev.ptr(pd_.t), pd_.code, n, m, pd_.ld,
-                     dev.ptr(td_.t), td_.ld, dev.ptr(Cm), rowp(A_dev, i), rowp(B_dev, i), dev.ptr(ab64), k,
-                     dev.ptr(raw), sc, sp())
+            has_next = i + 1 <= max_iters
+            ctx.call("xc_fw_step_begin", dev.ptr(pd_.t), pd_.code, n, m, pd_.ld, dev.ptr(td_.t), td_.ld,
+                     rowp(A_dev, i), rowp(B_dev, i), dev.ptr(ab64), k, dev.ptr(raw), 0 if first else 1, sp())
             comm.allreduce_sum_(raw)
             ctx.call("xc_fw_step_finish", C.byref(params), 1 if first else 0, dev.ptr(raw), dev.ptr(colsum), m,
                      C.c_double(float(n_global)), int(bool(normalize_conf_matrix)), int(bool(skip_tn)), dev.ptr(Cm),
                      dev.ptr(Ci), dev.ptr(alphas_dev) if search_for_best_alpha else None, n_alphas,
-                     C.c_double(2 / (i + 1)), dev.ptr(vals_dev), sc, sp())
+                     C.c_double(2 / (i + 1)), dev.ptr(vals_dev), sc,
+                     rowp(A_dev, i + 1) if has_next else None, rowp(B_dev, i + 1) if has_next else None,
+                     C.c_void_p(scal_all[i + 1].data_ptr()), 1, sp())
             host_all[i].copy_(scal_all[i], non_blocking=True)
-            ev = torch.cuda.Event()
+            if debug_ctl:
+                w = vals_dev.view(torch.int32)[ctl_off // 4: ctl_off // 4 + 32].cpu().tolist()
+                dbg_ctl.append((w[16], w[0], w[2]))   # stage-1 candidates, after refinement, label slices
+            ev = torch.cuda.Event(enable_timing=debug)
             ev.record(torch.cuda.current_stream(device))
             events[i] = ev
 
@@ -294,19 +306,34 @@ def find_classifier_using_fw(
         meta["utilities"].append(new_utility)
         P[:i] *= 1 - alpha
         P[i] = alpha
-    if not is_csr:
-        A = A_dev.cpu().numpy()
-        B = B_dev.cpu().numpy()
-    A, B, P = A[:n_used], B[:n_used], P[:n_used]
+    P = P[:n_used]
+    if isinstance(y_true, torch.Tensor):
+        # tensors in -> tensors out on the caller's device; dense classifiers never leave the GPU
+        src_a, src_b = (A_dev[:n_used], B_dev[:n_used]) if not is_csr else (torch.from_numpy(A[:n_used]), torch.from_numpy(B[:n_used]))
+        A, B = (v.to(device=y_proba.device, dtype=y_proba.dtype, copy=True) for v in (src_a, src_b))
+        P = torch.tensor(P, dtype=y_proba.dtype, device=y_proba.device)
+    elif not is_csr:
+        # one pinned staging buffer, one async copy, one sync (pageable copies cost ~1 ms each here)
+        stage = torch.empty((2, n_used, m), dtype=torch.float32).pin_memory()
+        stage[0].copy_(A_dev[:n_used], non_blocking=True)
+        stage[1].copy_(B_dev[:n_used], non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        A, B = stage[0].numpy(), stage[1].numpy()
+    else:
+        A, B = A[:n_used], B[:n_used]
     log_info(f"  Final utility of the randomized classifier: {new_utility}, number of sub-classifiers: {len(A)}", verbose)
 
-    if isinstance(y_true, torch.Tensor):
-        A, B, P = (torch.tensor(v, dtype=y_proba.dtype, device=y_proba.device) for v in (A, B, P))
     clf = RandomizedWeightedClassifier(k, A, B, P)
     if return_meta:
         meta["time"] = time() - meta["time"]
         meta["iters"] = i
         meta["launches"] = ctx.launches()
+        if debug:
+            meta["alpha_search_ctl"] = dbg_ctl   # per enqueued iteration: (stage-1 candidates, refined, slices)
+            if not is_csr:
+                torch.cuda.synchronize(device)
+                ks = sorted(events)
+                meta["step_ms"] = [events[a_].elapsed_time(events[b_]) for a_, b_ in zip(ks[:-1], ks[1:])]
         return clf, meta
     return clf
 
