@@ -287,8 +287,9 @@ XC_API int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4,
  * caller all-reduces raw[0..2m) when rows are sharded over ranks.
  *   begin : fused weighted top-k + accumulation of raw = [tp, cnt] with the classifier held in the
  *           float32 rows (a_row, b_row) (e.g. row i of the classifier matrices; written by the
- *           previous finish call).  ab64: 2*m doubles, used when dtype == XC_F64 (the float32 rows
- *           are widened like numpy promotes them).  raw_is_zero != 0: raw was already cleared by
+ *           previous finish call).  ab64: 2*(m+1) doubles, used when dtype == XC_F64 (the float32
+ *           rows are widened like numpy promotes them).  Rows that are 16-byte aligned are read
+ *           with 128-bit loads.  raw_is_zero != 0: raw was already cleared by
  *           the previous finish call (zero_raw), no memset is issued.
  *   finish: first != 0: Cm = confusion vectors of classifier 0, scal[0] = metric(Cm).  Otherwise
  *           Ci = confusion vectors of classifier i, scal[1] = metric(Ci), scal[2..3] = line search

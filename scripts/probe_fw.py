@@ -30,8 +30,11 @@ def main():
     if "XC_PROBE_CHILD" not in os.environ:
         for ab in ("rand",):
             os.environ["XC_PROBE_AB"] = ab
-            for path_env, occ in (("plain", "6"), ("staged", "6"), ("staged", "5"), ("staged", "4")):
-                child(path_env + ":" + ab, occ, n, m)
+            for r, d in (("2", "2"), ("2", "4"), ("1", "2"), ("1", "4")):
+                os.environ["XCOLUMNS_B200_DENSE_R"] = r
+                os.environ["XCOLUMNS_B200_FW_DEPTH"] = d
+                child(f"plain:R{r}:D{d}", "5", n, m)
+            child("staged:" + ab, "5", n, m)
         return
     from xcolumns_b200 import _device as dev
     from xcolumns_b200.synth import dense_probs_device

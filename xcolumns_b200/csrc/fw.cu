@@ -14,11 +14,11 @@ constexpr int kThreads = 256;
 // gains = eta * a + b with separate IEEE multiply/add in the dtype numpy would use
 // (weighted_prediction.py:37-41), top-k per row, then for the k selected labels
 //   tp[j] += y_true[i][j],  cnt[j] += 1        (float64 atomics)
-template <typename TE, int R>
+template <typename TE, int R, int DEPTH, class Xf>
 __global__ void __launch_bounds__(kThreads)
 fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_t ld, const TE *__restrict__ y_true,
-                        int64_t ld_true, XfMulAdd<TE> xf, int k, double *tp, double *cnt,
-                        int32_t *__restrict__ pred_idx, bool vec_ok)
+                        int64_t ld_true, Xf xf, int k, double *tp, double *cnt, int32_t *__restrict__ pred_idx,
+                        bool vec_ok)
 {
     const int lane = lane_id();
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -37,7 +37,7 @@ fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_
             tk[r].init();
             dummy[r] = -1;
         }
-        xc_scan_rows<TE, TE, R, false>(rp, m, vec_ok, xf, tk, dummy, k);
+        xc_scan_rows<TE, TE, R, false, Xf, DEPTH>(rp, m, vec_ok, xf, tk, dummy, k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (row_id[r] < 0) continue;
@@ -51,52 +51,6 @@ fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_
                 int v = __shfl_sync(XC_FULL, j, src);
                 if (lane < k) pred_idx[row_id[r] * k + lane] = v == 0x7fffffff ? -1 : v;
             }
-        }
-    }
-}
-
-// Same iterate with the classifier staged through shared memory (xc_scan.cuh, "CTA-cooperative scan"):
-// one row per warp, kWarpsS warps per CTA walking the column chunks together.
-constexpr int kThreadsS = 256;
-
-template <typename TE, int OCC>
-__global__ void __launch_bounds__(kThreadsS, OCC)
-fw_iterate_dense_staged_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_t ld,
-                               const TE *__restrict__ y_true, int64_t ld_true, StageMulAdd<TE> st, int k, double *tp,
-                               double *cnt, int32_t *__restrict__ pred_idx)
-{
-    __shared__ __align__(16) char smem[2 * XC_STAGE_BYTES];
-    constexpr int W = kThreadsS / 32;
-    const int lane = lane_id(), wid = threadIdx.x >> 5;
-    const int64_t ngroups = (n + W - 1) / W;
-    XcStagePipe<StageMulAdd<TE>> pipe(st, m, smem);
-    if ((int64_t)blockIdx.x >= ngroups) return;
-    pipe.prime();
-    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        int64_t i = grp * W + wid;
-        const bool valid = i < n;
-        if (!valid) i = grp * W;
-        const TE *rp = eta + i * ld;
-        WarpTopK<TE> tk;
-        tk.init();
-        const bool last_grp = grp + gridDim.x >= ngroups;
-        for (int c = 0; c < pipe.nch; ++c) {
-            // (a variant that issued the next double step's loads before the tile barrier was measured
-            // slower: 372 vs 351 us at 14 k x 31 k -- the extra live registers cost more than the bubbles)
-            const char *buf = pipe.acquire(!(last_grp && c + 1 == pipe.nch));
-            const int64_t cbeg = (int64_t)c * StageMulAdd<TE>::TC;
-            xc_scan_chunk_staged<TE, TE, false>(rp, cbeg, min(m, cbeg + StageMulAdd<TE>::TC), st, buf, tk, -1, k);
-        }
-        if (!valid) continue;
-        const int j = tk.idx;
-        if (lane < k && j != 0x7fffffff) {
-            atomicAdd(tp + j, (double)__ldg(y_true + i * ld_true + j));
-            atomicAdd(cnt + j, 1.0);
-        }
-        if (pred_idx) {
-            int src = warp_rank_src(j, k);
-            int v = __shfl_sync(XC_FULL, j, src);
-            if (lane < k) pred_idx[i * k + lane] = v == 0x7fffffff ? -1 : v;
         }
     }
 }
@@ -828,48 +782,41 @@ int launch_fw_dense(xc_ctx *ctx, const void *eta, int64_t n, int64_t m, int64_t 
     bool vec_ok = xc_aligned16(eta) && (ld % V == 0);
     XfMulAdd<TE> xf{(const TE *)a, (const TE *)b};
     const int64_t coef_bytes = 2 * m * (int64_t)sizeof(TE);
-    // classifier larger than L1: stage it through shared memory ($XCOLUMNS_B200_FW_PATH=plain|staged)
-    static int force_path = -1;
-    if (force_path < 0) {
-        const char *e = getenv("XCOLUMNS_B200_FW_PATH");
-        force_path = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'p' ? 2 : 0));
-    }
-    if (vec_ok && (force_path == 1 || (force_path == 0 && coef_bytes > 160 * 1024 && n >= 65536))) {
-        static int occ = -1;  // CTAs per SM the kernel is compiled for: $XCOLUMNS_B200_FW_OCC=4|5|6 (64 / 48 / 40 registers)
-        if (occ < 0) {
-            const char *e = getenv("XCOLUMNS_B200_FW_OCC");
-            occ = (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 5;
-        }
-        auto kern = occ == 4 ? fw_iterate_dense_staged_kernel<TE, 4>
-                             : (occ == 6 ? fw_iterate_dense_staged_kernel<TE, 6> : fw_iterate_dense_staged_kernel<TE, 5>);
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreadsS, 0);
-        if (per_sm < 1) per_sm = 1;
-        const int64_t ngroups = (n + kThreadsS / 32 - 1) / (kThreadsS / 32);
-        const int64_t resident = (int64_t)ctx->sm_count * per_sm;
-        const int64_t waves = (ngroups + resident - 1) / resident;
-        const int grid = (int)((ngroups + waves - 1) / waves);
-        StageMulAdd<TE> stage{(const TE *)a, (const TE *)b, (!a || xc_aligned16(a)) && (!b || xc_aligned16(b))};
-        kern<<<grid, kThreadsS, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true, stage, k, tp, cnt,
-                                         pred_idx);
-        XC_LAUNCHED(ctx);
-        return XC_OK;
-    }
     int rr = coef_bytes <= 160 * 1024 ? 1 : (coef_bytes <= 512 * 1024 ? 2 : 4);
+    // with 128-bit coefficient loads one row per warp wins even when the classifier spills out of L1
+    // (measured at 14 k x 31 k, 248 KB of coefficients: R = 1 286 us, R = 2 311 us)
+    if (vec_ok && a && b && xc_aligned16(a) && xc_aligned16(b) && coef_bytes <= 1024 * 1024) rr = 1;
     if (const char *e = getenv("XCOLUMNS_B200_DENSE_R")) {
         int v = atoi(e);
         if (v == 1 || v == 2 || v == 4) rr = v;
     }
-#define XC_GO(R)                                                                                             \
-    {                                                                                                        \
-        auto kern = fw_iterate_dense_kernel<TE, R>;                                                          \
+    // loads per row in flight
+    static int depth_env = -1;  // $XCOLUMNS_B200_FW_DEPTH=2|4
+    if (depth_env < 0) {
+        const char *e = getenv("XCOLUMNS_B200_FW_DEPTH");
+        depth_env = (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
+    }
+    const int depth = depth_env ? depth_env : 2;  // 4 measured slower (350 vs 334 us at 14 k x 31 k)
+    // classifier rows present and 16-byte aligned (the host shim pads the classifier matrices): vector loads
+    const bool coef_vec = vec_ok && a && b && xc_aligned16(a) && xc_aligned16(b);
+    XfMulAddVec<TE> xfv{(const TE *)a, (const TE *)b};
+#define XC_GO(R, D)                                                                                          \
+    if (coef_vec) {                                                                                          \
+        auto kern = fw_iterate_dense_kernel<TE, R, D, XfMulAddVec<TE>>;                                      \
+        int grid = grid_for(ctx, kern, (n + R - 1) / R);                                                     \
+        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true, xfv, k, tp,  \
+                                        cnt, pred_idx, vec_ok);                                              \
+    } else {                                                                                                 \
+        auto kern = fw_iterate_dense_kernel<TE, R, D, XfMulAdd<TE>>;                                         \
         int grid = grid_for(ctx, kern, (n + R - 1) / R);                                                     \
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true, xf, k, tp,   \
                                         cnt, pred_idx, vec_ok);                                              \
     }
-    if (rr == 4) XC_GO(4)
-    else if (rr == 2) XC_GO(2)
-    else XC_GO(1)
+    if (rr == 4) XC_GO(4, 2)
+    else if (rr == 2 && depth == 4) XC_GO(2, 4)
+    else if (rr == 2) XC_GO(2, 2)
+    else if (depth == 4) XC_GO(1, 4)
+    else XC_GO(1, 2)
 #undef XC_GO
     XC_LAUNCHED(ctx);
     return XC_OK;
@@ -1117,12 +1064,13 @@ extern "C" int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m
 // ---- one dense Frank-Wolfe iteration as two host calls (the all-reduce of the iterate's raw sums, if
 // any, happens between them) -----------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(kThreads) f32_to_f64_kernel(const float *a, const float *b, double *o, int64_t m)
+__global__ void __launch_bounds__(kThreads)
+f32_to_f64_kernel(const float *a, const float *b, double *oa, double *ob, int64_t m)
 {
     int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (j < m) {
-        o[j] = (double)a[j];
-        o[m + j] = (double)b[j];
+        oa[j] = (double)a[j];
+        ob[j] = (double)b[j];
     }
 }
 }  // namespace
@@ -1137,10 +1085,11 @@ extern "C" int xc_fw_step_begin(xc_ctx *ctx, const void *eta, int dtype, int64_t
     const void *a = a_row, *b = b_row;
     if (dtype == XC_F64) {  // numpy promotes the float32 classifier rows to float64 gains
         if (!ab64) return XC_ERR_INVALID;
-        f32_to_f64_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, st>>>(a_row, b_row, ab64, m);
+        double *b64 = ab64 + ((m + 1) & ~(int64_t)1);  // keeps the second vector 16-byte aligned
+        f32_to_f64_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, st>>>(a_row, b_row, ab64, b64, m);
         XC_LAUNCHED(ctx);
         a = ab64;
-        b = ab64 + m;
+        b = b64;
     } else if (dtype != XC_F32) {
         return XC_ERR_UNSUPPORTED;
     }

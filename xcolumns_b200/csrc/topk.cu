@@ -6,10 +6,10 @@ namespace {
 
 constexpr int kThreads = 256;
 
-template <typename TE, typename G, int R>
+template <typename TE, typename G, int R, class Xf = XfMulAdd<G>>
 __global__ void __launch_bounds__(kThreads)
 topk_dense_kernel(const TE *__restrict__ eta, int64_t n_rows, int64_t m, int64_t ld,
-                  const int32_t *__restrict__ rows, XfMulAdd<G> xf, int k, int32_t *__restrict__ out_idx,
+                  const int32_t *__restrict__ rows, Xf xf, int k, int32_t *__restrict__ out_idx,
                   G *__restrict__ out_val, bool vec_ok)
 {
     const int lane = lane_id();
@@ -30,7 +30,7 @@ topk_dense_kernel(const TE *__restrict__ eta, int64_t n_rows, int64_t m, int64_t
             tk[r].init();
             dummy[r] = -1;
         }
-        xc_scan_rows<TE, G, R, false>(rp, m, vec_ok, xf, tk, dummy, k);
+        xc_scan_rows<TE, G, R, false, Xf>(rp, m, vec_ok, xf, tk, dummy, k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             int src = warp_rank_src(tk[r].idx, k);
@@ -135,7 +135,13 @@ int launch_topk_dense(xc_ctx *ctx, const void *eta, int64_t n_rows, int64_t m, i
         // see dense_rows_per_warp in bca_batched.cu for the measurement
     const int64_t coef_bytes = ((a ? 1 : 0) + (b ? 1 : 0)) * m * (int64_t)sizeof(G);
     const int rr = coef_bytes <= 160 * 1024 ? 1 : (coef_bytes <= 512 * 1024 ? 2 : 4);
-    if (rr == 4) {
+    if (vec_ok && a && b && xc_aligned16(a) && xc_aligned16(b) && coef_bytes <= 1024 * 1024) {
+        // both vectors present and aligned: 128-bit coefficient loads, one row per warp (see XfMulAddVec)
+        XfMulAddVec<G> xfv{(const G *)a, (const G *)b};
+        auto kern = topk_dense_kernel<TE, G, 1, XfMulAddVec<G>>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows, xfv, k, out_idx, (G *)out_val, vec_ok);
+    } else if (rr == 4) {
         auto kern = topk_dense_kernel<TE, G, 4>;
         int grid = grid_for(ctx, kern, (n_rows + 3) / 4);
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows, xf, k, out_idx, (G *)out_val, vec_ok);

@@ -66,6 +66,39 @@ struct XfMulAdd {
     __device__ static __forceinline__ double add_rn(double x, double y) { return __dadd_rn(x, y); }
 };
 
+// Same arithmetic, both vectors present and 16-byte aligned: one 128-bit load per vector and chunk
+// instead of 2 V scalar loads and no null checks in the streaming loop (measured on the Frank-Wolfe
+// iterate at 14 k x 31 k: the scalar version kept the LSU pipe 68 % busy and capped the kernel at
+// 0.78 of the copy bandwidth).
+template <typename G>
+struct XfMulAddVec {
+    const G *a;
+    const G *b;
+    template <typename TE, int V>
+    __device__ __forceinline__ void apply_vec(int64_t c, const TE (&e)[V], G (&g)[V], G (&ca)[V], G (&cb)[V],
+                                              bool first) const
+    {
+        static_assert(V * sizeof(G) == 16 || V * sizeof(G) == 32, "one or two 16-byte loads per vector");
+        if (first) {
+            constexpr int Q = (int)(V * sizeof(G) / 16);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 u = __ldg(reinterpret_cast<const float4 *>(a + c) + q);
+                const float4 w = __ldg(reinterpret_cast<const float4 *>(b + c) + q);
+                memcpy(reinterpret_cast<char *>(ca) + 16 * q, &u, 16);
+                memcpy(reinterpret_cast<char *>(cb) + 16 * q, &w, 16);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) g[v] = XfMulAdd<G>::add_rn(XfMulAdd<G>::mul_rn((G)e[v], ca[v]), cb[v]);
+    }
+    template <typename TE>
+    __device__ __forceinline__ G apply_one(int64_t c, TE e) const
+    {
+        return XfMulAdd<G>::add_rn(XfMulAdd<G>::mul_rn((G)e, __ldg(a + c)), __ldg(b + c));
+    }
+};
+
 // gains = fma(B_j, eta, A_j) with interleaved float2 coefficients (B_j, A_j) (batched BCA)
 struct XfAffine {
     const float2 *coef;
@@ -140,7 +173,7 @@ __device__ __forceinline__ G xc_vmax(const G (&g)[V])
 // rp[r]: start of row r; vec_ok: rows are 16-byte aligned (base aligned and ld % V == 0).
 // old_idx[r]: (SKIP) lanes < k hold the labels already seeded into tk[r]; candidates equal to
 // one of them are ignored (their gain under the "selected" formula is already in the list).
-template <typename TE, typename G, int R, bool SKIP, class Xf>
+template <typename TE, typename G, int R, bool SKIP, class Xf, int DEPTH = 2>
 __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m, bool vec_ok, const Xf &xf,
                                              WarpTopK<G> (&tk)[R], const int (&old_idx)[R], int k)
 {
@@ -148,37 +181,32 @@ __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m
     constexpr int STEP = 32 * V;  // columns one warp covers per 16-byte load
     const int lane = lane_id();
     const int64_t mv = vec_ok ? (m / V) * V : 0;
-    const int64_t m2 = (mv / (2 * STEP)) * (2 * STEP);  // part covered by full, unguarded double steps
+    const int64_t m2 = (mv / (DEPTH * STEP)) * (DEPTH * STEP);  // part covered by full, unguarded multi-steps
     const G qnan = (G)NAN;
 
-    // ---- main loop: two 16-byte chunks per row in flight, no bounds checks, no local memory ----
-    for (int64_t c0 = 0; c0 < m2; c0 += 2 * STEP) {
-        const int64_t cA = c0 + (int64_t)lane * V;
-        const int64_t cB = cA + STEP;
-        TE eA[R][V], eB[R][V];
+    // ---- main loop: DEPTH 16-byte chunks per row in flight, no bounds checks, no local memory ----
+    // (DEPTH = 4 trades occupancy for bytes in flight: for short, wide inputs -- few row tasks per warp,
+    // grid below the occupancy limit -- the kernel is bound by the latency of its own loads)
+    for (int64_t c0 = 0; c0 < m2; c0 += DEPTH * STEP) {
+        TE e[DEPTH][R][V];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            XcVec<TE>::load(rp[r] + cA, eA[r]);
-            XcVec<TE>::load(rp[r] + cB, eB[r]);
-        }
-        G gA[R][V], gB[R][V], ca[V], cb[V];
+        for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+            for (int r = 0; r < R; ++r) XcVec<TE>::load(rp[r] + c0 + (int64_t)lane * V + d * STEP, e[d][r]);
+        G g[DEPTH][R][V], ca[V], cb[V];
         bool hit = false;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            xf.template apply_vec<TE, V>(cA, eA[r], gA[r], ca, cb, r == 0);
-            hit |= tk[r].passes(xc_vmax<G, V>(gA[r]));
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            xf.template apply_vec<TE, V>(cB, eB[r], gB[r], ca, cb, r == 0);
-            hit |= tk[r].passes(xc_vmax<G, V>(gB[r]));
-        }
-        if (__any_sync(XC_FULL, hit)) {
+        for (int d = 0; d < DEPTH; ++d)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                xc_scan_insert<G, V, SKIP>(tk[r], gA[r], c0, V, k, old_idx[r]);
-                xc_scan_insert<G, V, SKIP>(tk[r], gB[r], c0 + STEP, V, k, old_idx[r]);
+                xf.template apply_vec<TE, V>(c0 + (int64_t)lane * V + d * STEP, e[d][r], g[d][r], ca, cb, r == 0);
+                hit |= tk[r].passes(xc_vmax<G, V>(g[d][r]));
             }
+        if (__any_sync(XC_FULL, hit)) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int d = 0; d < DEPTH; ++d) xc_scan_insert<G, V, SKIP>(tk[r], g[d][r], c0 + d * STEP, V, k, old_idx[r]);
         }
     }
     // ---- guarded single steps for the rest of the vectorisable part ------------------------------
@@ -220,215 +248,6 @@ __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m
         }
     }
 }
-
-// ---- CTA-cooperative scan: coefficients staged through shared memory ------------------------------
-// When the per-label coefficient vectors outgrow L1 (2 m sizeof(G) > ~160 KB, e.g. the Frank-Wolfe
-// classifier at m = 31 k) every warp re-reads them from L2 for every row: coefficient traffic equals
-// the HBM stream and the kernel sits at 0.70 of the copy bandwidth.  Here all warps of a CTA walk the
-// column chunks in lock-step, the chunk's coefficients are copied once per CTA into a double-buffered
-// shared-memory tile with cp.async (chunk c+1 lands while chunk c is consumed; one barrier per chunk)
-// and are read back with conflict-free LDS.128.  One row per warp, so many independent CTAs per SM
-// keep the HBM queue full while a warp is in the list-update slow path.
-constexpr int XC_STAGE_BYTES = 16384;  // per buffer
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// gains = eta * a + b (XfMulAdd semantics, both vectors present), tile layout: G ca[TC] | G cb[TC]
-template <typename G>
-struct StageMulAdd {
-    static constexpr int TC = XC_STAGE_BYTES / (2 * (int)sizeof(G));
-    static constexpr int V = 16 / (int)sizeof(G);
-    const G *a;
-    const G *b;
-    bool al16;  // a and b are 16-byte aligned (chunk starts are multiples of TC)
-
-    // every thread of the CTA calls; copies columns [cbeg, min(m, cbeg + TC)) of a and b
-    __device__ __forceinline__ void issue(char *buf, int64_t cbeg, int64_t m, int tid, int nthreads) const
-    {
-        G *sa = reinterpret_cast<G *>(buf), *sb = sa + TC;
-        const int ncol = (int)min((int64_t)TC, m - cbeg);
-        const G *ga = a + cbeg, *gb = b + cbeg;
-        if (al16) {
-            const int nv = ncol / V;
-            for (int t = tid; t < nv; t += nthreads) {
-                cp_async16(sa + t * V, ga + t * V);
-                cp_async16(sb + t * V, gb + t * V);
-            }
-            for (int t = nv * V + tid; t < ncol; t += nthreads) {
-                sa[t] = __ldg(ga + t);
-                sb[t] = __ldg(gb + t);
-            }
-        } else {
-            for (int t = tid; t < ncol; t += nthreads) {
-                if (sizeof(G) == 4) {
-                    cp_async4(sa + t, ga + t);
-                    cp_async4(sb + t, gb + t);
-                } else {
-                    cp_async8(sa + t, ga + t);
-                    cp_async8(sb + t, gb + t);
-                }
-            }
-        }
-    }
-    // col: column inside the tile (multiple of V)
-    template <typename TE>
-    __device__ __forceinline__ void apply_vec(const char *buf, int col, const TE (&e)[V], G (&g)[V]) const
-    {
-        const G *sa = reinterpret_cast<const G *>(buf) + col;
-        G ca[V], cb[V];
-        const float4 u = *reinterpret_cast<const float4 *>(sa);
-        const float4 w = *reinterpret_cast<const float4 *>(sa + TC);
-        memcpy(ca, &u, 16);
-        memcpy(cb, &w, 16);
-#pragma unroll
-        for (int v = 0; v < V; ++v) g[v] = XfMulAdd<G>::add_rn(XfMulAdd<G>::mul_rn((G)e[v], ca[v]), cb[v]);
-    }
-    template <typename TE>
-    __device__ __forceinline__ G apply_one(const char *buf, int col, TE e) const
-    {
-        const G *sa = reinterpret_cast<const G *>(buf) + col;
-        return XfMulAdd<G>::add_rn(XfMulAdd<G>::mul_rn((G)e, sa[0]), sa[TC]);
-    }
-};
-
-// gains = fma(B_j, eta, A_j), interleaved float2 coefficients (batched BCA); tile: float2 coef[TC]
-struct StageAffine {
-    static constexpr int TC = XC_STAGE_BYTES / 8;
-    const float2 *coef;  // 16-byte aligned (allocated by the host shim)
-
-    __device__ __forceinline__ void issue(char *buf, int64_t cbeg, int64_t m, int tid, int nthreads) const
-    {
-        float2 *sc = reinterpret_cast<float2 *>(buf);
-        const int ncol = (int)min((int64_t)TC, m - cbeg);
-        const int nv = ncol / 2;
-        for (int t = tid; t < nv; t += nthreads) cp_async16(sc + 2 * t, coef + cbeg + 2 * t);
-        if ((ncol & 1) && tid == 0) sc[ncol - 1] = __ldg(coef + cbeg + ncol - 1);
-    }
-    template <typename TE, int V>
-    __device__ __forceinline__ void apply_vec(const char *buf, int col, const TE (&e)[V], float (&g)[V]) const
-    {
-        const float2 *sc = reinterpret_cast<const float2 *>(buf) + col;
-#pragma unroll
-        for (int v = 0; v < V; v += 2) {
-            const float4 u = *reinterpret_cast<const float4 *>(sc + v);
-            g[v] = fmaf(u.x, (float)e[v], u.y);
-            g[v + 1] = fmaf(u.z, (float)e[v + 1], u.w);
-        }
-    }
-    template <typename TE>
-    __device__ __forceinline__ float apply_one(const char *buf, int col, TE e) const
-    {
-        const float2 t = reinterpret_cast<const float2 *>(buf)[col];
-        return fmaf(t.x, (float)e, t.y);
-    }
-};
-
-// One chunk of one row: columns [cbeg, cend) inside one tile, coefficients in `buf`, tile_off = column of
-// cbeg inside the tile.  Rows must be 16-byte aligned (vec_ok); unaligned inputs use the unstaged kernels.
-template <typename TE, typename G, bool SKIP, class Stage>
-__device__ __forceinline__ void xc_scan_chunk_staged(const TE *rp, int64_t cbeg, int64_t cend, const Stage &st,
-                                                     const char *buf, WarpTopK<G> &tk, int old_idx, int k,
-                                                     int tile_off = 0)
-{
-    constexpr int V = XcVec<TE>::V;
-    constexpr int STEP = 32 * V;
-    const int lane = lane_id();
-    const int len = (int)(cend - cbeg);
-    const int len2 = (len / (2 * STEP)) * (2 * STEP);
-    const int lenv = (len / V) * V;
-    const G qnan = (G)NAN;
-    const TE *p = rp + cbeg;
-    for (int c0 = 0; c0 < len2; c0 += 2 * STEP) {
-        const int cA = c0 + lane * V, cB = cA + STEP;
-        TE eA[V], eB[V];
-        XcVec<TE>::load(p + cA, eA);
-        XcVec<TE>::load(p + cB, eB);
-        G gA[V], gB[V];
-        st.template apply_vec<TE>(buf, tile_off + cA, eA, gA);
-        st.template apply_vec<TE>(buf, tile_off + cB, eB, gB);
-        bool hit = tk.passes(xc_vmax<G, V>(gA)) | tk.passes(xc_vmax<G, V>(gB));
-        if (__any_sync(XC_FULL, hit)) {
-            xc_scan_insert<G, V, SKIP>(tk, gA, cbeg + c0, V, k, old_idx);
-            xc_scan_insert<G, V, SKIP>(tk, gB, cbeg + c0 + STEP, V, k, old_idx);
-        }
-    }
-    for (int c0 = len2; c0 < lenv; c0 += STEP) {
-        const int c = c0 + lane * V;
-        G g[V];
-        if (c < lenv) {
-            TE e[V];
-            XcVec<TE>::load(p + c, e);
-            st.template apply_vec<TE>(buf, tile_off + c, e, g);
-        } else {
-#pragma unroll
-            for (int v = 0; v < V; ++v) g[v] = qnan;
-        }
-        if (__any_sync(XC_FULL, tk.passes(xc_vmax<G, V>(g)))) xc_scan_insert<G, V, SKIP>(tk, g, cbeg + c0, V, k, old_idx);
-    }
-    for (int c0 = lenv; c0 < len; c0 += 32) {
-        const int c = c0 + lane;
-        G g1[1];
-        g1[0] = (c < len) ? st.template apply_one<TE>(buf, tile_off + c, ld_stream(p + c)) : qnan;
-        if (__any_sync(XC_FULL, tk.passes(g1[0]))) xc_scan_insert<G, 1, SKIP>(tk, g1, cbeg + c0, 1, k, old_idx);
-    }
-}
-
-// Flat (row group, chunk) pipeline state shared by the staged kernels.  Usage per CTA:
-//   XcStagePipe<Stage> pipe(st, m, smem);  pipe.prime();
-//   for each row group:  for (c = 0; c < pipe.nch; ++c) { const char *buf = pipe.acquire(more_work_follows);
-//                                                         xc_scan_chunk_staged(..., buf, ...); }
-template <class Stage>
-struct XcStagePipe {
-    const Stage &st;
-    const int64_t m;
-    char *smem;  // 2 * XC_STAGE_BYTES
-    int nch;
-    int next_c;   // chunk id the next issue() will copy
-    unsigned it;  // flat step counter (buffer = it & 1)
-
-    __device__ __forceinline__ XcStagePipe(const Stage &s, int64_t m_, char *smem_) : st(s), m(m_), smem(smem_)
-    {
-        nch = (int)((m + Stage::TC - 1) / Stage::TC);
-        next_c = 0;
-        it = 0;
-    }
-    __device__ __forceinline__ void prime()
-    {
-        st.issue(smem, 0, m, threadIdx.x, blockDim.x);
-        cp_async_commit();
-        next_c = nch > 1 ? 1 : 0;
-    }
-    // wait for the current chunk's tile, start the copy of the following one; returns the tile to read
-    __device__ __forceinline__ const char *acquire(bool more)
-    {
-        cp_async_wait_all();
-        __syncthreads();  // tile `it` is visible to everyone AND everyone is done with tile `it - 1`
-        char *cur = smem + (it & 1) * XC_STAGE_BYTES;
-        if (more) {
-            st.issue(smem + ((it + 1) & 1) * XC_STAGE_BYTES, (int64_t)next_c * Stage::TC, m, threadIdx.x, blockDim.x);
-            cp_async_commit();
-            next_c = next_c + 1 == nch ? 0 : next_c + 1;
-        }
-        ++it;
-        return cur;
-    }
-};
 
 // rank-sort helper: lane t (< k) learns which lane holds the label of rank t (ascending label id)
 __device__ __forceinline__ int warp_rank_src(int idx, int k)

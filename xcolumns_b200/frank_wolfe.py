@@ -227,12 +227,13 @@ def find_classifier_using_fw(
         ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, None, None, sptr(0), sp())
     else:
         # -------- dense rows: two C calls per iteration, classifier matrices live on the device
-        A_dev = torch.zeros((max_iters + 1, m), dtype=torch.float32, device=device)
-        B_dev = torch.zeros((max_iters + 1, m), dtype=torch.float32, device=device)
-        A_dev[0].copy_(torch.from_numpy(A[0]))
-        B_dev[0].copy_(torch.from_numpy(B[0]))
-        ab64 = torch.empty(2 * m, **f64) if pd_.code == 1 else None
-        rowp = lambda t, i: C.c_void_p(t.data_ptr() + 4 * m * i)
+        ldc = (m + 3) // 4 * 4      # classifier rows start 16-byte aligned -> 128-bit coefficient loads
+        A_dev = torch.zeros((max_iters + 1, ldc), dtype=torch.float32, device=device)
+        B_dev = torch.zeros((max_iters + 1, ldc), dtype=torch.float32, device=device)
+        A_dev[0, :m].copy_(torch.from_numpy(A[0]))
+        B_dev[0, :m].copy_(torch.from_numpy(B[0]))
+        ab64 = torch.empty(2 * (m + 1), **f64) if pd_.code == 1 else None
+        rowp = lambda t, i: C.c_void_p(t.data_ptr() + 4 * ldc * i)
         n_alphas = int(alphas.size)
 
         def step(i, first):
@@ -309,14 +310,14 @@ def find_classifier_using_fw(
     P = P[:n_used]
     if isinstance(y_true, torch.Tensor):
         # tensors in -> tensors out on the caller's device; dense classifiers never leave the GPU
-        src_a, src_b = (A_dev[:n_used], B_dev[:n_used]) if not is_csr else (torch.from_numpy(A[:n_used]), torch.from_numpy(B[:n_used]))
+        src_a, src_b = (A_dev[:n_used, :m], B_dev[:n_used, :m]) if not is_csr else (torch.from_numpy(A[:n_used]), torch.from_numpy(B[:n_used]))
         A, B = (v.to(device=y_proba.device, dtype=y_proba.dtype, copy=True) for v in (src_a, src_b))
         P = torch.tensor(P, dtype=y_proba.dtype, device=y_proba.device)
     elif not is_csr:
         # one pinned staging buffer, one async copy, one sync (pageable copies cost ~1 ms each here)
         stage = torch.empty((2, n_used, m), dtype=torch.float32).pin_memory()
-        stage[0].copy_(A_dev[:n_used], non_blocking=True)
-        stage[1].copy_(B_dev[:n_used], non_blocking=True)
+        stage[0].copy_(A_dev[:n_used, :m], non_blocking=True)
+        stage[1].copy_(B_dev[:n_used, :m], non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
         A, B = stage[0].numpy(), stage[1].numpy()
     else:
