@@ -29,7 +29,7 @@ extern "C" {
 
 #define XC_API __attribute__((visibility("default")))
 
-#define XC_ABI_VERSION 1
+#define XC_ABI_VERSION 2
 
 /* element types of probability matrices / weight vectors */
 enum { XC_F32 = 0, XC_F64 = 1 };
@@ -42,7 +42,8 @@ enum {
     XC_METRIC_JACCARD = 3,      /* tp / (tp + fp + fn + eps)                          :797 */
     XC_METRIC_BALANCED_ACC = 4, /* (tpr + tnr) / 2                                    :843 */
     XC_METRIC_GMEAN = 5,        /* sqrt(tpr * tnr)                                    :890 */
-    XC_METRIC_HMEAN = 6         /* 2 tpr tnr / (tpr + tnr)                            :939 */
+    XC_METRIC_HMEAN = 6,        /* 2 tpr tnr / (tpr + tnr)                            :939 */
+    XC_METRIC_PREC_AT_K = 7     /* tp / k  (c1 carries k)                             :513 */
 };
 
 /* summation order of label-wise reductions */
@@ -66,12 +67,16 @@ typedef struct {
     int32_t metric;    /* XC_METRIC_*                                                          */
     int32_t maximize;  /* 1: ascend, 0: descend (ref: block_coordinate.py:187-188)             */
     int32_t skip_tn;   /* 1: tn is a constant -1 vector (ref: confusion_matrix.py:391-393)     */
-    int32_t reserved;
+    int32_t mix;       /* 1: mixed utility (ref: block_coordinate.py:848-1045, frank_wolfe.py:838-915): */
+                       /*    ((1 - mix_alpha) * (tp / mix_k)) + ((mix_alpha * metric) / mix_m)          */
     double c1;         /* 1 + beta**2, computed by the host exactly like python does           */
     double beta2;      /* beta**2                                                              */
     double eps;        /* epsilon of the metric (metric_kwargs["epsilon"], default 1e-9)       */
     double n_div;      /* n if normalize_conf_matrix else 1 (ref: block_coordinate.py:149-151) */
     double n_rows;     /* number of instances (all ranks), whatever the normalisation           */
+    double mix_alpha;  /* weight of the macro metric in the mixed utility                      */
+    double mix_k;      /* k of precision@k                                                     */
+    double mix_m;      /* number of labels                                                     */
 } xc_metric_params;
 
 /* ---- context -------------------------------------------------------------------------- */

@@ -26,7 +26,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libxc_oracle.so")
 
 METRIC_IDS = {"precision": 0, "recall": 1, "fbeta": 2, "f1": 2, "jaccard": 3,
-              "balanced_accuracy": 4, "gmean": 5, "hmean": 6}
+              "balanced_accuracy": 4, "gmean": 5, "hmean": 6, "precision_at_k": 7}
 USES_TN = {4, 5, 6}
 
 
@@ -68,7 +68,27 @@ def metric_params(metric: str, beta: float = 1.0, epsilon: float = 1e-9):
     mid = METRIC_IDS[metric]
     if metric == "f1":
         beta = 1.0
+    if metric == "precision_at_k":      # tp / k: k travels in the c1 slot (pass beta=k)
+        return mid, float(beta), 0.0, float(epsilon)
     return mid, float(1 + beta ** 2), float(beta ** 2), float(epsilon)
+
+
+class _Mix:
+    """Scope of the mixed utility (1 - alpha) * tp / k + alpha * metric / m
+    (block_coordinate.py:848-1045): process-wide switch of the C restatement."""
+
+    def __init__(self, mix):
+        self.mix = mix
+
+    def __enter__(self):
+        if self.mix is not None:
+            a, k, m = self.mix
+            lib().orc_set_mix(C.c_int(1), C.c_double(a), C.c_double(k), C.c_double(m))
+
+    def __exit__(self, *exc):
+        if self.mix is not None:
+            lib().orc_set_mix(C.c_int(0), C.c_double(1.0), C.c_double(1.0), C.c_double(1.0))
+        return False
 
 
 # ------------------------------------------------------------------------------------------
@@ -241,7 +261,15 @@ def predict_using_bc_with_0approx(y_proba, metric: str, k: int, metric_aggregati
                                   normalize_conf_matrix=True, beta=1.0, epsilon=1e-9,
                                   maximize=True, tolerance=1e-6, init_y_pred="top", max_iters=100,
                                   shuffle_order=True, skip_tn=False, seed=None,
-                                  return_state=False):
+                                  return_state=False, mix=None):
+    """Sequential BCA; mix=(alpha, k, m) selects the mixed instance-precision utility.  See _bca."""
+    with _Mix(mix):
+        return _bca(y_proba, metric, k, metric_aggregation, normalize_conf_matrix, beta, epsilon, maximize,
+                    tolerance, init_y_pred, max_iters, shuffle_order, skip_tn, seed, return_state)
+
+
+def _bca(y_proba, metric, k, metric_aggregation, normalize_conf_matrix, beta, epsilon, maximize, tolerance,
+         init_y_pred, max_iters, shuffle_order, skip_tn, seed, return_state):
     """Sequential BCA.  Returns (pred, meta): pred is a dense uint8 0/1 matrix for dense input
     and an (n, k) int32 id matrix (ascending, -1 padded) for CSR input; meta carries
     "utilities" and "iters" like the reference's return_meta (:385, :479-480)."""
@@ -249,7 +277,7 @@ def predict_using_bc_with_0approx(y_proba, metric: str, k: int, metric_aggregati
     # Reference quirk kept on purpose: _calculate_utility (block_coordinate.py:54-63, called at
     # :438/:469) does NOT forward metric_kwargs, so the reported utilities and the stopping test
     # use the metric's default beta=1, epsilon=1e-9 while the gains (:174-185) use the kwargs.
-    _, u_c1, u_b2, u_eps = metric_params(metric)
+    _, u_c1, u_b2, u_eps = metric_params(metric, beta if metric == "precision_at_k" else 1.0)
     is_csr = isinstance(y_proba, csr_matrix)
     n, m = y_proba.shape
     n_div = n if normalize_conf_matrix else 1            # :403-405
@@ -485,9 +513,18 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
                              init_classifier="top", maximize=True, normalize_conf_matrix=True,
                              beta=1.0, epsilon=1e-9, tolerance=1e-6, search_for_best_alpha=True,
                              alpha_tolerance=0.001, alpha_uniform_search_step=0.0001,
-                             skip_tn=False, seed=None):
-    """Returns (a, b, p, meta) with the truncation rules of frank_wolfe.py:644-670."""
+                             skip_tn=False, seed=None, mix=None):
+    """Returns (a, b, p, meta) with the truncation rules of frank_wolfe.py:644-670.
+    mix=(alpha, k, m): objective sum_j [(1 - alpha) tp_j / k + alpha metric_j / m] (:838-915)."""
     mid, c1, b2, eps = metric_params(metric, beta, epsilon)
+
+    def macro_metric_and_grad_mix(metric, tp, fp, fn, tn, beta=1.0, epsilon=1e-9):
+        v, (gtp, gfp, gfn, gtn) = macro_metric_and_grad(metric, tp, fp, fn, tn, beta=beta, epsilon=epsilon)
+        if mix is None:
+            return v, (gtp, gfp, gfn, gtn)
+        al, kk, _ = mix
+        return al * v + (1 - al) * float(np.sum(tp)) / kk, (al * gtp + (1 - al) / kk, al * gfp, al * gfn, al * gtn)
+
     n, m = y_proba.shape
     rng = np.random.default_rng(seed)
     A = np.zeros((max_iters + 1, m), dtype=np.float32)   # :503-505
@@ -508,7 +545,7 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
             y_true, pred, normalize=normalize_conf_matrix, skip_tn=skip_tn)]
 
     def value(c):
-        return macro_metric_and_grad(metric, *c, beta=beta, epsilon=epsilon)[0]
+        return macro_metric_and_grad_mix(metric, *c, beta=beta, epsilon=epsilon)[0]
 
     Cm = conf(A[0], B[0])
     u0 = value(Cm)
@@ -519,7 +556,7 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
     new_u = u0
     for i in range(1, max_iters + 1):
         it = i
-        old_u, (gtp, gfp, gfn, gtn) = macro_metric_and_grad(metric, *Cm, beta=beta, epsilon=epsilon)
+        old_u, (gtp, gfp, gfn, gtn) = macro_metric_and_grad_mix(metric, *Cm, beta=beta, epsilon=epsilon)
         A[i] = gtp - gfp - gfn + gtn     # :595-596 (float32 store)
         B[i] = gfp - gtn
         if not maximize:
@@ -529,10 +566,11 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
         u_i = value(Ci)
         if search_for_best_alpha:
             ba, bv = C.c_double(), C.c_double()
-            lib().orc_fw_alpha_search(
-                C.c_int(mid), *[_p(x) for x in Cm], *[_p(x) for x in Ci], C.c_int64(m),
-                _p(alphas), C.c_int64(alphas.size), C.c_double(c1), C.c_double(b2),
-                C.c_double(eps), C.byref(ba), C.byref(bv))
+            with _Mix(mix):
+                lib().orc_fw_alpha_search(
+                    C.c_int(mid), *[_p(x) for x in Cm], *[_p(x) for x in Ci], C.c_int64(m),
+                    _p(alphas), C.c_int64(alphas.size), C.c_double(c1), C.c_double(b2),
+                    C.c_double(eps), C.byref(ba), C.byref(bv))
             alpha = ba.value
         else:
             alpha = 2 / (i + 1)

@@ -28,7 +28,8 @@ enum {
     ORC_JACCARD = 3,
     ORC_BALANCED_ACC = 4,
     ORC_GMEAN = 5,
-    ORC_HMEAN = 6
+    ORC_HMEAN = 6,
+    ORC_PREC_AT_K = 7 /* tp / k (metrics.py:497-513) */
 };
 
 /* Binary metrics on one label's (tp, fp, fn, tn), float64, operation order of the
@@ -39,10 +40,36 @@ enum {
  *   jaccard   :797   tp / (tp + fp + fn + epsilon)
  *   bal. acc  :843-845, gmean :890-892 ((tpr*tnr)**0.5 == sqrt), hmean :939-941
  * c1 = 1 + beta**2 and beta2 = beta**2 are computed by the python caller.            */
+/* Mixed utilities of block_coordinate.py:848-1045 / frank_wolfe.py:838-915:
+ *     (1 - alpha) * binary_precision_at_k(tp, k) + alpha * binary_metric(...) / m
+ * = ((1 - alpha) * (tp / k)) + ((alpha * metric) / m) in python's evaluation order.  The mix is
+ * process-wide test state (orc_set_mix) so that every restated step picks it up unchanged.   */
+static int g_mix_on = 0;
+static double g_mix_alpha = 1.0, g_mix_k = 1.0, g_mix_m = 1.0;
+void orc_set_mix(int on, double alpha, double k, double m)
+{
+    g_mix_on = on;
+    g_mix_alpha = alpha;
+    g_mix_k = k;
+    g_mix_m = m;
+}
+
+static inline double orc_base_metric(int metric, double tp, double fp, double fn, double tn,
+                                     double c1, double beta2, double eps);
+
 static inline double orc_binary_metric(int metric, double tp, double fp, double fn, double tn,
                                        double c1, double beta2, double eps)
 {
+    double v = orc_base_metric(metric, tp, fp, fn, tn, c1, beta2, eps);
+    if (g_mix_on) v = ((1.0 - g_mix_alpha) * (tp / g_mix_k)) + ((g_mix_alpha * v) / g_mix_m);
+    return v;
+}
+
+static inline double orc_base_metric(int metric, double tp, double fp, double fn, double tn,
+                                     double c1, double beta2, double eps)
+{
     switch (metric) {
+    case ORC_PREC_AT_K: return tp / c1; /* metrics.py:513, c1 carries k */
     case ORC_PRECISION: return tp / ((tp + fp) + eps);
     case ORC_RECALL: return tp / ((tp + fn) + eps);
     case ORC_FBETA: return (c1 * tp) / ((((beta2 * (tp + fp)) + tp) + fn) + eps);

@@ -207,5 +207,54 @@ def main():
     save("fw_dense", **out)
 
 
+def main_mixed():
+    """mixed.npz: instance precision and the mixed instance-precision / macro-metric wrappers
+    (block_coordinate.py:804-1045, frank_wolfe.py:838-915) on the live reference."""
+    _install_shims()
+    from xcolumns import block_coordinate as bc
+    from xcolumns import frank_wolfe as fw
+
+    from xcolumns_b200.synth import csr_probs, dense_probs
+
+    eta = dense_probs(300, 200, seed=1001)
+    ycsr = csr_probs(300, 3000, 40, seed=1004)
+    out = {"eta": eta, "data": ycsr.data, "indices": ycsr.indices, "indptr": ycsr.indptr, "shape": np.array(ycsr.shape)}
+
+    def run(name, fn, y, k, **kw):
+        yp, meta = fn(y, k, return_meta=True, **kw)
+        out[name + "_pred"] = pred_to_idx(yp, k)
+        out[name + "_util"] = np.array(meta["utilities"], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} util={meta['utilities'][-1]:.9f}")
+
+    run("mix_f1", bc.predict_optimizing_mixed_instance_precision_and_macro_f1_score_using_bc, eta, 5, alpha=0.3, seed=0)
+    run("mix_prec", bc.predict_optimizing_mixed_instance_precision_and_macro_precision_using_bc, eta, 3, alpha=0.5, seed=1)
+    run("mix_recall", bc.predict_optimizing_mixed_instance_precision_and_macro_recall_using_bc, eta, 5, alpha=0.8, seed=2)
+    run("mix_jaccard", bc.predict_optimizing_mixed_instance_precision_and_macro_jaccard_score_using_bc, eta, 5, alpha=0.5,
+        seed=3)
+    run("mix_balacc", bc.predict_optimizing_mixed_instance_precision_and_macro_balanced_accuracy_using_bc, eta, 5,
+        alpha=0.5, seed=4)
+    run("mix_f1_eps", bc.predict_optimizing_mixed_instance_precision_and_macro_f1_score_using_bc, eta, 5, alpha=0.6,
+        seed=5, metric_kwargs={"epsilon": 1e-5})
+    run("inst_prec", bc.predict_optimizing_instance_precision_using_bc, eta, 5, seed=6)
+    run("csr_mix_f1", bc.predict_optimizing_mixed_instance_precision_and_macro_f1_score_using_bc, ycsr, 5, alpha=0.4,
+        seed=0)
+
+    eta2 = dense_probs(400, 300, seed=1005)
+    out["eta_fw"] = eta2
+    for name, fn, al in (("fw_mix_f1", fw.find_classifier_optimizing_mixed_instance_precision_and_macro_f1_score_using_fw, 0.5),
+                         ("fw_mix_prec", fw.find_classifier_optimizing_mixed_instance_precision_and_macro_precision_using_fw, 0.7)):
+        clf, meta = fn(eta2, eta2, 5, alpha=al, max_iters=8, skip_tn=True, seed=0, return_meta=True)
+        out[name + "_a"], out[name + "_b"], out[name + "_p"] = clf.a, clf.b, clf.p
+        out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} util={out[name + '_util']}")
+    path = os.path.join(HERE, "mixed.npz")
+    np.savez_compressed(path, **out)
+    print(f"mixed: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "mixed":
+        main_mixed()
+    else:
+        main()

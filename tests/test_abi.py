@@ -46,7 +46,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(decls) >= 30
     for name in decls:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert lib.xc_abi_version() == 1
+    assert lib.xc_abi_version() == 2
     assert lib.xc_strerror(-1) == b"invalid argument"
 
 
@@ -76,8 +76,10 @@ def test_ctypes_prototypes_match_header():
 
 def test_metric_params_layout():
     from xcolumns_b200 import _lib
-    assert C.sizeof(_lib.MetricParams) == 56
-    assert _lib.MetricParams.c1.offset == 16 and _lib.MetricParams.n_div.offset == 40
+    assert C.sizeof(_lib.MetricParams) == 80
+    assert _lib.MetricParams.mix.offset == 12 and _lib.MetricParams.c1.offset == 16
+    assert _lib.MetricParams.n_div.offset == 40 and _lib.MetricParams.mix_alpha.offset == 56
+    assert _lib.MetricParams.mix_m.offset == 72
 
 
 def test_no_gpu_fails_loudly():

@@ -441,3 +441,65 @@ def test_fw_csr(xb, oracle):
     assert meta["iters"] == ometa["iters"]
     assert np.allclose(meta["utilities"], ometa["utilities"], rtol=0, atol=TOL)
     assert meta["utilities"][-1] > meta["utilities"][0]
+
+
+# ---- instance precision and mixed instance-precision / macro-metric utilities ----------------------
+MIXED = [("mix_f1", "f1_score", 5, dict(alpha=0.3, seed=0)), ("mix_prec", "precision", 3, dict(alpha=0.5, seed=1)),
+         ("mix_recall", "recall", 5, dict(alpha=0.8, seed=2)), ("mix_jaccard", "jaccard_score", 5, dict(alpha=0.5, seed=3)),
+         ("mix_balacc", "balanced_accuracy", 5, dict(alpha=0.5, seed=4)),
+         ("mix_f1_eps", "f1_score", 5, dict(alpha=0.6, seed=5, metric_kwargs={"epsilon": 1e-5}))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,metric,k,kw", MIXED, ids=[c[0] for c in MIXED])
+def test_bca_mixed_exact_golden(xb, golden, name, metric, k, kw):
+    """block_coordinate.py:848-1045 through the sequential-exact kernels: bit-equal to the live reference"""
+    g = golden("mixed")
+    fn = getattr(xb, f"predict_optimizing_mixed_instance_precision_and_macro_{metric}_using_bc")
+    pred, meta = fn(g["eta"], k, return_meta=True, mode="exact", **kw)
+    assert (_idx(pred, k) == g[name + "_pred"]).all()
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+@pytest.mark.gpu
+def test_bca_instance_precision_and_csr_mixed_golden(xb, golden):
+    g = golden("mixed")
+    pred, meta = xb.predict_optimizing_instance_precision_using_bc(g["eta"], 5, seed=6, return_meta=True, mode="exact")
+    assert (_idx(pred, 5) == g["inst_prec_pred"]).all()
+    assert (np.array(meta["utilities"]) == g["inst_prec_util"]).all()
+    y = csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    pred, meta = xb.predict_optimizing_mixed_instance_precision_and_macro_f1_score_using_bc(
+        y, 5, alpha=0.4, seed=0, return_meta=True, mode="exact")
+    assert (pred.indices.reshape(-1, 5) == g["csr_mix_f1_pred"]).all()
+    assert (np.array(meta["utilities"]) == g["csr_mix_f1_util"]).all()
+
+
+@pytest.mark.gpu
+def test_bca_mixed_batched_vs_oracle(xb, oracle):
+    """batched mode: the mixed gain stays affine in eta; final utility within 1e-4 of the sequential oracle"""
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(6000, 1500, seed=31)
+    n, m = eta.shape
+    for alpha in (0.3, 0.9):
+        pred, meta = xb.predict_optimizing_mixed_instance_precision_and_macro_f1_score_using_bc(
+            eta, 5, alpha=alpha, seed=0, return_meta=True, mode="batched")
+        _, ometa = oracle.predict_using_bc_with_0approx(eta, "f1", 5, metric_aggregation="sum", skip_tn=True, seed=0,
+                                                        mix=(alpha, 5, m))
+        assert meta["mode"] == "batched" and (pred.sum(1) == 5).all()
+        assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < 1e-4, (alpha, meta["utilities"], ometa["utilities"])
+    pred, meta = xb.predict_optimizing_instance_precision_using_bc(eta, 5, seed=0, return_meta=True, mode="batched")
+    top = xb.predict_top_k(eta, 5)
+    assert (pred == top).all()          # instance precision is maximised by the plain top-k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,metric,alpha", [("fw_mix_f1", "f1_score", 0.5), ("fw_mix_prec", "precision", 0.7)])
+def test_fw_mixed_golden(xb, golden, name, metric, alpha):
+    from xcolumns_b200 import frank_wolfe as fwm
+    g = golden("mixed")
+    eta = g["eta_fw"]
+    fn = getattr(fwm, f"find_classifier_optimizing_mixed_instance_precision_and_macro_{metric}_using_fw")
+    clf, meta = fn(eta, eta, 5, alpha=alpha, max_iters=8, skip_tn=True, seed=0, return_meta=True)
+    assert len(meta["utilities"]) == len(g[name + "_util"])
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+    assert clf.a.shape == g[name + "_a"].shape and np.allclose(clf.p, g[name + "_p"], atol=2e-3)

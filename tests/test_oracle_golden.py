@@ -140,3 +140,45 @@ def test_fw_dense(golden, oracle, name, metric, yt, kw):
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
     assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=2e-3)
     assert np.allclose(P, g[name + "_p"], rtol=0, atol=2e-3)
+
+
+MIXED = [("mix_f1", "f1", 5, 0.3, dict(seed=0)), ("mix_prec", "precision", 3, 0.5, dict(seed=1)),
+         ("mix_recall", "recall", 5, 0.8, dict(seed=2)), ("mix_jaccard", "jaccard", 5, 0.5, dict(seed=3)),
+         ("mix_balacc", "balanced_accuracy", 5, 0.5, dict(seed=4)),
+         ("mix_f1_eps", "f1", 5, 0.6, dict(seed=5, epsilon=1e-5))]
+
+
+@pytest.mark.parametrize("name,metric,k,alpha,kw", MIXED, ids=[c[0] for c in MIXED])
+def test_bca_mixed_dense(golden, oracle, name, metric, k, alpha, kw):
+    """mixed instance-precision / macro-metric utilities (block_coordinate.py:848-1045), bit-exact"""
+    g = golden("mixed")
+    eta = g["eta"]
+    pred, meta = oracle.predict_using_bc_with_0approx(eta, metric, k, metric_aggregation="sum", skip_tn=True,
+                                                      mix=(alpha, k, eta.shape[1]), **kw)
+    assert (_idx(pred, k) == g[name + "_pred"]).all()
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+def test_bca_instance_precision_and_csr_mixed(golden, oracle):
+    g = golden("mixed")
+    eta = g["eta"]
+    pred, meta = oracle.predict_using_bc_with_0approx(eta, "precision_at_k", 5, metric_aggregation="sum", beta=5,
+                                                      init_y_pred="random", seed=6)
+    assert (_idx(pred, 5) == g["inst_prec_pred"]).all()
+    assert (np.array(meta["utilities"]) == g["inst_prec_util"]).all()
+    y = csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    pred, meta = oracle.predict_using_bc_with_0approx(y, "f1", 5, metric_aggregation="sum", skip_tn=True, seed=0,
+                                                      mix=(0.4, 5, y.shape[1]))
+    assert (pred == g["csr_mix_f1_pred"]).all()
+    assert (np.array(meta["utilities"]) == g["csr_mix_f1_util"]).all()
+
+
+@pytest.mark.parametrize("name,metric,alpha", [("fw_mix_f1", "f1", 0.5), ("fw_mix_prec", "precision", 0.7)])
+def test_fw_mixed(golden, oracle, name, metric, alpha):
+    g = golden("mixed")
+    eta = g["eta_fw"]
+    a, b, p, meta = oracle.find_classifier_using_fw(eta, eta, metric, 5, max_iters=8, skip_tn=True, seed=0,
+                                                    mix=(alpha, 5, eta.shape[1]))
+    assert len(meta["utilities"]) == len(g[name + "_util"])
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+    assert a.shape == g[name + "_a"].shape

@@ -10,6 +10,14 @@ All heavy work runs in hand-written sm_100a CUDA kernels behind a C ABI
 """
 from .block_coordinate import (  # noqa: F401
     predict_optimizing_coverage_using_bc,
+    predict_optimizing_instance_precision_using_bc,
+    predict_optimizing_mixed_instance_precision_and_macro_balanced_accuracy_using_bc,
+    predict_optimizing_mixed_instance_precision_and_macro_f1_score_using_bc,
+    predict_optimizing_mixed_instance_precision_and_macro_gmean_using_bc,
+    predict_optimizing_mixed_instance_precision_and_macro_hmean_using_bc,
+    predict_optimizing_mixed_instance_precision_and_macro_jaccard_score_using_bc,
+    predict_optimizing_mixed_instance_precision_and_macro_precision_using_bc,
+    predict_optimizing_mixed_instance_precision_and_macro_recall_using_bc,
     predict_optimizing_macro_balanced_accuracy_using_bc,
     predict_optimizing_macro_f1_score_using_bc,
     predict_optimizing_macro_gmean_using_bc,
@@ -25,6 +33,9 @@ from .frank_wolfe import (  # noqa: F401
     find_classifier_optimizing_macro_f1_score_using_fw,
     find_classifier_optimizing_macro_precision_using_fw,
     find_classifier_optimizing_macro_recall_using_fw,
+    find_classifier_optimizing_mixed_instance_precision_and_macro_f1_score_using_fw,
+    find_classifier_optimizing_mixed_instance_precision_and_macro_precision_using_fw,
+    find_classifier_optimizing_mixed_instance_precision_and_macro_recall_using_fw,
     find_classifier_using_fw,
     predict_using_randomized_weighted_classifier,
 )

@@ -23,8 +23,9 @@ class XColumnsB200Error(RuntimeError):
 class MetricParams(C.Structure):
     """Mirror of xc_metric_params."""
     _fields_ = [("metric", C.c_int32), ("maximize", C.c_int32), ("skip_tn", C.c_int32),
-                ("reserved", C.c_int32), ("c1", C.c_double), ("beta2", C.c_double),
-                ("eps", C.c_double), ("n_div", C.c_double), ("n_rows", C.c_double)]
+                ("mix", C.c_int32), ("c1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("n_div", C.c_double), ("n_rows", C.c_double),
+                ("mix_alpha", C.c_double), ("mix_k", C.c_double), ("mix_m", C.c_double)]
 
 
 _vp, _i32, _i64, _dbl, _int = C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int

@@ -37,10 +37,13 @@ from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
 _AUTO_EXACT_MAX_ROWS = 4096
 
 
-def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n_rows=None) -> MetricParams:
+def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n_rows=None, mix=None) -> MetricParams:
     n_rows = n_div if n_rows is None else n_rows
-    return MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)), reserved=0,
-                        c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=float(n_div), n_rows=float(n_rows))
+    c1, beta2 = M.metric_c1_beta2(metric_id, beta)
+    alpha, mk, mm = mix if mix is not None else (1.0, 1.0, 1.0)
+    return MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)),
+                        mix=int(mix is not None), c1=c1, beta2=beta2, eps=float(eps), n_div=float(n_div),
+                        n_rows=float(n_rows), mix_alpha=alpha, mix_k=mk, mix_m=mm)
 
 
 def _resolve_mode(mode: Optional[str], n: int, needs_exact: bool) -> str:
@@ -317,6 +320,7 @@ def predict_using_bc_with_0approx(
     if k == 0 and isinstance(y_proba, csr_matrix):
         raise NotImplementedError("xcolumns_b200: BCA without a budget (k=0) is implemented for dense inputs only")
     metric_id, beta, eps = M.resolve_binary_metric(binary_metric_func, metric_kwargs)
+    mix = M.resolve_mix(binary_metric_func)
     if metric_id in M.TN_METRICS and skip_tn:
         log_warning("skip_tn=True with a metric that uses true negatives: tn is the constant -1 like in the reference")
 
@@ -324,7 +328,8 @@ def predict_using_bc_with_0approx(
     if k > m:
         raise ValueError(f"k={k} is larger than the number of labels m={m}")
     greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
-    mode = _resolve_mode(mode, n, greedy or k == 0 or metric_id not in M.AFFINE_GAIN_METRICS)
+    mode = _resolve_mode(mode, n, greedy or k == 0 or metric_id not in M.AFFINE_GAIN_METRICS or (
+        metric_id in M.TN_METRICS and skip_tn))
 
     device = dev.pick_device(y_proba)
     comm = make_comm(distributed, device)
@@ -340,8 +345,10 @@ def predict_using_bc_with_0approx(
     n_div = n if normalize_conf_matrix else 1            # block_coordinate.py:403-405
     n_div_global = comm.n_global(n) if normalize_conf_matrix else 1
     n_order = n if normalize_conf_matrix else 1          # order = arange(n) after the overwrite (:414)
-    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div_global, comm.n_global(n))
-    util_params = _metric_params(metric_id, 1.0, 1e-9, maximize, skip_tn, n_div_global, comm.n_global(n))  # no kwargs (:63)
+    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div_global, comm.n_global(n), mix)
+    # the utility / stopping test ignores metric_kwargs (:63); precision@k keeps its k (it is bound, not a kwarg)
+    util_beta = beta if metric_id == M.XC_METRIC_PREC_AT_K else 1.0
+    util_params = _metric_params(metric_id, util_beta, 1e-9, maximize, skip_tn, n_div_global, comm.n_global(n), mix)
 
     timing = os.environ.get("XCOLUMNS_B200_TIMING") == "1"
 
@@ -462,7 +469,7 @@ def _bca_k0_dense(y_proba, binary_metric_func, metric_id, beta, eps, aggregation
     n, m = data.n, data.m
     n_div = n if normalize_conf_matrix else 1
     n_order = n if normalize_conf_matrix else 1
-    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n)
+    params = _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n, M.resolve_mix(binary_metric_func))
     tdt = data.torch_dtype
     if isinstance(init_y_pred, str) and init_y_pred == "top":
         pred = (data.t[:, :m] >= 0).to(tdt)                       # predict_top_k(k=0): gains >= th = 0
@@ -693,3 +700,54 @@ predict_optimizing_macro_balanced_accuracy_using_bc = make_bc_wrapper(
     M.binary_balanced_accuracy_on_conf_matrix, "macro-averaged balanced accuracy")
 predict_optimizing_macro_hmean_using_bc = make_bc_wrapper(M.binary_hmean_on_conf_matrix, "macro-averaged H-mean")
 predict_optimizing_macro_gmean_using_bc = make_bc_wrapper(M.binary_gmean_on_conf_matrix, "macro-averaged G-mean")
+
+
+# ------------------------------------------------------------------------------------------
+# instance precision and the mixed instance-precision / macro-metric utilities
+# (block_coordinate.py:804-1045)
+# ------------------------------------------------------------------------------------------
+
+def predict_optimizing_instance_precision_using_bc(y_proba: Matrix, k: int, tolerance: float = 1e-6,
+                                                   init_y_pred: Union[str, Matrix] = "random", max_iters: int = 100,
+                                                   shuffle_order: bool = True, verbose: bool = False,
+                                                   return_meta: bool = False, **kwargs):
+    """BCA with instance precision@k (sum over labels of tp / k) as the target
+    (xcolumns/block_coordinate.py:804-838; same defaults, note init_y_pred="random")."""
+    return predict_using_bc_with_0approx(y_proba, binary_metric_func=M.PrecisionAtK(k), k=k, metric_aggregation="sum",
+                                         tolerance=tolerance, init_y_pred=init_y_pred, max_iters=max_iters,
+                                         shuffle_order=shuffle_order, verbose=verbose, return_meta=return_meta,
+                                         **kwargs)
+
+
+def make_mixed_bc_wrapper(binary_metric_func: Callable, metric_name: str):
+    """``predict_optimizing_mixed_instance_precision_and_<metric>_using_bc(y_proba, k, alpha=1, **kwargs)``:
+    BCA on  sum_j [(1 - alpha) * tp_j / k + alpha * metric_j / m]  (xcolumns/block_coordinate.py:848-1045;
+    like there: aggregation "sum", skip_tn=True -- for the tn-based metrics that reproduces the reference's
+    constant tn = -1, which only the sequential mode evaluates)."""
+
+    def predict_optimizing_mixed_metric_using_bc(y_proba: Matrix, k: int, alpha: float = 1, **kwargs):
+        n, m = y_proba.shape
+        return predict_using_bc_with_0approx(
+            y_proba, binary_metric_func=M.MixedInstancePrecisionMetric(binary_metric_func, alpha, k, m), k=k,
+            metric_aggregation="sum", skip_tn=True, **kwargs)
+
+    predict_optimizing_mixed_metric_using_bc.__doc__ = (
+        f"BCA with a weighted average of instance precision@k and {metric_name} as the target; "
+        f"see predict_using_bc_with_0approx.")
+    return predict_optimizing_mixed_metric_using_bc
+
+
+predict_optimizing_mixed_instance_precision_and_macro_precision_using_bc = make_mixed_bc_wrapper(
+    M.binary_precision_on_conf_matrix, "macro-averaged precision")
+predict_optimizing_mixed_instance_precision_and_macro_recall_using_bc = make_mixed_bc_wrapper(
+    M.binary_recall_on_conf_matrix, "macro-averaged recall")
+predict_optimizing_mixed_instance_precision_and_macro_f1_score_using_bc = make_mixed_bc_wrapper(
+    M.binary_f1_score_on_conf_matrix, "macro-averaged F1 score")
+predict_optimizing_mixed_instance_precision_and_macro_balanced_accuracy_using_bc = make_mixed_bc_wrapper(
+    M.binary_balanced_accuracy_on_conf_matrix, "macro-averaged balanced accuracy")
+predict_optimizing_mixed_instance_precision_and_macro_jaccard_score_using_bc = make_mixed_bc_wrapper(
+    M.binary_jaccard_score_on_conf_matrix, "macro-averaged Jaccard score")
+predict_optimizing_mixed_instance_precision_and_macro_gmean_using_bc = make_mixed_bc_wrapper(
+    M.binary_gmean_on_conf_matrix, "macro-averaged G-mean")
+predict_optimizing_mixed_instance_precision_and_macro_hmean_using_bc = make_mixed_bc_wrapper(
+    M.binary_hmean_on_conf_matrix, "macro-averaged H-mean")

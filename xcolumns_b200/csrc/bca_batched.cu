@@ -35,26 +35,39 @@ bca_coef_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *
     }
     const double sgn = p.maximize ? 1.0 : -1.0;
     const double E = p.eps * p.n_div;
+    double Bn, An, Bs, As;  // gain = A + B * eta for an unselected (n) / currently selected (s) label
     if (p.metric == XC_METRIC_BALANCED_ACC) {
         // tp + fn = sum_i eta_ij and tn + fp = sum_i (1 - eta_ij) do not depend on the prediction, so
         // gain = [eta / (S + E) - (1 - eta) / (NS + E)] / 2 for selected and unselected labels alike
         const double S = t + g;
         const double NS = p.n_rows - S;
-        const double B = 0.5 * (1.0 / (S + E) + 1.0 / (NS + E)), A = -0.5 / (NS + E);
-        coef_n[j] = make_float2((float)(sgn * B), (float)(sgn * A));
-        coef_s[j] = coef_n[j];
-        return;
+        Bn = Bs = 0.5 * (1.0 / (S + E) + 1.0 / (NS + E));
+        An = As = -0.5 / (NS + E);
+    } else if (p.metric == XC_METRIC_PREC_AT_K) {
+        // tp / k on the normalised counts (metrics.py:513): every label gains eta / (k n)
+        Bn = Bs = 1.0 / (p.c1 * p.n_div);
+        An = As = 0.0;
+    } else {
+        double c, u, v;
+        if (p.metric == XC_METRIC_PRECISION) { c = 1.0; u = 1.0; v = 0.0; }
+        else if (p.metric == XC_METRIC_RECALL) { c = 1.0; u = 0.0; v = 1.0; }
+        else { c = p.c1; u = p.beta2; v = 1.0; }
+        const double D = u * (t + f) + v * (t + g) + E;
+        const double ct = c * t;
+        // unselected: predict j for this row -> D grows by u
+        Bn = c / (D + u);
+        An = ct / (D + u) - ct / D;
+        // selected: un-predicting j -> D shrinks by u
+        Bs = c / (D - u);
+        As = ct / D - ct / (D - u);
     }
-    double c, u, v;
-    if (p.metric == XC_METRIC_PRECISION) { c = 1.0; u = 1.0; v = 0.0; }
-    else if (p.metric == XC_METRIC_RECALL) { c = 1.0; u = 0.0; v = 1.0; }
-    else { c = p.c1; u = p.beta2; v = 1.0; }
-    const double D = u * (t + f) + v * (t + g) + E;
-    const double ct = c * t;
-    // unselected: predict j for this row -> D grows by u
-    double Bn = c / (D + u), An = ct / (D + u) - ct / D;
-    // selected: un-predicting j -> D shrinks by u
-    double Bs = c / (D - u), As = ct / D - ct / (D - u);
+    if (p.mix) {
+        // (1 - alpha) * tp / k + alpha * metric / m, summed over the labels (block_coordinate.py:848-1045):
+        // the instance-precision part adds (1 - alpha) eta / (k n) to every gain
+        const double w1 = (1.0 - p.mix_alpha) / (p.mix_k * p.n_div), w2 = p.mix_alpha / p.mix_m;
+        Bn = w1 + w2 * Bn; An = w2 * An;
+        Bs = w1 + w2 * Bs; As = w2 * As;
+    }
     coef_n[j] = make_float2((float)(sgn * Bn), (float)(sgn * An));
     coef_s[j] = make_float2((float)(sgn * Bs), (float)(sgn * As));
 }
@@ -717,7 +730,7 @@ extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, d
     if (!ctx || !p || !tp || !fp || !fn || !coef_n || !coef_s || m <= 0) return XC_ERR_INVALID;
     if ((dtp || dfp || dfn) && !(dtp && dfp && dfn)) return XC_ERR_INVALID;
     if (p->metric != XC_METRIC_PRECISION && p->metric != XC_METRIC_RECALL && p->metric != XC_METRIC_FBETA &&
-        p->metric != XC_METRIC_BALANCED_ACC)
+        p->metric != XC_METRIC_BALANCED_ACC && p->metric != XC_METRIC_PREC_AT_K)
         return XC_ERR_UNSUPPORTED;  // gain not affine in eta
     bca_coef_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         *p, tp, fp, fn, dtp, dfp, dfn, m, (float2 *)coef_n, (float2 *)coef_s);

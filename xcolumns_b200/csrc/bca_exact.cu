@@ -159,10 +159,8 @@ bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
                 const double pos_fp = sfp[l] + (double)om;
                 const double neg_fn = sfn[l] + (double)pe;
                 const double neg_tn = use_tn ? stn[l] + (double)om : stn[l];
-                const double up = xc_binary_metric(p.metric, pos_tp / nd, pos_fp / nd, sfn[l] / nd, stn[l] / nd,
-                                                   p.c1, p.beta2, p.eps);
-                const double un = xc_binary_metric(p.metric, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn / nd,
-                                                   p.c1, p.beta2, p.eps);
+                const double up = xc_metric_eval(p, pos_tp / nd, pos_fp / nd, sfn[l] / nd, stn[l] / nd);
+                const double un = xc_metric_eval(p, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn / nd);
                 const double g = up - un;         //                                :129
                 gain[l] = p.maximize ? g : -g;
             }
@@ -367,10 +365,8 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
                 const double pos_fp = sfp[l] + (double)om;
                 const double neg_fn = sfn[l] + (double)pe;
                 const double neg_tn = use_tn ? stn[l] + (double)om : stn[l];
-                const double up = xc_binary_metric(p.metric, pos_tp / nd, pos_fp / nd, sfn[l] / nd, stn[l] / nd,
-                                                   p.c1, p.beta2, p.eps);
-                const double un = xc_binary_metric(p.metric, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn / nd,
-                                                   p.c1, p.beta2, p.eps);
+                const double up = xc_metric_eval(p, pos_tp / nd, pos_fp / nd, sfn[l] / nd, stn[l] / nd);
+                const double un = xc_metric_eval(p, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn / nd);
                 const double g = up - un;
                 gain[l] = p.maximize ? g : -g;
             }
@@ -510,8 +506,8 @@ bca_exact_dense_k0_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, con
         }
         const double pos_tp = stp + (double)pe, pos_fp = sfp + (double)om, neg_fn = sfn + (double)pe;
         const double neg_tn = use_tn ? stn + (double)om : stn;
-        const double up = xc_binary_metric(p.metric, pos_tp / nd, pos_fp / nd, sfn / nd, stn / nd, p.c1, p.beta2, p.eps);
-        const double un = xc_binary_metric(p.metric, stp / nd, sfp / nd, neg_fn / nd, neg_tn / nd, p.c1, p.beta2, p.eps);
+        const double up = xc_metric_eval(p, pos_tp / nd, pos_fp / nd, sfn / nd, stn / nd);
+        const double un = xc_metric_eval(p, stp / nd, sfp / nd, neg_fn / nd, neg_tn / nd);
         double g = up - un;
         if (p.maximize) g = -g;           // :187-188
         y = (g <= 0.0) ? one : (TE)0;     // :191, :200
@@ -622,8 +618,8 @@ bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
                     neg_tnn = (pos_tn + (double)om) / nd;
                     pos_tn = pos_tn / nd;
                 }
-                const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, pos_tn, p.c1, p.beta2, p.eps);
-                const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, neg_tnn, p.c1, p.beta2, p.eps);
+                const double up = xc_metric_eval(p, pos_tpp, pos_fpp, pos_fn, pos_tn);
+                const double un = xc_metric_eval(p, neg_tp, neg_fp, neg_fnn, neg_tnn);
                 const double gg = up - un;
                 g[0] = p.maximize ? gg : -gg;
             }
@@ -741,8 +737,8 @@ bca_exact_csr_fast_kernel(const T *__restrict__ data, const int32_t *__restrict_
                     neg_tp = neg_tp / nd; neg_fp = neg_fp / nd; pos_fn = pos_fn / nd;
                     double pos_tn = -1.0, neg_tnn = -1.0;
                     if (tn) { pos_tn = tn[j]; neg_tnn = (pos_tn + (double)om) / nd; pos_tn = pos_tn / nd; }
-                    const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, pos_tn, p.c1, p.beta2, p.eps);
-                    const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, neg_tnn, p.c1, p.beta2, p.eps);
+                    const double up = xc_metric_eval(p, pos_tpp, pos_fpp, pos_fn, pos_tn);
+                    const double un = xc_metric_eval(p, neg_tp, neg_fp, neg_fnn, neg_tnn);
                     const double gg = up - un;
                     g[0] = p.maximize ? gg : -gg;
                 }
@@ -833,8 +829,8 @@ bca_exact_csr_fast_kernel(const T *__restrict__ data, const int32_t *__restrict_
                     neg_tp = neg_tp / nd; neg_fp = neg_fp / nd; pos_fn = pos_fn / nd;
                     double pos_tn = -1.0, neg_tnn = -1.0;
                     if (tn) { pos_tn = stn[t]; neg_tnn = (pos_tn + (double)om) / nd; pos_tn = pos_tn / nd; }
-                    const double up = xc_binary_metric(p.metric, pos_tpp, pos_fpp, pos_fn, pos_tn, p.c1, p.beta2, p.eps);
-                    const double un = xc_binary_metric(p.metric, neg_tp, neg_fp, neg_fnn, neg_tnn, p.c1, p.beta2, p.eps);
+                    const double up = xc_metric_eval(p, pos_tpp, pos_fpp, pos_fn, pos_tn);
+                    const double un = xc_metric_eval(p, neg_tp, neg_fp, neg_fnn, neg_tnn);
                     const double gg = up - un;
                     g[0] = p.maximize ? gg : -gg;
                 }
@@ -1111,7 +1107,7 @@ extern "C" int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype,
 {
     if (!ctx || !eta || !order || !p || !pred_idx || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || ld < m || n_order < 0 || k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
-    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
     if (n_order == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     static int grid_only = -1;   // $XCOLUMNS_B200_EXACT_PATH=grid forces the cooperative-grid kernel
@@ -1139,7 +1135,7 @@ extern "C" int xc_bca_exact_sweep_dense_k0(xc_ctx *ctx, const void *eta, int dty
 {
     if (!ctx || !eta || !order || !p || !pred || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || ld < m || ld_pred < m || n_order < 0) return XC_ERR_INVALID;
-    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
     if (n_order == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned grid = (unsigned)((m + 127) / 128);
@@ -1160,7 +1156,7 @@ extern "C" int xc_bca_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, 
 {
     if (!ctx || !indptr || !order || !p || !pred_idx || !tp || !fp || !fn) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || n_order < 0 || k < 1 || k > 32) return XC_ERR_INVALID;
-    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
     if (!p->skip_tn && !tn) return XC_ERR_INVALID;
     if (n_order == 0) return XC_OK;
     double *tn_arg = p->skip_tn ? nullptr : tn;

@@ -421,8 +421,7 @@ utility_kernel(xc_metric_params p, int agg, const double *tp, const double *fp, 
     double s = 0.0;
     for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += (int64_t)gridDim.x * 256) {
         double t4 = tn ? tn[j] : -1.0;
-        s += xc_binary_metric(p.metric, tp[j] / p.n_div, fp[j] / p.n_div, fn[j] / p.n_div, t4 / p.n_div, p.c1,
-                              p.beta2, p.eps);
+        s += xc_metric_eval(p, tp[j] / p.n_div, fp[j] / p.n_div, fn[j] / p.n_div, t4 / p.n_div);
     }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -614,7 +613,7 @@ extern "C" int xc_utility(xc_ctx *ctx, const xc_metric_params *p, int agg, const
                           const double *fn, const double *tn, int64_t m, double *out_dev, void *stream)
 {
     if (!ctx || !p || !tp || !fp || !fn || !out_dev || m <= 0) return XC_ERR_INVALID;
-    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
     int64_t blocks = (m + 255) / 256;
     int grid = (int)(blocks < XC_RED_MAX_BLOCKS ? blocks : XC_RED_MAX_BLOCKS);
     if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;

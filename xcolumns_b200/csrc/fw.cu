@@ -173,6 +173,22 @@ __device__ __forceinline__ Grad4 metric_grad(int metric, double tp, double fp, d
     return r;
 }
 
+// metric_grad of the call's objective, scaled so that value = (1/m) sum_j v_j and grad = (1/m) g_j also
+// hold for the mixed objectives sum_j [(1 - alpha) tp_j / k + alpha metric_j / m] (frank_wolfe.py:838-915)
+__device__ __forceinline__ Grad4 metric_grad_p(const xc_metric_params &p, double tp, double fp, double fn, double tn)
+{
+    Grad4 g = metric_grad(p.metric, tp, fp, fn, tn, p.c1, p.beta2, p.eps);
+    if (p.mix) {
+        const double w = (1.0 - p.mix_alpha) * (p.mix_m / p.mix_k);
+        g.v = p.mix_alpha * g.v + w * tp;
+        g.gtp = p.mix_alpha * g.gtp + w;
+        g.gfp = p.mix_alpha * g.gfp;
+        g.gfn = p.mix_alpha * g.gfn;
+        g.gtn = p.mix_alpha * g.gtn;
+    }
+    return g;
+}
+
 __global__ void __launch_bounds__(256)
 fw_metric_grad_kernel(xc_metric_params p, const double *tp, const double *fp, const double *fn, const double *tn,
                       int64_t m, float *a_out, float *b_out, double *value, double *partials, unsigned *counter)
@@ -182,7 +198,7 @@ fw_metric_grad_kernel(xc_metric_params p, const double *tp, const double *fp, co
     const double sgn = p.maximize ? 1.0 : -1.0;
     const double inv_m = 1.0 / (double)m;
     for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += (int64_t)gridDim.x * 256) {
-        Grad4 g = metric_grad(p.metric, tp[j], fp[j], fn[j], tn ? tn[j] : -1.0, p.c1, p.beta2, p.eps);
+        Grad4 g = metric_grad_p(p, tp[j], fp[j], fn[j], tn ? tn[j] : -1.0);
         s += g.v;
         if (a_out) {
             double gtp = g.gtp * inv_m, gfp = g.gfp * inv_m, gfn = g.gfn * inv_m, gtn = g.gtn * inv_m;
@@ -571,7 +587,7 @@ fw_alpha_eval_kernel(xc_metric_params p, const double *__restrict__ C, const dou
     const int64_t count = ctl == nullptr ? n_alphas + 1 : ctl->count;
     const int slices = ctl == nullptr ? 1 : ctl->slices;
     const int64_t tiles = (count + AT64 - 1) / AT64;
-    const bool use_tn = p.metric >= XC_METRIC_BALANCED_ACC;
+    const bool use_tn = p.metric >= XC_METRIC_BALANCED_ACC && p.metric <= XC_METRIC_HMEAN;
     const int64_t per_slice = (m + slices - 1) / slices;
     for (int64_t item = blockIdx.x; item < tiles * slices; item += gridDim.x) {
         const int64_t tile = item / slices;
@@ -592,8 +608,8 @@ fw_alpha_eval_kernel(xc_metric_params p, const double *__restrict__ C, const dou
 #pragma unroll
             for (int t = 0; t < AT64; ++t) {
                 const double a1 = al[t], a0 = 1.0 - a1;
-                acc[t] += xc_binary_metric(p.metric, a0 * tp + a1 * tpi, a0 * fp + a1 * fpi, a0 * fn + a1 * fni,
-                                           a0 * tn + a1 * tni, p.c1, p.beta2, p.eps);
+                acc[t] += xc_metric_eval(p, a0 * tp + a1 * tpi, a0 * fp + a1 * fpi, a0 * fn + a1 * fni,
+                                           a0 * tn + a1 * tni);
             }
         }
 #pragma unroll
@@ -691,7 +707,7 @@ fw_conf_prep_kernel(xc_metric_params p, const double *__restrict__ tp_raw, const
         out[m + j] = f;
         out[2 * m + j] = g;
         out[3 * m + j] = tn;
-        s += metric_grad(p.metric, t, f, g, tn, p.c1, p.beta2, p.eps).v;
+        s += metric_grad_p(p, t, f, g, tn).v;
         if (lin) lin[j] = alpha_lin(p, Cm[j], Cm[m + j], Cm[2 * m + j], t, f, g, linE + j);
     }
     if (lin && (m & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -731,7 +747,7 @@ fw_finish_kernel(xc_metric_params p, double *__restrict__ C, const double *__res
                 C[t * m + j] = c[t];
             }
         }
-        Grad4 g = metric_grad(p.metric, c[0], c[1], c[2], c[3], p.c1, p.beta2, p.eps);
+        Grad4 g = metric_grad_p(p, c[0], c[1], c[2], c[3]);
         s += g.v;
         if (a_next) {
             double gtp = g.gtp * inv_m, gfp = g.gfp * inv_m, gfn = g.gfn * inv_m, gtn = g.gtn * inv_m;
@@ -963,7 +979,7 @@ bool alpha_two_stage(const xc_metric_params *p, int64_t n_alphas)
         const char *e = getenv("XCOLUMNS_B200_FW_SEARCH");
         force_full = (e && e[0] == 'f') ? 1 : 0;
     }
-    return !force_full && p->metric <= XC_METRIC_JACCARD && n_alphas >= 256;
+    return !force_full && !p->mix && p->metric <= XC_METRIC_JACCARD && n_alphas >= 256;
 }
 
 bool alpha_refine()

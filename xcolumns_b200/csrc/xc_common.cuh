@@ -195,6 +195,7 @@ __device__ __forceinline__ double xc_binary_metric(int metric, double tp, double
     case XC_METRIC_RECALL: return tp / ((tp + fn) + eps);
     case XC_METRIC_FBETA: return (c1 * tp) / ((((beta2 * (tp + fp)) + tp) + fn) + eps);
     case XC_METRIC_JACCARD: return tp / (((tp + fp) + fn) + eps);
+    case XC_METRIC_PREC_AT_K: return tp / c1;
     default: {
         double tpr = tp / ((tp + fn) + eps);
         double tnr = tn / ((tn + fp) + eps);
@@ -203,4 +204,13 @@ __device__ __forceinline__ double xc_binary_metric(int metric, double tp, double
         return ((2.0 * tpr) * tnr) / (tpr + tnr);
     }
     }
+}
+
+// the binary metric of the call, including the mixed utilities
+//   (1 - alpha) * binary_precision_at_k(tp, k) + alpha * metric / m     (python evaluation order)
+__device__ __forceinline__ double xc_metric_eval(const xc_metric_params &p, double tp, double fp, double fn, double tn)
+{
+    double v = xc_binary_metric(p.metric, tp, fp, fn, tn, p.c1, p.beta2, p.eps);
+    if (p.mix) v = ((1.0 - p.mix_alpha) * (tp / p.mix_k)) + ((p.mix_alpha * v) / p.mix_m);
+    return v;
 }

@@ -181,8 +181,11 @@ def find_classifier_using_fw(
         ctx.call("xc_colsum_dense", dev.ptr(td_.t), td_.code, n, m, td_.ld, dev.ptr(colsum), sp())
     comm.allreduce_sum_(colsum)
 
-    params = MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)), reserved=0,
-                          c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps), n_div=1.0, n_rows=float(n_global))
+    mix = M.resolve_mix(metric_func)
+    mix_alpha, mix_k, mix_m = mix if mix is not None else (1.0, 1.0, 1.0)
+    params = MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)),
+                          mix=int(mix is not None), c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps),
+                          n_div=1.0, n_rows=float(n_global), mix_alpha=mix_alpha, mix_k=mix_k, mix_m=mix_m)
     Cm = torch.empty(4 * m, **f64)       # running confusion vectors [tp, fp, fn, tn]
     Ci = torch.empty(4 * m, **f64)       # confusion vectors of the newest classifier
     raw = torch.empty((2, m), **f64)     # tp_raw, cnt of one iterate
@@ -368,3 +371,33 @@ find_classifier_optimizing_macro_balanced_accuracy_using_fw = make_frank_wolfe_w
     M.macro_balanced_accuracy_on_conf_matrix, "macro-averaged balanced accuracy")
 find_classifier_optimizing_macro_hmean_using_fw = make_frank_wolfe_wrapper(M.macro_hmean_on_conf_matrix, "macro-averaged H-mean")
 find_classifier_optimizing_macro_gmean_using_fw = make_frank_wolfe_wrapper(M.macro_gmean_on_conf_matrix, "macro-averaged G-mean")
+
+
+# ------------------------------------------------------------------------------------------
+# mixed instance-precision / macro-metric objectives (frank_wolfe.py:838-915)
+# ------------------------------------------------------------------------------------------
+
+def make_mixed_frank_wolfe_wrapper(binary_metric_func: Callable, metric_name: str):
+    """``find_classifier_optimizing_mixed_instance_precision_and_<metric>_using_fw(y_true, y_proba, k,
+    alpha=1, **kwargs)``: Frank-Wolfe on  sum_j [(1 - alpha) * tp_j / k + alpha * metric_j / m].  The line
+    search of these objectives runs the exhaustive float64 grid (the two-stage screen covers the pure
+    c*tp/D metrics only)."""
+
+    def find_classifier_optimizing_mixed_metric_using_fw(y_true: Matrix, y_proba: Matrix, k: int, alpha: float = 1,
+                                                         **kwargs):
+        n, m = y_true.shape
+        return find_classifier_using_fw(y_true, y_proba, M.MixedInstancePrecisionMacroMetric(binary_metric_func, alpha, k, m),
+                                        k, **kwargs)
+
+    find_classifier_optimizing_mixed_metric_using_fw.__doc__ = (
+        f"Find a randomized classifier maximizing a weighted average of instance precision@k and {metric_name} "
+        f"with the Frank-Wolfe algorithm; see find_classifier_using_fw.")
+    return find_classifier_optimizing_mixed_metric_using_fw
+
+
+find_classifier_optimizing_mixed_instance_precision_and_macro_precision_using_fw = make_mixed_frank_wolfe_wrapper(
+    M.binary_precision_on_conf_matrix, "macro-averaged precision")
+find_classifier_optimizing_mixed_instance_precision_and_macro_f1_score_using_fw = make_mixed_frank_wolfe_wrapper(
+    M.binary_f1_score_on_conf_matrix, "macro-averaged F1 score")
+find_classifier_optimizing_mixed_instance_precision_and_macro_recall_using_fw = make_mixed_frank_wolfe_wrapper(
+    M.binary_recall_on_conf_matrix, "macro-averaged recall")

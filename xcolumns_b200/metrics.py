@@ -14,8 +14,9 @@ from typing import Any, Callable, Dict, Optional, Tuple
 from .utils import add_kwargs_to_signature
 
 XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA, XC_METRIC_JACCARD = 0, 1, 2, 3
-XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN = 4, 5, 6
-AFFINE_GAIN_METRICS = (XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA, XC_METRIC_BALANCED_ACC)
+XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN, XC_METRIC_PREC_AT_K = 4, 5, 6, 7
+AFFINE_GAIN_METRICS = (XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA, XC_METRIC_BALANCED_ACC,
+                       XC_METRIC_PREC_AT_K)
 TN_METRICS = (XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN)
 
 
@@ -56,6 +57,49 @@ def binary_gmean_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
 def binary_hmean_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
     tpr, tnr = _rates(tp, fp, fn, tn, epsilon)
     return (2 * tpr * tnr) / (tpr + tnr)
+
+
+def binary_precision_at_k_on_conf_matrix(tp, fp, fn, tn, k: int):
+    """tp / k (xcolumns/metrics.py:497-513)."""
+    return tp / k
+
+
+class PrecisionAtK:
+    """``binary_precision_at_k_on_conf_matrix`` with k bound -- the callable
+    predict_optimizing_instance_precision_using_bc builds at block_coordinate.py:822-823, as an
+    object the resolver can recognise."""
+
+    def __init__(self, k: int):
+        self.k = k
+        self.__name__ = "instance_precision_with_specific_k"
+
+    def __call__(self, tp, fp, fn, tn):
+        return binary_precision_at_k_on_conf_matrix(tp, fp, fn, tn, self.k)
+
+
+class MixedInstancePrecisionMetric:
+    """The mixed utilities of block_coordinate.py:848-1045:
+    ``(1 - alpha) * binary_precision_at_k(tp, k) + alpha * binary_metric(tp, fp, fn, tn, epsilon) / m``
+    (evaluated per label and summed by the caller)."""
+
+    def __init__(self, binary_metric: Callable, alpha: float, k: int, m: int):
+        self.binary_metric, self.alpha, self.k, self.m = binary_metric, alpha, k, m
+        self.__name__ = "mixed_utility_fn"
+
+    def __call__(self, tp, fp, fn, tn, epsilon: float = 1e-9):
+        return (1 - self.alpha) * binary_precision_at_k_on_conf_matrix(tp, fp, fn, tn, self.k) + self.alpha * \
+            self.binary_metric(tp, fp, fn, tn, epsilon=epsilon) / self.m
+
+
+class MixedInstancePrecisionMacroMetric:
+    """Frank-Wolfe objective of frank_wolfe.py:838-915: the sum over labels of the mixed utility."""
+
+    def __init__(self, binary_metric: Callable, alpha: float, k: int, m: int):
+        self.per_label = MixedInstancePrecisionMetric(binary_metric, alpha, k, m)
+        self.__name__ = "mixed_metric_fn"
+
+    def __call__(self, tp, fp, fn, tn, epsilon: float = 1e-9):
+        return self.per_label(tp, fp, fn, tn, epsilon=epsilon).sum()
 
 
 _BINARY_IDS = {
@@ -106,6 +150,12 @@ def resolve_binary_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]
     """(metric id, beta, epsilon) of a built-in binary metric callable -- ours or the reference's
     own (matched by module + name).  Other callables cannot run inside the fused kernels."""
     kw = dict(metric_kwargs or {})
+    if isinstance(func, PrecisionAtK):
+        if kw:
+            raise ValueError(f"unknown metric_kwargs for precision@k: {sorted(kw)}")
+        return XC_METRIC_PREC_AT_K, float(func.k), 1e-9   # the "beta" slot carries k (see metric_c1)
+    if isinstance(func, MixedInstancePrecisionMetric):
+        return resolve_binary_metric(func.binary_metric, kw)
     name = getattr(func, "__name__", None)
     mod = getattr(func, "__module__", None)
     if name in _BINARY_IDS and mod in _OWN_MODULES:
@@ -122,8 +172,27 @@ def resolve_binary_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]
         f"the CUDA sweep and xcolumns_b200 has no CPU fallback")
 
 
+def resolve_mix(func: Callable) -> Optional[Tuple[float, float, float]]:
+    """(alpha, k, m) when func is one of the mixed instance-precision utilities, else None."""
+    if isinstance(func, MixedInstancePrecisionMacroMetric):
+        func = func.per_label
+    if isinstance(func, MixedInstancePrecisionMetric):
+        return float(func.alpha), float(func.k), float(func.m)
+    return None
+
+
+def metric_c1_beta2(metric_id: int, beta: float) -> Tuple[float, float]:
+    """(c1, beta2) of xc_metric_params: 1 + beta**2 and beta**2 exactly like python computes them;
+    precision@k passes k through c1."""
+    if metric_id == XC_METRIC_PREC_AT_K:
+        return float(beta), 0.0
+    return float(1 + beta**2), float(beta**2)
+
+
 def resolve_macro_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]] = None) -> Tuple[int, float, float]:
     """Same for a macro-averaged metric on the confusion matrix (Frank-Wolfe objective)."""
+    if isinstance(func, MixedInstancePrecisionMacroMetric):
+        return resolve_binary_metric(func.per_label.binary_metric, metric_kwargs)
     inner = getattr(func, "_xc_binary_metric", None)
     if inner is None and getattr(func, "__name__", "") == "macro_metric_on_conf_matrix" and func.__closure__:
         # the reference's factory closure (xcolumns/metrics.py:51-58) captures `binary_metric`
