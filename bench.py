@@ -87,7 +87,7 @@ def run_reference(args):
         "impl": "reference", "metric": "BCA macro-F1@5 instances/sec per sweep", "value": value,
         "unit": "instances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 scores, f64 state", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": args.rows, "labels": args.labels, "k": args.k},
         "cpu_baseline": {"value": value, "unit": "instances/s", "cores": 1, "kind": "port",
                          "sample": f"{n_sub} rows x {args.labels} labels of the same distribution, 1 sequential sweep per step "
@@ -171,7 +171,7 @@ def secondary(args):
         def step():
             sweep_no[0] += 1
             order = sess.permutation(n, 3 + 7919 * sweep_no[0])
-            sess.delta.zero_()
+            sess.zero_delta()
             sess.sweep_batched(order, batch)
             sess.recompute(XC_SUM_FAST)
             sess.utility_device(1)
@@ -218,7 +218,7 @@ def secondary(args):
         line = {"metric": "Frank-Wolfe macro-F1@5 iterations/sec", "value": iters / (ms / 1e3), "unit": "iterations/s",
                 "n_gpus": 1, "steps": iters, "warmup": args.warmup, "ms_per_step": ms / iters,
                 "ms_per_call": ms_call,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 scores, f64 state",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (y_true := y_proba)",
                 "config": {"workload": f"wiki10-31k-shape dense f32 n={n} m={m} k={k} macro-F1 FW, {iters} iterations incl. init pass"},
                 "roofline": {"bound": "hbm", "achieved": bytes_per_step * iters / (ms / 1e3) / 1e9, "peak": peak,
@@ -244,7 +244,7 @@ def secondary(args):
     ach = bytes_per_step * args.steps / (ms / 1e3) / 1e9
     line = {"metric": metric, "value": unit_count * args.steps / (ms / 1e3), "unit": unit, "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 scores, f64 state", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl, "batch_rows": batch},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "note": "algorithmic bytes = nnz*8 + (n+1)*8 per sweep; the sweep is bound by L2 gathers of "
@@ -297,7 +297,7 @@ def main():
     def one_sweep(events=None):
         sweep_no[0] += 1
         order = sess.permutation(n, 17 + 1000003 * rank + 7919 * sweep_no[0])
-        sess.delta.zero_()
+        sess.zero_delta()
         sess.sweep_batched(order, batch, n_batches, events=events)
         sess.recompute(XC_SUM_FAST)
         sess.utility_device(1)
@@ -357,7 +357,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "bca_batch_dense_kernel<float,4>",
+                "traffic": traffic, "kernel": "bca_batch_dense_kernel<float,1>",
                 "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "kernel_share_of_step": float(np.sum(kern_ms)) / ms,
                 "kernel_ms_per_sweep": [round(float(np.sum(kern_ms[i * len(kern_ms) // args.steps:(i + 1) * len(kern_ms) // args.steps])), 4)
@@ -367,17 +367,21 @@ def main():
     line = {
         "metric": "BCA macro-F1@5 instances/sec per sweep", "value": value, "unit": "instances/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 scores, f64 state",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows_per_gpu": n, "labels": m, "k": k, "mode": "batched",
                    "batch_rows_per_gpu": batch, "commits_per_sweep": n_batches,
                    "l2": "input 15.96 GB per GPU >> 126 MB L2, no flush needed",
-                   "collective": "NCCL all-reduce of 3*m float64 deltas per commit" if world > 1 else "none"},
+                   "collective": ("none" if world == 1 else
+                                  "peer-memory commit kernel (flags + P2P reads of the 3*m float64 deltas over NVLink) "
+                                  "between batches; NCCL all-reduce of 2*m float64 at sweep boundaries"
+                                  if sess.peer is not None else "NCCL all-reduce of 3*m float64 deltas per commit")},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": sampler.summary(),
         "utility_after_timed_sweeps": utilities[1],
     }
 
     # ---- end-to-end through the public API with host buffers (rank-local shard) ----------------
+    sess.close()
     if not args.no_e2e:
         del sess, init_pred
         host = torch.empty((n, m), dtype=torch.float32, pin_memory=True)

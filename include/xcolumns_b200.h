@@ -246,6 +246,28 @@ XC_API int xc_cov_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m
                               const double *Ef, int32_t *pred_idx, double *dEf, void *stream);
 XC_API int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void *stream);
 
+/* ---- commits over peer memory (rows sharded over the GPUs of one box) -------------------- */
+/* One window per rank: cudaMalloc'ed, exported with CUDA IPC (ipc_handle_out: 64 bytes), mapped by
+ * every other rank with xc_p2p_open(handles = the world * 64 gathered bytes).  xc_p2p_payload
+ * returns the local payload (device pointer, payload_bytes long, zero-initialised); for the batched
+ * sweep it holds two delta buffers of xc_bca_delta_stride(m) bytes each, [dtp | dfp | dfn].        */
+typedef struct xc_p2p xc_p2p;
+XC_API int xc_p2p_create(xc_ctx *ctx, int world, int rank, int64_t payload_bytes, xc_p2p **out,
+                         void *ipc_handle_out);
+XC_API int xc_p2p_open(xc_ctx *ctx, xc_p2p *w, const void *handles);
+XC_API void *xc_p2p_payload(xc_p2p *w);
+XC_API int xc_p2p_error(xc_ctx *ctx, xc_p2p *w, unsigned *out);
+XC_API void xc_p2p_destroy(xc_ctx *ctx, xc_p2p *w);
+XC_API int64_t xc_bca_delta_stride(int64_t m);
+/* The exchange step of the sharded batched sweep as ONE kernel: flag every peer, wait for every
+ * peer's flag, add the W delta vectors of buffer `buf` (read from the peers' windows over NVLink, in
+ * rank order: bit-identical on every rank) into tp/fp/fn, refresh the gain coefficients (like
+ * xc_bca_coef) and clear the local buffer buf ^ 1.  Every rank must call it the same number of
+ * times.  Replaces ncclAllReduce + xc_bca_coef between two batches.                              */
+XC_API int xc_bca_commit_p2p(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, double *tp,
+                             double *fp, double *fn, int64_t m, int buf, float *coef_n,
+                             float *coef_s, void *stream);
+
 /* ---- Frank-Wolfe iterate ----------------------------------------------------------------- */
 /* ref: frank_wolfe.py:601-606: weighted top-k of every row with the linear classifier (a, b)
  * fused with the accumulation of tp_j = sum_i y_true[i][j] * yhat[i][j] and

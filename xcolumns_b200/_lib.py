@@ -43,6 +43,10 @@ _SIGNATURES = {
     "xc_confmat_csr": [_vp, _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp],
     "xc_confmat_csr_compact": [_vp, _vp, _vp, _int, _vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp],
     "xc_confmat_csc_ordered": [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
+    "xc_p2p_create": [_int, _int, _i64, _vp, _vp],
+    "xc_p2p_open": [_vp, _vp],
+    "xc_p2p_error": [_vp, _vp],
+    "xc_bca_commit_p2p": [_vp, _MP, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp],
     "xc_colsum_dense": [_vp, _int, _i64, _i64, _i64, _vp, _vp],
     "xc_colsum_csr": [_vp, _int, _vp, _i64, _i64, _vp, _vp],
     "xc_utility": [_MP, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
@@ -100,6 +104,12 @@ def load():
         lib.xc_fw_alpha_scratch_bytes.restype = C.c_int64
         lib.xc_fw_alpha_ctl_offset.argtypes = [C.c_int64, C.c_int64]
         lib.xc_fw_alpha_ctl_offset.restype = C.c_int64
+        lib.xc_p2p_payload.argtypes = [C.c_void_p]
+        lib.xc_p2p_payload.restype = C.c_void_p
+        lib.xc_p2p_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        lib.xc_p2p_destroy.restype = None
+        lib.xc_bca_delta_stride.argtypes = [C.c_int64]
+        lib.xc_bca_delta_stride.restype = C.c_int64
         lib.xc_bca_coef_len.argtypes = [C.c_int64]
         lib.xc_bca_coef_len.restype = C.c_int64
         lib.xc_fill_pred_dense_host.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,

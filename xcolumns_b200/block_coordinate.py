@@ -29,7 +29,7 @@ from scipy.sparse import csr_matrix
 from . import _device as dev
 from . import metrics as M
 from ._lib import XC_SUM_FAST, XC_SUM_ORDERED, MetricParams
-from .distributed import Comm, make_comm
+from .distributed import Comm, PeerWindow, make_comm, peer_commit_enabled
 from .types import DefaultAccDataDType, Matrix
 from .utils import add_kwargs_to_signature, log_info, log_warning
 from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
@@ -108,6 +108,17 @@ class BcaSession:
         self.state = torch.zeros((4, self.m), **f64)           # tp, fp, fn, tn
         self.state[3].fill_(-1.0)
         self.delta = torch.zeros((3, self.m), **f64)           # pending batch deltas
+        self.peer: Optional[PeerWindow] = None                 # peer-memory commits (sharded dense/CSR batches)
+        if peer_commit_enabled(self.comm, self.device, self.m):
+            stride = int(self.ctx.lib.xc_bca_delta_stride(self.m))
+            peer = PeerWindow(self.ctx, self.comm, 2 * stride, self.device)
+            if peer.ok:
+                self.peer = peer
+                # the two delta buffers live in the window: batch b accumulates into buffer b & 1
+                self.delta2 = [peer.payload[b * stride: b * stride + 24 * self.m].view(torch.float64).view(3, self.m)
+                               for b in range(2)]
+            else:
+                peer.close()
         self.colsum: Optional[torch.Tensor] = None
         clen = int(self.ctx.lib.xc_bca_coef_len(self.m))       # padded to whole coefficient tiles
         self.coef_n = torch.zeros((clen, 2), dtype=torch.float32, device=self.device)
@@ -122,8 +133,23 @@ class BcaSession:
     def _sp(self, i):
         return C.c_void_p(self.state[i].data_ptr())
 
-    def _dp(self, i):
-        return C.c_void_p(self.delta[i].data_ptr())
+    def _dp(self, i, buf: int = 0):
+        t = self.delta2[buf] if self.peer is not None else self.delta
+        return C.c_void_p(t[i].data_ptr())
+
+    def zero_delta(self) -> None:
+        if self.peer is not None:
+            self.peer.payload.zero_()
+        else:
+            self.delta.zero_()
+
+    def close(self) -> None:
+        if self.peer is not None:
+            torch.cuda.synchronize(self.device)
+            self.comm.barrier()          # nobody may still be reading this rank's window
+            self.peer.check()
+            self.peer.close()
+            self.peer = None
 
     # -- state from the current prediction ---------------------------------------------------
     def recompute(self, order: int) -> None:
@@ -222,9 +248,19 @@ class BcaSession:
         for b in range(nb):
             lo = min(b * batch, n_loc)
             hi = min(lo + batch, n_loc)
-            # fold the pending deltas into the state, refresh the gain coefficients
-            self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
-                          self._dp(1), self._dp(2), self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
+            cur = b & 1 if self.peer is not None else 0
+            if self.peer is not None and b > 0:
+                # exchange + fold + coefficients in one kernel over peer memory (reads buffer (b-1) & 1)
+                self.ctx.call("xc_bca_commit_p2p", self.peer.handle, C.byref(self.p), self._sp(0), self._sp(1),
+                              self._sp(2), self.m, (b - 1) & 1, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
+            elif self.peer is not None:
+                # first batch of a sweep: the state is fresh, nothing to fold
+                self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), None, None, None,
+                              self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
+            else:
+                # fold the pending deltas into the state, refresh the gain coefficients
+                self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
+                              self._dp(1), self._dp(2), self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
             if hi > lo:
                 rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
                 if events is not None:
@@ -233,15 +269,15 @@ class BcaSession:
                 if self.is_csr:
                     self.ctx.call("xc_bca_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
                                   rows, hi - lo, k, dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
-                                  self._dp(0), self._dp(1), self._dp(2), self._s())
+                                  self._dp(0, cur), self._dp(1, cur), self._dp(2, cur), self._s())
                 else:
                     self.ctx.call("xc_bca_batch_dense", dev.ptr(d.t), d.code, d.m, d.ld, rows, hi - lo, k,
-                                  dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._dp(0),
-                                  self._dp(1), self._dp(2), self._s())
+                                  dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._dp(0, cur),
+                                  self._dp(1, cur), self._dp(2, cur), self._s())
                 if events is not None:
                     ev1.record(torch.cuda.current_stream(self.device))
                     events.append((ev0, ev1, hi - lo))
-            if self.comm.world > 1:
+            if self.comm.world > 1 and self.peer is None:
                 self.comm.allreduce_sum_(self.delta)
 
 
@@ -421,7 +457,7 @@ def predict_using_bc_with_0approx(
             saved[j] = sess.pred.clone()
             if shuffle_order:
                 order_dev = sess.permutation(n_order, base_seed + 0x632BE59BD9B4E019 * j)
-            sess.delta.zero_()
+            sess.zero_delta()
             sess.sweep_batched(order_dev, batch, n_batches)
             sess.recompute(XC_SUM_FAST)
             sess.utility_device(1)
@@ -450,6 +486,8 @@ def predict_using_bc_with_0approx(
                 break
 
     meta["launches"] = sess.ctx.launches()
+    meta["commit"] = "peer-memory" if sess.peer is not None else ("all-reduce" if comm.world > 1 else "local")
+    sess.close()
     _mark("sweeps")
     y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format)
     _mark("output")

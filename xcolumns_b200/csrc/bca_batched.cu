@@ -21,18 +21,9 @@ constexpr int kThreads = 256;
 // D = u*(tp+fp) + v*(tp+fn) + E with E = eps*n_div (eps is added AFTER dividing by n in the
 // reference, block_coordinate.py:176-183 + metrics.py), c = numerator factor:
 //   precision (c,u,v) = (1,1,0); recall (1,0,1); F-beta (1+b^2, b^2, 1).
-__global__ void __launch_bounds__(kThreads)
-bca_coef_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn,
-                int64_t m, float2 *coef_n, float2 *coef_s)
+__device__ __forceinline__ void bca_coef_of(const xc_metric_params &p, double t, double f, double g, float2 *cn,
+                                            float2 *cs)
 {
-    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (j >= m) return;
-    double t = tp[j], f = fp[j], g = fn[j];
-    if (dtp) {
-        t += dtp[j]; f += dfp[j]; g += dfn[j];
-        tp[j] = t; fp[j] = f; fn[j] = g;
-        dtp[j] = 0.0; dfp[j] = 0.0; dfn[j] = 0.0;
-    }
     const double sgn = p.maximize ? 1.0 : -1.0;
     const double E = p.eps * p.n_div;
     double Bn, An, Bs, As;  // gain = A + B * eta for an unselected (n) / currently selected (s) label
@@ -68,8 +59,95 @@ bca_coef_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *
         Bn = w1 + w2 * Bn; An = w2 * An;
         Bs = w1 + w2 * Bs; As = w2 * As;
     }
-    coef_n[j] = make_float2((float)(sgn * Bn), (float)(sgn * An));
-    coef_s[j] = make_float2((float)(sgn * Bs), (float)(sgn * As));
+    *cn = make_float2((float)(sgn * Bn), (float)(sgn * An));
+    *cs = make_float2((float)(sgn * Bs), (float)(sgn * As));
+}
+
+
+__global__ void __launch_bounds__(kThreads)
+bca_coef_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn,
+                int64_t m, float2 *coef_n, float2 *coef_s)
+{
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= m) return;
+    double t = tp[j], f = fp[j], g = fn[j];
+    if (dtp) {
+        t += dtp[j]; f += dfp[j]; g += dfn[j];
+        tp[j] = t; fp[j] = f; fn[j] = g;
+        dtp[j] = 0.0; dfp[j] = 0.0; dfn[j] = 0.0;
+    }
+    bca_coef_of(p, t, f, g, coef_n + j, coef_s + j);
+}
+
+// ---- commit over peer memory (rows sharded over the GPUs of one box) ----------------------------------
+// After a batch every rank holds the deltas of its own rows.  Instead of an NCCL all-reduce followed by
+// the coefficient kernel, ONE kernel per rank
+//   1. raises its flag in every peer's window (st.release.sys over NVLink),
+//   2. waits until every peer's flag for this commit has arrived (ld.acquire.sys on local memory),
+//   3. reads the W delta vectors straight out of the peers' windows (coalesced P2P loads, rank order,
+//      so every rank adds the same numbers in the same order and the replicated state stays bit-equal),
+//      folds them into its state, refreshes the gain coefficients and clears its OTHER delta buffer.
+// Deltas are double-buffered: batch b accumulates into buffer b & 1, so a peer that is one commit ahead
+// never overwrites what a slower rank is still reading (a rank passes barrier b only after every peer
+// finished commit b - 1).  A rank that waits longer than ~4 s raises the window's error word and leaves.
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bca_commit_p2p_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_t *const *windows, int world,
+                      int rank, unsigned epoch, int buf, int64_t m, int64_t delta_off, int64_t delta_stride,
+                      float2 *coef_n, float2 *coef_s)
+{
+    __shared__ int s_fail;
+    uint8_t *mine = windows[rank];
+    if (threadIdx.x == 0) s_fail = 0;
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned *>(windows[threadIdx.x]) + rank, epoch);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const unsigned *flag = reinterpret_cast<const unsigned *>(mine) + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        // flags only grow; a peer may already be one commit ahead (wrap-safe signed distance)
+        while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+            if (global_timer_ns() - t0 > 4000000000ULL) {
+                s_fail = 1;
+                reinterpret_cast<unsigned *>(mine)[XC_P2P_ERR_WORD] = epoch;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_fail) return;
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= m) return;
+    double dt = 0.0, df = 0.0, dg = 0.0;
+    for (int r = 0; r < world; ++r) {  // rank order on every rank: bit-identical sums
+        const double *d = reinterpret_cast<const double *>(windows[r] + delta_off + (int64_t)buf * delta_stride);
+        dt += __ldcv(d + j);
+        df += __ldcv(d + m + j);
+        dg += __ldcv(d + 2 * m + j);
+    }
+    const double t = tp[j] + dt, f = fp[j] + df, g = fn[j] + dg;
+    tp[j] = t; fp[j] = f; fn[j] = g;
+    double *nxt = reinterpret_cast<double *>(mine + delta_off + (int64_t)(buf ^ 1) * delta_stride);
+    nxt[j] = 0.0; nxt[m + j] = 0.0; nxt[2 * m + j] = 0.0;
+    bca_coef_of(p, t, f, g, coef_n + j, coef_s + j);
 }
 
 // ---- shared epilogue: compare new selection with the old one, emit deltas, store the row ----------
@@ -734,6 +812,25 @@ extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, d
         return XC_ERR_UNSUPPORTED;  // gain not affine in eta
     bca_coef_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         *p, tp, fp, fn, dtp, dfp, dfn, m, (float2 *)coef_n, (float2 *)coef_s);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int64_t xc_bca_delta_stride(int64_t m) { return ((3 * m * 8 + 255) / 256) * 256; }
+
+extern "C" int xc_bca_commit_p2p(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, double *tp, double *fp,
+                                 double *fn, int64_t m, int buf, float *coef_n, float *coef_s, void *stream)
+{
+    if (!ctx || !w || !w->opened || !p || !tp || !fp || !fn || !coef_n || !coef_s || m <= 0 || (buf & ~1)) return XC_ERR_INVALID;
+    if (p->metric != XC_METRIC_PRECISION && p->metric != XC_METRIC_RECALL && p->metric != XC_METRIC_FBETA &&
+        p->metric != XC_METRIC_BALANCED_ACC && p->metric != XC_METRIC_PREC_AT_K)
+        return XC_ERR_UNSUPPORTED;
+    const int64_t stride = xc_bca_delta_stride(m);
+    if ((size_t)(XC_P2P_HEADER + 2 * stride) > w->bytes) return XC_ERR_INVALID;
+    w->epoch += 1;
+    bca_commit_p2p_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        *p, tp, fp, fn, w->windows_dev, w->world, w->rank, w->epoch, buf, m, XC_P2P_HEADER, stride, (float2 *)coef_n,
+        (float2 *)coef_s);
     XC_LAUNCHED(ctx);
     return XC_OK;
 }

@@ -21,6 +21,22 @@ struct xc_ctx {
 
 constexpr int XC_RED_MAX_BLOCKS = 1024;
 
+// Peer-memory window of one rank (csrc/p2p.cu): cudaMalloc'ed, exported with CUDA IPC and mapped by
+// every other rank of the box.  Layout: [0, 256) one arrival flag per rank, word XC_P2P_ERR_WORD the
+// error word, [XC_P2P_HEADER, ...) payload (the double-buffered BCA delta vectors).
+constexpr int XC_P2P_MAX_WORLD = 16;
+constexpr int XC_P2P_ERR_WORD = 64;
+constexpr int XC_P2P_HEADER = 512;
+struct xc_p2p {
+    int world;
+    int rank;
+    size_t bytes;
+    uint8_t *windows[XC_P2P_MAX_WORLD];  // windows[rank] is the local allocation, the others are IPC mappings
+    uint8_t **windows_dev;               // the same table in device memory
+    unsigned epoch;                      // commits performed so far (identical on every rank)
+    bool opened;
+};
+
 #define XC_FULL 0xffffffffu
 
 #define XC_CUDA_TRY(ctx, expr)                    \

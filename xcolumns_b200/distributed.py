@@ -7,6 +7,8 @@ torch.distributed is plumbing here: the same code runs over gloo on CPU tensors 
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -78,3 +80,59 @@ def make_comm(distributed, device: Optional[torch.device] = None) -> Comm:
         raise RuntimeError("distributed=True needs torch.distributed.init_process_group() first")
     group = dist.group.WORLD if distributed is True else distributed
     return Comm(group, device)
+
+
+class _RawCuda:
+    """__cuda_array_interface__ view of device memory owned by the C library."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerWindow:
+    """This rank's peer-memory window plus the mappings of every other rank's window (csrc/p2p.cu).
+    The commit kernels signal and read through NVLink directly; torch.distributed is only used once,
+    to exchange the 64-byte CUDA IPC handles."""
+
+    def __init__(self, ctx, comm: "Comm", payload_bytes: int, device: torch.device):
+        self.ctx, self.comm, self.device = ctx, comm, device
+        self.handle = C.c_void_p()
+        ipc = (C.c_ubyte * 64)()
+        ctx.call("xc_p2p_create", comm.world, comm.rank, int(payload_bytes), C.byref(self.handle), ipc)
+        gathered = [None] * comm.world
+        dist.all_gather_object(gathered, bytes(ipc), group=comm.group)
+        ok = 1
+        try:
+            ctx.call("xc_p2p_open", self.handle, b"".join(gathered))
+        except Exception:           # e.g. no peer access between two of the GPUs
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
+        self.ok = bool(int(flag.item()))
+        ptr = ctx.lib.xc_p2p_payload(self.handle)
+        self.payload = torch.as_tensor(_RawCuda(int(ptr), int(payload_bytes)), device=device)
+
+    def check(self) -> None:
+        err = C.c_uint(0)
+        self.ctx.call("xc_p2p_error", self.handle, C.byref(err))
+        if err.value:
+            raise RuntimeError(f"xcolumns_b200: peer-memory commit {err.value} timed out waiting for another rank")
+
+    def close(self) -> None:
+        if self.handle:
+            self.payload = None
+            self.ctx.lib.xc_p2p_destroy(self.ctx.handle, self.handle)
+            self.handle = C.c_void_p()
+
+
+def peer_commit_enabled(comm: "Comm", device: torch.device, m: int) -> bool:
+    """Peer-memory commits: several ranks on CUDA devices of one box, delta vectors small enough that one
+    rank reading all W of them (W * 24 m bytes over NVLink) beats a bandwidth-optimal all-reduce.
+    $XCOLUMNS_B200_P2P=0 forces the NCCL all-reduce path."""
+    if not (comm.active and comm.world > 1 and device.type == "cuda"):
+        return False
+    if os.environ.get("XCOLUMNS_B200_P2P", "1") == "0" or comm.world > 16:
+        return False
+    if dist.get_backend(comm.group) != "nccl":
+        return False
+    return 24 * m <= (2 << 20)
