@@ -91,3 +91,25 @@ def test_no_gpu_fails_loudly():
     from xcolumns_b200._lib import XColumnsB200Error
     with pytest.raises(XColumnsB200Error):
         xb.predict_top_k(np.random.rand(4, 8).astype(np.float32), 2)
+
+
+def test_streaming_kernels_keep_their_occupancy():
+    """The HBM-bound scan kernels are tuned for 40 registers (6 CTAs of 256 threads per SM, no local
+    memory); a refactor of the shared scan loop that costs registers silently costs ~20 % of the
+    headline throughput (measured), so the built library is checked."""
+    import re
+    import shutil
+    import subprocess
+    from xcolumns_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    for m_ in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+        usage[m_.group(1)] = (int(m_.group(2)), int(m_.group(3)))
+    checked = 0
+    for name, (reg, stack) in usage.items():
+        if "bca_batch_dense_kernelIfLi1E" in name or "fw_iterate_dense_kernelIfLi1E11XfMulAddVec" in name:
+            assert reg <= 40 and stack == 0, (name, reg, stack)
+            checked += 1
+    assert checked >= 2, sorted(usage)[:5]

@@ -14,7 +14,7 @@ constexpr int kThreads = 256;
 // gains = eta * a + b with separate IEEE multiply/add in the dtype numpy would use
 // (weighted_prediction.py:37-41), top-k per row, then for the k selected labels
 //   tp[j] += y_true[i][j],  cnt[j] += 1        (float64 atomics)
-template <typename TE, int R, int DEPTH, class Xf>
+template <typename TE, int R, class Xf>
 __global__ void __launch_bounds__(kThreads)
 fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_t ld, const TE *__restrict__ y_true,
                         int64_t ld_true, Xf xf, int k, double *tp, double *cnt, int32_t *__restrict__ pred_idx,
@@ -37,7 +37,7 @@ fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_
             tk[r].init();
             dummy[r] = -1;
         }
-        xc_scan_rows<TE, TE, R, false, Xf, DEPTH>(rp, m, vec_ok, xf, tk, dummy, k);
+        xc_scan_rows<TE, TE, R, false, Xf>(rp, m, vec_ok, xf, tk, dummy, k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (row_id[r] < 0) continue;
@@ -806,33 +806,24 @@ int launch_fw_dense(xc_ctx *ctx, const void *eta, int64_t n, int64_t m, int64_t 
         int v = atoi(e);
         if (v == 1 || v == 2 || v == 4) rr = v;
     }
-    // loads per row in flight
-    static int depth_env = -1;  // $XCOLUMNS_B200_FW_DEPTH=2|4
-    if (depth_env < 0) {
-        const char *e = getenv("XCOLUMNS_B200_FW_DEPTH");
-        depth_env = (e && (e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 0;
-    }
-    const int depth = depth_env ? depth_env : 2;  // 4 measured slower (350 vs 334 us at 14 k x 31 k)
     // classifier rows present and 16-byte aligned (the host shim pads the classifier matrices): vector loads
     const bool coef_vec = vec_ok && a && b && xc_aligned16(a) && xc_aligned16(b);
     XfMulAddVec<TE> xfv{(const TE *)a, (const TE *)b};
-#define XC_GO(R, D)                                                                                          \
+#define XC_GO(R)                                                                                             \
     if (coef_vec) {                                                                                          \
-        auto kern = fw_iterate_dense_kernel<TE, R, D, XfMulAddVec<TE>>;                                      \
+        auto kern = fw_iterate_dense_kernel<TE, R, XfMulAddVec<TE>>;                                      \
         int grid = grid_for(ctx, kern, (n + R - 1) / R);                                                     \
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true, xfv, k, tp,  \
                                         cnt, pred_idx, vec_ok);                                              \
     } else {                                                                                                 \
-        auto kern = fw_iterate_dense_kernel<TE, R, D, XfMulAdd<TE>>;                                         \
+        auto kern = fw_iterate_dense_kernel<TE, R, XfMulAdd<TE>>;                                         \
         int grid = grid_for(ctx, kern, (n + R - 1) / R);                                                     \
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true, xf, k, tp,   \
                                         cnt, pred_idx, vec_ok);                                              \
     }
-    if (rr == 4) XC_GO(4, 2)
-    else if (rr == 2 && depth == 4) XC_GO(2, 4)
-    else if (rr == 2) XC_GO(2, 2)
-    else if (depth == 4) XC_GO(1, 4)
-    else XC_GO(1, 2)
+    if (rr == 4) XC_GO(4)
+    else if (rr == 2) XC_GO(2)
+    else XC_GO(1)
 #undef XC_GO
     XC_LAUNCHED(ctx);
     return XC_OK;
