@@ -126,6 +126,12 @@ XC_API int xc_scatter_pred_dense(xc_ctx *ctx, const int32_t *pred_idx, const voi
 XC_API int xc_fill_pred_dense_host(void *out_host, int out_dtype, int64_t n, int64_t m, int64_t ld,
                                    const int32_t *idx_host, const void *val_host, int val_dtype,
                                    int k, int nthreads);
+/* the two halves of the above: clear `bytes` of host memory on host threads (started by the shim at
+ * call entry, overlapping the upload and the sweeps), then only scatter into the cleared matrix     */
+XC_API int xc_zero_host(void *p, int64_t bytes, int nthreads);
+XC_API int xc_scatter_pred_dense_host(void *out_host, int out_dtype, int64_t n, int64_t m, int64_t ld,
+                                   const int32_t *idx_host, const void *val_host, int val_dtype,
+                                   int k, int nthreads);
 
 /* ---- label-wise confusion sums -------------------------------------------------------- */
 /* ref: confusion_matrix.py:160-202, :364-399 (calculate_confusion_matrix), dense x dense.

@@ -69,7 +69,8 @@ def test_ctypes_prototypes_match_header():
             else:
                 assert t is want, f"{name}: {p!r} bound as {t}"
     bound = set(_lib._SIGNATURES) | {"xc_abi_version", "xc_strerror", "xc_ctx_create", "xc_ctx_destroy",
-                                     "xc_last_cuda_error", "xc_launch_count", "xc_sm_count", "xc_fill_pred_dense_host", "xc_bca_coef_len", "xc_fw_alpha_scratch_bytes",
+                                     "xc_last_cuda_error", "xc_launch_count", "xc_sm_count", "xc_fill_pred_dense_host", "xc_scatter_pred_dense_host",
+                                     "xc_zero_host", "xc_bca_coef_len", "xc_fw_alpha_scratch_bytes",
                                      "xc_fw_alpha_ctl_offset", "xc_p2p_payload", "xc_p2p_destroy", "xc_bca_delta_stride"}
     assert set(decls) == bound, f"unbound: {set(decls) - bound}, undeclared: {bound - set(decls)}"
 

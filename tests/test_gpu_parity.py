@@ -503,3 +503,34 @@ def test_fw_mixed_golden(xb, golden, name, metric, alpha):
     assert len(meta["utilities"]) == len(g[name + "_util"])
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
     assert clf.a.shape == g[name + "_a"].shape and np.allclose(clf.p, g[name + "_p"], atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_dense_output_prefill_path(xb, oracle, monkeypatch):
+    """host inputs: the dense result is cleared on background threads during the upload / sweeps and only
+    scattered at the end -- same matrices as the plain path, for numpy and CPU-tensor inputs"""
+    import torch
+    from xcolumns_b200 import _device as dev
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(3000, 700, seed=91)
+    plain_top = xb.predict_top_k(eta, 5)
+    plain_bca = xb.predict_optimizing_macro_f1_score_using_bc(eta, 5, seed=0, mode="batched")
+    monkeypatch.setattr(dev.DenseOutputPrefill, "MIN_BYTES", 0)
+    started = []
+    orig = dev.DenseOutputPrefill.start
+
+    def spy(*a, **kw):
+        r = orig(*a, **kw)
+        started.append(r is not None)
+        return r
+
+    monkeypatch.setattr(dev.DenseOutputPrefill, "start", staticmethod(spy))
+    top = xb.predict_top_k(eta, 5)
+    assert started == [True] and top.dtype == eta.dtype and (top == plain_top).all()
+    ref_idx, _ = oracle.topk_indices_dense(eta, 5)
+    assert (np.nonzero(top)[1].reshape(-1, 5) == ref_idx).all()
+    bca = xb.predict_optimizing_macro_f1_score_using_bc(eta, 5, seed=0, mode="batched")
+    assert started == [True, True] and (bca == plain_bca).all()
+    w = xb.predict_weighted_per_instance(torch.from_numpy(eta), 4, keep_scores=True, dtype=torch.float64)
+    assert isinstance(w, torch.Tensor) and w.dtype == torch.float64 and ((w != 0).sum(1) == 4).all()
+    assert started == [True, True, True]

@@ -115,6 +115,10 @@ def load():
         lib.xc_fill_pred_dense_host.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                                 C.c_void_p, C.c_int, C.c_int, C.c_int]
         lib.xc_fill_pred_dense_host.restype = C.c_int
+        lib.xc_scatter_pred_dense_host.argtypes = lib.xc_fill_pred_dense_host.argtypes
+        lib.xc_scatter_pred_dense_host.restype = C.c_int
+        lib.xc_zero_host.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+        lib.xc_zero_host.restype = C.c_int
         for name, args in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = [C.c_void_p] + args

@@ -376,6 +376,8 @@ def predict_using_bc_with_0approx(
                              normalize_conf_matrix, maximize, tolerance, init_y_pred, max_iters, shuffle_order,
                              skip_tn, return_meta, seed, verbose, meta, device)
     is_csr = isinstance(y_proba, csr_matrix)
+    # host inputs with a large dense result: clear the result on host threads while the GPU works
+    prefill = None if (is_csr or y_pred_format != "same") else dev.DenseOutputPrefill.start(y_proba, n, m)
     data = dev.csr_to_device(y_proba, device) if is_csr else dev.dense_to_device(y_proba, device)
 
     n_div = n if normalize_conf_matrix else 1            # block_coordinate.py:403-405
@@ -489,7 +491,7 @@ def predict_using_bc_with_0approx(
     meta["commit"] = "peer-memory" if sess.peer is not None else ("all-reduce" if comm.world > 1 else "local")
     sess.close()
     _mark("sweeps")
-    y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format)
+    y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format, prefill)
     _mark("output")
     if return_meta:
         meta["time"] = time() - meta["time"]
@@ -567,12 +569,12 @@ def _bca_k0_dense(y_proba, binary_metric_func, metric_id, beta, eps, aggregation
     return y_pred
 
 
-def _finish_pred(y_proba, pred: torch.Tensor, m: int, y_pred_format: str):
+def _finish_pred(y_proba, pred: torch.Tensor, m: int, y_pred_format: str, prefill=None):
     if y_pred_format == "indices":
         return pred if isinstance(y_proba, torch.Tensor) and y_proba.is_cuda else pred.cpu().numpy()
     if isinstance(y_proba, csr_matrix):
         return dev.compact_to_csr_like(y_proba, pred, reference_padding=False)
-    return dev.compact_to_dense_like(y_proba, pred, m)
+    return dev.compact_to_dense_like(y_proba, pred, m, prefill=prefill)
 
 
 # ------------------------------------------------------------------------------------------

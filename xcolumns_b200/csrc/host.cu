@@ -1,6 +1,8 @@
 // Host-side helpers of the boundary (no device code): materialising the dense 0/1 prediction
 // matrix the reference API returns for dense inputs.  For AmazonCat-13K-shape outputs this is a
 // 16 GB host write (first-touch page faults + zeroing); it is spread over host threads.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <cstring>
 #include <thread>
@@ -11,11 +13,12 @@
 namespace {
 
 template <typename TO, typename TV>
-void fill_rows(TO *out, int64_t ld, int64_t m, const int32_t *idx, const TV *val, int k, int64_t r0, int64_t r1)
+void fill_rows(TO *out, int64_t ld, int64_t m, const int32_t *idx, const TV *val, int k, int64_t r0, int64_t r1,
+               bool zero)
 {
     for (int64_t i = r0; i < r1; ++i) {
         TO *row = out + i * ld;
-        std::memset(row, 0, sizeof(TO) * (size_t)m);
+        if (zero) std::memset(row, 0, sizeof(TO) * (size_t)m);
         for (int t = 0; t < k; ++t) {
             int j = idx[i * k + t];
             if (j >= 0 && j < m) row[j] = val ? (TO)val[i * k + t] : (TO)1;
@@ -24,7 +27,8 @@ void fill_rows(TO *out, int64_t ld, int64_t m, const int32_t *idx, const TV *val
 }
 
 template <typename TO, typename TV>
-int fill_threads(void *out, int64_t n, int64_t m, int64_t ld, const int32_t *idx, const void *val, int k, int nthreads)
+int fill_threads(void *out, int64_t n, int64_t m, int64_t ld, const int32_t *idx, const void *val, int k, int nthreads,
+                 bool zero)
 {
     if (nthreads < 1) nthreads = 1;
     int64_t chunk = (n + nthreads - 1) / nthreads;
@@ -32,10 +36,29 @@ int fill_threads(void *out, int64_t n, int64_t m, int64_t ld, const int32_t *idx
     for (int t = 0; t < nthreads; ++t) {
         int64_t r0 = t * chunk, r1 = std::min(n, r0 + chunk);
         if (r0 >= r1) break;
-        th.emplace_back(fill_rows<TO, TV>, (TO *)out, ld, m, idx, (const TV *)val, k, r0, r1);
+        th.emplace_back(fill_rows<TO, TV>, (TO *)out, ld, m, idx, (const TV *)val, k, r0, r1, zero);
     }
     for (auto &x : th) x.join();
     return XC_OK;
+}
+
+int default_threads()
+{
+    unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(hc ? hc : 1, 32);
+}
+
+int fill_dispatch(void *out_host, int out_dtype, int64_t n, int64_t m, int64_t ld, const int32_t *idx_host,
+                  const void *val_host, int val_dtype, int k, int nthreads, bool zero)
+{
+    if (!out_host || !idx_host || n < 0 || m <= 0 || ld < m || k < 1) return XC_ERR_INVALID;
+    if (nthreads <= 0) nthreads = default_threads();
+    if ((zero ? n * m : n * (int64_t)k) < (1 << 22)) nthreads = 1;
+    if (out_dtype == XC_F32 && (!val_host || val_dtype == XC_F32)) return fill_threads<float, float>(out_host, n, m, ld, idx_host, val_host, k, nthreads, zero);
+    if (out_dtype == XC_F32 && val_dtype == XC_F64) return fill_threads<float, double>(out_host, n, m, ld, idx_host, val_host, k, nthreads, zero);
+    if (out_dtype == XC_F64 && (!val_host || val_dtype == XC_F64)) return fill_threads<double, double>(out_host, n, m, ld, idx_host, val_host, k, nthreads, zero);
+    if (out_dtype == XC_F64 && val_dtype == XC_F32) return fill_threads<double, float>(out_host, n, m, ld, idx_host, val_host, k, nthreads, zero);
+    return XC_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -44,15 +67,39 @@ extern "C" int xc_fill_pred_dense_host(void *out_host, int out_dtype, int64_t n,
                                        const int32_t *idx_host, const void *val_host, int val_dtype, int k,
                                        int nthreads)
 {
-    if (!out_host || !idx_host || n < 0 || m <= 0 || ld < m || k < 1) return XC_ERR_INVALID;
-    if (nthreads <= 0) {
-        unsigned hc = std::thread::hardware_concurrency();
-        nthreads = (int)std::min<unsigned>(hc ? hc : 1, 32);
+    return fill_dispatch(out_host, out_dtype, n, m, ld, idx_host, val_host, val_dtype, k, nthreads, true);
+}
+
+// the scatter alone, into a matrix that xc_zero_host already cleared (the zero-fill of a 16 GB result
+// runs on host threads WHILE the scores are uploaded and swept; only this tiny step is left at the end)
+extern "C" int xc_scatter_pred_dense_host(void *out_host, int out_dtype, int64_t n, int64_t m, int64_t ld,
+                                          const int32_t *idx_host, const void *val_host, int val_dtype, int k,
+                                          int nthreads)
+{
+    return fill_dispatch(out_host, out_dtype, n, m, ld, idx_host, val_host, val_dtype, k, nthreads, false);
+}
+
+extern "C" int xc_zero_host(void *p, int64_t bytes, int nthreads)
+{
+    if (!p || bytes < 0) return XC_ERR_INVALID;
+    if (nthreads <= 0) nthreads = default_threads();
+    if (bytes < (1 << 24)) nthreads = 1;
+#ifdef MADV_HUGEPAGE
+    // fresh anonymous memory: ask for transparent huge pages so that first touch costs one fault per
+    // 2 MB instead of one per 4 KB (the page faults, not the stores, dominate a 16 GB clear)
+    {
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(p) + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + (uintptr_t)bytes) & ~(uintptr_t)((2u << 20) - 1);
+        if (hi > lo) madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
     }
-    if (n * m < (1 << 22)) nthreads = 1;
-    if (out_dtype == XC_F32 && (!val_host || val_dtype == XC_F32)) return fill_threads<float, float>(out_host, n, m, ld, idx_host, val_host, k, nthreads);
-    if (out_dtype == XC_F32 && val_dtype == XC_F64) return fill_threads<float, double>(out_host, n, m, ld, idx_host, val_host, k, nthreads);
-    if (out_dtype == XC_F64 && (!val_host || val_dtype == XC_F64)) return fill_threads<double, double>(out_host, n, m, ld, idx_host, val_host, k, nthreads);
-    if (out_dtype == XC_F64 && val_dtype == XC_F32) return fill_threads<double, float>(out_host, n, m, ld, idx_host, val_host, k, nthreads);
-    return XC_ERR_UNSUPPORTED;
+#endif
+    const int64_t chunk = ((bytes + nthreads - 1) / nthreads + 4095) & ~(int64_t)4095;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t b0 = t * chunk, b1 = std::min(bytes, b0 + chunk);
+        if (b0 >= b1) break;
+        th.emplace_back([=] { std::memset(static_cast<uint8_t *>(p) + b0, 0, (size_t)(b1 - b0)); });
+    }
+    for (auto &x : th) x.join();
+    return XC_OK;
 }

@@ -111,16 +111,17 @@ def predict_weighted_per_instance(
         else:
             y_pred = _threshold_csr(y_proba, c, ad, bd, th, dtype)
     else:
+        if k > m:
+            raise ValueError(f"k={k} is larger than the number of labels m={m}")
+        prefill = dev.DenseOutputPrefill.start(y_proba, n, m, dtype) if k > 0 else None
         d = dev.dense_to_device(y_proba, device)
         gdt = _gain_dtype(d.torch_dtype, a, b)
         g_code = XC_F32 if gdt == torch.float32 else XC_F64
         ad = dev.vec_to_device(a, device, gdt, m, "a")
         bd = dev.vec_to_device(b, device, gdt, m, "b")
         if k > 0:
-            if k > m:
-                raise ValueError(f"k={k} is larger than the number of labels m={m}")
             idx, vals = topk_dense_device(d, k, ad, bd, g_code, want_vals=keep_scores)
-            y_pred = dev.compact_to_dense_like(y_proba, idx, m, out_dtype=dtype, vals=vals)
+            y_pred = dev.compact_to_dense_like(y_proba, idx, m, out_dtype=dtype, vals=vals, prefill=prefill)
         else:
             y_pred = _threshold_dense(y_proba, d, ad, bd, g_code, th, dtype)
 
