@@ -312,6 +312,12 @@ XC_API int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const doub
                               const double *Ci, int64_t m, const double *alphas_dev,
                               int64_t n_alphas, double *scratch_dev, double *result_dev,
                               void *stream);
+/* ref: utils.py:187-201 (ternary_search) on the same objective, eps = alpha_tolerance
+ * (frank_wolfe.py:399-400, :627); result_dev[0] = alpha, [1] = value.  Follows the reference's
+ * comparison verbatim (it moves `high` when f(mid1) < f(mid2)).                                  */
+XC_API int xc_fw_alpha_ternary(xc_ctx *ctx, const xc_metric_params *p, const double *C,
+                               const double *Ci, int64_t m, double eps, double *result_dev,
+                               void *stream);
 /* C = (1 - alpha) C + alpha Ci on the 4 stacked m-vectors, alpha read from device memory */
 XC_API int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4,
                          const double *alpha_dev, void *stream);
@@ -327,7 +333,8 @@ XC_API int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4,
  *   finish: first != 0: Cm = confusion vectors of classifier 0, scal[0] = metric(Cm).  Otherwise
  *           Ci = confusion vectors of classifier i, scal[1] = metric(Ci), scal[2..3] = line search
  *           (alphas_dev != NULL) or the fixed step (alpha passed in fixed_alpha), Cm = (1-a) Cm + a Ci,
- *           scal[4] = metric(Cm).  In both cases, when a_next/b_next are given, the NEXT classifier
+ *           scal[4] = metric(Cm); ternary_eps > 0 selects the ternary search instead of the grid.
+ *           In both cases, when a_next/b_next are given, the NEXT classifier
  *           (gradient of the metric at the new Cm, :591-596) is written to them and scal_next[0]
  *           receives metric(Cm) (the next iteration's "old utility"); zero_raw != 0 clears raw.
  *           The per-label work is fused into two kernels (confusion vectors + utility +
@@ -341,7 +348,7 @@ XC_API int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int first, 
                              int skip_tn, double *Cm, double *Ci, const double *alphas_dev,
                              int64_t n_alphas, double fixed_alpha, double *scratch_dev, double *scal,
                              float *a_next, float *b_next, double *scal_next, int zero_raw,
-                             void *stream);
+                             double ternary_eps, void *stream);
 /* byte offset, inside the line-search scratch, of the control block {int count, full, slices, tiles}
  * the two-stage search leaves behind (diagnostics: number of float64 candidates)               */
 XC_API int64_t xc_fw_alpha_ctl_offset(int64_t m, int64_t n_alphas);

@@ -513,8 +513,9 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
                              init_classifier="top", maximize=True, normalize_conf_matrix=True,
                              beta=1.0, epsilon=1e-9, tolerance=1e-6, search_for_best_alpha=True,
                              alpha_tolerance=0.001, alpha_uniform_search_step=0.0001,
-                             skip_tn=False, seed=None, mix=None):
+                             skip_tn=False, seed=None, mix=None, alpha_search_algo="uniform"):
     """Returns (a, b, p, meta) with the truncation rules of frank_wolfe.py:644-670.
+    alpha_search_algo="ternary": utils.py:187-201 with eps = alpha_tolerance (:627).
     mix=(alpha, k, m): objective sum_j [(1 - alpha) tp_j / k + alpha metric_j / m] (:838-915)."""
     mid, c1, b2, eps = metric_params(metric, beta, epsilon)
 
@@ -566,11 +567,34 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
         u_i = value(Ci)
         if search_for_best_alpha:
             ba, bv = C.c_double(), C.c_double()
-            with _Mix(mix):
-                lib().orc_fw_alpha_search(
-                    C.c_int(mid), *[_p(x) for x in Cm], *[_p(x) for x in Ci], C.c_int64(m),
-                    _p(alphas), C.c_int64(alphas.size), C.c_double(c1), C.c_double(b2),
-                    C.c_double(eps), C.byref(ba), C.byref(bv))
+
+            def f_at(al):
+                """metric of (1 - al) C + al C_i (frank_wolfe.py:393-398): a one-point 'grid'"""
+                one = np.array([al], dtype=np.float64)
+                oa, ov = C.c_double(), C.c_double()
+                with _Mix(mix):
+                    lib().orc_fw_alpha_search(
+                        C.c_int(mid), *[_p(x) for x in Cm], *[_p(x) for x in Ci], C.c_int64(m),
+                        _p(one), C.c_int64(1), C.c_double(c1), C.c_double(b2), C.c_double(eps),
+                        C.byref(oa), C.byref(ov), C.c_int(1))
+                return ov.value
+
+            if alpha_search_algo == "ternary":           # utils.py:187-201, verbatim
+                low, high = 0, 1
+                while high - low > alpha_tolerance:
+                    mid1 = low + (high - low) / 3
+                    mid2 = high - (high - low) / 3
+                    if f_at(mid1) < f_at(mid2):
+                        high = mid2
+                    else:
+                        low = mid1
+                ba.value = (low + high) / 2
+            else:
+                with _Mix(mix):
+                    lib().orc_fw_alpha_search(
+                        C.c_int(mid), *[_p(x) for x in Cm], *[_p(x) for x in Ci], C.c_int64(m),
+                        _p(alphas), C.c_int64(alphas.size), C.c_double(c1), C.c_double(b2),
+                        C.c_double(eps), C.byref(ba), C.byref(bv), C.c_int(0))
             alpha = ba.value
         else:
             alpha = 2 / (i + 1)

@@ -144,10 +144,11 @@ void orc_fw_alpha_search(int metric, const double *tp, const double *fp, const d
                          const double *tn, const double *tp_i, const double *fp_i,
                          const double *fn_i, const double *tn_i, int64_t m, const double *alphas,
                          int64_t n_alphas, double c1, double beta2, double eps,
-                         double *best_alpha, double *best_val)
+                         double *best_alpha, double *best_val, int skip_zero)
 {
+    /* skip_zero: evaluate only the listed points (single-point evaluation for the ternary search) */
     double best = 0.0, bv = 0.0;
-    for (int64_t q = -1; q < n_alphas; ++q) {
+    for (int64_t q = skip_zero ? 0 : -1; q < n_alphas; ++q) {
         double al = q < 0 ? 0.0 : alphas[q];
         double s = 0.0;
         for (int64_t j = 0; j < m; ++j) {
@@ -158,7 +159,7 @@ void orc_fw_alpha_search(int metric, const double *tp, const double *fp, const d
             s += orc_binary_metric(metric, a, b, c, d, c1, beta2, eps);
         }
         s /= (double)m;
-        if (q < 0 || s > bv) { bv = s; best = al; } /* always a maximum, also when the FW
+        if (q < 0 || (skip_zero && q == 0) || s > bv) { bv = s; best = al; } /* always a maximum, also when the FW
                                                         driver minimises (frank_wolfe.py:616) */
     }
     *best_alpha = best;

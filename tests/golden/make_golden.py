@@ -253,8 +253,33 @@ def main_mixed():
     print(f"mixed: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def main_extra():
+    """extra.npz: Frank-Wolfe with alpha_search_algo="ternary" (utils.py:187-201) on the live reference."""
+    _install_shims()
+    from xcolumns import frank_wolfe as fw
+    from xcolumns import metrics as mt
+
+    from xcolumns_b200.synth import dense_probs
+
+    eta = dense_probs(400, 300, seed=1005)
+    out = {"eta": eta}
+    for name, metric, kw in (("tern_f1", mt.macro_f1_score_on_conf_matrix, dict(skip_tn=True)),
+                             ("tern_balacc", mt.macro_balanced_accuracy_on_conf_matrix, dict())):
+        clf, meta = fw.find_classifier_using_fw(eta, eta, metric, 5, max_iters=8, seed=0, alpha_search_algo="ternary",
+                                                return_meta=True, **kw)
+        out[name + "_a"], out[name + "_b"], out[name + "_p"] = clf.a, clf.b, clf.p
+        out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} alphas={out[name + '_alphas']} util={out[name + '_util']}")
+    path = os.path.join(HERE, "extra.npz")
+    np.savez_compressed(path, **out)
+    print(f"extra: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "mixed":
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        main_extra()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mixed":
         main_mixed()
     else:
         main()

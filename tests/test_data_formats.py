@@ -1,0 +1,103 @@
+"""On-disk formats (xcolumns_b200/data.py) against a literal per-token restatement of the reference's
+loaders (experiments/utils.py:112-228)."""
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+
+def _ref_txt_labels(path, header=True):
+    data, indices, indptr = [], [], [0]
+    with open(path) as f:
+        if header:
+            f.readline()
+        for line in f:
+            labels = line.split(" ")[0].split(",")
+            if len(labels) == 1 and labels[0].strip() == "":
+                indptr.append(len(indices))
+                continue
+            for l in labels:
+                indices.append(int(l))
+                data.append(1.0)
+            indptr.append(len(indices))
+    m = csr_matrix((data, indices, indptr), dtype=np.float32)
+    m.sort_indices()
+    return m
+
+
+def _ref_sparse_pred(path):
+    data, indices, indptr = [], [], [0]
+    with open(path) as f:
+        for line in f:
+            for p in line.split():
+                i, v = p.split(":")
+                indices.append(int(i))
+                data.append(float(v))
+            indptr.append(len(indices))
+    m = csr_matrix((data, indices, indptr), dtype=np.float32)
+    m.sort_indices()
+    return m
+
+
+def _same(a, b):
+    assert a.shape[0] == b.shape[0] and a.dtype == b.dtype == np.float32
+    assert (a.indptr == b.indptr).all() and (a.indices == b.indices).all() and (a.data == b.data).all()
+    assert a.has_sorted_indices
+
+
+def test_txt_labels_and_sparse_pred(tmp_path):
+    from xcolumns_b200 import data as D
+    rng = np.random.default_rng(0)
+    lab = tmp_path / "labels.txt"
+    with open(lab, "w") as f:
+        f.write("6 10 40\n")
+        for i in range(6):
+            if i == 3:
+                f.write(" 1:0.5 7:0.25\n")      # no labels on this line
+                continue
+            ls = rng.choice(40, size=rng.integers(1, 6), replace=False)   # unsorted on purpose
+            f.write(",".join(map(str, ls)) + " 0:1.0 3:0.5\n")
+    _same(D.load_txt_labels(str(lab)), _ref_txt_labels(str(lab)))
+    pred = tmp_path / "pred.txt"
+    with open(pred, "w") as f:
+        for i in range(7):
+            ls = rng.choice(50, size=rng.integers(0, 8), replace=False)
+            f.write(" ".join(f"{j}:{rng.random():.6f}" for j in ls) + "\n")
+    _same(D.load_txt_sparse_pred(str(pred)), _ref_sparse_pred(str(pred)))
+    # npy pair (LightXML) + npz cache
+    idx = np.stack([rng.choice(30, size=4, replace=False) for _ in range(5)])
+    sc = rng.random((5, 4)).astype(np.float32)
+    np.save(str(tmp_path / "lx-labels.npy"), idx)
+    np.save(str(tmp_path / "lx-scores.npy"), sc)
+    got = D.load_npy_sparse_pred(str(tmp_path / "lx"))
+    ref = csr_matrix((sc.flatten(), idx.flatten(), np.arange(6) * 4), dtype=np.float32)
+    ref.sort_indices()
+    _same(got, ref)
+    calls = []
+
+    def loader(p):
+        calls.append(p)
+        return D.load_npy_sparse_pred(p)
+
+    c1 = D.load_cache_npz_file(str(tmp_path / "lx"), loader)
+    c2 = D.load_cache_npz_file(str(tmp_path / "lx"), loader)
+    assert len(calls) == 1
+    _same(c1, c2)
+
+
+@pytest.mark.gpu
+def test_full_pred_sparsifier(tmp_path):
+    """dense .npy -> top-k CSR on the GPU == the reference's np.partition route on tie-free scores"""
+    from xcolumns_b200 import data as D
+    from xcolumns_b200.synth import dense_probs
+    eta = dense_probs(300, 900, seed=3)
+    path = str(tmp_path / "full.npy")
+    np.save(path, eta)
+    got = D.load_npy_full_pred(path, keep_top_k=20)
+    vals = -np.partition(-eta, 20, axis=1)[:, :20]
+    idx = np.argpartition(-eta, 20, axis=1)[:, :20]
+    ref = csr_matrix((vals.flatten(), idx.flatten(), np.arange(301) * 20), dtype=np.float32, shape=eta.shape)
+    ref.sort_indices()
+    assert got.shape == eta.shape
+    _same(got, ref)
+    with pytest.raises(ValueError):
+        D.sparsify_top_k(eta, 0)

@@ -534,3 +534,27 @@ def test_dense_output_prefill_path(xb, oracle, monkeypatch):
     w = xb.predict_weighted_per_instance(torch.from_numpy(eta), 4, keep_scores=True, dtype=torch.float64)
     assert isinstance(w, torch.Tensor) and w.dtype == torch.float64 and ((w != 0).sum(1) == 4).all()
     assert started == [True, True, True]
+
+
+@pytest.mark.gpu
+def test_fw_ternary_search(xb, golden, oracle):
+    """ternary line search: golden run of the live reference + step-by-step agreement with the oracle on a
+    run where the (verbatim, minimum-seeking) search keeps the iteration going"""
+    from xcolumns_b200 import metrics as M
+    from xcolumns_b200.synth import dense_probs
+    g = golden("extra")
+    eta = g["eta"]
+    for name, metric, kw in (("tern_f1", M.macro_f1_score_on_conf_matrix, dict(skip_tn=True)),
+                             ("tern_balacc", M.macro_balanced_accuracy_on_conf_matrix, dict())):
+        clf, meta = xb.find_classifier_using_fw(eta, eta, metric, 5, max_iters=8, seed=0, alpha_search_algo="ternary",
+                                                return_meta=True, **kw)
+        assert len(meta["utilities"]) == len(g[name + "_util"]) and clf.a.shape == g[name + "_a"].shape
+        assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+    eta2 = dense_probs(500, 260, seed=123)
+    kw = dict(max_iters=5, seed=0, alpha_search_algo="ternary", alpha_tolerance=1e-3, tolerance=-np.inf, maximize=False,
+              skip_tn=True)
+    clf, meta = xb.find_classifier_using_fw(eta2, eta2, M.macro_f1_score_on_conf_matrix, 5, return_meta=True, **kw)
+    oa, ob, op, ometa = oracle.find_classifier_using_fw(eta2, eta2, "f1", 5, **kw)
+    assert len(meta["alphas"]) == len(ometa["alphas"])
+    assert np.allclose(meta["alphas"], ometa["alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], ometa["utilities"], rtol=0, atol=1e-6)

@@ -182,3 +182,15 @@ def test_fw_mixed(golden, oracle, name, metric, alpha):
     assert len(meta["utilities"]) == len(g[name + "_util"])
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
     assert a.shape == g[name + "_a"].shape
+
+
+@pytest.mark.parametrize("name,metric,skip_tn", [("tern_f1", "f1", True), ("tern_balacc", "balanced_accuracy", False)])
+def test_fw_ternary_search(golden, oracle, name, metric, skip_tn):
+    """alpha_search_algo="ternary" (utils.py:187-201, which narrows towards the SMALLER probe): the
+    restatement follows it verbatim, so it stops where the live reference stops"""
+    g = golden("extra")
+    eta = g["eta"]
+    a, b, p, meta = oracle.find_classifier_using_fw(eta, eta, metric, 5, max_iters=8, skip_tn=skip_tn, seed=0,
+                                                    alpha_search_algo="ternary")
+    assert len(meta["utilities"]) == len(g[name + "_util"]) and a.shape == g[name + "_a"].shape
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)

@@ -70,7 +70,8 @@ _SIGNATURES = {
     "xc_fw_combine": [_vp, _vp, _i64, _vp, _vp],
     "xc_fw_step_begin": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _int, _vp, _int, _vp],
     "xc_fw_step_finish": [_MP, _int, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, _vp,
-                          _vp, _int, _vp],
+                          _vp, _int, _dbl, _vp],
+    "xc_fw_alpha_ternary": [_MP, _vp, _vp, _i64, _dbl, _vp, _vp],
 }
 
 _lib = None

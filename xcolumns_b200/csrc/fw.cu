@@ -680,6 +680,56 @@ fw_alpha_pick_kernel(const double *__restrict__ vals, int64_t vstride, int64_t m
     }
 }
 
+// ---- ternary search (utils.py:187-201 as called at frank_wolfe.py:399-400) ------------------------------
+// One CTA walks the reference's loop: both probes of a round are reduced over the labels in a fixed
+// order (thread-strided partial sums, shuffle tree, warp order), so the sequence of decisions -- and
+// with it the returned step -- is reproducible.  ~18 rounds for eps = 1e-3.
+__global__ void __launch_bounds__(1024)
+fw_alpha_ternary_kernel(xc_metric_params p, const double *__restrict__ C, const double *__restrict__ Ci, int64_t m,
+                        double eps, double *result)
+{
+    __shared__ double sm[2][32];
+    const bool use_tn = p.metric >= XC_METRIC_BALANCED_ACC && p.metric <= XC_METRIC_HMEAN;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    auto eval2 = [&](double a1, double a2, double &v1, double &v2) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int64_t j = threadIdx.x; j < m; j += 1024) {
+            const double tp = C[j], fp = C[m + j], fn = C[2 * m + j], tn = use_tn ? C[3 * m + j] : 0.0;
+            const double tpi = Ci[j], fpi = Ci[m + j], fni = Ci[2 * m + j], tni = use_tn ? Ci[3 * m + j] : 0.0;
+            const double b1 = 1.0 - a1, b2 = 1.0 - a2;
+            s1 += xc_metric_eval(p, b1 * tp + a1 * tpi, b1 * fp + a1 * fpi, b1 * fn + a1 * fni, b1 * tn + a1 * tni);
+            s2 += xc_metric_eval(p, b2 * tp + a2 * tpi, b2 * fp + a2 * fpi, b2 * fn + a2 * fni, b2 * tn + a2 * tni);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        __syncthreads();  // previous round's readers are done with sm
+        if (lane == 0) { sm[0][wid] = s1; sm[1][wid] = s2; }
+        __syncthreads();
+        v1 = 0.0;
+        v2 = 0.0;
+        for (int w = 0; w < 32; ++w) { v1 += sm[0][w]; v2 += sm[1][w]; }
+        const double div = p.mix ? 1.0 : (double)m;
+        v1 = v1 / div;
+        v2 = v2 / div;
+    };
+    double low = 0.0, high = 1.0;
+    while (high - low > eps) {
+        const double mid1 = low + (high - low) / 3.0;
+        const double mid2 = high - (high - low) / 3.0;
+        double f1, f2;
+        eval2(mid1, mid2, f1, f2);
+        if (f1 < f2) high = mid2;  // (sic) utils.py:194-197
+        else low = mid1;
+    }
+    const double best = (low + high) / 2.0;
+    double fb, dummy;
+    eval2(best, best, fb, dummy);
+    if (threadIdx.x == 0) {
+        result[0] = best;
+        result[1] = fb;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 fw_combine_kernel(double *C, const double *Ci, int64_t m4, const double *alpha_dev)
 {
@@ -1058,6 +1108,16 @@ extern "C" int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const 
     return alpha_search_launch(ctx, p, C, Ci, m, alphas_dev, n_alphas, s, result_dev, st);
 }
 
+extern "C" int xc_fw_alpha_ternary(xc_ctx *ctx, const xc_metric_params *p, const double *C, const double *Ci,
+                                   int64_t m, double eps, double *result_dev, void *stream)
+{
+    if (!ctx || !p || !C || !Ci || !result_dev || m <= 0 || !(eps > 0.0)) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
+    fw_alpha_ternary_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*p, C, Ci, m, eps, result_dev);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
 extern "C" int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4, const double *alpha_dev,
                              void *stream)
 {
@@ -1110,7 +1170,7 @@ extern "C" int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int fir
                                  const double *colsum, int64_t m, double n_global, int normalize, int skip_tn,
                                  double *Cm, double *Ci, const double *alphas_dev, int64_t n_alphas,
                                  double fixed_alpha, double *scratch_dev, double *scal, float *a_next, float *b_next,
-                                 double *scal_next, int zero_raw, void *stream)
+                                 double *scal_next, int zero_raw, double ternary_eps, void *stream)
 {
     if (!ctx || !p || !raw || !colsum || !Cm || !Ci || !scal || m <= 0) return XC_ERR_INVALID;
     if ((a_next == nullptr) != (b_next == nullptr)) return XC_ERR_INVALID;
@@ -1129,7 +1189,8 @@ extern "C" int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int fir
         }
         return XC_OK;
     }
-    const bool search = alphas_dev != nullptr;
+    const bool ternary = ternary_eps > 0.0;
+    const bool search = alphas_dev != nullptr && !ternary;
     if (search && !scratch_dev) return XC_ERR_INVALID;
     AlphaScratch s = alpha_scratch(scratch_dev, m, n_alphas);
     const bool two_stage = search && alpha_two_stage(p, n_alphas);
@@ -1137,7 +1198,10 @@ extern "C" int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int fir
                                               two_stage ? s.lin : nullptr, s.linE, scal + 1, ctx->red_partials,
                                               ctx->red_counter);
     XC_LAUNCHED(ctx);
-    if (search) {
+    if (ternary) {
+        int rc = xc_fw_alpha_ternary(ctx, p, Cm, Ci, m, ternary_eps, scal + 2, stream);
+        if (rc) return rc;
+    } else if (search) {
         int rc = alpha_search_launch(ctx, p, Cm, Ci, m, alphas_dev, n_alphas, s, scal + 2, st);
         if (rc) return rc;
     } else {

@@ -124,10 +124,11 @@ def find_classifier_using_fw(
     _check_k(k)
     if k <= 0:
         raise NotImplementedError("xcolumns_b200: Frank-Wolfe without a budget (k=0) is not implemented on the GPU path yet")
-    if alpha_search_algo not in ("uniform",) and search_for_best_alpha:
-        if alpha_search_algo == "ternary":
-            raise NotImplementedError("xcolumns_b200: alpha_search_algo='ternary' is not implemented; use 'uniform'")
+    if alpha_search_algo not in ("uniform", "ternary") and search_for_best_alpha:
         raise ValueError(f"Unknown search algorithm {alpha_search_algo}")
+    ternary_eps = float(alpha_tolerance) if (search_for_best_alpha and alpha_search_algo == "ternary") else 0.0
+    if ternary_eps < 0 or (search_for_best_alpha and alpha_search_algo == "ternary" and not ternary_eps > 0):
+        raise ValueError("alpha_search_algo='ternary' needs alpha_tolerance > 0 (it is the search's epsilon)")
     metric_id, beta, eps = M.resolve_macro_metric(metric_func, metric_kwargs)
     n, m = y_proba.shape
     device = dev.pick_device(y_proba, y_true)
@@ -253,7 +254,7 @@ def find_classifier_using_fw(
                      dev.ptr(Ci), dev.ptr(alphas_dev) if search_for_best_alpha else None, n_alphas,
                      C.c_double(2 / (i + 1)), dev.ptr(vals_dev), sc,
                      rowp(A_dev, i + 1) if has_next else None, rowp(B_dev, i + 1) if has_next else None,
-                     C.c_void_p(scal_all[i + 1].data_ptr()), 1, sp())
+                     C.c_void_p(scal_all[i + 1].data_ptr()), 1, C.c_double(ternary_eps), sp())
             host_all[i].copy_(scal_all[i], non_blocking=True)
             if debug_ctl:
                 w = vals_dev.view(torch.int32)[ctl_off // 4: ctl_off // 4 + 32].cpu().tolist()
@@ -277,7 +278,10 @@ def find_classifier_using_fw(
             ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, dev.ptr(a_dev), dev.ptr(b_dev), sptr(0), sp())
             iterate(Ci)
             ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Ci), m, None, None, sptr(1), sp())
-            if search_for_best_alpha:
+            if ternary_eps > 0:
+                ctx.call("xc_fw_alpha_ternary", C.byref(params), dev.ptr(Cm), dev.ptr(Ci), m, C.c_double(ternary_eps),
+                         sptr(2), sp())
+            elif search_for_best_alpha:
                 ctx.call("xc_fw_alpha_search", C.byref(params), dev.ptr(Cm), dev.ptr(Ci), m, dev.ptr(alphas_dev),
                          int(alphas.size), dev.ptr(vals_dev), sptr(2), sp())
             else:
