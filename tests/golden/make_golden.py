@@ -271,6 +271,26 @@ def main_extra():
         out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
         out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
         print(f"  {name}: iters={meta['iters']} alphas={out[name + '_alphas']} util={out[name + '_util']}")
+    # closed-form weighted strategies (weighted_prediction.py:223-560)
+    from xcolumns import weighted_prediction as wp
+    from xcolumns_b200.synth import csr_probs
+    etaw = dense_probs(120, 400, seed=21)
+    pri = etaw.mean(0).astype(np.float64)
+    ycsr = csr_probs(90, 1200, 30, seed=22, ragged=True)
+    pric = np.asarray(ycsr.mean(0)).ravel().astype(np.float64) + 1e-3
+    out.update({"w_eta": etaw, "w_pri": pri, "w_data": ycsr.data, "w_indices": ycsr.indices, "w_indptr": ycsr.indptr,
+                "w_shape": np.array(ycsr.shape), "w_pric": pric})
+    out["w_recall"] = pred_to_idx(wp.predict_optimizing_macro_recall(etaw, 5, pri), 5)
+    out["w_balacc"] = pred_to_idx(wp.predict_optimizing_macro_balanced_accuracy(etaw, 5, pri), 5)
+    out["w_balacc_k0"] = np.asarray(wp.predict_optimizing_macro_balanced_accuracy(etaw, 0, pri) != 0, dtype=np.uint8)
+    out["w_log"] = pred_to_idx(wp.predict_log_weighted_per_instance(etaw, 4, pri), 4)
+    out["w_pow"] = pred_to_idx(wp.predict_power_law_weighted_per_instance(etaw, 5, pri, 0.5), 5)
+    out["w_psp"] = pred_to_idx(wp.predict_optimizing_instance_propensity_scored_precision(
+        etaw, 3, propensities=(0.2 + 0.8 * pri / pri.max()).copy()), 3)
+    r = wp.predict_optimizing_macro_balanced_accuracy(ycsr, 5, pric)
+    out["w_balacc_csr_data"], out["w_balacc_csr_indices"], out["w_balacc_csr_indptr"] = r.data, r.indices, r.indptr
+    r = wp.predict_optimizing_macro_recall(ycsr, 5, pric)
+    out["w_recall_csr_data"], out["w_recall_csr_indices"], out["w_recall_csr_indptr"] = r.data, r.indices, r.indptr
     path = os.path.join(HERE, "extra.npz")
     np.savez_compressed(path, **out)
     print(f"extra: {os.path.getsize(path) / 1024:.0f} KiB")

@@ -558,3 +558,32 @@ def test_fw_ternary_search(xb, golden, oracle):
     assert len(meta["alphas"]) == len(ometa["alphas"])
     assert np.allclose(meta["alphas"], ometa["alphas"], rtol=0, atol=1e-9)
     assert np.allclose(meta["utilities"], ometa["utilities"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_closed_form_weighted_strategies_golden(xb, golden):
+    """weighted_prediction.py:223-560 (priors / propensities -> weights -> weighted top-k) vs the live reference"""
+    g = golden("extra")
+    eta, pri = g["w_eta"], g["w_pri"]
+    assert (_idx(xb.predict_optimizing_macro_recall(eta, 5, pri), 5) == g["w_recall"]).all()
+    assert (_idx(xb.predict_optimizing_macro_balanced_accuracy(eta, 5, pri), 5) == g["w_balacc"]).all()
+    k0 = xb.predict_optimizing_macro_balanced_accuracy(eta, 0, pri)
+    assert ((k0 != 0).astype(np.uint8) == g["w_balacc_k0"]).all()
+    assert (_idx(xb.predict_log_weighted_per_instance(eta, 4, pri), 4) == g["w_log"]).all()
+    assert (_idx(xb.predict_power_law_weighted_per_instance(eta, 5, pri, 0.5), 5) == g["w_pow"]).all()
+    prop = (0.2 + 0.8 * pri / pri.max()).copy()
+    assert (_idx(xb.predict_optimizing_instance_propensity_scored_precision(eta, 3, propensities=prop), 3)
+            == g["w_psp"]).all()
+    assert (xb.predict_optimizing_instance_precision(eta, 5) == xb.predict_top_k(eta, 5)).all()
+    y = csr_matrix((g["w_data"], g["w_indices"], g["w_indptr"]), shape=tuple(g["w_shape"]))
+    for name, fn in (("w_balacc_csr", xb.predict_optimizing_macro_balanced_accuracy),
+                     ("w_recall_csr", xb.predict_optimizing_macro_recall)):
+        r = fn(y, 5, g["w_pric"])
+        assert isinstance(r, csr_matrix) and r.dtype == y.dtype
+        assert (r.indptr == g[name + "_indptr"]).all(), name
+        assert (r.indices == g[name + "_indices"]).all(), name
+        assert (r.data == g[name + "_data"]).all(), name
+    with pytest.raises(ValueError):
+        xb.predict_optimizing_macro_recall(eta, 5, pri[:-1])
+    with pytest.raises(ValueError):
+        xb.predict_optimizing_instance_precision(eta, 0)

@@ -39,6 +39,15 @@ from .frank_wolfe import (  # noqa: F401
     find_classifier_using_fw,
     predict_using_randomized_weighted_classifier,
 )
-from .weighted_prediction import predict_top_k, predict_weighted_per_instance  # noqa: F401
+from .weighted_prediction import (  # noqa: F401
+    predict_log_weighted_per_instance,
+    predict_optimizing_instance_precision,
+    predict_optimizing_instance_propensity_scored_precision,
+    predict_optimizing_macro_balanced_accuracy,
+    predict_optimizing_macro_recall,
+    predict_power_law_weighted_per_instance,
+    predict_top_k,
+    predict_weighted_per_instance,
+)
 
 __version__ = "0.1.0"

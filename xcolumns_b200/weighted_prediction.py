@@ -174,3 +174,100 @@ def predict_top_k(
     """Top-k labels per row -- optimal for precision@k / nDCG@k
     (xcolumns/weighted_prediction.py:196-220)."""
     return predict_weighted_per_instance(y_proba, k=k, dtype=dtype, keep_scores=keep_scores, return_meta=return_meta)
+
+
+# ------------------------------------------------------------------------------------------
+# closed-form weighted strategies (xcolumns/weighted_prediction.py:223-560): per-label weights from
+# priors / propensities, then the weighted top-k kernel
+# ------------------------------------------------------------------------------------------
+
+def _check_vec(v, m: int, name: str):
+    if v.shape[0] != m:
+        raise ValueError(f"{name} must be of shape (y_proba[1],)")
+
+
+def predict_optimizing_macro_recall(y_proba: Matrix, k: int, priors: DenseMatrix, epsilon: float = 1e-6,
+                                    keep_scores: bool = False, dtype: Optional[DType] = None, return_meta: bool = False,
+                                    return_weights: bool = False):
+    """a = 1 / (priors + epsilon) (xcolumns/weighted_prediction.py:223-264)."""
+    _check_vec(priors, y_proba.shape[1], "priors")
+    return predict_weighted_per_instance(y_proba, k=k, a=1.0 / (priors + epsilon), dtype=dtype, keep_scores=keep_scores,
+                                         return_meta=return_meta, return_weights=return_weights)
+
+
+def predict_optimizing_macro_balanced_accuracy(y_proba: Matrix, k: int, priors: DenseMatrix, epsilon: float = 1e-6,
+                                               dtype: Optional[DType] = None, return_meta: bool = False):
+    """Optimal strategy for macro balanced accuracy (xcolumns/weighted_prediction.py:267-368):
+    gains = eta / pi - (1 - eta) / (1 - pi) with pi = priors + epsilon.  The gain is affine in eta,
+    g = eta * (1/pi + 1/(1-pi)) - 1/(1-pi); it is evaluated in that form (one multiply-add per element
+    instead of two divisions), which differs from the reference's expression by <= 1 ulp of the gain."""
+    _check_vec(priors, y_proba.shape[1], "priors")
+    if not isinstance(y_proba, (np.ndarray, torch.Tensor, csr_matrix)):
+        raise ValueError("y_proba must be either np.ndarray, torch.Tensor, or csr_matrix")
+    if return_meta:
+        meta = {"iters": 1, "time": time()}
+    pri = priors + epsilon
+    a = 1.0 / pri + 1.0 / (1 - pri)
+    b = -1.0 / (1 - pri)
+    if isinstance(y_proba, csr_matrix) and y_proba.dtype != np.float64:
+        # the reference forms the CSR gains in float64 (float32 data / float64 marginals,
+        # numba_csr_functions.py:679); the CSR top-k kernel works in the data dtype, so widen the data
+        y64 = csr_matrix((y_proba.data.astype(np.float64), y_proba.indices, y_proba.indptr), shape=y_proba.shape)
+        y_pred = predict_weighted_per_instance(y64, k=k, th=0.0, a=np.asarray(a, dtype=np.float64),
+                                               b=np.asarray(b, dtype=np.float64),
+                                               dtype=y_proba.dtype if dtype is None else dtype)
+    else:
+        y_pred = predict_weighted_per_instance(y_proba, k=k, th=0.0, a=a, b=b, dtype=dtype)
+    if return_meta:
+        meta["time"] = time() - meta["time"]
+        return y_pred, meta
+    return y_pred
+
+
+def predict_log_weighted_per_instance(y_proba: Matrix, k: int, priors: DenseMatrix, epsilon: float = 1e-6,
+                                      keep_scores: bool = False, dtype: Optional[DType] = None,
+                                      return_meta: bool = False, return_weights: bool = False):
+    """a = -log(priors + epsilon) (xcolumns/weighted_prediction.py:371-416)."""
+    _check_vec(priors, y_proba.shape[1], "priors")
+    pri = priors + epsilon
+    weights = -torch.log(pri) if isinstance(pri, torch.Tensor) else -np.log(pri)
+    return predict_weighted_per_instance(y_proba, k=k, a=weights, keep_scores=keep_scores, dtype=dtype,
+                                         return_meta=return_meta, return_weights=return_weights)
+
+
+def predict_power_law_weighted_per_instance(y_proba: Matrix, k: int, priors: DenseMatrix, beta: float,
+                                            epsilon: float = 1e-6, keep_scores: bool = False,
+                                            dtype: Optional[DType] = None, return_meta: bool = False,
+                                            return_weights: bool = False):
+    """a = (priors + epsilon) ** -beta (xcolumns/weighted_prediction.py:419-465)."""
+    _check_vec(priors, y_proba.shape[1], "priors")
+    return predict_weighted_per_instance(y_proba, k=k, a=(priors + epsilon) ** -beta, keep_scores=keep_scores,
+                                         dtype=dtype, return_meta=return_meta, return_weights=return_weights)
+
+
+def predict_optimizing_instance_precision(y_proba: Matrix, k: int, keep_scores: bool = False,
+                                          dtype: Optional[DType] = None, return_meta: bool = False):
+    """Plain top-k: optimal for precision@k and nDCG@k (xcolumns/weighted_prediction.py:468-497)."""
+    if k <= 0:
+        raise ValueError("k must be > 0")
+    return predict_top_k(y_proba, k=k, keep_scores=keep_scores, dtype=dtype, return_meta=return_meta)
+
+
+def predict_optimizing_instance_propensity_scored_precision(y_proba: Matrix, k: int,
+                                                            inverse_propensities: Optional[DenseMatrix] = None,
+                                                            propensities: Optional[DenseMatrix] = None,
+                                                            keep_scores: bool = False, dtype: Optional[DType] = None,
+                                                            return_meta: bool = False, return_weights: bool = False):
+    """a = inverse propensities (xcolumns/weighted_prediction.py:500-560; like there, zero entries of
+    `propensities` are set to 1 IN PLACE before inverting)."""
+    m = y_proba.shape[1]
+    if inverse_propensities is not None:
+        _check_vec(inverse_propensities, m, "inverse_propensities")
+    elif propensities is not None:
+        _check_vec(propensities, m, "propensities")
+        propensities[propensities == 0] = 1.0
+        inverse_propensities = 1.0 / propensities
+    else:
+        raise ValueError("either inverse_propensities or propensities must be provided")
+    return predict_weighted_per_instance(y_proba, k=k, a=inverse_propensities, keep_scores=keep_scores, dtype=dtype,
+                                         return_meta=return_meta, return_weights=return_weights)
