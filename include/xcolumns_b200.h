@@ -69,6 +69,8 @@ typedef struct {
     int32_t skip_tn;   /* 1: tn is a constant -1 vector (ref: confusion_matrix.py:391-393)     */
     int32_t mix;       /* 1: mixed utility (ref: block_coordinate.py:848-1045, frank_wolfe.py:838-915): */
                        /*    ((1 - mix_alpha) * (tp / mix_k)) + ((mix_alpha * metric) / mix_m)          */
+                       /* 2: micro average, metric(tp.sum(), fp.sum(), fn.sum(), tn.sum())              */
+                       /*    (ref: metrics.py:68-100; Frank-Wolfe objective only)                       */
     double c1;         /* 1 + beta**2, computed by the host exactly like python does           */
     double beta2;      /* beta**2                                                              */
     double eps;        /* epsilon of the metric (metric_kwargs["epsilon"], default 1e-9)       */

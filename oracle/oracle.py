@@ -513,13 +513,17 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
                              init_classifier="top", maximize=True, normalize_conf_matrix=True,
                              beta=1.0, epsilon=1e-9, tolerance=1e-6, search_for_best_alpha=True,
                              alpha_tolerance=0.001, alpha_uniform_search_step=0.0001,
-                             skip_tn=False, seed=None, mix=None, alpha_search_algo="uniform"):
+                             skip_tn=False, seed=None, mix=None, alpha_search_algo="uniform", micro=False):
     """Returns (a, b, p, meta) with the truncation rules of frank_wolfe.py:644-670.
     alpha_search_algo="ternary": utils.py:187-201 with eps = alpha_tolerance (:627).
     mix=(alpha, k, m): objective sum_j [(1 - alpha) tp_j / k + alpha metric_j / m] (:838-915)."""
     mid, c1, b2, eps = metric_params(metric, beta, epsilon)
 
     def macro_metric_and_grad_mix(metric, tp, fp, fn, tn, beta=1.0, epsilon=1e-9):
+        if micro:   # metrics.py:68-100: the metric of the four sums; every label gets the same gradient
+            sums = [np.array([np.sum(x)], dtype=np.float64) for x in (tp, fp, fn, tn)]
+            v, g = macro_metric_and_grad(metric, *sums, beta=beta, epsilon=epsilon)
+            return v, tuple(np.full(m, float(x[0])) for x in g)
         v, (gtp, gfp, gfn, gtn) = macro_metric_and_grad(metric, tp, fp, fn, tn, beta=beta, epsilon=epsilon)
         if mix is None:
             return v, (gtp, gfp, gfn, gtn)
@@ -570,6 +574,8 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
 
             def f_at(al):
                 """metric of (1 - al) C + al C_i (frank_wolfe.py:393-398): a one-point 'grid'"""
+                if micro:
+                    return value([(1 - al) * x + al * y for x, y in zip(Cm, Ci)])
                 one = np.array([al], dtype=np.float64)
                 oa, ov = C.c_double(), C.c_double()
                 with _Mix(mix):
@@ -589,6 +595,14 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
                     else:
                         low = mid1
                 ba.value = (low + high) / 2
+            elif micro:                                   # utils.py:174-184 on the scalar objective
+                grid = np.concatenate([[0.0], alphas])
+                S, Si = [float(np.sum(x)) for x in Cm], [float(np.sum(x)) for x in Ci]
+                T = [np.ascontiguousarray((1 - grid) * s_ + grid * si_) for s_, si_ in zip(S, Si)]
+                vals = np.empty(grid.size, dtype=np.float64)
+                lib().orc_binary_metric_vec(C.c_int(mid), *[_p(x) for x in T], C.c_int64(grid.size), C.c_double(1.0),
+                                            C.c_double(c1), C.c_double(b2), C.c_double(eps), _p(vals))
+                ba.value = float(grid[int(np.argmax(vals))])   # argmax = first maximum = first strict improvement
             else:
                 with _Mix(mix):
                     lib().orc_fw_alpha_search(

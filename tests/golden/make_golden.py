@@ -271,6 +271,14 @@ def main_extra():
         out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
         out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
         print(f"  {name}: iters={meta['iters']} alphas={out[name + '_alphas']} util={out[name + '_util']}")
+    # micro-averaged Frank-Wolfe objectives (frank_wolfe.py:758-832)
+    for name, fn, kw in (("micro_f1", fw.find_classifier_optimizing_micro_f1_score_using_fw, {}),
+                         ("micro_balacc", fw.find_classifier_optimizing_micro_balanced_accuracy_using_fw, {})):
+        clf, meta = fn(eta, eta, 5, max_iters=5, seed=0, init_classifier="random", return_meta=True, **kw)
+        out[name + "_a"], out[name + "_b"], out[name + "_p"] = clf.a, clf.b, clf.p
+        out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} alphas={out[name + '_alphas']} util={out[name + '_util']}")
     # closed-form weighted strategies (weighted_prediction.py:223-560)
     from xcolumns import weighted_prediction as wp
     from xcolumns_b200.synth import csr_probs

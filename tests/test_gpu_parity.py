@@ -587,3 +587,21 @@ def test_closed_form_weighted_strategies_golden(xb, golden):
         xb.predict_optimizing_macro_recall(eta, 5, pri[:-1])
     with pytest.raises(ValueError):
         xb.predict_optimizing_instance_precision(eta, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,metric", [("micro_f1", "f1_score"), ("micro_balacc", "balanced_accuracy")])
+def test_fw_micro_golden(xb, golden, name, metric):
+    from xcolumns_b200 import frank_wolfe as fwm
+    g = golden("extra")
+    eta = g["eta"]
+    fn = getattr(fwm, f"find_classifier_optimizing_micro_{metric}_using_fw")
+    clf, meta = fn(eta, eta, 5, max_iters=5, seed=0, init_classifier="random", return_meta=True)
+    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+    assert clf.a.shape == g[name + "_a"].shape and np.allclose(clf.p, g[name + "_p"], atol=1e-6)
+    # every label gets the same weights (the gradient of a micro-averaged metric is label-independent)
+    assert np.allclose(clf.a[1:], clf.a[1:, :1]) and np.allclose(clf.b[1:], clf.b[1:, :1])
+    y = csr_matrix(np.where(eta > np.sort(eta, axis=1)[:, [-30]], eta, 0).astype(np.float32))
+    clf2, meta2 = fn(y, y, 5, max_iters=4, seed=0, return_meta=True)
+    assert len(meta2["utilities"]) >= 1 and clf2.a.shape[1] == eta.shape[1]

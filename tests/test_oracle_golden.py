@@ -194,3 +194,15 @@ def test_fw_ternary_search(golden, oracle, name, metric, skip_tn):
                                                     alpha_search_algo="ternary")
     assert len(meta["utilities"]) == len(g[name + "_util"]) and a.shape == g[name + "_a"].shape
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,metric,skip_tn", [("micro_f1", "f1", True), ("micro_balacc", "balanced_accuracy", False)])
+def test_fw_micro(golden, oracle, name, metric, skip_tn):
+    """micro-averaged objectives (frank_wolfe.py:758-832): metric of the summed confusion entries"""
+    g = golden("extra")
+    eta = g["eta"]
+    a, b, p, meta = oracle.find_classifier_using_fw(eta, eta, metric, 5, max_iters=5, skip_tn=skip_tn, seed=0,
+                                                    init_classifier="random", micro=True)
+    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-6)
+    assert a.shape == g[name + "_a"].shape and np.allclose(p, g[name + "_p"], atol=1e-6)

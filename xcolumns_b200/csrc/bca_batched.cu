@@ -52,7 +52,7 @@ __device__ __forceinline__ void bca_coef_of(const xc_metric_params &p, double t,
         Bs = c / (D - u);
         As = ct / D - ct / (D - u);
     }
-    if (p.mix) {
+    if (p.mix == 1) {
         // (1 - alpha) * tp / k + alpha * metric / m, summed over the labels (block_coordinate.py:848-1045):
         // the instance-precision part adds (1 - alpha) eta / (k n) to every gain
         const double w1 = (1.0 - p.mix_alpha) / (p.mix_k * p.n_div), w2 = p.mix_alpha / p.mix_m;

@@ -178,7 +178,7 @@ __device__ __forceinline__ Grad4 metric_grad(int metric, double tp, double fp, d
 __device__ __forceinline__ Grad4 metric_grad_p(const xc_metric_params &p, double tp, double fp, double fn, double tn)
 {
     Grad4 g = metric_grad(p.metric, tp, fp, fn, tn, p.c1, p.beta2, p.eps);
-    if (p.mix) {
+    if (p.mix == 1) {
         const double w = (1.0 - p.mix_alpha) * (p.mix_m / p.mix_k);
         g.v = p.mix_alpha * g.v + w * tp;
         g.gtp = p.mix_alpha * g.gtp + w;
@@ -708,7 +708,7 @@ fw_alpha_ternary_kernel(xc_metric_params p, const double *__restrict__ C, const 
         v1 = 0.0;
         v2 = 0.0;
         for (int w = 0; w < 32; ++w) { v1 += sm[0][w]; v2 += sm[1][w]; }
-        const double div = p.mix ? 1.0 : (double)m;
+        const double div = p.mix == 1 ? 1.0 : (double)m;
         v1 = v1 / div;
         v2 = v2 / div;
     };
@@ -817,6 +817,122 @@ fw_finish_kernel(xc_metric_params p, double *__restrict__ C, const double *__res
         if (value) *value = total * inv_m;
         if (value_next) *value_next = total * inv_m;
     }
+}
+
+// ---- micro-averaged objectives (metrics.py:68-100: binary_metric(tp.sum(), fp.sum(), fn.sum(), tn.sum())) ----
+// The objective only sees the four sums, its gradient is the same for every label and the line search is a
+// scalar problem: one CTA does all of it.  S = sums of the running matrix, Si = sums of the newest
+// classifier's matrix (label-strided partial sums, shuffle tree, warp order: reproducible).
+//   scal[1] = metric(Si); scal[2..3] = step (grid / ternary / fixed) and its value; scal[4] = metric of the
+//   combined sums; scal[5..6] = the classifier (a, b) every label gets next (frank_wolfe.py:591-596).
+__global__ void __launch_bounds__(1024)
+fw_micro_kernel(xc_metric_params p, const double *__restrict__ C, const double *__restrict__ Ci, int64_t m, int first,
+                const double *__restrict__ alphas, int64_t n_alphas, double fixed_alpha, double ternary_eps,
+                double *scal, double *scal_next)
+{
+    __shared__ double sm[8][32];
+    __shared__ double s_sum[8];
+    __shared__ double s_bv[32];
+    __shared__ long long s_bq[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double part[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) part[t] = 0.0;
+    for (int64_t j = threadIdx.x; j < m; j += 1024) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            part[t] += C[t * m + j];
+            if (!first) part[4 + t] += Ci[t * m + j];
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const double v = warp_sum(part[t]);
+        if (lane == 0) sm[t][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0.0;
+        for (int w = 0; w < 32; ++w) v += sm[threadIdx.x][w];
+        s_sum[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const double S[4] = {s_sum[0], s_sum[1], s_sum[2], s_sum[3]};
+    const double Si[4] = {s_sum[4], s_sum[5], s_sum[6], s_sum[7]};
+    auto f_at = [&](double a1) {
+        const double a0 = 1.0 - a1;
+        return xc_binary_metric(p.metric, a0 * S[0] + a1 * Si[0], a0 * S[1] + a1 * Si[1], a0 * S[2] + a1 * Si[2],
+                                a0 * S[3] + a1 * Si[3], p.c1, p.beta2, p.eps);
+    };
+    double alpha = 0.0, best = 0.0;
+    if (!first) {
+        if (ternary_eps > 0.0) {  // utils.py:187-201 verbatim
+            double low = 0.0, high = 1.0;
+            while (high - low > ternary_eps) {
+                const double mid1 = low + (high - low) / 3.0, mid2 = high - (high - low) / 3.0;
+                if (f_at(mid1) < f_at(mid2)) high = mid2;
+                else low = mid1;
+            }
+            alpha = (low + high) / 2.0;
+            best = f_at(alpha);
+        } else if (alphas) {      // utils.py:174-184: first strict maximum over {0} + grid
+            double bv = -INFINITY;
+            long long bq = 0x7fffffffffffffffLL;
+            for (int64_t q = threadIdx.x; q <= n_alphas; q += 1024) {
+                const double v = f_at(q == 0 ? 0.0 : alphas[q - 1]);
+                if (v > bv || (v == bv && q < bq)) { bv = v; bq = q; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(XC_FULL, bv, o);
+                const long long oq = __shfl_xor_sync(XC_FULL, bq, o);
+                if (ov > bv || (ov == bv && oq < bq)) { bv = ov; bq = oq; }
+            }
+            if (lane == 0) { s_bv[wid] = bv; s_bq[wid] = bq; }
+            __syncthreads();
+            bv = s_bv[0];
+            bq = s_bq[0];
+            for (int w = 1; w < 32; ++w)
+                if (s_bv[w] > bv || (s_bv[w] == bv && s_bq[w] < bq)) { bv = s_bv[w]; bq = s_bq[w]; }
+            if (bq == 0x7fffffffffffffffLL) bq = 0;  // all NaN: keep alpha = 0 like the reference
+            alpha = bq == 0 ? 0.0 : alphas[bq - 1];
+            best = bv;
+        } else {
+            alpha = fixed_alpha;
+            best = f_at(alpha);
+        }
+    }
+    if (threadIdx.x == 0) {
+        double T[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) T[t] = first ? S[t] : (1.0 - alpha) * S[t] + alpha * Si[t];
+        const Grad4 g = metric_grad(p.metric, T[0], T[1], T[2], T[3], p.c1, p.beta2, p.eps);
+        const double sgn = p.maximize ? 1.0 : -1.0;
+        if (first) {
+            scal[0] = g.v;
+        } else {
+            scal[1] = xc_binary_metric(p.metric, Si[0], Si[1], Si[2], Si[3], p.c1, p.beta2, p.eps);
+            scal[2] = alpha;
+            scal[3] = best;
+            scal[4] = g.v;
+        }
+        scal[5] = sgn * (((g.gtp - g.gfp) - g.gfn) + g.gtn);
+        scal[6] = sgn * (g.gfp - g.gtn);
+        if (scal_next) scal_next[0] = g.v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fw_micro_fill_kernel(const double *__restrict__ ab, int64_t m, float *__restrict__ a_next, float *__restrict__ b_next,
+                     double *__restrict__ raw_zero)
+{
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= m) return;
+    if (a_next) {
+        a_next[j] = (float)ab[0];
+        b_next[j] = (float)ab[1];
+    }
+    if (raw_zero) { raw_zero[j] = 0.0; raw_zero[m + j] = 0.0; }
 }
 
 template <typename K>
@@ -1178,6 +1294,24 @@ extern "C" int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int fir
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = reduce_grid(ctx, m);
     double *zr = zero_raw ? raw : nullptr;
+    if (p->mix == 2) {  // micro-averaged objective: scalar value / gradient / line search in one CTA
+        const unsigned gm = (unsigned)((m + kThreads - 1) / kThreads);
+        fw_make_conf_kernel<<<gm, kThreads, 0, st>>>(raw, raw + m, colsum, m, n_global, normalize, skip_tn,
+                                                     first ? Cm : Ci);
+        XC_LAUNCHED(ctx);
+        fw_micro_kernel<<<1, 1024, 0, st>>>(*p, Cm, Ci, m, first, alphas_dev, n_alphas, fixed_alpha, ternary_eps, scal,
+                                            scal_next);
+        XC_LAUNCHED(ctx);
+        if (!first) {
+            fw_combine_kernel<<<(unsigned)((4 * m + kThreads - 1) / kThreads), kThreads, 0, st>>>(Cm, Ci, 4 * m, scal + 2);
+            XC_LAUNCHED(ctx);
+        }
+        if (a_next || zr) {
+            fw_micro_fill_kernel<<<gm, kThreads, 0, st>>>(scal + 5, m, a_next, b_next, zr);
+            XC_LAUNCHED(ctx);
+        }
+        return XC_OK;
+    }
     if (first) {  // classifier 0: its confusion vectors ARE the running ones (frank_wolfe.py:564-572)
         fw_conf_prep_kernel<<<grid, 256, 0, st>>>(*p, raw, raw + m, colsum, m, n_global, normalize, skip_tn, nullptr, Cm,
                                                   nullptr, nullptr, scal + 0, ctx->red_partials, ctx->red_counter);

@@ -227,6 +227,6 @@ __device__ __forceinline__ double xc_binary_metric(int metric, double tp, double
 __device__ __forceinline__ double xc_metric_eval(const xc_metric_params &p, double tp, double fp, double fn, double tn)
 {
     double v = xc_binary_metric(p.metric, tp, fp, fn, tn, p.c1, p.beta2, p.eps);
-    if (p.mix) v = ((1.0 - p.mix_alpha) * (tp / p.mix_k)) + ((p.mix_alpha * v) / p.mix_m);
+    if (p.mix == 1) v = ((1.0 - p.mix_alpha) * (tp / p.mix_k)) + ((p.mix_alpha * v) / p.mix_m);
     return v;
 }

@@ -184,86 +184,67 @@ def find_classifier_using_fw(
 
     mix = M.resolve_mix(metric_func)
     mix_alpha, mix_k, mix_m = mix if mix is not None else (1.0, 1.0, 1.0)
+    mix_code = 2 if M.is_micro_metric(metric_func) else int(mix is not None)
     params = MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)),
-                          mix=int(mix is not None), c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps),
+                          mix=mix_code, c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps),
                           n_div=1.0, n_rows=float(n_global), mix_alpha=mix_alpha, mix_k=mix_k, mix_m=mix_m)
     Cm = torch.empty(4 * m, **f64)       # running confusion vectors [tp, fp, fn, tn]
     Ci = torch.empty(4 * m, **f64)       # confusion vectors of the newest classifier
     raw = torch.empty((2, m), **f64)     # tp_raw, cnt of one iterate
-    a_dev = torch.empty(m, dtype=torch.float32, device=device)
-    b_dev = torch.empty(m, dtype=torch.float32, device=device)
-    scal_all = torch.zeros((max_iters + 2, 8), **f64)   # per iteration: [old_u, u_i, alpha, best_val, new_u]
-    scal = scal_all[0]
+    scal_all = torch.zeros((max_iters + 2, 8), **f64)   # per iteration: [old_u, u_i, alpha, best_val, new_u, a, b]
     host_all = torch.zeros((max_iters + 2, 8), dtype=torch.float64).pin_memory()
     events = {}
     alphas = np.arange(0 + alpha_uniform_search_step, 1, alpha_uniform_search_step)  # utils.py:179
     alphas_dev = torch.from_numpy(alphas).to(device)
     vals_dev = torch.empty((int(ctx.lib.xc_fw_alpha_scratch_bytes(m, int(alphas.size))) + 7) // 8, **f64)
-    sptr = lambda i: C.c_void_p(scal[i:].data_ptr())
     debug = bool(os.environ.get("XCOLUMNS_B200_FW_DEBUG"))   # diagnostics: meta["alpha_search_ctl"] (syncs!)
     debug_ctl = os.environ.get("XCOLUMNS_B200_FW_DEBUG") == "2"   # also read the search control block per step
     dbg_ctl = []
     ctl_off = int(ctx.lib.xc_fw_alpha_ctl_offset(m, int(alphas.size)))
 
-    def iterate(out: torch.Tensor):
-        """confusion vectors of the classifier held in (a_dev, b_dev) -> out (4m)"""
-        aw, bw = a_dev.to(wdt), b_dev.to(wdt)
+    # -------- two C calls per iteration (begin: streaming pass, finish: everything per label); the classifier
+    # matrices live on the device, rows padded so that every row starts 16-byte aligned
+    ldc = (m + 3) // 4 * 4
+    A_dev = torch.zeros((max_iters + 1, ldc), dtype=torch.float32, device=device)
+    B_dev = torch.zeros((max_iters + 1, ldc), dtype=torch.float32, device=device)
+    A_dev[0, :m].copy_(torch.from_numpy(A[0]))
+    B_dev[0, :m].copy_(torch.from_numpy(B[0]))
+    code = pd_.code
+    ab64 = torch.empty(2 * (m + 1), **f64) if (code == 1 and not is_csr) else None
+    rowp = lambda t, i: C.c_void_p(t.data_ptr() + 4 * ldc * i)
+    n_alphas = int(alphas.size)
+
+    def step(i, first):
+        """enqueue iteration i (no host sync); its scalars land in scal_all[i] / host_all[i].  The
+        finish call also writes classifier row i + 1 (gradient at the new running matrix) and
+        the next iteration's "old utility" into scal_all[i + 1][0]."""
+        sc = C.c_void_p(scal_all[i].data_ptr())
+        has_next = i + 1 <= max_iters
         if is_csr:
-            ctx.call("xc_fw_iterate_csr", dev.ptr(pd_.data), pd_.code, dev.ptr(pd_.indices), dev.ptr(pd_.indptr), n, m,
+            # the CSR kernel takes the classifier in the data dtype (weighted_prediction.py:72-75)
+            aw, bw = A_dev[i, :m].to(wdt), B_dev[i, :m].to(wdt)
+            ctx.call("xc_fw_iterate_csr", dev.ptr(pd_.data), code, dev.ptr(pd_.indices), dev.ptr(pd_.indptr), n, m,
                      dev.ptr(td_.data), dev.ptr(td_.indices), dev.ptr(td_.indptr), dev.ptr(aw), dev.ptr(bw), k,
                      C.c_void_p(raw[0].data_ptr()), C.c_void_p(raw[1].data_ptr()), None, sp())
         else:
-            ctx.call("xc_fw_iterate_dense", dev.ptr(pd_.t), pd_.code, n, m, pd_.ld, dev.ptr(td_.t), td_.ld,
-                     dev.ptr(aw), dev.ptr(bw), k, C.c_void_p(raw[0].data_ptr()), C.c_void_p(raw[1].data_ptr()), None,
-                     sp())
-        comm.allreduce_sum_(raw)
-        ctx.call("xc_fw_make_conf", C.c_void_p(raw[0].data_ptr()), C.c_void_p(raw[1].data_ptr()), dev.ptr(colsum), m,
-                 C.c_double(float(n_global)), int(bool(normalize_conf_matrix)), int(bool(skip_tn)), dev.ptr(out), sp())
-
-    def d2h_scalars():
-        return scal.cpu().numpy()                       # the only sync of an iteration
-
-    if is_csr:
-        # -------- CSR rows: granular calls, classifier rows staged through (a_dev, b_dev)
-        a_dev.copy_(torch.from_numpy(A[0]))
-        b_dev.copy_(torch.from_numpy(B[0]))
-        iterate(Cm)
-        ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, None, None, sptr(0), sp())
-    else:
-        # -------- dense rows: two C calls per iteration, classifier matrices live on the device
-        ldc = (m + 3) // 4 * 4      # classifier rows start 16-byte aligned -> 128-bit coefficient loads
-        A_dev = torch.zeros((max_iters + 1, ldc), dtype=torch.float32, device=device)
-        B_dev = torch.zeros((max_iters + 1, ldc), dtype=torch.float32, device=device)
-        A_dev[0, :m].copy_(torch.from_numpy(A[0]))
-        B_dev[0, :m].copy_(torch.from_numpy(B[0]))
-        ab64 = torch.empty(2 * (m + 1), **f64) if pd_.code == 1 else None
-        rowp = lambda t, i: C.c_void_p(t.data_ptr() + 4 * ldc * i)
-        n_alphas = int(alphas.size)
-
-        def step(i, first):
-            """enqueue iteration i (no host sync); its scalars land in scal_all[i] / host_all[i].  The
-            finish call also writes classifier row i + 1 (gradient at the new running matrix) and
-            the next iteration's "old utility" into scal_all[i + 1][0]."""
-            sc = C.c_void_p(scal_all[i].data_ptr())
-            has_next = i + 1 <= max_iters
-            ctx.call("xc_fw_step_begin", dev.ptr(pd_.t), pd_.code, n, m, pd_.ld, dev.ptr(td_.t), td_.ld,
+            ctx.call("xc_fw_step_begin", dev.ptr(pd_.t), code, n, m, pd_.ld, dev.ptr(td_.t), td_.ld,
                      rowp(A_dev, i), rowp(B_dev, i), dev.ptr(ab64), k, dev.ptr(raw), 0 if first else 1, sp())
-            comm.allreduce_sum_(raw)
-            ctx.call("xc_fw_step_finish", C.byref(params), 1 if first else 0, dev.ptr(raw), dev.ptr(colsum), m,
-                     C.c_double(float(n_global)), int(bool(normalize_conf_matrix)), int(bool(skip_tn)), dev.ptr(Cm),
-                     dev.ptr(Ci), dev.ptr(alphas_dev) if search_for_best_alpha else None, n_alphas,
-                     C.c_double(2 / (i + 1)), dev.ptr(vals_dev), sc,
-                     rowp(A_dev, i + 1) if has_next else None, rowp(B_dev, i + 1) if has_next else None,
-                     C.c_void_p(scal_all[i + 1].data_ptr()), 1, C.c_double(ternary_eps), sp())
-            host_all[i].copy_(scal_all[i], non_blocking=True)
-            if debug_ctl:
-                w = vals_dev.view(torch.int32)[ctl_off // 4: ctl_off // 4 + 32].cpu().tolist()
-                dbg_ctl.append((w[16], w[0], w[2]))   # stage-1 candidates, after refinement, label slices
-            ev = torch.cuda.Event(enable_timing=debug)
-            ev.record(torch.cuda.current_stream(device))
-            events[i] = ev
+        comm.allreduce_sum_(raw)
+        ctx.call("xc_fw_step_finish", C.byref(params), 1 if first else 0, dev.ptr(raw), dev.ptr(colsum), m,
+                 C.c_double(float(n_global)), int(bool(normalize_conf_matrix)), int(bool(skip_tn)), dev.ptr(Cm),
+                 dev.ptr(Ci), dev.ptr(alphas_dev) if search_for_best_alpha else None, n_alphas,
+                 C.c_double(2 / (i + 1)), dev.ptr(vals_dev), sc,
+                 rowp(A_dev, i + 1) if has_next else None, rowp(B_dev, i + 1) if has_next else None,
+                 C.c_void_p(scal_all[i + 1].data_ptr()), 1, C.c_double(ternary_eps), sp())
+        host_all[i].copy_(scal_all[i], non_blocking=True)
+        if debug_ctl:
+            w = vals_dev.view(torch.int32)[ctl_off // 4: ctl_off // 4 + 32].cpu().tolist()
+            dbg_ctl.append((w[16], w[0], w[2]))   # stage-1 candidates, after refinement, label slices
+        ev = torch.cuda.Event(enable_timing=debug)
+        ev.record(torch.cuda.current_stream(device))
+        events[i] = ev
 
-        step(0, True)
+    step(0, True)
     utility_i = float(scal_all[0, 0].item())
     meta: Dict[str, Any] = {"alphas": [], "classifiers_utilities": [utility_i], "utilities": [utility_i], "time": time()}
     log_info(f"    Metric value of the first (sub)classifier 0: {utility_i}", verbose)
@@ -273,36 +254,17 @@ def find_classifier_using_fw(
     n_used = max_iters + 1
     for i in range(1, max_iters + 1):
         log_info(f"  Starting iteration {i}/{max_iters} ...", verbose)
-        if is_csr:
-            # value + gradient -> next classifier (frank_wolfe.py:591-599), float32 rows
-            ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, dev.ptr(a_dev), dev.ptr(b_dev), sptr(0), sp())
-            iterate(Ci)
-            ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Ci), m, None, None, sptr(1), sp())
-            if ternary_eps > 0:
-                ctx.call("xc_fw_alpha_ternary", C.byref(params), dev.ptr(Cm), dev.ptr(Ci), m, C.c_double(ternary_eps),
-                         sptr(2), sp())
-            elif search_for_best_alpha:
-                ctx.call("xc_fw_alpha_search", C.byref(params), dev.ptr(Cm), dev.ptr(Ci), m, dev.ptr(alphas_dev),
-                         int(alphas.size), dev.ptr(vals_dev), sptr(2), sp())
-            else:
-                scal[2] = 2 / (i + 1)
-            ctx.call("xc_fw_combine", dev.ptr(Cm), dev.ptr(Ci), 4 * m, sptr(2), sp())
-            ctx.call("xc_fw_metric_grad", C.byref(params), dev.ptr(Cm), m, None, None, sptr(4), sp())
-            host = d2h_scalars()
-            A[i] = a_dev.cpu().numpy()
-            B[i] = b_dev.cpu().numpy()
-        else:
-            # The stopping rules need iteration i's scalars on the host, which would drain the GPU
-            # queue once per iteration (measured: 0.5 ms of idle GPU per 0.65 ms iteration).  So
-            # iteration i+1 is enqueued speculatively BEFORE iteration i's scalars are read; if i
-            # turns out to be the last one, the speculative classifier row is simply truncated
-            # like the reference truncates its arrays (frank_wolfe.py:659-661).
-            if i == 1:
-                step(1, False)
-            if i + 1 <= max_iters:
-                step(i + 1, False)
-            events[i].synchronize()
-            host = host_all[i].numpy()
+        # The stopping rules need iteration i's scalars on the host, which would drain the GPU
+        # queue once per iteration (measured: 0.5 ms of idle GPU per 0.65 ms iteration).  So
+        # iteration i+1 is enqueued speculatively BEFORE iteration i's scalars are read; if i
+        # turns out to be the last one, the speculative classifier row is simply truncated
+        # like the reference truncates its arrays (frank_wolfe.py:659-661).
+        if i == 1:
+            step(1, False)
+        if i + 1 <= max_iters:
+            step(i + 1, False)
+        events[i].synchronize()
+        host = host_all[i].numpy()
         old_utility, utility_i, alpha, new_utility = float(host[0]), float(host[1]), float(host[2]), float(host[4])
         log_info(f"    Iteration {i}/{max_iters} finished, alpha: {alpha}, metric: {old_utility} -> {new_utility}", verbose)
         if alpha < alpha_tolerance or (maximize and new_utility - old_utility < tolerance) or (
@@ -317,18 +279,15 @@ def find_classifier_using_fw(
     P = P[:n_used]
     if isinstance(y_true, torch.Tensor):
         # tensors in -> tensors out on the caller's device; dense classifiers never leave the GPU
-        src_a, src_b = (A_dev[:n_used, :m], B_dev[:n_used, :m]) if not is_csr else (torch.from_numpy(A[:n_used]), torch.from_numpy(B[:n_used]))
-        A, B = (v.to(device=y_proba.device, dtype=y_proba.dtype, copy=True) for v in (src_a, src_b))
+        A, B = (v.to(device=y_proba.device, dtype=y_proba.dtype, copy=True) for v in (A_dev[:n_used, :m], B_dev[:n_used, :m]))
         P = torch.tensor(P, dtype=y_proba.dtype, device=y_proba.device)
-    elif not is_csr:
+    else:
         # one pinned staging buffer, one async copy, one sync (pageable copies cost ~1 ms each here)
         stage = torch.empty((2, n_used, m), dtype=torch.float32).pin_memory()
         stage[0].copy_(A_dev[:n_used, :m], non_blocking=True)
         stage[1].copy_(B_dev[:n_used, :m], non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
         A, B = stage[0].numpy(), stage[1].numpy()
-    else:
-        A, B = A[:n_used], B[:n_used]
     log_info(f"  Final utility of the randomized classifier: {new_utility}, number of sub-classifiers: {len(A)}", verbose)
 
     clf = RandomizedWeightedClassifier(k, A, B, P)
@@ -338,10 +297,9 @@ def find_classifier_using_fw(
         meta["launches"] = ctx.launches()
         if debug:
             meta["alpha_search_ctl"] = dbg_ctl   # per enqueued iteration: (stage-1 candidates, refined, slices)
-            if not is_csr:
-                torch.cuda.synchronize(device)
-                ks = sorted(events)
-                meta["step_ms"] = [events[a_].elapsed_time(events[b_]) for a_, b_ in zip(ks[:-1], ks[1:])]
+            torch.cuda.synchronize(device)
+            ks = sorted(events)
+            meta["step_ms"] = [events[a_].elapsed_time(events[b_]) for a_, b_ in zip(ks[:-1], ks[1:])]
         return clf, meta
     return clf
 
@@ -375,6 +333,19 @@ find_classifier_optimizing_macro_balanced_accuracy_using_fw = make_frank_wolfe_w
     M.macro_balanced_accuracy_on_conf_matrix, "macro-averaged balanced accuracy")
 find_classifier_optimizing_macro_hmean_using_fw = make_frank_wolfe_wrapper(M.macro_hmean_on_conf_matrix, "macro-averaged H-mean")
 find_classifier_optimizing_macro_gmean_using_fw = make_frank_wolfe_wrapper(M.macro_gmean_on_conf_matrix, "macro-averaged G-mean")
+# micro-averaged objectives (xcolumns/frank_wolfe.py:758-832)
+find_classifier_optimizing_micro_precision_using_fw = make_frank_wolfe_wrapper(
+    M.micro_precision_on_conf_matrix, "micro-averaged precision", skip_tn=True, warn_k_eq_0=True)
+find_classifier_optimizing_micro_recall_using_fw = make_frank_wolfe_wrapper(
+    M.micro_recall_on_conf_matrix, "micro-averaged recall", skip_tn=True, warn_k_eq_0=True)
+find_classifier_optimizing_micro_f1_score_using_fw = make_frank_wolfe_wrapper(
+    M.micro_f1_score_on_conf_matrix, "micro-averaged F1 score", skip_tn=True)
+find_classifier_optimizing_micro_jaccard_score_using_fw = make_frank_wolfe_wrapper(
+    M.micro_jaccard_score_on_conf_matrix, "micro-averaged Jaccard score", skip_tn=True)
+find_classifier_optimizing_micro_balanced_accuracy_using_fw = make_frank_wolfe_wrapper(
+    M.micro_balanced_accuracy_on_conf_matrix, "micro-averaged balanced accuracy")
+find_classifier_optimizing_micro_hmean_using_fw = make_frank_wolfe_wrapper(M.micro_hmean_on_conf_matrix, "micro-averaged H-mean")
+find_classifier_optimizing_micro_gmean_using_fw = make_frank_wolfe_wrapper(M.micro_gmean_on_conf_matrix, "micro-averaged G-mean")
 
 
 # ------------------------------------------------------------------------------------------

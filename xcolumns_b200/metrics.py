@@ -137,6 +137,35 @@ macro_gmean_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_gmean_on_co
 macro_hmean_on_conf_matrix = make_macro_metric_on_conf_matrix(binary_hmean_on_conf_matrix, "H-mean")
 
 
+def make_micro_metric_on_conf_matrix(binary_metric: Callable, name: str) -> Callable:
+    """Micro average of a binary metric: the metric of the summed confusion entries
+    (xcolumns/metrics.py:68-100)."""
+
+    def micro_metric_on_conf_matrix(tp, fp, fn, tn, **kwargs):
+        return binary_metric(tp.sum(), fp.sum(), fn.sum(), tn.sum(), **kwargs)
+
+    micro_metric_on_conf_matrix.__doc__ = f"Micro-averaged {name} on the confusion vectors (tp, fp, fn, tn)."
+    micro_metric_on_conf_matrix._xc_binary_metric = binary_metric
+    micro_metric_on_conf_matrix._xc_micro = True
+    return add_kwargs_to_signature(micro_metric_on_conf_matrix, binary_metric)
+
+
+micro_precision_on_conf_matrix = make_micro_metric_on_conf_matrix(binary_precision_on_conf_matrix, "precision")
+micro_recall_on_conf_matrix = make_micro_metric_on_conf_matrix(binary_recall_on_conf_matrix, "recall")
+micro_fbeta_score_on_conf_matrix = make_micro_metric_on_conf_matrix(binary_fbeta_score_on_conf_matrix, "F-beta score")
+micro_f1_score_on_conf_matrix = make_micro_metric_on_conf_matrix(binary_fbeta_score_on_conf_matrix, "F1 score")
+micro_jaccard_score_on_conf_matrix = make_micro_metric_on_conf_matrix(binary_jaccard_score_on_conf_matrix, "Jaccard score")
+micro_balanced_accuracy_on_conf_matrix = make_micro_metric_on_conf_matrix(
+    binary_balanced_accuracy_on_conf_matrix, "balanced accuracy")
+micro_gmean_on_conf_matrix = make_micro_metric_on_conf_matrix(binary_gmean_on_conf_matrix, "G-mean")
+micro_hmean_on_conf_matrix = make_micro_metric_on_conf_matrix(binary_hmean_on_conf_matrix, "H-mean")
+
+
+def is_micro_metric(func: Callable) -> bool:
+    """True for our micro-averaged metrics and for the reference's own factory closures."""
+    return bool(getattr(func, "_xc_micro", False)) or getattr(func, "__name__", "") == "micro_metric_on_conf_matrix"
+
+
 def coverage_on_conf_matrix(tp, fp, fn, tn):
     """Fraction of labels with at least one true positive (xcolumns/metrics.py:972-990)."""
     return (tp > 0).mean()
@@ -194,7 +223,8 @@ def resolve_macro_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]]
     if isinstance(func, MixedInstancePrecisionMacroMetric):
         return resolve_binary_metric(func.per_label.binary_metric, metric_kwargs)
     inner = getattr(func, "_xc_binary_metric", None)
-    if inner is None and getattr(func, "__name__", "") == "macro_metric_on_conf_matrix" and func.__closure__:
+    if inner is None and getattr(func, "__name__", "") in ("macro_metric_on_conf_matrix",
+                                                            "micro_metric_on_conf_matrix") and func.__closure__:
         # the reference's factory closure (xcolumns/metrics.py:51-58) captures `binary_metric`
         for cell in func.__closure__:
             try:
@@ -205,6 +235,6 @@ def resolve_macro_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]]
                 inner = v
     if inner is None:
         raise UnsupportedMetricError(
-            f"metric_func={func!r} is not a built-in macro-averaged metric; xcolumns_b200 fuses "
-            f"macro precision / recall / F-beta / Jaccard / balanced accuracy / G-mean / H-mean")
+            f"metric_func={func!r} is not a built-in macro- or micro-averaged metric; xcolumns_b200 fuses "
+            f"precision / recall / F-beta / Jaccard / balanced accuracy / G-mean / H-mean")
     return resolve_binary_metric(inner, metric_kwargs)
