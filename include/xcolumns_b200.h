@@ -189,6 +189,16 @@ XC_API int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype, int
                                     int64_t ld, const int32_t *order, int64_t n_order, int k,
                                     const xc_metric_params *p, int greedy, int32_t *pred_idx,
                                     double *tp, double *fp, double *fn, double *tn, void *stream);
+/* Online / greedy micro-batch (ref: block_coordinate.py:132-209 called with greedy=True, only_pred=True,
+ * followed by confusion_matrix.py:402-435 _update_unnormalized_confusion_matrix, as driven by
+ * experiments/omma_wrappers_online_methods.py:192-270): rows 0..n_rows-1 in sequence, each predicted from
+ * the current state (its own contribution is not removed), then the state is advanced with the row of
+ * y_true (NULL: with the probabilities themselves, the "ETU" variant).  One cluster launch per micro-batch;
+ * label spaces beyond 32 k return XC_ERR_UNSUPPORTED.  The state stays on the device between calls.  */
+XC_API int xc_bca_online_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n_rows, int64_t m,
+                               int64_t ld, const void *y_true, int64_t ld_true, int k,
+                               const xc_metric_params *p, int32_t *pred_idx, double *tp, double *fp,
+                               double *fn, double *tn, void *stream);
 /* k == 0 (no budget, ref: block_coordinate.py:199-200): every label with gain >= 0 is predicted.
  * pred is a dense [n, ld_pred] 0/1 matrix of eta's dtype, updated in place.                     */
 XC_API int xc_bca_exact_sweep_dense_k0(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m,

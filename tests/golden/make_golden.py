@@ -271,6 +271,27 @@ def main_extra():
         out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
         out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
         print(f"  {name}: iters={meta['iters']} alphas={out[name + '_alphas']} util={out[name + '_util']}")
+    # online / greedy steps (block_coordinate.py:132-209 with greedy=True, only_pred=True, then
+    # confusion_matrix.py:402-435), driven like experiments/omma_wrappers_online_methods.py:192-270
+    from xcolumns import block_coordinate as bc
+    from xcolumns import confusion_matrix as cm
+    eo = dense_probs(250, 180, seed=33)
+    lab = (np.random.default_rng(9).random(eo.shape) < eo).astype(np.float32)
+    out.update({"on_eta": eo, "on_lab": lab})
+    for name, metric, skip_tn, etu in (("on_f1", mt.binary_f1_score_on_conf_matrix, True, False),
+                                       ("on_f1_etu", mt.binary_f1_score_on_conf_matrix, True, True),
+                                       ("on_balacc", mt.binary_balanced_accuracy_on_conf_matrix, False, False)):
+        m_ = eo.shape[1]
+        C_ = cm.ConfusionMatrix(*[np.full(m_, 1e-6, dtype=np.float64) for _ in range(4)])
+        yp = np.zeros_like(eo)
+        yt = eo if etu else lab
+        for i in range(eo.shape[0]):
+            bc._bc_with_0approx_step_dense(eo, yp, i, C_.tp, C_.fp, C_.fn, C_.tn, 5, metric, greedy=True,
+                                           skip_tn=skip_tn, only_pred=True)
+            cm._update_unnormalized_confusion_matrix(C_, yt[i], yp[i], skip_tn=skip_tn)
+        out[name + "_pred"] = pred_to_idx(yp, 5)
+        out[name + "_state"] = np.stack([C_.tp, C_.fp, C_.fn, C_.tn])
+        print(f"  {name}: tp sum {C_.tp.sum():.6f}")
     # micro-averaged Frank-Wolfe objectives (frank_wolfe.py:758-832)
     for name, fn, kw in (("micro_f1", fw.find_classifier_optimizing_micro_f1_score_using_fw, {}),
                          ("micro_balacc", fw.find_classifier_optimizing_micro_balanced_accuracy_using_fw, {})):

@@ -605,3 +605,26 @@ def test_fw_micro_golden(xb, golden, name, metric):
     y = csr_matrix(np.where(eta > np.sort(eta, axis=1)[:, [-30]], eta, 0).astype(np.float32))
     clf2, meta2 = fn(y, y, 5, max_iters=4, seed=0, return_meta=True)
     assert len(meta2["utilities"]) >= 1 and clf2.a.shape[1] == eta.shape[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,metric,skip_tn,etu", [("on_f1", "f1", True, False), ("on_f1_etu", "f1", True, True),
+                                                       ("on_balacc", "balanced_accuracy", False, False)])
+def test_online_greedy_golden(xb, golden, name, metric, skip_tn, etu):
+    """online greedy steps + state updates in one launch per micro-batch: predictions and float64 state bit-equal
+    to the live reference's step functions, also when the stream is cut into micro-batches"""
+    from xcolumns_b200.online import OnlineGreedy
+    g = golden("extra")
+    eta, lab = g["on_eta"], g["on_lab"]
+    n, m = eta.shape
+    for cuts in ([0, n], [0, 1, 64, 200, n]):
+        og = OnlineGreedy(m, 5, _metric(xb, metric), skip_tn=skip_tn, etu_variant=etu)
+        preds = [og.predict_update(eta[a:b], None if etu else lab[a:b], n_div=n, y_pred_format="indices")
+                 for a, b in zip(cuts[:-1], cuts[1:])]
+        assert (np.concatenate(preds) == g[name + "_pred"]).all()
+        assert (np.stack(list(og.C)) == g[name + "_state"]).all()
+    dense = OnlineGreedy(m, 5, _metric(xb, metric), skip_tn=skip_tn, etu_variant=etu).predict_update(
+        eta, None if etu else lab)
+    assert dense.shape == eta.shape and dense.dtype == eta.dtype and (_idx(dense, 5) == g[name + "_pred"]).all()
+    with pytest.raises(ValueError):
+        OnlineGreedy(m, 5, _metric(xb, metric)).predict_update(eta)

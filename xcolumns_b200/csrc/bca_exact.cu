@@ -288,8 +288,11 @@ template <typename TE, int L, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ order,
                                int64_t n_order, int k, xc_metric_params p, int greedy, int32_t *pred_idx, double *tp,
-                               double *fp, double *fn, double *tn)
+                               double *fp, double *fn, double *tn, const TE *__restrict__ addback, int64_t ld_add)
 {
+    // order == nullptr: rows 0 .. n_order-1 in sequence.  addback != nullptr (online mode, greedy): the state
+    // is updated with the row of `addback` (the true labels) instead of the probabilities themselves
+    // (confusion_matrix.py:402-435 after a step with only_pred=True).
     cg::cluster_group cluster = cg::this_cluster();
     const int nc = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -308,7 +311,7 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
     const TE one = (TE)1;
 
     double stp[L], sfp[L], sfn[L], stn[L];
-    TE pv[L], pnext[L];
+    TE pv[L], pnext[L], av[L], anext[L];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         int64_t j = j0 + l * stride;
@@ -318,28 +321,35 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
         sfn[l] = ok ? fn[j] : 0.0;
         stn[l] = ok ? tn[j] : 0.0;
         pnext[l] = (TE)0;
+        anext[l] = (TE)0;
     }
     if (n_order > 0) {
-        const TE *rp = eta + (int64_t)order[0] * ld;
+        const int64_t r0 = order ? (int64_t)order[0] : 0;
 #pragma unroll
         for (int l = 0; l < L; ++l) {
             int64_t j = j0 + l * stride;
-            if (j < m) pnext[l] = __ldg(rp + j);
+            if (j < m) {
+                pnext[l] = __ldg(eta + r0 * ld + j);
+                if (addback) anext[l] = __ldg(addback + r0 * ld_add + j);
+            }
         }
     }
     cluster.sync();
 
     for (int64_t s = 0; s < n_order; ++s) {
-        const int64_t row = order[s];
+        const int64_t row = order ? (int64_t)order[s] : s;
         int32_t *prow = pred_idx + row * k;
 #pragma unroll
-        for (int l = 0; l < L; ++l) pv[l] = pnext[l];
+        for (int l = 0; l < L; ++l) { pv[l] = pnext[l]; av[l] = anext[l]; }
         if (s + 1 < n_order) {
-            const TE *rn = eta + (int64_t)order[s + 1] * ld;
+            const int64_t rnext = order ? (int64_t)order[s + 1] : s + 1;
 #pragma unroll
             for (int l = 0; l < L; ++l) {
                 int64_t j = j0 + l * stride;
-                if (j < m) pnext[l] = __ldg(rn + j);
+                if (j < m) {
+                    pnext[l] = __ldg(eta + rnext * ld + j);
+                    if (addback) anext[l] = __ldg(addback + rnext * ld_add + j);
+                }
             }
         }
         // ---- 1. remove own contribution, gains (block_coordinate.py:157-185) --------------------------
@@ -450,7 +460,7 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
             bool sel = false;
             for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, fin, t) == (int)j);
             if (j < m) {
-                const TE pe = pv[l];
+                const TE pe = addback ? av[l] : pv[l];
                 const TE om = one - pe;
                 const TE y = sel ? one : (TE)0;
                 stp[l] = stp[l] + (double)(TE)(y * pe);
@@ -1015,7 +1025,8 @@ int launch_exact_dense(xc_ctx *ctx, int grid, const void *eta, int64_t m, int64_
 template <typename TE, int L, int THREADS>
 int launch_exact_cluster(xc_ctx *ctx, int nc, const void *eta, int64_t m, int64_t ld, const int32_t *order,
                          int64_t n_order, int k, const xc_metric_params *p, int greedy, int32_t *pred_idx, double *tp,
-                         double *fp, double *fn, double *tn, cudaStream_t st)
+                         double *fp, double *fn, double *tn, cudaStream_t st, const void *addback = nullptr,
+                         int64_t ld_add = 0)
 {
     auto kern = bca_exact_dense_cluster_kernel<TE, L, THREADS>;
     if (nc > 8) XC_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1037,7 +1048,7 @@ int launch_exact_cluster(xc_ctx *ctx, int nc, const void *eta, int64_t m, int64_
         return XC_ERR_UNSUPPORTED;  // caller falls back to the grid-barrier kernel
     }
     XC_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kern, (const TE *)eta, m, ld, order, n_order, k, *p, greedy, pred_idx, tp,
-                                        fp, fn, tn));
+                                        fp, fn, tn, (const TE *)addback, ld_add));
     XC_LAUNCHED(ctx);
     return XC_OK;
 }
@@ -1046,7 +1057,7 @@ int launch_exact_cluster(xc_ctx *ctx, int nc, const void *eta, int64_t m, int64_
 template <typename TE>
 int dispatch_exact_cluster(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, const int32_t *order, int64_t n_order,
                            int k, const xc_metric_params *p, int greedy, int32_t *pred_idx, double *tp, double *fp,
-                           double *fn, double *tn, cudaStream_t st)
+                           double *fn, double *tn, cudaStream_t st, const void *addback = nullptr, int64_t ld_add = 0)
 {
     auto ncta = [&](int64_t per_cta) { return (int)((m + per_cta - 1) / per_cta); };
 #define XC_TRY(LL, TH)                                                                                               \
@@ -1054,7 +1065,7 @@ int dispatch_exact_cluster(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, 
         int nc = ncta((int64_t)(TH) * (LL));                                                                         \
         if (nc <= CL_MAX)                                                                                            \
             return launch_exact_cluster<TE, LL, TH>(ctx, nc, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, \
-                                                    fp, fn, tn, st);                                                 \
+                                                    fp, fn, tn, st, addback, ld_add);                                \
     }
     if (ncta(512) <= 8) XC_TRY(1, 512)
     if (ncta(1024) <= 8) XC_TRY(2, 512)
@@ -1125,6 +1136,22 @@ extern "C" int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype,
         return dispatch_exact_dense<float>(ctx, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, st);
     if (dtype == XC_F64)
         return dispatch_exact_dense<double>(ctx, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, fp, fn, tn, st);
+    return XC_ERR_UNSUPPORTED;
+}
+
+extern "C" int xc_bca_online_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n_rows, int64_t m, int64_t ld,
+                                   const void *y_true, int64_t ld_true, int k, const xc_metric_params *p,
+                                   int32_t *pred_idx, double *tp, double *fp, double *fn, double *tn, void *stream)
+{
+    if (!ctx || !eta || !p || !pred_idx || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
+    if (n_rows < 0 || m <= 0 || ld < m || k < 1 || k > 32 || k > m || (y_true && ld_true < m)) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32)
+        return dispatch_exact_cluster<float>(ctx, eta, m, ld, nullptr, n_rows, k, p, 1, pred_idx, tp, fp, fn, tn, st, y_true, ld_true);
+    if (dtype == XC_F64)
+        return dispatch_exact_cluster<double>(ctx, eta, m, ld, nullptr, n_rows, k, p, 1, pred_idx, tp, fp, fn, tn, st, y_true, ld_true);
     return XC_ERR_UNSUPPORTED;
 }
 
