@@ -107,6 +107,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
         self.active = False  # samples are kept only while the timed region runs
+        self.ready = threading.Event()   # NVML is initialised (can take seconds on a fresh box)
 
     def run(self):
         try:
@@ -120,6 +121,7 @@ class ClockSampler(threading.Thread):
                 pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                 pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             }
+            self.ready.set()
             while not self.stop_flag:
                 clk = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
@@ -131,6 +133,7 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.001)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
@@ -314,6 +317,7 @@ def main():
         one_sweep()
     reset()
     torch.cuda.synchronize(device)
+    sampler.ready.wait(timeout=30)
     comm.barrier()
     torch.cuda.synchronize(device)
     sampler.active = True
