@@ -155,6 +155,8 @@ XC_API int xc_confmat_csr(xc_ctx *ctx, const void *t_data, const int32_t *t_idx,
                           const int64_t *p_ptr, int dtype, int64_t n, int64_t m, int order,
                           int acc_f32, double *tp, double *fp, double *fn, void *stream);
 /* CSR truth, compact prediction of ones */
+/* fn may be NULL with XC_SUM_FAST: only tp / fp are accumulated (k look-ups per row instead of a pass
+ * over the whole row); the caller derives fn = colsum(y_true) - tp.                                  */
 XC_API int xc_confmat_csr_compact(xc_ctx *ctx, const void *t_data, const int32_t *t_idx,
                                   const int64_t *t_ptr, int dtype, const int32_t *pred_idx, int k,
                                   int64_t n, int64_t m, int order, double *tp, double *fp,

@@ -164,10 +164,16 @@ class BcaSession:
                 self.ctx.call("xc_confmat_dense_compact", dev.ptr(d.t), d.code, d.ld, dev.ptr(self.pred), k, d.n, d.m,
                               order, None, self._sp(0), self._sp(1), self._sp(2), self._s())
         elif self.is_csr:
+            if self.colsum is None:  # sum_i eta_ij never changes: fn = colsum - tp, no pass over the rows per sweep
+                self.colsum = torch.empty(self.m, dtype=torch.float64, device=self.device)
+                self.ctx.call("xc_colsum_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), int(d.data.numel()), d.m,
+                              dev.ptr(self.colsum), self._s())
+                self.comm.allreduce_sum_(self.colsum)
             self.ctx.call("xc_confmat_csr_compact", dev.ptr(d.data), dev.ptr(d.indices), dev.ptr(d.indptr), d.code,
-                          dev.ptr(self.pred), k, d.n, d.m, order, self._sp(0), self._sp(1), self._sp(2), self._s())
+                          dev.ptr(self.pred), k, d.n, d.m, order, self._sp(0), self._sp(1), None, self._s())
             if self.comm.world > 1:
-                self.comm.allreduce_sum_(self.state[0:3])
+                self.comm.allreduce_sum_(self.state[0:2])
+            torch.sub(self.colsum, self.state[0], out=self.state[2])
         else:
             if self.colsum is None:  # sum_i eta_ij never changes: one extra pass per call, not per sweep
                 self.colsum = torch.empty(self.m, dtype=torch.float64, device=self.device)

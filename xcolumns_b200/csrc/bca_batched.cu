@@ -245,6 +245,13 @@ bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
 }
 
 // ---- CSR batch: one warp per row, candidates = stored labels ----------------------------------------
+// Rows with up to 32 * BC_RMAX stored labels are staged in registers: all loads of the row are issued up
+// front, the coefficient gathers follow in one wave, and everything after that (which stored entries
+// are currently selected, the probability of a label that leaves, the label / probability of a new
+// selection) is resolved with shuffles instead of dependent loads and binary searches.  Per row that is
+// 3 dependent memory round trips (row bounds -> entries -> coefficients) instead of ~12.
+constexpr int BC_RMAX = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bca_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
@@ -262,28 +269,110 @@ bca_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
         int32_t *pred_row = pred_idx + row * k;
         int old_j = -1;
         if (lane < k) old_j = pred_row[lane];
-        WarpTopK<float> tk;
-        tk.init();
-        // every stored label is a candidate; selected ones use coef_s
-        for (int64_t q0 = s; q0 < e; q0 += 32) {
-            int64_t q = q0 + lane;
-            float g[1];
-            g[0] = NAN;
-            const int j = q < e ? indices[q] : -2;
-            bool sel = false;
-            for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, old_j, t) == j);
-            if (q < e) {
-                float ev = (float)data[q];
-                float2 cf = __ldg((sel ? coef_s : coef_n) + j);
-                g[0] = fmaf(cf.x, ev, cf.y);
+        int new_j;
+        T new_e, old_e = (T)0;
+        bool old_found = false;
+        if (e - s <= 32 * BC_RMAX) {
+            // ---- register-staged row
+            const int nz = (int)(e - s);
+            int idx[BC_RMAX];
+            T val[BC_RMAX];
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                const int q = lane + 32 * t;
+                idx[t] = q < nz ? indices[s + q] : -2;
+                val[t] = q < nz ? data[s + q] : (T)0;
             }
-            if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<float, 1, false>(tk, g, q0 - s, 1, k, -1);
+            bool sel[BC_RMAX];
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) sel[t] = false;
+            for (int x = 0; x < k; ++x) {
+                const int px = __shfl_sync(XC_FULL, old_j, x);
+#pragma unroll
+                for (int t = 0; t < BC_RMAX; ++t) {
+                    const bool hit = px >= 0 && idx[t] == px;
+                    sel[t] |= hit;
+                    const unsigned bal = __ballot_sync(XC_FULL, hit);
+                    if (bal) {   // warp-uniform: the owner hands the probability of old label x to lane x
+                        const T v = __shfl_sync(XC_FULL, val[t], __ffs(bal) - 1);
+                        if (lane == x) { old_e = v; old_found = true; }
+                    }
+                }
+            }
+            WarpTopK<float> tk;
+            tk.init();
+            float g[BC_RMAX][1];
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                g[t][0] = NAN;
+                if (idx[t] >= 0) {
+                    const float2 cf = __ldg((sel[t] ? coef_s : coef_n) + idx[t]);
+                    g[t][0] = fmaf(cf.x, (float)val[t], cf.y);
+                }
+            }
+            // the row's current selection goes in first: it sets a tight threshold, so that in a converged
+            // sweep hardly any other entry reaches the list (an empty list would take all 32 lanes of the
+            // first chunk through the serial insertion path: ~1500 warp instructions per row, measured as
+            // the bound of this kernel)
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                float gs[1];
+                gs[0] = sel[t] ? g[t][0] : NAN;
+                if (32 * t < nz && __any_sync(XC_FULL, tk.passes(gs[0])))
+                    xc_scan_insert<float, 1, false>(tk, gs, 32 * t, 1, k, -1);
+                if (sel[t]) g[t][0] = NAN;
+            }
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t)
+                if (32 * t < nz && __any_sync(XC_FULL, tk.passes(g[t][0])))
+                    xc_scan_insert<float, 1, false>(tk, g[t], 32 * t, 1, k, -1);
+            // positions inside the row, ascending (== ascending label); fetch label / probability by shuffle
+            const int src = warp_rank_src(tk.idx, k);
+            const int pos = __shfl_sync(XC_FULL, tk.idx, src);
+            const bool none = pos == 0x7fffffff;
+            const int want_lane = none ? 0 : (pos & 31), want_t = none ? 0 : (pos >> 5);
+            int gj = 0;
+            T ge = (T)0;
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                const int vj = __shfl_sync(XC_FULL, idx[t], want_lane);
+                const T ve = __shfl_sync(XC_FULL, val[t], want_lane);
+                if (t == want_t) { gj = vj; ge = ve; }
+            }
+            new_j = none ? 0x7fffffff : gj;
+            new_e = none ? (T)0 : ge;
+        } else {
+            // ---- long row: stream it, look the leaving labels up afterwards
+            WarpTopK<float> tk;
+            tk.init();
+            for (int64_t q0 = s; q0 < e; q0 += 32) {
+                int64_t q = q0 + lane;
+                float g[1];
+                g[0] = NAN;
+                const int j = q < e ? indices[q] : -2;
+                bool sel = false;
+                for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, old_j, t) == j);
+                if (q < e) {
+                    float ev = (float)data[q];
+                    float2 cf = __ldg((sel ? coef_s : coef_n) + j);
+                    g[0] = fmaf(cf.x, ev, cf.y);
+                }
+                if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<float, 1, false>(tk, g, q0 - s, 1, k, -1);
+            }
+            int src = warp_rank_src(tk.idx, k);
+            int pos = __shfl_sync(XC_FULL, tk.idx, src);
+            new_j = pos == 0x7fffffff ? 0x7fffffff : indices[s + pos];
+            new_e = pos == 0x7fffffff ? (T)0 : data[s + pos];
+            if (lane < k && old_j >= 0) {
+                int64_t y = s, z = e;
+                while (y < z) {
+                    int64_t mid = (y + z) >> 1;
+                    int v = indices[mid];
+                    if (v == old_j) { old_e = data[mid]; old_found = true; break; }
+                    if (v < old_j) y = mid + 1; else z = mid;
+                }
+            }
         }
-        // list holds positions inside the row; translate to labels (ascending pos == ascending label)
-        int src = warp_rank_src(tk.idx, k);
-        int pos = __shfl_sync(XC_FULL, tk.idx, src);
-        int new_j = pos == 0x7fffffff ? 0x7fffffff : indices[s + pos];
-        T new_e = pos == 0x7fffffff ? (T)0 : data[s + pos];
         bool stays_old = false, stays_new = false;
         for (int t = 0; t < k; ++t) {
             int nj = __shfl_sync(XC_FULL, new_j, t);
@@ -293,20 +382,10 @@ bca_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
         }
         if (lane < k) {
             if (!stays_old && old_j >= 0) {
-                // eta of the leaving label (0 when the row does not store it)
-                int64_t y = s, z = e;
-                T oe = (T)0;
-                bool found = false;
-                while (y < z) {
-                    int64_t mid = (y + z) >> 1;
-                    int v = indices[mid];
-                    if (v == old_j) { oe = data[mid]; found = true; break; }
-                    if (v < old_j) y = mid + 1; else z = mid;
-                }
-                if (found) {
-                    atomicAdd(dtp + old_j, -(double)oe);
-                    atomicAdd(dfp + old_j, -(double)(T)(one - oe));
-                    atomicAdd(dfn + old_j, (double)oe);
+                if (old_found) {   // eta of the leaving label (a label the row does not store only had fp = 1)
+                    atomicAdd(dtp + old_j, -(double)old_e);
+                    atomicAdd(dfp + old_j, -(double)(T)(one - old_e));
+                    atomicAdd(dfn + old_j, (double)old_e);
                 } else {
                     atomicAdd(dfp + old_j, -1.0);
                 }

@@ -315,6 +315,7 @@ __device__ __forceinline__ void confmat_csrc_row(const T *t_data, const int32_t 
             add(fp + j, 1.0);
         }
     }
+    if (!fn) return;  // caller derives fn = colsum - tp (the row's unselected entries are never touched)
     for (int64_t y = ts + lane; y < te; y += nlanes) {
         int j = t_idx[y];
         bool sel = false;
@@ -591,12 +592,13 @@ extern "C" int xc_confmat_csr_compact(xc_ctx *ctx, const void *t_data, const int
                                       int dtype, const int32_t *pred_idx, int k, int64_t n, int64_t m, int order,
                                       double *tp, double *fp, double *fn, void *stream)
 {
-    if (!ctx || !t_ptr || !pred_idx || !tp || !fp || !fn || n <= 0 || m <= 0 || k < 1) return XC_ERR_INVALID;
+    if (!ctx || !t_ptr || !pred_idx || !tp || !fp || n <= 0 || m <= 0 || k < 1) return XC_ERR_INVALID;
+    if (!fn && order == XC_SUM_ORDERED) return XC_ERR_INVALID;  // fn may only be skipped in the fast order
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     XC_CUDA_TRY(ctx, cudaMemsetAsync(tp, 0, sizeof(double) * m, st));
     XC_CUDA_TRY(ctx, cudaMemsetAsync(fp, 0, sizeof(double) * m, st));
-    XC_CUDA_TRY(ctx, cudaMemsetAsync(fn, 0, sizeof(double) * m, st));
+    if (fn) XC_CUDA_TRY(ctx, cudaMemsetAsync(fn, 0, sizeof(double) * m, st));
     if (order == XC_SUM_ORDERED) {
         if (dtype == XC_F32) confmat_csrc_ordered_kernel<float><<<1, 128, 0, st>>>((const float *)t_data, t_idx, t_ptr, pred_idx, k, n, tp, fp, fn);
         else confmat_csrc_ordered_kernel<double><<<1, 128, 0, st>>>((const double *)t_data, t_idx, t_ptr, pred_idx, k, n, tp, fp, fn);
