@@ -15,7 +15,7 @@ constexpr int kThreads = 256;
 // (weighted_prediction.py:37-41), top-k per row, then for the k selected labels
 //   tp[j] += y_true[i][j],  cnt[j] += 1        (float64 atomics)
 template <typename TE, int R, class Xf>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, R == 1 ? 6 : 1)
 fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_t ld, const TE *__restrict__ y_true,
                         int64_t ld_true, Xf xf, int k, double *tp, double *cnt, int32_t *__restrict__ pred_idx,
                         bool vec_ok)

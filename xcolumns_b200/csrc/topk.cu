@@ -7,7 +7,7 @@ namespace {
 constexpr int kThreads = 256;
 
 template <typename TE, typename G, int R, class Xf = XfMulAdd<G>>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (R == 1 && sizeof(G) == 4) ? 6 : 1)
 topk_dense_kernel(const TE *__restrict__ eta, int64_t n_rows, int64_t m, int64_t ld,
                   const int32_t *__restrict__ rows, Xf xf, int k, int32_t *__restrict__ out_idx,
                   G *__restrict__ out_val, bool vec_ok)

@@ -136,8 +136,36 @@ struct WarpTopK {
                 val = pv;
                 idx = pi;
             }
-            thr = __shfl_sync(XC_FULL, val, k - 1);
-            thr_j = __shfl_sync(XC_FULL, idx, k - 1);
+            // the threshold only ever tightens: while the list is still filling, a bound set by prime()
+            // (k elements >= thr are known to exist) stays in force
+            const G nv = __shfl_sync(XC_FULL, val, k - 1);
+            const int nj = __shfl_sync(XC_FULL, idx, k - 1);
+            if (nv > thr || (nv == thr && nj < thr_j)) {
+                thr = nv;
+                thr_j = nj;
+            }
+        }
+    }
+    // Lower bound for the final k-th best from per-lane maxima of values that WILL be offered to the list:
+    // the k-th largest of the 32 lane maxima has at least k offered values at or above it.  Without it an
+    // empty list sends every lane of the first chunks through the serial insertion path.
+    // lane_max: NaN-free maximum of this lane's values (-inf if it has none); all 32 lanes must call.
+    __device__ __forceinline__ void prime(G lane_max, int k)
+    {
+        G m = lane_max;
+        G bound = -INFINITY;
+        for (int r = 0; r < k; ++r) {
+            G w = m;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(XC_FULL, w, o));
+            bound = w;  // r-th largest lane maximum (with multiplicity)
+            // retire ONE lane holding it
+            const unsigned bal = __ballot_sync(XC_FULL, m == w);
+            if (lane_id() == __ffs(bal) - 1) m = -INFINITY;
+        }
+        if (bound > thr) {
+            thr = bound;
+            thr_j = 0x7fffffff;  // ties with the bound still enter
         }
     }
     // does (g, j) have a chance to enter?  (cheap per-lane filter)

@@ -184,6 +184,23 @@ __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m
     const int64_t m2 = (mv / (2 * STEP)) * (2 * STEP);  // part covered by full, unguarded double steps
     const G qnan = (G)NAN;
 
+    // ---- lists built from scratch (no seed): bound the threshold from the first double step ----
+    if (!SKIP && m2 > 0) {
+        const int64_t cA = (int64_t)lane * V;
+        G ca[V], cb[V];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            TE eA[V], eB[V];
+            XcVec<TE>::load(rp[r] + cA, eA);
+            XcVec<TE>::load(rp[r] + cA + STEP, eB);
+            G gA[V], gB[V];
+            xf.template apply_vec<TE, V>(cA, eA, gA, ca, cb, true);
+            xf.template apply_vec<TE, V>(cA + STEP, eB, gB, ca, cb, true);
+            G mx = fmax(xc_vmax<G, V>(gA), xc_vmax<G, V>(gB));
+            tk[r].prime(mx == mx ? mx : (G)-INFINITY, k);
+        }
+    }
+
     // ---- main loop: two 16-byte chunks per row in flight, no bounds checks, no local memory ----
     // (a generalised loop with 4 chunks in flight was measured slower on the Frank-Wolfe iterate -- 350 vs
     // 334 us at 14 k x 31 k -- and its code shape cost the batched-BCA kernel 4 registers / one CTA per SM)
