@@ -266,6 +266,20 @@ XC_API int xc_cov_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m
                               const double *Ef, int32_t *pred_idx, double *dEf, void *stream);
 XC_API int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void *stream);
 
+/* Jaccard / G-mean / H-mean: the gain is not affine in eta but still a closed form of eta and four
+ * per-label numbers (rec: 4 floats per label, 16-byte aligned; see csrc/bca_batched.cu for the algebra).
+ * xc_bca_rec is the counterpart of xc_bca_coef (folds the pending deltas, writes the records);
+ * xc_bca_batch_dense_rec the counterpart of xc_bca_batch_dense (tp/fp/fn: the frozen state, read for the
+ * k currently selected labels of every row).  xc_bca_commit_p2p writes records instead of coefficients for
+ * these metrics (pass the record array as coef_n, coef_s may be NULL).                              */
+XC_API int xc_bca_rec(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
+                      double *dtp, double *dfp, double *dfn, int64_t m, float *rec, void *stream);
+XC_API int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype,
+                                  int64_t m, int64_t ld, const int32_t *rows, int64_t n_rows, int k,
+                                  const float *rec, const double *tp, const double *fp,
+                                  const double *fn, int32_t *pred_idx, double *dtp, double *dfp,
+                                  double *dfn, void *stream);
+
 /* ---- commits over peer memory (rows sharded over the GPUs of one box) -------------------- */
 /* One window per rank: cudaMalloc'ed, exported with CUDA IPC (ipc_handle_out: 64 bytes), mapped by
  * every other rank with xc_p2p_open(handles = the world * 64 gathered bytes).  xc_p2p_payload

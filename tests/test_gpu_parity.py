@@ -272,14 +272,15 @@ def test_coverage_exact_csr_golden(xb, golden, name, kw):
 # BCA, batched block-Jacobi mode: utilities within 1e-4 of the sequential reference
 # ------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("metric", ["f1", "recall", "precision", "balanced_accuracy"])
+@pytest.mark.parametrize("metric", ["f1", "recall", "precision", "balanced_accuracy", "jaccard", "gmean", "hmean"])
 def test_bca_batched_dense_vs_oracle(xb, oracle, metric):
     from xcolumns_b200.synth import dense_probs
     eta = dense_probs(6000, 2000, seed=1002)
-    skip = metric != "balanced_accuracy"
+    skip = metric not in ("balanced_accuracy", "gmean", "hmean")
     opred, ometa = oracle.predict_using_bc_with_0approx(eta, metric, 5, seed=0, skip_tn=skip)
     pred, meta = xb.predict_using_bc_with_0approx(eta, _metric(xb, metric), 5, seed=0, skip_tn=skip,
                                                   return_meta=True, mode="batched")
+    assert meta["mode"] == "batched"
     assert pred.shape == eta.shape and (pred.sum(1) == 5).all() and pred.dtype == eta.dtype
     # F1 / recall: the reference's seed-to-seed spread is < 1e-6 here, so tol = 1e-4;
     # macro-precision has many order-dependent fixed points (spread ~3e-4)

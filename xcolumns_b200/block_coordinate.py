@@ -125,6 +125,9 @@ class BcaSession:
         self.coef_s = torch.zeros((clen, 2), dtype=torch.float32, device=self.device)
         self.util_buf = torch.zeros(8, **f64)
         self.pred: Optional[torch.Tensor] = None
+        # Jaccard / G-mean / H-mean: 16-byte per-label records instead of the affine coefficient pairs
+        self.use_rec = (params.metric in M.RECORD_GAIN_METRICS) and not params.mix and not self.is_csr
+        self.rec = torch.zeros((clen, 4), dtype=torch.float32, device=self.device) if self.use_rec else None
 
     # -- small helpers ---------------------------------------------------------------------
     def _s(self):
@@ -255,18 +258,21 @@ class BcaSession:
             lo = min(b * batch, n_loc)
             hi = min(lo + batch, n_loc)
             cur = b & 1 if self.peer is not None else 0
+            coef_a = self.rec if self.use_rec else self.coef_n
             if self.peer is not None and b > 0:
                 # exchange + fold + coefficients in one kernel over peer memory (reads buffer (b-1) & 1)
                 self.ctx.call("xc_bca_commit_p2p", self.peer.handle, C.byref(self.p), self._sp(0), self._sp(1),
-                              self._sp(2), self.m, (b - 1) & 1, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
-            elif self.peer is not None:
-                # first batch of a sweep: the state is fresh, nothing to fold
-                self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), None, None, None,
-                              self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
+                              self._sp(2), self.m, (b - 1) & 1, dev.ptr(coef_a), dev.ptr(self.coef_s), self._s())
             else:
-                # fold the pending deltas into the state, refresh the gain coefficients
-                self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
-                              self._dp(1), self._dp(2), self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
+                # fold the pending deltas into the state (none yet in the first batch of a peer-memory sweep),
+                # refresh the gain coefficients / records
+                fold = (None, None, None) if self.peer is not None else (self._dp(0), self._dp(1), self._dp(2))
+                if self.use_rec:
+                    self.ctx.call("xc_bca_rec", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), *fold, self.m,
+                                  dev.ptr(self.rec), self._s())
+                else:
+                    self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), *fold, self.m,
+                                  dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
             if hi > lo:
                 rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
                 if events is not None:
@@ -276,6 +282,10 @@ class BcaSession:
                     self.ctx.call("xc_bca_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
                                   rows, hi - lo, k, dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
                                   self._dp(0, cur), self._dp(1, cur), self._dp(2, cur), self._s())
+                elif self.use_rec:
+                    self.ctx.call("xc_bca_batch_dense_rec", C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, rows,
+                                  hi - lo, k, dev.ptr(self.rec), self._sp(0), self._sp(1), self._sp(2),
+                                  dev.ptr(self.pred), self._dp(0, cur), self._dp(1, cur), self._dp(2, cur), self._s())
                 else:
                     self.ctx.call("xc_bca_batch_dense", dev.ptr(d.t), d.code, d.m, d.ld, rows, hi - lo, k,
                                   dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._dp(0, cur),
@@ -370,8 +380,10 @@ def predict_using_bc_with_0approx(
     if k > m:
         raise ValueError(f"k={k} is larger than the number of labels m={m}")
     greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
-    mode = _resolve_mode(mode, n, greedy or k == 0 or metric_id not in M.AFFINE_GAIN_METRICS or (
-        metric_id in M.TN_METRICS and skip_tn))
+    is_csr_in = isinstance(y_proba, csr_matrix)
+    batchable = metric_id in M.AFFINE_GAIN_METRICS or (
+        metric_id in M.RECORD_GAIN_METRICS and not is_csr_in and mix is None)
+    mode = _resolve_mode(mode, n, greedy or k == 0 or not batchable or (metric_id in M.TN_METRICS and skip_tn))
 
     device = dev.pick_device(y_proba)
     comm = make_comm(distributed, device)
@@ -440,13 +452,21 @@ def predict_using_bc_with_0approx(
     else:
         if greedy:
             raise NotImplementedError("init_y_pred='greedy' needs the sequential mode (mode='exact')")
-        if metric_id not in M.AFFINE_GAIN_METRICS:
+        if not batchable:
             raise NotImplementedError(
-                "xcolumns_b200 batched mode fuses the metrics whose marginal gain is affine in the probability "
-                "(precision, recall, F-beta/F1, balanced accuracy); use mode='exact' for Jaccard / G-mean / H-mean")
+                "xcolumns_b200 batched mode: Jaccard / G-mean / H-mean are fused for dense inputs only (and not in "
+                "the mixed utilities); use mode='exact' for CSR rows")
         if metric_id in M.TN_METRICS and skip_tn:
             raise NotImplementedError("batched mode evaluates tn-based metrics with the real tn: pass skip_tn=False")
-        batch = int(batch_size) if batch_size else default_batch_rows(n_order, sess.wave_rows())
+        if batch_size:
+            batch = int(batch_size)
+        elif metric_id == M.XC_METRIC_GMEAN:
+            # sqrt couples the rows of a batch strongly (a never-predicted label looks equally attractive to every
+            # row of the batch): measured on 6000 x 2000, n/8 and n/32 overshoot, ~100 rows per commit agree with
+            # the sequential reference to 1e-6.  The damping below shrinks further if a sweep still regresses.
+            batch = max(16, min(96, n_order // 64))
+        else:
+            batch = default_batch_rows(n_order, sess.wave_rows())
         n_batches = comm.max_int((n_order + batch - 1) // batch)
         base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
         order_dev = torch.arange(n_order, dtype=torch.int32, device=device)
@@ -459,12 +479,13 @@ def predict_using_bc_with_0approx(
         util_dev = torch.zeros((max_iters + 2, 2), dtype=torch.float64, device=device)
         util_host = torch.zeros((max_iters + 2, 2), dtype=torch.float64).pin_memory()
         events, saved = {}, {}
+        attempt = 0
 
         def enqueue(j):
             nonlocal order_dev
             saved[j] = sess.pred.clone()
             if shuffle_order:
-                order_dev = sess.permutation(n_order, base_seed + 0x632BE59BD9B4E019 * j)
+                order_dev = sess.permutation(n_order, base_seed + 0x632BE59BD9B4E019 * j + 0x9FB21C651E98DF25 * attempt)
             sess.zero_delta()
             sess.sweep_batched(order_dev, batch, n_batches)
             sess.recompute(XC_SUM_FAST)
@@ -477,12 +498,30 @@ def predict_using_bc_with_0approx(
             events[j] = ev
 
         enqueue(1)
-        for j in range(1, max_iters + 1):
+        j = 1
+        while j <= max_iters:
             log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
-            if j + 1 <= max_iters:
+            if j + 1 <= max_iters and j + 1 not in events:
                 enqueue(j + 1)
             events[j].synchronize()
             old_u, new_u = (float(v) for v in util_host[j])
+            regressed = (new_u < old_u - 1e-12) if maximize else (new_u > old_u + 1e-12)
+            if regressed and batch > 16 and not batch_size:
+                # Block-Jacobi overshoot (the rows of a batch all reacted to the same frozen state): the
+                # sequential sweep this mode stands in for cannot lose utility.  Roll the sweep (and the
+                # speculative one after it) back and repeat it with 4x more commits.
+                sess.pred = saved[j]
+                events.clear()
+                saved.clear()
+                batch = max(16, batch // 4)
+                n_batches = comm.max_int((n_order + batch - 1) // batch)
+                meta["batch_size"] = batch
+                attempt += 1
+                sess.recompute(XC_SUM_FAST)
+                sess.utility_device(0)
+                log_info(f"    Iteration {j} lost utility ({old_u} -> {new_u}); repeating with batches of {batch} rows", verbose)
+                enqueue(j)
+                continue
             saved.pop(j, None)
             meta["iters"] = j
             meta["utilities"].append(new_u)
@@ -492,6 +531,7 @@ def predict_using_bc_with_0approx(
                 if j + 1 in saved:
                     sess.pred = saved[j + 1]      # undo the speculative sweep
                 break
+            j += 1
 
     meta["launches"] = sess.ctx.launches()
     meta["commit"] = "peer-memory" if sess.peer is not None else ("all-reduce" if comm.world > 1 else "local")

@@ -79,6 +79,8 @@ bca_coef_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *
     bca_coef_of(p, t, f, g, coef_n + j, coef_s + j);
 }
 
+__device__ __forceinline__ float4 bca_rec_of(const xc_metric_params &p, double t, double f, double g);
+
 // ---- commit over peer memory (rows sharded over the GPUs of one box) ----------------------------------
 // After a batch every rank holds the deltas of its own rows.  Instead of an NCCL all-reduce followed by
 // the coefficient kernel, ONE kernel per rank
@@ -147,7 +149,10 @@ bca_commit_p2p_kernel(xc_metric_params p, double *tp, double *fp, double *fn, ui
     tp[j] = t; fp[j] = f; fn[j] = g;
     double *nxt = reinterpret_cast<double *>(mine + delta_off + (int64_t)(buf ^ 1) * delta_stride);
     nxt[j] = 0.0; nxt[m + j] = 0.0; nxt[2 * m + j] = 0.0;
-    bca_coef_of(p, t, f, g, coef_n + j, coef_s + j);
+    if (p.metric == XC_METRIC_JACCARD || p.metric == XC_METRIC_GMEAN || p.metric == XC_METRIC_HMEAN)
+        reinterpret_cast<float4 *>(coef_n)[j] = bca_rec_of(p, t, f, g);   // coef_n is the 16-byte record array here
+    else
+        bca_coef_of(p, t, f, g, coef_n + j, coef_s + j);
 }
 
 // ---- shared epilogue: compare new selection with the old one, emit deltas, store the row ----------
@@ -241,6 +246,125 @@ bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
             if (row_id[r] >= 0)  // warp-uniform
                 bca_commit_row<TE>(rp[r], k, old_j[r], old_e[r], tk[r].idx, pred_idx + row_id[r] * k, dtp, dfp, dfn);
         }
+    }
+}
+
+// ---- metrics whose gain is NOT affine in eta: Jaccard, G-mean, H-mean ------------------------------------
+// Against a frozen state the gain of an unselected label is still a closed form of eta and four per-label
+// numbers.  Evaluating psi(C + row) - psi(C - row) directly in float32 would lose the gain (~1/n) in the
+// rounding of psi (~1); the DIFFERENCE is therefore expanded algebraically so that float32 keeps ~1e-6
+// relative accuracy of the gain itself:
+//   Jaccard  (D = tp+fp+fn+E):        g = (eta (D + tp) - tp) / (D (D + 1 - eta))
+//   with x = tp/P, y = tn/N (P = tp+fn+E and N = tn+fp+E do not depend on the prediction),
+//        dx = eta/P, dy = -(1-eta)/N, x' = x+dx, y' = y+dy:
+//   G-mean:  g = (x dy + y dx + dx dy) / (sqrt(x' y') + sqrt(x y))
+//   H-mean:  g = 2 (x x' dy + y y' dx) / ((x' + y') (x + y))
+// The k currently selected labels of a row (own contribution to remove) are evaluated in float64 with
+// the reference's expression straight from the state vectors.
+__device__ __forceinline__ float4 bca_rec_of(const xc_metric_params &p, double t, double f, double g)
+{
+    const double E = p.eps * p.n_div;
+    if (p.metric == XC_METRIC_JACCARD) {
+        const double D = t + f + g + E;
+        return make_float4((float)(D + t), (float)t, (float)D, (float)(D + 1.0));
+    }
+    const double tn = p.n_rows - t - f - g;
+    const double P = t + g + E, N = tn + f + E;
+    return make_float4((float)(t / P), (float)(tn / N), (float)(1.0 / P), (float)(1.0 / N));
+}
+
+template <int METRIC>
+struct XfRecord {
+    const float4 *rec;
+    float sgn;
+    __device__ __forceinline__ float gain(const float4 r, float e) const
+    {
+        float g;
+        if (METRIC == XC_METRIC_JACCARD) {
+            g = fmaf(e, r.x, -r.y) * __frcp_rn(r.z * (r.w - e));
+        } else {
+            const float dx = e * r.z, dy = (e - 1.f) * r.w;
+            const float xn = r.x + dx, yn = r.y + dy;
+            if (METRIC == XC_METRIC_GMEAN) {
+                const float num = fmaf(r.x, dy, fmaf(r.y, dx, dx * dy));
+                const float den = sqrtf(fmaxf(xn * yn, 0.f)) + sqrtf(r.x * r.y);
+                g = num * __frcp_rn(fmaxf(den, 1e-30f));
+            } else {
+                const float num = 2.f * fmaf(r.x * xn, dy, r.y * yn * dx);
+                g = num * __frcp_rn(fmaxf((xn + yn) * (r.x + r.y), 1e-30f));
+            }
+        }
+        return sgn * g;
+    }
+    template <typename TE, int V>
+    __device__ __forceinline__ void apply_vec(int64_t c, const TE (&e)[V], float (&g)[V], float (&ca)[V],
+                                              float (&cb)[V], bool first) const
+    {
+#pragma unroll
+        for (int v = 0; v < V; ++v) g[v] = gain(__ldg(rec + c + v), (float)e[v]);
+    }
+    template <typename TE>
+    __device__ __forceinline__ float apply_one(int64_t c, TE e) const { return gain(__ldg(rec + c), (float)e); }
+};
+
+__global__ void __launch_bounds__(kThreads)
+bca_rec_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn, int64_t m,
+               float4 *rec)
+{
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (j >= m) return;
+    double t = tp[j], f = fp[j], g = fn[j];
+    if (dtp) {
+        t += dtp[j]; f += dfp[j]; g += dfn[j];
+        tp[j] = t; fp[j] = f; fn[j] = g;
+        dtp[j] = 0.0; dfp[j] = 0.0; dfn[j] = 0.0;
+    }
+    rec[j] = bca_rec_of(p, t, f, g);
+}
+
+// gain of keeping a currently selected label (float64, reference expression, own contribution removed)
+__device__ __forceinline__ double bca_selected_gain(const xc_metric_params &p, double t, double f, double g, double e,
+                                                    double om)
+{
+    const double nd = p.n_div;
+    const double tn = p.n_rows - t - f - g;
+    const double keep = xc_metric_eval(p, t / nd, f / nd, g / nd, tn / nd);
+    const double drop = xc_metric_eval(p, (t - e) / nd, (f - om) / nd, (g + e) / nd, (tn + om) / nd);
+    const double d = keep - drop;
+    return p.maximize ? d : -d;
+}
+
+template <typename TE, int METRIC>
+__global__ void __launch_bounds__(kThreads)
+bca_batch_dense_rec_kernel(xc_metric_params p, const TE *__restrict__ eta, int64_t m, int64_t ld,
+                           const int32_t *__restrict__ rows, int64_t n_rows, int k, const float4 *__restrict__ rec,
+                           const double *__restrict__ tp, const double *__restrict__ fp,
+                           const double *__restrict__ fn, int32_t *__restrict__ pred_idx, double *dtp, double *dfp,
+                           double *dfn, bool vec_ok)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    XfRecord<METRIC> xf{rec, p.maximize ? 1.f : -1.f};
+    const TE one = (TE)1;
+    for (int64_t i = warp; i < n_rows; i += nwarps) {
+        const int64_t row = rows ? (int64_t)rows[i] : i;
+        const TE *rp[1] = {eta + row * ld};
+        int old_j[1] = {-1};
+        TE old_e = (TE)0;
+        float g = 0.f;
+        if (lane < k) {
+            old_j[0] = pred_idx[row * k + lane];
+            if (old_j[0] >= 0) {
+                const int j = old_j[0];
+                old_e = rp[0][j];
+                g = (float)bca_selected_gain(p, tp[j], fp[j], fn[j], (double)old_e, (double)(TE)(one - old_e));
+            }
+        }
+        WarpTopK<float> tk[1];
+        seed_list(tk[0], g, old_j[0], k);
+        xc_scan_rows<TE, float, 1, true>(rp, m, vec_ok, xf, tk, old_j, k);
+        bca_commit_row<TE>(rp[0], k, old_j[0], old_e, tk[0].idx, pred_idx + row * k, dtp, dfp, dfn);
     }
 }
 
@@ -895,15 +1019,67 @@ extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, d
     return XC_OK;
 }
 
+extern "C" int xc_bca_rec(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn, double *dtp,
+                          double *dfp, double *dfn, int64_t m, float *rec, void *stream)
+{
+    if (!ctx || !p || !tp || !fp || !fn || !rec || m <= 0) return XC_ERR_INVALID;
+    if ((dtp || dfp || dfn) && !(dtp && dfp && dfn)) return XC_ERR_INVALID;
+    if (p->metric != XC_METRIC_JACCARD && p->metric != XC_METRIC_GMEAN && p->metric != XC_METRIC_HMEAN)
+        return XC_ERR_UNSUPPORTED;
+    if (p->metric != XC_METRIC_JACCARD && p->skip_tn) return XC_ERR_INVALID;  // G-mean / H-mean need the real tn
+    bca_rec_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        *p, tp, fp, fn, dtp, dfp, dfn, m, (float4 *)rec);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype, int64_t m,
+                                      int64_t ld, const int32_t *rows, int64_t n_rows, int k, const float *rec,
+                                      const double *tp, const double *fp, const double *fn, int32_t *pred_idx,
+                                      double *dtp, double *dfp, double *dfn, void *stream)
+{
+    if (!ctx || !p || !eta || !rec || !tp || !fp || !fn || !pred_idx || !dtp || !dfp || !dfn || m <= 0 || ld < m ||
+        n_rows < 0)
+        return XC_ERR_INVALID;
+    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (p->metric != XC_METRIC_JACCARD && p->metric != XC_METRIC_GMEAN && p->metric != XC_METRIC_HMEAN)
+        return XC_ERR_UNSUPPORTED;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define XC_GO(TE, METRIC)                                                                                        \
+    {                                                                                                            \
+        constexpr int V = 16 / sizeof(TE);                                                                       \
+        const bool vec_ok = xc_aligned16(eta) && (ld % V == 0);                                                  \
+        auto kern = bca_batch_dense_rec_kernel<TE, METRIC>;                                                      \
+        int grid = grid_for(ctx, kern, n_rows);                                                                  \
+        kern<<<grid, kThreads, 0, st>>>(*p, (const TE *)eta, m, ld, rows, n_rows, k, (const float4 *)rec, tp, fp, \
+                                        fn, pred_idx, dtp, dfp, dfn, vec_ok);                                    \
+    }
+    if (dtype == XC_F32) {
+        if (p->metric == XC_METRIC_JACCARD) XC_GO(float, XC_METRIC_JACCARD)
+        else if (p->metric == XC_METRIC_GMEAN) XC_GO(float, XC_METRIC_GMEAN)
+        else XC_GO(float, XC_METRIC_HMEAN)
+    } else if (dtype == XC_F64) {
+        if (p->metric == XC_METRIC_JACCARD) XC_GO(double, XC_METRIC_JACCARD)
+        else if (p->metric == XC_METRIC_GMEAN) XC_GO(double, XC_METRIC_GMEAN)
+        else XC_GO(double, XC_METRIC_HMEAN)
+    } else {
+        return XC_ERR_UNSUPPORTED;
+    }
+#undef XC_GO
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
 extern "C" int64_t xc_bca_delta_stride(int64_t m) { return ((3 * m * 8 + 255) / 256) * 256; }
 
 extern "C" int xc_bca_commit_p2p(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, double *tp, double *fp,
                                  double *fn, int64_t m, int buf, float *coef_n, float *coef_s, void *stream)
 {
-    if (!ctx || !w || !w->opened || !p || !tp || !fp || !fn || !coef_n || !coef_s || m <= 0 || (buf & ~1)) return XC_ERR_INVALID;
-    if (p->metric != XC_METRIC_PRECISION && p->metric != XC_METRIC_RECALL && p->metric != XC_METRIC_FBETA &&
-        p->metric != XC_METRIC_BALANCED_ACC && p->metric != XC_METRIC_PREC_AT_K)
-        return XC_ERR_UNSUPPORTED;
+    if (!ctx || !w || !w->opened || !p || !tp || !fp || !fn || !coef_n || m <= 0 || (buf & ~1)) return XC_ERR_INVALID;
+    const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
+    if (!rec && !coef_s) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
     const int64_t stride = xc_bca_delta_stride(m);
     if ((size_t)(XC_P2P_HEADER + 2 * stride) > w->bytes) return XC_ERR_INVALID;
     w->epoch += 1;

@@ -18,6 +18,8 @@ XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN, XC_METRIC_PREC_AT_K = 
 AFFINE_GAIN_METRICS = (XC_METRIC_PRECISION, XC_METRIC_RECALL, XC_METRIC_FBETA, XC_METRIC_BALANCED_ACC,
                        XC_METRIC_PREC_AT_K)
 TN_METRICS = (XC_METRIC_BALANCED_ACC, XC_METRIC_GMEAN, XC_METRIC_HMEAN)
+# gain not affine in eta but a closed form of eta and four per-label numbers (dense batched mode)
+RECORD_GAIN_METRICS = (XC_METRIC_JACCARD, XC_METRIC_GMEAN, XC_METRIC_HMEAN)
 
 
 def binary_precision_on_conf_matrix(tp, fp, fn, tn, epsilon: float = 1e-9):
