@@ -187,27 +187,32 @@ def secondary(args):
         unit_count, metric, unit = n, "BCA macro-F1@5 instances/sec per sweep (CSR)", "instances/s"
         wl = f"amazon670k-shape CSR f32 n={n} m={m} nnz/row={nnz} k={k} macro-F1 BCA (batched)"
     else:
+        import torch.distributed as dist
         from xcolumns_b200.frank_wolfe import find_classifier_using_fw
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        device = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=device)
         n, m = (args.rows if args.rows != 307000 else 14000), (args.labels if args.labels != 13000 else 31000)
-        eta_t = dense_probs_device(n, m, seed=1005, device=device)
+        eta_t = dense_probs_device(n, m, seed=1005 + rank, device=device)   # weak scaling: n rows per GPU
         state = {}
-
-        def step():
-            pass
-
-        def reset():
-            pass
 
         # FW runs through the public API on the device tensor (zero copy); per-iteration time from
         # CUDA events around the whole call divided by the iterations it performed
         def run(iters):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(device)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             clf, meta = find_classifier_using_fw(eta_t, eta_t, M.macro_f1_score_on_conf_matrix, k, max_iters=iters,
                                                  tolerance=-np.inf, alpha_tolerance=0.0, skip_tn=True, seed=0,
-                                                 return_meta=True)
+                                                 return_meta=True, distributed=(world > 1))
             e1.record()
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(device)
             state["meta"] = meta
             return e0.elapsed_time(e1), meta["iters"]
 
@@ -217,18 +222,28 @@ def secondary(args):
         # classifier's pass), so one-time setup (column sums, pinned buffers) is not smeared over
         # the iterations; the whole-call figure is reported next to it
         ms = state["meta"]["time"] * 1e3
+        if world > 1:
+            t = torch.tensor([ms, ms_call], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, ms_call = float(t[0]), float(t[1])
         bytes_per_step = n * m * 4
+        ach = bytes_per_step * iters / (ms / 1e3) / 1e9   # per GPU
         line = {"metric": "Frank-Wolfe macro-F1@5 iterations/sec", "value": iters / (ms / 1e3), "unit": "iterations/s",
-                "n_gpus": 1, "steps": iters, "warmup": args.warmup, "ms_per_step": ms / iters,
-                "ms_per_call": ms_call,
+                "n_gpus": world, "steps": iters, "warmup": args.warmup, "ms_per_step": ms / iters,
+                "ms_per_call": ms_call, "instances_per_s": n * world * iters / (ms / 1e3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (y_true := y_proba)",
-                "config": {"workload": f"wiki10-31k-shape dense f32 n={n} m={m} k={k} macro-F1 FW, {iters} iterations incl. init pass"},
-                "roofline": {"bound": "hbm", "achieved": bytes_per_step * iters / (ms / 1e3) / 1e9, "peak": peak,
-                             "unit": "GB/s", "frac": bytes_per_step * iters / (ms / 1e3) / 1e9 / peak,
-                             "traffic": None, "note": "iteration loop: one pass over y_proba per iteration / loop time"},
+                "config": {"workload": f"wiki10-31k-shape dense f32 n={n} rows per GPU, m={m} k={k} macro-F1 FW, "
+                                       f"{iters} iterations incl. init pass",
+                           "collective": "none" if world == 1 else "NCCL all-reduce of 2*m float64 per iterate"},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": None, "note": "iteration loop: one pass over the rank's y_proba shard per "
+                                                      "iteration / loop time (max over ranks)"},
                 "utilities": state["meta"]["utilities"][-3:]}
-        print(json.dumps(line))
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     reset()

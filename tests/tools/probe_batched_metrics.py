@@ -1,5 +1,6 @@
 import sys, numpy as np
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import xcolumns_b200 as xb
 from xcolumns_b200 import metrics as M
 from oracle import oracle as orc
