@@ -4,7 +4,6 @@ NCCL all-reduce path must give the same predictions and utilities."""
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -1,6 +1,5 @@
-"""GPU probe (development aid, not a test): times the Frank-Wolfe iterate kernel variants and the
-line-search stages at the C5 shape with CUDA events, checks the variants agree, and prints the
-number of float64 candidates the two-stage search keeps.
+"""GPU probe (development aid, not a test): times the Frank-Wolfe iterate kernel with CUDA events for the
+rows-per-warp variants ($XCOLUMNS_B200_DENSE_R) and checks the selection against torch.topk.
 
     python scripts/probe_fw.py [n] [m]
 """
@@ -15,26 +14,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def child(path_env, occ_env, n, m):
+def child(r, n, m):
     env = dict(os.environ)
-    env["XCOLUMNS_B200_FW_PATH"] = path_env.split(":")[0]
-    env["XCOLUMNS_B200_FW_OCC"] = occ_env
+    if r:
+        env["XCOLUMNS_B200_DENSE_R"] = r
     env["XC_PROBE_CHILD"] = "1"
     out = subprocess.run([sys.executable, __file__, str(n), str(m)], env=env, capture_output=True, text=True)
-    print(f"[{path_env} occ={occ_env}]", out.stdout.strip(), out.stderr.strip()[-400:])
+    print(f"[rows per warp: {r or 'auto'}]", out.stdout.strip(), out.stderr.strip()[-400:])
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 14000
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 31000
     if "XC_PROBE_CHILD" not in os.environ:
-        for ab in ("rand",):
-            os.environ["XC_PROBE_AB"] = ab
-            for r, d in (("2", "2"), ("2", "4"), ("1", "2"), ("1", "4")):
-                os.environ["XCOLUMNS_B200_DENSE_R"] = r
-                os.environ["XCOLUMNS_B200_FW_DEPTH"] = d
-                child(f"plain:R{r}:D{d}", "5", n, m)
-            child("staged:" + ab, "5", n, m)
+        for r in ("", "1", "2", "4"):
+            child(r, n, m)
         return
     from xcolumns_b200 import _device as dev
     from xcolumns_b200.synth import dense_probs_device
@@ -43,12 +37,8 @@ def main():
     ctx = dev.ctx_for(device)
     eta = dense_probs_device(n, m, seed=1005, device=device)
     g = torch.Generator(device=device).manual_seed(3)
-    if os.environ.get("XC_PROBE_AB", "rand") == "rand":
-        a = torch.rand(m, device=device, generator=g) + 0.5
-        b = torch.rand(m, device=device, generator=g) - 0.5
-    else:   # top-k by eta itself: large values sit in the first columns (Zipf priors), no list churn
-        a = torch.ones(m, device=device)
-        b = torch.zeros(m, device=device)
+    a = torch.rand(m, device=device, generator=g) + 0.5
+    b = torch.rand(m, device=device, generator=g) - 0.5
     raw = torch.zeros((2, m), dtype=torch.float64, device=device)
     pred = torch.empty((n, 5), dtype=torch.int32, device=device)
     sp = dev.stream_ptr(device)

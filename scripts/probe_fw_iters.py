@@ -2,7 +2,6 @@
 line-search control blocks ([candidates, full, slices, tiles]) when XCOLUMNS_B200_FW_DEBUG=1."""
 import os
 import sys
-import time
 
 import numpy as np
 import torch

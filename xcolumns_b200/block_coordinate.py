@@ -30,7 +30,7 @@ from . import _device as dev
 from . import metrics as M
 from ._lib import XC_SUM_FAST, XC_SUM_ORDERED, MetricParams
 from .distributed import Comm, PeerWindow, make_comm, peer_commit_enabled
-from .types import DefaultAccDataDType, Matrix
+from .types import Matrix
 from .utils import add_kwargs_to_signature, log_info, log_warning
 from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
 
@@ -549,7 +549,6 @@ def _bca_k0_dense(y_proba, binary_metric_func, metric_id, beta, eps, aggregation
                   tolerance, init_y_pred, max_iters, shuffle_order, skip_tn, return_meta, seed, verbose, meta, device):
     """k = 0: no budget, a label is predicted whenever its gain is >= 0 (block_coordinate.py:199-200).
     Labels are independent, so one thread per label walks the instance order (csrc/bca_exact.cu)."""
-    from .confusion_matrix import confusion_sums_device
     ctx = dev.ctx_for(device)
     data = dev.dense_to_device(y_proba, device)
     n, m = data.n, data.m

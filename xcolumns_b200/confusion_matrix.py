@@ -6,15 +6,15 @@ both matrices (the reference makes three passes with n x m temporaries); tn is d
 from __future__ import annotations
 
 import os
-from typing import Optional, Union
+from typing import Optional
 
 import numpy as np
 import torch
 from scipy.sparse import csr_matrix
 
 from . import _device as dev
-from ._lib import XC_F32, XC_F64, XC_SUM_FAST, XC_SUM_ORDERED
-from .types import DenseMatrix, DType, Matrix, Number
+from ._lib import XC_SUM_FAST, XC_SUM_ORDERED
+from .types import DType, Matrix
 
 
 class ConfusionMatrix:

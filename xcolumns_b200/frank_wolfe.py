@@ -24,7 +24,7 @@ from ._lib import MetricParams
 from .distributed import make_comm
 from .types import DefaultDataDType, DenseMatrix, DType, Matrix
 from .utils import add_kwargs_to_signature, log_info, log_warning
-from .weighted_prediction import _check_k, predict_weighted_per_instance
+from .weighted_prediction import _check_k
 
 
 class RandomizedWeightedClassifier:
