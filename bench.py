@@ -176,7 +176,7 @@ def secondary(args):
             order = sess.permutation(n, 3 + 7919 * sweep_no[0])
             sess.zero_delta()
             sess.sweep_batched(order, batch)
-            sess.recompute(XC_SUM_FAST)
+            sess.finish_sweep(full=(sweep_no[0] % 16 == 0))
             sess.utility_device(1)
 
         def reset():
@@ -317,7 +317,7 @@ def main():
         order = sess.permutation(n, 17 + 1000003 * rank + 7919 * sweep_no[0])
         sess.zero_delta()
         sess.sweep_batched(order, batch, n_batches, events=events)
-        sess.recompute(XC_SUM_FAST)
+        sess.finish_sweep(full=(sweep_no[0] % 16 == 0))   # like the public driver: fold, recompute every 16th sweep
         sess.utility_device(1)
 
     def reset():
