@@ -252,17 +252,21 @@ def find_classifier_using_fw(
     new_utility = utility_i
     i = 0
     n_used = max_iters + 1
+    next_step = 1
+    depth = max(1, int(os.environ.get("XCOLUMNS_B200_FW_SPECULATE", "3")))
     for i in range(1, max_iters + 1):
         log_info(f"  Starting iteration {i}/{max_iters} ...", verbose)
         # The stopping rules need iteration i's scalars on the host, which would drain the GPU
-        # queue once per iteration (measured: 0.5 ms of idle GPU per 0.65 ms iteration).  So
-        # iteration i+1 is enqueued speculatively BEFORE iteration i's scalars are read; if i
-        # turns out to be the last one, the speculative classifier row is simply truncated
-        # like the reference truncates its arrays (frank_wolfe.py:659-661).
-        if i == 1:
-            step(1, False)
-        if i + 1 <= max_iters:
-            step(i + 1, False)
+        # queue once per iteration (measured: 0.5 ms of idle GPU per 0.65 ms iteration).  So up to
+        # `depth` iterations are enqueued speculatively BEFORE iteration i's scalars are read; if i
+        # turns out to be the last one, the speculative classifier rows are simply truncated like
+        # the reference truncates its arrays (frank_wolfe.py:659-661).  A depth above 1 matters
+        # when rows are sharded: every iteration ends in an exchange all ranks must have enqueued,
+        # so one rank's host hiccup would otherwise stall all GPUs (8 GPUs, depth 1: 1.04 ms per
+        # iteration instead of 0.42).
+        while next_step <= min(max_iters, i + depth):
+            step(next_step, False)
+            next_step += 1
         events[i].synchronize()
         host = host_all[i].numpy()
         old_utility, utility_i, alpha, new_utility = float(host[0]), float(host[1]), float(host[2]), float(host[4])
