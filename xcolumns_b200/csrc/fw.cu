@@ -231,13 +231,16 @@ fw_metric_grad_kernel(xc_metric_params p, const double *tp, const double *fp, co
 //      are re-evaluated with the reference's float64 expression; the first strict maximum among them
 //      wins.  The candidates are spread over all SMs (label slices chosen on the device from the
 //      candidate count); partial sums are combined in a fixed order, so the result is reproducible.
-// If more than ALPHA_MAX_CAND points qualify (objective flat in alpha) the whole grid is evaluated in
-// float64.  Metrics that use tn always take that path.
+// Up to ALPHA_MAX_CAND (>= the default 10^4-point grid) screen candidates go through the refinement: on
+// many rows the objective gets so flat in alpha that ALL grid points are within 1e-5 of the maximum (seen
+// at 112 k rows from the 8th iteration on) -- the refinement then costs about as much as the screen
+// (~80 us) where the float64 evaluation of the whole grid costs 830 us.  Only finer grids than that fall
+// back to the float64 grid.  Metrics that use tn always take that path.
 constexpr int AT64 = 4;             // grid points per block tile, float64 kernel
 constexpr int AT32 = 32;            // grid points per block, stage-1 kernel
 constexpr int ALPHA_LS = 8;         // label slices of the stage-1 kernel (blockIdx.y)
 constexpr int ALPHA_LS2_MAX = 32;   // max label slices of the float64 kernel
-constexpr int ALPHA_MAX_CAND = 2048;
+constexpr int ALPHA_MAX_CAND = 16384;  // >= the default grid (10^4 points): a flat objective keeps them all
 constexpr float ALPHA_WINDOW = 1e-5f;
 constexpr int ATR = 16;             // candidate slots per block, refinement kernel
 constexpr int ALPHA_LSR = 8;        // label slices of the refinement kernel (blockIdx.y)
@@ -490,11 +493,13 @@ fw_alpha_refine_kernel(const float4 *__restrict__ lin, const float *__restrict__
     }
 }
 
-// prune the candidate list with the refined differences; writes the final list + control block
+// prune the candidate list with the refined differences; writes the final list + control block.
+// hi_buf: scratch of >= count floats (the stage-1 value array, no longer needed at this point).
 __global__ void __launch_bounds__(1024)
 fw_alpha_cand2_kernel(const float *__restrict__ part_d, const float *__restrict__ part_e,
                       const double *__restrict__ alphas, const int *__restrict__ cand_q,
-                      const AlphaCtl *__restrict__ ctl, int *__restrict__ cand_q2, AlphaCtl *ctl2, int eval_ctas)
+                      const AlphaCtl *__restrict__ ctl, float *__restrict__ hi_buf, int *__restrict__ cand_q2,
+                      AlphaCtl *ctl2, int eval_ctas)
 {
     __shared__ float s_lo[32];
     __shared__ int s_warp[32];
@@ -506,39 +511,35 @@ fw_alpha_cand2_kernel(const float *__restrict__ part_d, const float *__restrict_
     const int count = ctl->count, qs = ctl->qstar;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double astar = qs == 0 ? 0.0 : alphas[qs - 1];
-    // two slots per thread (ALPHA_MAX_CAND = 2 * 1024), contiguous so the list stays in grid order
-    float hi[2], lo = -INFINITY;
-    int qq[2];
+    // pass 1 (coalesced): refined difference and its error bound per slot, best lower bound
+    float lo = -INFINITY;
+    for (int slot = threadIdx.x; slot < count; slot += 1024) {
+        const int q = cand_q[slot];
+        float d = 0.f, er = 0.f;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int slot = threadIdx.x * 2 + u;
-        hi[u] = -INFINITY;
-        qq[u] = -1;
-        if (slot < count) {
-            const int q = cand_q[slot];
-            float d = 0.f, er = 0.f;
-#pragma unroll
-            for (int sl = 0; sl < ALPHA_LSR; ++sl) {
-                d += part_d[sl * ALPHA_MAX_CAND + slot];
-                er += part_e[sl * ALPHA_MAX_CAND + slot];
-            }
-            const float delta = (float)((q == 0 ? 0.0 : alphas[q - 1]) - astar);
-            d *= delta;
-            er = er * fabsf(delta) * ALPHA_REFINE_ULP;
-            if (q == qs) { d = 0.f; er = 0.f; }
-            if (!(d == d) || !(er == er)) { d = 0.f; er = INFINITY; }  // not a number: keep, bound nothing
-            hi[u] = d + er;
-            qq[u] = q;
-            lo = fmaxf(lo, d - er);
+        for (int sl = 0; sl < ALPHA_LSR; ++sl) {
+            d += part_d[sl * ALPHA_MAX_CAND + slot];
+            er += part_e[sl * ALPHA_MAX_CAND + slot];
         }
+        const float delta = (float)((q == 0 ? 0.0 : alphas[q - 1]) - astar);
+        d *= delta;
+        er = er * fabsf(delta) * ALPHA_REFINE_ULP;
+        if (q == qs) { d = 0.f; er = 0.f; }
+        if (!(d == d) || !(er == er)) { d = 0.f; er = INFINITY; }  // not a number: keep, bound nothing
+        hi_buf[slot] = d + er;
+        lo = fmaxf(lo, d - er);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lo = fmaxf(lo, __shfl_xor_sync(XC_FULL, lo, o));
     if (lane == 0) s_lo[wid] = lo;
-    __syncthreads();
+    __syncthreads();   // also publishes hi_buf to the block
     lo = s_lo[0];
     for (int w = 1; w < 32; ++w) lo = fmaxf(lo, s_lo[w]);
-    const int cnt = (hi[0] >= lo) + (hi[1] >= lo);
+    // pass 2: contiguous slices so that the surviving list stays in grid order
+    const int per = (count + 1023) / 1024;
+    const int b0 = threadIdx.x * per, b1 = min(count, b0 + per);
+    int cnt = 0;
+    for (int slot = b0; slot < b1; ++slot) cnt += hi_buf[slot] >= lo;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -559,8 +560,8 @@ fw_alpha_cand2_kernel(const float *__restrict__ part_d, const float *__restrict_
     }
     __syncthreads();
     int o = s_warp[wid] + incl - cnt;
-    if (hi[0] >= lo) cand_q2[o++] = qq[0];
-    if (hi[1] >= lo) cand_q2[o++] = qq[1];
+    for (int slot = b0; slot < b1; ++slot)
+        if (hi_buf[slot] >= lo) cand_q2[o++] = cand_q[slot];
     if (threadIdx.x == 0) {
         const int run = s_run;
         const int tiles = (run + AT64 - 1) / AT64;
@@ -1168,8 +1169,8 @@ int alpha_search_launch(xc_ctx *ctx, const xc_metric_params *p, const double *C,
             fw_alpha_refine_kernel<<<dim3(ALPHA_MAX_CAND / ATR, ALPHA_LSR), kThreads, 0, st>>>(
                 s.lin, s.linE, m, alphas_dev, s.cand_q, s.ctl1, s.part_d, s.part_e);
             XC_LAUNCHED(ctx);
-            fw_alpha_cand2_kernel<<<1, 1024, 0, st>>>(s.part_d, s.part_e, alphas_dev, s.cand_q, s.ctl1, s.cand_q2, s.ctl,
-                                                      grid64);
+            fw_alpha_cand2_kernel<<<1, 1024, 0, st>>>(s.part_d, s.part_e, alphas_dev, s.cand_q, s.ctl1, s.vfast, s.cand_q2,
+                                                      s.ctl, grid64);
             XC_LAUNCHED(ctx);
             cq = s.cand_q2;
             cc = s.ctl;
