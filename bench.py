@@ -381,7 +381,11 @@ def main():
                 "kernel_share_of_step": float(np.sum(kern_ms)) / ms,
                 "kernel_ms_per_sweep": [round(float(np.sum(kern_ms[i * len(kern_ms) // args.steps:(i + 1) * len(kern_ms) // args.steps])), 4)
                                         for i in range(args.steps)],
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "frac_of_nominal_8tbs": achieved / 8000.0,
+                "whole_step": {"achieved": n * m * 4 / (ms / args.steps / 1e3) / 1e9,
+                               "frac": n * m * 4 / (ms / args.steps / 1e3) / 1e9 / peak,
+                               "note": "score-matrix bytes of one sweep / ms_per_step (per GPU)"}}
 
     line = {
         "metric": "BCA macro-F1@5 instances/sec per sweep", "value": value, "unit": "instances/s",
