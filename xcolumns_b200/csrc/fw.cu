@@ -435,10 +435,10 @@ fw_alpha_refine_kernel(const float4 *__restrict__ lin, const float *__restrict__
     __shared__ float sm[2][ATR][kThreads / 32];
     if (ctl->full) return;
     const int count = ctl->count;
-    const int s0 = blockIdx.x * ATR;
-    if (s0 >= count) return;
     const int qs = ctl->qstar;
     const float astar = qs == 0 ? 0.f : (float)alphas[qs - 1];
+    // the candidate count is only known on the device: a fixed grid walks the slot tiles
+    for (int s0 = blockIdx.x * ATR; s0 < count; s0 += gridDim.x * ATR) {
     float al[ATR], accd[ATR], acce[ATR];
 #pragma unroll
     for (int t = 0; t < ATR; ++t) {
@@ -490,6 +490,8 @@ fw_alpha_refine_kernel(const float4 *__restrict__ lin, const float *__restrict__
             part_d[blockIdx.y * ALPHA_MAX_CAND + slot] = v;
             part_e[blockIdx.y * ALPHA_MAX_CAND + slot] = w;
         }
+    }
+    __syncthreads();   // sm is reused by the next tile
     }
 }
 
@@ -1166,7 +1168,7 @@ int alpha_search_launch(xc_ctx *ctx, const xc_metric_params *p, const double *C,
         const int *cq = s.cand_q;
         const AlphaCtl *cc = s.ctl1;
         if (alpha_refine()) {
-            fw_alpha_refine_kernel<<<dim3(ALPHA_MAX_CAND / ATR, ALPHA_LSR), kThreads, 0, st>>>(
+            fw_alpha_refine_kernel<<<dim3(2 * ctx->sm_count, ALPHA_LSR), kThreads, 0, st>>>(
                 s.lin, s.linE, m, alphas_dev, s.cand_q, s.ctl1, s.part_d, s.part_e);
             XC_LAUNCHED(ctx);
             fw_alpha_cand2_kernel<<<1, 1024, 0, st>>>(s.part_d, s.part_e, alphas_dev, s.cand_q, s.ctl1, s.vfast, s.cand_q2,
