@@ -280,6 +280,21 @@ XC_API int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, const 
                                   const double *fn, int32_t *pred_idx, double *dtp, double *dfp,
                                   double *dfn, void *stream);
 
+/* One whole batched sweep of a single process as one host call: per batch of `batch` entries of `order`
+ * the coefficient (or record) kernel with the fold of the pending deltas and the batch kernel, then a
+ * final fold, i.e. tp/fp/fn end up as the state after the sweep.  coef_a: the coefficient pairs of
+ * xc_bca_coef, or the records of xc_bca_rec for Jaccard / G-mean / H-mean.  Small problems are bound by
+ * the host-side call overhead of the per-batch entry points, not by the GPU.                       */
+XC_API int xc_bca_sweep_dense(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype, int64_t m,
+                              int64_t ld, const int32_t *order, int64_t n_order, int64_t batch, int k,
+                              float *coef_a, float *coef_s, int32_t *pred_idx, double *tp, double *fp,
+                              double *fn, double *dtp, double *dfp, double *dfn, void *stream);
+XC_API int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
+                            const int32_t *indices, const int64_t *indptr, int64_t m,
+                            const int32_t *order, int64_t n_order, int64_t batch, int k, float *coef_n,
+                            float *coef_s, int32_t *pred_idx, double *tp, double *fp, double *fn,
+                            double *dtp, double *dfp, double *dfn, void *stream);
+
 /* ---- commits over peer memory (rows sharded over the GPUs of one box) -------------------- */
 /* One window per rank: cudaMalloc'ed, exported with CUDA IPC (ipc_handle_out: 64 bytes), mapped by
  * every other rank with xc_p2p_open(handles = the world * 64 gathered bytes).  xc_p2p_payload

@@ -50,6 +50,10 @@ _SIGNATURES = {
     "xc_bca_online_dense": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _int, _MP, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_rec": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "xc_bca_batch_dense_rec": [_MP, _vp, _int, _i64, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "xc_bca_sweep_dense": [_MP, _vp, _int, _i64, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                           _vp],
+    "xc_bca_sweep_csr": [_MP, _vp, _int, _vp, _vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                         _vp, _vp],
     "xc_colsum_dense": [_vp, _int, _i64, _i64, _i64, _vp, _vp],
     "xc_colsum_csr": [_vp, _int, _vp, _i64, _i64, _vp, _vp],
     "xc_utility": [_MP, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp],

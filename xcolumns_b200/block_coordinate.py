@@ -151,6 +151,7 @@ class BcaSession:
             torch.cuda.synchronize(self.device)
             self.comm.barrier()          # nobody may still be reading this rank's window
             self.peer.check()
+            self.delta2 = None           # views into the window
             self.peer.close()
             self.peer = None
 
@@ -267,6 +268,27 @@ class BcaSession:
         if not self.p.skip_tn:
             n_total = self.comm.n_global(self.n)
             self.state[3] = -self.state[0] - self.state[1] - self.state[2] + n_total
+
+    def sweep_and_fold(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int], full: bool) -> None:
+        """sweep_batched + finish_sweep.  A single process without events to record issues the whole sweep
+        through one C call (xc_bca_sweep_*): small problems are bound by the per-call overhead of this shim."""
+        if self.comm.world > 1 or full:
+            self.sweep_batched(order_dev, batch, n_batches)
+            self.finish_sweep(full)
+            return
+        d, k = self.data, self.k
+        if self.is_csr:
+            self.ctx.call("xc_bca_sweep_csr", C.byref(self.p), dev.ptr(d.data), d.code, dev.ptr(d.indices),
+                          dev.ptr(d.indptr), d.m, dev.ptr(order_dev), int(order_dev.numel()), int(batch), k,
+                          dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._sp(0), self._sp(1),
+                          self._sp(2), self._dp(0), self._dp(1), self._dp(2), self._s())
+        else:
+            self.ctx.call("xc_bca_sweep_dense", C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, dev.ptr(order_dev),
+                          int(order_dev.numel()), int(batch), k, dev.ptr(self.rec if self.use_rec else self.coef_n),
+                          dev.ptr(self.coef_s), dev.ptr(self.pred), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
+                          self._dp(1), self._dp(2), self._s())
+        if not self.p.skip_tn:
+            self.state[3] = -self.state[0] - self.state[1] - self.state[2] + self.n
 
     def sweep_batched(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int] = None,
                       events: Optional[list] = None) -> None:
@@ -511,8 +533,7 @@ def predict_using_bc_with_0approx(
             if shuffle_order:
                 order_dev = sess.permutation(n_order, base_seed + 0x632BE59BD9B4E019 * j + 0x9FB21C651E98DF25 * attempt)
             sess.zero_delta()
-            sess.sweep_batched(order_dev, batch, n_batches)
-            sess.finish_sweep(full=(j % 16 == 0))
+            sess.sweep_and_fold(order_dev, batch, n_batches, full=(j % 16 == 0))
             sess.utility_device(1)
             util_dev[j].copy_(sess.util_buf[:2])
             sess.util_buf[0] = sess.util_buf[1]

@@ -1187,3 +1187,54 @@ extern "C" int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void
     XC_LAUNCHED(ctx);
     return XC_OK;
 }
+
+// ---- one whole batched sweep as ONE host call (single process: no exchange between the batches) ----------
+// For small problems the sweep is bound by the host, not the GPU: at 10 000 x 1 000 the ~20 calls of a sweep
+// cost ~0.5 ms through the Python shim while the kernels need ~0.06 ms.  This entry point issues the same
+// launches (coefficients / records with the fold of the pending deltas, batch kernel, ... , final fold) from
+// C; `rec` selects the Jaccard / G-mean / H-mean record kernels.  order: the sweep's visiting order (device).
+extern "C" int xc_bca_sweep_dense(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype, int64_t m,
+                                  int64_t ld, const int32_t *order, int64_t n_order, int64_t batch, int k, float *coef_a,
+                                  float *coef_s, int32_t *pred_idx, double *tp, double *fp, double *fn, double *dtp,
+                                  double *dfp, double *dfn, void *stream)
+{
+    if (!ctx || !p || !order || n_order < 0 || batch < 1) return XC_ERR_INVALID;
+    const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
+    for (int64_t lo = 0; lo <= n_order; lo += batch) {   // the last trip (lo >= n_order or empty) only folds
+        int rc = rec ? xc_bca_rec(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_a, stream)
+                     : xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_a, coef_s, stream);
+        if (rc) return rc;
+        const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
+        if (hi <= lo) break;
+        rc = rec ? xc_bca_batch_dense_rec(ctx, p, eta, dtype, m, ld, order + lo, hi - lo, k, coef_a, tp, fp, fn, pred_idx,
+                                          dtp, dfp, dfn, stream)
+                 : xc_bca_batch_dense(ctx, eta, dtype, m, ld, order + lo, hi - lo, k, coef_a, coef_s, pred_idx, dtp,
+                                      dfp, dfn, stream);
+        if (rc) return rc;
+        if (hi == n_order) {   // fold the last batch
+            rc = rec ? xc_bca_rec(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_a, stream)
+                     : xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_a, coef_s, stream);
+            return rc;
+        }
+    }
+    return XC_OK;
+}
+
+extern "C" int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
+                                const int32_t *indices, const int64_t *indptr, int64_t m, const int32_t *order,
+                                int64_t n_order, int64_t batch, int k, float *coef_n, float *coef_s, int32_t *pred_idx,
+                                double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn, void *stream)
+{
+    if (!ctx || !p || !order || n_order < 0 || batch < 1) return XC_ERR_INVALID;
+    for (int64_t lo = 0; lo <= n_order; lo += batch) {
+        int rc = xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, coef_s, stream);
+        if (rc) return rc;
+        const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
+        if (hi <= lo) break;
+        rc = xc_bca_batch_csr(ctx, data, dtype, indices, indptr, order + lo, hi - lo, k, coef_n, coef_s, pred_idx, dtp, dfp,
+                              dfn, stream);
+        if (rc) return rc;
+        if (hi == n_order) return xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, coef_s, stream);
+    }
+    return XC_OK;
+}
