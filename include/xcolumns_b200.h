@@ -348,7 +348,9 @@ XC_API int xc_fw_metric_grad(xc_ctx *ctx, const xc_metric_params *p, const doubl
  * (1-alpha) C + alpha Ci at alpha = 0 and at alphas_dev[0..n_alphas) (the host builds the grid
  * with numpy.arange so the grid points are bit-identical), keeps the FIRST strict maximum.
  * For the c*tp/D metrics a float32 pass over the whole grid pre-selects the points that can be
- * the float64 maximum; those are re-evaluated with the reference's float64 expression.
+ * the float64 maximum, a float32 evaluation of their DIFFERENCES to the pre-selected maximum (with a
+ * rigorous rounding bound) prunes them to a handful, and those are re-evaluated with the reference's
+ * float64 expression.  $XCOLUMNS_B200_FW_SEARCH=full evaluates the whole grid in float64 instead.
  * scratch_dev: xc_fw_alpha_scratch_bytes(m, n_alphas) bytes; result_dev[0] = alpha, [1] = value. */
 XC_API int64_t xc_fw_alpha_scratch_bytes(int64_t m, int64_t n_alphas);
 XC_API int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const double *C,

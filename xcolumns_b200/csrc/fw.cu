@@ -220,7 +220,8 @@ fw_metric_grad_kernel(xc_metric_params p, const double *tp, const double *fp, co
 // The reference evaluates the metric of (1-alpha) C + alpha C_i at ~10^4 grid points and keeps the
 // first strict maximum (utils.py:174-184): 10^4 x m IEEE float64 divisions per iteration (0.6-1.8 ms
 // at m = 31 k, several times the streaming pass).  For the metrics of the form c*tp/D with D linear
-// in the confusion entries (precision, recall, F-beta, Jaccard) the search runs in two stages:
+// in the confusion entries (precision, recall, F-beta, Jaccard) the search runs in three stages
+// (screen, refinement -- described at fw_alpha_refine_kernel --, float64):
 //   1. every grid point in float32 from a per-label linearisation T(a)/D(a) = (T0 + a dT) / (D0 + a dD).
 //      The reciprocal unit (MUFU, 16 lanes/clk/SM) is the scarce pipe, so two labels share one
 //      reciprocal: T1/D1 + T2/D2 = (T1 D2 + T2 D1) / (D1 D2), factors kept in product form so that no
@@ -228,8 +229,8 @@ fw_metric_grad_kernel(xc_metric_params p, const double *tp, const double *fp, co
 //      measured: 110 us for the one-label-per-reciprocal version at m = 31 k, 10^4 points);
 //   2. the grid points within 1e-5 (relative) of the float32 maximum -- the float32 pass is accurate to
 //      ~3e-6 in the worst case, so this is a superset of every point that can be the float64 maximum --
-//      are re-evaluated with the reference's float64 expression; the first strict maximum among them
-//      wins.  The candidates are spread over all SMs (label slices chosen on the device from the
+//      are pruned by the float32 difference refinement and the survivors re-evaluated with the
+//      reference's float64 expression; the first strict maximum among them wins.  The candidates are spread over all SMs (label slices chosen on the device from the
 //      candidate count); partial sums are combined in a fixed order, so the result is reproducible.
 // Up to ALPHA_MAX_CAND (>= the default 10^4-point grid) screen candidates go through the refinement: on
 // many rows the objective gets so flat in alpha that ALL grid points are within 1e-5 of the maximum (seen
