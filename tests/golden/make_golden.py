@@ -292,6 +292,16 @@ def main_extra():
         out[name + "_pred"] = pred_to_idx(yp, 5)
         out[name + "_state"] = np.stack([C_.tp, C_.fp, C_.fn, C_.tn])
         print(f"  {name}: tp sum {C_.tp.sum():.6f}")
+    # Frank-Wolfe without a budget (k = 0: every label with a non-negative gain)
+    clf, meta = fw.find_classifier_using_fw(eta, eta, mt.macro_f1_score_on_conf_matrix, 0, max_iters=6, skip_tn=True,
+                                            seed=0, return_meta=True)
+    out["fw_k0_a"], out["fw_k0_b"], out["fw_k0_p"] = clf.a, clf.b, clf.p
+    out["fw_k0_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+    out["fw_k0_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+    yk0 = clf.predict(eta, seed=3)
+    out["fw_k0_pred_rowsums"] = np.asarray(yk0.sum(1), dtype=np.float64)
+    out["fw_k0_pred"] = np.asarray(yk0 != 0, dtype=np.uint8)
+    print(f"  fw_k0: iters={meta['iters']} alphas={out['fw_k0_alphas']} util={out['fw_k0_util']}")
     # micro-averaged Frank-Wolfe objectives (frank_wolfe.py:758-832)
     for name, fn, kw in (("micro_f1", fw.find_classifier_optimizing_micro_f1_score_using_fw, {}),
                          ("micro_balacc", fw.find_classifier_optimizing_micro_balanced_accuracy_using_fw, {})):

@@ -629,3 +629,25 @@ def test_online_greedy_golden(xb, golden, name, metric, skip_tn, etu):
     assert dense.shape == eta.shape and dense.dtype == eta.dtype and (_idx(dense, 5) == g[name + "_pred"]).all()
     with pytest.raises(ValueError):
         OnlineGreedy(m, 5, _metric(xb, metric)).predict_update(eta)
+
+
+@pytest.mark.gpu
+def test_fw_no_budget_golden(xb, golden):
+    """Frank-Wolfe and the randomized classifier's prediction with k = 0 (threshold at 0) vs the live reference"""
+    from xcolumns_b200 import metrics as M
+    g = golden("extra")
+    eta = g["eta"]
+    clf, meta = xb.find_classifier_using_fw(eta, eta, M.macro_f1_score_on_conf_matrix, 0, max_iters=6, skip_tn=True,
+                                            seed=0, return_meta=True)
+    assert np.allclose(meta["alphas"], g["fw_k0_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["fw_k0_util"], rtol=0, atol=1e-5)
+    assert clf.a.shape == g["fw_k0_a"].shape and np.allclose(clf.p, g["fw_k0_p"], atol=1e-6)
+    # prediction with the REFERENCE's classifier (same numpy random stream): identical 0/1 matrix up to entries
+    # whose gain is within float32 rounding of the threshold
+    from xcolumns_b200.frank_wolfe import RandomizedWeightedClassifier
+    ref_clf = RandomizedWeightedClassifier(0, g["fw_k0_a"], g["fw_k0_b"], g["fw_k0_p"])
+    yp = ref_clf.predict(eta, seed=3)
+    assert yp.shape == eta.shape and yp.dtype == eta.dtype
+    assert ((yp != 0).astype(np.uint8) != g["fw_k0_pred"]).mean() < 1e-6
+    with pytest.raises(NotImplementedError):
+        xb.find_classifier_using_fw(csr_matrix(eta), csr_matrix(eta), M.macro_f1_score_on_conf_matrix, 0)

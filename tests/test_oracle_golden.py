@@ -206,3 +206,12 @@ def test_fw_micro(golden, oracle, name, metric, skip_tn):
     assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9)
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-6)
     assert a.shape == g[name + "_a"].shape and np.allclose(p, g[name + "_p"], atol=1e-6)
+
+
+def test_fw_no_budget(golden, oracle):
+    """k = 0: every label with eta * a + b >= 0 is predicted (frank_wolfe.py:601 with th = 0)"""
+    g = golden("extra")
+    eta = g["eta"]
+    a, b, p, meta = oracle.find_classifier_using_fw(eta, eta, "f1", 0, max_iters=6, skip_tn=True, seed=0)
+    assert np.allclose(meta["alphas"], g["fw_k0_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["fw_k0_util"], rtol=0, atol=1e-5)

@@ -55,6 +55,38 @@ fw_iterate_dense_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_
     }
 }
 
+// No budget (k = 0): every label with eta * a + b >= 0 is predicted (weighted_prediction.py:55-56 with the
+// th = 0 the Frank-Wolfe driver passes, frank_wolfe.py:601).  Column-oriented: 128 consecutive labels per
+// CTA, two row lanes, a strip of rows; eta AND y_true are streamed (2 n m sizeof bytes per iterate).
+constexpr int K0_COLS = 128, K0_STRIP = 512;
+
+template <typename TE>
+__global__ void __launch_bounds__(kThreads)
+fw_iterate_dense_k0_kernel(const TE *__restrict__ eta, int64_t n, int64_t m, int64_t ld,
+                           const TE *__restrict__ y_true, int64_t ld_true, const TE *__restrict__ a,
+                           const TE *__restrict__ b, double *tp, double *cnt)
+{
+    const int64_t j = (int64_t)blockIdx.x * K0_COLS + (threadIdx.x % K0_COLS);
+    if (j >= m) return;
+    const int lanes = kThreads / K0_COLS;
+    const int64_t r0 = (int64_t)blockIdx.y * K0_STRIP, r1 = min(n, r0 + K0_STRIP);
+    const TE aj = a ? a[j] : (TE)1, bj = b ? b[j] : (TE)0;
+    double t = 0.0, c = 0.0;
+    for (int64_t i = r0 + threadIdx.x / K0_COLS; i < r1; i += lanes) {
+        TE g = ld_stream(eta + i * ld + j);
+        if (a) g = XfMulAdd<TE>::mul_rn(g, aj);
+        if (b) g = XfMulAdd<TE>::add_rn(g, bj);
+        if (g >= (TE)0) {
+            t += (double)ld_stream(y_true + i * ld_true + j);
+            c += 1.0;
+        }
+    }
+    if (c != 0.0) {
+        atomicAdd(tp + j, t);
+        atomicAdd(cnt + j, c);
+    }
+}
+
 __device__ __forceinline__ int64_t csr_find(const int32_t *idx, int64_t s, int64_t e, int j)
 {
     while (s < e) {
@@ -964,6 +996,14 @@ int launch_fw_dense(xc_ctx *ctx, const void *eta, int64_t n, int64_t m, int64_t 
                     int64_t ld_true, const void *a, const void *b, int k, double *tp, double *cnt, int32_t *pred_idx,
                     cudaStream_t st)
 {
+    if (k == 0) {
+        if (pred_idx) return XC_ERR_INVALID;  // no compact prediction without a budget
+        dim3 grid((unsigned)((m + K0_COLS - 1) / K0_COLS), (unsigned)((n + K0_STRIP - 1) / K0_STRIP));
+        fw_iterate_dense_k0_kernel<TE><<<grid, kThreads, 0, st>>>((const TE *)eta, n, m, ld, (const TE *)y_true, ld_true,
+                                                                  (const TE *)a, (const TE *)b, tp, cnt);
+        XC_LAUNCHED(ctx);
+        return XC_OK;
+    }
     constexpr int V = 16 / sizeof(TE);
     bool vec_ok = xc_aligned16(eta) && (ld % V == 0);
     XfMulAdd<TE> xf{(const TE *)a, (const TE *)b};
@@ -1006,7 +1046,7 @@ extern "C" int xc_fw_iterate_dense(xc_ctx *ctx, const void *eta, int dtype, int6
                                    double *tp, double *cnt, int32_t *pred_idx, void *stream)
 {
     if (!ctx || !eta || !y_true || !tp || !cnt || n <= 0 || m <= 0 || ld < m || ld_true < m) return XC_ERR_INVALID;
-    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (k < 0 || k > 32 || k > m) return XC_ERR_INVALID;   // k == 0: no budget, threshold at 0
     cudaStream_t st = (cudaStream_t)stream;
     XC_CUDA_TRY(ctx, cudaMemsetAsync(tp, 0, sizeof(double) * m, st));
     XC_CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, sizeof(double) * m, st));
@@ -1267,7 +1307,7 @@ extern "C" int xc_fw_step_begin(xc_ctx *ctx, const void *eta, int dtype, int64_t
                                 double *ab64, int k, double *raw, int raw_is_zero, void *stream)
 {
     if (!ctx || !eta || !y_true || !a_row || !b_row || !raw) return XC_ERR_INVALID;
-    if (n <= 0 || m <= 0 || ld < m || ld_true < m || k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (n <= 0 || m <= 0 || ld < m || ld_true < m || k < 0 || k > 32 || k > m) return XC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const void *a = a_row, *b = b_row;
     if (dtype == XC_F64) {  // numpy promotes the float32 classifier rows to float64 gains

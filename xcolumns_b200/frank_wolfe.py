@@ -54,8 +54,10 @@ def predict_using_randomized_weighted_classifier(y_proba: Matrix, k: int, classi
     if not isinstance(y_proba, (np.ndarray, torch.Tensor, csr_matrix)):
         raise ValueError("y_proba must be either np.ndarray, torch.Tensor, or csr_matrix")
     _check_k(k)
-    if k <= 0:
-        raise NotImplementedError("xcolumns_b200: randomized classifier prediction needs k > 0")
+    if k < 0:
+        raise ValueError("k must be >= 0")
+    if k == 0 and isinstance(y_proba, csr_matrix):
+        raise NotImplementedError("xcolumns_b200: prediction without a budget (k=0) is implemented for dense inputs")
     to_np = lambda v: v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
     A, B, P = to_np(classifiers_a), to_np(classifiers_b), to_np(classifiers_proba)
     n, m = y_proba.shape
@@ -67,6 +69,24 @@ def predict_using_randomized_weighted_classifier(y_proba: Matrix, k: int, classi
     rng_range = np.arange(P.shape[0])
     choice = np.array([rng.choice(rng_range, p=P) for _ in range(n)], dtype=np.int64)
     device = dev.pick_device(y_proba)
+    if k == 0:
+        # no budget: every label with a non-negative gain under the row's classifier (frank_wolfe.py:80-105
+        # with k = 0 -> weighted_prediction.py:55-56); rows are grouped by classifier like below
+        from .weighted_prediction import _threshold_dense
+        d = dev.dense_to_device(y_proba, device)
+        gdt = torch.promote_types(d.torch_dtype, torch.from_numpy(A[:0]).dtype)
+        g_code = 0 if gdt == torch.float32 else 1
+        out = torch.zeros((n, m), dtype=d.torch_dtype, device=device)
+        for c in np.unique(choice):
+            rows = torch.from_numpy(np.nonzero(choice == c)[0]).to(device)
+            sub = dev.DenseDev(d.t[rows][:, :m].contiguous(), int(rows.numel()), m, m, d.code, 0)
+            a = dev.vec_to_device(A[c], device, gdt, m, "a")
+            b = dev.vec_to_device(B[c], device, gdt, m, "b")
+            out[rows] = _threshold_dense(out, sub, a, b, g_code, 0.0, None)
+        if isinstance(y_proba, torch.Tensor):
+            return out.to(device=y_proba.device, dtype=y_proba.dtype if dtype is None else dtype)
+        res = out.cpu().numpy()
+        return res if dtype is None else res.astype(dtype)
     pred = torch.full((n, k), -1, dtype=torch.int32, device=device)
     if isinstance(y_proba, csr_matrix):
         from .weighted_prediction import topk_csr_device
@@ -122,8 +142,10 @@ def find_classifier_using_fw(
     if tuple(y_true.shape) != tuple(y_proba.shape):
         raise ValueError(f"y_true and y_proba must have the same shape, got {y_true.shape} and {y_proba.shape}")
     _check_k(k)
-    if k <= 0:
-        raise NotImplementedError("xcolumns_b200: Frank-Wolfe without a budget (k=0) is not implemented on the GPU path yet")
+    if k < 0:
+        raise ValueError("k must be >= 0")
+    if k == 0 and isinstance(y_proba, csr_matrix):
+        raise NotImplementedError("xcolumns_b200: Frank-Wolfe without a budget (k=0) is implemented for dense inputs")
     if alpha_search_algo not in ("uniform", "ternary") and search_for_best_alpha:
         raise ValueError(f"Unknown search algorithm {alpha_search_algo}")
     ternary_eps = float(alpha_tolerance) if (search_for_best_alpha and alpha_search_algo == "ternary") else 0.0
