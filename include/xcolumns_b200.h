@@ -71,6 +71,8 @@ typedef struct {
                        /*    ((1 - mix_alpha) * (tp / mix_k)) + ((mix_alpha * metric) / mix_m)          */
                        /* 2: micro average, metric(tp.sum(), fp.sum(), fn.sum(), tn.sum())              */
                        /*    (ref: metrics.py:68-100; Frank-Wolfe objective only)                       */
+                       /* 3: (1 - mix_alpha) * recall + mix_alpha * precision, summed over the labels   */
+                       /*    (ref: frank_wolfe.py:917-938; metric = XC_METRIC_PRECISION, FW only)       */
     double c1;         /* 1 + beta**2, computed by the host exactly like python does           */
     double beta2;      /* beta**2                                                              */
     double eps;        /* epsilon of the metric (metric_kwargs["epsilon"], default 1e-9)       */

@@ -513,13 +513,19 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
                              init_classifier="top", maximize=True, normalize_conf_matrix=True,
                              beta=1.0, epsilon=1e-9, tolerance=1e-6, search_for_best_alpha=True,
                              alpha_tolerance=0.001, alpha_uniform_search_step=0.0001,
-                             skip_tn=False, seed=None, mix=None, alpha_search_algo="uniform", micro=False):
+                             skip_tn=False, seed=None, mix=None, alpha_search_algo="uniform", micro=False,
+                             recall_precision_alpha=None):
     """Returns (a, b, p, meta) with the truncation rules of frank_wolfe.py:644-670.
     alpha_search_algo="ternary": utils.py:187-201 with eps = alpha_tolerance (:627).
     mix=(alpha, k, m): objective sum_j [(1 - alpha) tp_j / k + alpha metric_j / m] (:838-915)."""
     mid, c1, b2, eps = metric_params(metric, beta, epsilon)
 
     def macro_metric_and_grad_mix(metric, tp, fp, fn, tn, beta=1.0, epsilon=1e-9):
+        if recall_precision_alpha is not None:   # frank_wolfe.py:917-938: sum_j (1 - al) recall_j + al precision_j
+            al = recall_precision_alpha
+            vr, gr = macro_metric_and_grad("recall", tp, fp, fn, tn, epsilon=epsilon)
+            vp, gp = macro_metric_and_grad("precision", tp, fp, fn, tn, epsilon=epsilon)
+            return m * ((1 - al) * vr + al * vp), tuple(m * ((1 - al) * x + al * y) for x, y in zip(gr, gp))
         if micro:   # metrics.py:68-100: the metric of the four sums; every label gets the same gradient
             sums = [np.array([np.sum(x)], dtype=np.float64) for x in (tp, fp, fn, tn)]
             v, g = macro_metric_and_grad(metric, *sums, beta=beta, epsilon=epsilon)
@@ -574,7 +580,7 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
 
             def f_at(al):
                 """metric of (1 - al) C + al C_i (frank_wolfe.py:393-398): a one-point 'grid'"""
-                if micro:
+                if micro or recall_precision_alpha is not None:
                     return value([(1 - al) * x + al * y for x, y in zip(Cm, Ci)])
                 one = np.array([al], dtype=np.float64)
                 oa, ov = C.c_double(), C.c_double()
@@ -595,6 +601,13 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
                     else:
                         low = mid1
                 ba.value = (low + high) / 2
+            elif recall_precision_alpha is not None:      # utils.py:174-184, point by point
+                best, best_val = 0.0, f_at(0.0)
+                for al_ in alphas:
+                    sc = f_at(al_)
+                    if sc > best_val:
+                        best, best_val = al_, sc
+                ba.value = best
             elif micro:                                   # utils.py:174-184 on the scalar objective
                 grid = np.concatenate([[0.0], alphas])
                 S, Si = [float(np.sum(x)) for x in Cm], [float(np.sum(x)) for x in Ci]

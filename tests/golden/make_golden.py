@@ -302,6 +302,13 @@ def main_extra():
     out["fw_k0_pred_rowsums"] = np.asarray(yk0.sum(1), dtype=np.float64)
     out["fw_k0_pred"] = np.asarray(yk0 != 0, dtype=np.uint8)
     print(f"  fw_k0: iters={meta['iters']} alphas={out['fw_k0_alphas']} util={out['fw_k0_util']}")
+    # mixed macro recall / macro precision (frank_wolfe.py:917-938)
+    clf, meta = fw.find_classifier_optimizing_mixed_macro_recall_and_macro_precision_using_fw(
+        eta, eta, 5, alpha=0.4, max_iters=4, skip_tn=True, seed=0, alpha_uniform_search_step=0.002, return_meta=True)
+    out["fw_rp_a"], out["fw_rp_p"] = clf.a, clf.p
+    out["fw_rp_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+    out["fw_rp_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+    print(f"  fw_rp: iters={meta['iters']} alphas={out['fw_rp_alphas']} util={out['fw_rp_util']}")
     # micro-averaged Frank-Wolfe objectives (frank_wolfe.py:758-832)
     for name, fn, kw in (("micro_f1", fw.find_classifier_optimizing_micro_f1_score_using_fw, {}),
                          ("micro_balacc", fw.find_classifier_optimizing_micro_balanced_accuracy_using_fw, {})):

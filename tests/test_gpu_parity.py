@@ -651,3 +651,14 @@ def test_fw_no_budget_golden(xb, golden):
     assert ((yp != 0).astype(np.uint8) != g["fw_k0_pred"]).mean() < 1e-6
     with pytest.raises(NotImplementedError):
         xb.find_classifier_using_fw(csr_matrix(eta), csr_matrix(eta), M.macro_f1_score_on_conf_matrix, 0)
+
+
+@pytest.mark.gpu
+def test_fw_mixed_macro_recall_and_precision_golden(xb, golden):
+    g = golden("extra")
+    eta = g["eta"]
+    clf, meta = xb.find_classifier_optimizing_mixed_macro_recall_and_macro_precision_using_fw(
+        eta, eta, 5, alpha=0.4, max_iters=4, skip_tn=True, seed=0, alpha_uniform_search_step=0.002, return_meta=True)
+    assert np.allclose(meta["alphas"], g["fw_rp_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["fw_rp_util"], rtol=1e-6, atol=0)
+    assert clf.a.shape == g["fw_rp_a"].shape and np.allclose(clf.p, g["fw_rp_p"], atol=1e-6)

@@ -215,3 +215,13 @@ def test_fw_no_budget(golden, oracle):
     a, b, p, meta = oracle.find_classifier_using_fw(eta, eta, "f1", 0, max_iters=6, skip_tn=True, seed=0)
     assert np.allclose(meta["alphas"], g["fw_k0_alphas"], rtol=0, atol=1e-9)
     assert np.allclose(meta["utilities"], g["fw_k0_util"], rtol=0, atol=1e-5)
+
+
+def test_fw_mixed_macro_recall_and_precision(golden, oracle):
+    """frank_wolfe.py:917-938: sum_j [(1 - alpha) recall_j + alpha precision_j]"""
+    g = golden("extra")
+    eta = g["eta"]
+    a, b, p, meta = oracle.find_classifier_using_fw(eta, eta, "precision", 5, max_iters=4, skip_tn=True, seed=0,
+                                                    alpha_uniform_search_step=0.002, recall_precision_alpha=0.4)
+    assert np.allclose(meta["alphas"], g["fw_rp_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["fw_rp_util"], rtol=1e-6, atol=0)

@@ -36,6 +36,7 @@ from .frank_wolfe import (  # noqa: F401
     find_classifier_optimizing_mixed_instance_precision_and_macro_f1_score_using_fw,
     find_classifier_optimizing_mixed_instance_precision_and_macro_precision_using_fw,
     find_classifier_optimizing_mixed_instance_precision_and_macro_recall_using_fw,
+    find_classifier_optimizing_mixed_macro_recall_and_macro_precision_using_fw,
     find_classifier_using_fw,
     predict_using_randomized_weighted_classifier,
 )

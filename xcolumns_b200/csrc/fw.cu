@@ -217,6 +217,16 @@ __device__ __forceinline__ Grad4 metric_grad_p(const xc_metric_params &p, double
         g.gfp = p.mix_alpha * g.gfp;
         g.gfn = p.mix_alpha * g.gfn;
         g.gtn = p.mix_alpha * g.gtn;
+    } else if (p.mix == 3) {
+        // sum_j [(1 - alpha) recall_j + alpha precision_j] (frank_wolfe.py:917-938); scaled by m because the
+        // callers report (1/m) sum_j v_j and (1/m) g_j
+        const Grad4 r = metric_grad(XC_METRIC_RECALL, tp, fp, fn, tn, p.c1, p.beta2, p.eps);
+        const double wa = p.mix_alpha * p.mix_m, wr = (1.0 - p.mix_alpha) * p.mix_m;
+        g.v = wa * g.v + wr * r.v;
+        g.gtp = wa * g.gtp + wr * r.gtp;
+        g.gfp = wa * g.gfp + wr * r.gfp;
+        g.gfn = wa * g.gfn + wr * r.gfn;
+        g.gtn = wa * g.gtn + wr * r.gtn;
     }
     return g;
 }
@@ -744,7 +754,7 @@ fw_alpha_ternary_kernel(xc_metric_params p, const double *__restrict__ C, const 
         v1 = 0.0;
         v2 = 0.0;
         for (int w = 0; w < 32; ++w) { v1 += sm[0][w]; v2 += sm[1][w]; }
-        const double div = p.mix == 1 ? 1.0 : (double)m;
+        const double div = (p.mix == 1 || p.mix == 3) ? 1.0 : (double)m;
         v1 = v1 / div;
         v2 = v2 / div;
     };

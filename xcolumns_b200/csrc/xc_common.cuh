@@ -256,5 +256,7 @@ __device__ __forceinline__ double xc_metric_eval(const xc_metric_params &p, doub
 {
     double v = xc_binary_metric(p.metric, tp, fp, fn, tn, p.c1, p.beta2, p.eps);
     if (p.mix == 1) v = ((1.0 - p.mix_alpha) * (tp / p.mix_k)) + ((p.mix_alpha * v) / p.mix_m);
+    // mix == 3 (frank_wolfe.py:917-938): (1 - alpha) * recall + alpha * precision, metric id = precision
+    if (p.mix == 3) v = ((1.0 - p.mix_alpha) * (tp / ((tp + fn) + p.eps))) + (p.mix_alpha * v);
     return v;
 }

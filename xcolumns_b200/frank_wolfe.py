@@ -207,6 +207,8 @@ def find_classifier_using_fw(
     mix = M.resolve_mix(metric_func)
     mix_alpha, mix_k, mix_m = mix if mix is not None else (1.0, 1.0, 1.0)
     mix_code = 2 if M.is_micro_metric(metric_func) else int(mix is not None)
+    if isinstance(metric_func, M.MixedMacroRecallPrecisionMetric):
+        mix_code, mix_alpha, mix_m = 3, float(metric_func.alpha), float(metric_func.m)
     params = MetricParams(metric=metric_id, maximize=int(bool(maximize)), skip_tn=int(bool(skip_tn)),
                           mix=mix_code, c1=float(1 + beta**2), beta2=float(beta**2), eps=float(eps),
                           n_div=1.0, n_rows=float(n_global), mix_alpha=mix_alpha, mix_k=mix_k, mix_m=mix_m)
@@ -402,3 +404,11 @@ find_classifier_optimizing_mixed_instance_precision_and_macro_f1_score_using_fw 
     M.binary_f1_score_on_conf_matrix, "macro-averaged F1 score")
 find_classifier_optimizing_mixed_instance_precision_and_macro_recall_using_fw = make_mixed_frank_wolfe_wrapper(
     M.binary_recall_on_conf_matrix, "macro-averaged recall")
+
+
+def find_classifier_optimizing_mixed_macro_recall_and_macro_precision_using_fw(y_true: Matrix, y_proba: Matrix, k: int,
+                                                                               alpha: float = 1, **kwargs):
+    """Find a randomized classifier maximizing  sum_j [(1 - alpha) * recall_j + alpha * precision_j]  with the
+    Frank-Wolfe algorithm (xcolumns/frank_wolfe.py:917-938); see find_classifier_using_fw."""
+    n, m = y_true.shape
+    return find_classifier_using_fw(y_true, y_proba, M.MixedMacroRecallPrecisionMetric(alpha, m), k, **kwargs)

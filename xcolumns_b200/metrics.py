@@ -104,6 +104,19 @@ class MixedInstancePrecisionMacroMetric:
         return self.per_label(tp, fp, fn, tn, epsilon=epsilon).sum()
 
 
+class MixedMacroRecallPrecisionMetric:
+    """Frank-Wolfe objective of frank_wolfe.py:917-938:
+    ``((1 - alpha) * binary_recall + alpha * binary_precision).sum()``."""
+
+    def __init__(self, alpha: float, m: int):
+        self.alpha, self.m = alpha, m
+        self.__name__ = "mixed_metric_fn"
+
+    def __call__(self, tp, fp, fn, tn, epsilon: float = 1e-9):
+        return ((1 - self.alpha) * binary_recall_on_conf_matrix(tp, fp, fn, tn, epsilon=epsilon) + self.alpha *
+                binary_precision_on_conf_matrix(tp, fp, fn, tn, epsilon=epsilon)).sum()
+
+
 _BINARY_IDS = {
     "binary_precision_on_conf_matrix": XC_METRIC_PRECISION,
     "binary_recall_on_conf_matrix": XC_METRIC_RECALL,
@@ -224,6 +237,8 @@ def resolve_macro_metric(func: Callable, metric_kwargs: Optional[Dict[str, Any]]
     """Same for a macro-averaged metric on the confusion matrix (Frank-Wolfe objective)."""
     if isinstance(func, MixedInstancePrecisionMacroMetric):
         return resolve_binary_metric(func.per_label.binary_metric, metric_kwargs)
+    if isinstance(func, MixedMacroRecallPrecisionMetric):
+        return resolve_binary_metric(binary_precision_on_conf_matrix, metric_kwargs)
     inner = getattr(func, "_xc_binary_metric", None)
     if inner is None and getattr(func, "__name__", "") in ("macro_metric_on_conf_matrix",
                                                             "micro_metric_on_conf_matrix") and func.__closure__:
