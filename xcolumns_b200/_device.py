@@ -176,8 +176,11 @@ class DenseOutputPrefill:
     def __init__(self, n: int, m: int, np_dtype):
         self.out = np.empty((n, m), dtype=np_dtype)
         lib = _lib.load()
-        self._thread = threading.Thread(target=lib.xc_zero_host, args=(self.out.ctypes.data, self.out.nbytes, 0),
-                                        daemon=True)   # ctypes drops the GIL for the duration of the call
+
+        def clear(arr=self.out):   # the closure keeps the array alive even if the caller bails out early
+            lib.xc_zero_host(arr.ctypes.data, arr.nbytes, 0)   # ctypes drops the GIL for the duration of the call
+
+        self._thread = threading.Thread(target=clear, daemon=True)
         self._thread.start()
 
     @staticmethod
