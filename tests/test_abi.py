@@ -114,3 +114,30 @@ def test_streaming_kernels_keep_their_occupancy():
             assert reg <= 40 and stack == 0, (name, reg, stack)
             checked += 1
     assert checked >= 2, sorted(usage)[:5]
+
+
+def test_dense_output_prefill_host_side(monkeypatch):
+    """host-only half of the boundary: the dense result is cleared on background threads and only scattered
+    at the end (csrc/host.cu: xc_zero_host / xc_scatter_pred_dense_host); an abandoned prefill must not crash"""
+    import gc
+    import time
+    import numpy as np
+    from xcolumns_b200 import _device as dev
+    monkeypatch.setattr(dev.DenseOutputPrefill, "MIN_BYTES", 0)
+    like = np.zeros((300, 50), dtype=np.float32)
+    p = dev.DenseOutputPrefill.start(like, 300, 50)
+    idx = np.tile(np.array([1, 7, 49], dtype=np.int32), (300, 1))
+    idx[5] = [-1, 2, 3]                                  # unused slot
+    vals = np.full((300, 3), 0.25, dtype=np.float32)
+    out = p.finish(idx, vals)
+    assert out.shape == (300, 50) and out.dtype == np.float32
+    assert (out[0, [1, 7, 49]] == 0.25).all() and out[0].sum() == 0.75 and out[5].sum() == 0.5
+    for dt in (np.float64, np.float32):
+        q = dev.DenseOutputPrefill.start(like.astype(dt), 300, 50)
+        o = q.finish(idx, None)
+        assert o.dtype == dt and (o.sum(1)[:5] == 3).all()
+    assert dev.DenseOutputPrefill.start(like.astype(np.int32), 300, 50) is None      # unsupported dtype: plain path
+    abandoned = dev.DenseOutputPrefill.start(like, 300, 50)
+    del abandoned
+    gc.collect()
+    time.sleep(0.1)
