@@ -276,6 +276,11 @@ XC_API int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void *st
  * these metrics (pass the record array as coef_n, coef_s may be NULL).                              */
 XC_API int xc_bca_rec(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
                       double *dtp, double *dfp, double *dfn, int64_t m, float *rec, void *stream);
+XC_API int xc_bca_batch_csr_rec(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
+                                const int32_t *indices, const int64_t *indptr, const int32_t *rows,
+                                int64_t n_rows, int k, const float *rec, const double *tp,
+                                const double *fp, const double *fn, int32_t *pred_idx, double *dtp,
+                                double *dfp, double *dfn, void *stream);
 XC_API int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype,
                                   int64_t m, int64_t ld, const int32_t *rows, int64_t n_rows, int k,
                                   const float *rec, const double *tp, const double *fp,

@@ -662,3 +662,21 @@ def test_fw_mixed_macro_recall_and_precision_golden(xb, golden):
     assert np.allclose(meta["alphas"], g["fw_rp_alphas"], rtol=0, atol=1e-9)
     assert np.allclose(meta["utilities"], g["fw_rp_util"], rtol=1e-6, atol=0)
     assert clf.a.shape == g["fw_rp_a"].shape and np.allclose(clf.p, g["fw_rp_p"], atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric", ["jaccard", "hmean", "gmean"])
+def test_bca_batched_csr_record_metrics_vs_oracle(xb, oracle, metric):
+    """Jaccard / G-mean / H-mean on CSR rows in batched mode: within 1e-4 (2x the reference's own seed spread) of
+    the sequential oracle, and the reported utility is the utility of the returned prediction"""
+    from xcolumns_b200.synth import csr_probs
+    y = csr_probs(3000, 900, 30, seed=77)
+    skip = metric == "jaccard"
+    _, ometa = oracle.predict_using_bc_with_0approx(y, metric, 5, seed=0, skip_tn=skip)
+    pred, meta = xb.predict_using_bc_with_0approx(y, _metric(xb, metric), 5, seed=0, skip_tn=skip, return_meta=True,
+                                                  mode="batched")
+    assert meta["mode"] == "batched" and isinstance(pred, csr_matrix) and (np.diff(pred.indptr) == 5).all()
+    tol = _tol_from_reference_spread(
+        lambda s: oracle.predict_using_bc_with_0approx(y, metric, 5, seed=s, skip_tn=skip)[1]["utilities"][-1],
+        ometa["utilities"][-1])
+    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol, (meta["utilities"], ometa["utilities"])

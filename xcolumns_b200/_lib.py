@@ -48,6 +48,7 @@ _SIGNATURES = {
     "xc_p2p_error": [_vp, _vp],
     "xc_bca_commit_p2p": [_vp, _MP, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp],
     "xc_bca_online_dense": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _int, _MP, _vp, _vp, _vp, _vp, _vp, _vp],
+    "xc_bca_batch_csr_rec": [_MP, _vp, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_rec": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "xc_bca_batch_dense_rec": [_MP, _vp, _int, _i64, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_sweep_dense": [_MP, _vp, _int, _i64, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

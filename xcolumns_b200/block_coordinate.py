@@ -126,7 +126,7 @@ class BcaSession:
         self.util_buf = torch.zeros(8, **f64)
         self.pred: Optional[torch.Tensor] = None
         # Jaccard / G-mean / H-mean: 16-byte per-label records instead of the affine coefficient pairs
-        self.use_rec = (params.metric in M.RECORD_GAIN_METRICS) and not params.mix and not self.is_csr
+        self.use_rec = (params.metric in M.RECORD_GAIN_METRICS) and not params.mix
         self.rec = torch.zeros((clen, 4), dtype=torch.float32, device=self.device) if self.use_rec else None
 
     # -- small helpers ---------------------------------------------------------------------
@@ -280,7 +280,8 @@ class BcaSession:
         if self.is_csr:
             self.ctx.call("xc_bca_sweep_csr", C.byref(self.p), dev.ptr(d.data), d.code, dev.ptr(d.indices),
                           dev.ptr(d.indptr), d.m, dev.ptr(order_dev), int(order_dev.numel()), int(batch), k,
-                          dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._sp(0), self._sp(1),
+                          dev.ptr(self.rec if self.use_rec else self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
+                          self._sp(0), self._sp(1),
                           self._sp(2), self._dp(0), self._dp(1), self._dp(2), self._s())
         else:
             self.ctx.call("xc_bca_sweep_dense", C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, dev.ptr(order_dev),
@@ -324,7 +325,12 @@ class BcaSession:
                 if events is not None:
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record(torch.cuda.current_stream(self.device))
-                if self.is_csr:
+                if self.is_csr and self.use_rec:
+                    self.ctx.call("xc_bca_batch_csr_rec", C.byref(self.p), dev.ptr(d.data), d.code, dev.ptr(d.indices),
+                                  dev.ptr(d.indptr), rows, hi - lo, k, dev.ptr(self.rec), self._sp(0), self._sp(1),
+                                  self._sp(2), dev.ptr(self.pred), self._dp(0, cur), self._dp(1, cur),
+                                  self._dp(2, cur), self._s())
+                elif self.is_csr:
                     self.ctx.call("xc_bca_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
                                   rows, hi - lo, k, dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
                                   self._dp(0, cur), self._dp(1, cur), self._dp(2, cur), self._s())
@@ -426,9 +432,7 @@ def predict_using_bc_with_0approx(
     if k > m:
         raise ValueError(f"k={k} is larger than the number of labels m={m}")
     greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
-    is_csr_in = isinstance(y_proba, csr_matrix)
-    batchable = metric_id in M.AFFINE_GAIN_METRICS or (
-        metric_id in M.RECORD_GAIN_METRICS and not is_csr_in and mix is None)
+    batchable = metric_id in M.AFFINE_GAIN_METRICS or (metric_id in M.RECORD_GAIN_METRICS and mix is None)
     mode = _resolve_mode(mode, n, greedy or k == 0 or not batchable or (metric_id in M.TN_METRICS and skip_tn))
 
     device = dev.pick_device(y_proba)
@@ -500,8 +504,8 @@ def predict_using_bc_with_0approx(
             raise NotImplementedError("init_y_pred='greedy' needs the sequential mode (mode='exact')")
         if not batchable:
             raise NotImplementedError(
-                "xcolumns_b200 batched mode: Jaccard / G-mean / H-mean are fused for dense inputs only (and not in "
-                "the mixed utilities); use mode='exact' for CSR rows")
+                "xcolumns_b200 batched mode: Jaccard / G-mean / H-mean are not fused inside the mixed utilities; "
+                "use mode='exact'")
         if metric_id in M.TN_METRICS and skip_tn:
             raise NotImplementedError("batched mode evaluates tn-based metrics with the real tn: pass skip_tn=False")
         if batch_size:

@@ -368,162 +368,6 @@ bca_batch_dense_rec_kernel(xc_metric_params p, const TE *__restrict__ eta, int64
     }
 }
 
-// ---- CSR batch: one warp per row, candidates = stored labels ----------------------------------------
-// Rows with up to 32 * BC_RMAX stored labels are staged in registers: all loads of the row are issued up
-// front, the coefficient gathers follow in one wave, and everything after that (which stored entries
-// are currently selected, the probability of a label that leaves, the label / probability of a new
-// selection) is resolved with shuffles instead of dependent loads and binary searches.  Per row that is
-// 3 dependent memory round trips (row bounds -> entries -> coefficients) instead of ~12.
-constexpr int BC_RMAX = 4;
-
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-bca_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
-                     const int64_t *__restrict__ indptr, const int32_t *__restrict__ rows, int64_t n_rows, int k,
-                     const float2 *__restrict__ coef_n, const float2 *__restrict__ coef_s,
-                     int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn)
-{
-    const int lane = lane_id();
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
-    const T one = (T)1;
-    for (int64_t w = warp; w < n_rows; w += nwarps) {
-        const int64_t row = rows ? (int64_t)rows[w] : w;
-        const int64_t s = indptr[row], e = indptr[row + 1];
-        int32_t *pred_row = pred_idx + row * k;
-        int old_j = -1;
-        if (lane < k) old_j = pred_row[lane];
-        int new_j;
-        T new_e, old_e = (T)0;
-        bool old_found = false;
-        if (e - s <= 32 * BC_RMAX) {
-            // ---- register-staged row
-            const int nz = (int)(e - s);
-            int idx[BC_RMAX];
-            T val[BC_RMAX];
-#pragma unroll
-            for (int t = 0; t < BC_RMAX; ++t) {
-                const int q = lane + 32 * t;
-                idx[t] = q < nz ? indices[s + q] : -2;
-                val[t] = q < nz ? data[s + q] : (T)0;
-            }
-            bool sel[BC_RMAX];
-#pragma unroll
-            for (int t = 0; t < BC_RMAX; ++t) sel[t] = false;
-            for (int x = 0; x < k; ++x) {
-                const int px = __shfl_sync(XC_FULL, old_j, x);
-#pragma unroll
-                for (int t = 0; t < BC_RMAX; ++t) {
-                    const bool hit = px >= 0 && idx[t] == px;
-                    sel[t] |= hit;
-                    const unsigned bal = __ballot_sync(XC_FULL, hit);
-                    if (bal) {   // warp-uniform: the owner hands the probability of old label x to lane x
-                        const T v = __shfl_sync(XC_FULL, val[t], __ffs(bal) - 1);
-                        if (lane == x) { old_e = v; old_found = true; }
-                    }
-                }
-            }
-            WarpTopK<float> tk;
-            tk.init();
-            float g[BC_RMAX][1];
-#pragma unroll
-            for (int t = 0; t < BC_RMAX; ++t) {
-                g[t][0] = NAN;
-                if (idx[t] >= 0) {
-                    const float2 cf = __ldg((sel[t] ? coef_s : coef_n) + idx[t]);
-                    g[t][0] = fmaf(cf.x, (float)val[t], cf.y);
-                }
-            }
-            // the row's current selection goes in first: it sets a tight threshold, so that in a converged
-            // sweep hardly any other entry reaches the list (an empty list would take all 32 lanes of the
-            // first chunk through the serial insertion path: ~1500 warp instructions per row, measured as
-            // the bound of this kernel)
-#pragma unroll
-            for (int t = 0; t < BC_RMAX; ++t) {
-                float gs[1];
-                gs[0] = sel[t] ? g[t][0] : NAN;
-                if (32 * t < nz && __any_sync(XC_FULL, tk.passes(gs[0])))
-                    xc_scan_insert<float, 1, false>(tk, gs, 32 * t, 1, k, -1);
-                if (sel[t]) g[t][0] = NAN;
-            }
-#pragma unroll
-            for (int t = 0; t < BC_RMAX; ++t)
-                if (32 * t < nz && __any_sync(XC_FULL, tk.passes(g[t][0])))
-                    xc_scan_insert<float, 1, false>(tk, g[t], 32 * t, 1, k, -1);
-            // positions inside the row, ascending (== ascending label); fetch label / probability by shuffle
-            const int src = warp_rank_src(tk.idx, k);
-            const int pos = __shfl_sync(XC_FULL, tk.idx, src);
-            const bool none = pos == 0x7fffffff;
-            const int want_lane = none ? 0 : (pos & 31), want_t = none ? 0 : (pos >> 5);
-            int gj = 0;
-            T ge = (T)0;
-#pragma unroll
-            for (int t = 0; t < BC_RMAX; ++t) {
-                const int vj = __shfl_sync(XC_FULL, idx[t], want_lane);
-                const T ve = __shfl_sync(XC_FULL, val[t], want_lane);
-                if (t == want_t) { gj = vj; ge = ve; }
-            }
-            new_j = none ? 0x7fffffff : gj;
-            new_e = none ? (T)0 : ge;
-        } else {
-            // ---- long row: stream it, look the leaving labels up afterwards
-            WarpTopK<float> tk;
-            tk.init();
-            for (int64_t q0 = s; q0 < e; q0 += 32) {
-                int64_t q = q0 + lane;
-                float g[1];
-                g[0] = NAN;
-                const int j = q < e ? indices[q] : -2;
-                bool sel = false;
-                for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, old_j, t) == j);
-                if (q < e) {
-                    float ev = (float)data[q];
-                    float2 cf = __ldg((sel ? coef_s : coef_n) + j);
-                    g[0] = fmaf(cf.x, ev, cf.y);
-                }
-                if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<float, 1, false>(tk, g, q0 - s, 1, k, -1);
-            }
-            int src = warp_rank_src(tk.idx, k);
-            int pos = __shfl_sync(XC_FULL, tk.idx, src);
-            new_j = pos == 0x7fffffff ? 0x7fffffff : indices[s + pos];
-            new_e = pos == 0x7fffffff ? (T)0 : data[s + pos];
-            if (lane < k && old_j >= 0) {
-                int64_t y = s, z = e;
-                while (y < z) {
-                    int64_t mid = (y + z) >> 1;
-                    int v = indices[mid];
-                    if (v == old_j) { old_e = data[mid]; old_found = true; break; }
-                    if (v < old_j) y = mid + 1; else z = mid;
-                }
-            }
-        }
-        bool stays_old = false, stays_new = false;
-        for (int t = 0; t < k; ++t) {
-            int nj = __shfl_sync(XC_FULL, new_j, t);
-            int oj = __shfl_sync(XC_FULL, old_j, t);
-            stays_old |= (nj == old_j);
-            stays_new |= (oj == new_j);
-        }
-        if (lane < k) {
-            if (!stays_old && old_j >= 0) {
-                if (old_found) {   // eta of the leaving label (a label the row does not store only had fp = 1)
-                    atomicAdd(dtp + old_j, -(double)old_e);
-                    atomicAdd(dfp + old_j, -(double)(T)(one - old_e));
-                    atomicAdd(dfn + old_j, (double)old_e);
-                } else {
-                    atomicAdd(dfp + old_j, -1.0);
-                }
-            }
-            if (!stays_new && new_j != 0x7fffffff) {
-                atomicAdd(dtp + new_j, (double)new_e);
-                atomicAdd(dfp + new_j, (double)(T)(one - new_e));
-                atomicAdd(dfn + new_j, -(double)new_e);
-            }
-            pred_row[lane] = new_j == 0x7fffffff ? -1 : new_j;
-        }
-    }
-}
-
 // ---- coverage ------------------------------------------------------------------------------------
 // gain = Ef_j * eta (unselected) | Ef_j / (1 - eta) * eta (selected), optionally mixed with
 // precision@k: alpha * gain + (1 - alpha) * eta / k   (block_coordinate.py:562-569)
@@ -885,6 +729,174 @@ __global__ void __launch_bounds__(kThreads) cov_fold_kernel(double *Ef, double *
     }
 }
 
+// ---- CSR batch: one warp per row, candidates = stored labels ----------------------------------------
+// Rows with up to 32 * BC_RMAX stored labels are staged in registers: all loads of the row are issued up
+// front, the coefficient gathers follow in one wave, and everything after that (which stored entries
+// are currently selected, the probability of a label that leaves, the label / probability of a new
+// selection) is resolved with shuffles instead of dependent loads and binary searches.  Per row that is
+// 3 dependent memory round trips (row bounds -> entries -> coefficients) instead of ~12.
+constexpr int BC_RMAX = 4;
+
+// gain of one stored entry: affine coefficient pairs (METRIC < 0) or the record form of Jaccard / G-mean /
+// H-mean (unselected: float32 difference formula, selected: float64 reference expression on the state)
+template <typename T, int METRIC>
+struct CsrGain {
+    const float2 *coef_n, *coef_s;
+    const float4 *rec;
+    const double *tp, *fp, *fn;
+    xc_metric_params p;
+    __device__ __forceinline__ float operator()(bool sel, int j, T ev) const
+    {
+        if (METRIC < 0) {
+            const float2 cf = __ldg((sel ? coef_s : coef_n) + j);
+            return fmaf(cf.x, (float)ev, cf.y);
+        }
+        if (sel) return (float)bca_selected_gain(p, tp[j], fp[j], fn[j], (double)ev, (double)(T)((T)1 - ev));
+        XfRecord<(METRIC < 0 ? XC_METRIC_JACCARD : METRIC)> xf{rec, p.maximize ? 1.f : -1.f};
+        return xf.gain(__ldg(rec + j), (float)ev);
+    }
+};
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(kThreads, METRIC < 0 ? 6 : 1)
+bca_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                     const int64_t *__restrict__ indptr, const int32_t *__restrict__ rows, int64_t n_rows, int k,
+                     CsrGain<T, METRIC> gain, int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const T one = (T)1;
+    for (int64_t w = warp; w < n_rows; w += nwarps) {
+        const int64_t row = rows ? (int64_t)rows[w] : w;
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        int32_t *pred_row = pred_idx + row * k;
+        int old_j = -1;
+        if (lane < k) old_j = pred_row[lane];
+        int new_j;
+        T new_e, old_e = (T)0;
+        bool old_found = false;
+        if (e - s <= 32 * BC_RMAX) {
+            // ---- register-staged row
+            const int nz = (int)(e - s);
+            int idx[BC_RMAX];
+            T val[BC_RMAX];
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                const int q = lane + 32 * t;
+                idx[t] = q < nz ? indices[s + q] : -2;
+                val[t] = q < nz ? data[s + q] : (T)0;
+            }
+            bool sel[BC_RMAX];
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) sel[t] = false;
+            for (int x = 0; x < k; ++x) {
+                const int px = __shfl_sync(XC_FULL, old_j, x);
+#pragma unroll
+                for (int t = 0; t < BC_RMAX; ++t) {
+                    const bool hit = px >= 0 && idx[t] == px;
+                    sel[t] |= hit;
+                    const unsigned bal = __ballot_sync(XC_FULL, hit);
+                    if (bal) {   // warp-uniform: the owner hands the probability of old label x to lane x
+                        const T v = __shfl_sync(XC_FULL, val[t], __ffs(bal) - 1);
+                        if (lane == x) { old_e = v; old_found = true; }
+                    }
+                }
+            }
+            WarpTopK<float> tk;
+            tk.init();
+            float g[BC_RMAX][1];
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                g[t][0] = NAN;
+                if (idx[t] >= 0) g[t][0] = gain(sel[t], idx[t], val[t]);
+            }
+            // the row's current selection goes in first: it sets a tight threshold, so that in a converged
+            // sweep hardly any other entry reaches the list (an empty list would take all 32 lanes of the
+            // first chunk through the serial insertion path: ~1500 warp instructions per row, measured as
+            // the bound of this kernel)
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                float gs[1];
+                gs[0] = sel[t] ? g[t][0] : NAN;
+                if (32 * t < nz && __any_sync(XC_FULL, tk.passes(gs[0])))
+                    xc_scan_insert<float, 1, false>(tk, gs, 32 * t, 1, k, -1);
+                if (sel[t]) g[t][0] = NAN;
+            }
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t)
+                if (32 * t < nz && __any_sync(XC_FULL, tk.passes(g[t][0])))
+                    xc_scan_insert<float, 1, false>(tk, g[t], 32 * t, 1, k, -1);
+            // positions inside the row, ascending (== ascending label); fetch label / probability by shuffle
+            const int src = warp_rank_src(tk.idx, k);
+            const int pos = __shfl_sync(XC_FULL, tk.idx, src);
+            const bool none = pos == 0x7fffffff;
+            const int want_lane = none ? 0 : (pos & 31), want_t = none ? 0 : (pos >> 5);
+            int gj = 0;
+            T ge = (T)0;
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                const int vj = __shfl_sync(XC_FULL, idx[t], want_lane);
+                const T ve = __shfl_sync(XC_FULL, val[t], want_lane);
+                if (t == want_t) { gj = vj; ge = ve; }
+            }
+            new_j = none ? 0x7fffffff : gj;
+            new_e = none ? (T)0 : ge;
+        } else {
+            // ---- long row: stream it, look the leaving labels up afterwards
+            WarpTopK<float> tk;
+            tk.init();
+            for (int64_t q0 = s; q0 < e; q0 += 32) {
+                int64_t q = q0 + lane;
+                float g[1];
+                g[0] = NAN;
+                const int j = q < e ? indices[q] : -2;
+                bool sel = false;
+                for (int t = 0; t < k; ++t) sel |= (__shfl_sync(XC_FULL, old_j, t) == j);
+                if (q < e) g[0] = gain(sel, j, data[q]);
+                if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<float, 1, false>(tk, g, q0 - s, 1, k, -1);
+            }
+            int src = warp_rank_src(tk.idx, k);
+            int pos = __shfl_sync(XC_FULL, tk.idx, src);
+            new_j = pos == 0x7fffffff ? 0x7fffffff : indices[s + pos];
+            new_e = pos == 0x7fffffff ? (T)0 : data[s + pos];
+            if (lane < k && old_j >= 0) {
+                int64_t y = s, z = e;
+                while (y < z) {
+                    int64_t mid = (y + z) >> 1;
+                    int v = indices[mid];
+                    if (v == old_j) { old_e = data[mid]; old_found = true; break; }
+                    if (v < old_j) y = mid + 1; else z = mid;
+                }
+            }
+        }
+        bool stays_old = false, stays_new = false;
+        for (int t = 0; t < k; ++t) {
+            int nj = __shfl_sync(XC_FULL, new_j, t);
+            int oj = __shfl_sync(XC_FULL, old_j, t);
+            stays_old |= (nj == old_j);
+            stays_new |= (oj == new_j);
+        }
+        if (lane < k) {
+            if (!stays_old && old_j >= 0) {
+                if (old_found) {   // eta of the leaving label (a label the row does not store only had fp = 1)
+                    atomicAdd(dtp + old_j, -(double)old_e);
+                    atomicAdd(dfp + old_j, -(double)(T)(one - old_e));
+                    atomicAdd(dfn + old_j, (double)old_e);
+                } else {
+                    atomicAdd(dfp + old_j, -1.0);
+                }
+            }
+            if (!stays_new && new_j != 0x7fffffff) {
+                atomicAdd(dtp + new_j, (double)new_e);
+                atomicAdd(dfp + new_j, (double)(T)(one - new_e));
+                atomicAdd(dfn + new_j, -(double)new_e);
+            }
+            pred_row[lane] = new_j == 0x7fffffff ? -1 : new_j;
+        }
+    }
+}
+
 template <typename K>
 int grid_for(xc_ctx *ctx, K kernel, int64_t work_warps)
 {
@@ -1106,6 +1118,23 @@ extern "C" int xc_bca_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64
     return XC_ERR_UNSUPPORTED;
 }
 
+namespace {
+template <typename T, int METRIC>
+int launch_batch_csr(xc_ctx *ctx, const xc_metric_params *p, const void *data, const int32_t *indices,
+                     const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k, const float *coef_n,
+                     const float *coef_s, const float *rec, const double *tp, const double *fp, const double *fn,
+                     int32_t *pred_idx, double *dtp, double *dfp, double *dfn, cudaStream_t st)
+{
+    auto kern = bca_batch_csr_kernel<T, METRIC>;
+    int grid = grid_for(ctx, kern, n_rows);
+    CsrGain<T, METRIC> gain{(const float2 *)coef_n, (const float2 *)coef_s, (const float4 *)rec, tp, fp, fn,
+                            p ? *p : xc_metric_params{}};
+    kern<<<grid, kThreads, 0, st>>>((const T *)data, indices, indptr, rows, n_rows, k, gain, pred_idx, dtp, dfp, dfn);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+}  // namespace
+
 extern "C" int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
                                 const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k,
                                 const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
@@ -1115,21 +1144,42 @@ extern "C" int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const 
     if (k < 1 || k > 32) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == XC_F32) {
-        auto kern = bca_batch_csr_kernel<float>;
-        int grid = grid_for(ctx, kern, n_rows);
-        kern<<<grid, kThreads, 0, st>>>((const float *)data, indices, indptr, rows, n_rows, k, (const float2 *)coef_n,
-                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn);
-    } else if (dtype == XC_F64) {
-        auto kern = bca_batch_csr_kernel<double>;
-        int grid = grid_for(ctx, kern, n_rows);
-        kern<<<grid, kThreads, 0, st>>>((const double *)data, indices, indptr, rows, n_rows, k,
-                                        (const float2 *)coef_n, (const float2 *)coef_s, pred_idx, dtp, dfp, dfn);
-    } else {
+    if (dtype == XC_F32)
+        return launch_batch_csr<float, -1>(ctx, nullptr, data, indices, indptr, rows, n_rows, k, coef_n, coef_s, nullptr,
+                                           nullptr, nullptr, nullptr, pred_idx, dtp, dfp, dfn, st);
+    if (dtype == XC_F64)
+        return launch_batch_csr<double, -1>(ctx, nullptr, data, indices, indptr, rows, n_rows, k, coef_n, coef_s, nullptr,
+                                            nullptr, nullptr, nullptr, pred_idx, dtp, dfp, dfn, st);
+    return XC_ERR_UNSUPPORTED;
+}
+
+extern "C" int xc_bca_batch_csr_rec(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
+                                    const int32_t *indices, const int64_t *indptr, const int32_t *rows, int64_t n_rows,
+                                    int k, const float *rec, const double *tp, const double *fp, const double *fn,
+                                    int32_t *pred_idx, double *dtp, double *dfp, double *dfn, void *stream)
+{
+    if (!ctx || !p || !indptr || !rec || !tp || !fp || !fn || !pred_idx || !dtp || !dfp || !dfn || n_rows < 0)
+        return XC_ERR_INVALID;
+    if (k < 1 || k > 32) return XC_ERR_INVALID;
+    if (p->metric != XC_METRIC_JACCARD && p->metric != XC_METRIC_GMEAN && p->metric != XC_METRIC_HMEAN)
         return XC_ERR_UNSUPPORTED;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define XC_GO(T, METRIC)                                                                                          \
+    return launch_batch_csr<T, METRIC>(ctx, p, data, indices, indptr, rows, n_rows, k, nullptr, nullptr, rec, tp, fp, \
+                                       fn, pred_idx, dtp, dfp, dfn, st)
+    if (dtype == XC_F32) {
+        if (p->metric == XC_METRIC_JACCARD) XC_GO(float, XC_METRIC_JACCARD);
+        if (p->metric == XC_METRIC_GMEAN) XC_GO(float, XC_METRIC_GMEAN);
+        XC_GO(float, XC_METRIC_HMEAN);
     }
-    XC_LAUNCHED(ctx);
-    return XC_OK;
+    if (dtype == XC_F64) {
+        if (p->metric == XC_METRIC_JACCARD) XC_GO(double, XC_METRIC_JACCARD);
+        if (p->metric == XC_METRIC_GMEAN) XC_GO(double, XC_METRIC_GMEAN);
+        XC_GO(double, XC_METRIC_HMEAN);
+    }
+#undef XC_GO
+    return XC_ERR_UNSUPPORTED;
 }
 
 extern "C" int xc_cov_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
@@ -1226,15 +1276,22 @@ extern "C" int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const vo
                                 double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn, void *stream)
 {
     if (!ctx || !p || !order || n_order < 0 || batch < 1) return XC_ERR_INVALID;
+    const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
+    auto fold = [&]() {   // coef_n is the record array for the record metrics
+        return rec ? xc_bca_rec(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, stream)
+                   : xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, coef_s, stream);
+    };
     for (int64_t lo = 0; lo <= n_order; lo += batch) {
-        int rc = xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, coef_s, stream);
+        int rc = fold();
         if (rc) return rc;
         const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
         if (hi <= lo) break;
-        rc = xc_bca_batch_csr(ctx, data, dtype, indices, indptr, order + lo, hi - lo, k, coef_n, coef_s, pred_idx, dtp, dfp,
-                              dfn, stream);
+        rc = rec ? xc_bca_batch_csr_rec(ctx, p, data, dtype, indices, indptr, order + lo, hi - lo, k, coef_n, tp, fp, fn,
+                                        pred_idx, dtp, dfp, dfn, stream)
+                 : xc_bca_batch_csr(ctx, data, dtype, indices, indptr, order + lo, hi - lo, k, coef_n, coef_s, pred_idx, dtp,
+                                    dfp, dfn, stream);
         if (rc) return rc;
-        if (hi == n_order) return xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, coef_s, stream);
+        if (hi == n_order) return fold();
     }
     return XC_OK;
 }
