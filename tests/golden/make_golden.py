@@ -302,6 +302,34 @@ def main_extra():
     out["fw_k0_pred_rowsums"] = np.asarray(yk0.sum(1), dtype=np.float64)
     out["fw_k0_pred"] = np.asarray(yk0 != 0, dtype=np.uint8)
     print(f"  fw_k0: iters={meta['iters']} alphas={out['fw_k0_alphas']} util={out['fw_k0_util']}")
+    # driver options: un-normalised confusion matrix (quirk: only instance 0 is visited, block_coordinate.py
+    # :403-414), minimisation, fixed step sizes, explicit / random initial classifiers
+    from xcolumns import block_coordinate as bc2
+    eo2 = dense_probs(120, 90, seed=44)
+    out["opt_eta"] = eo2
+    for name, kw in (("opt_bca_nonorm", dict(normalize_conf_matrix=False, seed=0, skip_tn=True)),
+                     ("opt_bca_min", dict(maximize=False, seed=1, skip_tn=True, max_iters=3)),
+                     ("opt_bca_noshuffle_tn", dict(shuffle_order=False, seed=2, skip_tn=False))):
+        yp, meta = bc2.predict_using_bc_with_0approx(eo2, mt.binary_f1_score_on_conf_matrix, 4, return_meta=True, **kw)
+        out[name + "_pred"] = pred_to_idx(yp, 4)
+        out[name + "_util"] = np.array(meta["utilities"], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} util={meta['utilities']}")
+    rng_ab = np.random.default_rng(11)
+    a0 = (0.5 + rng_ab.random(eta.shape[1])).astype(np.float32)
+    b0 = (0.1 * rng_ab.standard_normal(eta.shape[1])).astype(np.float32)
+    out["opt_a0"], out["opt_b0"] = a0, b0
+    for name, kw in (("opt_fw_nonorm", dict(normalize_conf_matrix=False, skip_tn=True, max_iters=4)),
+                     ("opt_fw_fixed", dict(search_for_best_alpha=False, skip_tn=True, max_iters=5)),
+                     ("opt_fw_tuple", dict(init_classifier=(a0, b0), skip_tn=True, max_iters=4)),
+                     ("opt_fw_random", dict(init_classifier="random", skip_tn=True, max_iters=4, seed=5)),
+                     ("opt_fw_coarse", dict(alpha_uniform_search_step=0.01, skip_tn=True, max_iters=4))):
+        kw.setdefault("seed", 0)
+        clf, meta = fw.find_classifier_using_fw(eta, eta, mt.macro_f1_score_on_conf_matrix, 5, return_meta=True, **kw)
+        out[name + "_p"] = clf.p
+        out[name + "_ashape"] = np.array(clf.a.shape)
+        out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        print(f"  {name}: iters={meta['iters']} alphas={out[name + '_alphas']} util={out[name + '_util']}")
     # mixed macro recall / macro precision (frank_wolfe.py:917-938)
     clf, meta = fw.find_classifier_optimizing_mixed_macro_recall_and_macro_precision_using_fw(
         eta, eta, 5, alpha=0.4, max_iters=4, skip_tn=True, seed=0, alpha_uniform_search_step=0.002, return_meta=True)

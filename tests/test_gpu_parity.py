@@ -680,3 +680,39 @@ def test_bca_batched_csr_record_metrics_vs_oracle(xb, oracle, metric):
         lambda s: oracle.predict_using_bc_with_0approx(y, metric, 5, seed=s, skip_tn=skip)[1]["utilities"][-1],
         ometa["utilities"][-1])
     assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol, (meta["utilities"], ometa["utilities"])
+
+
+# ---- driver options of both algorithms against golden runs of the live reference -----------------------
+OPT_BCA = [("opt_bca_nonorm", dict(normalize_conf_matrix=False, seed=0, skip_tn=True)),
+           ("opt_bca_min", dict(maximize=False, seed=1, skip_tn=True, max_iters=3)),
+           ("opt_bca_noshuffle_tn", dict(shuffle_order=False, seed=2, skip_tn=False))]
+OPT_FW = [("opt_fw_nonorm", dict(normalize_conf_matrix=False, skip_tn=True, max_iters=4)),
+          ("opt_fw_fixed", dict(search_for_best_alpha=False, skip_tn=True, max_iters=5)),
+          ("opt_fw_tuple", dict(init_classifier="tuple", skip_tn=True, max_iters=4)),
+          ("opt_fw_random", dict(init_classifier="random", skip_tn=True, max_iters=4, seed=5)),
+          ("opt_fw_coarse", dict(alpha_uniform_search_step=0.01, skip_tn=True, max_iters=4))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", OPT_BCA, ids=[c[0] for c in OPT_BCA])
+def test_bca_driver_options_golden(xb, golden, name, kw):
+    g = golden("extra")
+    pred, meta = xb.predict_using_bc_with_0approx(g["opt_eta"], _metric(xb, "f1"), 4, return_meta=True, mode="exact", **kw)
+    assert (_idx(pred, 4) == g[name + "_pred"]).all()
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", OPT_FW, ids=[c[0] for c in OPT_FW])
+def test_fw_driver_options_golden(xb, golden, name, kw):
+    from xcolumns_b200 import metrics as M
+    g = golden("extra")
+    kw = dict(kw)
+    if kw.get("init_classifier") == "tuple":
+        kw["init_classifier"] = (g["opt_a0"], g["opt_b0"])
+    kw.setdefault("seed", 0)
+    clf, meta = xb.find_classifier_using_fw(g["eta"], g["eta"], M.macro_f1_score_on_conf_matrix, 5, return_meta=True, **kw)
+    assert tuple(clf.a.shape) == tuple(g[name + "_ashape"])
+    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+    assert np.allclose(clf.p, g[name + "_p"], atol=1e-6)

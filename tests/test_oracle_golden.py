@@ -225,3 +225,37 @@ def test_fw_mixed_macro_recall_and_precision(golden, oracle):
                                                     alpha_uniform_search_step=0.002, recall_precision_alpha=0.4)
     assert np.allclose(meta["alphas"], g["fw_rp_alphas"], rtol=0, atol=1e-9)
     assert np.allclose(meta["utilities"], g["fw_rp_util"], rtol=1e-6, atol=0)
+
+
+OPT_BCA = [("opt_bca_nonorm", dict(normalize_conf_matrix=False, seed=0, skip_tn=True)),
+           ("opt_bca_min", dict(maximize=False, seed=1, skip_tn=True, max_iters=3)),
+           ("opt_bca_noshuffle_tn", dict(shuffle_order=False, seed=2, skip_tn=False))]
+OPT_FW = [("opt_fw_nonorm", dict(normalize_conf_matrix=False, skip_tn=True, max_iters=4)),
+          ("opt_fw_fixed", dict(search_for_best_alpha=False, skip_tn=True, max_iters=5)),
+          ("opt_fw_tuple", dict(init_classifier="tuple", skip_tn=True, max_iters=4)),
+          ("opt_fw_random", dict(init_classifier="random", skip_tn=True, max_iters=4, seed=5)),
+          ("opt_fw_coarse", dict(alpha_uniform_search_step=0.01, skip_tn=True, max_iters=4))]
+
+
+@pytest.mark.parametrize("name,kw", OPT_BCA, ids=[c[0] for c in OPT_BCA])
+def test_bca_driver_options(golden, oracle, name, kw):
+    """un-normalised confusion matrix (only instance 0 is visited, block_coordinate.py:403-414), minimisation,
+    fixed order with true negatives: bit-equal to the live reference"""
+    g = golden("extra")
+    pred, meta = oracle.predict_using_bc_with_0approx(g["opt_eta"], "f1", 4, **kw)
+    assert (_idx(pred, 4) == g[name + "_pred"]).all()
+    assert (np.array(meta["utilities"]) == g[name + "_util"]).all()
+
+
+@pytest.mark.parametrize("name,kw", OPT_FW, ids=[c[0] for c in OPT_FW])
+def test_fw_driver_options(golden, oracle, name, kw):
+    g = golden("extra")
+    kw = dict(kw)
+    if kw.get("init_classifier") == "tuple":
+        kw["init_classifier"] = (g["opt_a0"], g["opt_b0"])
+    kw.setdefault("seed", 0)
+    a, b, p, meta = oracle.find_classifier_using_fw(g["eta"], g["eta"], "f1", 5, **kw)
+    assert tuple(a.shape) == tuple(g[name + "_ashape"])
+    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
+    assert np.allclose(p, g[name + "_p"], atol=1e-6)
