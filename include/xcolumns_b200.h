@@ -29,7 +29,7 @@ extern "C" {
 
 #define XC_API __attribute__((visibility("default")))
 
-#define XC_ABI_VERSION 2
+#define XC_ABI_VERSION 3
 
 /* element types of probability matrices / weight vectors */
 enum { XC_F32 = 0, XC_F64 = 1 };
@@ -268,12 +268,29 @@ XC_API int xc_cov_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m
                               const double *Ef, int32_t *pred_idx, double *dEf, void *stream);
 XC_API int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void *stream);
 
+/* One whole batched coverage sweep of a single process as one host call (batch kernel + fold per `batch`
+ * entries of `order`); dEf must hold ones on entry and holds ones on return.                          */
+XC_API int xc_cov_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                            const int64_t *indptr, int64_t m, const int32_t *order, int64_t n_order,
+                            int64_t batch, int k, double alpha, double *Ef, int32_t *pred_idx, double *dEf,
+                            void *stream);
+XC_API int xc_cov_sweep_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld,
+                              const int32_t *order, int64_t n_order, int64_t batch, int k, double alpha,
+                              double *Ef, int32_t *pred_idx, double *dEf, void *stream);
+/* Ef of a compact prediction over DENSE rows (any order, float64 compare-and-swap products); zero
+ * probabilities count as "not stored", i.e. the CSR semantics of block_coordinate.py:539-580 that the
+ * coverage path follows for both layouts.  ref: numba_csr_functions.py:325-382.                       */
+XC_API int xc_cov_state_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m, int64_t ld,
+                              const int32_t *pred_idx, int k, double *Ef, void *stream);
+/* out_dev[0] = 1 - mean(Ef), ref: block_coordinate.py:583-597 (the alpha = 1 part)                    */
+XC_API int xc_cov_utility(xc_ctx *ctx, const double *Ef, int64_t m, double *out_dev, void *stream);
+
 /* Jaccard / G-mean / H-mean: the gain is not affine in eta but still a closed form of eta and four
  * per-label numbers (rec: 4 floats per label, 16-byte aligned; see csrc/bca_batched.cu for the algebra).
  * xc_bca_rec is the counterpart of xc_bca_coef (folds the pending deltas, writes the records);
  * xc_bca_batch_dense_rec the counterpart of xc_bca_batch_dense (tp/fp/fn: the frozen state, read for the
- * k currently selected labels of every row).  xc_bca_commit_p2p writes records instead of coefficients for
- * these metrics (pass the record array as coef_n, coef_s may be NULL).                              */
+ * k currently selected labels of every row).  xc_bca_sweep_dense_pipe takes the record array in place of the
+ * coefficient sets for these metrics.                              */
 XC_API int xc_bca_rec(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
                       double *dtp, double *dfp, double *dfn, int64_t m, float *rec, void *stream);
 XC_API int xc_bca_batch_csr_rec(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
@@ -306,7 +323,8 @@ XC_API int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const void *
 /* One window per rank: cudaMalloc'ed, exported with CUDA IPC (ipc_handle_out: 64 bytes), mapped by
  * every other rank with xc_p2p_open(handles = the world * 64 gathered bytes).  xc_p2p_payload
  * returns the local payload (device pointer, payload_bytes long, zero-initialised); for the batched
- * sweep it holds two delta buffers of xc_bca_delta_stride(m) bytes each, [dtp | dfp | dfn].        */
+ * sweep it holds xc_bca_pipe_buffers(lag) delta buffers of xc_bca_delta_stride(m) bytes each,
+ * [dtp | dfp | dfn].        */
 typedef struct xc_p2p xc_p2p;
 XC_API int xc_p2p_create(xc_ctx *ctx, int world, int rank, int64_t payload_bytes, xc_p2p **out,
                          void *ipc_handle_out);
@@ -315,14 +333,45 @@ XC_API void *xc_p2p_payload(xc_p2p *w);
 XC_API int xc_p2p_error(xc_ctx *ctx, xc_p2p *w, unsigned *out);
 XC_API void xc_p2p_destroy(xc_ctx *ctx, xc_p2p *w);
 XC_API int64_t xc_bca_delta_stride(int64_t m);
-/* The exchange step of the sharded batched sweep as ONE kernel: flag every peer, wait for every
- * peer's flag, add the W delta vectors of buffer `buf` (read from the peers' windows over NVLink, in
- * rank order: bit-identical on every rank) into tp/fp/fn, refresh the gain coefficients (like
- * xc_bca_coef) and clear the local buffer buf ^ 1.  Every rank must call it the same number of
- * times.  Replaces ncclAllReduce + xc_bca_coef between two batches.                              */
-XC_API int xc_bca_commit_p2p(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, double *tp,
-                             double *fp, double *fn, int64_t m, int buf, float *coef_n,
-                             float *coef_s, void *stream);
+/* One block-Jacobi sweep over this rank's rows as ONE host call, single process (w = NULL) or with the rows
+ * sharded over the GPUs of one box (w = the peer window; every rank calls with the same n_batches / lag).
+ * ref: block_coordinate.py:448-463 (the per-instance loop of one sweep) evaluated batch-wise.
+ * Per batch b (rows order[b * batch ...]): the streaming batch kernel accumulates the deltas of its rows
+ * into delta buffer (batch0 + b) % NB; the commit kernel then folds that buffer -- with a window: flags every
+ * peer, waits for every peer's flag and adds the W buffers read over NVLink in rank order, so that the
+ * replicated state stays bit-identical -- into tp/fp/fn, refreshes the gain coefficients (or the records
+ * of Jaccard / G-mean / H-mean) and clears buffer (batch0 + b + lag + 1) % NB.  NB = xc_bca_pipe_buffers(lag)
+ * buffers of xc_bca_delta_stride(m) bytes each: in the window's payload, or `delta` when w is NULL; all
+ * zero before the first call, never touched by the host afterwards.  batch0: number of batches of all
+ * earlier calls on these buffers (the buffer rotation continues across sweeps).
+ * lag = 0: strict order K_0, commit_0, K_1, ... on `stream`.  lag = 1: batch b sees the state after commit
+ * b - 2; consecutive batch kernels run concurrently on two internal streams and every commit overlaps the
+ * next batch's streaming (the call forks from and joins `stream`; record metrics always run with lag 0).
+ * coef: (lag + 1) sets of 4 * xc_bca_coef_len(m) floats, each [coef_n | coef_s] (or the records).
+ * On return (stream order) tp/fp/fn hold the state after all n_batches commits.                      */
+XC_API int xc_bca_pipe_buffers(int lag);
+XC_API int xc_bca_sweep_dense_pipe(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, const void *eta,
+                                   int dtype, int64_t m, int64_t ld, const int32_t *order, int64_t n_order,
+                                   int64_t batch, int64_t n_batches, int lag, int64_t batch0, int k,
+                                   float *coef, int32_t *pred_idx, double *tp, double *fp, double *fn,
+                                   double *delta, void *stream);
+
+/* ---- host -> device upload of PAGEABLE host memory (what a numpy caller of the reference passes) ---- */
+/* rows x width_bytes from src_host (pitch src_pitch, ordinary pageable memory) to dst_dev (pitch dst_pitch):
+ * host threads copy chunk c + 1 into one of two pinned staging buffers while the DMA of chunk c runs.
+ * Returns when the last DMA has completed.  Replaces the implicit staged copy of the reference's
+ * torch / numpy conversion at its entry points (block_coordinate.py:388-401).                         */
+XC_API int xc_h2d_staged(xc_ctx *ctx, void *dst_dev, int64_t dst_pitch, const void *src_host,
+                         int64_t src_pitch, int64_t width_bytes, int64_t rows, int nthreads, void *stream);
+
+/* ---- per-launch timing of the streaming batch kernels (measurement only) ------------------ */
+/* While enabled, xc_bca_sweep_dense_pipe brackets every batch kernel with CUDA events on the stream it
+ * is launched on.  xc_timing_read synchronises the device and returns for up to `cap` launches the start
+ * and end time (ms since the first recorded event) and the rows processed (HOST arrays), the number of
+ * recorded launches in *count_host, and clears the log.                                              */
+XC_API int xc_timing_enable(xc_ctx *ctx, int on);
+XC_API int xc_timing_read(xc_ctx *ctx, int cap, double *start_ms_host, double *end_ms_host,
+                          int64_t *rows_host, int *count_host);
 
 /* ---- Frank-Wolfe iterate ----------------------------------------------------------------- */
 /* ref: frank_wolfe.py:601-606: weighted top-k of every row with the linear classifier (a, b)

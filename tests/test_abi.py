@@ -46,7 +46,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(decls) >= 30
     for name in decls:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert lib.xc_abi_version() == 2
+    assert lib.xc_abi_version() == 3
     assert lib.xc_strerror(-1) == b"invalid argument"
 
 
@@ -71,7 +71,8 @@ def test_ctypes_prototypes_match_header():
     bound = set(_lib._SIGNATURES) | {"xc_abi_version", "xc_strerror", "xc_ctx_create", "xc_ctx_destroy",
                                      "xc_last_cuda_error", "xc_launch_count", "xc_sm_count", "xc_fill_pred_dense_host", "xc_scatter_pred_dense_host",
                                      "xc_zero_host", "xc_bca_coef_len", "xc_fw_alpha_scratch_bytes",
-                                     "xc_fw_alpha_ctl_offset", "xc_p2p_payload", "xc_p2p_destroy", "xc_bca_delta_stride"}
+                                     "xc_fw_alpha_ctl_offset", "xc_p2p_payload", "xc_p2p_destroy", "xc_bca_delta_stride",
+                                     "xc_bca_pipe_buffers"}
     assert set(decls) == bound, f"unbound: {set(decls) - bound}, undeclared: {bound - set(decls)}"
 
 

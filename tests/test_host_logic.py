@@ -106,3 +106,18 @@ def test_confusion_matrix_container():
     assert (b.tp == 2 * a.tp).all() and ((a * 2).fn == b.fn).all() and ((b / 2).fp == a.fp).all()
     n = a.normalize()
     assert np.allclose(n.tp + n.fp + n.fn + n.tn, 1.0)
+
+
+def test_vectorised_classifier_draw_is_the_reference_stream():
+    """predict_using_randomized_weighted_classifier draws one classifier per row; the vectorised draw consumes the
+    same Generator stream as the reference's per-row rng.choice(arange(len(p)), p=p) (frank_wolfe.py:70)"""
+    from xcolumns_b200.frank_wolfe import _draw_classifiers
+    for seed in (0, 3):
+        for dt in (np.float32, np.float64):
+            p = np.random.default_rng(5).random(21).astype(dt)
+            p /= p.sum()
+            rng = np.random.default_rng(seed)
+            ref = np.array([rng.choice(np.arange(p.shape[0]), p=p) for _ in range(4000)])
+            assert (_draw_classifiers(p, 4000, seed) == ref).all()
+    with pytest.raises(ValueError):
+        _draw_classifiers(np.array([0.5, 0.6]), 10, 0)

@@ -21,6 +21,7 @@ _NP2CODE = {np.dtype(np.float32): XC_F32, np.dtype(np.float64): XC_F64}
 _T2CODE = {torch.float32: XC_F32, torch.float64: XC_F64}
 _CODE2T = {XC_F32: torch.float32, XC_F64: torch.float64}
 _T2NP = {torch.float32: np.float32, torch.float64: np.float64}
+_STAGED_MIN_BYTES = 64 << 20
 
 
 def pick_device(*objs) -> torch.device:
@@ -125,7 +126,16 @@ def dense_to_device(x, device: torch.device, dtype=None, pad: bool = True) -> De
     vec = 4 if code == XC_F32 else 2
     ld = ((m + vec - 1) // vec) * vec if pad else m
     nbytes = n * m * src.element_size()
-    if ld == m:
+    if nbytes >= _STAGED_MIN_BYTES and not src.is_pinned():
+        # an ordinary (pageable) numpy array -- what a caller of the reference passes: threaded copies into two
+        # pinned staging buffers overlapped with the DMA (csrc/host.cu: xc_h2d_staged)
+        t = torch.empty((n, ld), dtype=src.dtype, device=device)
+        if ld != m:
+            t[:, m:].zero_()
+        es = src.element_size()
+        ctx_for(device).call("xc_h2d_staged", C.c_void_p(t.data_ptr()), ld * es, C.c_void_p(src.data_ptr()), m * es,
+                             m * es, n, 0, stream_ptr(device))
+    elif ld == m:
         t = src.to(device, non_blocking=True)
     else:
         t = torch.zeros((n, ld), dtype=src.dtype, device=device)

@@ -46,7 +46,11 @@ _SIGNATURES = {
     "xc_p2p_create": [_int, _int, _i64, _vp, _vp],
     "xc_p2p_open": [_vp, _vp],
     "xc_p2p_error": [_vp, _vp],
-    "xc_bca_commit_p2p": [_vp, _MP, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp],
+    "xc_bca_sweep_dense_pipe": [_vp, _MP, _vp, _int, _i64, _i64, _vp, _i64, _i64, _i64, _int, _i64, _int, _vp, _vp,
+                                _vp, _vp, _vp, _vp, _vp],
+    "xc_h2d_staged": [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp],
+    "xc_timing_enable": [_int],
+    "xc_timing_read": [_int, _vp, _vp, _vp, _vp],
     "xc_bca_online_dense": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _int, _MP, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_batch_csr_rec": [_MP, _vp, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_rec": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
@@ -70,6 +74,10 @@ _SIGNATURES = {
     "xc_cov_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _dbl, _vp, _vp, _vp, _vp],
     "xc_cov_batch_dense": [_vp, _int, _i64, _i64, _vp, _i64, _int, _dbl, _vp, _vp, _vp, _vp],
     "xc_cov_fold": [_vp, _vp, _i64, _vp],
+    "xc_cov_sweep_csr": [_vp, _int, _vp, _vp, _i64, _vp, _i64, _i64, _int, _dbl, _vp, _vp, _vp, _vp],
+    "xc_cov_sweep_dense": [_vp, _int, _i64, _i64, _vp, _i64, _i64, _int, _dbl, _vp, _vp, _vp, _vp],
+    "xc_cov_state_dense": [_vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp],
+    "xc_cov_utility": [_vp, _i64, _vp, _vp],
     "xc_fw_iterate_dense": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _int, _vp, _vp, _vp, _vp],
     "xc_fw_iterate_csr": [_vp, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp],
     "xc_fw_make_conf": [_vp, _vp, _vp, _i64, _dbl, _int, _int, _vp, _vp],
@@ -119,6 +127,8 @@ def load():
         lib.xc_p2p_destroy.restype = None
         lib.xc_bca_delta_stride.argtypes = [C.c_int64]
         lib.xc_bca_delta_stride.restype = C.c_int64
+        lib.xc_bca_pipe_buffers.argtypes = [C.c_int]
+        lib.xc_bca_pipe_buffers.restype = C.c_int
         lib.xc_bca_coef_len.argtypes = [C.c_int64]
         lib.xc_bca_coef_len.restype = C.c_int64
         lib.xc_fill_pred_dense_host.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,

@@ -37,6 +37,12 @@ from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
 _AUTO_EXACT_MAX_ROWS = 4096
 
 
+def _default_lag() -> int:
+    """Commits applied this many batches late in the pipelined dense sweep (csrc/bca_batched.cu:
+    xc_bca_sweep_dense_pipe); $XCOLUMNS_B200_LAG=0 restores the strict batch order."""
+    return 0 if os.environ.get("XCOLUMNS_B200_LAG", "1") == "0" else 1
+
+
 def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n_rows=None, mix=None) -> MetricParams:
     n_rows = n_div if n_rows is None else n_rows
     c1, beta2 = M.metric_c1_beta2(metric_id, beta)
@@ -107,27 +113,34 @@ class BcaSession:
         f64 = dict(dtype=torch.float64, device=self.device)
         self.state = torch.zeros((4, self.m), **f64)           # tp, fp, fn, tn
         self.state[3].fill_(-1.0)
-        self.delta = torch.zeros((3, self.m), **f64)           # pending batch deltas
-        self.peer: Optional[PeerWindow] = None                 # peer-memory commits (sharded dense/CSR batches)
-        if peer_commit_enabled(self.comm, self.device, self.m):
-            stride = int(self.ctx.lib.xc_bca_delta_stride(self.m))
-            peer = PeerWindow(self.ctx, self.comm, 2 * stride, self.device)
-            if peer.ok:
-                self.peer = peer
-                # the two delta buffers live in the window: batch b accumulates into buffer b & 1
-                self.delta2 = [peer.payload[b * stride: b * stride + 24 * self.m].view(torch.float64).view(3, self.m)
-                               for b in range(2)]
-            else:
-                peer.close()
-        self.colsum: Optional[torch.Tensor] = None
-        clen = int(self.ctx.lib.xc_bca_coef_len(self.m))       # padded to whole coefficient tiles
-        self.coef_n = torch.zeros((clen, 2), dtype=torch.float32, device=self.device)
-        self.coef_s = torch.zeros((clen, 2), dtype=torch.float32, device=self.device)
-        self.util_buf = torch.zeros(8, **f64)
-        self.pred: Optional[torch.Tensor] = None
+        self.delta = torch.zeros((3, self.m), **f64)           # pending batch deltas (per-batch entry points)
         # Jaccard / G-mean / H-mean: 16-byte per-label records instead of the affine coefficient pairs
         self.use_rec = (params.metric in M.RECORD_GAIN_METRICS) and not params.mix
+        clen = int(self.ctx.lib.xc_bca_coef_len(self.m))       # padded to whole coefficient tiles
+        # Dense rows of one process, or of the ranks of one box with a peer window: the whole sweep is ONE C call
+        # (xc_bca_sweep_dense_pipe); commits are applied `lag` batches late so consecutive batches overlap.
+        self.lag = 0 if (self.is_csr or self.use_rec) else _default_lag()
+        self.pipe = (not self.is_csr) and self.comm.world == 1
+        self._gb = 0                                           # batches issued so far (delta-buffer rotation)
+        self.peer: Optional[PeerWindow] = None                 # peer-memory commits (sharded dense rows)
+        stride = int(self.ctx.lib.xc_bca_delta_stride(self.m))
+        nbuf = int(self.ctx.lib.xc_bca_pipe_buffers(self.lag))
+        if (not self.is_csr) and peer_commit_enabled(self.comm, self.device, self.m):
+            peer = PeerWindow(self.ctx, self.comm, nbuf * stride, self.device)
+            if peer.ok:
+                self.peer = peer
+                self.pipe = True
+            else:
+                peer.close()
+        self.delta_pipe = (torch.zeros(nbuf * stride, dtype=torch.uint8, device=self.device)
+                           if (self.pipe and self.peer is None) else None)
+        self.colsum: Optional[torch.Tensor] = None
+        # [set][coef_n | coef_s][label][B, A]: set 1 is the second coefficient version of the pipelined sweep
+        self.coef = torch.zeros((2, 2, clen, 2), dtype=torch.float32, device=self.device)
+        self.coef_n, self.coef_s = self.coef[0, 0], self.coef[0, 1]
         self.rec = torch.zeros((clen, 4), dtype=torch.float32, device=self.device) if self.use_rec else None
+        self.util_buf = torch.zeros(8, **f64)
+        self.pred: Optional[torch.Tensor] = None
 
     # -- small helpers ---------------------------------------------------------------------
     def _s(self):
@@ -136,14 +149,14 @@ class BcaSession:
     def _sp(self, i):
         return C.c_void_p(self.state[i].data_ptr())
 
-    def _dp(self, i, buf: int = 0):
-        t = self.delta2[buf] if self.peer is not None else self.delta
-        return C.c_void_p(t[i].data_ptr())
+    def _dp(self, i):
+        return C.c_void_p(self.delta[i].data_ptr())
 
     def zero_delta(self) -> None:
-        if self.peer is not None:
-            self.peer.payload.zero_()
-        else:
+        """Only the per-batch entry points (xc_bca_coef / xc_bca_batch_*) keep pending deltas in self.delta; the
+        pipelined sweep rotates and clears its own buffers on the device (no host-side clearing: a slower peer
+        may still be reading this rank's window)."""
+        if not self.pipe:
             self.delta.zero_()
 
     def close(self) -> None:
@@ -151,7 +164,6 @@ class BcaSession:
             torch.cuda.synchronize(self.device)
             self.comm.barrier()          # nobody may still be reading this rank's window
             self.peer.check()
-            self.delta2 = None           # views into the window
             self.peer.close()
             self.peer = None
 
@@ -255,11 +267,7 @@ class BcaSession:
         if full or os.environ.get("XCOLUMNS_B200_SWEEP_RECOMPUTE") == "1":   # the switch restores the reference's cadence
             self.recompute(XC_SUM_FAST)
             return
-        coef_a = self.rec if self.use_rec else self.coef_n
-        if self.peer is not None:
-            self.ctx.call("xc_bca_commit_p2p", self.peer.handle, C.byref(self.p), self._sp(0), self._sp(1),
-                          self._sp(2), self.m, self._last_buf, dev.ptr(coef_a), dev.ptr(self.coef_s), self._s())
-        elif self.use_rec:
+        if self.use_rec:
             self.ctx.call("xc_bca_rec", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
                           self._dp(1), self._dp(2), self.m, dev.ptr(self.rec), self._s())
         else:
@@ -270,82 +278,72 @@ class BcaSession:
             self.state[3] = -self.state[0] - self.state[1] - self.state[2] + n_total
 
     def sweep_and_fold(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int], full: bool) -> None:
-        """sweep_batched + finish_sweep.  A single process without events to record issues the whole sweep
-        through one C call (xc_bca_sweep_*): small problems are bound by the per-call overhead of this shim."""
-        if self.comm.world > 1 or full:
+        """One block-Jacobi sweep + the state after it.  Dense rows (one process, or sharded with a peer window) and
+        single-process CSR rows issue the whole sweep through ONE C call (small problems are bound by the per-call
+        overhead of this shim; sharded sweeps by the arrival skew a host-driven batch loop feeds into the barriers).
+        full: recompute the state from the prediction afterwards (block_coordinate.py:465-467)."""
+        d, k = self.data, self.k
+        n_loc = int(order_dev.numel())
+        if self.pipe:
+            nb = n_batches if n_batches is not None else (n_loc + batch - 1) // batch
+            self.ctx.call("xc_bca_sweep_dense_pipe", self.peer.handle if self.peer is not None else None,
+                          C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, dev.ptr(order_dev), n_loc, int(batch),
+                          int(nb), int(self.lag), int(self._gb), k, dev.ptr(self.rec if self.use_rec else self.coef),
+                          dev.ptr(self.pred), self._sp(0), self._sp(1), self._sp(2), dev.ptr(self.delta_pipe), self._s())
+            self._gb += nb
+            if full or os.environ.get("XCOLUMNS_B200_SWEEP_RECOMPUTE") == "1":
+                self.recompute(XC_SUM_FAST)
+            elif not self.p.skip_tn:
+                self.state[3] = -self.state[0] - self.state[1] - self.state[2] + self.comm.n_global(self.n)
+            return
+        if self.comm.world > 1 or full or not self.is_csr:
             self.sweep_batched(order_dev, batch, n_batches)
             self.finish_sweep(full)
             return
-        d, k = self.data, self.k
-        if self.is_csr:
-            self.ctx.call("xc_bca_sweep_csr", C.byref(self.p), dev.ptr(d.data), d.code, dev.ptr(d.indices),
-                          dev.ptr(d.indptr), d.m, dev.ptr(order_dev), int(order_dev.numel()), int(batch), k,
-                          dev.ptr(self.rec if self.use_rec else self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
-                          self._sp(0), self._sp(1),
-                          self._sp(2), self._dp(0), self._dp(1), self._dp(2), self._s())
-        else:
-            self.ctx.call("xc_bca_sweep_dense", C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, dev.ptr(order_dev),
-                          int(order_dev.numel()), int(batch), k, dev.ptr(self.rec if self.use_rec else self.coef_n),
-                          dev.ptr(self.coef_s), dev.ptr(self.pred), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
-                          self._dp(1), self._dp(2), self._s())
+        self.ctx.call("xc_bca_sweep_csr", C.byref(self.p), dev.ptr(d.data), d.code, dev.ptr(d.indices),
+                      dev.ptr(d.indptr), d.m, dev.ptr(order_dev), n_loc, int(batch), k,
+                      dev.ptr(self.rec if self.use_rec else self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
+                      self._sp(0), self._sp(1), self._sp(2), self._dp(0), self._dp(1), self._dp(2), self._s())
         if not self.p.skip_tn:
             self.state[3] = -self.state[0] - self.state[1] - self.state[2] + self.n
 
-    def sweep_batched(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int] = None,
-                      events: Optional[list] = None) -> None:
-        """One block-Jacobi sweep over the (local) rows in order_dev, `batch` rows per commit.
-        n_batches (distributed): common number of commits so every rank joins every all-reduce.
-        events: if a list, (start, end, rows) CUDA-event triples around every batch kernel are
-        appended (bench.py's per-launch roofline measurement)."""
+    def sweep_batched(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int] = None) -> None:
+        """One block-Jacobi sweep over the (local) rows in order_dev through the per-batch entry points, `batch`
+        rows per commit; with several ranks and no peer window (CSR label spaces, gloo) the deltas of every batch
+        are all-reduced.  n_batches (distributed): common number of commits so every rank joins every all-reduce.
+        The pending deltas of the last batch are folded by finish_sweep."""
         d, k = self.data, self.k
         n_loc = int(order_dev.numel())
         nb = n_batches if n_batches is not None else (n_loc + batch - 1) // batch
-        self._last_buf = (nb - 1) & 1 if self.peer is not None else 0
         for b in range(nb):
             lo = min(b * batch, n_loc)
             hi = min(lo + batch, n_loc)
-            cur = b & 1 if self.peer is not None else 0
-            coef_a = self.rec if self.use_rec else self.coef_n
-            if self.peer is not None and b > 0:
-                # exchange + fold + coefficients in one kernel over peer memory (reads buffer (b-1) & 1)
-                self.ctx.call("xc_bca_commit_p2p", self.peer.handle, C.byref(self.p), self._sp(0), self._sp(1),
-                              self._sp(2), self.m, (b - 1) & 1, dev.ptr(coef_a), dev.ptr(self.coef_s), self._s())
+            # fold the pending deltas into the state, refresh the gain coefficients / records
+            if self.use_rec:
+                self.ctx.call("xc_bca_rec", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
+                              self._dp(1), self._dp(2), self.m, dev.ptr(self.rec), self._s())
             else:
-                # fold the pending deltas into the state (none yet in the first batch of a peer-memory sweep),
-                # refresh the gain coefficients / records
-                fold = (None, None, None) if self.peer is not None else (self._dp(0), self._dp(1), self._dp(2))
-                if self.use_rec:
-                    self.ctx.call("xc_bca_rec", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), *fold, self.m,
-                                  dev.ptr(self.rec), self._s())
-                else:
-                    self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), *fold, self.m,
-                                  dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
+                self.ctx.call("xc_bca_coef", C.byref(self.p), self._sp(0), self._sp(1), self._sp(2), self._dp(0),
+                              self._dp(1), self._dp(2), self.m, dev.ptr(self.coef_n), dev.ptr(self.coef_s), self._s())
             if hi > lo:
                 rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
-                if events is not None:
-                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    ev0.record(torch.cuda.current_stream(self.device))
                 if self.is_csr and self.use_rec:
                     self.ctx.call("xc_bca_batch_csr_rec", C.byref(self.p), dev.ptr(d.data), d.code, dev.ptr(d.indices),
                                   dev.ptr(d.indptr), rows, hi - lo, k, dev.ptr(self.rec), self._sp(0), self._sp(1),
-                                  self._sp(2), dev.ptr(self.pred), self._dp(0, cur), self._dp(1, cur),
-                                  self._dp(2, cur), self._s())
+                                  self._sp(2), dev.ptr(self.pred), self._dp(0), self._dp(1), self._dp(2), self._s())
                 elif self.is_csr:
                     self.ctx.call("xc_bca_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
                                   rows, hi - lo, k, dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
-                                  self._dp(0, cur), self._dp(1, cur), self._dp(2, cur), self._s())
+                                  self._dp(0), self._dp(1), self._dp(2), self._s())
                 elif self.use_rec:
                     self.ctx.call("xc_bca_batch_dense_rec", C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, rows,
                                   hi - lo, k, dev.ptr(self.rec), self._sp(0), self._sp(1), self._sp(2),
-                                  dev.ptr(self.pred), self._dp(0, cur), self._dp(1, cur), self._dp(2, cur), self._s())
+                                  dev.ptr(self.pred), self._dp(0), self._dp(1), self._dp(2), self._s())
                 else:
                     self.ctx.call("xc_bca_batch_dense", dev.ptr(d.t), d.code, d.m, d.ld, rows, hi - lo, k,
-                                  dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._dp(0, cur),
-                                  self._dp(1, cur), self._dp(2, cur), self._s())
-                if events is not None:
-                    ev1.record(torch.cuda.current_stream(self.device))
-                    events.append((ev0, ev1, hi - lo))
-            if self.comm.world > 1 and self.peer is None:
+                                  dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred), self._dp(0),
+                                  self._dp(1), self._dp(2), self._s())
+            if self.comm.world > 1:
                 self.comm.allreduce_sum_(self.delta)
 
 
@@ -518,6 +516,7 @@ def predict_using_bc_with_0approx(
         else:
             batch = default_batch_rows(n_order, sess.wave_rows())
         n_batches = comm.max_int((n_order + batch - 1) // batch)
+        batch_max = comm.max_int(batch)      # ragged shards: ranks may differ by a row, decisions must not
         base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
         order_dev = torch.arange(n_order, dtype=torch.int32, device=device)
         sess.recompute(XC_SUM_FAST)
@@ -555,22 +554,32 @@ def predict_using_bc_with_0approx(
             events[j].synchronize()
             old_u, new_u = (float(v) for v in util_host[j])
             regressed = (new_u < old_u - 1e-12) if maximize else (new_u > old_u + 1e-12)
-            if regressed and batch > 16 and not batch_size:
+            if regressed:
                 # Block-Jacobi overshoot (the rows of a batch all reacted to the same frozen state): the
                 # sequential sweep this mode stands in for cannot lose utility.  Roll the sweep (and the
-                # speculative one after it) back and repeat it with 4x more commits.
+                # speculative one after it) back ...
                 sess.pred = saved[j]
                 events.clear()
                 saved.clear()
-                batch = max(16, batch // 4)
-                n_batches = comm.max_int((n_order + batch - 1) // batch)
-                meta["batch_size"] = batch
-                attempt += 1
                 sess.recompute(XC_SUM_FAST)
                 sess.utility_device(0)
-                log_info(f"    Iteration {j} lost utility ({old_u} -> {new_u}); repeating with batches of {batch} rows", verbose)
-                enqueue(j)
-                continue
+                # (the decision is taken on numbers every rank agrees on: the utilities come from the
+                #  replicated state, batch_max is all-reduced)
+                if batch_max > 16 and not batch_size:
+                    # ... and repeat it with 4x more commits
+                    batch = max(16, batch // 4)
+                    batch_max = max(16, batch_max // 4)
+                    n_batches = comm.max_int((n_order + batch - 1) // batch)
+                    meta["batch_size"] = batch
+                    attempt += 1
+                    log_info(f"    Iteration {j} lost utility ({old_u} -> {new_u}); repeating with batches of {batch} rows", verbose)
+                    enqueue(j)
+                    continue
+                # ... or, with a caller-chosen / already minimal batch, keep the prediction the sweep started
+                # from: the result is never worse than what the sweep began with
+                log_info(f"  Stopping: iteration {j} lost utility ({old_u} -> {new_u}) and cannot be repeated "
+                         f"with smaller batches", verbose)
+                break
             saved.pop(j, None)
             meta["iters"] = j
             meta["utilities"].append(new_u)
@@ -583,6 +592,7 @@ def predict_using_bc_with_0approx(
             j += 1
 
     meta["launches"] = sess.ctx.launches()
+    meta["lag"] = sess.lag if (mode == "batched" and sess.pipe) else 0
     meta["commit"] = "peer-memory" if sess.peer is not None else ("all-reduce" if comm.world > 1 else "local")
     sess.close()
     _mark("sweeps")
@@ -675,6 +685,118 @@ def _finish_pred(y_proba, pred: torch.Tensor, m: int, y_pred_format: str, prefil
 # coverage (block_coordinate.py:600-701; CSR semantics for both layouts)
 # ------------------------------------------------------------------------------------------
 
+class CoverageSession:
+    """State of one coverage-BCA run on one device (block_coordinate.py:539-701, CSR semantics for both layouts):
+    Ef[j] = prod_i (1 - yhat_ij eta_ij) in float64, the compact prediction, the batch factors dEf.  With a
+    torch.distributed communicator every rank holds a row shard: Ef is replicated, the per-batch factors and the
+    recomputed state are all-reduced with a product."""
+
+    def __init__(self, data, k: int, alpha: float, comm: Optional[Comm] = None):
+        self.data = data
+        self.is_csr = isinstance(data, dev.CsrDev)
+        self.device = (data.data if self.is_csr else data.t).device
+        self.ctx = dev.ctx_for(self.device)
+        self.k, self.alpha = k, float(alpha)
+        self.comm = comm or Comm(None)
+        self.n, self.m = data.n, data.m
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.Ef = torch.empty(self.m, **f64)
+        self.dEf = torch.ones(self.m, **f64)
+        self.util_buf = torch.zeros(4, **f64)
+        self.pred: Optional[torch.Tensor] = None
+        self._csr_view = data if self.is_csr else None
+
+    def _s(self):
+        return dev.stream_ptr(self.device)
+
+    def csr_view(self):
+        """stored entries of every row: the rows themselves, or (sequential mode on dense rows only) the
+        non-zeros of the dense rows -- what csr_matrix(dense) holds"""
+        if self._csr_view is None:
+            self._csr_view = _dense_as_csr(self.data)
+        return self._csr_view
+
+    def state(self, order: int) -> None:
+        """Ef from the current prediction (numba_csr_functions.py:325-382 as called at :665 / :676)"""
+        d, k = self.data, self.k
+        if self.is_csr or order == XC_SUM_ORDERED:
+            v = self.csr_view()
+            self.ctx.call("xc_cov_state_csr", dev.ptr(v.data), v.code, dev.ptr(v.indices), dev.ptr(v.indptr), self.n,
+                          self.m, dev.ptr(self.pred), k, order, dev.ptr(self.Ef), self._s())
+        else:
+            self.ctx.call("xc_cov_state_dense", dev.ptr(d.t), d.code, d.n, d.m, d.ld, dev.ptr(self.pred), k,
+                          dev.ptr(self.Ef), self._s())
+        self.comm.allreduce_prod_(self.Ef)
+
+    def _precision_part(self) -> torch.Tensor:
+        """sum_j tp_j / n / k on the device (:593-595)"""
+        d, k = self.data, self.k
+        tp = torch.zeros(self.m, dtype=torch.float64, device=self.device)
+        fp, fn = torch.zeros_like(tp), torch.zeros_like(tp)
+        if self.is_csr:
+            self.ctx.call("xc_confmat_csr_compact", dev.ptr(d.data), dev.ptr(d.indices), dev.ptr(d.indptr), d.code,
+                          dev.ptr(self.pred), k, self.n, self.m, XC_SUM_FAST, dev.ptr(tp), dev.ptr(fp), dev.ptr(fn), self._s())
+        else:
+            self.ctx.call("xc_confmat_dense_compact", dev.ptr(d.t), d.code, d.ld, dev.ptr(self.pred), k, d.n, d.m,
+                          XC_SUM_FAST, None, dev.ptr(tp), dev.ptr(fp), dev.ptr(fn), self._s())
+        self.comm.allreduce_sum_(tp)
+        return (tp / self.comm.n_global(self.n) / k).sum()
+
+    def utility_host(self) -> float:
+        """the reference's expression on the host (numpy's pairwise mean: bit-equal in the sequential mode)"""
+        cov = 1 - float(self.Ef.cpu().numpy().mean())       # :592
+        if self.alpha < 1:
+            cov = self.alpha * cov + (1 - self.alpha) * float(self._precision_part())
+        return cov
+
+    def utility_device(self, slot: int) -> None:
+        self.ctx.call("xc_cov_utility", dev.ptr(self.Ef), self.m, C.c_void_p(self.util_buf[slot:].data_ptr()), self._s())
+        if self.alpha < 1:
+            self.util_buf[slot] = self.alpha * self.util_buf[slot] + (1 - self.alpha) * self._precision_part()
+
+    def sweep_exact(self, order_dev: torch.Tensor, greedy: bool) -> None:
+        v = self.csr_view()
+        self.ctx.call("xc_cov_exact_sweep_csr", dev.ptr(v.data), v.code, dev.ptr(v.indices), dev.ptr(v.indptr), self.n,
+                      self.m, dev.ptr(order_dev), int(order_dev.numel()), self.k, C.c_double(self.alpha), int(greedy),
+                      dev.ptr(self.pred), dev.ptr(self.Ef), self._s())
+
+    def sweep_batched(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int] = None) -> None:
+        """one block-Jacobi sweep: a single process issues it through ONE C call; sharded rows all-reduce the
+        batch factors (product) between the batch kernel and the fold"""
+        d, k, n_loc = self.data, self.k, int(order_dev.numel())
+        al = C.c_double(self.alpha)
+        if self.comm.world == 1:
+            if self.is_csr:
+                self.ctx.call("xc_cov_sweep_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr), self.m,
+                              dev.ptr(order_dev), n_loc, int(batch), k, al, dev.ptr(self.Ef), dev.ptr(self.pred),
+                              dev.ptr(self.dEf), self._s())
+            else:
+                self.ctx.call("xc_cov_sweep_dense", dev.ptr(d.t), d.code, d.m, d.ld, dev.ptr(order_dev), n_loc,
+                              int(batch), k, al, dev.ptr(self.Ef), dev.ptr(self.pred), dev.ptr(self.dEf), self._s())
+            return
+        nb = n_batches if n_batches is not None else (n_loc + batch - 1) // batch
+        for b in range(nb):
+            lo = min(b * batch, n_loc)
+            hi = min(lo + batch, n_loc)
+            if hi > lo:
+                rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
+                if self.is_csr:
+                    self.ctx.call("xc_cov_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
+                                  rows, hi - lo, k, al, dev.ptr(self.Ef), dev.ptr(self.pred), dev.ptr(self.dEf), self._s())
+                else:
+                    self.ctx.call("xc_cov_batch_dense", dev.ptr(d.t), d.code, d.m, d.ld, rows, hi - lo, k, al,
+                                  dev.ptr(self.Ef), dev.ptr(self.pred), dev.ptr(self.dEf), self._s())
+            self.comm.allreduce_prod_(self.dEf)
+            self.ctx.call("xc_cov_fold", dev.ptr(self.Ef), dev.ptr(self.dEf), self.m, self._s())
+
+
+def coverage_batch_rows(n: int) -> int:
+    """rows one rank commits together in the batched coverage sweep: coverage couples the rows of a batch much
+    more strongly than the F-measures (every row of a batch rushes to the same uncovered label): n/32 keeps the
+    block-Jacobi fixed point within 1e-4 of the sequential one, n/8 does not (measured, tests/test_gpu_parity.py)"""
+    return max(1, min(4096, n // 32))
+
+
 def predict_optimizing_coverage_using_bc(
     y_proba: Matrix,
     k: int,
@@ -690,9 +812,11 @@ def predict_optimizing_coverage_using_bc(
 ) -> Union[Matrix, Tuple[Matrix, Dict[str, Any]]]:
     """Block coordinate ascent for coverage@k (optionally mixed with precision@k through alpha).
     State: Ef[j] = prod_i (1 - yhat_ij * eta_ij), the probability that label j is never covered.
-    Same arguments as the reference; ``mode`` / ``batch_size`` / ``y_pred_format`` as above."""
+    Same arguments as the reference (block_coordinate.py:600-701); ``mode`` / ``batch_size`` /
+    ``distributed`` / ``y_pred_format`` as in :func:`predict_using_bc_with_0approx`."""
     mode = kwargs.pop("mode", None)
     batch_size = kwargs.pop("batch_size", None)
+    distributed = kwargs.pop("distributed", False)
     y_pred_format = kwargs.pop("y_pred_format", "same")
     log_info(f"Starting optimization of ETU coverage@{k} metric using block coordinate ascent algorithm ...", verbose)
     if not isinstance(k, int) or k <= 0:
@@ -707,78 +831,66 @@ def predict_optimizing_coverage_using_bc(
     greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
     mode = _resolve_mode(mode, n, greedy)
     device = dev.pick_device(y_proba)
-    ctx = dev.ctx_for(device)
+    comm = make_comm(distributed, device)
+    if mode == "exact" and comm.world > 1:
+        raise NotImplementedError("sequential-exact coverage BCA does not shard (replicas only); use mode='batched'")
     is_csr = isinstance(y_proba, csr_matrix)
     data = dev.csr_to_device(y_proba, device) if is_csr else dev.dense_to_device(y_proba, device)
-    csr_view = data if is_csr else _dense_as_csr(data)
-    pred = _initial_pred(y_proba, data, init_y_pred if not greedy else "random", k, seed, device)
-    Ef = torch.empty(m, dtype=torch.float64, device=device)
-    sp = lambda: dev.stream_ptr(device)
-
-    def state(order):
-        ctx.call("xc_cov_state_csr", dev.ptr(csr_view.data), csr_view.code, dev.ptr(csr_view.indices),
-                 dev.ptr(csr_view.indptr), n, m, dev.ptr(pred), k, order, dev.ptr(Ef), sp())
-
-    def utility() -> float:
-        cov = 1 - float(Ef.cpu().numpy().mean())       # :592 (numpy pairwise mean, like the reference)
-        if alpha < 1:                                   # :593-595
-            tp = torch.zeros(m, dtype=torch.float64, device=device)
-            fp, fn = torch.zeros_like(tp), torch.zeros_like(tp)
-            ctx.call("xc_confmat_csr_compact", dev.ptr(csr_view.data), dev.ptr(csr_view.indices),
-                     dev.ptr(csr_view.indptr), csr_view.code, dev.ptr(pred), k, n, m, XC_SUM_FAST, dev.ptr(tp),
-                     dev.ptr(fp), dev.ptr(fn), sp())
-            cov = alpha * cov + (1 - alpha) * float((tp / n / k).sum())
-        return cov
-
+    sess = CoverageSession(data, k, alpha, comm)
+    sess.pred = _initial_pred(y_proba, data, init_y_pred if not greedy else "random", k, seed, device)
     meta["mode"] = mode
-    rng = np.random.default_rng(seed)
-    order = np.arange(n)
-    sum_order = XC_SUM_ORDERED if mode == "exact" else XC_SUM_FAST
-    # coverage couples the rows of a batch much more strongly than the F-measures (every row of a
-    # batch rushes to the same uncovered label): n/32 keeps the block-Jacobi fixed point within
-    # 1e-4 of the sequential one, n/8 does not (measured, tests/test_gpu_parity.py)
-    batch = int(batch_size) if batch_size else max(1, min(4096, n // 32))
-    dEf = torch.ones(m, dtype=torch.float64, device=device)
-    new_cov = None
-    for j in range(1, max_iters + 1):
-        log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
-        if shuffle_order:
-            rng.shuffle(order)
-        if greedy:
-            Ef.fill_(1.0)
-            old_cov = utility()
-        elif new_cov is None:
-            state(sum_order)
-            old_cov = utility()
-        else:
-            old_cov = new_cov
-        order_dev = torch.from_numpy(order.astype(np.int32)).to(device)
-        if mode == "exact":
-            ctx.call("xc_cov_exact_sweep_csr", dev.ptr(csr_view.data), csr_view.code, dev.ptr(csr_view.indices),
-                     dev.ptr(csr_view.indptr), n, m, dev.ptr(order_dev), n, k, C.c_double(float(alpha)), int(greedy),
-                     dev.ptr(pred), dev.ptr(Ef), sp())
-        else:
-            for lo in range(0, n, batch):
-                hi = min(n, lo + batch)
-                rows = C.c_void_p(order_dev.data_ptr() + 4 * lo)
-                if is_csr:
-                    ctx.call("xc_cov_batch_csr", dev.ptr(data.data), data.code, dev.ptr(data.indices),
-                             dev.ptr(data.indptr), rows, hi - lo, k, C.c_double(float(alpha)), dev.ptr(Ef),
-                             dev.ptr(pred), dev.ptr(dEf), sp())
-                else:
-                    ctx.call("xc_cov_batch_dense", dev.ptr(data.t), data.code, m, data.ld, rows, hi - lo, k,
-                             C.c_double(float(alpha)), dev.ptr(Ef), dev.ptr(pred), dev.ptr(dEf), sp())
-                ctx.call("xc_cov_fold", dev.ptr(Ef), dev.ptr(dEf), m, sp())
-        state(sum_order)
-        new_cov = utility()
-        greedy = False
-        meta["iters"] = j
-        meta["utilities"].append(new_cov)
-        log_info(f"    Iteration {j}/{max_iters} finished, expected coverage: {old_cov} -> {new_cov}", verbose)
-        if new_cov <= old_cov + tolerance:              # :690
-            log_info(f"  Stopping because improvement of expected coverage is smaller than {tolerance}", verbose)
-            break
-    y_pred = _finish_pred(y_proba, pred, m, y_pred_format)
+    if mode == "exact":
+        rng = np.random.default_rng(seed)
+        order = np.arange(n)
+        new_cov = None
+        for j in range(1, max_iters + 1):
+            log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+            if shuffle_order:
+                rng.shuffle(order)
+            if greedy:
+                sess.Ef.fill_(1.0)
+                old_cov = sess.utility_host()
+            elif new_cov is None:
+                sess.state(XC_SUM_ORDERED)
+                old_cov = sess.utility_host()
+            else:
+                old_cov = new_cov
+            order_dev = torch.from_numpy(order.astype(np.int32)).to(device)
+            sess.sweep_exact(order_dev, greedy)
+            sess.state(XC_SUM_ORDERED)
+            new_cov = sess.utility_host()
+            greedy = False
+            meta["iters"] = j
+            meta["utilities"].append(new_cov)
+            log_info(f"    Iteration {j}/{max_iters} finished, expected coverage: {old_cov} -> {new_cov}", verbose)
+            if new_cov <= old_cov + tolerance:              # :690
+                log_info(f"  Stopping because improvement of expected coverage is smaller than {tolerance}", verbose)
+                break
+    else:
+        batch = int(batch_size) if batch_size else coverage_batch_rows(n)
+        n_batches = comm.max_int((n + batch - 1) // batch)
+        base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
+        order_dev = torch.arange(n, dtype=torch.int32, device=device)
+        sess.state(XC_SUM_FAST)
+        sess.utility_device(0)
+        meta["batch_size"] = batch
+        for j in range(1, max_iters + 1):
+            log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+            if shuffle_order:
+                sess.ctx.call("xc_permutation", n, C.c_uint64((base_seed + 0x632BE59BD9B4E019 * j) & (2**64 - 1)),
+                              dev.ptr(order_dev), sess._s())
+            sess.sweep_batched(order_dev, batch, n_batches)
+            sess.state(XC_SUM_FAST)                         # :676 (the products are recomputed, like the reference)
+            sess.utility_device(1)
+            old_cov, new_cov = (float(v) for v in sess.util_buf[:2].cpu())
+            sess.util_buf[0] = sess.util_buf[1]
+            meta["iters"] = j
+            meta["utilities"].append(new_cov)
+            log_info(f"    Iteration {j}/{max_iters} finished, expected coverage: {old_cov} -> {new_cov}", verbose)
+            if new_cov <= old_cov + tolerance:              # :690
+                log_info(f"  Stopping because improvement of expected coverage is smaller than {tolerance}", verbose)
+                break
+    y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format)
     if return_meta:
         meta["time"] = time() - meta["time"]
         return y_pred, meta
@@ -786,8 +898,9 @@ def predict_optimizing_coverage_using_bc(
 
 
 def _dense_as_csr(d: dev.DenseDev) -> dev.CsrDev:
-    """Dense rows seen as CSR rows that store every non-zero label (what csr_matrix(dense) holds);
-    used only by the coverage state/sequential kernels, which are defined on stored entries."""
+    """Dense rows seen as CSR rows that store every non-zero label (what csr_matrix(dense) holds); used only by
+    the SEQUENTIAL coverage kernels (small inputs), which are defined on stored entries.  The batched mode works
+    on the dense rows directly (xc_cov_batch_dense / xc_cov_state_dense)."""
     x = d.t[:, :d.m]
     nz = x != 0
     counts = nz.sum(1)

@@ -1,4 +1,5 @@
 // Context management and error reporting of the C ABI (include/xcolumns_b200.h).
+#include <cstdlib>
 #include <new>
 
 #include "xc_common.cuh"
@@ -41,7 +42,13 @@ extern "C" int xc_ctx_create(int device, xc_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->red_partials = nullptr;
     ctx->red_counter = nullptr;
-    cudaSetDevice(device);
+    ctx->aux_ready = false;
+    ctx->timing_on = false;
+    ctx->timing_count = ctx->timing_cap = 0;
+    ctx->timing_ev = nullptr;
+    ctx->timing_rows = nullptr;
+    ctx->stage[0] = ctx->stage[1] = nullptr;
+    XcDeviceGuard guard(ctx);   // allocate on `device`, leave the caller's current device untouched
     if (cudaMalloc(&ctx->red_partials, sizeof(double) * XC_RED_MAX_BLOCKS) != cudaSuccess ||
         cudaMalloc(&ctx->red_counter, 64) != cudaSuccess || cudaMemset(ctx->red_counter, 0, 64) != cudaSuccess) {
         delete ctx;
@@ -54,10 +61,95 @@ extern "C" int xc_ctx_create(int device, xc_ctx **out)
 extern "C" void xc_ctx_destroy(xc_ctx *ctx)
 {
     if (!ctx) return;
+    XcDeviceGuard guard(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->red_partials) cudaFree(ctx->red_partials);
     if (ctx->red_counter) cudaFree(ctx->red_counter);
+    if (ctx->aux_ready) {
+        for (int i = 0; i < 2; ++i) {
+            cudaStreamDestroy(ctx->aux[i]);
+            cudaEventDestroy(ctx->ev_commit[i]);
+            cudaEventDestroy(ctx->ev_join[i]);
+        }
+        cudaEventDestroy(ctx->ev_fork);
+    }
+    for (int i = 0; i < 2 * ctx->timing_cap; ++i) cudaEventDestroy(ctx->timing_ev[i]);
+    free(ctx->timing_ev);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->stage[i]) {
+            cudaFreeHost(ctx->stage[i]);
+            cudaEventDestroy(ctx->stage_ev[i]);
+        }
+    free(ctx->timing_rows);
     delete ctx;
+}
+
+// ---- per-launch timing of the streaming batch kernels (bench.py's roofline leg) --------------------------
+// While enabled, the batched-sweep entry points bracket every batch kernel with CUDA events on the stream it
+// is launched on.  xc_timing_read synchronises the device and returns, per launch, start / end in ms relative
+// to the first recorded event plus the rows it processed.
+extern "C" int xc_timing_enable(xc_ctx *ctx, int on)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx) return XC_ERR_INVALID;
+    ctx->timing_on = on != 0;
+    ctx->timing_count = 0;
+    return XC_OK;
+}
+
+int xc_timing_slot(xc_ctx *ctx, int64_t rows, cudaEvent_t *start, cudaEvent_t *end)
+{
+    if (ctx->timing_count == ctx->timing_cap) {
+        const int cap = ctx->timing_cap ? 2 * ctx->timing_cap : 256;
+        cudaEvent_t *ev = static_cast<cudaEvent_t *>(realloc(ctx->timing_ev, sizeof(cudaEvent_t) * 2 * cap));
+        if (!ev) return XC_ERR_NOMEM;
+        ctx->timing_ev = ev;
+        int64_t *rw = static_cast<int64_t *>(realloc(ctx->timing_rows, sizeof(int64_t) * cap));
+        if (!rw) return XC_ERR_NOMEM;
+        ctx->timing_rows = rw;
+        for (int i = 2 * ctx->timing_cap; i < 2 * cap; ++i) XC_CUDA_TRY(ctx, cudaEventCreate(&ctx->timing_ev[i]));
+        ctx->timing_cap = cap;
+    }
+    const int i = ctx->timing_count++;
+    ctx->timing_rows[i] = rows;
+    *start = ctx->timing_ev[2 * i];
+    *end = ctx->timing_ev[2 * i + 1];
+    return XC_OK;
+}
+
+extern "C" int xc_timing_read(xc_ctx *ctx, int cap, double *start_ms_host, double *end_ms_host, int64_t *rows_host,
+                              int *count_host)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !count_host || cap < 0) return XC_ERR_INVALID;
+    XC_CUDA_TRY(ctx, cudaDeviceSynchronize());
+    const int n = ctx->timing_count < cap ? ctx->timing_count : cap;
+    for (int i = 0; i < n; ++i) {
+        float a = 0.f, b = 0.f;
+        XC_CUDA_TRY(ctx, cudaEventElapsedTime(&a, ctx->timing_ev[0], ctx->timing_ev[2 * i]));
+        XC_CUDA_TRY(ctx, cudaEventElapsedTime(&b, ctx->timing_ev[0], ctx->timing_ev[2 * i + 1]));
+        if (start_ms_host) start_ms_host[i] = a;
+        if (end_ms_host) end_ms_host[i] = b;
+        if (rows_host) rows_host[i] = ctx->timing_rows[i];
+    }
+    *count_host = ctx->timing_count;
+    ctx->timing_count = 0;
+    return XC_OK;
+}
+
+int xc_ctx_aux_streams(xc_ctx *ctx)
+{
+    if (ctx->aux_ready) return XC_OK;
+    int lo = 0, hi = 0;
+    XC_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int i = 0; i < 2; ++i) {
+        XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, hi));
+        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_commit[i], cudaEventDisableTiming));
+        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    ctx->aux_ready = true;
+    return XC_OK;
 }
 
 extern "C" const char *xc_last_cuda_error(xc_ctx *ctx)
@@ -117,6 +209,7 @@ __global__ void __launch_bounds__(256) permutation_kernel(int64_t n, uint64_t se
 
 extern "C" int xc_permutation(xc_ctx *ctx, int64_t n, uint64_t seed, int32_t *out, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !out || n < 0 || n > 0x7fffffffLL) return XC_ERR_INVALID;
     if (n == 0) return XC_OK;
     int bits = 2;

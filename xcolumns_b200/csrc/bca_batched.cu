@@ -109,50 +109,87 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-__global__ void __launch_bounds__(kThreads)
-bca_commit_p2p_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_t *const *windows, int world,
-                      int rank, unsigned epoch, int buf, int64_t m, int64_t delta_off, int64_t delta_stride,
-                      float2 *coef_n, float2 *coef_s)
+// One commit = fold the deltas of one batch into the float64 state, refresh the gain coefficients (or the
+// Jaccard / G-mean / H-mean records) and clear the delta buffer a later batch will accumulate into.
+//   windows == nullptr : single process, the deltas are this GPU's own buffer `cur`
+//   windows != nullptr : peer-memory exchange as described above (flags + P2P reads in rank order)
+//   cur < 0            : no fold -- coefficients of the current state only (start of a sweep)
+// 64 threads and <= 64 registers per CTA: 4096 registers, which is what six resident CTAs of the streaming
+// batch kernel (6 x 256 x 40) leave free on an SM, so a commit never has to wait for a streaming CTA to
+// retire when the next batch is already running (pipelined sweep, see xc_bca_sweep_dense_pipe).
+constexpr int kCommitThreads = 64;
+
+template <int WMAX>
+__global__ void __launch_bounds__(kCommitThreads)
+bca_commit_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_t *const *windows, int world, int rank,
+                  unsigned epoch, double *local, int64_t win_off, int64_t stride, int cur, int clr, int64_t m,
+                  float2 *coef_n, float2 *coef_s, float2 *coef_n2, float2 *coef_s2, int rec)
 {
     __shared__ int s_fail;
-    uint8_t *mine = windows[rank];
-    if (threadIdx.x == 0) s_fail = 0;
-    if (blockIdx.x == 0 && threadIdx.x < world) {
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned *>(windows[threadIdx.x]) + rank, epoch);
-    }
-    __syncthreads();
-    if (threadIdx.x < world) {
-        const unsigned *flag = reinterpret_cast<const unsigned *>(mine) + threadIdx.x;
-        const unsigned long long t0 = global_timer_ns();
-        // flags only grow; a peer may already be one commit ahead (wrap-safe signed distance)
-        while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-            if (global_timer_ns() - t0 > 4000000000ULL) {
-                s_fail = 1;
-                reinterpret_cast<unsigned *>(mine)[XC_P2P_ERR_WORD] = epoch;
-                break;
+    if (windows && cur >= 0) {
+        uint8_t *mine = windows[rank];
+        if (threadIdx.x == 0) s_fail = 0;
+        if (blockIdx.x == 0 && threadIdx.x < world) {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<unsigned *>(windows[threadIdx.x]) + rank, epoch);
+        }
+        __syncthreads();
+        if (threadIdx.x < world) {
+            const unsigned *flag = reinterpret_cast<const unsigned *>(mine) + threadIdx.x;
+            const unsigned long long t0 = global_timer_ns();
+            // flags only grow; a peer may already be ahead (wrap-safe signed distance)
+            while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+                if (global_timer_ns() - t0 > 4000000000ULL) {
+                    s_fail = 1;
+                    reinterpret_cast<unsigned *>(mine)[XC_P2P_ERR_WORD] = epoch;
+                    break;
+                }
             }
         }
+        __syncthreads();
+        if (s_fail) return;
     }
-    __syncthreads();
-    if (s_fail) return;
-    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (j >= m) return;
-    double dt = 0.0, df = 0.0, dg = 0.0;
-    for (int r = 0; r < world; ++r) {  // rank order on every rank: bit-identical sums
-        const double *d = reinterpret_cast<const double *>(windows[r] + delta_off + (int64_t)buf * delta_stride);
-        dt += __ldcv(d + j);
-        df += __ldcv(d + m + j);
-        dg += __ldcv(d + 2 * m + j);
+    for (int64_t j = (int64_t)blockIdx.x * kCommitThreads + threadIdx.x; j < m; j += (int64_t)gridDim.x * kCommitThreads) {
+        double t = tp[j], f = fp[j], g = fn[j];
+        if (cur >= 0) {
+            double d[3];
+            if (windows) {
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    double x[WMAX];   // all peers' values in flight, then added in rank order (bit-identical on every rank)
+#pragma unroll
+                    for (int r = 0; r < WMAX; ++r) {
+                        x[r] = 0.0;
+                        if (r < world)
+                            x[r] = __ldcv(reinterpret_cast<const double *>(windows[r] + win_off + (int64_t)cur * stride) +
+                                          v * m + j);
+                    }
+                    double acc = 0.0;
+#pragma unroll
+                    for (int r = 0; r < WMAX; ++r) acc += x[r];   // x[r] = 0 beyond world: exact
+                    d[v] = acc;
+                }
+            } else {
+                const double *dl = reinterpret_cast<const double *>(reinterpret_cast<const uint8_t *>(local) +
+                                                                    (int64_t)cur * stride);
+                d[0] = dl[j]; d[1] = dl[m + j]; d[2] = dl[2 * m + j];
+            }
+            t += d[0]; f += d[1]; g += d[2];
+            tp[j] = t; fp[j] = f; fn[j] = g;
+        }
+        if (clr >= 0) {
+            double *nxt = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(local) + (int64_t)clr * stride);
+            nxt[j] = 0.0; nxt[m + j] = 0.0; nxt[2 * m + j] = 0.0;
+        }
+        if (rec) {
+            reinterpret_cast<float4 *>(coef_n)[j] = bca_rec_of(p, t, f, g);   // coef_n is the 16-byte record array here
+        } else {
+            float2 cn, cs;
+            bca_coef_of(p, t, f, g, &cn, &cs);
+            coef_n[j] = cn; coef_s[j] = cs;
+            if (coef_n2) { coef_n2[j] = cn; coef_s2[j] = cs; }
+        }
     }
-    const double t = tp[j] + dt, f = fp[j] + df, g = fn[j] + dg;
-    tp[j] = t; fp[j] = f; fn[j] = g;
-    double *nxt = reinterpret_cast<double *>(mine + delta_off + (int64_t)(buf ^ 1) * delta_stride);
-    nxt[j] = 0.0; nxt[m + j] = 0.0; nxt[2 * m + j] = 0.0;
-    if (p.metric == XC_METRIC_JACCARD || p.metric == XC_METRIC_GMEAN || p.metric == XC_METRIC_HMEAN)
-        reinterpret_cast<float4 *>(coef_n)[j] = bca_rec_of(p, t, f, g);   // coef_n is the 16-byte record array here
-    else
-        bca_coef_of(p, t, f, g, coef_n + j, coef_s + j);
 }
 
 // ---- shared epilogue: compare new selection with the old one, emit deltas, store the row ----------
@@ -1004,6 +1041,7 @@ extern "C" int64_t xc_bca_coef_len(int64_t m) { return ((m + TMA_TC - 1) / TMA_T
 
 extern "C" int xc_bca_wave_rows(xc_ctx *ctx, int dtype, int64_t m)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
     if (dtype == XC_F32 && dense_path_override() == 2) return ctx->sm_count * TMA_ROWS;
@@ -1020,6 +1058,7 @@ extern "C" int xc_bca_wave_rows(xc_ctx *ctx, int dtype, int64_t m)
 extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn, double *dtp,
                            double *dfp, double *dfn, int64_t m, float *coef_n, float *coef_s, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !tp || !fp || !fn || !coef_n || !coef_s || m <= 0) return XC_ERR_INVALID;
     if ((dtp || dfp || dfn) && !(dtp && dfp && dfn)) return XC_ERR_INVALID;
     if (p->metric != XC_METRIC_PRECISION && p->metric != XC_METRIC_RECALL && p->metric != XC_METRIC_FBETA &&
@@ -1034,6 +1073,7 @@ extern "C" int xc_bca_coef(xc_ctx *ctx, const xc_metric_params *p, double *tp, d
 extern "C" int xc_bca_rec(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn, double *dtp,
                           double *dfp, double *dfn, int64_t m, float *rec, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !tp || !fp || !fn || !rec || m <= 0) return XC_ERR_INVALID;
     if ((dtp || dfp || dfn) && !(dtp && dfp && dfn)) return XC_ERR_INVALID;
     if (p->metric != XC_METRIC_JACCARD && p->metric != XC_METRIC_GMEAN && p->metric != XC_METRIC_HMEAN)
@@ -1050,6 +1090,7 @@ extern "C" int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, co
                                       const double *tp, const double *fp, const double *fn, int32_t *pred_idx,
                                       double *dtp, double *dfp, double *dfn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !eta || !rec || !tp || !fp || !fn || !pred_idx || !dtp || !dfp || !dfn || m <= 0 || ld < m ||
         n_rows < 0)
         return XC_ERR_INVALID;
@@ -1085,27 +1126,11 @@ extern "C" int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, co
 
 extern "C" int64_t xc_bca_delta_stride(int64_t m) { return ((3 * m * 8 + 255) / 256) * 256; }
 
-extern "C" int xc_bca_commit_p2p(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, double *tp, double *fp,
-                                 double *fn, int64_t m, int buf, float *coef_n, float *coef_s, void *stream)
-{
-    if (!ctx || !w || !w->opened || !p || !tp || !fp || !fn || !coef_n || m <= 0 || (buf & ~1)) return XC_ERR_INVALID;
-    const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
-    if (!rec && !coef_s) return XC_ERR_INVALID;
-    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
-    const int64_t stride = xc_bca_delta_stride(m);
-    if ((size_t)(XC_P2P_HEADER + 2 * stride) > w->bytes) return XC_ERR_INVALID;
-    w->epoch += 1;
-    bca_commit_p2p_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        *p, tp, fp, fn, w->windows_dev, w->world, w->rank, w->epoch, buf, m, XC_P2P_HEADER, stride, (float2 *)coef_n,
-        (float2 *)coef_s);
-    XC_LAUNCHED(ctx);
-    return XC_OK;
-}
-
 extern "C" int xc_bca_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld, const int32_t *rows,
                                   int64_t n_rows, int k, const float *coef_n, const float *coef_s, int32_t *pred_idx,
                                   double *dtp, double *dfp, double *dfn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !coef_n || !coef_s || !pred_idx || !dtp || !dfp || !dfn || m <= 0 || ld < m || n_rows < 0)
         return XC_ERR_INVALID;
     if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
@@ -1140,6 +1165,7 @@ extern "C" int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const 
                                 const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
                                 double *dfn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !coef_n || !coef_s || !pred_idx || !dtp || !dfp || !dfn || n_rows < 0) return XC_ERR_INVALID;
     if (k < 1 || k > 32) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
@@ -1158,6 +1184,7 @@ extern "C" int xc_bca_batch_csr_rec(xc_ctx *ctx, const xc_metric_params *p, cons
                                     int k, const float *rec, const double *tp, const double *fp, const double *fn,
                                     int32_t *pred_idx, double *dtp, double *dfp, double *dfn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !indptr || !rec || !tp || !fp || !fn || !pred_idx || !dtp || !dfp || !dfn || n_rows < 0)
         return XC_ERR_INVALID;
     if (k < 1 || k > 32) return XC_ERR_INVALID;
@@ -1186,6 +1213,7 @@ extern "C" int xc_cov_batch_csr(xc_ctx *ctx, const void *data, int dtype, const 
                                 const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k, double alpha,
                                 const double *Ef, int32_t *pred_idx, double *dEf, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !Ef || !pred_idx || !dEf || n_rows < 0) return XC_ERR_INVALID;
     if (k < 1 || k > 32) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
@@ -1209,6 +1237,7 @@ extern "C" int xc_cov_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64
                                   int64_t n_rows, int k, double alpha, const double *Ef, int32_t *pred_idx,
                                   double *dEf, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !Ef || !pred_idx || !dEf || m <= 0 || ld < m || n_rows < 0) return XC_ERR_INVALID;
     if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
@@ -1232,6 +1261,7 @@ extern "C" int xc_cov_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64
 
 extern "C" int xc_cov_fold(xc_ctx *ctx, double *Ef, double *dEf, int64_t m, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !Ef || !dEf || m <= 0) return XC_ERR_INVALID;
     cov_fold_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(Ef, dEf, m);
     XC_LAUNCHED(ctx);
@@ -1248,6 +1278,7 @@ extern "C" int xc_bca_sweep_dense(xc_ctx *ctx, const xc_metric_params *p, const 
                                   float *coef_s, int32_t *pred_idx, double *tp, double *fp, double *fn, double *dtp,
                                   double *dfp, double *dfn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !order || n_order < 0 || batch < 1) return XC_ERR_INVALID;
     const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
     for (int64_t lo = 0; lo <= n_order; lo += batch) {   // the last trip (lo >= n_order or empty) only folds
@@ -1275,6 +1306,7 @@ extern "C" int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const vo
                                 int64_t n_order, int64_t batch, int k, float *coef_n, float *coef_s, int32_t *pred_idx,
                                 double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !order || n_order < 0 || batch < 1) return XC_ERR_INVALID;
     const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
     auto fold = [&]() {   // coef_n is the record array for the record metrics
@@ -1292,6 +1324,246 @@ extern "C" int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const vo
                                     dfp, dfn, stream);
         if (rc) return rc;
         if (hi == n_order) return fold();
+    }
+    return XC_OK;
+}
+
+// ---- pipelined sweep: batches overlap, commits are applied `lag` batches late ----------------------------------
+// The strict block-Jacobi order  K_0, commit_0, K_1, commit_1, ...  leaves the GPU under-filled at every batch
+// boundary: the tail of the batch kernel, the commit (a cross-GPU barrier when the rows are sharded), the ramp of
+// the next kernel -- and a batch smaller than one wave of resident warps (strong scaling: 38 k rows per GPU cut
+// into 8 commits = 0.68 wave) cannot saturate HBM by itself.  With lag = 1 batch b is evaluated against the state
+// after commit b-2: K_b and K_{b+1} have no dependency on each other, so they run on two streams, and the chain
+//     K_b -> commit_b -> K_{b+2}                      (stream b & 1)
+//     commit_{b-1} -> commit_b                        (event: the state is folded in batch order)
+// keeps two batch kernels in flight; the commit of one overlaps the streaming of the other (the commit kernel is
+// sized to fit next to six resident streaming CTAs).  Staleness grows from "up to one batch" to "one to two
+// batches"; measured against the sequential reference this moves the final macro-F1 by < 1e-6 (scripts/
+// probe_lag.py, tests/test_gpu_parity.py).  lag = 0 is the strict order on the caller's stream.
+//
+// Delta buffers: batch g (global index, continues over sweeps) accumulates into buffer g % NB, NB = 2 (lag + 1);
+// commit_g folds buffer g % NB and clears buffer (g + lag + 1) % NB, the one batch g + lag + 1 will use -- with
+// sharded rows that buffer was last read by the peers during commit g - lag - 1, which every peer has left before
+// it raised its flag for commit g.  No host-side clearing, no race with a slower peer.
+namespace {
+
+struct PipeCommit {
+    xc_ctx *ctx;
+    xc_p2p *w;
+    const xc_metric_params *p;
+    double *tp, *fp, *fn;
+    double *local;
+    int64_t win_off, stride, m;
+    int rec;
+};
+
+int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *set_b, int64_t clen, cudaStream_t st)
+{
+    const int64_t want = (c.m + kCommitThreads - 1) / kCommitThreads;
+    const int grid = (int)(want < c.ctx->sm_count ? want : c.ctx->sm_count);
+    float2 *an = (float2 *)set_a, *as = c.rec ? nullptr : (float2 *)(set_a + 2 * clen);
+    float2 *bn = set_b ? (float2 *)set_b : nullptr, *bs = set_b ? (float2 *)(set_b + 2 * clen) : nullptr;
+    uint8_t *const *windows = c.w ? c.w->windows_dev : nullptr;
+    const int world = c.w ? c.w->world : 1, rank = c.w ? c.w->rank : 0;
+    unsigned epoch = 0;
+    if (c.w && cur >= 0) epoch = ++c.w->epoch;
+#define XC_GO(WMAX)                                                                                                   \
+    bca_commit_kernel<WMAX><<<grid, kCommitThreads, 0, st>>>(*c.p, c.tp, c.fp, c.fn, windows, world, rank, epoch,       \
+                                                             c.local, c.win_off, c.stride, cur, clr, c.m, an, as, bn, \
+                                                             bs, c.rec)
+    if (world <= 2) XC_GO(2);
+    else if (world <= 4) XC_GO(4);
+    else if (world <= 8) XC_GO(8);
+    else XC_GO(16);
+#undef XC_GO
+    XC_LAUNCHED(c.ctx);
+    return XC_OK;
+}
+
+}  // namespace
+
+extern "C" int xc_bca_pipe_buffers(int lag) { return 2 * ((lag > 0 ? 1 : 0) + 1); }
+
+extern "C" int xc_bca_sweep_dense_pipe(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, const void *eta, int dtype,
+                                       int64_t m, int64_t ld, const int32_t *order, int64_t n_order, int64_t batch,
+                                       int64_t n_batches, int lag, int64_t batch0, int k, float *coef,
+                                       int32_t *pred_idx, double *tp, double *fp, double *fn, double *delta,
+                                       void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !p || !eta || !coef || !pred_idx || !tp || !fp || !fn || n_order < 0 || batch < 1 || n_batches < 0 ||
+        batch0 < 0 || m <= 0 || ld < m)
+        return XC_ERR_INVALID;
+    if (n_order > 0 && !order) return XC_ERR_INVALID;
+    if (!w && !delta) return XC_ERR_INVALID;
+    if (w && !w->opened) return XC_ERR_INVALID;
+    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
+    const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
+    if (rec && p->metric != XC_METRIC_JACCARD && p->skip_tn) return XC_ERR_INVALID;
+    if (rec) lag = 0;   // the record kernels read the float64 state of the selected labels: no overlap with a commit
+    const int S = (lag > 0 ? 1 : 0) + 1, NB = 2 * S;
+    const int64_t stride = xc_bca_delta_stride(m), clen = xc_bca_coef_len(m);
+    if (w && (size_t)(XC_P2P_HEADER + NB * stride) > w->bytes) return XC_ERR_INVALID;
+    if (n_batches * batch < n_order) return XC_ERR_INVALID;
+    cudaStream_t caller = (cudaStream_t)stream;
+    double *local = w ? reinterpret_cast<double *>(w->windows[w->rank] + XC_P2P_HEADER) : delta;
+    PipeCommit c{ctx, w, p, tp, fp, fn, local, (int64_t)XC_P2P_HEADER, stride, m, rec ? 1 : 0};
+    float *set[2] = {coef, coef + 4 * clen};
+    // coefficients of the state the sweep starts from, for every set
+    int rc = launch_commit(c, -1, -1, set[0], S > 1 ? set[1] : nullptr, clen, caller);
+    if (rc) return rc;
+    cudaStream_t st[2] = {caller, caller};
+    // $XCOLUMNS_B200_PIPE_SERIAL=1 (tests): the same dependency order on ONE stream, nothing overlaps
+    const bool serial = getenv("XCOLUMNS_B200_PIPE_SERIAL") && atoi(getenv("XCOLUMNS_B200_PIPE_SERIAL")) == 1;
+    const bool forked = S > 1 && !serial;
+    if (forked) {
+        rc = xc_ctx_aux_streams(ctx);
+        if (rc) return rc;
+        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, caller));
+        for (int i = 0; i < 2; ++i) {
+            st[i] = ctx->aux[i];
+            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_fork, 0));
+        }
+    }
+    for (int64_t b = 0; b < n_batches; ++b) {
+        const int64_t g = batch0 + b;
+        const int si = (int)(b % S);
+        const int cur = (int)(g % NB), clr = (int)((g + S) % NB);
+        const int64_t lo = b * batch < n_order ? b * batch : n_order;
+        const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
+        double *d = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(local) + (int64_t)cur * stride);
+        if (hi > lo) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (ctx->timing_on) {
+                rc = xc_timing_slot(ctx, hi - lo, &e0, &e1);
+                if (rc) return rc;
+                XC_CUDA_TRY(ctx, cudaEventRecord(e0, st[si]));
+            }
+            rc = rec ? xc_bca_batch_dense_rec(ctx, p, eta, dtype, m, ld, order + lo, hi - lo, k, set[si], tp, fp, fn,
+                                              pred_idx, d, d + m, d + 2 * m, st[si])
+                     : xc_bca_batch_dense(ctx, eta, dtype, m, ld, order + lo, hi - lo, k, set[si], set[si] + 2 * clen,
+                                          pred_idx, d, d + m, d + 2 * m, st[si]);
+            if (rc) return rc;
+            if (e1) XC_CUDA_TRY(ctx, cudaEventRecord(e1, st[si]));
+        }
+        if (forked && b > 0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[si], ctx->ev_commit[(b - 1) % S], 0));
+        rc = launch_commit(c, cur, clr, set[si], nullptr, clen, st[si]);
+        if (rc) return rc;
+        if (forked) XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_commit[si], st[si]));
+    }
+    if (forked) {
+        for (int i = 0; i < 2; ++i) {
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], st[i]));
+            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(caller, ctx->ev_join[i], 0));
+        }
+    }
+    return XC_OK;
+}
+
+// ---- coverage: whole sweeps, dense state, utility on the device ------------------------------------------------
+// ref: block_coordinate.py:600-701.  Ef_j = prod_i (1 - yhat_ij eta_ij); a batch accumulates multiplicative
+// factors into dEf (1 = unchanged) which the fold multiplies into Ef.  With the rows sharded over several ranks
+// the host shim all-reduces dEf (product) between the batch kernel and the fold, so these one-call sweeps are the
+// single-process form.
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cov_state_dense_kernel(const T *__restrict__ eta, int64_t ld, int64_t n, const int32_t *__restrict__ pred_idx, int k,
+                       double *Ef)
+{
+    const T one = (T)1;
+    const int64_t total = n * k;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+        const int pj = pred_idx[t];
+        if (pj < 0) continue;
+        const T e = eta[(t / k) * ld + pj];
+        if (e != (T)0) atomic_mul(Ef + pj, (double)(T)((double)one * (1.0 - (double)e)));   // zeros are not stored entries
+    }
+}
+
+__global__ void __launch_bounds__(256) cov_fill_kernel(double *x, double v, int64_t m)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j < m) x[j] = v;
+}
+
+// out[0] = 1 - mean(Ef)   (block_coordinate.py:592), deterministic block-ordered sum
+__global__ void __launch_bounds__(256)
+cov_utility_kernel(const double *__restrict__ Ef, int64_t m, double *out, double *partials, unsigned *counter)
+{
+    __shared__ double sm[8];
+    double s = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += (int64_t)gridDim.x * 256) s += Ef[j];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double bsum = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) bsum += sm[w];
+    double total;
+    if (xc_grid_sum_last(bsum, partials, counter, &total)) *out = 1.0 - total / (double)m;
+}
+
+}  // namespace
+
+extern "C" int xc_cov_state_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m, int64_t ld,
+                                  const int32_t *pred_idx, int k, double *Ef, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !eta || !pred_idx || !Ef || n <= 0 || m <= 0 || ld < m || k < 1 || k > 32) return XC_ERR_INVALID;
+    if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cov_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(Ef, 1.0, m);
+    XC_LAUNCHED(ctx);
+    const int64_t blocks = (n * k + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    if (dtype == XC_F32) cov_state_dense_kernel<float><<<grid, 256, 0, st>>>((const float *)eta, ld, n, pred_idx, k, Ef);
+    else cov_state_dense_kernel<double><<<grid, 256, 0, st>>>((const double *)eta, ld, n, pred_idx, k, Ef);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_cov_utility(xc_ctx *ctx, const double *Ef, int64_t m, double *out_dev, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !Ef || !out_dev || m <= 0) return XC_ERR_INVALID;
+    int64_t blocks = (m + 255) / 256;
+    const int grid = (int)(blocks < XC_RED_MAX_BLOCKS ? blocks : XC_RED_MAX_BLOCKS);
+    cov_utility_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Ef, m, out_dev, ctx->red_partials, ctx->red_counter);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
+}
+
+extern "C" int xc_cov_sweep_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices, const int64_t *indptr,
+                                int64_t m, const int32_t *order, int64_t n_order, int64_t batch, int k, double alpha,
+                                double *Ef, int32_t *pred_idx, double *dEf, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !order || n_order < 0 || batch < 1 || m <= 0) return XC_ERR_INVALID;
+    for (int64_t lo = 0; lo < n_order; lo += batch) {
+        const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
+        int rc = xc_cov_batch_csr(ctx, data, dtype, indices, indptr, order + lo, hi - lo, k, alpha, Ef, pred_idx, dEf, stream);
+        if (rc) return rc;
+        rc = xc_cov_fold(ctx, Ef, dEf, m, stream);
+        if (rc) return rc;
+    }
+    return XC_OK;
+}
+
+extern "C" int xc_cov_sweep_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld, const int32_t *order,
+                                  int64_t n_order, int64_t batch, int k, double alpha, double *Ef, int32_t *pred_idx,
+                                  double *dEf, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !order || n_order < 0 || batch < 1 || m <= 0) return XC_ERR_INVALID;
+    for (int64_t lo = 0; lo < n_order; lo += batch) {
+        const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
+        int rc = xc_cov_batch_dense(ctx, eta, dtype, m, ld, order + lo, hi - lo, k, alpha, Ef, pred_idx, dEf, stream);
+        if (rc) return rc;
+        rc = xc_cov_fold(ctx, Ef, dEf, m, stream);
+        if (rc) return rc;
     }
     return XC_OK;
 }

@@ -1116,6 +1116,7 @@ extern "C" int xc_bca_exact_sweep_dense(xc_ctx *ctx, const void *eta, int dtype,
                                         int greedy, int32_t *pred_idx, double *tp, double *fp, double *fn, double *tn,
                                         void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !order || !p || !pred_idx || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || ld < m || n_order < 0 || k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
@@ -1143,6 +1144,7 @@ extern "C" int xc_bca_online_dense(xc_ctx *ctx, const void *eta, int dtype, int6
                                    const void *y_true, int64_t ld_true, int k, const xc_metric_params *p,
                                    int32_t *pred_idx, double *tp, double *fp, double *fn, double *tn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !p || !pred_idx || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
     if (n_rows < 0 || m <= 0 || ld < m || k < 1 || k > 32 || k > m || (y_true && ld_true < m)) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
@@ -1160,6 +1162,7 @@ extern "C" int xc_bca_exact_sweep_dense_k0(xc_ctx *ctx, const void *eta, int dty
                                            int greedy, void *pred, int64_t ld_pred, double *tp, double *fp, double *fn,
                                            double *tn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !order || !p || !pred || !tp || !fp || !fn || !tn) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || ld < m || ld_pred < m || n_order < 0) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
@@ -1181,6 +1184,7 @@ extern "C" int xc_bca_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, 
                                       int64_t n_order, int k, const xc_metric_params *p, int greedy, int32_t *pred_idx,
                                       double *tp, double *fp, double *fn, double *tn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !order || !p || !pred_idx || !tp || !fp || !fn) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || n_order < 0 || k < 1 || k > 32) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
@@ -1226,6 +1230,7 @@ extern "C" int xc_cov_exact_sweep_csr(xc_ctx *ctx, const void *data, int dtype, 
                                       int64_t n_order, int k, double alpha, int greedy, int32_t *pred_idx, double *Ef,
                                       void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !order || !pred_idx || !Ef) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || n_order < 0 || k < 1 || k > 32) return XC_ERR_INVALID;
     if (n_order == 0) return XC_OK;
@@ -1244,6 +1249,7 @@ extern "C" int xc_cov_state_csr(xc_ctx *ctx, const void *data, int dtype, const 
                                 const int64_t *indptr, int64_t n, int64_t m, const int32_t *pred_idx, int k, int order,
                                 double *Ef, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !pred_idx || !Ef || n <= 0 || m <= 0 || k < 1 || k > 32) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;

@@ -447,6 +447,7 @@ extern "C" int xc_confmat_dense(xc_ctx *ctx, const void *y_true, int64_t ldt, co
                                 int dtype, int64_t n, int64_t m, int axis, int order, int acc_f32, double *tp,
                                 double *fp, double *fn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !y_true || !y_pred || !tp || !fp || !fn || n <= 0 || m <= 0 || ldt < m || ldp < m) return XC_ERR_INVALID;
     if (axis != 0 && axis != 1) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
@@ -492,6 +493,7 @@ extern "C" int xc_confmat_dense(xc_ctx *ctx, const void *y_true, int64_t ldt, co
 extern "C" int xc_colsum_dense(xc_ctx *ctx, const void *x, int dtype, int64_t n, int64_t m, int64_t ld, double *out,
                                void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !x || !out || n <= 0 || m <= 0 || ld < m) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -517,6 +519,7 @@ extern "C" int xc_colsum_dense(xc_ctx *ctx, const void *x, int dtype, int64_t n,
 extern "C" int xc_colsum_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices, int64_t nnz, int64_t m,
                              double *out, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !out || nnz < 0 || m <= 0) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -533,6 +536,7 @@ extern "C" int xc_confmat_dense_compact(xc_ctx *ctx, const void *y_true, int dty
                                         const int32_t *pred_idx, int k, int64_t n, int64_t m, int order,
                                         const double *colsum, double *tp, double *fp, double *fn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !y_true || !pred_idx || !tp || !fp || !fn || n <= 0 || m <= 0 || ld < m || k < 1) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -567,6 +571,7 @@ extern "C" int xc_confmat_csr(xc_ctx *ctx, const void *t_data, const int32_t *t_
                               const void *p_data, const int32_t *p_idx, const int64_t *p_ptr, int dtype, int64_t n,
                               int64_t m, int order, int acc_f32, double *tp, double *fp, double *fn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !t_ptr || !p_ptr || !tp || !fp || !fn || n <= 0 || m <= 0) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -592,6 +597,7 @@ extern "C" int xc_confmat_csr_compact(xc_ctx *ctx, const void *t_data, const int
                                       int dtype, const int32_t *pred_idx, int k, int64_t n, int64_t m, int order,
                                       double *tp, double *fp, double *fn, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !t_ptr || !pred_idx || !tp || !fp || n <= 0 || m <= 0 || k < 1) return XC_ERR_INVALID;
     if (!fn && order == XC_SUM_ORDERED) return XC_ERR_INVALID;  // fn may only be skipped in the fast order
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;
@@ -614,6 +620,7 @@ extern "C" int xc_confmat_csr_compact(xc_ctx *ctx, const void *t_data, const int
 extern "C" int xc_utility(xc_ctx *ctx, const xc_metric_params *p, int agg, const double *tp, const double *fp,
                           const double *fn, const double *tn, int64_t m, double *out_dev, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !tp || !fp || !fn || !out_dev || m <= 0) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
     int64_t blocks = (m + 255) / 256;
@@ -630,6 +637,7 @@ extern "C" int xc_confmat_csc_ordered(xc_ctx *ctx, const void *c_data, int dtype
                                       const int32_t *pred_idx, int k, int64_t n, int64_t m, double *tp, double *fp,
                                       double *fn, int *lone_flag_dev, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !c_rows || !c_ptr || !t_ptr || !pred_idx || !tp || !fp || !fn || !lone_flag_dev) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || k < 1) return XC_ERR_INVALID;
     if (dtype != XC_F32 && dtype != XC_F64) return XC_ERR_UNSUPPORTED;

@@ -1055,6 +1055,7 @@ extern "C" int xc_fw_iterate_dense(xc_ctx *ctx, const void *eta, int dtype, int6
                                    const void *y_true, int64_t ld_true, const void *a, const void *b, int k,
                                    double *tp, double *cnt, int32_t *pred_idx, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !y_true || !tp || !cnt || n <= 0 || m <= 0 || ld < m || ld_true < m) return XC_ERR_INVALID;
     if (k < 0 || k > 32 || k > m) return XC_ERR_INVALID;   // k == 0: no budget, threshold at 0
     cudaStream_t st = (cudaStream_t)stream;
@@ -1070,6 +1071,7 @@ extern "C" int xc_fw_iterate_csr(xc_ctx *ctx, const void *data, int dtype, const
                                  const int32_t *t_idx, const int64_t *t_ptr, const void *a, const void *b, int k,
                                  double *tp, double *cnt, int32_t *pred_idx, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !t_ptr || !tp || !cnt || n <= 0 || m <= 0) return XC_ERR_INVALID;
     if (k < 1 || k > 32) return XC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1097,6 +1099,7 @@ extern "C" int xc_fw_iterate_csr(xc_ctx *ctx, const void *data, int dtype, const
 extern "C" int xc_fw_make_conf(xc_ctx *ctx, const double *tp_raw, const double *cnt, const double *colsum, int64_t m,
                                double n, int normalize, int skip_tn, double *Ci, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !tp_raw || !cnt || !colsum || !Ci || m <= 0) return XC_ERR_INVALID;
     fw_make_conf_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         tp_raw, cnt, colsum, m, n, normalize, skip_tn, Ci);
@@ -1107,6 +1110,7 @@ extern "C" int xc_fw_make_conf(xc_ctx *ctx, const double *tp_raw, const double *
 extern "C" int xc_fw_metric_grad(xc_ctx *ctx, const xc_metric_params *p, const double *C, int64_t m, float *a_out,
                                  float *b_out, double *value_dev, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !C || m <= 0) return XC_ERR_INVALID;
     if ((a_out == nullptr) != (b_out == nullptr)) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
@@ -1266,6 +1270,7 @@ extern "C" int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const 
                                   int64_t m, const double *alphas_dev, int64_t n_alphas, double *scratch_dev,
                                   double *result_dev, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !C || !Ci || !scratch_dev || !result_dev || m <= 0 || n_alphas < 0) return XC_ERR_INVALID;
     if (n_alphas > 0 && !alphas_dev) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
@@ -1281,6 +1286,7 @@ extern "C" int xc_fw_alpha_search(xc_ctx *ctx, const xc_metric_params *p, const 
 extern "C" int xc_fw_alpha_ternary(xc_ctx *ctx, const xc_metric_params *p, const double *C, const double *Ci,
                                    int64_t m, double eps, double *result_dev, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !C || !Ci || !result_dev || m <= 0 || !(eps > 0.0)) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;
     fw_alpha_ternary_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*p, C, Ci, m, eps, result_dev);
@@ -1291,6 +1297,7 @@ extern "C" int xc_fw_alpha_ternary(xc_ctx *ctx, const xc_metric_params *p, const
 extern "C" int xc_fw_combine(xc_ctx *ctx, double *C, const double *Ci, int64_t m4, const double *alpha_dev,
                              void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !C || !Ci || !alpha_dev || m4 <= 0) return XC_ERR_INVALID;
     fw_combine_kernel<<<(unsigned)((m4 + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(C, Ci, m4,
                                                                                                           alpha_dev);
@@ -1316,6 +1323,7 @@ extern "C" int xc_fw_step_begin(xc_ctx *ctx, const void *eta, int dtype, int64_t
                                 const void *y_true, int64_t ld_true, const float *a_row, const float *b_row,
                                 double *ab64, int k, double *raw, int raw_is_zero, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !y_true || !a_row || !b_row || !raw) return XC_ERR_INVALID;
     if (n <= 0 || m <= 0 || ld < m || ld_true < m || k < 0 || k > 32 || k > m) return XC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1342,6 +1350,7 @@ extern "C" int xc_fw_step_finish(xc_ctx *ctx, const xc_metric_params *p, int fir
                                  double fixed_alpha, double *scratch_dev, double *scal, float *a_next, float *b_next,
                                  double *scal_next, int zero_raw, double ternary_eps, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !raw || !colsum || !Cm || !Ci || !scal || m <= 0) return XC_ERR_INVALID;
     if ((a_next == nullptr) != (b_next == nullptr)) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_HMEAN) return XC_ERR_INVALID;

@@ -103,3 +103,61 @@ extern "C" int xc_zero_host(void *p, int64_t bytes, int nthreads)
     for (auto &x : th) x.join();
     return XC_OK;
 }
+
+// ---- pageable host memory -> device ---------------------------------------------------------------------------
+// What a caller of the reference passes is an ordinary numpy array: pageable memory, which the driver can only
+// DMA through its own small staging buffers (~10 GB/s).  Here host threads copy chunk c + 1 into one of two pinned
+// staging buffers while the DMA of chunk c runs, so the upload proceeds at min(threaded memcpy, PCIe) instead.
+// Rows of width_bytes are copied from src (pitch src_pitch) to dst (pitch dst_pitch).  The call returns when the
+// last chunk has been queued on `stream`; src may be reused once the stream has passed that copy.
+namespace {
+constexpr size_t kStageBytes = (size_t)128 << 20;
+
+void copy_rows_threads(uint8_t *dst, const uint8_t *src, int64_t src_pitch, int64_t width, int64_t rows, int nthreads)
+{
+    const int64_t per = (rows + nthreads - 1) / nthreads;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t r0 = t * per, r1 = std::min(rows, r0 + per);
+        if (r0 >= r1) break;
+        th.emplace_back([=] {
+            if (src_pitch == width) std::memcpy(dst + r0 * width, src + r0 * src_pitch, (size_t)((r1 - r0) * width));
+            else for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + r * width, src + r * src_pitch, (size_t)width);
+        });
+    }
+    for (auto &x : th) x.join();
+}
+}  // namespace
+
+extern "C" int xc_h2d_staged(xc_ctx *ctx, void *dst_dev, int64_t dst_pitch, const void *src_host, int64_t src_pitch,
+                             int64_t width_bytes, int64_t rows, int nthreads, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !dst_dev || !src_host || width_bytes <= 0 || rows < 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+        return XC_ERR_INVALID;
+    if ((size_t)width_bytes > kStageBytes) return XC_ERR_UNSUPPORTED;
+    if (rows == 0) return XC_OK;
+    if (nthreads <= 0) nthreads = std::min(default_threads(), 16);
+    if (!ctx->stage[0]) {
+        for (int i = 0; i < 2; ++i) {
+            XC_CUDA_TRY(ctx, cudaHostAlloc(&ctx->stage[i], kStageBytes, cudaHostAllocDefault));
+            XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)(kStageBytes / (size_t)width_bytes));
+    int c = 0;
+    for (int64_t r0 = 0; r0 < rows; r0 += rows_per_chunk, ++c) {
+        const int64_t nr = std::min(rows_per_chunk, rows - r0);
+        const int b = c & 1;
+        if (c >= 2) XC_CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[b]));   // the DMA out of this buffer is done
+        copy_rows_threads(static_cast<uint8_t *>(ctx->stage[b]), static_cast<const uint8_t *>(src_host) + r0 * src_pitch,
+                          src_pitch, width_bytes, nr, nr * width_bytes < (1 << 22) ? 1 : nthreads);
+        XC_CUDA_TRY(ctx, cudaMemcpy2DAsync(static_cast<uint8_t *>(dst_dev) + r0 * dst_pitch, (size_t)dst_pitch, ctx->stage[b],
+                                           (size_t)width_bytes, (size_t)width_bytes, (size_t)nr, cudaMemcpyHostToDevice, st));
+        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[b], st));
+    }
+    // the staging buffers belong to the context: the next call may overwrite them, so wait for the last DMAs here
+    for (int b = 0; b < 2 && b < c; ++b) XC_CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[b]));
+    return XC_OK;
+}

@@ -11,6 +11,7 @@
 extern "C" int xc_p2p_create(xc_ctx *ctx, int world, int rank, int64_t payload_bytes, xc_p2p **out,
                              void *ipc_handle_out)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !out || !ipc_handle_out || world < 1 || world > XC_P2P_MAX_WORLD || rank < 0 || rank >= world ||
         payload_bytes <= 0)
         return XC_ERR_INVALID;
@@ -24,7 +25,6 @@ extern "C" int xc_p2p_create(xc_ctx *ctx, int world, int rank, int64_t payload_b
     w->opened = false;
     w->windows_dev = nullptr;
     for (int r = 0; r < XC_P2P_MAX_WORLD; ++r) w->windows[r] = nullptr;
-    cudaSetDevice(ctx->device);
     void *base = nullptr;
     cudaError_t e = cudaMalloc(&base, w->bytes);
     if (e == cudaSuccess) e = cudaMemset(base, 0, w->bytes);
@@ -48,8 +48,8 @@ extern "C" int xc_p2p_create(xc_ctx *ctx, int world, int rank, int64_t payload_b
 // handles: world * 64 bytes, the handle of rank r at offset 64 r (as gathered by the host shim)
 extern "C" int xc_p2p_open(xc_ctx *ctx, xc_p2p *w, const void *handles)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !w || !handles || w->opened) return XC_ERR_INVALID;
-    cudaSetDevice(ctx->device);
     for (int r = 0; r < w->world; ++r) {
         if (r == w->rank) continue;
         cudaIpcMemHandle_t h;
@@ -68,6 +68,7 @@ extern "C" void *xc_p2p_payload(xc_p2p *w) { return w ? w->windows[w->rank] + XC
 // error word of the local window (0 = fine, otherwise the commit number that timed out); synchronises
 extern "C" int xc_p2p_error(xc_ctx *ctx, xc_p2p *w, unsigned *out)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !w || !out) return XC_ERR_INVALID;
     XC_CUDA_TRY(ctx, cudaMemcpy(out, w->windows[w->rank] + 4 * XC_P2P_ERR_WORD, 4, cudaMemcpyDeviceToHost));
     return XC_OK;
@@ -76,7 +77,7 @@ extern "C" int xc_p2p_error(xc_ctx *ctx, xc_p2p *w, unsigned *out)
 extern "C" void xc_p2p_destroy(xc_ctx *ctx, xc_p2p *w)
 {
     if (!w) return;
-    if (ctx) cudaSetDevice(ctx->device);
+    XcDeviceGuard xc_guard__(ctx);
     for (int r = 0; r < w->world; ++r) {
         if (!w->windows[r]) continue;
         if (r == w->rank) cudaFree(w->windows[r]);

@@ -164,6 +164,7 @@ extern "C" int xc_topk_dense(xc_ctx *ctx, const void *eta, int eta_dtype, int64_
                              const int32_t *rows, const void *a, const void *b, int g_dtype, int k,
                              int32_t *out_idx, void *out_val, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !out_idx || n_rows < 0 || m <= 0 || ld < m) return XC_ERR_INVALID;
     if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
@@ -181,6 +182,7 @@ extern "C" int xc_topk_csr(xc_ctx *ctx, const void *data, int dtype, const int32
                            int64_t n_rows, const void *a, const void *b, int k, int32_t *out_idx, void *out_val,
                            void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !out_idx || n_rows < 0) return XC_ERR_INVALID;
     if (k < 1 || k > 32) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
@@ -206,6 +208,7 @@ extern "C" int xc_threshold_dense(xc_ctx *ctx, const void *eta, int eta_dtype, i
                                   int64_t ld, const void *a, const void *b, int g_dtype, double th, void *out,
                                   int64_t ld_out, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !out || n_rows < 0 || m <= 0 || ld < m || ld_out < m) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -233,6 +236,7 @@ extern "C" int xc_threshold_dense(xc_ctx *ctx, const void *eta, int eta_dtype, i
 extern "C" int xc_scatter_pred_dense(xc_ctx *ctx, const int32_t *pred_idx, const void *val, int val_dtype, int k,
                                      int64_t n_rows, void *out, int out_dtype, int64_t ld_out, void *stream)
 {
+    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !pred_idx || !out || k < 1 || n_rows < 0) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;

@@ -17,6 +17,18 @@ struct xc_ctx {
     // scratch of the deterministic multi-block reductions (block partials + ticket counter)
     double *red_partials;
     unsigned *red_counter;
+    // pipelined batched sweep (bca_batched.cu): two internal streams + ordering events, created on first use
+    cudaStream_t aux[2];
+    cudaEvent_t ev_fork, ev_commit[2], ev_join[2];
+    bool aux_ready;
+    // optional per-launch timing of the batch kernels (xc_timing_*): events in launch order
+    bool timing_on;
+    int timing_count, timing_cap;
+    cudaEvent_t *timing_ev;      // 2 per launch (start, end)
+    int64_t *timing_rows;        // rows of the launch
+    // pinned staging buffers of xc_h2d_staged (host.cu), allocated on first use
+    void *stage[2];
+    cudaEvent_t stage_ev[2];
 };
 
 constexpr int XC_RED_MAX_BLOCKS = 1024;
@@ -60,6 +72,26 @@ struct xc_p2p {
     } while (0)
 
 int xc_ctx_scratch(xc_ctx *ctx, size_t bytes, void **out);
+int xc_ctx_aux_streams(xc_ctx *ctx);
+int xc_timing_slot(xc_ctx *ctx, int64_t rows, cudaEvent_t *start, cudaEvent_t *end);
+
+// Every entry point runs on the context's device whatever the caller's current device is, and leaves the
+// caller's current device as it found it (a single process may drive several GPUs, one context each).
+struct XcDeviceGuard {
+    int prev;
+    bool switched;
+    explicit XcDeviceGuard(const xc_ctx *ctx) : prev(-1), switched(false)
+    {
+        if (!ctx) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~XcDeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+    XcDeviceGuard(const XcDeviceGuard &) = delete;
+    XcDeviceGuard &operator=(const XcDeviceGuard &) = delete;
+};
 
 static inline bool xc_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

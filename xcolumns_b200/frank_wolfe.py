@@ -46,6 +46,26 @@ class RandomizedWeightedClassifier:
         return predict_using_randomized_weighted_classifier(y_proba, self.k, self.a, self.b, self.p, dtype=dtype, seed=seed)
 
 
+def _draw_classifiers(P: np.ndarray, n: int, seed) -> np.ndarray:
+    """One classifier index per row, the same stream as the reference's per-row
+    ``rng.choice(arange(len(p)), p=p)`` (frank_wolfe.py:70, :199): Generator.choice with probabilities draws ONE
+    uniform double per call and returns cdf.searchsorted(u, side="right") on the normalised cumulative sum, so n
+    calls consume exactly the n doubles of one rng.random(n).  Vectorised: seconds -> milliseconds at n = 307 k."""
+    rng = np.random.default_rng(seed)
+    p = np.asarray(P, dtype=np.float64)
+    # the checks Generator.choice applies to p (non-negative, sums to 1 within sqrt(eps))
+    if p.ndim != 1 or (p < 0).any() or not np.isfinite(p).all():
+        raise ValueError("probabilities are not non-negative")
+    atol = np.sqrt(np.finfo(np.float64).eps)
+    if isinstance(P, np.ndarray) and np.issubdtype(P.dtype, np.floating):
+        atol = max(atol, np.sqrt(np.finfo(P.dtype).eps))
+    if abs(float(np.sum(p)) - 1.0) > atol:
+        raise ValueError("probabilities do not sum to 1")
+    cdf = p.cumsum()
+    cdf /= cdf[-1]
+    return cdf.searchsorted(rng.random(n), side="right").astype(np.int64)
+
+
 def predict_using_randomized_weighted_classifier(y_proba: Matrix, k: int, classifiers_a, classifiers_b,
                                                  classifiers_proba, dtype=None, seed=None) -> Matrix:
     """Prediction of a randomized weighted classifier (xcolumns/frank_wolfe.py:175-291): every row
@@ -65,9 +85,7 @@ def predict_using_randomized_weighted_classifier(y_proba: Matrix, k: int, classi
         raise ValueError("classifiers_a, classifier_b, and classifiers_proba must have the same number of columns as y_proba")
     if A.shape[0] != B.shape[0] or A.shape[0] != P.shape[0]:
         raise ValueError("classifiers_a, classifier_b, and classifiers_proba must have the same number of rows")
-    rng = np.random.default_rng(seed)
-    rng_range = np.arange(P.shape[0])
-    choice = np.array([rng.choice(rng_range, p=P) for _ in range(n)], dtype=np.int64)
+    choice = _draw_classifiers(P, n, seed)
     device = dev.pick_device(y_proba)
     if k == 0:
         # no budget: every label with a non-negative gain under the row's classifier (frank_wolfe.py:80-105
@@ -170,10 +188,18 @@ def find_classifier_using_fw(
     elif isinstance(init_classifier, str) and init_classifier == "random":
         A[0] = rng.random(m)
         B[0] = rng.random(m) - 0.5
+        if comm.world > 1:   # one classifier for the whole job: rank 0's draw (seed=None draws differ per rank)
+            ab = torch.from_numpy(np.stack([A[0], B[0]])).to(device)
+            torch.distributed.broadcast(ab, src=torch.distributed.get_global_rank(comm.group, 0), group=comm.group)
+            A[0], B[0] = ab.cpu().numpy()
     elif isinstance(init_classifier, str) and init_classifier == "prior":
         freq = np.asarray(y_true.sum(axis=0), dtype=DefaultDataDType).flatten() if not isinstance(
             y_true, torch.Tensor) else y_true.sum(0).float().cpu().numpy()
-        A[0] = 1.0 / ((freq + 0.1) / y_true.shape[0])
+        if comm.world > 1:   # label frequencies of ALL rows, not of this rank's shard
+            fq = torch.from_numpy(np.ascontiguousarray(freq, dtype=np.float64)).to(device)
+            comm.allreduce_sum_(fq)
+            freq = fq.cpu().numpy().astype(DefaultDataDType)
+        A[0] = 1.0 / ((freq + 0.1) / n_global)
         B[0] = 0
     elif (isinstance(init_classifier, (tuple, list)) and len(init_classifier) == 2
           and all(isinstance(v, (np.ndarray, torch.Tensor)) and tuple(v.shape) == (m,) for v in init_classifier)):

@@ -137,6 +137,21 @@ def predict_weighted_per_instance(
 def _threshold_dense(like, d: dev.DenseDev, ad, bd, g_code, th, dtype):
     device = d.t.device
     ctx = dev.ctx_for(device)
+    if not np.isscalar(th) and getattr(th, "ndim", 0) > 0:
+        # a vector of per-label thresholds (weighted_prediction.py:118): same gains (separate IEEE multiply and
+        # add in the gain dtype), compared label-wise; k = 0 is not a hot path, elementwise torch on the device
+        gdt = torch.float32 if g_code == XC_F32 else torch.float64
+        thv = dev.vec_to_device(th, device, gdt, d.m, "th")
+        g = d.t[:, :d.m].to(gdt)
+        if ad is not None:
+            g = g * ad
+        if bd is not None:
+            g = g + bd
+        out = (g >= thv).to(d.torch_dtype)
+        if isinstance(like, torch.Tensor):
+            return out.to(device=like.device, dtype=like.dtype if dtype is None else dtype)
+        res = out.cpu().numpy()
+        return res if dtype is None else res.astype(dtype)
     out = torch.empty((d.n, d.m), dtype=d.torch_dtype, device=device)
     ctx.call("xc_threshold_dense", dev.ptr(d.t), d.code, d.n, d.m, d.ld, dev.ptr(ad), dev.ptr(bd), g_code,
              C.c_double(float(th)), dev.ptr(out), d.m, dev.stream_ptr(device))
@@ -155,6 +170,8 @@ def _threshold_csr(like: csr_matrix, c: dev.CsrDev, ad, bd, th, dtype):
         g = g * ad[idx]
     if bd is not None:
         g = g + bd[idx]
+    if not np.isscalar(th) and getattr(th, "ndim", 0) > 0:
+        th = dev.vec_to_device(th, c.data.device, c.data.dtype, c.m, "th")[idx]
     keep = g >= th
     row_of = torch.repeat_interleave(torch.arange(c.n, device=c.data.device), c.indptr[1:] - c.indptr[:-1])
     counts = torch.zeros(c.n, dtype=torch.int64, device=c.data.device).index_add_(0, row_of[keep], torch.ones_like(row_of[keep]))
