@@ -201,8 +201,10 @@ def union_ms(st, en):
     return float(tot + cur_e - cur_s)
 
 
-def timed(fn, steps, device, comm=None):
-    """steps calls of fn between two CUDA events, barrier + synchronize on both sides; ms (max over ranks)"""
+def timed(fn, steps, device, comm=None, after_enqueue=None):
+    """steps calls of fn between two CUDA events, barrier + synchronize on both sides; ms (max over ranks).
+    after_enqueue runs on the host once everything (incl. the closing event) is queued, i.e. while the GPU is
+    still executing the timed steps."""
     import torch
     import torch.distributed as dist
     if comm is not None:
@@ -213,6 +215,8 @@ def timed(fn, steps, device, comm=None):
     for _ in range(steps):
         fn()
     e1.record()
+    if after_enqueue is not None:
+        after_enqueue()
     torch.cuda.synchronize(device)
     if comm is not None:
         comm.barrier()
@@ -327,10 +331,7 @@ def bench_csr(args, device, what, n=153000, m=670000, nnz=100, cpu=True):
 
         def step():
             sweep_no[0] += 1
-            order = sess.permutation(n, 3 + 7919 * sweep_no[0])
-            sess.zero_delta()
-            sess.sweep_and_fold(order, batch, None, full=(sweep_no[0] % 16 == 0))
-            sess.utility_device(1)
+            sess.run_sweep(sweep_no[0], 3 + 7919 * sweep_no[0], True, batch, None, sweep_no[0] % 16 == 0, sess.util_buf[1:])
 
         def reset():
             sess.pred = init_pred.clone()
@@ -446,12 +447,12 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
     n_batches = comm.max_int((n_local + batch - 1) // batch)
     sweep_no = [0]
 
-    def one_sweep():
+    util = torch.zeros(4096, dtype=torch.float64, device=device)
+
+    def one_sweep():   # what the public driver enqueues per sweep (order, snapshot, batches + commits, utility)
         sweep_no[0] += 1
-        order = sess.permutation(n_local, 17 + 1000003 * comm.rank + 7919 * sweep_no[0])
-        sess.zero_delta()
-        sess.sweep_and_fold(order, batch, n_batches, full=(sweep_no[0] % 16 == 0))   # like the public driver
-        sess.utility_device(1)
+        j = sweep_no[0]
+        sess.run_sweep(j, 17 + 1000003 * comm.rank + 7919 * j, True, batch, n_batches, j % 16 == 0, util[j % 4096:])
 
     def reset():
         sess.pred = init_pred.clone()
@@ -470,23 +471,13 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
     if want_roofline:
         sess.ctx.call("xc_timing_enable", 1)
 
-    def loop_tail():
-        if sampler is not None:
-            sampler.sample_now()
-
-    steps_done = [0]
-
-    def step():
-        one_sweep()
-        steps_done[0] += 1
-        if steps_done[0] == args.steps:
-            loop_tail()   # the queued sweeps are still executing: at least one clock sample under load
-
-    ms = timed(step, args.steps, device, comm)
+    # the queued sweeps are still executing when the host has enqueued them all: one clock sample under load
+    ms = timed(one_sweep, args.steps, device, comm, after_enqueue=(sampler.sample_now if sampler is not None else None))
     if sampler is not None:
         sampler.active = False
     launches = sess.ctx.launches() - launches0
-    utilities = sess.util_buf[:2].cpu().tolist()
+    sess.join()
+    utilities = [0.0, float(util[sweep_no[0] % 4096].item())]
     res = {"ms": ms, "value": n_global * args.steps / (ms / 1e3), "n_global": n_global, "batch": batch,
            "n_batches": n_batches, "launches": int(launches), "utility": utilities[1], "lag": sess.lag,
            "commit": ("peer-memory" if sess.peer is not None else ("all-reduce" if comm.world > 1 else "local")),

@@ -333,28 +333,54 @@ XC_API void *xc_p2p_payload(xc_p2p *w);
 XC_API int xc_p2p_error(xc_ctx *ctx, xc_p2p *w, unsigned *out);
 XC_API void xc_p2p_destroy(xc_ctx *ctx, xc_p2p *w);
 XC_API int64_t xc_bca_delta_stride(int64_t m);
-/* One block-Jacobi sweep over this rank's rows as ONE host call, single process (w = NULL) or with the rows
- * sharded over the GPUs of one box (w = the peer window; every rank calls with the same n_batches / lag).
- * ref: block_coordinate.py:448-463 (the per-instance loop of one sweep) evaluated batch-wise.
- * Per batch b (rows order[b * batch ...]): the streaming batch kernel accumulates the deltas of its rows
- * into delta buffer (batch0 + b) % NB; the commit kernel then folds that buffer -- with a window: flags every
- * peer, waits for every peer's flag and adds the W buffers read over NVLink in rank order, so that the
- * replicated state stays bit-identical -- into tp/fp/fn, refreshes the gain coefficients (or the records
- * of Jaccard / G-mean / H-mean) and clears buffer (batch0 + b + lag + 1) % NB.  NB = xc_bca_pipe_buffers(lag)
- * buffers of xc_bca_delta_stride(m) bytes each: in the window's payload, or `delta` when w is NULL; all
- * zero before the first call, never touched by the host afterwards.  batch0: number of batches of all
- * earlier calls on these buffers (the buffer rotation continues across sweeps).
- * lag = 0: strict order K_0, commit_0, K_1, ... on `stream`.  lag = 1: batch b sees the state after commit
- * b - 2; consecutive batch kernels run concurrently on two internal streams and every commit overlaps the
- * next batch's streaming (the call forks from and joins `stream`; record metrics always run with lag 0).
- * coef: (lag + 1) sets of 4 * xc_bca_coef_len(m) floats, each [coef_n | coef_s] (or the records).
- * On return (stream order) tp/fp/fn hold the state after all n_batches commits.                      */
+/* Pipelined block-Jacobi sweeps over this rank's DENSE rows, one host call per sweep, single process (w = NULL)
+ * or with the rows sharded over the GPUs of one box (w = the peer window; every rank calls with the same
+ * n_batches / lag / flags).  ref: block_coordinate.py:415-493 (the sweep loop: shuffle :419, per-instance steps
+ * :448-463, utility :465-476) evaluated batch-wise.
+ * Per batch g = batch0 + b (rows order[b * batch ...]): the streaming batch kernel accumulates the deltas of its
+ * rows into delta buffer g % NB; the commit kernel then folds that buffer -- with a window: flags every peer,
+ * waits for every peer's flag and adds the W buffers read over NVLink in rank order, so that the replicated
+ * state stays bit-identical -- into tp/fp/fn, refreshes gain-coefficient set g % (lag + 1) (or the records of
+ * Jaccard / G-mean / H-mean) and clears buffer (g + lag + 1) % NB.  NB = xc_bca_pipe_buffers(lag) buffers of
+ * xc_bca_delta_stride(m) bytes each: in the window's payload, or `delta` when w is NULL; all zero before the
+ * first call, never touched by the host afterwards.  batch0: number of batches of all earlier calls on these
+ * buffers (the rotation continues across sweeps).
+ * lag = 0: strict order K_0, commit_0, K_1, ... on `stream`.  lag = 1: batch g sees the state after commit
+ * g - 2; consecutive batch kernels run concurrently on two internal streams, every commit overlaps the next
+ * batch's streaming, and the pipeline keeps running ACROSS calls: a sweep only waits for the previous sweep's
+ * batch kernels, the previous sweep's utility is computed behind its last commit, and `stream` is made to wait
+ * for that utility only.  XC_PIPE_FORK (or the first call, or a call after xc_bca_pipe_join) re-synchronises with
+ * `stream` first and recomputes every coefficient set from tp/fp/fn (needed after the host changed the state or
+ * the prediction).  xc_bca_pipe_join makes `stream` wait for everything in flight; it must precede any access
+ * to pred_idx / tp / fp / fn from `stream`.  Record metrics always run with lag 0.                          */
+enum { XC_PIPE_FORK = 1, XC_PIPE_SHUFFLE = 2 };
+typedef struct {
+    const xc_metric_params *params;
+    const void *eta;          /* [n_rows, ld] row-major                                                        */
+    int32_t dtype;            /* XC_F32 / XC_F64                                                               */
+    int32_t k;
+    int64_t m, ld, n_rows;
+    int64_t batch, n_batches; /* rows per commit; commits of this sweep (>= ceil(n_rows / batch): ragged shards) */
+    int64_t batch0;
+    int32_t lag;
+    int32_t flags;            /* XC_PIPE_*                                                                     */
+    uint64_t seed;            /* XC_PIPE_SHUFFLE: visiting order = xc_permutation(n_rows, seed), ref :419      */
+    int64_t sweep;            /* sweep counter: with XC_PIPE_SHUFFLE the order lives in order + (sweep & 1) * n_rows */
+    int32_t *order;           /* 2 * n_rows int32 with XC_PIPE_SHUFFLE (scratch), else the n_rows visiting order */
+    float *coef;              /* (lag + 1) sets of 4 * xc_bca_coef_len(m) floats, each [coef_n | coef_s] (or records) */
+    int32_t *pred_idx;        /* [n_rows, k], rewritten                                                        */
+    int32_t *pred_snapshot;   /* optional: copy of pred_idx as it was BEFORE this sweep (roll-back)            */
+    double *tp, *fp, *fn;     /* replicated float64 state                                                     */
+    double *delta;            /* w == NULL: the NB delta buffers                                               */
+    const xc_metric_params *util_params;  /* optional: utility of the state after this sweep (ref :468-476) -> */
+    double *util_out;         /*           util_out[0] (device)                                                */
+    int32_t agg;              /* 0 mean, 1 sum                                                                 */
+    int32_t reserved;
+    double util_tn_rows;      /* >= 0: tn = -tp - fp - fn + util_tn_rows inside the utility; < 0: tn = -1     */
+} xc_bca_pipe_args;
 XC_API int xc_bca_pipe_buffers(int lag);
-XC_API int xc_bca_sweep_dense_pipe(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, const void *eta,
-                                   int dtype, int64_t m, int64_t ld, const int32_t *order, int64_t n_order,
-                                   int64_t batch, int64_t n_batches, int lag, int64_t batch0, int k,
-                                   float *coef, int32_t *pred_idx, double *tp, double *fp, double *fn,
-                                   double *delta, void *stream);
+XC_API int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args *a, void *stream);
+XC_API int xc_bca_pipe_join(xc_ctx *ctx, void *stream);
 
 /* ---- host -> device upload of PAGEABLE host memory (what a numpy caller of the reference passes) ---- */
 /* rows x width_bytes from src_host (pitch src_pitch, ordinary pageable memory) to dst_dev (pitch dst_pitch):
@@ -365,7 +391,7 @@ XC_API int xc_h2d_staged(xc_ctx *ctx, void *dst_dev, int64_t dst_pitch, const vo
                          int64_t src_pitch, int64_t width_bytes, int64_t rows, int nthreads, void *stream);
 
 /* ---- per-launch timing of the streaming batch kernels (measurement only) ------------------ */
-/* While enabled, xc_bca_sweep_dense_pipe brackets every batch kernel with CUDA events on the stream it
+/* While enabled, xc_bca_pipe_sweep brackets every batch kernel with CUDA events on the stream it
  * is launched on.  xc_timing_read synchronises the device and returns for up to `cap` launches the start
  * and end time (ms since the first recorded event) and the rows processed (HOST arrays), the number of
  * recorded launches in *count_host, and clears the log.                                              */

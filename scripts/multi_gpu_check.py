@@ -90,11 +90,12 @@ assert sess.peer is not None and sess.pipe
 from xcolumns_b200.weighted_prediction import topk_dense_device  # noqa: E402
 sess.pred = topk_dense_device(sess.data, k, None, None, XC_F32)[0]
 sess.recompute(XC_SUM_FAST)
+util = torch.zeros(64, dtype=torch.float64, device=device)
 for it in range(60):
     if (it + rank) % 2 == 0:
         torch.cuda._sleep(int(2e6 * (1 + (it % 3))))        # ~1-3 ms of device-side delay on alternating ranks
-    order = sess.permutation(ns, 11 + 7919 * it + 13 * rank)
-    sess.sweep_and_fold(order, 100, 30, full=(it % 16 == 15))
+    sess.run_sweep(it + 1, 11 + 7919 * it + 13 * rank, True, 100, 30, it % 16 == 15, util[it:])
+sess.join()
 st = sess.state[:3].clone()
 gs = [torch.empty_like(st) for _ in range(world)]
 dist.all_gather(gs, st)

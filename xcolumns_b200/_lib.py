@@ -31,6 +31,20 @@ class MetricParams(C.Structure):
 _vp, _i32, _i64, _dbl, _int = C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int
 _MP = C.POINTER(MetricParams)
 
+XC_PIPE_FORK, XC_PIPE_SHUFFLE = 1, 2
+
+
+class PipeArgs(C.Structure):
+    """Mirror of xc_bca_pipe_args (one pipelined dense sweep, include/xcolumns_b200.h)."""
+    _fields_ = [("params", _MP), ("eta", C.c_void_p), ("dtype", C.c_int32), ("k", C.c_int32),
+                ("m", C.c_int64), ("ld", C.c_int64), ("n_rows", C.c_int64),
+                ("batch", C.c_int64), ("n_batches", C.c_int64), ("batch0", C.c_int64),
+                ("lag", C.c_int32), ("flags", C.c_int32), ("seed", C.c_uint64), ("sweep", C.c_int64),
+                ("order", C.c_void_p), ("coef", C.c_void_p), ("pred_idx", C.c_void_p), ("pred_snapshot", C.c_void_p),
+                ("tp", C.c_void_p), ("fp", C.c_void_p), ("fn", C.c_void_p), ("delta", C.c_void_p),
+                ("util_params", _MP), ("util_out", C.c_void_p), ("agg", C.c_int32), ("reserved", C.c_int32),
+                ("util_tn_rows", C.c_double)]
+
 # name -> argtypes (after ctx); every function returns int unless listed in _RESTYPES
 _SIGNATURES = {
     "xc_permutation": [_i64, C.c_uint64, _vp, _vp],
@@ -46,8 +60,8 @@ _SIGNATURES = {
     "xc_p2p_create": [_int, _int, _i64, _vp, _vp],
     "xc_p2p_open": [_vp, _vp],
     "xc_p2p_error": [_vp, _vp],
-    "xc_bca_sweep_dense_pipe": [_vp, _MP, _vp, _int, _i64, _i64, _vp, _i64, _i64, _i64, _int, _i64, _int, _vp, _vp,
-                                _vp, _vp, _vp, _vp, _vp],
+    "xc_bca_pipe_sweep": [_vp, _vp, _vp],
+    "xc_bca_pipe_join": [_vp],
     "xc_h2d_staged": [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp],
     "xc_timing_enable": [_int],
     "xc_timing_read": [_int, _vp, _vp, _vp, _vp],

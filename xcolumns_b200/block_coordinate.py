@@ -28,7 +28,7 @@ from scipy.sparse import csr_matrix
 
 from . import _device as dev
 from . import metrics as M
-from ._lib import XC_SUM_FAST, XC_SUM_ORDERED, MetricParams
+from ._lib import XC_PIPE_FORK, XC_PIPE_SHUFFLE, XC_SUM_FAST, XC_SUM_ORDERED, MetricParams, PipeArgs
 from .distributed import Comm, PeerWindow, make_comm, peer_commit_enabled
 from .types import Matrix
 from .utils import add_kwargs_to_signature, log_info, log_warning
@@ -134,6 +134,11 @@ class BcaSession:
                 peer.close()
         self.delta_pipe = (torch.zeros(nbuf * stride, dtype=torch.uint8, device=self.device)
                            if (self.pipe and self.peer is None) else None)
+        self._n_order = self.n          # rows a sweep visits (1 with the reference's normalize_conf_matrix=False quirk)
+        self._inflight = False          # the pipeline's internal streams hold work this stream has not joined
+        self._need_fork = True          # the host touched the state / prediction since the last pipelined sweep
+        self._order2: Optional[torch.Tensor] = None
+        self._snaps: List[torch.Tensor] = []
         self.colsum: Optional[torch.Tensor] = None
         # [set][coef_n | coef_s][label][B, A]: set 1 is the second coefficient version of the pipelined sweep
         self.coef = torch.zeros((2, 2, clen, 2), dtype=torch.float32, device=self.device)
@@ -159,7 +164,16 @@ class BcaSession:
         if not self.pipe:
             self.delta.zero_()
 
+    def join(self) -> None:
+        """this stream waits for everything the pipelined sweeps still have in flight; required before the host
+        (or any kernel on this stream) reads or rewrites the prediction or the state"""
+        if self._inflight:
+            self.ctx.call("xc_bca_pipe_join", self._s())
+            self._inflight = False
+        self._need_fork = True
+
     def close(self) -> None:
+        self.join()
         if self.peer is not None:
             torch.cuda.synchronize(self.device)
             self.comm.barrier()          # nobody may still be reading this rank's window
@@ -170,6 +184,7 @@ class BcaSession:
     # -- state from the current prediction ---------------------------------------------------
     def recompute(self, order: int) -> None:
         """tp / fp / fn (and tn) from scratch (block_coordinate.py:430-436, :465-467)."""
+        self.join()
         d, k = self.data, self.k
         if order == XC_SUM_ORDERED:
             if self.comm.world > 1:
@@ -243,8 +258,77 @@ class BcaSession:
 
     def utility_device(self, slot: int) -> None:
         """block_coordinate.py:54-90 on the device; result lands in util_buf[slot]."""
+        self.utility_into(self.util_buf[slot:])
+
+    def utility_into(self, out: torch.Tensor) -> None:
+        """utility of the current state into out[0] (float64, device)"""
+        self.join()
         self.ctx.call("xc_utility", C.byref(self.up), self.agg, self._sp(0), self._sp(1), self._sp(2), self._sp(3),
-                      self.m, C.c_void_p(self.util_buf[slot:].data_ptr()), self._s())
+                      self.m, C.c_void_p(out.data_ptr()), self._s())
+
+    # -- one batched sweep, whichever path the session uses ---------------------------------------
+    def run_sweep(self, j: int, seed: int, shuffle: bool, batch: int, n_batches: Optional[int], full: bool,
+                  util_out: torch.Tensor) -> torch.Tensor:
+        """Sweep number j (>= 1) over this rank's rows: visiting order xc_permutation(n, seed) (or 0..n-1), `batch`
+        rows per commit, the state after the sweep, its utility into util_out[0].  Returns a snapshot of the
+        prediction as it was before the sweep (valid until three sweeps later) for restore()."""
+        if self.pipe:
+            d = self.data
+            if self._order2 is None:
+                self._order2 = torch.arange(self._n_order, dtype=torch.int32, device=self.device).repeat(2)
+                self._snaps = [torch.empty_like(self.pred) for _ in range(3)]
+            snap = self._snaps[j % 3]
+            snap_ptr = snap.data_ptr()
+            if self._n_order != self.n:      # only the visited rows are copied by the call: take a whole copy here
+                self.join()
+                snap.copy_(self.pred)
+                snap_ptr = None
+            nb = n_batches if n_batches is not None else (self._n_order + batch - 1) // batch
+            flags = (XC_PIPE_SHUFFLE if shuffle else 0) | (XC_PIPE_FORK if self._need_fork else 0)
+            a = PipeArgs(params=C.pointer(self.p), eta=d.t.data_ptr(), dtype=d.code, k=self.k, m=d.m, ld=d.ld,
+                         n_rows=self._n_order, batch=int(batch), n_batches=int(nb), batch0=int(self._gb), lag=int(self.lag),
+                         flags=flags, seed=seed & 0xFFFFFFFFFFFFFFFF, sweep=j, order=self._order2.data_ptr(),
+                         coef=(self.rec if self.use_rec else self.coef).data_ptr(), pred_idx=self.pred.data_ptr(),
+                         pred_snapshot=snap_ptr, tp=self.state[0].data_ptr(), fp=self.state[1].data_ptr(),
+                         fn=self.state[2].data_ptr(),
+                         delta=self.delta_pipe.data_ptr() if self.delta_pipe is not None else None,
+                         util_params=C.pointer(self.up), util_out=util_out.data_ptr(), agg=self.agg, reserved=0,
+                         util_tn_rows=-1.0 if self.p.skip_tn else float(self.comm.n_global(self.n)))
+            self.ctx.call("xc_bca_pipe_sweep", self.peer.handle if self.peer is not None else None, C.byref(a), self._s())
+            self._gb += nb
+            self._inflight, self._need_fork = self.lag > 0, False
+            if full or os.environ.get("XCOLUMNS_B200_SWEEP_RECOMPUTE") == "1":
+                self.recompute(XC_SUM_FAST)       # joins; the next sweep re-forks and refreshes its coefficients
+                self.utility_into(util_out)
+            return snap
+        snap = self.pred.clone()
+        order = (self.permutation(self._n_order, seed, self._order_buf()) if shuffle else self._order_buf(True))
+        self.zero_delta()
+        self.sweep_and_fold(order, batch, n_batches, full)
+        self.utility_into(util_out)
+        return snap
+
+    def _order_buf(self, identity: bool = False) -> torch.Tensor:
+        if getattr(self, "_order1", None) is None:
+            self._order1 = torch.arange(self._n_order, dtype=torch.int32, device=self.device)
+        elif identity and not getattr(self, "_order1_identity", True):
+            torch.arange(self._n_order, dtype=torch.int32, device=self.device, out=self._order1)
+        self._order1_identity = identity
+        return self._order1
+
+    def restore(self, snapshot: torch.Tensor) -> None:
+        """put a prediction snapshot back (roll-back of a sweep); the state must be recomputed afterwards"""
+        self.join()
+        if snapshot.data_ptr() != self.pred.data_ptr():
+            self.pred.copy_(snapshot)
+
+    def sync_tn(self) -> None:
+        """tn of the current tp / fp / fn (kept lazily by the pipelined sweeps)"""
+        self.join()
+        if self.p.skip_tn:
+            self.state[3].fill_(-1.0)
+        else:
+            self.state[3] = -self.state[0] - self.state[1] - self.state[2] + self.comm.n_global(self.n)
 
     # -- sweeps -------------------------------------------------------------------------------
     def sweep_exact(self, order_dev: torch.Tensor, greedy: bool) -> None:
@@ -278,24 +362,13 @@ class BcaSession:
             self.state[3] = -self.state[0] - self.state[1] - self.state[2] + n_total
 
     def sweep_and_fold(self, order_dev: torch.Tensor, batch: int, n_batches: Optional[int], full: bool) -> None:
-        """One block-Jacobi sweep + the state after it.  Dense rows (one process, or sharded with a peer window) and
-        single-process CSR rows issue the whole sweep through ONE C call (small problems are bound by the per-call
-        overhead of this shim; sharded sweeps by the arrival skew a host-driven batch loop feeds into the barriers).
+        """One block-Jacobi sweep + the state after it on the NON-pipelined paths (CSR rows, dense rows of several
+        ranks without a peer window); dense rows of one process or of a box with peer windows go through
+        run_sweep -> xc_bca_pipe_sweep.  Single-process CSR rows issue the whole sweep through ONE C call (small
+        problems are bound by the per-call overhead of this shim).
         full: recompute the state from the prediction afterwards (block_coordinate.py:465-467)."""
         d, k = self.data, self.k
         n_loc = int(order_dev.numel())
-        if self.pipe:
-            nb = n_batches if n_batches is not None else (n_loc + batch - 1) // batch
-            self.ctx.call("xc_bca_sweep_dense_pipe", self.peer.handle if self.peer is not None else None,
-                          C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, dev.ptr(order_dev), n_loc, int(batch),
-                          int(nb), int(self.lag), int(self._gb), k, dev.ptr(self.rec if self.use_rec else self.coef),
-                          dev.ptr(self.pred), self._sp(0), self._sp(1), self._sp(2), dev.ptr(self.delta_pipe), self._s())
-            self._gb += nb
-            if full or os.environ.get("XCOLUMNS_B200_SWEEP_RECOMPUTE") == "1":
-                self.recompute(XC_SUM_FAST)
-            elif not self.p.skip_tn:
-                self.state[3] = -self.state[0] - self.state[1] - self.state[2] + self.comm.n_global(self.n)
-            return
         if self.comm.world > 1 or full or not self.is_csr:
             self.sweep_batched(order_dev, batch, n_batches)
             self.finish_sweep(full)
@@ -518,29 +591,22 @@ def predict_using_bc_with_0approx(
         n_batches = comm.max_int((n_order + batch - 1) // batch)
         batch_max = comm.max_int(batch)      # ragged shards: ranks may differ by a row, decisions must not
         base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
-        order_dev = torch.arange(n_order, dtype=torch.int32, device=device)
-        sess.recompute(XC_SUM_FAST)
-        sess.utility_device(0)
+        sess._n_order = n_order
         meta["batch_size"] = batch
-        # Sweep j+1 is enqueued before sweep j's utilities are read on the host, so the GPU queue
-        # never drains at the stopping test; if sweep j was the last one the prediction saved
-        # before the speculative sweep is restored.
-        util_dev = torch.zeros((max_iters + 2, 2), dtype=torch.float64, device=device)
+        # util_all[0]: utility of the initial prediction, util_all[j]: after sweep j (float64, device).  Sweep j+1 is
+        # enqueued before sweep j's utility is read on the host, so the GPU queue never drains at the stopping
+        # test; if sweep j turns out to be the last one, the snapshot taken before the speculative sweep is restored.
+        util_all = torch.zeros(max_iters + 2, dtype=torch.float64, device=device)
         util_host = torch.zeros((max_iters + 2, 2), dtype=torch.float64).pin_memory()
+        sess.recompute(XC_SUM_FAST)
+        sess.utility_into(util_all)
         events, saved = {}, {}
         attempt = 0
 
         def enqueue(j):
-            nonlocal order_dev
-            saved[j] = sess.pred.clone()
-            if shuffle_order:
-                order_dev = sess.permutation(n_order, base_seed + 0x632BE59BD9B4E019 * j + 0x9FB21C651E98DF25 * attempt)
-            sess.zero_delta()
-            sess.sweep_and_fold(order_dev, batch, n_batches, full=(j % 16 == 0))
-            sess.utility_device(1)
-            util_dev[j].copy_(sess.util_buf[:2])
-            sess.util_buf[0] = sess.util_buf[1]
-            util_host[j].copy_(util_dev[j], non_blocking=True)
+            saved[j] = sess.run_sweep(j, base_seed + 0x632BE59BD9B4E019 * j + 0x9FB21C651E98DF25 * attempt, shuffle_order,
+                                      batch, n_batches, j % 16 == 0, util_all[j:])
+            util_host[j].copy_(util_all[j - 1:j + 1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(device))
             events[j] = ev
@@ -558,11 +624,11 @@ def predict_using_bc_with_0approx(
                 # Block-Jacobi overshoot (the rows of a batch all reacted to the same frozen state): the
                 # sequential sweep this mode stands in for cannot lose utility.  Roll the sweep (and the
                 # speculative one after it) back ...
-                sess.pred = saved[j]
+                sess.restore(saved[j])
                 events.clear()
                 saved.clear()
                 sess.recompute(XC_SUM_FAST)
-                sess.utility_device(0)
+                sess.utility_into(util_all[j - 1:])
                 # (the decision is taken on numbers every rank agrees on: the utilities come from the
                 #  replicated state, batch_max is all-reduced)
                 if batch_max > 16 and not batch_size:
@@ -580,16 +646,17 @@ def predict_using_bc_with_0approx(
                 log_info(f"  Stopping: iteration {j} lost utility ({old_u} -> {new_u}) and cannot be repeated "
                          f"with smaller batches", verbose)
                 break
-            saved.pop(j, None)
             meta["iters"] = j
             meta["utilities"].append(new_u)
             log_info(f"    Iteration {j}/{max_iters} finished, expected metric value: {old_u} -> {new_u}", verbose)
             if (maximize and new_u - old_u < tolerance) or (not maximize and new_u - old_u > tolerance):
                 log_info(f"  Stopping because improvement of expected metric value is smaller than {tolerance}", verbose)
                 if j + 1 in saved:
-                    sess.pred = saved[j + 1]      # undo the speculative sweep
+                    sess.restore(saved[j + 1])    # undo the speculative sweep
                 break
+            saved.pop(j, None)
             j += 1
+        sess.join()
 
     meta["launches"] = sess.ctx.launches()
     meta["lag"] = sess.lag if (mode == "batched" and sess.pipe) else 0
@@ -869,20 +936,40 @@ def predict_optimizing_coverage_using_bc(
     else:
         batch = int(batch_size) if batch_size else coverage_batch_rows(n)
         n_batches = comm.max_int((n + batch - 1) // batch)
+        batch_max = comm.max_int(batch)
         base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
         order_dev = torch.arange(n, dtype=torch.int32, device=device)
         sess.state(XC_SUM_FAST)
         sess.utility_device(0)
         meta["batch_size"] = batch
-        for j in range(1, max_iters + 1):
+        j, attempt = 1, 0
+        while j <= max_iters:
             log_info(f"  Starting iteration {j}/{max_iters} ...", verbose)
+            saved = sess.pred.clone()
             if shuffle_order:
-                sess.ctx.call("xc_permutation", n, C.c_uint64((base_seed + 0x632BE59BD9B4E019 * j) & (2**64 - 1)),
+                sess.ctx.call("xc_permutation", n, C.c_uint64((base_seed + 0x632BE59BD9B4E019 * j +
+                                                               0x9FB21C651E98DF25 * attempt) & (2**64 - 1)),
                               dev.ptr(order_dev), sess._s())
             sess.sweep_batched(order_dev, batch, n_batches)
             sess.state(XC_SUM_FAST)                         # :676 (the products are recomputed, like the reference)
             sess.utility_device(1)
             old_cov, new_cov = (float(v) for v in sess.util_buf[:2].cpu())
+            if new_cov < old_cov - 1e-12:
+                # block-Jacobi overshoot: the rows of a batch all rushed to the same uncovered labels, which the
+                # sequential sweep this mode stands in for cannot do (it never loses coverage).  Roll the sweep back
+                # and repeat it with 4x more commits; with a caller-chosen or already minimal batch keep the
+                # prediction the sweep started from.
+                sess.pred = saved
+                sess.state(XC_SUM_FAST)
+                sess.utility_device(0)
+                if batch_max > 16 and not batch_size:
+                    batch, batch_max = max(16, batch // 4), max(16, batch_max // 4)
+                    n_batches = comm.max_int((n + batch - 1) // batch)
+                    meta["batch_size"] = batch
+                    attempt += 1
+                    log_info(f"    Iteration {j} lost coverage ({old_cov} -> {new_cov}); repeating with batches of {batch} rows", verbose)
+                    continue
+                break
             sess.util_buf[0] = sess.util_buf[1]
             meta["iters"] = j
             meta["utilities"].append(new_cov)
@@ -890,6 +977,7 @@ def predict_optimizing_coverage_using_bc(
             if new_cov <= old_cov + tolerance:              # :690
                 log_info(f"  Stopping because improvement of expected coverage is smaller than {tolerance}", verbose)
                 break
+            j += 1
     y_pred = _finish_pred(y_proba, sess.pred, m, y_pred_format)
     if return_meta:
         meta["time"] = time() - meta["time"]

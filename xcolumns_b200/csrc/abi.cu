@@ -43,6 +43,8 @@ extern "C" int xc_ctx_create(int device, xc_ctx **out)
     ctx->red_partials = nullptr;
     ctx->red_counter = nullptr;
     ctx->aux_ready = false;
+    ctx->pipe_active = false;
+    ctx->pipe_commits = 0;
     ctx->timing_on = false;
     ctx->timing_count = ctx->timing_cap = 0;
     ctx->timing_ev = nullptr;
@@ -70,8 +72,11 @@ extern "C" void xc_ctx_destroy(xc_ctx *ctx)
             cudaStreamDestroy(ctx->aux[i]);
             cudaEventDestroy(ctx->ev_commit[i]);
             cudaEventDestroy(ctx->ev_join[i]);
+            cudaEventDestroy(ctx->ev_k[i]);
         }
         cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_pro);
+        cudaEventDestroy(ctx->ev_util);
     }
     for (int i = 0; i < 2 * ctx->timing_cap; ++i) cudaEventDestroy(ctx->timing_ev[i]);
     free(ctx->timing_ev);
@@ -146,8 +151,11 @@ int xc_ctx_aux_streams(xc_ctx *ctx)
         XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, hi));
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_commit[i], cudaEventDisableTiming));
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
     }
     XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_pro, cudaEventDisableTiming));
+    XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_util, cudaEventDisableTiming));
     ctx->aux_ready = true;
     return XC_OK;
 }

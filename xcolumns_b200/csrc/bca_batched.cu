@@ -1328,23 +1328,28 @@ extern "C" int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const vo
     return XC_OK;
 }
 
-// ---- pipelined sweep: batches overlap, commits are applied `lag` batches late ----------------------------------
+// ---- pipelined sweeps: batches overlap, commits are applied `lag` batches late ---------------------------------
 // The strict block-Jacobi order  K_0, commit_0, K_1, commit_1, ...  leaves the GPU under-filled at every batch
 // boundary: the tail of the batch kernel, the commit (a cross-GPU barrier when the rows are sharded), the ramp of
 // the next kernel -- and a batch smaller than one wave of resident warps (strong scaling: 38 k rows per GPU cut
-// into 8 commits = 0.68 wave) cannot saturate HBM by itself.  With lag = 1 batch b is evaluated against the state
-// after commit b-2: K_b and K_{b+1} have no dependency on each other, so they run on two streams, and the chain
-//     K_b -> commit_b -> K_{b+2}                      (stream b & 1)
-//     commit_{b-1} -> commit_b                        (event: the state is folded in batch order)
+// into 8 commits = 0.68 wave) cannot saturate HBM by itself.  With lag = 1 batch g (global index, counted over
+// all sweeps) is evaluated against the state after commit g-2: K_g and K_{g+1} have no dependency on each other,
+// so they run on two streams, and the chain
+//     K_g -> commit_g -> K_{g+2}                      (stream g & 1, coefficient set g & 1)
+//     commit_{g-1} -> commit_g                        (event: the state is folded in batch order)
 // keeps two batch kernels in flight; the commit of one overlaps the streaming of the other (the commit kernel is
-// sized to fit next to six resident streaming CTAs).  Staleness grows from "up to one batch" to "one to two
-// batches"; measured against the sequential reference this moves the final macro-F1 by < 1e-6 (scripts/
-// probe_lag.py, tests/test_gpu_parity.py).  lag = 0 is the strict order on the caller's stream.
+// sized to fit next to six resident streaming CTAs).  The pipeline does NOT drain between sweeps: a sweep's
+// prologue (its visiting order, a snapshot of the prediction for roll-backs) only waits for the previous sweep's
+// last two batch KERNELS (a row must not be visited by two sweeps at once), not for their commits, and the
+// utility of the finished sweep is evaluated behind its last commit while the next sweep already streams.  The
+// caller's stream waits for that utility only.  Staleness grows from "up to one batch" to "one to two batches";
+// measured against the sequential reference this moves the final macro-F1 by < 1e-6 (scripts/probe_lag.py,
+// tests/test_gpu_baseline_shapes.py).  lag = 0 is the strict order on the caller's stream.
 //
-// Delta buffers: batch g (global index, continues over sweeps) accumulates into buffer g % NB, NB = 2 (lag + 1);
-// commit_g folds buffer g % NB and clears buffer (g + lag + 1) % NB, the one batch g + lag + 1 will use -- with
-// sharded rows that buffer was last read by the peers during commit g - lag - 1, which every peer has left before
-// it raised its flag for commit g.  No host-side clearing, no race with a slower peer.
+// Delta buffers: batch g accumulates into buffer g % NB, NB = 2 (lag + 1); commit_g folds buffer g % NB and
+// clears buffer (g + lag + 1) % NB, the one batch g + lag + 1 will use -- with sharded rows that buffer was last
+// read by the peers during commit g - lag - 1, which every peer has left before it raised its flag for commit g.
+// No host-side clearing, no race with a slower peer.
 namespace {
 
 struct PipeCommit {
@@ -1382,56 +1387,102 @@ int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *se
 
 }  // namespace
 
+static_assert(sizeof(xc_bca_pipe_args) == 192, "xc_bca_pipe_args layout (mirrored by ctypes in _lib.py)");
+
 extern "C" int xc_bca_pipe_buffers(int lag) { return 2 * ((lag > 0 ? 1 : 0) + 1); }
 
-extern "C" int xc_bca_sweep_dense_pipe(xc_ctx *ctx, xc_p2p *w, const xc_metric_params *p, const void *eta, int dtype,
-                                       int64_t m, int64_t ld, const int32_t *order, int64_t n_order, int64_t batch,
-                                       int64_t n_batches, int lag, int64_t batch0, int k, float *coef,
-                                       int32_t *pred_idx, double *tp, double *fp, double *fn, double *delta,
-                                       void *stream)
+// the caller's stream waits for everything the pipeline still has in flight (before the host reads or rewrites
+// the prediction / the state: recompute, roll-back, end of the call)
+extern "C" int xc_bca_pipe_join(xc_ctx *ctx, void *stream)
 {
     XcDeviceGuard xc_guard__(ctx);
-    if (!ctx || !p || !eta || !coef || !pred_idx || !tp || !fp || !fn || n_order < 0 || batch < 1 || n_batches < 0 ||
-        batch0 < 0 || m <= 0 || ld < m)
+    if (!ctx) return XC_ERR_INVALID;
+    if (!ctx->pipe_active) return XC_OK;
+    for (int i = 0; i < 2; ++i) {
+        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+        XC_CUDA_TRY(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_join[i], 0));
+    }
+    ctx->pipe_active = false;
+    return XC_OK;
+}
+
+extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args *a, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !a) return XC_ERR_INVALID;
+    const xc_metric_params *p = a->params;
+    const int64_t m = a->m, n_order = a->n_rows;
+    if (!p || !a->eta || !a->coef || !a->pred_idx || !a->tp || !a->fp || !a->fn || n_order < 0 || a->batch < 1 ||
+        a->n_batches < 0 || a->batch0 < 0 || m <= 0 || a->ld < m)
         return XC_ERR_INVALID;
-    if (n_order > 0 && !order) return XC_ERR_INVALID;
-    if (!w && !delta) return XC_ERR_INVALID;
+    if (n_order > 0 && !a->order) return XC_ERR_INVALID;
+    if (!w && !a->delta) return XC_ERR_INVALID;
     if (w && !w->opened) return XC_ERR_INVALID;
-    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (a->k < 1 || a->k > 32 || a->k > m) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
+    if (a->n_batches * a->batch < n_order) return XC_ERR_INVALID;
+    if (a->util_out && !a->util_params) return XC_ERR_INVALID;
     const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
     if (rec && p->metric != XC_METRIC_JACCARD && p->skip_tn) return XC_ERR_INVALID;
+    int lag = a->lag;
     if (rec) lag = 0;   // the record kernels read the float64 state of the selected labels: no overlap with a commit
     const int S = (lag > 0 ? 1 : 0) + 1, NB = 2 * S;
     const int64_t stride = xc_bca_delta_stride(m), clen = xc_bca_coef_len(m);
     if (w && (size_t)(XC_P2P_HEADER + NB * stride) > w->bytes) return XC_ERR_INVALID;
-    if (n_batches * batch < n_order) return XC_ERR_INVALID;
     cudaStream_t caller = (cudaStream_t)stream;
-    double *local = w ? reinterpret_cast<double *>(w->windows[w->rank] + XC_P2P_HEADER) : delta;
-    PipeCommit c{ctx, w, p, tp, fp, fn, local, (int64_t)XC_P2P_HEADER, stride, m, rec ? 1 : 0};
-    float *set[2] = {coef, coef + 4 * clen};
-    // coefficients of the state the sweep starts from, for every set
-    int rc = launch_commit(c, -1, -1, set[0], S > 1 ? set[1] : nullptr, clen, caller);
-    if (rc) return rc;
-    cudaStream_t st[2] = {caller, caller};
+    double *local = w ? reinterpret_cast<double *>(w->windows[w->rank] + XC_P2P_HEADER) : a->delta;
+    PipeCommit c{ctx, w, p, a->tp, a->fp, a->fn, local, (int64_t)XC_P2P_HEADER, stride, m, rec ? 1 : 0};
+    float *set[2] = {a->coef, a->coef + 4 * clen};
     // $XCOLUMNS_B200_PIPE_SERIAL=1 (tests): the same dependency order on ONE stream, nothing overlaps
     const bool serial = getenv("XCOLUMNS_B200_PIPE_SERIAL") && atoi(getenv("XCOLUMNS_B200_PIPE_SERIAL")) == 1;
     const bool forked = S > 1 && !serial;
+    int rc;
+    bool fresh = !forked || !ctx->pipe_active || (a->flags & XC_PIPE_FORK);
+    if (fresh) {
+        if (ctx->pipe_active) {
+            rc = xc_bca_pipe_join(ctx, stream);
+            if (rc) return rc;
+        }
+        // coefficients of the state the caller hands over, for every set
+        rc = launch_commit(c, -1, -1, set[0], S > 1 ? set[1] : nullptr, clen, caller);
+        if (rc) return rc;
+    }
+    cudaStream_t st[2] = {caller, caller};
     if (forked) {
         rc = xc_ctx_aux_streams(ctx);
         if (rc) return rc;
-        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, caller));
-        for (int i = 0; i < 2; ++i) {
-            st[i] = ctx->aux[i];
-            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_fork, 0));
+        st[0] = ctx->aux[0];
+        st[1] = ctx->aux[1];
+        if (fresh) {
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, caller));
+            for (int i = 0; i < 2; ++i) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_fork, 0));
+            ctx->pipe_commits = 0;
         }
+        ctx->pipe_active = true;
     }
-    for (int64_t b = 0; b < n_batches; ++b) {
-        const int64_t g = batch0 + b;
-        const int si = (int)(b % S);
+    // ---- prologue on the stream of the sweep's first batch: order + snapshot, after the previous sweep's kernels
+    const int s0 = (int)(a->batch0 % S);
+    if (forked && !fresh) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[s0 ^ 1], 0));
+    const int32_t *order = a->order + ((a->flags & XC_PIPE_SHUFFLE) ? (a->sweep & 1) * n_order : 0);
+    if ((a->flags & XC_PIPE_SHUFFLE) && n_order > 0) {
+        rc = xc_permutation(ctx, n_order, a->seed, const_cast<int32_t *>(order), st[s0]);
+        if (rc) return rc;
+    }
+    if (a->pred_snapshot && n_order > 0)
+        XC_CUDA_TRY(ctx, cudaMemcpyAsync(a->pred_snapshot, a->pred_idx, sizeof(int32_t) * (size_t)n_order * a->k,
+                                         cudaMemcpyDeviceToDevice, st[s0]));
+    if (forked) {
+        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pro, st[s0]));
+        XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0 ^ 1], ctx->ev_pro, 0));
+    }
+    // ---- batches
+    int last_si = s0;
+    for (int64_t b = 0; b < a->n_batches; ++b) {
+        const int64_t g = a->batch0 + b;
+        const int si = (int)(g % S);
         const int cur = (int)(g % NB), clr = (int)((g + S) % NB);
-        const int64_t lo = b * batch < n_order ? b * batch : n_order;
-        const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
+        const int64_t lo = b * a->batch < n_order ? b * a->batch : n_order;
+        const int64_t hi = lo + a->batch < n_order ? lo + a->batch : n_order;
         double *d = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(local) + (int64_t)cur * stride);
         if (hi > lo) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1440,23 +1491,40 @@ extern "C" int xc_bca_sweep_dense_pipe(xc_ctx *ctx, xc_p2p *w, const xc_metric_p
                 if (rc) return rc;
                 XC_CUDA_TRY(ctx, cudaEventRecord(e0, st[si]));
             }
-            rc = rec ? xc_bca_batch_dense_rec(ctx, p, eta, dtype, m, ld, order + lo, hi - lo, k, set[si], tp, fp, fn,
-                                              pred_idx, d, d + m, d + 2 * m, st[si])
-                     : xc_bca_batch_dense(ctx, eta, dtype, m, ld, order + lo, hi - lo, k, set[si], set[si] + 2 * clen,
-                                          pred_idx, d, d + m, d + 2 * m, st[si]);
+            rc = rec ? xc_bca_batch_dense_rec(ctx, p, a->eta, a->dtype, m, a->ld, order + lo, hi - lo, a->k, set[si],
+                                              a->tp, a->fp, a->fn, a->pred_idx, d, d + m, d + 2 * m, st[si])
+                     : xc_bca_batch_dense(ctx, a->eta, a->dtype, m, a->ld, order + lo, hi - lo, a->k, set[si],
+                                          set[si] + 2 * clen, a->pred_idx, d, d + m, d + 2 * m, st[si]);
             if (rc) return rc;
             if (e1) XC_CUDA_TRY(ctx, cudaEventRecord(e1, st[si]));
         }
-        if (forked && b > 0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[si], ctx->ev_commit[(b - 1) % S], 0));
+        if (forked) {
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[si], st[si]));   // "the last batch kernel of this stream is done"
+            if (ctx->pipe_commits > 0)   // the state is folded in batch order
+                XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[si], ctx->ev_commit[(ctx->pipe_commits - 1) & 1], 0));
+        }
         rc = launch_commit(c, cur, clr, set[si], nullptr, clen, st[si]);
         if (rc) return rc;
-        if (forked) XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_commit[si], st[si]));
-    }
-    if (forked) {
-        for (int i = 0; i < 2; ++i) {
-            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], st[i]));
-            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(caller, ctx->ev_join[i], 0));
+        last_si = si;
+        const bool last = b + 1 == a->n_batches;
+        if (last && a->util_out) {   // the finished sweep's utility, behind its last commit (the next commit waits for it)
+            rc = xc_utility_launch(ctx, a->util_params, a->agg, a->tp, a->fp, a->fn, nullptr, a->util_tn_rows, m,
+                                   a->util_out, st[si]);
+            if (rc) return rc;
         }
+        if (forked) {
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_commit[ctx->pipe_commits & 1], st[si]));
+            ctx->pipe_commits += 1;
+        }
+    }
+    if (a->n_batches == 0 && a->util_out) {
+        rc = xc_utility_launch(ctx, a->util_params, a->agg, a->tp, a->fp, a->fn, nullptr, a->util_tn_rows, m, a->util_out,
+                               st[last_si]);
+        if (rc) return rc;
+    }
+    if (forked) {   // the caller's stream sees the utility (and with it the state after the last commit), nothing else
+        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_util, st[last_si]));
+        XC_CUDA_TRY(ctx, cudaStreamWaitEvent(caller, ctx->ev_util, 0));
     }
     return XC_OK;
 }

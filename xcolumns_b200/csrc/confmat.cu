@@ -416,12 +416,13 @@ confmat_lone_check_kernel(const int32_t *__restrict__ t_idx, const int64_t *__re
 // ---- utility: mean / sum over labels of the binary metric, fixed reduction order -----------------
 __global__ void __launch_bounds__(256)
 utility_kernel(xc_metric_params p, int agg, const double *tp, const double *fp, const double *fn, const double *tn,
-               int64_t m, double *out, double *partials, unsigned *counter)
+               double tn_rows, int64_t m, double *out, double *partials, unsigned *counter)
 {
     __shared__ double sm[8];
     double s = 0.0;
     for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += (int64_t)gridDim.x * 256) {
-        double t4 = tn ? tn[j] : -1.0;
+        // tn: the stored vector, or (tn_rows >= 0) -tp - fp - fn + rows formed on the fly (confusion_matrix.py:397)
+        double t4 = tn_rows >= 0.0 ? ((-tp[j] - fp[j]) - fn[j]) + tn_rows : (tn ? tn[j] : -1.0);
         s += xc_metric_eval(p, tp[j] / p.n_div, fp[j] / p.n_div, fn[j] / p.n_div, t4 / p.n_div);
     }
     s = warp_sum(s);
@@ -617,19 +618,25 @@ extern "C" int xc_confmat_csr_compact(xc_ctx *ctx, const void *t_data, const int
     return XC_OK;
 }
 
-extern "C" int xc_utility(xc_ctx *ctx, const xc_metric_params *p, int agg, const double *tp, const double *fp,
-                          const double *fn, const double *tn, int64_t m, double *out_dev, void *stream)
+int xc_utility_launch(xc_ctx *ctx, const xc_metric_params *p, int agg, const double *tp, const double *fp,
+                      const double *fn, const double *tn, double tn_rows, int64_t m, double *out_dev, cudaStream_t st)
 {
-    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !tp || !fp || !fn || !out_dev || m <= 0) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
     int64_t blocks = (m + 255) / 256;
     int grid = (int)(blocks < XC_RED_MAX_BLOCKS ? blocks : XC_RED_MAX_BLOCKS);
     if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
-    utility_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, agg, tp, fp, fn, tn, m, out_dev, ctx->red_partials,
-                                                            ctx->red_counter);
+    utility_kernel<<<grid, 256, 0, st>>>(*p, agg, tp, fp, fn, tn, tn_rows, m, out_dev, ctx->red_partials,
+                                         ctx->red_counter);
     XC_LAUNCHED(ctx);
     return XC_OK;
+}
+
+extern "C" int xc_utility(xc_ctx *ctx, const xc_metric_params *p, int agg, const double *tp, const double *fp,
+                          const double *fn, const double *tn, int64_t m, double *out_dev, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    return xc_utility_launch(ctx, p, agg, tp, fp, fn, tn, -1.0, m, out_dev, (cudaStream_t)stream);
 }
 
 extern "C" int xc_confmat_csc_ordered(xc_ctx *ctx, const void *c_data, int dtype, const int32_t *c_rows,

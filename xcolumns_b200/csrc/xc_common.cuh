@@ -19,8 +19,10 @@ struct xc_ctx {
     unsigned *red_counter;
     // pipelined batched sweep (bca_batched.cu): two internal streams + ordering events, created on first use
     cudaStream_t aux[2];
-    cudaEvent_t ev_fork, ev_commit[2], ev_join[2];
+    cudaEvent_t ev_fork, ev_commit[2], ev_join[2], ev_k[2], ev_pro, ev_util;
     bool aux_ready;
+    bool pipe_active;            // the internal streams hold work the caller's stream has not joined yet
+    int64_t pipe_commits;        // commits issued since the fork (alternates ev_commit)
     // optional per-launch timing of the batch kernels (xc_timing_*): events in launch order
     bool timing_on;
     int timing_count, timing_cap;
@@ -74,6 +76,8 @@ struct xc_p2p {
 int xc_ctx_scratch(xc_ctx *ctx, size_t bytes, void **out);
 int xc_ctx_aux_streams(xc_ctx *ctx);
 int xc_timing_slot(xc_ctx *ctx, int64_t rows, cudaEvent_t *start, cudaEvent_t *end);
+int xc_utility_launch(xc_ctx *ctx, const xc_metric_params *p, int agg, const double *tp, const double *fp,
+                      const double *fn, const double *tn, double tn_rows, int64_t m, double *out_dev, cudaStream_t st);
 
 // Every entry point runs on the context's device whatever the caller's current device is, and leaves the
 // caller's current device as it found it (a single process may drive several GPUs, one context each).
