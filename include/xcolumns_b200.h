@@ -253,10 +253,20 @@ XC_API int xc_bca_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m
                               const int32_t *rows, int64_t n_rows, int k, const float *coef_n,
                               const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
                               double *dfn, void *stream);
+/* CSR rows.  max_row_nnz: an upper bound of the stored labels per row if the caller knows one, else 0; rows of at
+ * most 128 labels are held in registers and selected by warp reductions.  touch_*: optional "touched label" list
+ * (flag [m] zero-initialised, list [m], ctl [4] zero-initialised; only with 0 < max_row_nnz <= 128): every label
+ * whose deltas the batch changes is appended once, so that xc_bca_fold_touched can fold / refresh just those
+ * labels instead of all m.  ref: block_coordinate.py:212-293 (_bc_with_0approx_step_csr), frozen state.        */
 XC_API int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
                             const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k,
                             const float *coef_n, const float *coef_s, int32_t *pred_idx,
-                            double *dtp, double *dfp, double *dfn, void *stream);
+                            double *dtp, double *dfp, double *dfn, int max_row_nnz, int32_t *touch_flag,
+                            int32_t *touch_list, int32_t *touch_ctl, void *stream);
+XC_API int xc_bca_fold_touched(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
+                               double *dtp, double *dfp, double *dfn, int32_t *touch_flag,
+                               int32_t *touch_list, int32_t *touch_ctl, float *coef_n, float *coef_s,
+                               void *stream);
 /* coverage: gain = Ef_j * eta (not selected) or Ef_j / (1 - eta) * eta (selected); the batch
  * accumulates multiplicative factors into dEf (init 1), folded by xc_cov_fold.               */
 XC_API int xc_cov_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
@@ -313,11 +323,14 @@ XC_API int xc_bca_sweep_dense(xc_ctx *ctx, const xc_metric_params *p, const void
                               int64_t ld, const int32_t *order, int64_t n_order, int64_t batch, int k,
                               float *coef_a, float *coef_s, int32_t *pred_idx, double *tp, double *fp,
                               double *fn, double *dtp, double *dfp, double *dfn, void *stream);
+/* CSR form; max_row_nnz / touch_* as in xc_bca_batch_csr (NULL: every fold visits all m labels); refresh != 0:
+ * the host changed tp/fp/fn since the last call, all coefficients are recomputed first.                */
 XC_API int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
                             const int32_t *indices, const int64_t *indptr, int64_t m,
                             const int32_t *order, int64_t n_order, int64_t batch, int k, float *coef_n,
                             float *coef_s, int32_t *pred_idx, double *tp, double *fp, double *fn,
-                            double *dtp, double *dfp, double *dfn, void *stream);
+                            double *dtp, double *dfp, double *dfn, int max_row_nnz, int32_t *touch_flag,
+                            int32_t *touch_list, int32_t *touch_ctl, int refresh, void *stream);
 
 /* ---- commits over peer memory (rows sharded over the GPUs of one box) -------------------- */
 /* One window per rank: cudaMalloc'ed, exported with CUDA IPC (ipc_handle_out: 64 bytes), mapped by

@@ -72,7 +72,8 @@ _SIGNATURES = {
     "xc_bca_sweep_dense": [_MP, _vp, _int, _i64, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                            _vp],
     "xc_bca_sweep_csr": [_MP, _vp, _int, _vp, _vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                         _vp, _vp],
+                         _vp, _int, _vp, _vp, _vp, _int, _vp],
+    "xc_bca_fold_touched": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_colsum_dense": [_vp, _int, _i64, _i64, _i64, _vp, _vp],
     "xc_colsum_csr": [_vp, _int, _vp, _i64, _i64, _vp, _vp],
     "xc_utility": [_MP, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
@@ -84,7 +85,7 @@ _SIGNATURES = {
     "xc_bca_coef": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "xc_bca_wave_rows": [_int, _i64],
     "xc_bca_batch_dense": [_vp, _int, _i64, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "xc_bca_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "xc_bca_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp],
     "xc_cov_batch_csr": [_vp, _int, _vp, _vp, _vp, _i64, _int, _dbl, _vp, _vp, _vp, _vp],
     "xc_cov_batch_dense": [_vp, _int, _i64, _i64, _vp, _i64, _int, _dbl, _vp, _vp, _vp, _vp],
     "xc_cov_fold": [_vp, _vp, _i64, _vp],

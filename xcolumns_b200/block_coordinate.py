@@ -134,6 +134,17 @@ class BcaSession:
                 peer.close()
         self.delta_pipe = (torch.zeros(nbuf * stride, dtype=torch.uint8, device=self.device)
                            if (self.pipe and self.peer is None) else None)
+        # CSR rows of one process: rows that fit one warp's registers take the reduction-based batch kernel and keep a
+        # list of the labels a batch touched (folds then visit those labels only, not all m)
+        self.max_row_nnz = 0
+        self.touch_flag = self.touch_list = self.touch_ctl = None
+        self._csr_refresh = True
+        if self.is_csr and self.n > 0:
+            self.max_row_nnz = int((data.indptr[1:] - data.indptr[:-1]).max().item())
+            if self.comm.world == 1 and not self.use_rec and 0 < self.max_row_nnz <= 128:
+                self.touch_flag = torch.zeros(self.m, dtype=torch.int32, device=self.device)
+                self.touch_list = torch.empty(self.m, dtype=torch.int32, device=self.device)
+                self.touch_ctl = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._n_order = self.n          # rows a sweep visits (1 with the reference's normalize_conf_matrix=False quirk)
         self._inflight = False          # the pipeline's internal streams hold work this stream has not joined
         self._need_fork = True          # the host touched the state / prediction since the last pipelined sweep
@@ -185,6 +196,7 @@ class BcaSession:
     def recompute(self, order: int) -> None:
         """tp / fp / fn (and tn) from scratch (block_coordinate.py:430-436, :465-467)."""
         self.join()
+        self._csr_refresh = True
         d, k = self.data, self.k
         if order == XC_SUM_ORDERED:
             if self.comm.world > 1:
@@ -296,7 +308,7 @@ class BcaSession:
                          util_tn_rows=-1.0 if self.p.skip_tn else float(self.comm.n_global(self.n)))
             self.ctx.call("xc_bca_pipe_sweep", self.peer.handle if self.peer is not None else None, C.byref(a), self._s())
             self._gb += nb
-            self._inflight, self._need_fork = self.lag > 0, False
+            self._inflight, self._need_fork = True, False
             if full or os.environ.get("XCOLUMNS_B200_SWEEP_RECOMPUTE") == "1":
                 self.recompute(XC_SUM_FAST)       # joins; the next sweep re-forks and refreshes its coefficients
                 self.utility_into(util_out)
@@ -376,7 +388,10 @@ class BcaSession:
         self.ctx.call("xc_bca_sweep_csr", C.byref(self.p), dev.ptr(d.data), d.code, dev.ptr(d.indices),
                       dev.ptr(d.indptr), d.m, dev.ptr(order_dev), n_loc, int(batch), k,
                       dev.ptr(self.rec if self.use_rec else self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
-                      self._sp(0), self._sp(1), self._sp(2), self._dp(0), self._dp(1), self._dp(2), self._s())
+                      self._sp(0), self._sp(1), self._sp(2), self._dp(0), self._dp(1), self._dp(2), self.max_row_nnz,
+                      dev.ptr(self.touch_flag), dev.ptr(self.touch_list), dev.ptr(self.touch_ctl),
+                      int(self._csr_refresh), self._s())
+        self._csr_refresh = False
         if not self.p.skip_tn:
             self.state[3] = -self.state[0] - self.state[1] - self.state[2] + self.n
 
@@ -407,7 +422,7 @@ class BcaSession:
                 elif self.is_csr:
                     self.ctx.call("xc_bca_batch_csr", dev.ptr(d.data), d.code, dev.ptr(d.indices), dev.ptr(d.indptr),
                                   rows, hi - lo, k, dev.ptr(self.coef_n), dev.ptr(self.coef_s), dev.ptr(self.pred),
-                                  self._dp(0), self._dp(1), self._dp(2), self._s())
+                                  self._dp(0), self._dp(1), self._dp(2), self.max_row_nnz, None, None, None, self._s())
                 elif self.use_rec:
                     self.ctx.call("xc_bca_batch_dense_rec", C.byref(self.p), dev.ptr(d.t), d.code, d.m, d.ld, rows,
                                   hi - lo, k, dev.ptr(self.rec), self._sp(0), self._sp(1), self._sp(2),
@@ -444,7 +459,7 @@ def default_batch_rows(n: int, wave_rows: int = 0) -> int:
     """Rows one rank commits together: about n/8 (<= n/6 keeps the reference's
     fixed point within 3e-7 for F-measures), rounded down to whole waves of the streaming kernel so
     that no launch ends with a partially filled wave; tiny inputs use n/8 as is."""
-    b = max(1, n // 8)
+    b = max(1, (n + 7) // 8)      # rounded up: n = 8 q + r must not end in a ninth commit over r rows
     if wave_rows > 0 and b >= wave_rows:
         b = (b // wave_rows) * wave_rows
     return b

@@ -44,6 +44,7 @@ extern "C" int xc_ctx_create(int device, xc_ctx **out)
     ctx->red_counter = nullptr;
     ctx->aux_ready = false;
     ctx->pipe_active = false;
+    ctx->pipe_forked = false;
     ctx->pipe_commits = 0;
     ctx->timing_on = false;
     ctx->timing_count = ctx->timing_cap = 0;

@@ -240,8 +240,8 @@ __device__ __forceinline__ void seed_list(WarpTopK<G> &tk, G g, int j, int k)
     }
 }
 
-template <typename TE, int R>
-__global__ void __launch_bounds__(kThreads)
+template <typename TE, int R, bool DEEP = false>
+__global__ void __launch_bounds__(kThreads, DEEP ? 4 : ((R == 1 && sizeof(TE) == 4) ? 6 : 1))
 bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ rows,
                        int64_t n_rows, int k, const float2 *__restrict__ coef_n, const float2 *__restrict__ coef_s,
                        int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn, bool vec_ok)
@@ -277,7 +277,7 @@ bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
             }
             seed_list(tk[r], g, old_j[r], k);
         }
-        xc_scan_rows<TE, float, R, true>(rp, m, vec_ok, xf, tk, old_j, k);
+        xc_scan_rows<TE, float, R, true, XfAffine, DEEP>(rp, m, vec_ok, xf, tk, old_j, k);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (row_id[r] >= 0)  // warp-uniform
@@ -934,6 +934,188 @@ bca_batch_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
     }
 }
 
+// ---- CSR batch, second generation: rows of up to 128 stored labels, selection by warp reductions ------------------
+// The first kernel above builds the row's top-k through the serial list insertion shared with the dense scan
+// (~1500-2000 warp instructions per row, measured: the kernel was issue bound at 4.5 % of the HBM roofline).  A
+// CSR row of this path is tiny -- the whole row sits in 4 registers per lane -- so the k best are taken by k
+// rounds of two hardware warp reductions (REDUX.MAX on an order-preserving integer image of the gain, REDUX.MIN
+// on the position for ties: lower position = lower label id, the same rule as xc_better), ~12 instructions each.
+// Which stored entries are currently selected is resolved by k broadcasts; the probability of a label that
+// leaves is looked up only when a label really leaves (rare once a sweep has converged).
+// Labels whose deltas change are appended once to a "touched" list, so that the fold after the batch only
+// recomputes the coefficients of those labels instead of all m (C4: m = 670 k, but <= 2 k B labels can change).
+__device__ __forceinline__ unsigned gain_key(float g)
+{
+    const unsigned u = __float_as_uint(g + 0.0f);   // -0 -> +0: equal gains must have equal images
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct TouchList {
+    int32_t *flag;    // [m] 0 / 1
+    int32_t *list;    // [m]
+    int32_t *count;   // [0] entries, [1] ticket of the fold kernel
+    __device__ __forceinline__ void add(int j) const
+    {
+        if (flag && atomicExch(flag + j, 1) == 0) list[atomicAdd(count, 1)] = j;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 6)
+bca_batch_csr_redux_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                           const int64_t *__restrict__ indptr, const int32_t *__restrict__ rows, int64_t n_rows, int k,
+                           const float2 *__restrict__ coef_n, const float2 *__restrict__ coef_s,
+                           int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn, TouchList touch)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const T one = (T)1;
+    for (int64_t w = warp; w < n_rows; w += nwarps) {
+        const int64_t row = rows ? (int64_t)rows[w] : w;
+        const int64_t s = indptr[row], e = indptr[row + 1];
+        if (e - s > 32 * BC_RMAX) continue;   // cannot happen: the launcher only takes this kernel for max_row_nnz <= 128
+        const int nz = (int)(e - s);
+        int32_t *pred_row = pred_idx + row * k;
+        int old_j = -1;
+        if (lane < k) old_j = pred_row[lane];
+        int idx[BC_RMAX];
+        T val[BC_RMAX];
+#pragma unroll
+        for (int t = 0; t < BC_RMAX; ++t) {
+            const int q = lane + 32 * t;
+            idx[t] = q < nz ? indices[s + q] : -2;
+            val[t] = q < nz ? data[s + q] : (T)0;
+        }
+        unsigned selm = 0;   // bit t: my entry t is one of the row's current labels
+        for (int x = 0; x < k; ++x) {
+            const int px = __shfl_sync(XC_FULL, old_j, x);
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) selm |= (px >= 0 && idx[t] == px) ? (1u << t) : 0u;
+        }
+        unsigned key[BC_RMAX];
+#pragma unroll
+        for (int t = 0; t < BC_RMAX; ++t) {
+            key[t] = 0u;   // 0 = no entry / already taken (the image of any float is >= 0x007fffff)
+            if (idx[t] >= 0) {
+                const float2 cf = __ldg(((selm >> t) & 1u ? coef_s : coef_n) + idx[t]);
+                key[t] = gain_key(fmaf(cf.x, (float)val[t], cf.y));
+            }
+        }
+        // k rounds: best remaining entry of the row
+        unsigned my_pos = 0xffffffffu;   // lane t < k: position of the t-th best
+        for (int t = 0; t < k; ++t) {
+            unsigned bk = key[0];
+            int bs = 0;
+#pragma unroll
+            for (int u = 1; u < BC_RMAX; ++u)
+                if (key[u] > bk) { bk = key[u]; bs = u; }
+            const unsigned wmax = __reduce_max_sync(XC_FULL, bk);
+            const unsigned pos = (wmax != 0u && bk == wmax) ? (unsigned)(bs * 32 + lane) : 0xffffffffu;
+            const unsigned wpos = __reduce_min_sync(XC_FULL, pos);
+            if (lane == t) my_pos = wpos;
+            if (wpos != 0xffffffffu && (int)(wpos & 31u) == lane) {
+#pragma unroll
+                for (int u = 0; u < BC_RMAX; ++u)
+                    if ((int)(wpos >> 5) == u) key[u] = 0u;
+            }
+        }
+        // ascending position == ascending label: rank the k positions, then fetch label / probability by shuffle
+        int rank = 0;
+        for (int t = 0; t < k; ++t) {
+            const unsigned o = __shfl_sync(XC_FULL, my_pos, t);
+            rank += (o < my_pos) ? 1 : 0;   // positions are distinct; the "none" marker sorts last (rank by lane)
+            rank += (o == my_pos && t < lane) ? 1 : 0;
+        }
+        unsigned pos_sorted = 0xffffffffu;
+        for (int t = 0; t < k; ++t) {
+            const unsigned bal = __ballot_sync(XC_FULL, lane < k && rank == t);
+            const unsigned v = __shfl_sync(XC_FULL, my_pos, bal ? __ffs(bal) - 1 : 0);
+            if (lane == t) pos_sorted = v;
+        }
+        const bool none = pos_sorted == 0xffffffffu;
+        const int want_lane = none ? 0 : (int)(pos_sorted & 31u), want_t = none ? 0 : (int)(pos_sorted >> 5);
+        int gj = 0;
+        T ge = (T)0;
+#pragma unroll
+        for (int t = 0; t < BC_RMAX; ++t) {
+            const int vj = __shfl_sync(XC_FULL, idx[t], want_lane);
+            const T ve = __shfl_sync(XC_FULL, val[t], want_lane);
+            if (t == want_t) { gj = vj; ge = ve; }
+        }
+        const int new_j = (none || lane >= k) ? 0x7fffffff : gj;
+        const T new_e = none ? (T)0 : ge;
+        bool stays_old = false, stays_new = false;
+        for (int t = 0; t < k; ++t) {
+            const int nj = __shfl_sync(XC_FULL, new_j, t);
+            const int oj = __shfl_sync(XC_FULL, old_j, t);
+            stays_old |= (nj == old_j);
+            stays_new |= (oj == new_j);
+        }
+        const bool leaves = lane < k && !stays_old && old_j >= 0;
+        const unsigned leaving = __ballot_sync(XC_FULL, leaves);
+        if (leaving == 0u && __all_sync(XC_FULL, lane >= k || stays_new || new_j == 0x7fffffff)) continue;  // unchanged row
+        // probability of every label that leaves (its entry is somewhere in the row's registers)
+        T old_e = (T)0;
+        bool old_found = false;
+        for (unsigned lm = leaving; lm; lm &= lm - 1) {
+            const int x = __ffs(lm) - 1;
+            const int px = __shfl_sync(XC_FULL, old_j, x);
+#pragma unroll
+            for (int t = 0; t < BC_RMAX; ++t) {
+                const unsigned bal = __ballot_sync(XC_FULL, idx[t] == px);
+                if (bal) {
+                    const T v = __shfl_sync(XC_FULL, val[t], __ffs(bal) - 1);
+                    if (lane == x) { old_e = v; old_found = true; }
+                }
+            }
+        }
+        if (lane < k) {
+            if (leaves) {
+                if (old_found) {   // eta of the leaving label (a label the row does not store only had fp = 1)
+                    atomicAdd(dtp + old_j, -(double)old_e);
+                    atomicAdd(dfp + old_j, -(double)(T)(one - old_e));
+                    atomicAdd(dfn + old_j, (double)old_e);
+                } else {
+                    atomicAdd(dfp + old_j, -1.0);
+                }
+                touch.add(old_j);
+            }
+            if (!stays_new && new_j != 0x7fffffff) {
+                atomicAdd(dtp + new_j, (double)new_e);
+                atomicAdd(dfp + new_j, (double)(T)(one - new_e));
+                atomicAdd(dfn + new_j, -(double)new_e);
+                touch.add(new_j);
+            }
+            pred_row[lane] = new_j == 0x7fffffff ? -1 : new_j;
+        }
+    }
+}
+
+// fold + coefficients for the touched labels only; the last block re-arms the list
+__global__ void __launch_bounds__(kThreads)
+bca_fold_touched_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn,
+                        TouchList touch, float2 *coef_n, float2 *coef_s)
+{
+    const int cnt = touch.count[0];
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < cnt; i += gridDim.x * kThreads) {
+        const int j = touch.list[i];
+        const double t = tp[j] + dtp[j], f = fp[j] + dfp[j], g = fn[j] + dfn[j];
+        tp[j] = t; fp[j] = f; fn[j] = g;
+        dtp[j] = 0.0; dfp[j] = 0.0; dfn[j] = 0.0;
+        touch.flag[j] = 0;
+        bca_coef_of(p, t, f, g, coef_n + j, coef_s + j);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(touch.count + 1, 1) == (int)gridDim.x - 1) {   // every block has read the count
+            touch.count[0] = 0;
+            touch.count[1] = 0;
+        }
+    }
+}
+
 template <typename K>
 int grid_for(xc_ctx *ctx, K kernel, int64_t work_warps)
 {
@@ -971,6 +1153,17 @@ int dense_rows_per_warp(int64_t m)
     if (m * 8 <= 160 * 1024) return 1;
     if (m * 8 <= 512 * 1024) return 2;
     return 4;
+}
+
+// $XCOLUMNS_B200_DENSE_DEEP=0 disables the deep-prefetch variant for sub-wave batches
+bool dense_deep_ok()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("XCOLUMNS_B200_DENSE_DEEP");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // 0 = auto (LDG kernel), 1 = force the LDG kernel, 2 = force the TMA-ring kernel
@@ -1029,6 +1222,15 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
     const int rr = dense_rows_per_warp(m);
     if (rr == 4) XC_GO(4)
     else if (rr == 2) XC_GO(2)
+    else if (sizeof(TE) == 4 && vec_ok && dense_deep_ok() &&
+             n_rows * 4 <= (int64_t)ctx->sm_count * 6 * (kThreads / 32) * 3) {
+        // fewer rows than 3/4 of a wave of the 6-CTA kernel: the launch cannot fill the GPU, so each warp keeps
+        // twice the bytes in flight instead (4 CTAs per SM of the deep variant hold a 2/3-wave batch at once)
+        auto kern = bca_batch_dense_kernel<TE, 1, true>;
+        int grid = grid_for(ctx, kern, n_rows);
+        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, m, ld, rows, n_rows, k, (const float2 *)coef_n,
+                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok);
+    }
     else XC_GO(1)
 #undef XC_GO
     XC_LAUNCHED(ctx);
@@ -1163,13 +1365,33 @@ int launch_batch_csr(xc_ctx *ctx, const xc_metric_params *p, const void *data, c
 extern "C" int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
                                 const int64_t *indptr, const int32_t *rows, int64_t n_rows, int k,
                                 const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
-                                double *dfn, void *stream)
+                                double *dfn, int max_row_nnz, int32_t *touch_flag, int32_t *touch_list,
+                                int32_t *touch_ctl, void *stream)
 {
     XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !coef_n || !coef_s || !pred_idx || !dtp || !dfp || !dfn || n_rows < 0) return XC_ERR_INVALID;
     if (k < 1 || k > 32) return XC_ERR_INVALID;
+    if ((touch_flag || touch_list || touch_ctl) && !(touch_flag && touch_list && touch_ctl)) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (max_row_nnz > 0 && max_row_nnz <= 32 * BC_RMAX && (dtype == XC_F32 || dtype == XC_F64)) {
+        // every row fits the registers of one warp: selection by warp reductions, touched-label list
+        TouchList touch{touch_flag, touch_list, touch_ctl};
+        if (dtype == XC_F32) {
+            auto kern = bca_batch_csr_redux_kernel<float>;
+            kern<<<grid_for(ctx, kern, n_rows), kThreads, 0, st>>>((const float *)data, indices, indptr, rows, n_rows, k,
+                                                                   (const float2 *)coef_n, (const float2 *)coef_s,
+                                                                   pred_idx, dtp, dfp, dfn, touch);
+        } else {
+            auto kern = bca_batch_csr_redux_kernel<double>;
+            kern<<<grid_for(ctx, kern, n_rows), kThreads, 0, st>>>((const double *)data, indices, indptr, rows, n_rows, k,
+                                                                    (const float2 *)coef_n, (const float2 *)coef_s,
+                                                                    pred_idx, dtp, dfp, dfn, touch);
+        }
+        XC_LAUNCHED(ctx);
+        return XC_OK;
+    }
+    if (touch_flag) return XC_ERR_UNSUPPORTED;   // the streaming kernel does not maintain the touched list
     if (dtype == XC_F32)
         return launch_batch_csr<float, -1>(ctx, nullptr, data, indices, indptr, rows, n_rows, k, coef_n, coef_s, nullptr,
                                            nullptr, nullptr, nullptr, pred_idx, dtp, dfp, dfn, st);
@@ -1177,6 +1399,25 @@ extern "C" int xc_bca_batch_csr(xc_ctx *ctx, const void *data, int dtype, const 
         return launch_batch_csr<double, -1>(ctx, nullptr, data, indices, indptr, rows, n_rows, k, coef_n, coef_s, nullptr,
                                             nullptr, nullptr, nullptr, pred_idx, dtp, dfp, dfn, st);
     return XC_ERR_UNSUPPORTED;
+}
+
+// fold of the pending deltas + coefficients of the labels on the touched list only (the list is emptied)
+extern "C" int xc_bca_fold_touched(xc_ctx *ctx, const xc_metric_params *p, double *tp, double *fp, double *fn,
+                                   double *dtp, double *dfp, double *dfn, int32_t *touch_flag, int32_t *touch_list,
+                                   int32_t *touch_ctl, float *coef_n, float *coef_s, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !p || !tp || !fp || !fn || !dtp || !dfp || !dfn || !touch_flag || !touch_list || !touch_ctl || !coef_n ||
+        !coef_s)
+        return XC_ERR_INVALID;
+    if (p->metric != XC_METRIC_PRECISION && p->metric != XC_METRIC_RECALL && p->metric != XC_METRIC_FBETA &&
+        p->metric != XC_METRIC_BALANCED_ACC && p->metric != XC_METRIC_PREC_AT_K)
+        return XC_ERR_UNSUPPORTED;
+    TouchList touch{touch_flag, touch_list, touch_ctl};
+    bca_fold_touched_kernel<<<ctx->sm_count, kThreads, 0, (cudaStream_t)stream>>>(*p, tp, fp, fn, dtp, dfp, dfn, touch,
+                                                                                  (float2 *)coef_n, (float2 *)coef_s);
+    XC_LAUNCHED(ctx);
+    return XC_OK;
 }
 
 extern "C" int xc_bca_batch_csr_rec(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
@@ -1304,26 +1545,46 @@ extern "C" int xc_bca_sweep_dense(xc_ctx *ctx, const xc_metric_params *p, const 
 extern "C" int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const void *data, int dtype,
                                 const int32_t *indices, const int64_t *indptr, int64_t m, const int32_t *order,
                                 int64_t n_order, int64_t batch, int k, float *coef_n, float *coef_s, int32_t *pred_idx,
-                                double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn, void *stream)
+                                double *tp, double *fp, double *fn, double *dtp, double *dfp, double *dfn,
+                                int max_row_nnz, int32_t *touch_flag, int32_t *touch_list, int32_t *touch_ctl,
+                                int refresh, void *stream)
 {
     XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !order || n_order < 0 || batch < 1) return XC_ERR_INVALID;
     const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
-    auto fold = [&]() {   // coef_n is the record array for the record metrics
+    // touched-label lists: rows that fit one warp's registers, affine-gain metrics; the fold after a batch then
+    // only visits the labels the batch changed instead of all m
+    const bool lists = !rec && touch_flag && touch_list && touch_ctl && max_row_nnz > 0 && max_row_nnz <= 32 * BC_RMAX;
+    auto fold_all = [&]() {   // coef_n is the record array for the record metrics
         return rec ? xc_bca_rec(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, stream)
                    : xc_bca_coef(ctx, p, tp, fp, fn, dtp, dfp, dfn, m, coef_n, coef_s, stream);
     };
+    auto fold = [&]() {
+        return lists ? xc_bca_fold_touched(ctx, p, tp, fp, fn, dtp, dfp, dfn, touch_flag, touch_list, touch_ctl, coef_n,
+                                           coef_s, stream)
+                     : fold_all();
+    };
+    if (lists && refresh) {   // the host changed the state: every coefficient from scratch (pending deltas are zero)
+        int rc = fold_all();
+        if (rc) return rc;
+    }
     for (int64_t lo = 0; lo <= n_order; lo += batch) {
-        int rc = fold();
+        int rc = XC_OK;
+        if (!lists) rc = fold_all();
         if (rc) return rc;
         const int64_t hi = lo + batch < n_order ? lo + batch : n_order;
         if (hi <= lo) break;
         rc = rec ? xc_bca_batch_csr_rec(ctx, p, data, dtype, indices, indptr, order + lo, hi - lo, k, coef_n, tp, fp, fn,
                                         pred_idx, dtp, dfp, dfn, stream)
                  : xc_bca_batch_csr(ctx, data, dtype, indices, indptr, order + lo, hi - lo, k, coef_n, coef_s, pred_idx, dtp,
-                                    dfp, dfn, stream);
+                                    dfp, dfn, lists ? max_row_nnz : 0, lists ? touch_flag : nullptr,
+                                    lists ? touch_list : nullptr, lists ? touch_ctl : nullptr, stream);
         if (rc) return rc;
-        if (hi == n_order) return fold();
+        if (lists) {
+            rc = fold();
+            if (rc) return rc;
+        }
+        if (hi == n_order) return lists ? XC_OK : fold_all();
     }
     return XC_OK;
 }
@@ -1398,11 +1659,13 @@ extern "C" int xc_bca_pipe_join(xc_ctx *ctx, void *stream)
     XcDeviceGuard xc_guard__(ctx);
     if (!ctx) return XC_ERR_INVALID;
     if (!ctx->pipe_active) return XC_OK;
-    for (int i = 0; i < 2; ++i) {
-        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
-        XC_CUDA_TRY(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_join[i], 0));
+    if (ctx->pipe_forked) {
+        for (int i = 0; i < 2; ++i) {
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+            XC_CUDA_TRY(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_join[i], 0));
+        }
     }
-    ctx->pipe_active = false;
+    ctx->pipe_active = ctx->pipe_forked = false;
     return XC_OK;
 }
 
@@ -1437,7 +1700,10 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
     const bool serial = getenv("XCOLUMNS_B200_PIPE_SERIAL") && atoi(getenv("XCOLUMNS_B200_PIPE_SERIAL")) == 1;
     const bool forked = S > 1 && !serial;
     int rc;
-    bool fresh = !forked || !ctx->pipe_active || (a->flags & XC_PIPE_FORK);
+    // fresh: the caller hands over a state the commits of earlier calls did not produce (first call, after a join,
+    // XC_PIPE_FORK); otherwise the sweep continues on the coefficient sets the previous sweep's commits left behind
+    // (same dependency structure whether the batches overlap on two streams or are serialised on one)
+    const bool fresh = !ctx->pipe_active || (a->flags & XC_PIPE_FORK) || (forked != ctx->pipe_forked);
     if (fresh) {
         if (ctx->pipe_active) {
             rc = xc_bca_pipe_join(ctx, stream);
@@ -1458,8 +1724,9 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             for (int i = 0; i < 2; ++i) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_fork, 0));
             ctx->pipe_commits = 0;
         }
-        ctx->pipe_active = true;
     }
+    ctx->pipe_active = true;
+    ctx->pipe_forked = forked;
     // ---- prologue on the stream of the sweep's first batch: order + snapshot, after the previous sweep's kernels
     const int s0 = (int)(a->batch0 % S);
     if (forked && !fresh) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[s0 ^ 1], 0));

@@ -21,7 +21,8 @@ struct xc_ctx {
     cudaStream_t aux[2];
     cudaEvent_t ev_fork, ev_commit[2], ev_join[2], ev_k[2], ev_pro, ev_util;
     bool aux_ready;
-    bool pipe_active;            // the internal streams hold work the caller's stream has not joined yet
+    bool pipe_active;            // sweeps issued since the last join: the coefficient sets follow the commits
+    bool pipe_forked;            // ... on the internal streams (work the caller's stream has not joined yet)
     int64_t pipe_commits;        // commits issued since the fork (alternates ev_commit)
     // optional per-launch timing of the batch kernels (xc_timing_*): events in launch order
     bool timing_on;

@@ -173,7 +173,11 @@ __device__ __forceinline__ G xc_vmax(const G (&g)[V])
 // rp[r]: start of row r; vec_ok: rows are 16-byte aligned (base aligned and ld % V == 0).
 // old_idx[r]: (SKIP) lanes < k hold the labels already seeded into tk[r]; candidates equal to
 // one of them are ignored (their gain under the "selected" formula is already in the list).
-template <typename TE, typename G, int R, bool SKIP, class Xf>
+// DEEP: four 16-byte chunks per row in flight instead of two (R = 1 only).  At full occupancy the extra registers
+// cost a resident CTA and the kernel gets slower (measured in round 1); a launch that cannot fill the GPU anyway
+// (a batch of less than one wave of rows: strong scaling, tiny commits) is bound by the bytes each warp keeps in
+// flight, and there the deeper loop wins.
+template <typename TE, typename G, int R, bool SKIP, class Xf, bool DEEP = false>
 __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m, bool vec_ok, const Xf &xf,
                                              WarpTopK<G> (&tk)[R], const int (&old_idx)[R], int k)
 {
@@ -182,6 +186,7 @@ __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m
     const int lane = lane_id();
     const int64_t mv = vec_ok ? (m / V) * V : 0;
     const int64_t m2 = (mv / (2 * STEP)) * (2 * STEP);  // part covered by full, unguarded double steps
+    const int64_t m4 = (DEEP && R == 1) ? (mv / (4 * STEP)) * (4 * STEP) : 0;  // ... by quadruple steps
     const G qnan = (G)NAN;
 
     // ---- lists built from scratch (no seed): bound the threshold from the first double step ----
@@ -204,7 +209,27 @@ __device__ __forceinline__ void xc_scan_rows(const TE *const (&rp)[R], int64_t m
     // ---- main loop: two 16-byte chunks per row in flight, no bounds checks, no local memory ----
     // (a generalised loop with 4 chunks in flight was measured slower on the Frank-Wolfe iterate -- 350 vs
     // 334 us at 14 k x 31 k -- and its code shape cost the batched-BCA kernel 4 registers / one CTA per SM)
-    for (int64_t c0 = 0; c0 < m2; c0 += 2 * STEP) {
+    if (DEEP && R == 1) {
+        for (int64_t c0 = 0; c0 < m4; c0 += 4 * STEP) {
+            const int64_t cA = c0 + (int64_t)lane * V;
+            TE e[4][V];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) XcVec<TE>::load(rp[0] + cA + q * STEP, e[q]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {   // two pairs, each handled like one double step of the loop below
+                G gA[V], gB[V], ca[V], cb[V];
+                xf.template apply_vec<TE, V>(cA + (2 * h) * STEP, e[2 * h], gA, ca, cb, true);
+                bool hit = tk[0].passes(xc_vmax<G, V>(gA));
+                xf.template apply_vec<TE, V>(cA + (2 * h + 1) * STEP, e[2 * h + 1], gB, ca, cb, true);
+                hit |= tk[0].passes(xc_vmax<G, V>(gB));
+                if (__any_sync(XC_FULL, hit)) {
+                    xc_scan_insert<G, V, SKIP>(tk[0], gA, c0 + (2 * h) * STEP, V, k, old_idx[0]);
+                    xc_scan_insert<G, V, SKIP>(tk[0], gB, c0 + (2 * h + 1) * STEP, V, k, old_idx[0]);
+                }
+            }
+        }
+    }
+    for (int64_t c0 = m4; c0 < m2; c0 += 2 * STEP) {
         const int64_t cA = c0 + (int64_t)lane * V;
         const int64_t cB = cA + STEP;
         TE eA[R][V], eB[R][V];
