@@ -358,9 +358,9 @@ XC_API int64_t xc_bca_delta_stride(int64_t m);
  * xc_bca_delta_stride(m) bytes each: in the window's payload, or `delta` when w is NULL; all zero before the
  * first call, never touched by the host afterwards.  batch0: number of batches of all earlier calls on these
  * buffers (the rotation continues across sweeps).
- * lag = 0: strict order K_0, commit_0, K_1, ... on `stream`.  lag = 1: batch g sees the state after commit
- * g - 2; consecutive batch kernels run concurrently on two internal streams, every commit overlaps the next
- * batch's streaming, and the pipeline keeps running ACROSS calls: a sweep only waits for the previous sweep's
+ * lag = 0: strict order K_0, commit_0, K_1, ... on `stream`.  lag = L (1..3): batch g sees the state after commit
+ * g - L - 1; L + 1 consecutive batch kernels run concurrently on as many internal streams, every commit overlaps
+ * the other batches' streaming, and the pipeline keeps running ACROSS calls: a sweep only waits for the previous sweep's
  * batch kernels, the previous sweep's utility is computed behind its last commit, and `stream` is made to wait
  * for that utility only.  XC_PIPE_FORK (or the first call, or a call after xc_bca_pipe_join) re-synchronises with
  * `stream` first and recomputes every coefficient set from tp/fp/fn (needed after the host changed the state or

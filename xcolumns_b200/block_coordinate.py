@@ -39,8 +39,12 @@ _AUTO_EXACT_MAX_ROWS = 4096
 
 def _default_lag() -> int:
     """Commits applied this many batches late in the pipelined dense sweep (csrc/bca_batched.cu:
-    xc_bca_sweep_dense_pipe); $XCOLUMNS_B200_LAG=0 restores the strict batch order."""
-    return 0 if os.environ.get("XCOLUMNS_B200_LAG", "1") == "0" else 1
+    xc_bca_pipe_sweep): lag + 1 batches are in flight on as many streams; $XCOLUMNS_B200_LAG=0 restores the
+    strict batch order, values up to 3 are accepted."""
+    try:
+        return max(0, min(3, int(os.environ.get("XCOLUMNS_B200_LAG", "1"))))
+    except ValueError:
+        return 1
 
 
 def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n_rows=None, mix=None) -> MetricParams:
@@ -151,8 +155,8 @@ class BcaSession:
         self._order2: Optional[torch.Tensor] = None
         self._snaps: List[torch.Tensor] = []
         self.colsum: Optional[torch.Tensor] = None
-        # [set][coef_n | coef_s][label][B, A]: set 1 is the second coefficient version of the pipelined sweep
-        self.coef = torch.zeros((2, 2, clen, 2), dtype=torch.float32, device=self.device)
+        # [set][coef_n | coef_s][label][B, A]: one coefficient version per batch in flight of the pipelined sweep
+        self.coef = torch.zeros((self.lag + 1, 2, clen, 2), dtype=torch.float32, device=self.device)
         self.coef_n, self.coef_s = self.coef[0, 0], self.coef[0, 1]
         self.rec = torch.zeros((clen, 4), dtype=torch.float32, device=self.device) if self.use_rec else None
         self.util_buf = torch.zeros(8, **f64)

@@ -69,12 +69,12 @@ extern "C" void xc_ctx_destroy(xc_ctx *ctx)
     if (ctx->red_partials) cudaFree(ctx->red_partials);
     if (ctx->red_counter) cudaFree(ctx->red_counter);
     if (ctx->aux_ready) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) {
             cudaStreamDestroy(ctx->aux[i]);
-            cudaEventDestroy(ctx->ev_commit[i]);
             cudaEventDestroy(ctx->ev_join[i]);
             cudaEventDestroy(ctx->ev_k[i]);
         }
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->ev_commit[i]);
         cudaEventDestroy(ctx->ev_fork);
         cudaEventDestroy(ctx->ev_pro);
         cudaEventDestroy(ctx->ev_util);
@@ -148,12 +148,12 @@ int xc_ctx_aux_streams(xc_ctx *ctx)
     if (ctx->aux_ready) return XC_OK;
     int lo = 0, hi = 0;
     XC_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) {
         XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, hi));
-        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_commit[i], cudaEventDisableTiming));
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; ++i) XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_commit[i], cudaEventDisableTiming));
     XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_pro, cudaEventDisableTiming));
     XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_util, cudaEventDisableTiming));

@@ -1155,13 +1155,16 @@ int dense_rows_per_warp(int64_t m)
     return 4;
 }
 
-// $XCOLUMNS_B200_DENSE_DEEP=0 disables the deep-prefetch variant for sub-wave batches
+// $XCOLUMNS_B200_DENSE_DEEP=1 selects the deep-prefetch variant for sub-wave batches.  Measured on B200 at the
+// 8-GPU shard shape (38 375 rows x 13 000, 8 commits, pipelined): 0.452 ms per sweep against 0.400 ms for the
+// standard kernel -- four of its CTAs fill an SM's register file, so the NEXT batch's CTAs cannot move in
+// while this batch drains, which costs more than the deeper loads gain.  It stays opt-in.
 bool dense_deep_ok()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("XCOLUMNS_B200_DENSE_DEEP");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
 }
@@ -1650,7 +1653,7 @@ int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *se
 
 static_assert(sizeof(xc_bca_pipe_args) == 192, "xc_bca_pipe_args layout (mirrored by ctypes in _lib.py)");
 
-extern "C" int xc_bca_pipe_buffers(int lag) { return 2 * ((lag > 0 ? 1 : 0) + 1); }
+extern "C" int xc_bca_pipe_buffers(int lag) { return 2 * ((lag < 0 ? 0 : (lag > XC_PIPE_MAX_LAG ? XC_PIPE_MAX_LAG : lag)) + 1); }
 
 // the caller's stream waits for everything the pipeline still has in flight (before the host reads or rewrites
 // the prediction / the state: recompute, roll-back, end of the call)
@@ -1660,7 +1663,7 @@ extern "C" int xc_bca_pipe_join(xc_ctx *ctx, void *stream)
     if (!ctx) return XC_ERR_INVALID;
     if (!ctx->pipe_active) return XC_OK;
     if (ctx->pipe_forked) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < XC_PIPE_MAX_LAG + 1; ++i) {
             XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
             XC_CUDA_TRY(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_join[i], 0));
         }
@@ -1687,15 +1690,16 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
     if (a->util_out && !a->util_params) return XC_ERR_INVALID;
     const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;
     if (rec && p->metric != XC_METRIC_JACCARD && p->skip_tn) return XC_ERR_INVALID;
-    int lag = a->lag;
+    int lag = a->lag < 0 ? 0 : (a->lag > XC_PIPE_MAX_LAG ? XC_PIPE_MAX_LAG : a->lag);
     if (rec) lag = 0;   // the record kernels read the float64 state of the selected labels: no overlap with a commit
-    const int S = (lag > 0 ? 1 : 0) + 1, NB = 2 * S;
+    const int S = lag + 1, NB = 2 * S;   // S batches in flight on S streams, S coefficient sets, 2 S delta buffers
     const int64_t stride = xc_bca_delta_stride(m), clen = xc_bca_coef_len(m);
     if (w && (size_t)(XC_P2P_HEADER + NB * stride) > w->bytes) return XC_ERR_INVALID;
     cudaStream_t caller = (cudaStream_t)stream;
     double *local = w ? reinterpret_cast<double *>(w->windows[w->rank] + XC_P2P_HEADER) : a->delta;
     PipeCommit c{ctx, w, p, a->tp, a->fp, a->fn, local, (int64_t)XC_P2P_HEADER, stride, m, rec ? 1 : 0};
-    float *set[2] = {a->coef, a->coef + 4 * clen};
+    float *set[XC_PIPE_MAX_LAG + 1];
+    for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) set[i] = a->coef + (int64_t)(i < S ? i : 0) * 4 * clen;
     // $XCOLUMNS_B200_PIPE_SERIAL=1 (tests): the same dependency order on ONE stream, nothing overlaps
     const bool serial = getenv("XCOLUMNS_B200_PIPE_SERIAL") && atoi(getenv("XCOLUMNS_B200_PIPE_SERIAL")) == 1;
     const bool forked = S > 1 && !serial;
@@ -1710,18 +1714,20 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             if (rc) return rc;
         }
         // coefficients of the state the caller hands over, for every set
-        rc = launch_commit(c, -1, -1, set[0], S > 1 ? set[1] : nullptr, clen, caller);
-        if (rc) return rc;
+        for (int i = 0; i < S; i += 2) {
+            rc = launch_commit(c, -1, -1, set[i], i + 1 < S ? set[i + 1] : nullptr, clen, caller);
+            if (rc) return rc;
+        }
     }
-    cudaStream_t st[2] = {caller, caller};
+    cudaStream_t st[XC_PIPE_MAX_LAG + 1];
+    for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) st[i] = caller;
     if (forked) {
         rc = xc_ctx_aux_streams(ctx);
         if (rc) return rc;
-        st[0] = ctx->aux[0];
-        st[1] = ctx->aux[1];
+        for (int i = 0; i < S; ++i) st[i] = ctx->aux[i];
         if (fresh) {
             XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, caller));
-            for (int i = 0; i < 2; ++i) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_fork, 0));
+            for (int i = 0; i < S; ++i) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_fork, 0));
             ctx->pipe_commits = 0;
         }
     }
@@ -1729,7 +1735,9 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
     ctx->pipe_forked = forked;
     // ---- prologue on the stream of the sweep's first batch: order + snapshot, after the previous sweep's kernels
     const int s0 = (int)(a->batch0 % S);
-    if (forked && !fresh) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[s0 ^ 1], 0));
+    if (forked && !fresh)
+        for (int i = 0; i < S; ++i)
+            if (i != s0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[i], 0));
     const int32_t *order = a->order + ((a->flags & XC_PIPE_SHUFFLE) ? (a->sweep & 1) * n_order : 0);
     if ((a->flags & XC_PIPE_SHUFFLE) && n_order > 0) {
         rc = xc_permutation(ctx, n_order, a->seed, const_cast<int32_t *>(order), st[s0]);
@@ -1740,7 +1748,8 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
                                          cudaMemcpyDeviceToDevice, st[s0]));
     if (forked) {
         XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pro, st[s0]));
-        XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0 ^ 1], ctx->ev_pro, 0));
+        for (int i = 0; i < S; ++i)
+            if (i != s0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_pro, 0));
     }
     // ---- batches
     int last_si = s0;

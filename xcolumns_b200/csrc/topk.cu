@@ -103,6 +103,131 @@ scatter_pred_kernel(const int32_t *__restrict__ pred_idx, const TV *__restrict__
     }
 }
 
+// ---- k > 32: one CTA per row, radix select -------------------------------------------------------------------
+// The warp-list kernels hold the running top-k in 32 lanes.  Larger k (the sparsifier of the on-disk formats keeps
+// the top 100 - 1000 scores of a row, experiments/utils.py:199-211) selects by value instead: the k-th largest
+// gain of the row is found digit by digit (11-bit histograms in shared memory over an order-preserving integer
+// image of the gain), then one ordered pass writes every label above it plus, for ties at the threshold, the
+// lowest label ids -- in ascending label order, the compact-prediction layout.  The row is read once from HBM and
+// then from L2 (a row is at most a few hundred KB).
+constexpr int kSelThreads = 512;
+constexpr int kSelDigit = 11;
+constexpr int kSelBins = 1 << kSelDigit;
+
+__device__ __forceinline__ uint32_t sel_key(float g)
+{
+    const uint32_t u = __float_as_uint(g + 0.0f);
+    if (g != g) return 0u;   // NaN sorts last
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t sel_key(double g)
+{
+    const uint64_t u = (uint64_t)__double_as_longlong(g + 0.0);
+    if (g != g) return 0ull;
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+template <typename G> struct SelKey;
+template <> struct SelKey<float> { using type = uint32_t; static constexpr int bits = 32; };
+template <> struct SelKey<double> { using type = uint64_t; static constexpr int bits = 64; };
+
+// inclusive block scan of one int per thread (kSelThreads threads); returns the block total in *total
+__device__ __forceinline__ int sel_block_scan(int v, int *warp_sums, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(XC_FULL, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < kSelThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(XC_FULL, w, o);
+            if (lane >= o) w += y;
+        }
+        if (lane < kSelThreads / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[kSelThreads / 32 - 1];
+    __syncthreads();   // warp_sums is reused by the next scan
+    return base + x;
+}
+
+template <typename TE, typename G>
+__global__ void __launch_bounds__(kSelThreads)
+topk_select_kernel(const TE *__restrict__ eta, int64_t n_rows, int64_t m, int64_t ld, const int32_t *__restrict__ rows,
+                   XfMulAdd<G> xf, int k, int32_t *__restrict__ out_idx, G *__restrict__ out_val)
+{
+    using Key = typename SelKey<G>::type;
+    __shared__ int hist[kSelBins];
+    __shared__ int warp_sums[kSelThreads / 32];
+    __shared__ Key s_prefix;
+    __shared__ int s_need;
+    for (int64_t i = blockIdx.x; i < n_rows; i += gridDim.x) {
+        const int64_t row = rows ? (int64_t)rows[i] : i;
+        const TE *rp = eta + row * ld;
+        // ---- the k-th largest key, one digit per pass
+        Key prefix = 0, known = 0;   // `known`: mask of the digits fixed so far
+        int need = k;                // how many of the elements matching the prefix are still wanted
+        for (int shift = SelKey<G>::bits - kSelDigit; ; shift -= kSelDigit) {
+            const int sh = shift < 0 ? 0 : shift;
+            const int width = shift < 0 ? kSelDigit + shift : kSelDigit;   // the last digit may be narrower
+            for (int b = threadIdx.x; b < kSelBins; b += kSelThreads) hist[b] = 0;
+            __syncthreads();
+            for (int64_t c = threadIdx.x; c < m; c += kSelThreads) {
+                const Key key = sel_key(xf.template apply_one<TE>(c, rp[c]));
+                if ((key & known) == prefix) atomicAdd(&hist[(int)((key >> sh) & (Key)((1 << width) - 1))], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {   // walk the bins from the top: 2048 adds, negligible next to the pass over the row
+                int acc = 0, d = (1 << width) - 1;
+                for (; d > 0; --d) {
+                    if (acc + hist[d] >= need) break;
+                    acc += hist[d];
+                }
+                s_prefix = prefix | ((Key)d << sh);
+                s_need = need - acc;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            need = s_need;
+            known |= (Key)((1 << width) - 1) << sh;
+            __syncthreads();
+            if (sh == 0) break;
+        }
+        // prefix is now the exact key of the k-th largest gain; `need` of the elements equal to it are taken
+        // ---- ordered output: labels ascending
+        int written = 0, eq_seen = 0;
+        for (int64_t c0 = 0; c0 < m; c0 += kSelThreads) {
+            const int64_t c = c0 + threadIdx.x;
+            G g = (G)0;
+            Key key = 0;
+            if (c < m) {
+                g = xf.template apply_one<TE>(c, rp[c]);
+                key = sel_key(g);
+            }
+            const int is_eq = (c < m && key == prefix) ? 1 : 0;
+            int tot_eq;
+            const int eq_rank = eq_seen + sel_block_scan(is_eq, warp_sums, &tot_eq) - is_eq;
+            const int take = (c < m && (key > prefix || (is_eq && eq_rank < need))) ? 1 : 0;
+            int tot_take;
+            const int pos = written + sel_block_scan(take, warp_sums, &tot_take) - take;
+            if (take && pos < k) {
+                out_idx[i * k + pos] = (int32_t)c;
+                if (out_val) out_val[i * k + pos] = g;
+            }
+            written += tot_take;
+            eq_seen += tot_eq;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename K>
 int grid_for(xc_ctx *ctx, K kernel, int64_t work_warps)
 {
@@ -166,9 +291,25 @@ extern "C" int xc_topk_dense(xc_ctx *ctx, const void *eta, int eta_dtype, int64_
 {
     XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !eta || !out_idx || n_rows < 0 || m <= 0 || ld < m) return XC_ERR_INVALID;
-    if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
+    if (k < 1 || k > m) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (k > 32) {   // one CTA per row, radix select (any k <= m)
+        if (m > 0x7fffffffLL) return XC_ERR_UNSUPPORTED;
+        const int64_t cap = (int64_t)ctx->sm_count * 4;
+        const int grid = (int)(n_rows < cap ? n_rows : cap);
+#define XC_SEL(TE, G)                                                                                              \
+    topk_select_kernel<TE, G><<<grid, kSelThreads, 0, st>>>((const TE *)eta, n_rows, m, ld, rows,                     \
+                                                            XfMulAdd<G>{(const G *)a, (const G *)b}, k, out_idx,    \
+                                                            (G *)out_val)
+        if (eta_dtype == XC_F32 && g_dtype == XC_F32) XC_SEL(float, float);
+        else if (eta_dtype == XC_F32 && g_dtype == XC_F64) XC_SEL(float, double);
+        else if (eta_dtype == XC_F64 && g_dtype == XC_F64) XC_SEL(double, double);
+        else return XC_ERR_UNSUPPORTED;
+#undef XC_SEL
+        XC_LAUNCHED(ctx);
+        return XC_OK;
+    }
     if (eta_dtype == XC_F32 && g_dtype == XC_F32)
         return launch_topk_dense<float, float>(ctx, eta, n_rows, m, ld, rows, a, b, k, out_idx, out_val, st);
     if (eta_dtype == XC_F32 && g_dtype == XC_F64)

@@ -5,6 +5,8 @@
 
 #include "../../include/xcolumns_b200.h"
 
+constexpr int XC_PIPE_MAX_LAG = 3;   // pipelined sweeps: at most 4 batches in flight
+
 struct xc_ctx {
     int device;
     int sm_count;
@@ -18,8 +20,8 @@ struct xc_ctx {
     double *red_partials;
     unsigned *red_counter;
     // pipelined batched sweep (bca_batched.cu): two internal streams + ordering events, created on first use
-    cudaStream_t aux[2];
-    cudaEvent_t ev_fork, ev_commit[2], ev_join[2], ev_k[2], ev_pro, ev_util;
+    cudaStream_t aux[XC_PIPE_MAX_LAG + 1];
+    cudaEvent_t ev_fork, ev_commit[2], ev_join[XC_PIPE_MAX_LAG + 1], ev_k[XC_PIPE_MAX_LAG + 1], ev_pro, ev_util;
     bool aux_ready;
     bool pipe_active;            // sweeps issued since the last join: the coefficient sets follow the commits
     bool pipe_forked;            // ... on the internal streams (work the caller's stream has not joined yet)

@@ -23,10 +23,12 @@ from .types import DenseMatrix, DType, Matrix
 _MAX_K = 32
 
 
-def _check_k(k):
+def _check_k(k, limit: Optional[int] = _MAX_K):
+    """k is an int; the warp-list kernels (BCA, Frank-Wolfe, CSR top-k) hold k <= 32 labels, the dense weighted
+    top-k takes any k <= m (block-level radix select beyond 32)."""
     if not isinstance(k, int) or isinstance(k, bool):
         raise ValueError("k must be an integer")
-    if k > _MAX_K:
+    if limit is not None and k > limit:
         raise NotImplementedError(f"xcolumns_b200 kernels support k <= {_MAX_K}, got k={k}")
 
 
@@ -88,7 +90,7 @@ def predict_weighted_per_instance(
         y_proba = y_proba.reshape(1, -1)
     elif len(y_proba.shape) > 2:
         raise ValueError("y_proba must be 1d or 2d")
-    _check_k(k)
+    _check_k(k, _MAX_K if isinstance(y_proba, csr_matrix) else None)
     n, m = y_proba.shape
     for name, v in (("a", a), ("b", b)):
         if v is not None:
