@@ -379,10 +379,12 @@ typedef struct {
     int32_t flags;            /* XC_PIPE_*                                                                     */
     uint64_t seed;            /* XC_PIPE_SHUFFLE: visiting order = xc_permutation(n_rows, seed), ref :419      */
     int64_t sweep;            /* sweep counter: with XC_PIPE_SHUFFLE the order lives in order + (sweep & 1) * n_rows */
-    int32_t *order;           /* 2 * n_rows int32 with XC_PIPE_SHUFFLE (scratch), else the n_rows visiting order */
+    int32_t *order;           /* XC_PIPE_SHUFFLE: 4 * n_rows int32 of scratch [order A | order B | scratch |      */
+                              /* stamps, zero before the first call]; else the n_rows visiting order              */
     float *coef;              /* (lag + 1) sets of 4 * xc_bca_coef_len(m) floats, each [coef_n | coef_s] (or records) */
     int32_t *pred_idx;        /* [n_rows, k], rewritten                                                        */
-    int32_t *pred_snapshot;   /* optional: copy of pred_idx as it was BEFORE this sweep (roll-back)            */
+    int32_t *pred_snapshot;   /* optional [n_rows, k]: every visited row's selection as it was BEFORE this sweep */
+                              /* (written by the batch kernels; complete when the sweep is; roll-back)           */
     double *tp, *fp, *fn;     /* replicated float64 state                                                     */
     double *delta;            /* w == NULL: the NB delta buffers                                               */
     const xc_metric_params *util_params;  /* optional: utility of the state after this sweep (ref :468-476) -> */
@@ -390,6 +392,10 @@ typedef struct {
     int32_t agg;              /* 0 mean, 1 sum                                                                 */
     int32_t reserved;
     double util_tn_rows;      /* >= 0: tn = -tp - fp - fn + util_tn_rows inside the utility; < 0: tn = -1     */
+    int64_t prev_tail_from;   /* position in the PREVIOUS sweep's order where its last `lag` batches begin, -1:   */
+                              /* unknown.  With XC_PIPE_SHUFFLE and a known tail the new order is repaired so    */
+                              /* that its first `lag` batches avoid those rows and the sweeps overlap without a  */
+                              /* drain; otherwise the new sweep's kernels wait for the previous sweep's.          */
 } xc_bca_pipe_args;
 XC_API int xc_bca_pipe_buffers(int lag);
 XC_API int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args *a, void *stream);

@@ -152,6 +152,6 @@ def test_dense_output_prefill_host_side(monkeypatch):
 
 def test_pipe_args_layout():
     from xcolumns_b200 import _lib
-    assert C.sizeof(_lib.PipeArgs) == 192   # static_assert'ed on the C side (csrc/bca_batched.cu)
+    assert C.sizeof(_lib.PipeArgs) == 200   # static_assert'ed on the C side (csrc/bca_batched.cu)
     assert _lib.PipeArgs.seed.offset == 80 and _lib.PipeArgs.order.offset == 96
     assert _lib.PipeArgs.delta.offset == 152 and _lib.PipeArgs.util_tn_rows.offset == 184

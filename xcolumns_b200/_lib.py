@@ -43,7 +43,7 @@ class PipeArgs(C.Structure):
                 ("order", C.c_void_p), ("coef", C.c_void_p), ("pred_idx", C.c_void_p), ("pred_snapshot", C.c_void_p),
                 ("tp", C.c_void_p), ("fp", C.c_void_p), ("fn", C.c_void_p), ("delta", C.c_void_p),
                 ("util_params", _MP), ("util_out", C.c_void_p), ("agg", C.c_int32), ("reserved", C.c_int32),
-                ("util_tn_rows", C.c_double)]
+                ("util_tn_rows", C.c_double), ("prev_tail_from", C.c_int64)]
 
 # name -> argtypes (after ctx); every function returns int unless listed in _RESTYPES
 _SIGNATURES = {

@@ -152,6 +152,7 @@ class BcaSession:
         self._n_order = self.n          # rows a sweep visits (1 with the reference's normalize_conf_matrix=False quirk)
         self._inflight = False          # the pipeline's internal streams hold work this stream has not joined
         self._need_fork = True          # the host touched the state / prediction since the last pipelined sweep
+        self._prev_tail_from = -1
         self._order2: Optional[torch.Tensor] = None
         self._snaps: List[torch.Tensor] = []
         self.colsum: Optional[torch.Tensor] = None
@@ -291,28 +292,31 @@ class BcaSession:
         if self.pipe:
             d = self.data
             if self._order2 is None:
-                self._order2 = torch.arange(self._n_order, dtype=torch.int32, device=self.device).repeat(2)
+                # [order A | order B | scratch | stamps]; without shuffling the first n entries are the order
+                self._order2 = torch.zeros(4 * self._n_order, dtype=torch.int32, device=self.device)
+                self._order2[:self._n_order] = torch.arange(self._n_order, dtype=torch.int32, device=self.device)
                 self._snaps = [torch.empty_like(self.pred) for _ in range(3)]
             snap = self._snaps[j % 3]
-            snap_ptr = snap.data_ptr()
-            if self._n_order != self.n:      # only the visited rows are copied by the call: take a whole copy here
+            if self._n_order != self.n:      # only the visited rows are written by the kernels: take a whole copy first
                 self.join()
                 snap.copy_(self.pred)
-                snap_ptr = None
             nb = n_batches if n_batches is not None else (self._n_order + batch - 1) // batch
             flags = (XC_PIPE_SHUFFLE if shuffle else 0) | (XC_PIPE_FORK if self._need_fork else 0)
             a = PipeArgs(params=C.pointer(self.p), eta=d.t.data_ptr(), dtype=d.code, k=self.k, m=d.m, ld=d.ld,
                          n_rows=self._n_order, batch=int(batch), n_batches=int(nb), batch0=int(self._gb), lag=int(self.lag),
                          flags=flags, seed=seed & 0xFFFFFFFFFFFFFFFF, sweep=j, order=self._order2.data_ptr(),
                          coef=(self.rec if self.use_rec else self.coef).data_ptr(), pred_idx=self.pred.data_ptr(),
-                         pred_snapshot=snap_ptr, tp=self.state[0].data_ptr(), fp=self.state[1].data_ptr(),
+                         pred_snapshot=snap.data_ptr(), tp=self.state[0].data_ptr(), fp=self.state[1].data_ptr(),
                          fn=self.state[2].data_ptr(),
                          delta=self.delta_pipe.data_ptr() if self.delta_pipe is not None else None,
                          util_params=C.pointer(self.up), util_out=util_out.data_ptr(), agg=self.agg, reserved=0,
-                         util_tn_rows=-1.0 if self.p.skip_tn else float(self.comm.n_global(self.n)))
+                         util_tn_rows=-1.0 if self.p.skip_tn else float(self.comm.n_global(self.n)),
+                         prev_tail_from=-1 if self._need_fork else int(self._prev_tail_from))
             self.ctx.call("xc_bca_pipe_sweep", self.peer.handle if self.peer is not None else None, C.byref(a), self._s())
             self._gb += nb
             self._inflight, self._need_fork = True, False
+            # where this sweep's last `lag` batches begin in its order (the next sweep's first batches avoid them)
+            self._prev_tail_from = min(self._n_order, max(0, (nb - self.lag) * int(batch))) if shuffle else -1
             if full or os.environ.get("XCOLUMNS_B200_SWEEP_RECOMPUTE") == "1":
                 self.recompute(XC_SUM_FAST)       # joins; the next sweep re-forks and refreshes its coefficients
                 self.utility_into(util_out)

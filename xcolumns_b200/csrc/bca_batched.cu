@@ -244,7 +244,8 @@ template <typename TE, int R, bool DEEP = false>
 __global__ void __launch_bounds__(kThreads, DEEP ? 4 : ((R == 1 && sizeof(TE) == 4) ? 6 : 1))
 bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const int32_t *__restrict__ rows,
                        int64_t n_rows, int k, const float2 *__restrict__ coef_n, const float2 *__restrict__ coef_s,
-                       int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn, bool vec_ok)
+                       int32_t *__restrict__ pred_idx, double *dtp, double *dfp, double *dfn, bool vec_ok,
+                       int32_t *__restrict__ snap)
 {
     const int lane = lane_id();
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -269,6 +270,9 @@ bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
             float g = 0.f;
             if (lane < k) {
                 old_j[r] = pred_idx[row * k + lane];
+                // the row's selection BEFORE this sweep, kept for roll-backs (every row is visited once per sweep,
+                // so the snapshot is complete when the sweep is)
+                if (snap && valid) snap[row * k + lane] = old_j[r];
                 if (old_j[r] >= 0) {
                     old_e[r] = rp[r][old_j[r]];
                     float2 cs = __ldg(coef_s + old_j[r]);
@@ -377,7 +381,7 @@ bca_batch_dense_rec_kernel(xc_metric_params p, const TE *__restrict__ eta, int64
                            const int32_t *__restrict__ rows, int64_t n_rows, int k, const float4 *__restrict__ rec,
                            const double *__restrict__ tp, const double *__restrict__ fp,
                            const double *__restrict__ fn, int32_t *__restrict__ pred_idx, double *dtp, double *dfp,
-                           double *dfn, bool vec_ok)
+                           double *dfn, bool vec_ok, int32_t *__restrict__ snap)
 {
     const int lane = lane_id();
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -392,6 +396,7 @@ bca_batch_dense_rec_kernel(xc_metric_params p, const TE *__restrict__ eta, int64
         float g = 0.f;
         if (lane < k) {
             old_j[0] = pred_idx[row * k + lane];
+            if (snap) snap[row * k + lane] = old_j[0];
             if (old_j[0] >= 0) {
                 const int j = old_j[0];
                 old_e = rp[0][j];
@@ -1201,11 +1206,11 @@ int launch_batch_dense_tma(xc_ctx *ctx, const float *eta, int64_t m, int64_t ld,
 template <typename TE>
 int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, const int32_t *rows, int64_t n_rows, int k,
                        const float *coef_n, const float *coef_s, int32_t *pred_idx, double *dtp, double *dfp,
-                       double *dfn, cudaStream_t st)
+                       double *dfn, cudaStream_t st, int32_t *snap = nullptr)
 {
     constexpr int V = 16 / sizeof(TE);
     bool vec_ok = xc_aligned16(eta) && (ld % V == 0) && xc_aligned16(coef_n);
-    if (sizeof(TE) == 4 && vec_ok && dense_path_override() != 1) {
+    if (sizeof(TE) == 4 && vec_ok && dense_path_override() != 1 && !snap) {
         // the coefficient tile is copied in whole TMA_TC units: needs the padded coefficient
         // arrays the host shim allocates (xc_bca_coef_len)
         // Measured (profiles/r01_notes.md): the TMA ring keeps 200 KB / SM in flight but its 8
@@ -1220,7 +1225,7 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
         auto kern = bca_batch_dense_kernel<TE, R>;                                                            \
         int grid = grid_for(ctx, kern, (n_rows + R - 1) / R);                                                 \
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, m, ld, rows, n_rows, k, (const float2 *)coef_n,      \
-                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok);             \
+                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok, snap);       \
     }
     const int rr = dense_rows_per_warp(m);
     if (rr == 4) XC_GO(4)
@@ -1232,7 +1237,7 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
         auto kern = bca_batch_dense_kernel<TE, 1, true>;
         int grid = grid_for(ctx, kern, n_rows);
         kern<<<grid, kThreads, 0, st>>>((const TE *)eta, m, ld, rows, n_rows, k, (const float2 *)coef_n,
-                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok);
+                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok, snap);
     }
     else XC_GO(1)
 #undef XC_GO
@@ -1290,12 +1295,11 @@ extern "C" int xc_bca_rec(xc_ctx *ctx, const xc_metric_params *p, double *tp, do
     return XC_OK;
 }
 
-extern "C" int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype, int64_t m,
-                                      int64_t ld, const int32_t *rows, int64_t n_rows, int k, const float *rec,
-                                      const double *tp, const double *fp, const double *fn, int32_t *pred_idx,
-                                      double *dtp, double *dfp, double *dfn, void *stream)
+static int batch_dense_rec_impl(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype, int64_t m,
+                                int64_t ld, const int32_t *rows, int64_t n_rows, int k, const float *rec,
+                                const double *tp, const double *fp, const double *fn, int32_t *pred_idx, double *dtp,
+                                double *dfp, double *dfn, void *stream, int32_t *snap)
 {
-    XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !p || !eta || !rec || !tp || !fp || !fn || !pred_idx || !dtp || !dfp || !dfn || m <= 0 || ld < m ||
         n_rows < 0)
         return XC_ERR_INVALID;
@@ -1311,7 +1315,7 @@ extern "C" int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, co
         auto kern = bca_batch_dense_rec_kernel<TE, METRIC>;                                                      \
         int grid = grid_for(ctx, kern, n_rows);                                                                  \
         kern<<<grid, kThreads, 0, st>>>(*p, (const TE *)eta, m, ld, rows, n_rows, k, (const float4 *)rec, tp, fp, \
-                                        fn, pred_idx, dtp, dfp, dfn, vec_ok);                                    \
+                                        fn, pred_idx, dtp, dfp, dfn, vec_ok, snap);                              \
     }
     if (dtype == XC_F32) {
         if (p->metric == XC_METRIC_JACCARD) XC_GO(float, XC_METRIC_JACCARD)
@@ -1329,23 +1333,40 @@ extern "C" int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, co
     return XC_OK;
 }
 
-extern "C" int64_t xc_bca_delta_stride(int64_t m) { return ((3 * m * 8 + 255) / 256) * 256; }
-
-extern "C" int xc_bca_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld, const int32_t *rows,
-                                  int64_t n_rows, int k, const float *coef_n, const float *coef_s, int32_t *pred_idx,
-                                  double *dtp, double *dfp, double *dfn, void *stream)
+extern "C" int xc_bca_batch_dense_rec(xc_ctx *ctx, const xc_metric_params *p, const void *eta, int dtype, int64_t m,
+                                      int64_t ld, const int32_t *rows, int64_t n_rows, int k, const float *rec,
+                                      const double *tp, const double *fp, const double *fn, int32_t *pred_idx,
+                                      double *dtp, double *dfp, double *dfn, void *stream)
 {
     XcDeviceGuard xc_guard__(ctx);
+    return batch_dense_rec_impl(ctx, p, eta, dtype, m, ld, rows, n_rows, k, rec, tp, fp, fn, pred_idx, dtp, dfp, dfn, stream,
+                                nullptr);
+}
+
+extern "C" int64_t xc_bca_delta_stride(int64_t m) { return ((3 * m * 8 + 255) / 256) * 256; }
+
+static int batch_dense_impl(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld, const int32_t *rows,
+                            int64_t n_rows, int k, const float *coef_n, const float *coef_s, int32_t *pred_idx,
+                            double *dtp, double *dfp, double *dfn, void *stream, int32_t *snap)
+{
     if (!ctx || !eta || !coef_n || !coef_s || !pred_idx || !dtp || !dfp || !dfn || m <= 0 || ld < m || n_rows < 0)
         return XC_ERR_INVALID;
     if (k < 1 || k > 32 || k > m) return XC_ERR_INVALID;
     if (n_rows == 0) return XC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == XC_F32)
-        return launch_batch_dense<float>(ctx, eta, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx, dtp, dfp, dfn, st);
+        return launch_batch_dense<float>(ctx, eta, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx, dtp, dfp, dfn, st, snap);
     if (dtype == XC_F64)
-        return launch_batch_dense<double>(ctx, eta, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx, dtp, dfp, dfn, st);
+        return launch_batch_dense<double>(ctx, eta, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx, dtp, dfp, dfn, st, snap);
     return XC_ERR_UNSUPPORTED;
+}
+
+extern "C" int xc_bca_batch_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t m, int64_t ld, const int32_t *rows,
+                                  int64_t n_rows, int k, const float *coef_n, const float *coef_s, int32_t *pred_idx,
+                                  double *dtp, double *dfp, double *dfn, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    return batch_dense_impl(ctx, eta, dtype, m, ld, rows, n_rows, k, coef_n, coef_s, pred_idx, dtp, dfp, dfn, stream, nullptr);
 }
 
 namespace {
@@ -1616,6 +1637,60 @@ extern "C" int xc_bca_sweep_csr(xc_ctx *ctx, const xc_metric_params *p, const vo
 // No host-side clearing, no race with a slower peer.
 namespace {
 
+// ---- no drain between sweeps ------------------------------------------------------------------------------------
+// When a new sweep starts, the previous sweep's last lag batches may still be streaming.  A row must not be visited
+// by two sweeps at once, so the new sweep's first batches must not contain rows of those batches.  Instead of
+// waiting for them (a drain: the tail of a batch kernel is a whole row time, ~50 us, every sweep), the new visiting
+// order is repaired: within its first `window` positions the rows that are still "busy" are moved behind the
+// others (stable partition), which puts them beyond the first lag batches -- behind at least one commit of the new
+// sweep, by which time the old sweep's kernels have retired.  Only which rows share a batch matters to a
+// block-Jacobi sweep, not the order inside a batch, and the order stays a permutation.
+// One CTA: stamp the busy rows, count, scan, scatter through a scratch buffer.
+constexpr int kFixThreads = 1024;
+__global__ void __launch_bounds__(kFixThreads)
+order_fix_kernel(int32_t *__restrict__ order, int64_t window, const int32_t *__restrict__ prev_order, int64_t prev_from,
+                 int64_t prev_to, int32_t *__restrict__ stamp, int32_t mark, int32_t *__restrict__ scratch)
+{
+    __shared__ int s_warp[kFixThreads / 32];
+    __shared__ int s_total;
+    for (int64_t i = prev_from + threadIdx.x; i < prev_to; i += kFixThreads) stamp[prev_order[i]] = mark;
+    __syncthreads();
+    const int64_t per = (window + kFixThreads - 1) / kFixThreads;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < window ? lo + per : window;
+    int free_cnt = 0;
+    for (int64_t i = lo; i < hi; ++i) free_cnt += stamp[order[i]] != mark;
+    // exclusive block scan of free_cnt
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = free_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(XC_FULL, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(XC_FULL, w, o);
+            if (lane >= o) w += y;
+        }
+        s_warp[lane] = w;
+        if (lane == 31) s_total = w;
+    }
+    __syncthreads();
+    int64_t free_pos = (wid ? s_warp[wid - 1] : 0) + x - free_cnt;          // free rows before my chunk
+    int64_t busy_pos = (int64_t)s_total + (lo - free_pos);                  // busy rows go behind all free ones
+    for (int64_t i = lo; i < hi; ++i) {
+        const int32_t r = order[i];
+        if (stamp[r] != mark) scratch[free_pos++] = r;
+        else scratch[busy_pos++] = r;
+    }
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < window; i += kFixThreads) order[i] = scratch[i];
+}
+
 struct PipeCommit {
     xc_ctx *ctx;
     xc_p2p *w;
@@ -1651,7 +1726,7 @@ int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *se
 
 }  // namespace
 
-static_assert(sizeof(xc_bca_pipe_args) == 192, "xc_bca_pipe_args layout (mirrored by ctypes in _lib.py)");
+static_assert(sizeof(xc_bca_pipe_args) == 200, "xc_bca_pipe_args layout (mirrored by ctypes in _lib.py)");
 
 extern "C" int xc_bca_pipe_buffers(int lag) { return 2 * ((lag < 0 ? 0 : (lag > XC_PIPE_MAX_LAG ? XC_PIPE_MAX_LAG : lag)) + 1); }
 
@@ -1733,19 +1808,32 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
     }
     ctx->pipe_active = true;
     ctx->pipe_forked = forked;
-    // ---- prologue on the stream of the sweep's first batch: order + snapshot, after the previous sweep's kernels
+    // ---- prologue on the stream of the sweep's first batch: the visiting order.  The previous sweep's last `lag`
+    // batch kernels may still run: either the new order is repaired so that its first batches avoid their rows
+    // (no drain, see order_fix_kernel), or this sweep's kernels wait for them.
     const int s0 = (int)(a->batch0 % S);
-    if (forked && !fresh)
-        for (int i = 0; i < S; ++i)
-            if (i != s0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[i], 0));
-    const int32_t *order = a->order + ((a->flags & XC_PIPE_SHUFFLE) ? (a->sweep & 1) * n_order : 0);
-    if ((a->flags & XC_PIPE_SHUFFLE) && n_order > 0) {
-        rc = xc_permutation(ctx, n_order, a->seed, const_cast<int32_t *>(order), st[s0]);
+    const bool shuffle = (a->flags & XC_PIPE_SHUFFLE) != 0;
+    int32_t *order = a->order + (shuffle ? (a->sweep & 1) * n_order : 0);
+    if (shuffle && n_order > 0) {
+        rc = xc_permutation(ctx, n_order, a->seed, order, st[s0]);
         if (rc) return rc;
     }
-    if (a->pred_snapshot && n_order > 0)
-        XC_CUDA_TRY(ctx, cudaMemcpyAsync(a->pred_snapshot, a->pred_idx, sizeof(int32_t) * (size_t)n_order * a->k,
-                                         cudaMemcpyDeviceToDevice, st[s0]));
+    if (!fresh && lag > 0) {   // (also in the serialised test schedule: the order is part of the algorithm)
+        const int64_t head = (int64_t)lag * a->batch, tail = a->prev_tail_from >= 0 ? n_order - a->prev_tail_from : -1;
+        const bool repair = shuffle && tail >= 0 && head + tail <= n_order && a->n_batches >= S;
+        if (repair) {
+            if (tail > 0) {
+                const int32_t *prev = a->order + ((a->sweep + 1) & 1) * n_order;
+                order_fix_kernel<<<1, kFixThreads, 0, st[s0]>>>(order, head + tail, prev, a->prev_tail_from, n_order,
+                                                               a->order + 3 * n_order, (int32_t)(a->sweep + 1),
+                                                               a->order + 2 * n_order);
+                XC_LAUNCHED(ctx);
+            }
+        } else if (forked) {
+            for (int i = 0; i < S; ++i)
+                if (i != s0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[i], 0));
+        }
+    }
     if (forked) {
         XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pro, st[s0]));
         for (int i = 0; i < S; ++i)
@@ -1767,10 +1855,10 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
                 if (rc) return rc;
                 XC_CUDA_TRY(ctx, cudaEventRecord(e0, st[si]));
             }
-            rc = rec ? xc_bca_batch_dense_rec(ctx, p, a->eta, a->dtype, m, a->ld, order + lo, hi - lo, a->k, set[si],
-                                              a->tp, a->fp, a->fn, a->pred_idx, d, d + m, d + 2 * m, st[si])
-                     : xc_bca_batch_dense(ctx, a->eta, a->dtype, m, a->ld, order + lo, hi - lo, a->k, set[si],
-                                          set[si] + 2 * clen, a->pred_idx, d, d + m, d + 2 * m, st[si]);
+            rc = rec ? batch_dense_rec_impl(ctx, p, a->eta, a->dtype, m, a->ld, order + lo, hi - lo, a->k, set[si], a->tp,
+                                            a->fp, a->fn, a->pred_idx, d, d + m, d + 2 * m, st[si], a->pred_snapshot)
+                     : batch_dense_impl(ctx, a->eta, a->dtype, m, a->ld, order + lo, hi - lo, a->k, set[si],
+                                        set[si] + 2 * clen, a->pred_idx, d, d + m, d + 2 * m, st[si], a->pred_snapshot);
             if (rc) return rc;
             if (e1) XC_CUDA_TRY(ctx, cudaEventRecord(e1, st[si]));
         }
