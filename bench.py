@@ -492,6 +492,10 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
             busy_ms = float(np.sum(busy))
             bytes_total = float(rows.sum()) * m * 4
             achieved = bytes_total / (busy_ms / 1e3) / 1e9
+            if os.environ.get("BENCH_DUMP_TIMELINE"):   # per-launch (start, end, rows) of the last timed sweep, ms
+                t0 = float(st[-per:].min())
+                res["timeline_last_sweep"] = [[round(float(a - t0), 4), round(float(b - t0), 4), int(r)]
+                                              for a, b, r in zip(st[-per:], en[-per:], rows[-per:])]
             res["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "bca_batch_dense_kernel<float,1>",
@@ -579,6 +583,8 @@ def main():
     }
     if parity is not None:
         line["parity_multi_gpu"] = parity
+    if "timeline_last_sweep" in res:
+        line["timeline_last_sweep"] = res["timeline_last_sweep"]
 
     # ---- end-to-end through the public API with host buffers (rank-local shard) ----------------
     if not args.no_e2e:

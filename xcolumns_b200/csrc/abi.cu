@@ -45,7 +45,6 @@ extern "C" int xc_ctx_create(int device, xc_ctx **out)
     ctx->aux_ready = false;
     ctx->pipe_active = false;
     ctx->pipe_forked = false;
-    ctx->pipe_commits = 0;
     ctx->timing_on = false;
     ctx->timing_count = ctx->timing_cap = 0;
     ctx->timing_ev = nullptr;
@@ -71,10 +70,11 @@ extern "C" void xc_ctx_destroy(xc_ctx *ctx)
     if (ctx->aux_ready) {
         for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) {
             cudaStreamDestroy(ctx->aux[i]);
-            cudaEventDestroy(ctx->ev_join[i]);
             cudaEventDestroy(ctx->ev_k[i]);
+            cudaEventDestroy(ctx->ev_c[i]);
         }
-        for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->ev_commit[i]);
+        for (int i = 0; i <= XC_PIPE_MAX_LAG + 1; ++i) cudaEventDestroy(ctx->ev_join[i]);
+        cudaStreamDestroy(ctx->cstream);
         cudaEventDestroy(ctx->ev_fork);
         cudaEventDestroy(ctx->ev_pro);
         cudaEventDestroy(ctx->ev_util);
@@ -148,12 +148,15 @@ int xc_ctx_aux_streams(xc_ctx *ctx)
     if (ctx->aux_ready) return XC_OK;
     int lo = 0, hi = 0;
     XC_CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // (cudaDeviceGetStreamPriorityRange: `lo` is the numerically greatest = lowest priority, `hi` the highest)
     for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) {
-        XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, hi));
-        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+        XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, lo));
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_c[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < 2; ++i) XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_commit[i], cudaEventDisableTiming));
+    for (int i = 0; i <= XC_PIPE_MAX_LAG + 1; ++i)
+        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->cstream, cudaStreamNonBlocking, hi));
     XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_pro, cudaEventDisableTiming));
     XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_util, cudaEventDisableTiming));

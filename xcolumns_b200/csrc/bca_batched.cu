@@ -1738,8 +1738,8 @@ extern "C" int xc_bca_pipe_join(xc_ctx *ctx, void *stream)
     if (!ctx) return XC_ERR_INVALID;
     if (!ctx->pipe_active) return XC_OK;
     if (ctx->pipe_forked) {
-        for (int i = 0; i < XC_PIPE_MAX_LAG + 1; ++i) {
-            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+        for (int i = 0; i <= XC_PIPE_MAX_LAG + 1; ++i) {
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join[i], i <= XC_PIPE_MAX_LAG ? ctx->aux[i] : ctx->cstream));
             XC_CUDA_TRY(ctx, cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev_join[i], 0));
         }
     }
@@ -1794,16 +1794,21 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             if (rc) return rc;
         }
     }
-    cudaStream_t st[XC_PIPE_MAX_LAG + 1];
+    // batch kernels: one low-priority stream per batch in flight; commits (and the sweep's utility): ONE
+    // high-priority stream -- they are serial anyway (the state is folded in batch order), and the priority lets a
+    // commit's few small CTAs be dispatched ahead of the pending CTAs of the batch kernels queued behind it (the
+    // hardware otherwise hands out CTAs grid by grid in launch order: measured, a commit waited a whole row time)
+    cudaStream_t st[XC_PIPE_MAX_LAG + 1], cst = caller;
     for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) st[i] = caller;
     if (forked) {
         rc = xc_ctx_aux_streams(ctx);
         if (rc) return rc;
         for (int i = 0; i < S; ++i) st[i] = ctx->aux[i];
+        cst = ctx->cstream;
         if (fresh) {
             XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, caller));
             for (int i = 0; i < S; ++i) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_fork, 0));
-            ctx->pipe_commits = 0;
+            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(cst, ctx->ev_fork, 0));
         }
     }
     ctx->pipe_active = true;
@@ -1840,7 +1845,6 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             if (i != s0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[i], ctx->ev_pro, 0));
     }
     // ---- batches
-    int last_si = s0;
     for (int64_t b = 0; b < a->n_batches; ++b) {
         const int64_t g = a->batch0 + b;
         const int si = (int)(g % S);
@@ -1862,32 +1866,31 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             if (rc) return rc;
             if (e1) XC_CUDA_TRY(ctx, cudaEventRecord(e1, st[si]));
         }
-        if (forked) {
-            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[si], st[si]));   // "the last batch kernel of this stream is done"
-            if (ctx->pipe_commits > 0)   // the state is folded in batch order
-                XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[si], ctx->ev_commit[(ctx->pipe_commits - 1) & 1], 0));
+        if (forked) {   // commit_g follows K_g (and, on its own stream, commit_{g-1})
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[si], st[si]));
+            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(cst, ctx->ev_k[si], 0));
         }
-        rc = launch_commit(c, cur, clr, set[si], nullptr, clen, st[si]);
+        rc = launch_commit(c, cur, clr, set[si], nullptr, clen, cst);
         if (rc) return rc;
-        last_si = si;
-        const bool last = b + 1 == a->n_batches;
-        if (last && a->util_out) {   // the finished sweep's utility, behind its last commit (the next commit waits for it)
-            rc = xc_utility_launch(ctx, a->util_params, a->agg, a->tp, a->fp, a->fn, nullptr, a->util_tn_rows, m,
-                                   a->util_out, st[si]);
-            if (rc) return rc;
+        if (forked) {   // K_{g+S}, the next kernel on this batch stream, follows commit_g
+            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_c[si], cst));
+            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[si], ctx->ev_c[si], 0));
         }
-        if (forked) {
-            XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_commit[ctx->pipe_commits & 1], st[si]));
-            ctx->pipe_commits += 1;
+        if (b + 1 == a->n_batches && a->util_out) {
+            // the finished sweep's utility, behind its last commit; the next sweep's first commit queues behind it on
+            // the commit stream, its batch kernels do not wait for it
+            rc = xc_utility_launch(ctx, a->util_params, a->agg, a->tp, a->fp, a->fn, nullptr, a->util_tn_rows, m,
+                                   a->util_out, cst);
+            if (rc) return rc;
         }
     }
     if (a->n_batches == 0 && a->util_out) {
         rc = xc_utility_launch(ctx, a->util_params, a->agg, a->tp, a->fp, a->fn, nullptr, a->util_tn_rows, m, a->util_out,
-                               st[last_si]);
+                               cst);
         if (rc) return rc;
     }
     if (forked) {   // the caller's stream sees the utility (and with it the state after the last commit), nothing else
-        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_util, st[last_si]));
+        XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_util, cst));
         XC_CUDA_TRY(ctx, cudaStreamWaitEvent(caller, ctx->ev_util, 0));
     }
     return XC_OK;

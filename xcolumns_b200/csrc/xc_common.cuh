@@ -20,12 +20,12 @@ struct xc_ctx {
     double *red_partials;
     unsigned *red_counter;
     // pipelined batched sweep (bca_batched.cu): two internal streams + ordering events, created on first use
-    cudaStream_t aux[XC_PIPE_MAX_LAG + 1];
-    cudaEvent_t ev_fork, ev_commit[2], ev_join[XC_PIPE_MAX_LAG + 1], ev_k[XC_PIPE_MAX_LAG + 1], ev_pro, ev_util;
+    cudaStream_t aux[XC_PIPE_MAX_LAG + 1];   // batch kernels, one stream per batch in flight (low priority)
+    cudaStream_t cstream;                    // commits + sweep utilities (high priority: dispatched ahead of pending batch CTAs)
+    cudaEvent_t ev_fork, ev_c[XC_PIPE_MAX_LAG + 1], ev_join[XC_PIPE_MAX_LAG + 2], ev_k[XC_PIPE_MAX_LAG + 1], ev_pro, ev_util;
     bool aux_ready;
     bool pipe_active;            // sweeps issued since the last join: the coefficient sets follow the commits
     bool pipe_forked;            // ... on the internal streams (work the caller's stream has not joined yet)
-    int64_t pipe_commits;        // commits issued since the fork (alternates ev_commit)
     // optional per-launch timing of the batch kernels (xc_timing_*): events in launch order
     bool timing_on;
     int timing_count, timing_cap;
