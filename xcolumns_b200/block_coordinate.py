@@ -153,6 +153,7 @@ class BcaSession:
         self._inflight = False          # the pipeline's internal streams hold work this stream has not joined
         self._need_fork = True          # the host touched the state / prediction since the last pipelined sweep
         self._prev_tail_from = -1
+        self._sweep_ctr = 0
         self._order2: Optional[torch.Tensor] = None
         self._snaps: List[torch.Tensor] = []
         self.colsum: Optional[torch.Tensor] = None
@@ -292,11 +293,12 @@ class BcaSession:
         if self.pipe:
             d = self.data
             if self._order2 is None:
-                # [order A | order B | scratch | stamps]; without shuffling the first n entries are the order
-                self._order2 = torch.zeros(4 * self._n_order, dtype=torch.int32, device=self.device)
+                # [order A | order B | raw order | stamps | counters]; without shuffling the first n entries are the order
+                self._order2 = torch.zeros(4 * self._n_order + 4, dtype=torch.int32, device=self.device)
                 self._order2[:self._n_order] = torch.arange(self._n_order, dtype=torch.int32, device=self.device)
                 self._snaps = [torch.empty_like(self.pred) for _ in range(3)]
             snap = self._snaps[j % 3]
+            self._sweep_ctr += 1             # consecutive calls: order-buffer parity and the busy-row stamps rely on it
             if self._n_order != self.n:      # only the visited rows are written by the kernels: take a whole copy first
                 self.join()
                 snap.copy_(self.pred)
@@ -304,7 +306,7 @@ class BcaSession:
             flags = (XC_PIPE_SHUFFLE if shuffle else 0) | (XC_PIPE_FORK if self._need_fork else 0)
             a = PipeArgs(params=C.pointer(self.p), eta=d.t.data_ptr(), dtype=d.code, k=self.k, m=d.m, ld=d.ld,
                          n_rows=self._n_order, batch=int(batch), n_batches=int(nb), batch0=int(self._gb), lag=int(self.lag),
-                         flags=flags, seed=seed & 0xFFFFFFFFFFFFFFFF, sweep=j, order=self._order2.data_ptr(),
+                         flags=flags, seed=seed & 0xFFFFFFFFFFFFFFFF, sweep=self._sweep_ctr, order=self._order2.data_ptr(),
                          coef=(self.rec if self.use_rec else self.coef).data_ptr(), pred_idx=self.pred.data_ptr(),
                          pred_snapshot=snap.data_ptr(), tp=self.state[0].data_ptr(), fp=self.state[1].data_ptr(),
                          fn=self.state[2].data_ptr(),

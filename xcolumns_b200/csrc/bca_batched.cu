@@ -248,8 +248,9 @@ bca_batch_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
                        int32_t *__restrict__ snap)
 {
     const int lane = lane_id();
-    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int wpc = (int)(blockDim.x >> 5);   // 8 warps per CTA, or 2 for launches of one row per warp (see launcher)
+    const int64_t warp = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * wpc;
     XfAffine xf{coef_n};
     for (int64_t grp = warp; grp * R < n_rows; grp += nwarps) {
         const TE *rp[R];
@@ -1174,6 +1175,17 @@ bool dense_deep_ok()
     return v == 1;
 }
 
+// $XCOLUMNS_B200_DENSE_SMALL_CTA=0: always 256-thread CTAs
+bool dense_small_cta_ok()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("XCOLUMNS_B200_DENSE_SMALL_CTA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // 0 = auto (LDG kernel), 1 = force the LDG kernel, 2 = force the TMA-ring kernel
 int dense_path_override()
 {
@@ -1224,8 +1236,16 @@ int launch_batch_dense(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, cons
     {                                                                                                         \
         auto kern = bca_batch_dense_kernel<TE, R>;                                                            \
         int grid = grid_for(ctx, kern, (n_rows + R - 1) / R);                                                 \
-        kern<<<grid, kThreads, 0, st>>>((const TE *)eta, m, ld, rows, n_rows, k, (const float2 *)coef_n,      \
-                                        (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok, snap);       \
+        int threads = kThreads;                                                                               \
+        if (R == 1 && dense_small_cta_ok() && (int64_t)grid * (kThreads / 32) >= n_rows) {                    \
+            /* one row per warp (a batch of at most one wave): a CTA holds its registers until its slowest */ \
+            /* warp is done, so 2-warp CTAs hand the SM's slots to the next batch's rows sooner than       */ \
+            /* 8-warp CTAs (rows differ in how often they touch their top-k list)                          */ \
+            threads = 64;                                                                                     \
+            grid = (int)((n_rows + 1) / 2);                                                                   \
+        }                                                                                                     \
+        kern<<<grid, threads, 0, st>>>((const TE *)eta, m, ld, rows, n_rows, k, (const float2 *)coef_n,       \
+                                       (const float2 *)coef_s, pred_idx, dtp, dfp, dfn, vec_ok, snap);        \
     }
     const int rr = dense_rows_per_warp(m);
     if (rr == 4) XC_GO(4)
@@ -1645,50 +1665,48 @@ namespace {
 // others (stable partition), which puts them beyond the first lag batches -- behind at least one commit of the new
 // sweep, by which time the old sweep's kernels have retired.  Only which rows share a batch matters to a
 // block-Jacobi sweep, not the order inside a batch, and the order stays a permutation.
-// One CTA: stamp the busy rows, count, scan, scatter through a scratch buffer.
-constexpr int kFixThreads = 1024;
-__global__ void __launch_bounds__(kFixThreads)
-order_fix_kernel(int32_t *__restrict__ order, int64_t window, const int32_t *__restrict__ prev_order, int64_t prev_from,
-                 int64_t prev_to, int32_t *__restrict__ stamp, int32_t mark, int32_t *__restrict__ scratch)
+// The raw permutation is generated into a scratch buffer; this kernel writes the sweep's order from it: positions
+// beyond the window are copied, positions inside are partitioned (free rows fill the window from the front, busy
+// rows from the back: two counters, one warp-aggregated atomic per warp, no scan -- the order inside the window
+// is irrelevant), and the rows of THIS sweep's last `lag` batches are stamped with the sweep's mark for the next
+// sweep's test (every row is handled by exactly one thread, which is the only one to read and write its stamp).
+__global__ void __launch_bounds__(256)
+order_fix_kernel(const int32_t *__restrict__ raw, int32_t *__restrict__ order, int64_t n, int64_t window,
+                 int32_t *__restrict__ stamp, int32_t prev_mark, int64_t tail_from, int32_t mark, int32_t *ctl)
 {
-    __shared__ int s_warp[kFixThreads / 32];
-    __shared__ int s_total;
-    for (int64_t i = prev_from + threadIdx.x; i < prev_to; i += kFixThreads) stamp[prev_order[i]] = mark;
-    __syncthreads();
-    const int64_t per = (window + kFixThreads - 1) / kFixThreads;
-    const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < window ? lo + per : window;
-    int free_cnt = 0;
-    for (int64_t i = lo; i < hi; ++i) free_cnt += stamp[order[i]] != mark;
-    // exclusive block scan of free_cnt
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int x = free_cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(XC_FULL, x, o);
-        if (lane >= o) x += y;
-    }
-    if (lane == 31) s_warp[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        int w = s_warp[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(XC_FULL, w, o);
-            if (lane >= o) w += y;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    const int32_t r = valid ? raw[i] : 0;
+    int64_t pos = i;
+    if ((int64_t)blockIdx.x * 256 < window) {   // block-uniform: this block holds window positions
+        const bool inw = valid && i < window;
+        const bool busy = inw && stamp[r] == prev_mark;
+        const unsigned mf = __ballot_sync(XC_FULL, inw && !busy), mb = __ballot_sync(XC_FULL, busy);
+        int bf = 0, bb = 0;
+        if (lane == 0) {
+            if (mf) bf = atomicAdd(ctl + 0, __popc(mf));
+            if (mb) bb = atomicAdd(ctl + 1, __popc(mb));
         }
-        s_warp[lane] = w;
-        if (lane == 31) s_total = w;
+        bf = __shfl_sync(XC_FULL, bf, 0);
+        bb = __shfl_sync(XC_FULL, bb, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (inw) pos = busy ? window - 1 - (bb + __popc(mb & below)) : bf + __popc(mf & below);
     }
-    __syncthreads();
-    int64_t free_pos = (wid ? s_warp[wid - 1] : 0) + x - free_cnt;          // free rows before my chunk
-    int64_t busy_pos = (int64_t)s_total + (lo - free_pos);                  // busy rows go behind all free ones
-    for (int64_t i = lo; i < hi; ++i) {
-        const int32_t r = order[i];
-        if (stamp[r] != mark) scratch[free_pos++] = r;
-        else scratch[busy_pos++] = r;
+    if (valid) {
+        order[pos] = r;
+        if (pos >= tail_from) stamp[r] = mark;
     }
+    // the last block re-arms the counters for the next sweep
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < window; i += kFixThreads) order[i] = scratch[i];
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ctl + 2, 1) == (int)gridDim.x - 1) {
+            ctl[0] = 0;
+            ctl[1] = 0;
+            ctl[2] = 0;
+        }
+    }
 }
 
 struct PipeCommit {
@@ -1819,25 +1837,26 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
     const int s0 = (int)(a->batch0 % S);
     const bool shuffle = (a->flags & XC_PIPE_SHUFFLE) != 0;
     int32_t *order = a->order + (shuffle ? (a->sweep & 1) * n_order : 0);
-    if (shuffle && n_order > 0) {
-        rc = xc_permutation(ctx, n_order, a->seed, order, st[s0]);
-        if (rc) return rc;
-    }
+    // where this sweep's last `lag` batches begin in its order
+    const int64_t my_tail = a->n_batches > lag ? (a->n_batches - lag) * a->batch : 0;
+    bool repair = false;
     if (!fresh && lag > 0) {   // (also in the serialised test schedule: the order is part of the algorithm)
         const int64_t head = (int64_t)lag * a->batch, tail = a->prev_tail_from >= 0 ? n_order - a->prev_tail_from : -1;
-        const bool repair = shuffle && tail >= 0 && head + tail <= n_order && a->n_batches >= S;
-        if (repair) {
-            if (tail > 0) {
-                const int32_t *prev = a->order + ((a->sweep + 1) & 1) * n_order;
-                order_fix_kernel<<<1, kFixThreads, 0, st[s0]>>>(order, head + tail, prev, a->prev_tail_from, n_order,
-                                                               a->order + 3 * n_order, (int32_t)(a->sweep + 1),
-                                                               a->order + 2 * n_order);
-                XC_LAUNCHED(ctx);
-            }
-        } else if (forked) {
+        repair = shuffle && tail >= 0 && head + tail <= my_tail && my_tail <= n_order && a->n_batches >= S;
+        if (!repair && forked)
             for (int i = 0; i < S; ++i)
                 if (i != s0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[i], 0));
-        }
+    }
+    if (shuffle && n_order > 0) {
+        // layout of a->order: [order A | order B | raw permutation | stamps | 4 counters]
+        int32_t *raw = a->order + 2 * n_order, *stamp = a->order + 3 * n_order, *ctl = a->order + 4 * n_order;
+        rc = xc_permutation(ctx, n_order, a->seed, raw, st[s0]);
+        if (rc) return rc;
+        const int64_t window = repair ? (int64_t)lag * a->batch + (n_order - a->prev_tail_from) : 0;
+        order_fix_kernel<<<(unsigned)((n_order + 255) / 256), 256, 0, st[s0]>>>(
+            raw, order, n_order, window, stamp, (int32_t)(a->sweep & 0x3fffffff), my_tail < n_order ? my_tail : n_order,
+            (int32_t)((a->sweep + 1) & 0x3fffffff), ctl);
+        XC_LAUNCHED(ctx);
     }
     if (forked) {
         XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pro, st[s0]));
