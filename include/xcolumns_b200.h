@@ -379,8 +379,8 @@ typedef struct {
     int32_t flags;            /* XC_PIPE_*                                                                     */
     uint64_t seed;            /* XC_PIPE_SHUFFLE: visiting order = xc_permutation(n_rows, seed), ref :419      */
     int64_t sweep;            /* sweep counter, +1 per call: with XC_PIPE_SHUFFLE the order lives in order + (sweep & 1) * n_rows */
-    int32_t *order;           /* XC_PIPE_SHUFFLE: 4 * n_rows + 4 int32 of scratch [order A | order B | raw order |  */
-                              /* stamps | counters], zero before the first call; else the n_rows visiting order   */
+    int32_t *order;           /* XC_PIPE_SHUFFLE: 4 * n_rows + n_rows / 256 + 8 int32 of scratch [order A | order B |  */
+                              /* raw order | stamps | counts], zero before the first call; else the visiting order */
     float *coef;              /* (lag + 1) sets of 4 * xc_bca_coef_len(m) floats, each [coef_n | coef_s] (or records) */
     int32_t *pred_idx;        /* [n_rows, k], rewritten                                                        */
     int32_t *pred_snapshot;   /* optional [n_rows, k]: every visited row's selection as it was BEFORE this sweep */

@@ -6,14 +6,14 @@ import json,sys
 b=json.loads(sys.stdin.read()); r=b['roofline']
 print(json.dumps({'rows':$1,'lag':$2,'batch':$3,'env':'$4','ms':round(b['ms_per_step'],4),'Minst_s':round(b['value']/1e6,1),'whole':round(r['whole_step']['frac'],3),'commits':b['config']['commits_per_sweep'],'u':b['utility_after_timed_sweeps']}))" >> $out; }
 run 38375 1 0
-run 38375 1 0 XCOLUMNS_B200_DENSE_SMALL_CTA=0
-run 38375 2 3200
-run 38375 2 4797
-run 38375 3 2400
+run 38375 2 0
+run 38375 3 0
 run 76750 1 0
-run 76750 1 0 XCOLUMNS_B200_DENSE_SMALL_CTA=0
-run 76750 3 3552
-run 76750 2 4736
-run 153500 1 0
+run 76750 2 0
+run 76750 2 9594
+run 76750 3 0
+run 153500 2 0
+run 153500 2 19188
 run 307000 1 0
+run 307000 2 0
 cat $out

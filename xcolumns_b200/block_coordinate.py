@@ -293,8 +293,9 @@ class BcaSession:
         if self.pipe:
             d = self.data
             if self._order2 is None:
-                # [order A | order B | raw order | stamps | counters]; without shuffling the first n entries are the order
-                self._order2 = torch.zeros(4 * self._n_order + 4, dtype=torch.int32, device=self.device)
+                # [order A | order B | raw order | stamps | per-block counts]; without shuffling the first n entries are the order
+                self._order2 = torch.zeros(4 * self._n_order + self._n_order // 256 + 8, dtype=torch.int32,
+                                           device=self.device)
                 self._order2[:self._n_order] = torch.arange(self._n_order, dtype=torch.int32, device=self.device)
                 self._snaps = [torch.empty_like(self.pred) for _ in range(3)]
             snap = self._snaps[j % 3]

@@ -1665,47 +1665,74 @@ namespace {
 // others (stable partition), which puts them beyond the first lag batches -- behind at least one commit of the new
 // sweep, by which time the old sweep's kernels have retired.  Only which rows share a batch matters to a
 // block-Jacobi sweep, not the order inside a batch, and the order stays a permutation.
-// The raw permutation is generated into a scratch buffer; this kernel writes the sweep's order from it: positions
-// beyond the window are copied, positions inside are partitioned (free rows fill the window from the front, busy
-// rows from the back: two counters, one warp-aggregated atomic per warp, no scan -- the order inside the window
-// is irrelevant), and the rows of THIS sweep's last `lag` batches are stamped with the sweep's mark for the next
-// sweep's test (every row is handled by exactly one thread, which is the only one to read and write its stamp).
+// The raw permutation is generated into a scratch buffer; two small kernels write the sweep's order from it:
+// order_count_kernel counts the free rows of every 256-entry block of the window, order_fix_kernel copies the
+// positions beyond the window, partitions the window stably (free rows first, then the busy ones: every block
+// adds up the counts of the blocks before it -- deterministic, the same order on every run) and stamps the rows
+// of THIS sweep's last `lag` batches with the sweep's mark for the next sweep's test (every row is handled by
+// exactly one thread, the only one to read and write its stamp).
+__global__ void __launch_bounds__(256)
+order_count_kernel(const int32_t *__restrict__ raw, int64_t window, const int32_t *__restrict__ stamp,
+                   int32_t prev_mark, int32_t *__restrict__ counts)
+{
+    __shared__ int s_cnt[8];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool free_row = i < window && stamp[raw[i]] != prev_mark;
+    const unsigned mf = __ballot_sync(XC_FULL, free_row);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(mf);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int w = 0; w < 8; ++w) c += s_cnt[w];
+        counts[blockIdx.x] = c;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 order_fix_kernel(const int32_t *__restrict__ raw, int32_t *__restrict__ order, int64_t n, int64_t window,
-                 int32_t *__restrict__ stamp, int32_t prev_mark, int64_t tail_from, int32_t mark, int32_t *ctl)
+                 int32_t *__restrict__ stamp, int32_t prev_mark, int64_t tail_from, int32_t mark,
+                 const int32_t *__restrict__ counts)
 {
+    __shared__ int s_red[8], s_red2[8];
+    __shared__ int s_before, s_total, s_wfree[8];
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool valid = i < n;
     const int32_t r = valid ? raw[i] : 0;
     int64_t pos = i;
     if ((int64_t)blockIdx.x * 256 < window) {   // block-uniform: this block holds window positions
+        const int nblk = (int)((window + 255) / 256);
+        int before = 0, total = 0;
+        for (int b = threadIdx.x; b < nblk; b += 256) {
+            const int c = counts[b];
+            total += c;
+            if (b < (int)blockIdx.x) before += c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            before += __shfl_xor_sync(XC_FULL, before, o);
+            total += __shfl_xor_sync(XC_FULL, total, o);
+        }
         const bool inw = valid && i < window;
         const bool busy = inw && stamp[r] == prev_mark;
-        const unsigned mf = __ballot_sync(XC_FULL, inw && !busy), mb = __ballot_sync(XC_FULL, busy);
-        int bf = 0, bb = 0;
-        if (lane == 0) {
-            if (mf) bf = atomicAdd(ctl + 0, __popc(mf));
-            if (mb) bb = atomicAdd(ctl + 1, __popc(mb));
+        const unsigned mf = __ballot_sync(XC_FULL, inw && !busy);
+        if (lane == 0) { s_red[wid] = before; s_red2[wid] = total; s_wfree[wid] = __popc(mf); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int bsum = 0, tsum = 0;
+            for (int w = 0; w < 8; ++w) { bsum += s_red[w]; tsum += s_red2[w]; }
+            s_before = bsum;
+            s_total = tsum;
         }
-        bf = __shfl_sync(XC_FULL, bf, 0);
-        bb = __shfl_sync(XC_FULL, bb, 0);
-        const unsigned below = (1u << lane) - 1u;
-        if (inw) pos = busy ? window - 1 - (bb + __popc(mb & below)) : bf + __popc(mf & below);
+        __syncthreads();
+        int wfree_before = 0;
+        for (int w = 0; w < wid; ++w) wfree_before += s_wfree[w];
+        const int free_rank = s_before + wfree_before + __popc(mf & ((1u << lane) - 1u));   // free rows before me
+        if (inw) pos = busy ? (int64_t)s_total + (i - free_rank) : free_rank;
     }
     if (valid) {
         order[pos] = r;
         if (pos >= tail_from) stamp[r] = mark;
-    }
-    // the last block re-arms the counters for the next sweep
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(ctl + 2, 1) == (int)gridDim.x - 1) {
-            ctl[0] = 0;
-            ctl[1] = 0;
-            ctl[2] = 0;
-        }
     }
 }
 
@@ -1848,14 +1875,18 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
                 if (i != s0) XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[s0], ctx->ev_k[i], 0));
     }
     if (shuffle && n_order > 0) {
-        // layout of a->order: [order A | order B | raw permutation | stamps | 4 counters]
-        int32_t *raw = a->order + 2 * n_order, *stamp = a->order + 3 * n_order, *ctl = a->order + 4 * n_order;
+        // layout of a->order: [order A | order B | raw permutation | stamps | per-block counts]
+        int32_t *raw = a->order + 2 * n_order, *stamp = a->order + 3 * n_order, *counts = a->order + 4 * n_order;
         rc = xc_permutation(ctx, n_order, a->seed, raw, st[s0]);
         if (rc) return rc;
         const int64_t window = repair ? (int64_t)lag * a->batch + (n_order - a->prev_tail_from) : 0;
+        const int32_t prev_mark = (int32_t)(a->sweep & 0x3fffffff), mark = (int32_t)((a->sweep + 1) & 0x3fffffff);
+        if (window > 0) {
+            order_count_kernel<<<(unsigned)((window + 255) / 256), 256, 0, st[s0]>>>(raw, window, stamp, prev_mark, counts);
+            XC_LAUNCHED(ctx);
+        }
         order_fix_kernel<<<(unsigned)((n_order + 255) / 256), 256, 0, st[s0]>>>(
-            raw, order, n_order, window, stamp, (int32_t)(a->sweep & 0x3fffffff), my_tail < n_order ? my_tail : n_order,
-            (int32_t)((a->sweep + 1) & 0x3fffffff), ctl);
+            raw, order, n_order, window, stamp, prev_mark, my_tail < n_order ? my_tail : n_order, mark, counts);
         XC_LAUNCHED(ctx);
     }
     if (forked) {
