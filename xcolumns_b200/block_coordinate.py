@@ -37,14 +37,23 @@ from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
 _AUTO_EXACT_MAX_ROWS = 4096
 
 
-def _default_lag() -> int:
+def _default_lag(batch_rows: int = 0, wave_rows: int = 0) -> int:
     """Commits applied this many batches late in the pipelined dense sweep (csrc/bca_batched.cu:
-    xc_bca_pipe_sweep): lag + 1 batches are in flight on as many streams; $XCOLUMNS_B200_LAG=0 restores the
-    strict batch order, values up to 3 are accepted."""
-    try:
-        return max(0, min(3, int(os.environ.get("XCOLUMNS_B200_LAG", "1"))))
-    except ValueError:
-        return 1
+    xc_bca_pipe_sweep): lag + 1 batches are in flight on as many streams.  Default: 1 when a batch is at least four
+    waves of the streaming kernel (two such kernels keep the GPU full: 307 k x 13 k on one GPU, 2.50 vs 2.56 ms per
+    sweep), 2 for smaller batches, where a third batch in flight fills the slots a finishing batch frees while its
+    commit is pending (8-GPU shard of the same matrix, 38 k rows: 0.351 vs 0.373 ms; 77 k rows: 0.628 vs 0.694 ms;
+    measured on B200, profiles/r02_notes.md).  $XCOLUMNS_B200_LAG=0 restores the strict batch order, values up to 3
+    are accepted."""
+    env = os.environ.get("XCOLUMNS_B200_LAG")
+    if env is not None:
+        try:
+            return max(0, min(3, int(env)))
+        except ValueError:
+            pass
+    if batch_rows > 0 and wave_rows > 0 and batch_rows < 4 * wave_rows:
+        return 2
+    return 1
 
 
 def _metric_params(metric_id, beta, eps, maximize, skip_tn, n_div, n_rows=None, mix=None) -> MetricParams:
@@ -123,7 +132,12 @@ class BcaSession:
         clen = int(self.ctx.lib.xc_bca_coef_len(self.m))       # padded to whole coefficient tiles
         # Dense rows of one process, or of the ranks of one box with a peer window: the whole sweep is ONE C call
         # (xc_bca_sweep_dense_pipe); commits are applied `lag` batches late so consecutive batches overlap.
-        self.lag = 0 if (self.is_csr or self.use_rec) else _default_lag()
+        if self.is_csr or self.use_rec:
+            self.lag = 0
+        else:   # decided on numbers every rank agrees on (ragged shards differ by a row)
+            n_ref = self.comm.max_int(self.n)
+            wave = self.wave_rows()
+            self.lag = _default_lag(default_batch_rows(n_ref, wave), wave)
         self.pipe = (not self.is_csr) and self.comm.world == 1
         self._gb = 0                                           # batches issued so far (delta-buffer rotation)
         self.peer: Optional[PeerWindow] = None                 # peer-memory commits (sharded dense rows)
