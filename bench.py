@@ -469,7 +469,7 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
         sampler.active = True
     launches0 = sess.ctx.launches()
     if want_roofline:
-        sess.ctx.call("xc_timing_enable", 1)
+        sess.ctx.call("xc_timing_enable", 2 if os.environ.get("BENCH_DUMP_TIMELINE") else 1)
 
     # the queued sweeps are still executing when the host has enqueued them all: one clock sample under load
     ms = timed(one_sweep, args.steps, device, comm, after_enqueue=(sampler.sample_now if sampler is not None else None))
@@ -486,16 +486,19 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
         st, en, rows = read_kernel_timing(sess.ctx)
         sess.ctx.call("xc_timing_enable", 0)
         peak, peak_src = load_peak()
+        if os.environ.get("BENCH_DUMP_TIMELINE") and len(st):   # diagnostics: last sweep incl. commits (rows = 0), ms
+            per_all = len(st) // args.steps
+            t0 = float(st[-per_all:].min())
+            res["timeline_last_sweep"] = [[round(float(a - t0), 4), round(float(b - t0), 4), int(r)]
+                                          for a, b, r in zip(st[-per_all:], en[-per_all:], rows[-per_all:])]
+            keep = rows > 0
+            st, en, rows = st[keep], en[keep], rows[keep]
         if len(st):
             per = len(st) // args.steps
             busy = [union_ms(st[i * per:(i + 1) * per], en[i * per:(i + 1) * per]) for i in range(args.steps)]
             busy_ms = float(np.sum(busy))
             bytes_total = float(rows.sum()) * m * 4
             achieved = bytes_total / (busy_ms / 1e3) / 1e9
-            if os.environ.get("BENCH_DUMP_TIMELINE"):   # per-launch (start, end, rows) of the last timed sweep, ms
-                t0 = float(st[-per:].min())
-                res["timeline_last_sweep"] = [[round(float(a - t0), 4), round(float(b - t0), 4), int(r)]
-                                              for a, b, r in zip(st[-per:], en[-per:], rows[-per:])]
             res["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "bca_batch_dense_kernel<float,1>",

@@ -203,6 +203,17 @@ XC_API int xc_bca_online_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t 
                                int64_t ld, const void *y_true, int64_t ld_true, int k,
                                const xc_metric_params *p, int32_t *pred_idx, double *tp, double *fp,
                                double *fn, double *tn, void *stream);
+/* The same for CSR rows (ref: block_coordinate.py:212-293 with greedy=True, only_pred=True, then
+ * confusion_matrix.py:421-432 -> numba_csr_functions.py:421-452; experiments/omma_wrappers_online_methods.py:223-266):
+ * candidates are the row's stored labels; t_*: the CSR rows of y_true (pass the probability rows again for the
+ * "ETU" variant).  The reference adds 1 to tn of every label per instance; here that is replayed lazily and
+ * bit-exactly (tn_last [m] int32, zero before the first call; step0 = instances of earlier calls); on return tn
+ * is up to date for all labels.  pred_idx [n_rows, k]: ascending labels, -1 for rows with fewer than k entries. */
+XC_API int xc_bca_online_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices,
+                             const int64_t *indptr, const void *t_data, const int32_t *t_indices,
+                             const int64_t *t_indptr, int64_t n_rows, int64_t m, int k,
+                             const xc_metric_params *p, int32_t *pred_idx, double *tp, double *fp, double *fn,
+                             double *tn, int32_t *tn_last, int64_t step0, void *stream);
 /* k == 0 (no budget, ref: block_coordinate.py:199-200): every label with gain >= 0 is predicted.
  * pred is a dense [n, ld_pred] 0/1 matrix of eta's dtype, updated in place.                     */
 XC_API int xc_bca_exact_sweep_dense_k0(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m,
@@ -414,7 +425,7 @@ XC_API int xc_h2d_staged(xc_ctx *ctx, void *dst_dev, int64_t dst_pitch, const vo
  * is launched on.  xc_timing_read synchronises the device and returns for up to `cap` launches the start
  * and end time (ms since the first recorded event) and the rows processed (HOST arrays), the number of
  * recorded launches in *count_host, and clears the log.                                              */
-XC_API int xc_timing_enable(xc_ctx *ctx, int on);
+XC_API int xc_timing_enable(xc_ctx *ctx, int on);   /* 0 off, 1 batch kernels, 2 also commits (logged with rows = 0) */
 XC_API int xc_timing_read(xc_ctx *ctx, int cap, double *start_ms_host, double *end_ms_host,
                           int64_t *rows_host, int *count_host);
 

@@ -640,3 +640,81 @@ def find_classifier_using_fw(y_true, y_proba, metric: str, k: int, max_iters=100
     meta["time"] = time.time() - t0
     meta["final_utility"] = new_u
     return A, B, P, meta
+
+
+# ------------------------------------------------------------------------------------------
+# online / greedy steps on CSR rows (block_coordinate.py:212-293 with greedy=True, only_pred=True, then
+# confusion_matrix.py:421-432 -> numba_csr_functions.py:421-452), driven like
+# experiments/omma_wrappers_online_methods.py:223-266.  numpy restatement, one python step per instance.
+# ------------------------------------------------------------------------------------------
+
+def _metric_vec(mid, c1, b2, eps, tp, fp, fn, tn):
+    out = np.empty(tp.shape[0], dtype=np.float64)
+    lib().orc_binary_metric_vec(C.c_int(mid), _p(np.ascontiguousarray(tp)), _p(np.ascontiguousarray(fp)),
+                                _p(np.ascontiguousarray(fn)), _p(np.ascontiguousarray(tn)), C.c_int64(tp.shape[0]),
+                                C.c_double(1.0), C.c_double(c1), C.c_double(b2), C.c_double(eps), _p(out))
+    return out
+
+
+def online_greedy_csr(y_proba: csr_matrix, y_true: csr_matrix, k: int, metric: str, skip_tn: bool = False,
+                      init=(1e-6, 1e-6, 1e-6, 1e-6), maximize: bool = True):
+    """Returns (pred_idx [n, k] ascending label ids, state [4, m]).  Ties between equal gains go to the lowest label
+    id (the reference's argpartition order is unpinned)."""
+    n, m = y_proba.shape
+    mid, c1, b2, eps = metric_params(metric)
+    tp, fp, fn, tn = (np.full(m, float(v), dtype=np.float64) for v in init)
+    pred = np.full((n, k), -1, dtype=np.int32)
+    dt = y_proba.data.dtype
+    one = dt.type(1)
+    for i in range(n):
+        s, e = y_proba.indptr[i], y_proba.indptr[i + 1]
+        t_data, t_idx = y_proba.data[s:e], y_proba.indices[s:e]
+        om = (one - t_data).astype(dt)                      # :252 (1 - t_data) in the data dtype
+        neg_tp, neg_fp, pos_fn = tp[t_idx], fp[t_idx], fn[t_idx]
+        pos_tpp = (neg_tp + t_data) / n
+        pos_fpp = (neg_fp + om) / n
+        neg_fnn = (pos_fn + t_data) / n
+        neg_tp, neg_fp, pos_fn = neg_tp / n, neg_fp / n, pos_fn / n
+        pos_tn = tn[t_idx]
+        neg_tnn = pos_tn
+        if not skip_tn:
+            neg_tnn = (pos_tn + om) / n
+            pos_tn = pos_tn / n
+        gains = _metric_vec(mid, c1, b2, eps, pos_tpp, pos_fpp, pos_fn, pos_tn) - _metric_vec(
+            mid, c1, b2, eps, neg_tp, neg_fp, neg_fnn, neg_tnn)
+        if not maximize:
+            gains = -gains
+        if t_idx.size > k:                                  # numba_csr_functions.py:456-466
+            sel = np.sort(np.lexsort((t_idx, -gains))[:k])
+            p_idx = t_idx[sel]
+        else:
+            p_idx = t_idx.copy()
+        pred[i, :p_idx.size] = p_idx
+        # update with the true row (prediction entries are ones of the data dtype)
+        us, ue = y_true.indptr[i], y_true.indptr[i + 1]
+        u_data, u_idx = y_true.data[us:ue].astype(dt), y_true.indices[us:ue]
+        true_of = dict(zip(u_idx.tolist(), u_data.tolist()))
+        in_pred = set(p_idx.tolist())
+        if not skip_tn:
+            tn += 1
+        for j in p_idx.tolist():
+            if j in true_of:
+                v = dt.type(true_of[j])
+                tpd = dt.type(one * v)
+                ftd = dt.type(float(one) * (1.0 - float(v)))
+                tp[j] += tpd
+                fp[j] += ftd
+                if not skip_tn:
+                    tn[j] -= tpd
+                    tn[j] -= ftd
+            else:
+                fp[j] += float(one)
+                if not skip_tn:
+                    tn[j] -= float(one)
+        for j, v in zip(u_idx.tolist(), u_data.tolist()):
+            v = dt.type(v)
+            fnd = dt.type(float(v) * (1.0 - 1.0)) if j in in_pred else v
+            fn[j] += fnd
+            if not skip_tn:
+                tn[j] -= fnd
+    return pred, np.stack([tp, fp, fn, tn])

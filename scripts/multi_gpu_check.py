@@ -112,6 +112,7 @@ y = csr_probs(nc, mc, 40, seed=1006)
 lo, hi = shard_rows(nc, rank, world)
 predc, metac = xb.predict_optimizing_coverage_using_bc(y[lo:hi], k, seed=0, mode="batched", distributed=True,
                                                        return_meta=True, y_pred_format="indices")
+say("coverage sharded meta:", {kk: metac[kk] for kk in ("utilities", "iters", "batch_size")})
 if rank == 0:
     _, mex = xb.predict_optimizing_coverage_using_bc(y, k, seed=0, mode="exact", return_meta=True)
     say(f"coverage: sharded {metac['utilities'][-1]:.9f} exact {mex['utilities'][-1]:.9f}")

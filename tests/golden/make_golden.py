@@ -370,8 +370,53 @@ def main_extra():
     print(f"extra: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def main_online_csr():
+    """online_csr.npz: the online / greedy steps on CSR rows (block_coordinate.py:212-293 with greedy=True,
+    only_pred=True, then confusion_matrix.py:421-432), driven like experiments/omma_wrappers_online_methods.py:223-266
+    on the live reference."""
+    _install_shims()
+    from xcolumns import block_coordinate as bc
+    from xcolumns import confusion_matrix as cm
+    from xcolumns import metrics as mt
+
+    from xcolumns_b200.synth import csr_probs
+
+    n, m, k = 300, 120, 5
+    y = csr_probs(n, m, 18, seed=71)
+    rng = np.random.default_rng(13)
+    # true labels: Bernoulli draws on the stored entries plus a few positives the probability row does not store
+    keep = rng.random(y.nnz) < y.data
+    rows = np.repeat(np.arange(n), np.diff(y.indptr))
+    extra_r, extra_c = rng.integers(0, n, 60), rng.integers(0, m, 60)
+    t = csr_matrix((np.ones(keep.sum() + 60, dtype=np.float32),
+                    (np.concatenate([rows[keep], extra_r]), np.concatenate([y.indices[keep], extra_c]))), shape=(n, m))
+    t.sum_duplicates()
+    t.data[:] = 1.0
+    t.sort_indices()
+    out = {"y_data": y.data, "y_indices": y.indices, "y_indptr": y.indptr, "t_data": t.data, "t_indices": t.indices,
+           "t_indptr": t.indptr, "shape": np.array([n, m, k])}
+    for name, metric, skip_tn, etu in (("f1", mt.binary_f1_score_on_conf_matrix, True, False),
+                                       ("f1_etu", mt.binary_f1_score_on_conf_matrix, True, True),
+                                       ("balacc", mt.binary_balanced_accuracy_on_conf_matrix, False, False),
+                                       ("gmean_etu", mt.binary_gmean_on_conf_matrix, False, True)):
+        C_ = cm.ConfusionMatrix(*[np.full(m, 1e-6, dtype=np.float64) for _ in range(4)])
+        yp = csr_matrix((n, m), dtype=np.float32)
+        yt = y if etu else t
+        for i in range(n):
+            bc._bc_with_0approx_step_csr(y, yp, i, C_.tp, C_.fp, C_.fn, C_.tn, k, metric, greedy=True, skip_tn=skip_tn,
+                                         only_pred=True)
+            cm._update_unnormalized_confusion_matrix(C_, yt[i], yp[i], skip_tn=skip_tn)
+        assert (np.diff(yp.indptr) == k).all()
+        out[name + "_pred"] = np.asarray(yp.indices[:n * k], dtype=np.int32).reshape(n, k).copy()
+        out[name + "_state"] = np.stack([C_.tp, C_.fp, C_.fn, C_.tn])
+        print(f"  online csr {name}: tp sum {C_.tp.sum():.6f} tn sum {C_.tn.sum():.6f}")
+    np.savez_compressed(os.path.join(HERE, "online_csr.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+    if len(sys.argv) > 1 and sys.argv[1] == "online_csr":
+        main_online_csr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "extra":
         main_extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "mixed":
         main_mixed()

@@ -716,3 +716,27 @@ def test_fw_driver_options_golden(xb, golden, name, kw):
     assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9)
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
     assert np.allclose(clf.p, g[name + "_p"], atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,metric,skip_tn,etu", [("f1", "f1", True, False), ("f1_etu", "f1", True, True),
+                                                       ("balacc", "balanced_accuracy", False, False),
+                                                       ("gmean_etu", "gmean", False, True)])
+def test_online_greedy_csr_golden(xb, golden, name, metric, skip_tn, etu):
+    """online greedy on CSR rows (experiments/omma_wrappers_online_methods.py:223-266): predictions and the float64
+    state -- including tn, whose per-instance "+1 for every label" is replayed lazily -- bit-equal to the live
+    reference, also when the stream is cut into micro-batches"""
+    from xcolumns_b200.online import OnlineGreedy
+    g = golden("online_csr")
+    n, m, k = (int(v) for v in g["shape"])
+    y = csr_matrix((g["y_data"], g["y_indices"], g["y_indptr"]), shape=(n, m))
+    t = csr_matrix((g["t_data"], g["t_indices"], g["t_indptr"]), shape=(n, m))
+    for cuts in ([0, n], [0, 1, 50, 177, n]):
+        og = OnlineGreedy(m, k, _metric(xb, metric), skip_tn=skip_tn, etu_variant=etu)
+        preds = [og.predict_update(y[a:b], None if etu else t[a:b], n_div=n, y_pred_format="indices")
+                 for a, b in zip(cuts[:-1], cuts[1:])]
+        assert (np.concatenate(preds) == g[name + "_pred"]).all()
+        assert np.array_equal(np.stack(list(og.C)), g[name + "_state"])
+    out = OnlineGreedy(m, k, _metric(xb, metric), skip_tn=skip_tn, etu_variant=etu).predict_update(y, None if etu else t)
+    assert isinstance(out, csr_matrix) and out.shape == y.shape and out.dtype == y.dtype
+    assert (np.diff(out.indptr) == k).all() and (out.indices.reshape(n, k) == g[name + "_pred"]).all()

@@ -259,3 +259,18 @@ def test_fw_driver_options(golden, oracle, name, kw):
     assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9)
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5)
     assert np.allclose(p, g[name + "_p"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name,metric,skip_tn,etu", [("f1", "f1", True, False), ("f1_etu", "f1", True, True),
+                                                       ("balacc", "balanced_accuracy", False, False),
+                                                       ("gmean_etu", "gmean", False, True)])
+def test_online_greedy_csr_golden(oracle, golden, name, metric, skip_tn, etu):
+    """online / greedy steps on CSR rows: oracle == live reference, label ids and float64 state bit for bit"""
+    from scipy.sparse import csr_matrix
+    g = golden("online_csr")
+    n, m, k = (int(v) for v in g["shape"])
+    y = csr_matrix((g["y_data"], g["y_indices"], g["y_indptr"]), shape=(n, m))
+    t = csr_matrix((g["t_data"], g["t_indices"], g["t_indptr"]), shape=(n, m))
+    pred, state = oracle.online_greedy_csr(y, y if etu else t, k, metric, skip_tn=skip_tn)
+    assert (pred == g[name + "_pred"]).all()
+    assert np.array_equal(state, g[name + "_state"])

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "xc_h2d_staged": [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp],
     "xc_timing_enable": [_int],
     "xc_timing_read": [_int, _vp, _vp, _vp, _vp],
+    "xc_bca_online_csr": [_vp, _int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                          _vp],
     "xc_bca_online_dense": [_vp, _int, _i64, _i64, _i64, _vp, _i64, _int, _MP, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_batch_csr_rec": [_MP, _vp, _int, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xc_bca_rec": [_MP, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],

@@ -630,6 +630,7 @@ def predict_using_bc_with_0approx(
             batch = default_batch_rows(n_order, sess.wave_rows())
         n_batches = comm.max_int((n_order + batch - 1) // batch)
         batch_max = comm.max_int(batch)      # ragged shards: ranks may differ by a row, decisions must not
+        min_batch = max(1, 16 // comm.world)  # every rank commits `batch` rows at once: the floor is per job, not per rank
         base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
         sess._n_order = n_order
         meta["batch_size"] = batch
@@ -671,10 +672,10 @@ def predict_using_bc_with_0approx(
                 sess.utility_into(util_all[j - 1:])
                 # (the decision is taken on numbers every rank agrees on: the utilities come from the
                 #  replicated state, batch_max is all-reduced)
-                if batch_max > 16 and not batch_size:
+                if batch_max > min_batch and not batch_size:
                     # ... and repeat it with 4x more commits
-                    batch = max(16, batch // 4)
-                    batch_max = max(16, batch_max // 4)
+                    batch = max(min_batch, batch // 4)
+                    batch_max = max(min_batch, batch_max // 4)
                     n_batches = comm.max_int((n_order + batch - 1) // batch)
                     meta["batch_size"] = batch
                     attempt += 1
@@ -977,6 +978,7 @@ def predict_optimizing_coverage_using_bc(
         batch = int(batch_size) if batch_size else coverage_batch_rows(n)
         n_batches = comm.max_int((n + batch - 1) // batch)
         batch_max = comm.max_int(batch)
+        min_batch = max(1, 16 // comm.world)   # every rank commits `batch` rows at once: the floor is per job, not per rank
         base_seed = (0x9E3779B97F4A7C15 * (1 + (0 if seed is None else int(seed))) + 7919 * comm.rank) & (2**64 - 1)
         order_dev = torch.arange(n, dtype=torch.int32, device=device)
         sess.state(XC_SUM_FAST)
@@ -1002,8 +1004,8 @@ def predict_optimizing_coverage_using_bc(
                 sess.pred = saved
                 sess.state(XC_SUM_FAST)
                 sess.utility_device(0)
-                if batch_max > 16 and not batch_size:
-                    batch, batch_max = max(16, batch // 4), max(16, batch_max // 4)
+                if batch_max > min_batch and not batch_size:
+                    batch, batch_max = max(min_batch, batch // 4), max(min_batch, batch_max // 4)
                     n_batches = comm.max_int((n + batch - 1) // batch)
                     meta["batch_size"] = batch
                     attempt += 1

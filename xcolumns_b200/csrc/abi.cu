@@ -46,6 +46,7 @@ extern "C" int xc_ctx_create(int device, xc_ctx **out)
     ctx->pipe_active = false;
     ctx->pipe_forked = false;
     ctx->timing_on = false;
+    ctx->timing_commits = false;
     ctx->timing_count = ctx->timing_cap = 0;
     ctx->timing_ev = nullptr;
     ctx->timing_rows = nullptr;
@@ -99,6 +100,7 @@ extern "C" int xc_timing_enable(xc_ctx *ctx, int on)
     XcDeviceGuard xc_guard__(ctx);
     if (!ctx) return XC_ERR_INVALID;
     ctx->timing_on = on != 0;
+    ctx->timing_commits = on == 2;
     ctx->timing_count = 0;
     return XC_OK;
 }

@@ -1920,8 +1920,15 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[si], st[si]));
             XC_CUDA_TRY(ctx, cudaStreamWaitEvent(cst, ctx->ev_k[si], 0));
         }
+        cudaEvent_t c0 = nullptr, c1 = nullptr;
+        if (ctx->timing_on && ctx->timing_commits) {   // (diagnostics: rows = 0 marks a commit in the timing log)
+            rc = xc_timing_slot(ctx, 0, &c0, &c1);
+            if (rc) return rc;
+            XC_CUDA_TRY(ctx, cudaEventRecord(c0, cst));
+        }
         rc = launch_commit(c, cur, clr, set[si], nullptr, clen, cst);
         if (rc) return rc;
+        if (c1) XC_CUDA_TRY(ctx, cudaEventRecord(c1, cst));
         if (forked) {   // K_{g+S}, the next kernel on this batch stream, follows commit_g
             XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_c[si], cst));
             XC_CUDA_TRY(ctx, cudaStreamWaitEvent(st[si], ctx->ev_c[si], 0));

@@ -645,6 +645,124 @@ bca_exact_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ ind
     }
 }
 
+// ---- CSR, online / greedy micro-batch -----------------------------------------------------------------
+// ref: block_coordinate.py:212-293 called with greedy=True, only_pred=True (the row is predicted from the current
+// confusion matrix, nothing is removed or re-added), followed by confusion_matrix.py:402-435 ->
+// numba_add_to_unnormalized_confusion_matrix_csr with the row of y_true, as driven by
+// experiments/omma_wrappers_online_methods.py:223-266.
+//
+// The reference's update adds 1 to tn of EVERY label per instance (numba_csr_functions.py:448) and corrects the
+// touched ones -- O(m) per instance.  Here tn is kept lazily: last[j] counts the instances whose "+1" label j
+// has already received; a label is brought up to date when a row touches it (and all labels at the end of the
+// launch).  Bit-exact: a float64 "+1" is only rounded when the sum crosses into the next binade, so c pending
+// additions are replayed as exact block additions up to the binade boundary plus one rounded addition across it.
+__device__ __forceinline__ double tn_fast_forward(double x, long long c)
+{
+    while (c > 0) {
+        if (!(x >= 1.0) || !(x < 4503599627370496.0)) {   // below 1 (or absurdly large): plain rounded additions
+            x = x + 1.0;
+            --c;
+            continue;
+        }
+        const double limit = ldexp(1.0, ilogb(x) + 1);        // x in [limit / 2, limit)
+        long long s = (long long)ceil(limit - x) - 1;         // additions that stay below the boundary: exact
+        if (s > c) s = c;
+        if (s > 0) {
+            x = x + (double)s;
+            c -= s;
+        } else {
+            x = x + 1.0;                                      // the addition that crosses the boundary (rounded)
+            --c;
+        }
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(256) tn_flush_kernel(double *tn, int32_t *last, int64_t m, int32_t now)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= m) return;
+    const int c = now - last[j];
+    if (c > 0) tn[j] = tn_fast_forward(tn[j], c);
+    last[j] = now;
+}
+
+// bring tn of the labels of one CSR row up to date (lane-parallel, labels of a row are distinct)
+__device__ __forceinline__ void tn_catch_up_row(const int32_t *indices, int64_t s, int64_t e, double *tn, int32_t *last,
+                                                int32_t now)
+{
+    for (int64_t q = s + lane_id(); q < e; q += 32) {
+        const int j = indices[q];
+        const int c = now - last[j];
+        if (c > 0) {
+            tn[j] = tn_fast_forward(tn[j], c);
+            last[j] = now;
+        }
+    }
+    __syncwarp();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32)
+bca_online_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                      const int64_t *__restrict__ indptr, const T *__restrict__ t_data,
+                      const int32_t *__restrict__ t_indices, const int64_t *__restrict__ t_indptr, int64_t n_rows, int k,
+                      xc_metric_params p, int32_t *pred_idx, double *tp, double *fp, double *fn, double *tn,
+                      int32_t *tn_last, int32_t step0)
+{
+    const int lane = lane_id();
+    const double nd = p.n_div;
+    const T one = (T)1;
+    const bool use_tn = !p.skip_tn;
+    for (int64_t i = 0; i < n_rows; ++i) {
+        const int32_t now = step0 + (int32_t)i;   // instances whose "+1" every label should have received so far
+        const int64_t ts = indptr[i], te = indptr[i + 1];
+        if (use_tn) tn_catch_up_row(indices, ts, te, tn, tn_last, now);
+        WarpTopK<double> tk;
+        tk.init();
+        for (int64_t q0 = ts; q0 < te; q0 += 32) {  // block_coordinate.py:243-282 (greedy: no removal)
+            const int64_t q = q0 + lane;
+            double g[1];
+            g[0] = NAN;
+            if (q < te) {
+                const int j = indices[q];
+                const T t = data[q];
+                const T om = one - t;
+                double neg_tp = tp[j], neg_fp = fp[j], pos_fn = fn[j];
+                const double pos_tpp = (neg_tp + (double)t) / nd;
+                const double pos_fpp = (neg_fp + (double)om) / nd;
+                const double neg_fnn = (pos_fn + (double)t) / nd;
+                neg_tp = neg_tp / nd;
+                neg_fp = neg_fp / nd;
+                pos_fn = pos_fn / nd;
+                double pos_tn = tn[j], neg_tnn = pos_tn;     // :258-264: raw tn on both sides when skip_tn
+                if (use_tn) {
+                    neg_tnn = (pos_tn + (double)om) / nd;
+                    pos_tn = pos_tn / nd;
+                }
+                const double up = xc_metric_eval(p, pos_tpp, pos_fpp, pos_fn, pos_tn);
+                const double un = xc_metric_eval(p, neg_tp, neg_fp, neg_fnn, neg_tnn);
+                const double gg = up - un;
+                g[0] = p.maximize ? gg : -gg;
+            }
+            if (__any_sync(XC_FULL, tk.passes(g[0]))) xc_scan_insert<double, 1, false>(tk, g, q0 - ts, 1, k, -1);
+        }
+        const int src = warp_rank_src(tk.idx, k);
+        const int pos = __shfl_sync(XC_FULL, tk.idx, src);
+        const int pj = (lane < k && pos != 0x7fffffff) ? indices[ts + pos] : -1;
+        if (lane < k) pred_idx[i * k + lane] = pj;
+        // confusion_matrix.py:402-435 with the row of y_true (prediction entries are ones)
+        const int64_t us = t_indptr[i], ue = t_indptr[i + 1];
+        if (use_tn) tn_catch_up_row(t_indices, us, ue, tn, tn_last, now);   // (predicted labels: caught up above)
+        csr_apply_row<T>(t_data, t_indices, us, ue, pj, k, 1.0, tp, fp, fn, use_tn ? tn : nullptr);
+        if (use_tn) {   // the touched labels have now received this instance's "+1" as well
+            if (lane < k && pj >= 0) tn_last[pj] = now + 1;
+            for (int64_t q = us + lane; q < ue; q += 32) tn_last[t_indices[q]] = now + 1;
+            __syncwarp();
+        }
+    }
+}
+
 // ---- CSR, register-staged fast path ------------------------------------------------------------------
 // The generic kernel above walks every step through ~30 dependent L2 round trips (order -> indptr ->
 // row -> binary searches -> state ...): 26 us per instance.  Here a parallel prologue resolves all
@@ -1155,6 +1273,37 @@ extern "C" int xc_bca_online_dense(xc_ctx *ctx, const void *eta, int dtype, int6
     if (dtype == XC_F64)
         return dispatch_exact_cluster<double>(ctx, eta, m, ld, nullptr, n_rows, k, p, 1, pred_idx, tp, fp, fn, tn, st, y_true, ld_true);
     return XC_ERR_UNSUPPORTED;
+}
+
+/* tn_last [m] int32 (zero before the first call): see bca_online_csr_kernel; step0: instances processed by earlier
+ * calls.  On return tn is up to date for every label (tn_last = step0 + n_rows). */
+extern "C" int xc_bca_online_csr(xc_ctx *ctx, const void *data, int dtype, const int32_t *indices, const int64_t *indptr,
+                                 const void *t_data, const int32_t *t_indices, const int64_t *t_indptr, int64_t n_rows,
+                                 int64_t m, int k, const xc_metric_params *p, int32_t *pred_idx, double *tp, double *fp,
+                                 double *fn, double *tn, int32_t *tn_last, int64_t step0, void *stream)
+{
+    XcDeviceGuard xc_guard__(ctx);
+    if (!ctx || !indptr || !t_indptr || !p || !pred_idx || !tp || !fp || !fn || !tn || !tn_last) return XC_ERR_INVALID;
+    if (n_rows < 0 || m <= 0 || k < 1 || k > 32 || step0 < 0 || step0 + n_rows > 0x7fffffffLL) return XC_ERR_INVALID;
+    if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
+    if (n_rows == 0) return XC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == XC_F32)
+        bca_online_csr_kernel<float><<<1, 32, 0, st>>>((const float *)data, indices, indptr, (const float *)t_data, t_indices,
+                                                       t_indptr, n_rows, k, *p, pred_idx, tp, fp, fn, tn, tn_last,
+                                                       (int32_t)step0);
+    else if (dtype == XC_F64)
+        bca_online_csr_kernel<double><<<1, 32, 0, st>>>((const double *)data, indices, indptr, (const double *)t_data,
+                                                        t_indices, t_indptr, n_rows, k, *p, pred_idx, tp, fp, fn, tn,
+                                                        tn_last, (int32_t)step0);
+    else
+        return XC_ERR_UNSUPPORTED;
+    XC_LAUNCHED(ctx);
+    if (!p->skip_tn) {
+        tn_flush_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(tn, tn_last, m, (int32_t)(step0 + n_rows));
+        XC_LAUNCHED(ctx);
+    }
+    return XC_OK;
 }
 
 extern "C" int xc_bca_exact_sweep_dense_k0(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m, int64_t ld,

@@ -28,6 +28,7 @@ struct xc_ctx {
     bool pipe_forked;            // ... on the internal streams (work the caller's stream has not joined yet)
     // optional per-launch timing of the batch kernels (xc_timing_*): events in launch order
     bool timing_on;
+    bool timing_commits;         // xc_timing_enable(2): commits are logged too (rows = 0)
     int timing_count, timing_cap;
     cudaEvent_t *timing_ev;      // 2 per launch (start, end)
     int64_t *timing_rows;        // rows of the launch

@@ -16,6 +16,7 @@ from typing import Any, Callable, Dict, Optional, Sequence, Union
 
 import numpy as np
 import torch
+from scipy.sparse import csr_matrix
 
 from . import _device as dev
 from . import metrics as M
@@ -49,6 +50,8 @@ class OnlineGreedy:
         for i, v in enumerate(initial_confusion_matrix):
             self.state[i].fill_(float(v))
         self.n = float(sum(initial_confusion_matrix))   # like the reference: instances seen (+ the regulariser)
+        self._steps = 0                                  # instances processed through the CSR path (lazy tn)
+        self._tn_last: Optional[torch.Tensor] = None
 
     @property
     def C(self) -> ConfusionMatrix:
@@ -62,8 +65,10 @@ class OnlineGreedy:
         matching row of ``y_true`` (or of ``y_proba`` itself for the ETU variant).  ``n_div``: the divisor of
         the step's normalisation (block_coordinate.py:149-151: the number of rows of the matrix the reference
         step is handed); defaults to ``y_proba.shape[0]``."""
+        if isinstance(y_proba, csr_matrix):
+            return self._predict_update_csr(y_proba, y_true, n_div, y_pred_format)
         if not isinstance(y_proba, (np.ndarray, torch.Tensor)):
-            raise ValueError("y_proba must be np.ndarray or torch.Tensor (dense rows)")
+            raise ValueError("y_proba must be np.ndarray, torch.Tensor or csr_matrix")
         if y_proba.shape[1] != self.m:
             raise ValueError(f"y_proba must have {self.m} columns")
         if not self.etu_variant:
@@ -86,3 +91,35 @@ class OnlineGreedy:
         if y_pred_format == "indices":
             return pred if isinstance(y_proba, torch.Tensor) and y_proba.is_cuda else pred.cpu().numpy()
         return dev.compact_to_dense_like(y_proba, pred, self.m)
+
+    def _predict_update_csr(self, y_proba: csr_matrix, y_true: Optional[csr_matrix], n_div: Optional[int],
+                            y_pred_format: str):
+        """CSR rows (block_coordinate.py:212-293 with greedy=True, only_pred=True, then
+        confusion_matrix.py:421-432, as driven by experiments/omma_wrappers_online_methods.py:223-266): candidates are
+        the row's stored labels; rows with fewer than k of them keep them all.  Returns a csr_matrix of ones (same
+        dtypes as y_proba) or, with y_pred_format="indices", the (n, k) label ids (-1 = unused slot)."""
+        if y_proba.shape[1] != self.m:
+            raise ValueError(f"y_proba must have {self.m} columns")
+        if not self.etu_variant:
+            if y_true is None:
+                raise ValueError("y_true is required unless etu_variant=True")
+            if not isinstance(y_true, csr_matrix) or tuple(y_true.shape) != tuple(y_proba.shape):
+                raise ValueError("y_true must be a csr_matrix of y_proba's shape")
+        n = y_proba.shape[0]
+        c = dev.csr_to_device(y_proba, self.device)
+        t = c if self.etu_variant else dev.csr_to_device(y_true, self.device, np.dtype(np.float32 if c.code == 0 else np.float64))
+        metric_id, beta, eps = self._resolved
+        p = _metric_params(metric_id, beta, eps, self.maximize, self.skip_tn, float(n if n_div is None else n_div),
+                           mix=self._mix)
+        if self._tn_last is None:
+            self._tn_last = torch.zeros(self.m, dtype=torch.int32, device=self.device)
+        pred = torch.empty((n, self.k), dtype=torch.int32, device=self.device)
+        sp = lambda i: C.c_void_p(self.state[i].data_ptr())
+        self.ctx.call("xc_bca_online_csr", dev.ptr(c.data), c.code, dev.ptr(c.indices), dev.ptr(c.indptr), dev.ptr(t.data),
+                      dev.ptr(t.indices), dev.ptr(t.indptr), n, self.m, self.k, C.byref(p), dev.ptr(pred), sp(0), sp(1),
+                      sp(2), sp(3), dev.ptr(self._tn_last), int(self._steps), dev.stream_ptr(self.device))
+        self._steps += n
+        self.n += n
+        if y_pred_format == "indices":
+            return pred.cpu().numpy()
+        return dev.compact_to_csr_like(y_proba, pred, reference_padding=False)
