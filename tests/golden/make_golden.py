@@ -413,8 +413,48 @@ def main_online_csr():
     np.savez_compressed(os.path.join(HERE, "online_csr.npz"), **out)
 
 
+def custom_fmeasure_like(tp, fp, fn, tn, gamma=0.3):
+    """a metric none of the libraries ships (used as the "arbitrary callable" of the goldens and of the tests)"""
+    return (tp + gamma * tp * tp) / (tp + 0.5 * fp + 0.7 * fn + 1e-6)
+
+
+def custom_with_tn(tp, fp, fn, tn):
+    return tp / (tp + fn + 1e-7) - 0.25 * fp / (fp + tn + 1e-7)
+
+
+def main_callables():
+    """callables.npz: predict_using_bc_with_0approx with an arbitrary callable and with a list of m callables
+    (block_coordinate.py:54-129) on the live reference."""
+    _install_shims()
+    from functools import partial
+
+    from xcolumns import block_coordinate as bc
+
+    from xcolumns_b200.synth import dense_probs
+
+    eta = dense_probs(260, 90, seed=52)
+    out = {"eta": eta}
+    m = eta.shape[1]
+    cases = {
+        "custom": (custom_fmeasure_like, dict(seed=0, skip_tn=True, metric_kwargs={"gamma": 0.3})),
+        "custom_tn_sum": (custom_with_tn, dict(seed=1, skip_tn=False, metric_aggregation="sum")),
+        "custom_min": (custom_fmeasure_like, dict(seed=2, skip_tn=True, maximize=False, max_iters=3)),
+        # a list of m callables: two distinct functions alternating over the labels
+        "list": ([custom_fmeasure_like if j % 2 == 0 else partial(custom_fmeasure_like, gamma=0.0) for j in range(m)],
+                 dict(seed=3, skip_tn=True)),
+    }
+    for name, (func, kw) in cases.items():
+        yp, meta = bc.predict_using_bc_with_0approx(eta, func, 4, return_meta=True, **kw)
+        out[name + "_pred"] = pred_to_idx(yp, 4)
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        print(f"  callables {name}: iters={meta['iters']} util={out[name + '_util']}")
+    np.savez_compressed(os.path.join(HERE, "callables.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "online_csr":
+    if len(sys.argv) > 1 and sys.argv[1] == "callables":
+        main_callables()
+    elif len(sys.argv) > 1 and sys.argv[1] == "online_csr":
         main_online_csr()
     elif len(sys.argv) > 1 and sys.argv[1] == "extra":
         main_extra()

@@ -491,6 +491,14 @@ def test_bca_mixed_batched_vs_oracle(xb, oracle):
     pred, meta = xb.predict_optimizing_instance_precision_using_bc(eta, 5, seed=0, return_meta=True, mode="batched")
     top = xb.predict_top_k(eta, 5)
     assert (pred == top).all()          # instance precision is maximised by the plain top-k
+    # mixed utility over a metric whose gain is NOT affine in eta (Jaccard: per-label records, block_coordinate.py:1000-1015)
+    for alpha in (0.4, 0.95):
+        pred, meta = xb.predict_optimizing_mixed_instance_precision_and_macro_jaccard_score_using_bc(
+            eta, 5, alpha=alpha, seed=0, return_meta=True, mode="batched")
+        _, ometa = oracle.predict_using_bc_with_0approx(eta, "jaccard", 5, metric_aggregation="sum", skip_tn=True, seed=0,
+                                                        mix=(alpha, 5, m))
+        assert meta["mode"] == "batched" and (pred.sum(1) == 5).all()
+        assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < 1e-4, (alpha, meta["utilities"], ometa["utilities"])
 
 
 @pytest.mark.gpu
@@ -740,3 +748,43 @@ def test_online_greedy_csr_golden(xb, golden, name, metric, skip_tn, etu):
     out = OnlineGreedy(m, k, _metric(xb, metric), skip_tn=skip_tn, etu_variant=etu).predict_update(y, None if etu else t)
     assert isinstance(out, csr_matrix) and out.shape == y.shape and out.dtype == y.dtype
     assert (np.diff(out.indptr) == k).all() and (out.indices.reshape(n, k) == g[name + "_pred"]).all()
+
+
+# ---- arbitrary metric callables / lists of callables (block_coordinate.py:54-129) -------------------------------
+def _custom_fmeasure_like(tp, fp, fn, tn, gamma=0.3):
+    return (tp + gamma * tp * tp) / (tp + 0.5 * fp + 0.7 * fn + 1e-6)
+
+
+def _custom_with_tn(tp, fp, fn, tn):
+    return tp / (tp + fn + 1e-7) - 0.25 * fp / (fp + tn + 1e-7)
+
+
+@pytest.mark.gpu
+def test_bca_arbitrary_callables_golden(xb, golden):
+    """a callable the library does not ship, and a list of m callables: evaluated on the device through torch tensors;
+    the sequential mode reproduces the live reference's predictions and utilities, the batched mode its final utility"""
+    from functools import partial
+    g = golden("callables")
+    eta = g["eta"]
+    m = eta.shape[1]
+    cases = {
+        "custom": (_custom_fmeasure_like, dict(seed=0, skip_tn=True, metric_kwargs={"gamma": 0.3})),
+        "custom_tn_sum": (_custom_with_tn, dict(seed=1, skip_tn=False, metric_aggregation="sum")),
+        "custom_min": (_custom_fmeasure_like, dict(seed=2, skip_tn=True, maximize=False, max_iters=3)),
+        "list": ([_custom_fmeasure_like if j % 2 == 0 else partial(_custom_fmeasure_like, gamma=0.0) for j in range(m)],
+                 dict(seed=3, skip_tn=True)),
+    }
+    for name, (func, kw) in cases.items():
+        pred, meta = xb.predict_using_bc_with_0approx(eta, func, 4, return_meta=True, mode="exact", **kw)
+        assert pred.dtype == eta.dtype and pred.shape == eta.shape
+        assert (_idx(pred, 4) == g[name + "_pred"]).all(), name
+        assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-12), name
+        if name in ("custom", "list"):
+            _, mb = xb.predict_using_bc_with_0approx(eta, func, 4, return_meta=True, mode="batched", batch_size=16, **kw)
+            assert abs(mb["utilities"][-1] - g[name + "_util"][-1]) < TOL, (name, mb["utilities"])
+    # torch input stays on its device
+    t = torch.from_numpy(eta).cuda()
+    pt = xb.predict_using_bc_with_0approx(t, _custom_fmeasure_like, 4, seed=0, skip_tn=True, mode="exact")
+    assert pt.is_cuda and (_idx(pt, 4) == g["custom_pred"]).all()
+    with pytest.raises(ValueError):
+        xb.predict_using_bc_with_0approx(eta, [_custom_with_tn] * 3, 4)

@@ -128,7 +128,7 @@ class BcaSession:
         self.state[3].fill_(-1.0)
         self.delta = torch.zeros((3, self.m), **f64)           # pending batch deltas (per-batch entry points)
         # Jaccard / G-mean / H-mean: 16-byte per-label records instead of the affine coefficient pairs
-        self.use_rec = (params.metric in M.RECORD_GAIN_METRICS) and not params.mix
+        self.use_rec = params.metric in M.RECORD_GAIN_METRICS
         clen = int(self.ctx.lib.xc_bca_coef_len(self.m))       # padded to whole coefficient tiles
         # Dense rows of one process, or of the ranks of one box with a peer window: the whole sweep is ONE C call
         # (xc_bca_sweep_dense_pipe); commits are applied `lag` batches late so consecutive batches overlap.
@@ -534,7 +534,15 @@ def predict_using_bc_with_0approx(
         raise ValueError("k must be >= 0")
     if k == 0 and isinstance(y_proba, csr_matrix):
         raise NotImplementedError("xcolumns_b200: BCA without a budget (k=0) is implemented for dense inputs only")
-    metric_id, beta, eps = M.resolve_binary_metric(binary_metric_func, metric_kwargs)
+    try:
+        metric_id, beta, eps = M.resolve_binary_metric(binary_metric_func, metric_kwargs)
+    except M.UnsupportedMetricError:
+        # any other callable, or a list of m callables (block_coordinate.py:54-129): evaluated on the device through
+        # torch tensors instead of inside the fused kernels (xcolumns_b200/generic_metric.py)
+        from .generic_metric import bca_generic
+        return bca_generic(y_proba, binary_metric_func, k, metric_aggregation, normalize_conf_matrix, metric_kwargs,
+                           maximize, tolerance, init_y_pred, max_iters, shuffle_order, skip_tn, return_meta, seed, verbose,
+                           mode, batch_size, y_pred_format, _initial_pred, _finish_pred)
     mix = M.resolve_mix(binary_metric_func)
     if metric_id in M.TN_METRICS and skip_tn:
         log_warning("skip_tn=True with a metric that uses true negatives: tn is the constant -1 like in the reference")
@@ -543,7 +551,7 @@ def predict_using_bc_with_0approx(
     if k > m:
         raise ValueError(f"k={k} is larger than the number of labels m={m}")
     greedy = isinstance(init_y_pred, str) and init_y_pred == "greedy"
-    batchable = metric_id in M.AFFINE_GAIN_METRICS or (metric_id in M.RECORD_GAIN_METRICS and mix is None)
+    batchable = metric_id in M.AFFINE_GAIN_METRICS or metric_id in M.RECORD_GAIN_METRICS
     mode = _resolve_mode(mode, n, greedy or k == 0 or not batchable or (metric_id in M.TN_METRICS and skip_tn))
 
     device = dev.pick_device(y_proba)

@@ -319,6 +319,18 @@ template <int METRIC>
 struct XfRecord {
     const float4 *rec;
     float sgn;
+    // mixed utility (1 - alpha) tp / k + alpha metric / m (block_coordinate.py:960-1045): the instance-precision part
+    // adds w1 * eta to every gain, the metric part is scaled by w2; (0, 1) for the plain metric
+    float w1, w2;
+    __device__ static XfRecord make(const float4 *rec, const xc_metric_params &p)
+    {
+        XfRecord x{rec, p.maximize ? 1.f : -1.f, 0.f, 1.f};
+        if (p.mix == 1) {
+            x.w1 = (float)((1.0 - p.mix_alpha) / (p.mix_k * p.n_div));
+            x.w2 = (float)(p.mix_alpha / p.mix_m);
+        }
+        return x;
+    }
     __device__ __forceinline__ float gain(const float4 r, float e) const
     {
         float g;
@@ -336,7 +348,7 @@ struct XfRecord {
                 g = num * __frcp_rn(fmaxf((xn + yn) * (r.x + r.y), 1e-30f));
             }
         }
-        return sgn * g;
+        return sgn * fmaf(w2, g, w1 * e);
     }
     template <typename TE, int V>
     __device__ __forceinline__ void apply_vec(int64_t c, const TE (&e)[V], float (&g)[V], float (&ca)[V],
@@ -387,7 +399,7 @@ bca_batch_dense_rec_kernel(xc_metric_params p, const TE *__restrict__ eta, int64
     const int lane = lane_id();
     const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
-    XfRecord<METRIC> xf{rec, p.maximize ? 1.f : -1.f};
+    const XfRecord<METRIC> xf = XfRecord<METRIC>::make(rec, p);
     const TE one = (TE)1;
     for (int64_t i = warp; i < n_rows; i += nwarps) {
         const int64_t row = rows ? (int64_t)rows[i] : i;
@@ -795,7 +807,7 @@ struct CsrGain {
             return fmaf(cf.x, (float)ev, cf.y);
         }
         if (sel) return (float)bca_selected_gain(p, tp[j], fp[j], fn[j], (double)ev, (double)(T)((T)1 - ev));
-        XfRecord<(METRIC < 0 ? XC_METRIC_JACCARD : METRIC)> xf{rec, p.maximize ? 1.f : -1.f};
+        const auto xf = XfRecord<(METRIC < 0 ? XC_METRIC_JACCARD : METRIC)>::make(rec, p);
         return xf.gain(__ldg(rec + j), (float)ev);
     }
 };
