@@ -362,12 +362,13 @@ XC_API int64_t xc_bca_delta_stride(int64_t m);
  * n_batches / lag / flags).  ref: block_coordinate.py:415-493 (the sweep loop: shuffle :419, per-instance steps
  * :448-463, utility :465-476) evaluated batch-wise.
  * Per batch g = batch0 + b (rows order[b * batch ...]): the streaming batch kernel accumulates the deltas of its
- * rows into delta buffer g % NB; the commit kernel then folds that buffer -- with a window: flags every peer,
- * waits for every peer's flag and adds the W buffers read over NVLink in rank order, so that the replicated
- * state stays bit-identical -- into tp/fp/fn, refreshes gain-coefficient set g % (lag + 1) (or the records of
+ * rows into delta buffer g % NB; the commit then folds that buffer -- with a window: a push kernel copies it into
+ * this rank's slot of every peer's inbox over NVLink and raises the rank's flag there, the commit kernel waits for
+ * every rank's flag and adds the W buffers (local memory) in rank order, so that the replicated state stays
+ * bit-identical -- into tp/fp/fn, refreshes gain-coefficient set g % (lag + 1) (or the records of
  * Jaccard / G-mean / H-mean) and clears buffer (g + lag + 1) % NB.  NB = xc_bca_pipe_buffers(lag) buffers of
- * xc_bca_delta_stride(m) bytes each: in the window's payload, or `delta` when w is NULL; all zero before the
- * first call, never touched by the host afterwards.  batch0: number of batches of all earlier calls on these
+ * xc_bca_delta_stride(m) bytes each: at the start of the window's payload (xc_bca_window_bytes), or `delta` when w
+ * is NULL; all zero before the first call, never touched by the host afterwards.  batch0: number of batches of all earlier calls on these
  * buffers (the rotation continues across sweeps).
  * lag = 0: strict order K_0, commit_0, K_1, ... on `stream`.  lag = L (1..3): batch g sees the state after commit
  * g - L - 1; L + 1 consecutive batch kernels run concurrently on as many internal streams, every commit overlaps
@@ -409,6 +410,9 @@ typedef struct {
                               /* drain; otherwise the new sweep's kernels wait for the previous sweep's.          */
 } xc_bca_pipe_args;
 XC_API int xc_bca_pipe_buffers(int lag);
+/* payload bytes a peer window needs for xc_bca_pipe_sweep: NB own delta buffers + world x NB inbox buffers (every
+ * rank PUSHES its deltas into its slot of every peer's inbox after a batch, so a commit only reads local memory) */
+XC_API int64_t xc_bca_window_bytes(int64_t m, int lag, int world);
 XC_API int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args *a, void *stream);
 XC_API int xc_bca_pipe_join(xc_ctx *ctx, void *stream);
 

@@ -107,9 +107,30 @@ sess.close()
 say("protocol stress: 60 sweeps x 30 commits with a delayed rank, state bit-identical on all ranks")
 
 # ---- 4: coverage -------------------------------------------------------------------------------------------------
+# (the product all-reduce the sharded coverage sweep relies on)
+probe = torch.full((5,), 1.0 + 0.125 * (rank + 1), dtype=torch.float64, device=device)
+comm.allreduce_prod_(probe)
+want = float(np.prod([1.0 + 0.125 * (r + 1) for r in range(world)]))
+assert abs(float(probe[0]) - want) < 1e-12 * want, (float(probe[0]), want)
 nc, mc = 2000 * world, 3000
 y = csr_probs(nc, mc, 40, seed=1006)
 lo, hi = shard_rows(nc, rank, world)
+# one sharded sweep by hand: the folded Ef must equal the Ef recomputed from the new predictions
+from xcolumns_b200.block_coordinate import CoverageSession  # noqa: E402
+from xcolumns_b200.weighted_prediction import topk_csr_device  # noqa: E402
+cs = CoverageSession(dev.csr_to_device(y[lo:hi], device), k, 1.0, comm)
+cs.pred = topk_csr_device(cs.data, k, None, None)[0]
+cs.state(XC_SUM_FAST)
+cs.utility_device(0)
+order_c = torch.randperm(hi - lo, device=device).int()
+cs.sweep_batched(order_c, 8, 250)
+ef_fold = cs.Ef.clone()
+cs.state(XC_SUM_FAST)
+cs.utility_device(1)
+rel = float(((ef_fold - cs.Ef).abs() / cs.Ef.abs().clamp_min(1e-300)).max())
+say(f"coverage by hand: u0={float(cs.util_buf[0]):.9f} u1={float(cs.util_buf[1]):.9f} max rel |Ef_fold - Ef_recomputed| = {rel:.2e}")
+assert rel < 1e-9, rel
+assert float(cs.util_buf[1]) >= float(cs.util_buf[0]) - 1e-9
 predc, metac = xb.predict_optimizing_coverage_using_bc(y[lo:hi], k, seed=0, mode="batched", distributed=True,
                                                        return_meta=True, y_pred_format="indices")
 say("coverage sharded meta:", {kk: metac[kk] for kk in ("utilities", "iters", "batch_size")})

@@ -72,7 +72,7 @@ def test_ctypes_prototypes_match_header():
                                      "xc_last_cuda_error", "xc_launch_count", "xc_sm_count", "xc_fill_pred_dense_host", "xc_scatter_pred_dense_host",
                                      "xc_zero_host", "xc_bca_coef_len", "xc_fw_alpha_scratch_bytes",
                                      "xc_fw_alpha_ctl_offset", "xc_p2p_payload", "xc_p2p_destroy", "xc_bca_delta_stride",
-                                     "xc_bca_pipe_buffers"}
+                                     "xc_bca_pipe_buffers", "xc_bca_window_bytes"}
     assert set(decls) == bound, f"unbound: {set(decls) - bound}, undeclared: {bound - set(decls)}"
 
 
@@ -117,10 +117,10 @@ def test_streaming_kernels_keep_their_occupancy():
         if "bca_batch_dense_kernelIfLi1ELb1E" in name:   # deep-prefetch variant: 4 CTAs + one commit CTA per SM
             assert reg <= 56 and stack == 0, (name, reg, stack)
             checked += 1
-        if "bca_commit_kernelILi8E" in name:             # must fit next to six resident streaming CTAs
+        if "bca_commit_kernel" in name or "bca_push_kernel" in name:             # must fit next to six resident streaming CTAs
             assert reg <= 64 and stack == 0, (name, reg, stack)
             checked += 1
-    assert checked >= 4, sorted(usage)[:5]
+    assert checked >= 5, sorted(usage)[:5]
 
 
 def test_dense_output_prefill_host_side(monkeypatch):

@@ -24,6 +24,19 @@ _T2NP = {torch.float32: np.float32, torch.float64: np.float64}
 _STAGED_MIN_BYTES = 64 << 20
 
 
+def host_threads() -> int:
+    """Host threads one process may use for the host-side helpers (clearing / filling the dense result, staging
+    copies): all cores of a single process, an equal share when several ranks of one box (torchrun sets
+    LOCAL_WORLD_SIZE) run the same helpers at the same time -- eight ranks with 32 threads each only fight over
+    the memory bus of the one host."""
+    cores = os.cpu_count() or 1
+    try:
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    except ValueError:
+        local_world = 1
+    return max(2, min(32, cores // local_world))
+
+
 def pick_device(*objs) -> torch.device:
     """Device of the first CUDA tensor among objs, else cuda:LOCAL_RANK / current device."""
     for o in objs:
@@ -134,7 +147,7 @@ def dense_to_device(x, device: torch.device, dtype=None, pad: bool = True) -> De
             t[:, m:].zero_()
         es = src.element_size()
         ctx_for(device).call("xc_h2d_staged", C.c_void_p(t.data_ptr()), ld * es, C.c_void_p(src.data_ptr()), m * es,
-                             m * es, n, 0, stream_ptr(device))
+                             m * es, n, min(16, host_threads()), stream_ptr(device))
     elif ld == m:
         t = src.to(device, non_blocking=True)
     else:
@@ -188,7 +201,7 @@ class DenseOutputPrefill:
         lib = _lib.load()
 
         def clear(arr=self.out):   # the closure keeps the array alive even if the caller bails out early
-            lib.xc_zero_host(arr.ctypes.data, arr.nbytes, 0)   # ctypes drops the GIL for the duration of the call
+            lib.xc_zero_host(arr.ctypes.data, arr.nbytes, host_threads())   # ctypes drops the GIL for the duration of the call
 
         self._thread = threading.Thread(target=clear, daemon=True)
         self._thread.start()
@@ -256,7 +269,7 @@ def _scatter_host(out: np.ndarray, idx: np.ndarray, vals: Optional[np.ndarray], 
     if out.dtype in _NP2CODE and out.flags.c_contiguous:
         fn = lib.xc_fill_pred_dense_host if zero else lib.xc_scatter_pred_dense_host
         rc = fn(out.ctypes.data, _NP2CODE[out.dtype], n, out.shape[1], out.shape[1], idx.ctypes.data,
-                None if v is None else v.ctypes.data, 0 if v is None else _NP2CODE[v.dtype], k, 0)
+                None if v is None else v.ctypes.data, 0 if v is None else _NP2CODE[v.dtype], k, host_threads())
         if rc != 0:
             raise XColumnsB200Error(f"xc_fill_pred_dense_host failed ({rc})")
         return

@@ -146,6 +146,8 @@ def load():
         lib.xc_bca_delta_stride.restype = C.c_int64
         lib.xc_bca_pipe_buffers.argtypes = [C.c_int]
         lib.xc_bca_pipe_buffers.restype = C.c_int
+        lib.xc_bca_window_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
+        lib.xc_bca_window_bytes.restype = C.c_int64
         lib.xc_bca_coef_len.argtypes = [C.c_int64]
         lib.xc_bca_coef_len.restype = C.c_int64
         lib.xc_fill_pred_dense_host.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,

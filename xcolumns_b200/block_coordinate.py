@@ -29,7 +29,7 @@ from scipy.sparse import csr_matrix
 from . import _device as dev
 from . import metrics as M
 from ._lib import XC_PIPE_FORK, XC_PIPE_SHUFFLE, XC_SUM_FAST, XC_SUM_ORDERED, MetricParams, PipeArgs
-from .distributed import Comm, PeerWindow, make_comm, peer_commit_enabled
+from .distributed import Comm, PeerWindow, borrow_window, make_comm, peer_commit_enabled
 from .types import Matrix
 from .utils import add_kwargs_to_signature, log_info, log_warning
 from .weighted_prediction import _check_k, topk_csr_device, topk_dense_device
@@ -144,12 +144,12 @@ class BcaSession:
         stride = int(self.ctx.lib.xc_bca_delta_stride(self.m))
         nbuf = int(self.ctx.lib.xc_bca_pipe_buffers(self.lag))
         if (not self.is_csr) and peer_commit_enabled(self.comm, self.device, self.m):
-            peer = PeerWindow(self.ctx, self.comm, nbuf * stride, self.device)
-            if peer.ok:
+            peer = borrow_window(self.ctx, self.comm,
+                                 int(self.ctx.lib.xc_bca_window_bytes(self.m, self.lag, self.comm.world)), nbuf * stride,
+                                 self.device)
+            if peer is not None:
                 self.peer = peer
                 self.pipe = True
-            else:
-                peer.close()
         self.delta_pipe = (torch.zeros(nbuf * stride, dtype=torch.uint8, device=self.device)
                            if (self.pipe and self.peer is None) else None)
         # CSR rows of one process: rows that fit one warp's registers take the reduction-based batch kernel and keep a
@@ -207,10 +207,9 @@ class BcaSession:
         self.join()
         if self.peer is not None:
             torch.cuda.synchronize(self.device)
-            self.comm.barrier()          # nobody may still be reading this rank's window
+            self.comm.barrier()          # every rank has left its last commit: the window can be handed back
             self.peer.check()
-            self.peer.close()
-            self.peer = None
+            self.peer = None             # (kept in the cache of xcolumns_b200.distributed for the next call)
 
     # -- state from the current prediction ---------------------------------------------------
     def recompute(self, order: int) -> None:

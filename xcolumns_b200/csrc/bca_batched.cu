@@ -81,17 +81,7 @@ bca_coef_kernel(xc_metric_params p, double *tp, double *fp, double *fn, double *
 
 __device__ __forceinline__ float4 bca_rec_of(const xc_metric_params &p, double t, double f, double g);
 
-// ---- commit over peer memory (rows sharded over the GPUs of one box) ----------------------------------
-// After a batch every rank holds the deltas of its own rows.  Instead of an NCCL all-reduce followed by
-// the coefficient kernel, ONE kernel per rank
-//   1. raises its flag in every peer's window (st.release.sys over NVLink),
-//   2. waits until every peer's flag for this commit has arrived (ld.acquire.sys on local memory),
-//   3. reads the W delta vectors straight out of the peers' windows (coalesced P2P loads, rank order,
-//      so every rank adds the same numbers in the same order and the replicated state stays bit-equal),
-//      folds them into its state, refreshes the gain coefficients and clears its OTHER delta buffer.
-// Deltas are double-buffered: batch b accumulates into buffer b & 1, so a peer that is one commit ahead
-// never overwrites what a slower rank is still reading (a rank passes barrier b only after every peer
-// finished commit b - 1).  A rank that waits longer than ~4 s raises the window's error word and leaves.
+// ---- commit over peer memory (rows sharded over the GPUs of one box): system-scope flag helpers ---------------
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -109,30 +99,64 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-// One commit = fold the deltas of one batch into the float64 state, refresh the gain coefficients (or the
-// Jaccard / G-mean / H-mean records) and clear the delta buffer a later batch will accumulate into.
-//   windows == nullptr : single process, the deltas are this GPU's own buffer `cur`
-//   windows != nullptr : peer-memory exchange as described above (flags + P2P reads in rank order)
-//   cur < 0            : no fold -- coefficients of the current state only (start of a sweep)
-// 64 threads and <= 64 registers per CTA: 4096 registers, which is what six resident CTAs of the streaming
-// batch kernel (6 x 256 x 40) leave free on an SM, so a commit never has to wait for a streaming CTA to
-// retire when the next batch is already running (pipelined sweep, see xc_bca_sweep_dense_pipe).
+// Exchange of one batch's deltas between the ranks of a box, PUSH model.  After its batch kernel every rank copies
+// its delta buffer into its slot of every peer's "inbox" (remote STORES over NVLink are posted: no round trip),
+// fences, and the last CTA to finish raises the rank's flag in every peer's window.  The commit kernel then waits
+// for all flags and reads nothing but LOCAL memory.  (First version: the commit kernel PULLED the peers' buffers
+// with remote loads -- three dependent rounds of NVLink round trips per label; measured on 8 x B200: 62 us per
+// commit, which made the commit chain, not the streaming, the critical path of a strong-scaled sweep.)
+// Window payload: [NB own delta buffers | world x NB inbox buffers], each xc_bca_delta_stride(m) bytes.
+// A slot is overwritten NB = 2 (lag + 1) commits later; by then its reader has left the commit that read it (see the
+// flag argument at xc_bca_pipe_sweep).
 constexpr int kCommitThreads = 64;
 
-template <int WMAX>
 __global__ void __launch_bounds__(kCommitThreads)
-bca_commit_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_t *const *windows, int world, int rank,
-                  unsigned epoch, double *local, int64_t win_off, int64_t stride, int cur, int clr, int64_t m,
-                  float2 *coef_n, float2 *coef_s, float2 *coef_n2, float2 *coef_s2, int rec)
+bca_push_kernel(uint8_t *const *windows, int world, int rank, unsigned epoch, int64_t own_off, int64_t inbox_off,
+                int64_t stride, int nb, int cur, int64_t m)
 {
-    __shared__ int s_fail;
-    if (windows && cur >= 0) {
-        uint8_t *mine = windows[rank];
-        if (threadIdx.x == 0) s_fail = 0;
-        if (blockIdx.x == 0 && threadIdx.x < world) {
+    __shared__ int s_last;
+    uint8_t *mine = windows[rank];
+    const double *src = reinterpret_cast<const double *>(mine + own_off + (int64_t)cur * stride);
+    const int64_t slot = inbox_off + ((int64_t)rank * nb + cur) * stride;
+    for (int64_t i = (int64_t)blockIdx.x * kCommitThreads + threadIdx.x; i < 3 * m; i += (int64_t)gridDim.x * kCommitThreads) {
+        const double v = src[i];
+        for (int r = 0; r < world; ++r)
+            if (r != rank) reinterpret_cast<double *>(windows[r] + slot)[i] = v;
+    }
+    __threadfence_system();   // this thread's stores are visible system-wide before the ticket
+    __syncthreads();
+    unsigned *ticket = reinterpret_cast<unsigned *>(mine) + XC_P2P_ERR_WORD + 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {   // every CTA of this rank has pushed: tell the peers
+        if (threadIdx.x == 0) *ticket = 0;
+        if (threadIdx.x < world) {
             __threadfence_system();
             st_release_sys(reinterpret_cast<unsigned *>(windows[threadIdx.x]) + rank, epoch);
         }
+    }
+}
+
+// One commit = fold the deltas of one batch into the float64 state, refresh the gain coefficients (or the
+// Jaccard / G-mean / H-mean records) and clear the delta buffer a later batch will accumulate into.
+//   windows == nullptr : single process, the deltas are this GPU's own buffer `cur`
+//   windows != nullptr : wait for every rank's flag (bca_push_kernel), then add the W buffers -- the peers' from the
+//                        local inbox, in rank order, so every rank adds the same numbers in the same order and the
+//                        replicated state stays bit-equal.  A rank that waits longer than ~4 s raises the window's
+//                        error word and leaves.
+//   cur < 0            : no fold -- coefficients of the current state only (start of a sweep)
+// 64 threads and <= 64 registers per CTA: 4096 registers, which is what six resident CTAs of the streaming
+// batch kernel (6 x 256 x 40) leave free on an SM, so a commit never has to wait for a streaming CTA to
+// retire when the next batch is already running (pipelined sweep, see xc_bca_pipe_sweep).
+__global__ void __launch_bounds__(kCommitThreads, 16)
+bca_commit_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_t *const *windows, int world, int rank,
+                  unsigned epoch, double *local, int64_t inbox_off, int64_t stride, int nb, int cur, int clr, int64_t m,
+                  float2 *coef_n, float2 *coef_s, float2 *coef_n2, float2 *coef_s2, int rec)
+{
+    __shared__ int s_fail;
+    const uint8_t *mine = windows ? windows[rank] : nullptr;
+    if (windows && cur >= 0) {
+        if (threadIdx.x == 0) s_fail = 0;
         __syncthreads();
         if (threadIdx.x < world) {
             const unsigned *flag = reinterpret_cast<const unsigned *>(mine) + threadIdx.x;
@@ -141,7 +165,7 @@ bca_commit_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_
             while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
                 if (global_timer_ns() - t0 > 4000000000ULL) {
                     s_fail = 1;
-                    reinterpret_cast<unsigned *>(mine)[XC_P2P_ERR_WORD] = epoch;
+                    reinterpret_cast<unsigned *>(windows[rank])[XC_P2P_ERR_WORD] = epoch;
                     break;
                 }
             }
@@ -152,26 +176,20 @@ bca_commit_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_
     for (int64_t j = (int64_t)blockIdx.x * kCommitThreads + threadIdx.x; j < m; j += (int64_t)gridDim.x * kCommitThreads) {
         double t = tp[j], f = fp[j], g = fn[j];
         if (cur >= 0) {
-            double d[3];
-            if (windows) {
-#pragma unroll
-                for (int v = 0; v < 3; ++v) {
-                    double x[WMAX];   // all peers' values in flight, then added in rank order (bit-identical on every rank)
-#pragma unroll
-                    for (int r = 0; r < WMAX; ++r) {
-                        x[r] = 0.0;
-                        if (r < world)
-                            x[r] = __ldcv(reinterpret_cast<const double *>(windows[r] + win_off + (int64_t)cur * stride) +
-                                          v * m + j);
-                    }
-                    double acc = 0.0;
-#pragma unroll
-                    for (int r = 0; r < WMAX; ++r) acc += x[r];   // x[r] = 0 beyond world: exact
-                    d[v] = acc;
+            const double *dl = reinterpret_cast<const double *>(reinterpret_cast<const uint8_t *>(local) +
+                                                                (int64_t)cur * stride);
+            double d[3] = {0.0, 0.0, 0.0};
+            if (windows) {   // every rank's buffer is local memory by now; added in rank order
+#pragma unroll 4
+                for (int r = 0; r < world; ++r) {
+                    const double *src = r == rank ? dl
+                                                  : reinterpret_cast<const double *>(mine + inbox_off +
+                                                                                     ((int64_t)r * nb + cur) * stride);
+                    d[0] += __ldcv(src + j);
+                    d[1] += __ldcv(src + m + j);
+                    d[2] += __ldcv(src + 2 * m + j);
                 }
             } else {
-                const double *dl = reinterpret_cast<const double *>(reinterpret_cast<const uint8_t *>(local) +
-                                                                    (int64_t)cur * stride);
                 d[0] = dl[j]; d[1] = dl[m + j]; d[2] = dl[2 * m + j];
             }
             t += d[0]; f += d[1]; g += d[2];
@@ -1753,9 +1771,10 @@ struct PipeCommit {
     xc_p2p *w;
     const xc_metric_params *p;
     double *tp, *fp, *fn;
-    double *local;
-    int64_t win_off, stride, m;
-    int rec;
+    double *local;                 // this rank's NB delta buffers
+    int64_t win_off, inbox_off;    // byte offsets inside a window: own buffers, inbox (world x NB buffers)
+    int64_t stride, m;
+    int nb, rec;
 };
 
 int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *set_b, int64_t clen, cudaStream_t st)
@@ -1767,16 +1786,15 @@ int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *se
     uint8_t *const *windows = c.w ? c.w->windows_dev : nullptr;
     const int world = c.w ? c.w->world : 1, rank = c.w ? c.w->rank : 0;
     unsigned epoch = 0;
-    if (c.w && cur >= 0) epoch = ++c.w->epoch;
-#define XC_GO(WMAX)                                                                                                   \
-    bca_commit_kernel<WMAX><<<grid, kCommitThreads, 0, st>>>(*c.p, c.tp, c.fp, c.fn, windows, world, rank, epoch,       \
-                                                             c.local, c.win_off, c.stride, cur, clr, c.m, an, as, bn, \
-                                                             bs, c.rec)
-    if (world <= 2) XC_GO(2);
-    else if (world <= 4) XC_GO(4);
-    else if (world <= 8) XC_GO(8);
-    else XC_GO(16);
-#undef XC_GO
+    if (c.w && cur >= 0) {
+        epoch = ++c.w->epoch;
+        // my deltas into every peer's inbox, then my flag
+        bca_push_kernel<<<grid, kCommitThreads, 0, st>>>(windows, world, rank, epoch, c.win_off, c.inbox_off, c.stride,
+                                                         c.nb, cur, c.m);
+        XC_LAUNCHED(c.ctx);
+    }
+    bca_commit_kernel<<<grid, kCommitThreads, 0, st>>>(*c.p, c.tp, c.fp, c.fn, windows, world, rank, epoch, c.local,
+                                                       c.inbox_off, c.stride, c.nb, cur, clr, c.m, an, as, bn, bs, c.rec);
     XC_LAUNCHED(c.ctx);
     return XC_OK;
 }
@@ -1784,6 +1802,13 @@ int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *se
 }  // namespace
 
 static_assert(sizeof(xc_bca_pipe_args) == 200, "xc_bca_pipe_args layout (mirrored by ctypes in _lib.py)");
+
+// payload bytes of a peer window for the pipelined sweep: NB own delta buffers + world x NB inbox buffers
+extern "C" int64_t xc_bca_window_bytes(int64_t m, int lag, int world)
+{
+    const int64_t nb = 2 * ((lag < 0 ? 0 : (lag > XC_PIPE_MAX_LAG ? XC_PIPE_MAX_LAG : lag)) + 1);
+    return (nb + (int64_t)(world < 1 ? 1 : world) * nb) * xc_bca_delta_stride(m);
+}
 
 extern "C" int xc_bca_pipe_buffers(int lag) { return 2 * ((lag < 0 ? 0 : (lag > XC_PIPE_MAX_LAG ? XC_PIPE_MAX_LAG : lag)) + 1); }
 
@@ -1826,10 +1851,11 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
     if (rec) lag = 0;   // the record kernels read the float64 state of the selected labels: no overlap with a commit
     const int S = lag + 1, NB = 2 * S;   // S batches in flight on S streams, S coefficient sets, 2 S delta buffers
     const int64_t stride = xc_bca_delta_stride(m), clen = xc_bca_coef_len(m);
-    if (w && (size_t)(XC_P2P_HEADER + NB * stride) > w->bytes) return XC_ERR_INVALID;
+    if (w && (size_t)(XC_P2P_HEADER + xc_bca_window_bytes(m, lag, w->world)) > w->bytes) return XC_ERR_INVALID;
     cudaStream_t caller = (cudaStream_t)stream;
     double *local = w ? reinterpret_cast<double *>(w->windows[w->rank] + XC_P2P_HEADER) : a->delta;
-    PipeCommit c{ctx, w, p, a->tp, a->fp, a->fn, local, (int64_t)XC_P2P_HEADER, stride, m, rec ? 1 : 0};
+    PipeCommit c{ctx, w, p, a->tp, a->fp, a->fn, local, (int64_t)XC_P2P_HEADER, (int64_t)XC_P2P_HEADER + NB * stride,
+                 stride, m, NB, rec ? 1 : 0};
     float *set[XC_PIPE_MAX_LAG + 1];
     for (int i = 0; i <= XC_PIPE_MAX_LAG; ++i) set[i] = a->coef + (int64_t)(i < S ? i : 0) * 4 * clen;
     // $XCOLUMNS_B200_PIPE_SERIAL=1 (tests): the same dependency order on ONE stream, nothing overlaps
