@@ -382,10 +382,19 @@ def test_permutation_is_a_bijection(xb):
             assert not torch.equal(outs[0], torch.arange(n, dtype=torch.int32, device=device))
 
 
-def test_unsupported_metric_is_loud(xb):
+def test_unsupported_requests_are_loud(xb):
+    """what no kernel exists for fails with NotImplementedError instead of falling back to the CPU: arbitrary callables on
+    CSR rows / without a budget, an arbitrary Frank-Wolfe objective"""
     eta = np.random.rand(10, 20).astype(np.float32)
     with pytest.raises(NotImplementedError):
-        xb.predict_using_bc_with_0approx(eta, lambda tp, fp, fn, tn: tp, 3)
+        xb.predict_using_bc_with_0approx(csr_matrix(eta), lambda tp, fp, fn, tn: tp, 3)
+    with pytest.raises(NotImplementedError):
+        xb.predict_using_bc_with_0approx(eta, lambda tp, fp, fn, tn: tp, 0)
+    with pytest.raises(NotImplementedError):
+        xb.find_classifier_using_fw(eta, eta, lambda tp, fp, fn, tn: tp.mean(), 3)
+    # an arbitrary callable on dense rows runs on the device (tests below); tp maximised -> plain top-k of eta
+    pred = xb.predict_using_bc_with_0approx(eta, lambda tp, fp, fn, tn: tp, 3, seed=0)
+    assert (_idx(pred, 3) == np.sort(np.argsort(-eta, axis=1, kind="stable")[:, :3], axis=1)).all()
 
 
 # ------------------------------------------------------------------------------------------
