@@ -112,6 +112,11 @@ probe = torch.full((5,), 1.0 + 0.125 * (rank + 1), dtype=torch.float64, device=d
 comm.allreduce_prod_(probe)
 want = float(np.prod([1.0 + 0.125 * (r + 1) for r in range(world)]))
 assert abs(float(probe[0]) - want) < 1e-12 * want, (float(probe[0]), want)
+# NCCL's own product all-reduce on a vector of the size the coverage sweep uses (diagnostic only: Comm avoids it)
+big = torch.full((3000,), 1.0, dtype=torch.float64, device=device)
+big[rank::world] = 0.5
+dist.all_reduce(big, op=dist.ReduceOp.PRODUCT)
+say("NCCL ReduceOp.PRODUCT on 3000 float64: max |x - 0.5| =", float((big - 0.5).abs().max()), "(0 = correct)")
 nc, mc = 2000 * world, 3000
 y = csr_probs(nc, mc, 40, seed=1006)
 lo, hi = shard_rows(nc, rank, world)

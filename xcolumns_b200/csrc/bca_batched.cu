@@ -1777,6 +1777,22 @@ struct PipeCommit {
     int nb, rec;
 };
 
+// my deltas of buffer `cur` into every peer's inbox, then my flag (sharded rows only).  Issued on the BATCH stream
+// right behind the batch kernel: a push depends on nothing but its own batch, so it must not queue behind the
+// (serial) commits of earlier batches -- measured at 8 GPUs: push + commit on the commit stream made every commit
+// 36 us and the commit chain the critical path of the sweep (0.46 ms), see profiles/r02_notes.md.
+int launch_push(const PipeCommit &c, int cur, cudaStream_t st)
+{
+    if (!c.w) return XC_OK;
+    const int64_t want = (3 * c.m + kCommitThreads - 1) / kCommitThreads;
+    const int grid = (int)(want < c.ctx->sm_count ? want : c.ctx->sm_count);
+    const unsigned epoch = ++c.w->epoch;
+    bca_push_kernel<<<grid, kCommitThreads, 0, st>>>(c.w->windows_dev, c.w->world, c.w->rank, epoch, c.win_off, c.inbox_off,
+                                                     c.stride, c.nb, cur, c.m);
+    XC_LAUNCHED(c.ctx);
+    return XC_OK;
+}
+
 int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *set_b, int64_t clen, cudaStream_t st)
 {
     const int64_t want = (c.m + kCommitThreads - 1) / kCommitThreads;
@@ -1785,14 +1801,7 @@ int launch_commit(const PipeCommit &c, int cur, int clr, float *set_a, float *se
     float2 *bn = set_b ? (float2 *)set_b : nullptr, *bs = set_b ? (float2 *)(set_b + 2 * clen) : nullptr;
     uint8_t *const *windows = c.w ? c.w->windows_dev : nullptr;
     const int world = c.w ? c.w->world : 1, rank = c.w ? c.w->rank : 0;
-    unsigned epoch = 0;
-    if (c.w && cur >= 0) {
-        epoch = ++c.w->epoch;
-        // my deltas into every peer's inbox, then my flag
-        bca_push_kernel<<<grid, kCommitThreads, 0, st>>>(windows, world, rank, epoch, c.win_off, c.inbox_off, c.stride,
-                                                         c.nb, cur, c.m);
-        XC_LAUNCHED(c.ctx);
-    }
+    const unsigned epoch = (c.w && cur >= 0) ? c.w->epoch : 0u;   // the epoch launch_push raised the flags with
     bca_commit_kernel<<<grid, kCommitThreads, 0, st>>>(*c.p, c.tp, c.fp, c.fn, windows, world, rank, epoch, c.local,
                                                        c.inbox_off, c.stride, c.nb, cur, clr, c.m, an, as, bn, bs, c.rec);
     XC_LAUNCHED(c.ctx);
@@ -1954,6 +1963,8 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             if (rc) return rc;
             if (e1) XC_CUDA_TRY(ctx, cudaEventRecord(e1, st[si]));
         }
+        rc = launch_push(c, cur, st[si]);   // sharded rows: publish this batch's deltas as soon as the batch is done
+        if (rc) return rc;
         if (forked) {   // commit_g follows K_g (and, on its own stream, commit_{g-1})
             XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[si], st[si]));
             XC_CUDA_TRY(ctx, cudaStreamWaitEvent(cst, ctx->ev_k[si], 0));

@@ -334,15 +334,21 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
             }
         }
     }
+    // the row's current selection is prefetched one step ahead like the row itself (a row is visited once per
+    // sweep, so nobody rewrites it before its turn)
+    int myp_next = -1;
+    if (n_order > 0 && lane < k) myp_next = __ldg(pred_idx + (order ? (int64_t)order[0] : 0) * k + lane);
     cluster.sync();
 
     for (int64_t s = 0; s < n_order; ++s) {
         const int64_t row = order ? (int64_t)order[s] : s;
         int32_t *prow = pred_idx + row * k;
+        const int myp = myp_next;   // the row's current selection, one label per lane
 #pragma unroll
         for (int l = 0; l < L; ++l) { pv[l] = pnext[l]; av[l] = anext[l]; }
         if (s + 1 < n_order) {
             const int64_t rnext = order ? (int64_t)order[s + 1] : s + 1;
+            if (lane < k) myp_next = __ldg(pred_idx + rnext * k + lane);
 #pragma unroll
             for (int l = 0; l < L; ++l) {
                 int64_t j = j0 + l * stride;
@@ -353,7 +359,6 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
             }
         }
         // ---- 1. remove own contribution, gains (block_coordinate.py:157-185) --------------------------
-        int myp = lane < k ? __ldg(prow + lane) : -1;   // the row's current selection, one label per lane
         double gain[L];
 #pragma unroll
         for (int l = 0; l < L; ++l) {
@@ -1184,6 +1189,19 @@ int dispatch_exact_cluster(xc_ctx *ctx, const void *eta, int64_t m, int64_t ld, 
         if (nc <= CL_MAX)                                                                                            \
             return launch_exact_cluster<TE, LL, TH>(ctx, nc, eta, m, ld, order, n_order, k, p, greedy, pred_idx, tp, \
                                                     fp, fn, tn, st, addback, ld_add);                                \
+    }
+    // Few labels per CTA and many CTAs: the per-instance cost is the float64 divisions of the gains (10 per label;
+    // vector FP64 is ~16 lanes / clk / SM on this part), which a single SM with 512 labels needs ~5 us for --
+    // the cluster barrier and the DSMEM exchange cost ~1.5 us whatever the cluster size.  $XCOLUMNS_B200_EXACT_CTA=512
+    // restores the wide CTAs.
+    static int wide = -1;
+    if (wide < 0) {
+        const char *e = getenv("XCOLUMNS_B200_EXACT_CTA");
+        wide = (e && atoi(e) == 512) ? 1 : 0;
+    }
+    if (!wide) {
+        if (ncta(128) <= CL_MAX) XC_TRY(1, 128)
+        if (ncta(256) <= CL_MAX) XC_TRY(1, 256)
     }
     if (ncta(512) <= 8) XC_TRY(1, 512)
     if (ncta(1024) <= 8) XC_TRY(2, 512)
