@@ -126,5 +126,7 @@ def test_error_convention(xb):
         xb.find_classifier_using_fw(eta, eta, M.macro_f1_score_on_conf_matrix, 2, init_classifier="nope")
     with pytest.raises(ValueError):
         xb.find_classifier_using_fw(eta, eta, M.macro_f1_score_on_conf_matrix, 2, alpha_search_algo="golden")
-    with pytest.raises(NotImplementedError):
-        xb.predict_using_bc_with_0approx(eta, lambda tp, fp, fn, tn: tp, 2)   # arbitrary callable: loud, no fallback
+    with pytest.raises(NotImplementedError):   # arbitrary callables run on the device for dense rows only: loud, no fallback
+        xb.predict_using_bc_with_0approx(csr_matrix(eta), lambda tp, fp, fn, tn: tp, 2)
+    with pytest.raises(ValueError):             # a list of callables must have one entry per label
+        xb.predict_using_bc_with_0approx(eta, [M.binary_f1_score_on_conf_matrix] * 3, 2)
