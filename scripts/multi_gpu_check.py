@@ -107,20 +107,13 @@ sess.close()
 say("protocol stress: 60 sweeps x 30 commits with a delayed rank, state bit-identical on all ranks")
 
 # ---- 4: coverage -------------------------------------------------------------------------------------------------
-# (the product all-reduce the sharded coverage sweep relies on)
-probe = torch.full((5,), 1.0 + 0.125 * (rank + 1), dtype=torch.float64, device=device)
-comm.allreduce_prod_(probe)
-want = float(np.prod([1.0 + 0.125 * (r + 1) for r in range(world)]))
-assert abs(float(probe[0]) - want) < 1e-12 * want, (float(probe[0]), want)
-# NCCL's own product all-reduce on a vector of the size the coverage sweep uses (diagnostic only: Comm avoids it)
-big = torch.full((3000,), 1.0, dtype=torch.float64, device=device)
-big[rank::world] = 0.5
-dist.all_reduce(big, op=dist.ReduceOp.PRODUCT)
-say("NCCL ReduceOp.PRODUCT on 3000 float64: max |x - 0.5| =", float((big - 0.5).abs().max()), "(0 = correct)")
-nc, mc = 2000 * world, 3000
+# the same 4 000 x 3 000 problem whatever the number of ranks (the rows every commit gathers, batch x world, stay a
+# fixed fraction of n like in the single-GPU mode)
+nc, mc = 4000, 3000
 y = csr_probs(nc, mc, 40, seed=1006)
 lo, hi = shard_rows(nc, rank, world)
-# one sharded sweep by hand: the folded Ef must equal the Ef recomputed from the new predictions
+# one sharded sweep by hand: the folded Ef must equal the Ef recomputed from the new predictions (absolute: products
+# of thousands of factors run into the denormals, where the two orders of multiplication legitimately differ)
 from xcolumns_b200.block_coordinate import CoverageSession  # noqa: E402
 from xcolumns_b200.weighted_prediction import topk_csr_device  # noqa: E402
 cs = CoverageSession(dev.csr_to_device(y[lo:hi], device), k, 1.0, comm)
@@ -128,13 +121,14 @@ cs.pred = topk_csr_device(cs.data, k, None, None)[0]
 cs.state(XC_SUM_FAST)
 cs.utility_device(0)
 order_c = torch.randperm(hi - lo, device=device).int()
-cs.sweep_batched(order_c, 8, 250)
+bsz = max(1, 16 // world)
+cs.sweep_batched(order_c, bsz, comm.max_int((hi - lo + bsz - 1) // bsz))
 ef_fold = cs.Ef.clone()
 cs.state(XC_SUM_FAST)
 cs.utility_device(1)
-rel = float(((ef_fold - cs.Ef).abs() / cs.Ef.abs().clamp_min(1e-300)).max())
-say(f"coverage by hand: u0={float(cs.util_buf[0]):.9f} u1={float(cs.util_buf[1]):.9f} max rel |Ef_fold - Ef_recomputed| = {rel:.2e}")
-assert rel < 1e-9, rel
+err = float((ef_fold - cs.Ef).abs().max())
+say(f"coverage by hand: u0={float(cs.util_buf[0]):.9f} u1={float(cs.util_buf[1]):.9f} max |Ef_fold - Ef_recomputed| = {err:.2e}")
+assert err < 1e-12, err
 assert float(cs.util_buf[1]) >= float(cs.util_buf[0]) - 1e-9
 predc, metac = xb.predict_optimizing_coverage_using_bc(y[lo:hi], k, seed=0, mode="batched", distributed=True,
                                                        return_meta=True, y_pred_format="indices")

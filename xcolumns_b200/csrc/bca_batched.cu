@@ -125,14 +125,16 @@ bca_push_kernel(uint8_t *const *windows, int world, int rank, unsigned epoch, in
     }
     __threadfence_system();   // this thread's stores are visible system-wide before the ticket
     __syncthreads();
-    unsigned *ticket = reinterpret_cast<unsigned *>(mine) + XC_P2P_ERR_WORD + 1;
+    // (one ticket and one flag per buffer: the pushes of consecutive batches run on different streams and may
+    //  overlap or finish out of order; pushes into the same buffer are NB batches apart on one stream)
+    unsigned *ticket = reinterpret_cast<unsigned *>(mine) + XC_P2P_TICKET_WORD + cur;
     if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (s_last) {   // every CTA of this rank has pushed: tell the peers
+    if (s_last) {   // every CTA of this rank has pushed buffer `cur`: tell the peers
         if (threadIdx.x == 0) *ticket = 0;
         if (threadIdx.x < world) {
             __threadfence_system();
-            st_release_sys(reinterpret_cast<unsigned *>(windows[threadIdx.x]) + rank, epoch);
+            st_release_sys(reinterpret_cast<unsigned *>(windows[threadIdx.x]) + cur * XC_P2P_MAX_WORLD + rank, epoch);
         }
     }
 }
@@ -159,9 +161,9 @@ bca_commit_kernel(xc_metric_params p, double *tp, double *fp, double *fn, uint8_
         if (threadIdx.x == 0) s_fail = 0;
         __syncthreads();
         if (threadIdx.x < world) {
-            const unsigned *flag = reinterpret_cast<const unsigned *>(mine) + threadIdx.x;
+            const unsigned *flag = reinterpret_cast<const unsigned *>(mine) + cur * XC_P2P_MAX_WORLD + threadIdx.x;
             const unsigned long long t0 = global_timer_ns();
-            // flags only grow; a peer may already be ahead (wrap-safe signed distance)
+            // the flag of (buffer, sender) only grows; a peer may already be a rotation ahead (wrap-safe signed distance)
             while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
                 if (global_timer_ns() - t0 > 4000000000ULL) {
                     s_fail = 1;
@@ -1852,6 +1854,7 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
     if (w && !w->opened) return XC_ERR_INVALID;
     if (a->k < 1 || a->k > 32 || a->k > m) return XC_ERR_INVALID;
     if (p->metric < 0 || p->metric > XC_METRIC_PREC_AT_K) return XC_ERR_INVALID;
+    static_assert(2 * (XC_PIPE_MAX_LAG + 1) <= XC_P2P_MAX_BUF, "one flag row / ticket per delta buffer");
     if (a->n_batches * a->batch < n_order) return XC_ERR_INVALID;
     if (a->util_out && !a->util_params) return XC_ERR_INVALID;
     const bool rec = p->metric == XC_METRIC_JACCARD || p->metric == XC_METRIC_GMEAN || p->metric == XC_METRIC_HMEAN;

@@ -71,6 +71,7 @@ extern "C" int xc_p2p_error(xc_ctx *ctx, xc_p2p *w, unsigned *out)
     XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !w || !out) return XC_ERR_INVALID;
     XC_CUDA_TRY(ctx, cudaMemcpy(out, w->windows[w->rank] + 4 * XC_P2P_ERR_WORD, 4, cudaMemcpyDeviceToHost));
+    if (*out) XC_CUDA_TRY(ctx, cudaMemset(w->windows[w->rank] + 4 * XC_P2P_ERR_WORD, 0, 4));   // reported once (windows are reused)
     return XC_OK;
 }
 

@@ -40,11 +40,15 @@ struct xc_ctx {
 constexpr int XC_RED_MAX_BLOCKS = 1024;
 
 // Peer-memory window of one rank (csrc/p2p.cu): cudaMalloc'ed, exported with CUDA IPC and mapped by
-// every other rank of the box.  Layout: [0, 256) one arrival flag per rank, word XC_P2P_ERR_WORD the
-// error word, [XC_P2P_HEADER, ...) payload (the double-buffered BCA delta vectors).
+// every other rank of the box.  Header layout (32-bit words): flag[buffer][sender] at buffer * XC_P2P_MAX_WORLD + sender
+// for the XC_P2P_MAX_BUF rotating delta buffers (a flag holds the epoch of the last push into that buffer slot; pushes
+// of different buffers may complete out of order, pushes into one buffer are stream-ordered), the error word, one
+// ticket counter per buffer (the pushes of different buffers run concurrently); [XC_P2P_HEADER, ...) payload.
 constexpr int XC_P2P_MAX_WORLD = 16;
-constexpr int XC_P2P_ERR_WORD = 64;
-constexpr int XC_P2P_HEADER = 512;
+constexpr int XC_P2P_MAX_BUF = 8;                                   // 2 * (XC_PIPE_MAX_LAG + 1)
+constexpr int XC_P2P_ERR_WORD = XC_P2P_MAX_WORLD * XC_P2P_MAX_BUF;  // 128
+constexpr int XC_P2P_TICKET_WORD = XC_P2P_ERR_WORD + 1;             // 129 .. 136
+constexpr int XC_P2P_HEADER = 1024;
 struct xc_p2p {
     int world;
     int rank;

@@ -46,19 +46,8 @@ class Comm:
         return t
 
     def allreduce_prod_(self, t: torch.Tensor) -> torch.Tensor:
-        """element-wise product over the ranks, in rank order on every rank (bit-identical results).  Not
-        ReduceOp.PRODUCT: measured on 8 x B200 (NCCL 2.28.9), the product all-reduce of a 24 KB float64 vector returned
-        wrong values while a 40-byte one was right (scripts/multi_gpu_check.py) -- the sharded coverage sweep multiplied
-        garbage into its state.  An all-gather + local product is exact and, for the m-length vectors of this path,
-        just as cheap."""
         if self.active and self.world > 1:
-            flat = t.contiguous().view(-1)
-            buf = torch.empty((self.world, flat.numel()), dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(buf.view(-1), flat, group=self.group)
-            acc = buf[0].clone()
-            for r in range(1, self.world):
-                acc.mul_(buf[r])
-            t.copy_(acc.view_as(t))
+            dist.all_reduce(t, op=dist.ReduceOp.PRODUCT, group=self.group)
             self.n_allreduce += 1
         return t
 
