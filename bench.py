@@ -60,6 +60,29 @@ def parse():
     return ap.parse_args()
 
 
+def kernel_source_sha():
+    """hash of the sources the dominant kernel is compiled from (ties profiles/traffic.json to a build)"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("bca_batched.cu", "xc_scan.cuh", "xc_common.cuh"):
+        with open(os.path.join(ROOT, "xcolumns_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def load_traffic():
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by scripts/ncu_traffic.py).  Returned only if the capture was taken with the
+    sources of THIS build; a stale capture reads as null instead of silently describing another kernel."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t.get("source_sha") == kernel_source_sha():
+            return t
+        return {"stale": True, "captured_with": t.get("source_sha"), "this_build": kernel_source_sha()}
+    except Exception:
+        return None
+
+
 def load_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
@@ -486,6 +509,7 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
         st, en, rows = read_kernel_timing(sess.ctx)
         sess.ctx.call("xc_timing_enable", 0)
         peak, peak_src = load_peak()
+        traffic = load_traffic()
         if os.environ.get("BENCH_DUMP_TIMELINE") and len(st):   # diagnostics: last sweep incl. commits (rows = 0), ms
             per_all = len(st) // args.steps
             t0 = float(st[-per_all:].min())
@@ -501,7 +525,8 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
             achieved = bytes_total / (busy_ms / 1e3) / 1e9
             res["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "bca_batch_dense_kernel<float,1>",
+                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "traffic_detail": traffic, "kernel": "bca_batch_dense_kernel<float,1>",
                 "bytes_per_launch": bytes_total / len(st), "avg_launch_ms": busy_ms / len(st),
                 "launches": int(len(st)),
                 "timing": ("CUDA events around every launch on the stream it is launched on; consecutive batches run on two "

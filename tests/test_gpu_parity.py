@@ -15,9 +15,25 @@ TOL = 1e-4  # north_star: batched-BCA and FW metric values within 1e-4 absolute
 def _tol_from_reference_spread(run_oracle, base):
     """1e-4, unless the REFERENCE algorithm itself moves more than that between instance orders
     (seeds) on this input -- BCA stops in order-dependent fixed points for some objectives; then
-    the block-Jacobi result is held to twice the reference's own seed-to-seed spread."""
+    the block-Jacobi result is held to twice the reference's own seed-to-seed spread.  The flat-1e-4 checks at
+    BASELINE.json's own shapes live in tests/test_gpu_baseline_shapes.py; the measured deviations of the cases below
+    are recorded by _record (gpurun_out/parity_deltas.jsonl) and summarised in DESIGN.md section 2."""
     vals = [base] + [run_oracle(s) for s in (1, 2)]
     return max(TOL, 2 * (max(vals) - min(vals)))
+
+
+def _record(case, delta, tol):
+    """append a measured batched-vs-reference deviation to gpurun_out/parity_deltas.jsonl (scratch) and print it"""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_deltas.jsonl"), "a") as f:
+            f.write(json.dumps({"case": case, "delta": float(delta), "tolerance_used": float(tol)}) + "\n")
+    except OSError:
+        pass
+    print(case, "delta", float(delta), "tolerance", float(tol))
 
 
 @pytest.fixture(scope="module")
@@ -289,6 +305,7 @@ def test_bca_batched_dense_vs_oracle(xb, oracle, metric):
         ometa["utilities"][-1])
     if metric in ("f1", "recall", "balanced_accuracy"):
         assert tol == TOL
+    _record(f"dense_6000x2000_{metric}_batched_vs_oracle", meta["utilities"][-1] - ometa["utilities"][-1], tol)
     assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol
     # the returned prediction really has the reported utility (recomputed by the oracle)
     tp, fp, fn, tn = oracle.calculate_confusion_matrix(eta, pred, skip_tn=skip, dtype=np.float64)
@@ -324,6 +341,7 @@ def test_bca_batched_csr_vs_oracle(xb, oracle):
     tol = _tol_from_reference_spread(
         lambda s: oracle.predict_using_bc_with_0approx(y, "f1", 5, seed=s, skip_tn=True)[1]["utilities"][-1],
         ometa["utilities"][-1])
+    _record("csr_4000x20000_f1_batched_vs_oracle", meta["utilities"][-1] - ometa["utilities"][-1], tol)
     assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol
 
 
@@ -418,8 +436,12 @@ def test_fw_dense_golden(xb, golden, name, metric, yt, kw):
     assert clf.a.shape == g[name + "_a"].shape and clf.a.dtype == np.float32 and clf.p.dtype == np.float32
     assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=TOL)
     assert np.allclose(meta["classifiers_utilities"], g[name + "_cutil"], rtol=0, atol=TOL)
-    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=5e-3)
-    assert np.allclose(clf.p, g[name + "_p"], rtol=0, atol=5e-3)
+    # the line search's arg-max within ONE step of the reference's 1e-4 grid (the CPU oracle reproduces the live
+    # reference's alphas exactly; the float32 screen + float64 refinement of the GPU search must land on the same point
+    # or, where the objective is flat to float64 rounding, its neighbour)
+    _record(f"fw_{name}_max_dalpha", float(np.abs(np.asarray(meta["alphas"]) - g[name + "_alphas"]).max()), 1.01e-4)
+    assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1.01e-4)
+    assert np.allclose(clf.p, g[name + "_p"], rtol=0, atol=5e-4)
 
 
 def test_fw_vs_oracle_and_predict(xb, oracle):
@@ -696,6 +718,7 @@ def test_bca_batched_csr_record_metrics_vs_oracle(xb, oracle, metric):
     tol = _tol_from_reference_spread(
         lambda s: oracle.predict_using_bc_with_0approx(y, metric, 5, seed=s, skip_tn=skip)[1]["utilities"][-1],
         ometa["utilities"][-1])
+    _record(f"csr_3000x900_{metric}_batched_vs_oracle", meta["utilities"][-1] - ometa["utilities"][-1], tol)
     assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol, (meta["utilities"], ometa["utilities"])
 
 

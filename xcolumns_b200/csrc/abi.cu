@@ -73,6 +73,8 @@ extern "C" void xc_ctx_destroy(xc_ctx *ctx)
             cudaStreamDestroy(ctx->aux[i]);
             cudaEventDestroy(ctx->ev_k[i]);
             cudaEventDestroy(ctx->ev_c[i]);
+            cudaStreamDestroy(ctx->pstream[i]);
+            cudaEventDestroy(ctx->ev_p[i]);
         }
         for (int i = 0; i <= XC_PIPE_MAX_LAG + 1; ++i) cudaEventDestroy(ctx->ev_join[i]);
         cudaStreamDestroy(ctx->cstream);
@@ -155,6 +157,8 @@ int xc_ctx_aux_streams(xc_ctx *ctx)
         XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, lo));
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_c[i], cudaEventDisableTiming));
+        XC_CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->pstream[i], cudaStreamNonBlocking, hi));
+        XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_p[i], cudaEventDisableTiming));
     }
     for (int i = 0; i <= XC_PIPE_MAX_LAG + 1; ++i)
         XC_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));

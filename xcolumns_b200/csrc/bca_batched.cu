@@ -1966,11 +1966,26 @@ extern "C" int xc_bca_pipe_sweep(xc_ctx *ctx, xc_p2p *w, const xc_bca_pipe_args 
             if (rc) return rc;
             if (e1) XC_CUDA_TRY(ctx, cudaEventRecord(e1, st[si]));
         }
-        rc = launch_push(c, cur, st[si]);   // sharded rows: publish this batch's deltas as soon as the batch is done
-        if (rc) return rc;
-        if (forked) {   // commit_g follows K_g (and, on its own stream, commit_{g-1})
+        if (forked) {
+            // commit_g follows K_g (and, on its own stream, commit_{g-1}).  Sharded rows: the batch's deltas are
+            // published as soon as the batch is done, by a push on a HIGH-priority stream of its own -- a push depends on
+            // nothing but its batch, so it neither queues behind the (serial) commits of earlier batches nor, as a
+            // low-priority launch on the batch stream would, behind the pending CTAs of the batch kernels already in
+            // the hardware queue (measured at 8 GPUs: 36 us per commit in the first case, pushes delayed by a whole
+            // row time in the second; profiles/r02_notes.md section 2)
             XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_k[si], st[si]));
-            XC_CUDA_TRY(ctx, cudaStreamWaitEvent(cst, ctx->ev_k[si], 0));
+            if (w) {
+                XC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->pstream[si], ctx->ev_k[si], 0));
+                rc = launch_push(c, cur, ctx->pstream[si]);
+                if (rc) return rc;
+                XC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_p[si], ctx->pstream[si]));
+                XC_CUDA_TRY(ctx, cudaStreamWaitEvent(cst, ctx->ev_p[si], 0));
+            } else {
+                XC_CUDA_TRY(ctx, cudaStreamWaitEvent(cst, ctx->ev_k[si], 0));
+            }
+        } else {
+            rc = launch_push(c, cur, st[si]);
+            if (rc) return rc;
         }
         cudaEvent_t c0 = nullptr, c1 = nullptr;
         if (ctx->timing_on && ctx->timing_commits) {   // (diagnostics: rows = 0 marks a commit in the timing log)

@@ -22,6 +22,8 @@ struct xc_ctx {
     // pipelined batched sweep (bca_batched.cu): two internal streams + ordering events, created on first use
     cudaStream_t aux[XC_PIPE_MAX_LAG + 1];   // batch kernels, one stream per batch in flight (low priority)
     cudaStream_t cstream;                    // commits + sweep utilities (high priority: dispatched ahead of pending batch CTAs)
+    cudaStream_t pstream[XC_PIPE_MAX_LAG + 1];   // pushes of the batch deltas to the peers (high priority, one per batch stream)
+    cudaEvent_t ev_p[XC_PIPE_MAX_LAG + 1];
     cudaEvent_t ev_fork, ev_c[XC_PIPE_MAX_LAG + 1], ev_join[XC_PIPE_MAX_LAG + 2], ev_k[XC_PIPE_MAX_LAG + 1], ev_pro, ev_util;
     bool aux_ready;
     bool pipe_active;            // sweeps issued since the last join: the coefficient sets follow the commits
