@@ -121,3 +121,28 @@ def test_vectorised_classifier_draw_is_the_reference_stream():
             assert (_draw_classifiers(p, 4000, seed) == ref).all()
     with pytest.raises(ValueError):
         _draw_classifiers(np.array([0.5, 0.6]), 10, 0)
+
+
+def test_batch_and_lag_policy(monkeypatch):
+    """host-side scheduling rules of the batched sweeps (xcolumns_b200/block_coordinate.py)"""
+    from xcolumns_b200 import _device as dev
+    from xcolumns_b200.block_coordinate import _default_lag, coverage_batch_rows, default_batch_rows
+    wave = 7104
+    # n/8 rounded UP (no ninth commit over a handful of rows), whole waves once a batch exceeds one
+    assert default_batch_rows(38375, wave) == 4797 and -(-38375 // 4797) == 8
+    assert default_batch_rows(307000, wave) == 35520 and default_batch_rows(307000, wave) % wave == 0
+    assert default_batch_rows(5, 0) == 1 and default_batch_rows(0, wave) == 1
+    monkeypatch.delenv("XCOLUMNS_B200_LAG", raising=False)
+    # two batch kernels in flight fill the GPU when a batch is >= 4 waves; smaller batches get a third
+    assert _default_lag(35520, wave) == 1 and _default_lag(14208, wave) == 2 and _default_lag(4797, wave) == 2
+    monkeypatch.setenv("XCOLUMNS_B200_LAG", "0")
+    assert _default_lag(4797, wave) == 0
+    monkeypatch.setenv("XCOLUMNS_B200_LAG", "9")
+    assert _default_lag(4797, wave) == 3
+    assert coverage_batch_rows(153000) == 4096 and coverage_batch_rows(3000) == 93 and coverage_batch_rows(10) == 1
+    # host threads of the result helpers: an equal share per local rank
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    monkeypatch.setattr("os.cpu_count", lambda: 32)
+    assert dev.host_threads() == 4
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert dev.host_threads() == 32

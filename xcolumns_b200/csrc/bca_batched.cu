@@ -1779,10 +1779,8 @@ struct PipeCommit {
     int nb, rec;
 };
 
-// my deltas of buffer `cur` into every peer's inbox, then my flag (sharded rows only).  Issued on the BATCH stream
-// right behind the batch kernel: a push depends on nothing but its own batch, so it must not queue behind the
-// (serial) commits of earlier batches -- measured at 8 GPUs: push + commit on the commit stream made every commit
-// 36 us and the commit chain the critical path of the sweep (0.46 ms), see profiles/r02_notes.md.
+// my deltas of buffer `cur` into every peer's inbox, then my flag (sharded rows only); see the call site for the
+// stream it is issued on
 int launch_push(const PipeCommit &c, int cur, cudaStream_t st)
 {
     if (!c.w) return XC_OK;
