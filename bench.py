@@ -520,7 +520,7 @@ def bench_dense(args, device, comm, n_local, n_global_hint, sampler=None, want_r
         if len(st):
             per = len(st) // args.steps
             busy = [union_ms(st[i * per:(i + 1) * per], en[i * per:(i + 1) * per]) for i in range(args.steps)]
-            busy_ms = float(np.sum(busy))
+            busy_ms = union_ms(st, en)   # over the whole timed region (consecutive sweeps overlap, too)
             bytes_total = float(rows.sum()) * m * 4
             achieved = bytes_total / (busy_ms / 1e3) / 1e9
             res["roofline"] = {

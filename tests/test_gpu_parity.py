@@ -306,7 +306,9 @@ def test_bca_batched_dense_vs_oracle(xb, oracle, metric):
     if metric in ("f1", "recall", "balanced_accuracy"):
         assert tol == TOL
     _record(f"dense_6000x2000_{metric}_batched_vs_oracle", meta["utilities"][-1] - ometa["utilities"][-1], tol)
-    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol
+    # flat 1e-4 for every metric on this input (measured: |delta| <= 2.5e-5, macro-precision included); `tol` only
+    # documents how far the reference itself moves between instance orders
+    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < TOL
     # the returned prediction really has the reported utility (recomputed by the oracle)
     tp, fp, fn, tn = oracle.calculate_confusion_matrix(eta, pred, skip_tn=skip, dtype=np.float64)
     mid, c1, b2, eps = oracle.metric_params(metric)
@@ -341,8 +343,11 @@ def test_bca_batched_csr_vs_oracle(xb, oracle):
     tol = _tol_from_reference_spread(
         lambda s: oracle.predict_using_bc_with_0approx(y, "f1", 5, seed=s, skip_tn=True)[1]["utilities"][-1],
         ometa["utilities"][-1])
-    _record("csr_4000x20000_f1_batched_vs_oracle", meta["utilities"][-1] - ometa["utilities"][-1], tol)
-    assert abs(meta["utilities"][-1] - ometa["utilities"][-1]) < tol
+    d = meta["utilities"][-1] - ometa["utilities"][-1]
+    _record("csr_4000x20000_f1_batched_vs_oracle", d, tol)
+    # never worse than the sequential reference by more than 1e-4; on this very sparse input the block-Jacobi fixed point
+    # is BETTER (measured +3.1e-4, the reference's own seed-to-seed spread is 2.4e-4), bounded by twice that spread
+    assert d > -TOL and abs(d) < tol
 
 
 def test_coverage_batched_vs_oracle(xb, oracle):
