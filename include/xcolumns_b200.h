@@ -438,7 +438,9 @@ XC_API int xc_timing_read(xc_ctx *ctx, int cap, double *start_ms_host, double *e
  * fused with the accumulation of tp_j = sum_i y_true[i][j] * yhat[i][j] and
  * cnt_j = sum_i yhat[i][j] (float64).  a, b and y_true have eta's dtype (numpy promotes the
  * float32 classifier rows to it); gains = eta * a + b with separate IEEE multiply and add.
- * y_true may alias eta.  tp/cnt are zeroed by the call.  pred_idx [n, k] is optional.         */
+ * y_true may alias eta.  tp/cnt are zeroed by the call.  pred_idx [n, k] is optional.
+ * k = 0 (no budget): every label with a gain >= 0 is predicted; on CSR rows only the STORED
+ * labels take part (numba_csr_functions.py:516-517, :631-653); pred_idx must be NULL then.    */
 XC_API int xc_fw_iterate_dense(xc_ctx *ctx, const void *eta, int dtype, int64_t n, int64_t m,
                                int64_t ld, const void *y_true, int64_t ld_true, const void *a,
                                const void *b, int k, double *tp, double *cnt, int32_t *pred_idx,

@@ -141,9 +141,22 @@ def predict_weighted_per_instance(y_proba, k: int, th: float = 0.0, a=None, b=No
                                   dtype=None, keep_scores: bool = False):
     """Same container/dtype/shape contract as the reference (weighted_prediction.py:91-188)."""
     if isinstance(y_proba, csr_matrix):
-        if k <= 0:
-            raise NotImplementedError("oracle: CSR k=0")
         n, m = y_proba.shape
+        if k <= 0:
+            # numba_csr_functions.py:631-653 -> :564-570 -> :516-517: the STORED labels of a row whose gain
+            # (data * a[idx] + b[idx], numpy promotion) is >= th, appended row by row; data = ones in the data dtype
+            g = y_proba.data
+            if a is not None:
+                g = g * np.asarray(a)[y_proba.indices]
+            if b is not None:
+                g = g + np.asarray(b)[y_proba.indices]
+            thv = np.asarray(th)[y_proba.indices] if np.ndim(th) > 0 else th
+            keep = g >= thv
+            rows = np.repeat(np.arange(n), np.diff(y_proba.indptr))
+            counts = np.bincount(rows[keep], minlength=n)
+            indptr = np.concatenate([[0], np.cumsum(counts)]).astype(y_proba.indptr.dtype)
+            return csr_matrix((np.ones(int(keep.sum()), dtype=y_proba.data.dtype), y_proba.indices[keep], indptr),
+                              shape=(n, m), dtype=dtype)
         idx, val = topk_indices_csr(y_proba, k, a, b, keep_scores)
         indptr = (np.arange(n + 1, dtype=y_proba.indptr.dtype) * k)
         return csr_matrix((val.reshape(-1), idx.reshape(-1).astype(y_proba.indices.dtype), indptr),

@@ -451,9 +451,119 @@ def main_callables():
     np.savez_compressed(os.path.join(HERE, "callables.npz"), **out)
 
 
+def custom_tversky(tp, fp, fn, tn, gamma=0.5):
+    """a macro objective the library does not ship (Tversky index): plain arithmetic + .mean(), so it runs on numpy
+    arrays, autograd boxes and torch tensors alike"""
+    return ((1 + gamma) * tp / ((1 + gamma) * tp + gamma * fp + fn + 1e-6)).mean()
+
+
+def custom_tpr_tnr(tp, fp, fn, tn):
+    return (tp / (tp + fn + 1e-6) * tn / (tn + fp + 1e-6)).mean()
+
+
+def main_fw_generic():
+    """fw_generic.npz: (a) Frank-Wolfe and randomized-classifier prediction WITHOUT a budget (k = 0) on CSR inputs
+    (frank_wolfe.py:130-172, numba_csr_functions.py:516-517, :631-653); (b) find_classifier_using_fw with objective
+    callables that are not built-in metrics (frank_wolfe.py:368-376), dense and CSR -- all on the live reference."""
+    _install_shims()
+    from xcolumns import frank_wolfe as fw
+    from xcolumns import metrics as mt
+
+    from xcolumns_b200.synth import csr_probs, dense_probs
+
+    out = {}
+    y = csr_probs(300, 400, 12, seed=3)
+    rng = np.random.default_rng(1)
+    yt = y.copy()
+    yt.data = (rng.random(y.nnz) < y.data).astype(y.data.dtype)
+    yt.eliminate_zeros()
+    for nm, mat in (("y", y), ("yt", yt)):
+        out[nm + "_data"], out[nm + "_indices"], out[nm + "_indptr"] = mat.data, mat.indices, mat.indptr
+    out["shape"] = np.array(y.shape)
+
+    def store(name, clf, meta):
+        out[name + "_a"], out[name + "_b"], out[name + "_p"] = np.asarray(clf.a), np.asarray(clf.b), np.asarray(clf.p)
+        out[name + "_alphas"] = np.array(meta["alphas"], dtype=np.float64)
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        out[name + "_cutil"] = np.array([float(u) for u in meta["classifiers_utilities"]], dtype=np.float64)
+        out[name + "_iters"] = np.array(meta["iters"])
+        print(f"  {name}: iters={meta['iters']} alphas={out[name + '_alphas']} util={out[name + '_util']}")
+
+    # (a) k = 0 on CSR rows
+    clf, meta = fw.find_classifier_using_fw(yt, y, mt.macro_f1_score_on_conf_matrix, 0, max_iters=8, seed=0,
+                                            skip_tn=True, return_meta=True)
+    store("k0_f1", clf, meta)
+    yp = clf.predict(y, seed=5)
+    yp.sort_indices()
+    out["k0_f1_pred_indices"], out["k0_f1_pred_indptr"] = yp.indices[:yp.indptr[-1]].copy(), yp.indptr.copy()
+    clf, meta = fw.find_classifier_using_fw(yt, y, mt.macro_balanced_accuracy_on_conf_matrix, 0, max_iters=5, seed=0,
+                                            return_meta=True)
+    store("k0_balacc", clf, meta)
+    # randomized prediction without a budget from hand-made classifiers (weights in the data dtype: the reference's
+    # numba step cannot unify float32 rows with float64 weights)
+    ra = (0.5 + rng.random((3, 400))).astype(np.float32)
+    rb = (0.4 * rng.standard_normal((3, 400)) - 0.3).astype(np.float32)
+    rp = np.array([0.5, 0.3, 0.2])
+    yp = fw.predict_using_randomized_weighted_classifier(y, 0, ra, rb, rp, seed=11)
+    yp.sort_indices()
+    out["rnd_a"], out["rnd_b"], out["rnd_p"] = ra, rb, rp
+    out["rnd_pred_indices"], out["rnd_pred_indptr"] = yp.indices[:yp.indptr[-1]].copy(), yp.indptr.copy()
+    print(f"  rnd k0: nnz={yp.indptr[-1]}")
+
+    # (b) objectives that are not built-in metrics
+    eta = dense_probs(300, 200, seed=77)
+    lab = (np.random.default_rng(6).random(eta.shape) < eta).astype(np.float32)
+    out["eta"], out["lab"] = eta, lab
+    clf, meta = fw.find_classifier_using_fw(lab, eta, custom_tversky, 4, max_iters=8, seed=0, skip_tn=True,
+                                            metric_kwargs={"gamma": 0.7}, return_meta=True)
+    store("tversky", clf, meta)
+    clf, meta = fw.find_classifier_using_fw(lab, eta, custom_tpr_tnr, 4, max_iters=6, seed=0, return_meta=True)
+    store("tpr_tnr", clf, meta)
+    clf, meta = fw.find_classifier_using_fw(lab, eta, custom_tversky, 4, max_iters=6, seed=0, skip_tn=True,
+                                            alpha_search_algo="ternary", return_meta=True)
+    store("tversky_ternary", clf, meta)
+    clf, meta = fw.find_classifier_using_fw(lab, eta, custom_tversky, 4, max_iters=5, seed=0, skip_tn=True,
+                                            search_for_best_alpha=False, return_meta=True)
+    store("tversky_fixed", clf, meta)
+    clf, meta = fw.find_classifier_using_fw(yt, y, custom_tversky, 3, max_iters=6, seed=0, skip_tn=True,
+                                            return_meta=True)
+    store("tversky_csr", clf, meta)
+    np.savez_compressed(os.path.join(HERE, "fw_generic.npz"), **out)
+    print(f"fw_generic: {os.path.getsize(os.path.join(HERE, 'fw_generic.npz')) / 1024:.0f} KiB")
+
+
+def main_callables_csr():
+    """callables_csr.npz: predict_using_bc_with_0approx on CSR rows with callables that are not built-in metrics
+    (block_coordinate.py:212-293 through :93-129) on the live reference."""
+    _install_shims()
+    from xcolumns import block_coordinate as bc
+    from xcolumns import weighted_prediction as wp
+
+    from xcolumns_b200.synth import csr_probs
+
+    y = csr_probs(220, 300, 14, seed=61, ragged=True)
+    out = {"data": y.data, "indices": y.indices, "indptr": y.indptr, "shape": np.array(y.shape)}
+    cases = {
+        "custom": (custom_fmeasure_like, 4, dict(seed=0, skip_tn=True, metric_kwargs={"gamma": 0.3})),
+        "custom_tn_sum": (custom_with_tn, 3, dict(seed=1, skip_tn=False, metric_aggregation="sum")),
+        "custom_min": (custom_fmeasure_like, 4, dict(seed=2, skip_tn=True, maximize=False, max_iters=3)),
+    }
+    for name, (func, k, kw) in cases.items():
+        yp, meta = bc.predict_using_bc_with_0approx(y, func, k, return_meta=True, **kw)
+        yp.sort_indices()
+        out[name + "_indices"], out[name + "_indptr"] = yp.indices[:yp.indptr[-1]].copy(), yp.indptr.copy()
+        out[name + "_util"] = np.array([float(u) for u in meta["utilities"]], dtype=np.float64)
+        print(f"  callables_csr {name}: iters={meta['iters']} util={out[name + '_util']}")
+    np.savez_compressed(os.path.join(HERE, "callables_csr.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "callables":
         main_callables()
+    elif len(sys.argv) > 1 and sys.argv[1] == "callables_csr":
+        main_callables_csr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "fw_generic":
+        main_fw_generic()
     elif len(sys.argv) > 1 and sys.argv[1] == "online_csr":
         main_online_csr()
     elif len(sys.argv) > 1 and sys.argv[1] == "extra":

@@ -406,15 +406,19 @@ def test_permutation_is_a_bijection(xb):
 
 
 def test_unsupported_requests_are_loud(xb):
-    """what no kernel exists for fails with NotImplementedError instead of falling back to the CPU: arbitrary callables on
-    CSR rows / without a budget, an arbitrary Frank-Wolfe objective"""
+    """what no device path exists for fails with NotImplementedError instead of falling back to the CPU: arbitrary
+    callables without a budget, a LIST of callables on CSR rows (the reference's own CSR step indexes such a list by the
+    position of a stored entry, block_coordinate.py:110-127)"""
     eta = np.random.rand(10, 20).astype(np.float32)
     with pytest.raises(NotImplementedError):
-        xb.predict_using_bc_with_0approx(csr_matrix(eta), lambda tp, fp, fn, tn: tp, 3)
+        xb.predict_using_bc_with_0approx(csr_matrix(eta), [lambda tp, fp, fn, tn: tp] * 20, 3)
     with pytest.raises(NotImplementedError):
         xb.predict_using_bc_with_0approx(eta, lambda tp, fp, fn, tn: tp, 0)
-    with pytest.raises(NotImplementedError):
-        xb.find_classifier_using_fw(eta, eta, lambda tp, fp, fn, tn: tp.mean(), 3)
+    # an arbitrary callable on CSR rows and as a Frank-Wolfe objective runs on the device (tests below)
+    predc = xb.predict_using_bc_with_0approx(csr_matrix(eta), lambda tp, fp, fn, tn: tp, 3, seed=0)
+    assert isinstance(predc, csr_matrix) and (np.diff(predc.indptr) == 3).all()
+    clf = xb.find_classifier_using_fw(eta, eta, lambda tp, fp, fn, tn: tp.mean(), 3, max_iters=2)
+    assert clf.a.shape[1] == 20
     # an arbitrary callable on dense rows runs on the device (tests below); tp maximised -> plain top-k of eta
     pred = xb.predict_using_bc_with_0approx(eta, lambda tp, fp, fn, tn: tp, 3, seed=0)
     assert (_idx(pred, 3) == np.sort(np.argsort(-eta, axis=1, kind="stable")[:, :3], axis=1)).all()
@@ -693,8 +697,6 @@ def test_fw_no_budget_golden(xb, golden):
     yp = ref_clf.predict(eta, seed=3)
     assert yp.shape == eta.shape and yp.dtype == eta.dtype
     assert ((yp != 0).astype(np.uint8) != g["fw_k0_pred"]).mean() < 1e-6
-    with pytest.raises(NotImplementedError):
-        xb.find_classifier_using_fw(csr_matrix(eta), csr_matrix(eta), M.macro_f1_score_on_conf_matrix, 0)
 
 
 @pytest.mark.gpu
@@ -825,3 +827,107 @@ def test_bca_arbitrary_callables_golden(xb, golden):
     assert pt.is_cuda and (_idx(pt, 4) == g["custom_pred"]).all()
     with pytest.raises(ValueError):
         xb.predict_using_bc_with_0approx(eta, [_custom_with_tn] * 3, 4)
+
+
+def _fw_generic_csr(g):
+    shape = tuple(g["shape"])
+    y = csr_matrix((g["y_data"], g["y_indices"], g["y_indptr"]), shape=shape)
+    yt = csr_matrix((g["yt_data"], g["yt_indices"], g["yt_indptr"]), shape=shape)
+    return y, yt
+
+
+@pytest.mark.gpu
+def test_fw_and_randomized_prediction_no_budget_csr_golden(xb, golden):
+    """k = 0 on CSR rows (the STORED labels with data * a + b >= 0; numba_csr_functions.py:516-517, :631-653) in
+    Frank-Wolfe and in the randomized classifier's prediction vs the live reference"""
+    from xcolumns_b200 import metrics as M
+    from xcolumns_b200.frank_wolfe import RandomizedWeightedClassifier
+    g = golden("fw_generic")
+    y, yt = _fw_generic_csr(g)
+    clf, meta = xb.find_classifier_using_fw(yt, y, M.macro_f1_score_on_conf_matrix, 0, max_iters=8, seed=0,
+                                            skip_tn=True, return_meta=True)
+    assert np.allclose(meta["alphas"], g["k0_f1_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["k0_f1_util"], rtol=0, atol=1e-5)
+    assert clf.a.shape == g["k0_f1_a"].shape and np.allclose(clf.p, g["k0_f1_p"], atol=1e-6)
+    clf, meta = xb.find_classifier_using_fw(yt, y, M.macro_balanced_accuracy_on_conf_matrix, 0, max_iters=5, seed=0,
+                                            return_meta=True)
+    assert np.allclose(meta["alphas"], g["k0_balacc_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["k0_balacc_util"], rtol=0, atol=1e-5)
+    # float64 rows go through the float64 instantiation of the kernel
+    y64, yt64 = y.astype(np.float64), yt.astype(np.float64)
+    _, meta64 = xb.find_classifier_using_fw(yt64, y64, M.macro_f1_score_on_conf_matrix, 0, max_iters=8, seed=0,
+                                            skip_tn=True, return_meta=True)
+    assert np.allclose(meta64["utilities"], g["k0_f1_util"], rtol=0, atol=1e-5)
+    # prediction with the REFERENCE's classifiers and numpy's random stream: the same CSR matrix
+    ref_clf = RandomizedWeightedClassifier(0, g["k0_f1_a"], g["k0_f1_b"], g["k0_f1_p"])
+    yp = ref_clf.predict(y, seed=5)
+    assert isinstance(yp, csr_matrix) and yp.shape == y.shape and yp.dtype == y.dtype
+    assert (yp.indptr == g["k0_f1_pred_indptr"]).all() and (yp.indices == g["k0_f1_pred_indices"]).all()
+    assert (yp.data == 1).all()
+    yr = xb.predict_using_randomized_weighted_classifier(y, 0, g["rnd_a"], g["rnd_b"], g["rnd_p"], seed=11)
+    assert (yr.indptr == g["rnd_pred_indptr"]).all() and (yr.indices == g["rnd_pred_indices"]).all()
+
+
+def _tversky(tp, fp, fn, tn, gamma=0.5):
+    return ((1 + gamma) * tp / ((1 + gamma) * tp + gamma * fp + fn + 1e-6)).mean()
+
+
+def _tpr_tnr(tp, fp, fn, tn):
+    return (tp / (tp + fn + 1e-6) * tn / (tn + fp + 1e-6)).mean()
+
+
+@pytest.mark.gpu
+def test_fw_arbitrary_objective_callables_golden(xb, golden):
+    """find_classifier_using_fw with objectives that are NOT built-in metrics (frank_wolfe.py:368-376): streaming
+    kernels + torch autograd / vmapped line search on the device (generic_fw.py) vs the live reference"""
+    g = golden("fw_generic")
+    eta, lab = g["eta"], g["lab"]
+    y, yt = _fw_generic_csr(g)
+    cases = [("tversky", lab, eta, _tversky, 4, dict(max_iters=8, skip_tn=True, metric_kwargs={"gamma": 0.7})),
+             ("tpr_tnr", lab, eta, _tpr_tnr, 4, dict(max_iters=6)),
+             ("tversky_ternary", lab, eta, _tversky, 4, dict(max_iters=6, skip_tn=True, alpha_search_algo="ternary")),
+             ("tversky_fixed", lab, eta, _tversky, 4, dict(max_iters=5, skip_tn=True, search_for_best_alpha=False)),
+             ("tversky_csr", yt, y, _tversky, 3, dict(max_iters=6, skip_tn=True))]
+    for name, t, p, func, k, kw in cases:
+        clf, meta = xb.find_classifier_using_fw(t, p, func, k, seed=0, return_meta=True, **kw)
+        assert meta["iters"] == int(g[name + "_iters"]), name
+        assert np.allclose(meta["alphas"], g[name + "_alphas"], rtol=0, atol=1e-9), (name, meta["alphas"])
+        assert np.allclose(meta["utilities"], g[name + "_util"], rtol=0, atol=1e-5), (name, meta["utilities"])
+        assert np.allclose(meta["classifiers_utilities"], g[name + "_cutil"], rtol=0, atol=1e-5), name
+        assert isinstance(clf.a, np.ndarray) and clf.a.dtype == np.float32 and clf.a.shape == g[name + "_a"].shape
+        assert np.allclose(clf.p, g[name + "_p"], atol=1e-6), name
+        assert np.allclose(clf.a, g[name + "_a"], rtol=2e-3, atol=1e-4), name
+        assert np.allclose(clf.b, g[name + "_b"], rtol=2e-3, atol=1e-4), name
+    # tensors in -> tensors out on the same device
+    clf, meta = xb.find_classifier_using_fw(torch.from_numpy(lab).cuda(), torch.from_numpy(eta).cuda(), _tversky, 4,
+                                            seed=0, return_meta=True, max_iters=8, skip_tn=True,
+                                            metric_kwargs={"gamma": 0.7})
+    assert clf.a.is_cuda and clf.p.is_cuda
+    assert np.allclose(meta["utilities"], g["tversky_util"], rtol=0, atol=1e-5)
+    # a callable that does not return a scalar is refused
+    with pytest.raises(ValueError):
+        xb.find_classifier_using_fw(lab, eta, lambda tp, fp, fn, tn: tp, 4, max_iters=2)
+
+
+@pytest.mark.gpu
+def test_bca_arbitrary_callables_csr_golden(xb, golden):
+    """metric callables that are not built-in, on CSR rows (block_coordinate.py:212-293): sequential mode vs the live
+    reference (rows with fewer than k stored labels included), block-Jacobi mode vs its final utility"""
+    g = golden("callables_csr")
+    y = csr_matrix((g["data"], g["indices"], g["indptr"]), shape=tuple(g["shape"]))
+    cases = {
+        "custom": (_custom_fmeasure_like, 4, dict(seed=0, skip_tn=True, metric_kwargs={"gamma": 0.3})),
+        "custom_tn_sum": (_custom_with_tn, 3, dict(seed=1, skip_tn=False, metric_aggregation="sum")),
+        "custom_min": (_custom_fmeasure_like, 4, dict(seed=2, skip_tn=True, maximize=False, max_iters=3)),
+    }
+    for name, (func, k, kw) in cases.items():
+        pred, meta = xb.predict_using_bc_with_0approx(y, func, k, return_meta=True, mode="exact", **kw)
+        assert isinstance(pred, csr_matrix) and pred.shape == y.shape
+        assert (pred.indptr == g[name + "_indptr"]).all() and (pred.indices == g[name + "_indices"]).all(), name
+        # first sweep: the reference's (label 0, value 1) filler of short rows is not replayed (see
+        # tests/test_generic_metric_csr_cpu.py); later sweeps are the reference's
+        assert np.allclose(meta["utilities"][:1], g[name + "_util"][:1], rtol=0, atol=1e-5), name
+        assert np.allclose(meta["utilities"][1:], g[name + "_util"][1:], rtol=0, atol=1e-12), (name, meta["utilities"])
+    _, mb = xb.predict_using_bc_with_0approx(y, _custom_fmeasure_like, 4, return_meta=True, mode="batched",
+                                             batch_size=16, seed=0, skip_tn=True, metric_kwargs={"gamma": 0.3})
+    assert abs(mb["utilities"][-1] - g["custom_util"][-1]) < TOL, mb["utilities"]

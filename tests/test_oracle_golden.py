@@ -274,3 +274,43 @@ def test_online_greedy_csr_golden(oracle, golden, name, metric, skip_tn, etu):
     pred, state = oracle.online_greedy_csr(y, y if etu else t, k, metric, skip_tn=skip_tn)
     assert (pred == g[name + "_pred"]).all()
     assert np.array_equal(state, g[name + "_state"])
+
+
+def _fw_generic_csr(g):
+    from scipy.sparse import csr_matrix
+    shape = tuple(g["shape"])
+    y = csr_matrix((g["y_data"], g["y_indices"], g["y_indptr"]), shape=shape)
+    yt = csr_matrix((g["yt_data"], g["yt_indices"], g["yt_indptr"]), shape=shape)
+    return y, yt
+
+
+def test_fw_no_budget_csr(golden, oracle):
+    """k = 0 on CSR rows: the STORED labels with data * a + b >= 0 are predicted (numba_csr_functions.py:516-517,
+    :631-653), in Frank-Wolfe (frank_wolfe.py:601 with th = 0) -- pinned to the live reference"""
+    g = golden("fw_generic")
+    y, yt = _fw_generic_csr(g)
+    a, b, p, meta = oracle.find_classifier_using_fw(yt, y, "f1", 0, max_iters=8, skip_tn=True, seed=0)
+    assert np.allclose(meta["alphas"], g["k0_f1_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["k0_f1_util"], rtol=0, atol=1e-5)
+    assert a.shape == g["k0_f1_a"].shape
+    a, b, p, meta = oracle.find_classifier_using_fw(yt, y, "balanced_accuracy", 0, max_iters=5, seed=0)
+    assert np.allclose(meta["alphas"], g["k0_balacc_alphas"], rtol=0, atol=1e-9)
+    assert np.allclose(meta["utilities"], g["k0_balacc_util"], rtol=0, atol=1e-5)
+
+
+def test_threshold_csr_rows_of_randomized_prediction(golden, oracle):
+    """randomized-classifier prediction without a budget on CSR rows (frank_wolfe.py:130-172): per classifier the
+    oracle's thresholded rows, rows drawn with numpy's Generator like the reference draws them"""
+    g = golden("fw_generic")
+    y, _ = _fw_generic_csr(g)
+    n = y.shape[0]
+    rng = np.random.default_rng(11)
+    choice = np.array([rng.choice(np.arange(3), p=g["rnd_p"]) for _ in range(n)])
+    per_cls = [oracle.predict_weighted_per_instance(y, 0, th=0.0, a=g["rnd_a"][c], b=g["rnd_b"][c]) for c in range(3)]
+    idx, ptr = [], [0]
+    for i in range(n):
+        r = per_cls[choice[i]]
+        idx.extend(r.indices[r.indptr[i]:r.indptr[i + 1]])
+        ptr.append(len(idx))
+    assert (np.array(ptr) == g["rnd_pred_indptr"]).all()
+    assert (np.array(idx) == g["rnd_pred_indices"]).all()

@@ -131,6 +131,34 @@ fw_iterate_csr_kernel(const T *__restrict__ data, const int32_t *__restrict__ in
     }
 }
 
+// No budget on CSR rows (k = 0): the STORED labels of a row whose gain data * a[j] + b[j] is >= 0 are predicted
+// (numba_csr_functions.py:516-517 through :631-653 with the th = 0 of frank_wolfe.py:601); labels a row does not
+// store are never predicted, whatever b says.  One warp per row, lanes over the stored entries.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+fw_iterate_csr_k0_kernel(const T *__restrict__ data, const int32_t *__restrict__ indices,
+                         const int64_t *__restrict__ indptr, int64_t n, const T *__restrict__ t_data,
+                         const int32_t *__restrict__ t_idx, const int64_t *__restrict__ t_ptr, XfMulAdd<T> xf,
+                         double *tp, double *cnt)
+{
+    const int lane = lane_id();
+    const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int64_t s = indptr[i], e = indptr[i + 1];
+        const int64_t ts = t_ptr[i], te = t_ptr[i + 1];
+        for (int64_t q = s + lane; q < e; q += 32) {
+            const int j = indices[q];
+            const T g = xf.template apply_one<T>(j, data[q]);
+            if (g >= (T)0) {
+                int64_t y = csr_find(t_idx, ts, te, j);
+                if (y >= 0) atomicAdd(tp + j, (double)t_data[y]);
+                atomicAdd(cnt + j, 1.0);
+            }
+        }
+    }
+}
+
 // ---- confusion vectors of the iterate: C_i = [tp, fp, fn, tn] (4 stacked m-vectors) ----------------
 // fp = cnt - tp, fn = colsum(y_true) - tp, optional /n, tn = -tp - fp - fn + (1 | n)  or -1
 // (confusion_matrix.py:386-399)
@@ -1073,11 +1101,23 @@ extern "C" int xc_fw_iterate_csr(xc_ctx *ctx, const void *data, int dtype, const
 {
     XcDeviceGuard xc_guard__(ctx);
     if (!ctx || !indptr || !t_ptr || !tp || !cnt || n <= 0 || m <= 0) return XC_ERR_INVALID;
-    if (k < 1 || k > 32) return XC_ERR_INVALID;
+    if (k < 0 || k > 32 || (k == 0 && pred_idx)) return XC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     XC_CUDA_TRY(ctx, cudaMemsetAsync(tp, 0, sizeof(double) * m, st));
     XC_CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, sizeof(double) * m, st));
-    if (dtype == XC_F32) {
+    if (k == 0 && dtype == XC_F32) {
+        auto kern = fw_iterate_csr_k0_kernel<float>;
+        int grid = grid_for(ctx, kern, n);
+        XfMulAdd<float> xf{(const float *)a, (const float *)b};
+        kern<<<grid, kThreads, 0, st>>>((const float *)data, indices, indptr, n, (const float *)t_data, t_idx, t_ptr,
+                                        xf, tp, cnt);
+    } else if (k == 0 && dtype == XC_F64) {
+        auto kern = fw_iterate_csr_k0_kernel<double>;
+        int grid = grid_for(ctx, kern, n);
+        XfMulAdd<double> xf{(const double *)a, (const double *)b};
+        kern<<<grid, kThreads, 0, st>>>((const double *)data, indices, indptr, n, (const double *)t_data, t_idx, t_ptr,
+                                        xf, tp, cnt);
+    } else if (dtype == XC_F32) {
         auto kern = fw_iterate_csr_kernel<float>;
         int grid = grid_for(ctx, kern, n);
         XfMulAdd<float> xf{(const float *)a, (const float *)b};

@@ -76,8 +76,6 @@ def predict_using_randomized_weighted_classifier(y_proba: Matrix, k: int, classi
     _check_k(k)
     if k < 0:
         raise ValueError("k must be >= 0")
-    if k == 0 and isinstance(y_proba, csr_matrix):
-        raise NotImplementedError("xcolumns_b200: prediction without a budget (k=0) is implemented for dense inputs")
     to_np = lambda v: v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
     A, B, P = to_np(classifiers_a), to_np(classifiers_b), to_np(classifiers_proba)
     n, m = y_proba.shape
@@ -87,6 +85,25 @@ def predict_using_randomized_weighted_classifier(y_proba: Matrix, k: int, classi
         raise ValueError("classifiers_a, classifier_b, and classifiers_proba must have the same number of rows")
     choice = _draw_classifiers(P, n, seed)
     device = dev.pick_device(y_proba)
+    if k == 0 and isinstance(y_proba, csr_matrix):
+        # no budget on CSR rows: the STORED labels whose gain under the row's classifier is >= 0
+        # (frank_wolfe.py:152-170 -> numba_csr_functions.py:516-517); elementwise on the nnz entries on the device,
+        # gains formed like numpy does there (data dtype x classifier dtype, separate multiply and add)
+        c = dev.csr_to_device(y_proba, device)
+        gdt = torch.promote_types(c.data.dtype, torch.from_numpy(A[:0]).dtype)
+        Ad = torch.from_numpy(np.ascontiguousarray(A)).to(device=device, dtype=gdt)
+        Bd = torch.from_numpy(np.ascontiguousarray(B)).to(device=device, dtype=gdt)
+        counts = c.indptr[1:] - c.indptr[:-1]
+        cls_of = torch.repeat_interleave(torch.from_numpy(choice).to(device), counts)
+        row_of = torch.repeat_interleave(torch.arange(n, device=device), counts)
+        idx = c.indices.long()
+        keep = (c.data.to(gdt) * Ad[cls_of, idx] + Bd[cls_of, idx]) >= 0
+        kept = torch.zeros(n, dtype=torch.int64, device=device).index_add_(0, row_of[keep], torch.ones_like(row_of[keep]))
+        indptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=device), kept.cumsum(0)])
+        new_idx = c.indices[keep].cpu().numpy().astype(y_proba.indices.dtype)
+        out_dt = y_proba.data.dtype if dtype is None else dtype
+        return csr_matrix((np.ones(new_idx.shape[0], dtype=out_dt), new_idx,
+                           indptr.cpu().numpy().astype(y_proba.indptr.dtype)), shape=y_proba.shape)
     if k == 0:
         # no budget: every label with a non-negative gain under the row's classifier (frank_wolfe.py:80-105
         # with k = 0 -> weighted_prediction.py:55-56); rows are grouped by classifier like below
@@ -148,8 +165,10 @@ def find_classifier_using_fw(
     return_meta: bool = False,
     **kwargs,
 ) -> Union[RandomizedWeightedClassifier, Tuple[RandomizedWeightedClassifier, Dict[str, Any]]]:
-    """Frank-Wolfe over the confusion-matrix polytope for a macro-averaged built-in metric; same
-    arguments / defaults / return value / ``meta`` keys as xcolumns/frank_wolfe.py:407-690.
+    """Frank-Wolfe over the confusion-matrix polytope; same arguments / defaults / return value / ``meta`` keys as
+    xcolumns/frank_wolfe.py:407-690.  Built-in macro / micro / mixed objectives run the fused per-label kernels; any
+    other differentiable callable of (tp, fp, fn, tn) keeps the streaming kernels and takes its gradient and line
+    search through torch on the device (generic_fw.py).
     ``distributed=True``: y_true / y_proba are this rank's row shard; the per-iterate confusion sums
     are all-reduced and every rank ends with the same classifier."""
     distributed = kwargs.pop("distributed", False)
@@ -162,14 +181,20 @@ def find_classifier_using_fw(
     _check_k(k)
     if k < 0:
         raise ValueError("k must be >= 0")
-    if k == 0 and isinstance(y_proba, csr_matrix):
-        raise NotImplementedError("xcolumns_b200: Frank-Wolfe without a budget (k=0) is implemented for dense inputs")
     if alpha_search_algo not in ("uniform", "ternary") and search_for_best_alpha:
         raise ValueError(f"Unknown search algorithm {alpha_search_algo}")
     ternary_eps = float(alpha_tolerance) if (search_for_best_alpha and alpha_search_algo == "ternary") else 0.0
     if ternary_eps < 0 or (search_for_best_alpha and alpha_search_algo == "ternary" and not ternary_eps > 0):
         raise ValueError("alpha_search_algo='ternary' needs alpha_tolerance > 0 (it is the search's epsilon)")
-    metric_id, beta, eps = M.resolve_macro_metric(metric_func, metric_kwargs)
+    try:
+        metric_id, beta, eps = M.resolve_macro_metric(metric_func, metric_kwargs)
+        generic = False
+    except M.UnsupportedMetricError:
+        # any other differentiable callable of (tp, fp, fn, tn): same streaming kernels, gradient and line search
+        # through torch on the device (generic_fw.py; frank_wolfe.py:368-376 differentiates with autograd)
+        if not callable(metric_func):
+            raise
+        metric_id, beta, eps, generic = 0, 1.0, 1e-9, True
     n, m = y_proba.shape
     device = dev.pick_device(y_proba, y_true)
     comm = make_comm(distributed, device)
@@ -229,6 +254,30 @@ def find_classifier_using_fw(
     else:
         ctx.call("xc_colsum_dense", dev.ptr(td_.t), td_.code, n, m, td_.ld, dev.ptr(colsum), sp())
     comm.allreduce_sum_(colsum)
+
+    if generic:
+        from . import generic_fw
+        conf = generic_fw.device_conf(ctx=ctx, comm=comm, device=device, pd_=pd_, td_=td_, is_csr=is_csr, colsum=colsum,
+                                      n=n, m=m, n_global=n_global, k=k, normalize_conf_matrix=normalize_conf_matrix,
+                                      skip_tn=skip_tn)
+        A_used, B_used, P, meta = generic_fw.run(
+            conf=conf, device=device, m=m, A=A, B=B, P=P, max_iters=max_iters, maximize=maximize,
+            metric_func=metric_func, metric_kwargs=metric_kwargs, tolerance=tolerance,
+            search_for_best_alpha=search_for_best_alpha, alpha_search_algo=alpha_search_algo,
+            alpha_tolerance=alpha_tolerance, alpha_uniform_search_step=alpha_uniform_search_step, verbose=verbose)
+        if isinstance(y_true, torch.Tensor):
+            A, B = (v.to(device=y_proba.device, dtype=y_proba.dtype, copy=True) for v in (A_used, B_used))
+            P = torch.tensor(P, dtype=y_proba.dtype, device=y_proba.device)
+        else:
+            A, B = A_used.cpu().numpy(), B_used.cpu().numpy()
+        log_info(f"  Final utility of the randomized classifier: {meta.pop('final_utility')}, "
+                 f"number of sub-classifiers: {len(A)}", verbose)
+        clf = RandomizedWeightedClassifier(k, A, B, P)
+        if return_meta:
+            meta["time"] = time() - meta["time"]
+            meta["launches"] = ctx.launches()
+            return clf, meta
+        return clf
 
     mix = M.resolve_mix(metric_func)
     mix_alpha, mix_k, mix_m = mix if mix is not None else (1.0, 1.0, 1.0)
