@@ -126,7 +126,8 @@ def test_error_convention(xb):
         xb.find_classifier_using_fw(eta, eta, M.macro_f1_score_on_conf_matrix, 2, init_classifier="nope")
     with pytest.raises(ValueError):
         xb.find_classifier_using_fw(eta, eta, M.macro_f1_score_on_conf_matrix, 2, alpha_search_algo="golden")
-    with pytest.raises(NotImplementedError):   # arbitrary callables run on the device for dense rows only: loud, no fallback
-        xb.predict_using_bc_with_0approx(csr_matrix(eta), lambda tp, fp, fn, tn: tp, 2)
+    with pytest.raises(NotImplementedError):   # a LIST of callables on CSR rows: loud, no fallback (the reference's own
+        # CSR step indexes such a list by stored position, block_coordinate.py:110-127)
+        xb.predict_using_bc_with_0approx(csr_matrix(eta), [lambda tp, fp, fn, tn: tp] * 10, 2)
     with pytest.raises(ValueError):             # a list of callables must have one entry per label
         xb.predict_using_bc_with_0approx(eta, [M.binary_f1_score_on_conf_matrix] * 3, 2)

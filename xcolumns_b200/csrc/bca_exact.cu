@@ -265,22 +265,32 @@ constexpr int CL_MAX = 16;
 // than k do, stores it at dst[rank].  All threads of the CTA call it; the caller synchronises.
 // Measured motivation (profiles/r01_notes.md): with k rounds of warp arg-max run by warp 0 alone, 47 %
 // of all warp samples of the sweep were other warps parked at the barriers behind those merges.
+// The caller has filled dst[0 .. k) with empty candidates (slots no candidate claims -- fewer than k real
+// candidates -- must read as empty) and has put a block barrier between that fill and this call: the fill used to
+// live here behind a barrier of its own, two of the six block barriers of an instance.
+// Four threads share one candidate: each counts the better ones among a quarter of the list, two shuffles add the
+// partial ranks.  With cnt = 20 .. 40 candidates the old "thread t ranks candidate t" left one or two warps
+// walking the whole list while the rest of the CTA sat at the barrier behind them (ncu source page,
+// profiles/r02_notes.md section 7: 16 % of all warp samples of the sweep were that wait).
 __device__ __forceinline__ void rank_topk_smem(const Cand *src, int cnt, int k, Cand *dst)
 {
-    if (threadIdx.x < k) {   // slots no candidate claims (fewer than k real candidates) must read as empty
-        Cand e;
-        e.g = KEY_NEG_INF; e.j = 0x7fffffff; e.pad = 0;
-        dst[threadIdx.x] = e;
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
-        const Cand me = src[t];
+    const int lane = threadIdx.x & 31;
+    const int total = cnt * 4;
+    for (int base = (int)threadIdx.x - lane; base < total; base += (int)blockDim.x) {   // warp-uniform trip count
+        const int u = base + lane;
+        const bool active = u < total;
+        const int c = active ? (u >> 2) : 0, h = u & 3;
+        const Cand me = src[c];
         int rank = 0;
-        for (int q = 0; q < cnt; ++q) {
-            const Cand o = src[q];
-            rank += xc_better(o.g, o.j, me.g, me.j) ? 1 : 0;   // strict order: labels are distinct
+        if (active) {
+            for (int q = h; q < cnt; q += 4) {
+                const Cand o = src[q];
+                rank += xc_better(o.g, o.j, me.g, me.j) ? 1 : 0;   // strict order: labels are distinct
+            }
         }
-        if (rank < k) dst[rank] = me;
+        rank += __shfl_xor_sync(XC_FULL, rank, 1);
+        rank += __shfl_xor_sync(XC_FULL, rank, 2);
+        if (active && h == 0 && rank < k) dst[rank] = me;
     }
 }
 
@@ -297,11 +307,10 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
     const int nc = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     constexpr int NW = THREADS / 32;
-    __shared__ Cand s_warp[NW * 32];          // per-warp top-k (k <= 32 each)
     __shared__ Cand s_blk[32];                // block top-k
     __shared__ Cand s_in[2][CL_MAX * 32];     // candidates pushed by every CTA of the cluster (double buffered)
     __shared__ Cand s_fin[32];                // final top-k of the step
-    __shared__ Cand s_tmp[NW * 32];           // warp candidates, densely packed
+    __shared__ Cand s_tmp[NW * 32];           // per-warp top-k, densely packed: warp w owns [w * k, (w + 1) * k)
     __shared__ Cand s_keys[L == 1 ? NW * 32 : 1];   // per-warp key exchange (L == 1)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t stride = (int64_t)nc * THREADS;
@@ -338,16 +347,33 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
     // sweep, so nobody rewrites it before its turn)
     int myp_next = -1;
     if (n_order > 0 && lane < k) myp_next = __ldg(pred_idx + (order ? (int64_t)order[0] : 0) * k + lane);
+    // The visiting order is read TWO steps ahead: an in-order warp stalls at the first consumer of a load, and with
+    // one warp per scheduler nothing else can issue meanwhile (ncu, profiles/r02_exact_cluster_source.csv: 6 % of
+    // all samples sat on `row = order[s]`, 2 % on the address arithmetic behind `order[s + 1]`).
+    int64_t row_cur = n_order > 0 ? (order ? (int64_t)order[0] : 0) : 0;
+    int64_t row_n1 = n_order > 1 ? (order ? (int64_t)order[1] : 1) : 0;
+    // the index arithmetic of the DSMEM push (q / k, q % k: ~25 instructions each with a run-time k) is loop
+    // invariant for a thread's first -- and, unless nc * k > THREADS, only -- candidate
+    const int push_dst0 = (int)threadIdx.x / k, push_r0 = (int)threadIdx.x % k;
+    Cand c_empty;
+    c_empty.g = KEY_NEG_INF; c_empty.j = 0x7fffffff; c_empty.pad = 0;
+    double stn_n[L];   // used with skip_tn only: tn is never updated then, neither is its quotient
+#pragma unroll
+    for (int l = 0; l < L; ++l) stn_n[l] = stn[l] / nd;
     cluster.sync();
 
     for (int64_t s = 0; s < n_order; ++s) {
-        const int64_t row = order ? (int64_t)order[s] : s;
+        const int64_t row = row_cur;
         int32_t *prow = pred_idx + row * k;
         const int myp = myp_next;   // the row's current selection, one label per lane
+        // s_blk was last read by the push of the previous instance (a cluster barrier and a block barrier ago)
+        if (threadIdx.x < k) s_blk[threadIdx.x] = c_empty;
 #pragma unroll
         for (int l = 0; l < L; ++l) { pv[l] = pnext[l]; av[l] = anext[l]; }
         if (s + 1 < n_order) {
-            const int64_t rnext = order ? (int64_t)order[s + 1] : s + 1;
+            const int64_t rnext = row_n1;
+            row_cur = rnext;
+            if (s + 2 < n_order) row_n1 = order ? (int64_t)order[s + 2] : s + 2;
             if (lane < k) myp_next = __ldg(pred_idx + rnext * k + lane);
 #pragma unroll
             for (int l = 0; l < L; ++l) {
@@ -380,8 +406,12 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
                 const double pos_fp = sfp[l] + (double)om;
                 const double neg_fn = sfn[l] + (double)pe;
                 const double neg_tn = use_tn ? stn[l] + (double)om : stn[l];
-                const double up = xc_metric_eval(p, pos_tp / nd, pos_fp / nd, sfn[l] / nd, stn[l] / nd);
-                const double un = xc_metric_eval(p, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn / nd);
+                // skip_tn: tn is never updated (the constant -1 vector of confusion_matrix.py:391-393), so its
+                // quotient is loop invariant: 2 of the 10 float64 divisions of a label and instance
+                const double pos_tn_n = use_tn ? stn[l] / nd : stn_n[l];
+                const double neg_tn_n = use_tn ? neg_tn / nd : stn_n[l];
+                const double up = xc_metric_eval(p, pos_tp / nd, pos_fp / nd, sfn[l] / nd, pos_tn_n);
+                const double un = xc_metric_eval(p, stp[l] / nd, sfp[l] / nd, neg_fn / nd, neg_tn_n);
                 const double g = up - un;
                 gain[l] = p.maximize ? g : -g;
             }
@@ -394,21 +424,37 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
             me.g = j0 < m ? gain_key(gain[0]) : KEY_NEG_INF;
             me.j = j0 < m ? (int)j0 : 0x7fffffff;
             me.pad = 0;
-            Cand *wk = s_keys + warp * 32;
-            wk[lane] = me;
-            if (lane < k) {   // fewer than k labels in this warp: the unused slots stay empty
-                Cand e;
-                e.g = KEY_NEG_INF; e.j = 0x7fffffff; e.pad = 0;
-                s_warp[warp * 32 + lane] = e;
-            }
-            __syncwarp();
-            int rank = 0;
+            if (k <= 8) {
+                // small budgets: k rounds of hardware warp reductions on the two halves of the key (REDUX.MAX on
+                // the signed high word, then on the unsigned low word among the lanes that hold that high word);
+                // the lowest such lane wins, and lanes are in label order, so ties go to the lowest label.  ~11
+                // instructions per round against 32 x (LDS.128 + a 64-bit compare chain) for the ranking below.
+                const int khi = (int)(me.g >> 32);
+                const unsigned klo = (unsigned)(me.g & 0xffffffffLL);
+                bool alive = true;
+                for (int r = 0; r < k; ++r) {
+                    const int mh = __reduce_max_sync(XC_FULL, alive ? khi : (int)0x80000000);
+                    const bool c1 = alive && khi == mh;
+                    const unsigned ml = __reduce_max_sync(XC_FULL, c1 ? klo : 0u);
+                    const unsigned b = __ballot_sync(XC_FULL, c1 && klo == ml);
+                    if (lane == __ffs(b) - 1) {
+                        s_tmp[warp * k + r] = me;   // padding lanes carry the empty candidate
+                        alive = false;
+                    }
+                }
+            } else {
+                Cand *wk = s_keys + warp * 32;
+                wk[lane] = me;
+                if (lane < k) s_tmp[warp * k + lane] = c_empty;   // fewer than k labels in this warp: unused slots stay empty
+                __syncwarp();
+                int rank = 0;
 #pragma unroll 8
-            for (int q = 0; q < 32; ++q) {
-                const Cand o = wk[q];
-                rank += xc_better(o.g, o.j, me.g, me.j) ? 1 : 0;
+                for (int q = 0; q < 32; ++q) {
+                    const Cand o = wk[q];
+                    rank += xc_better(o.g, o.j, me.g, me.j) ? 1 : 0;
+                }
+                if (rank < k) s_tmp[warp * k + rank] = me;
             }
-            if (rank < k) s_warp[warp * 32 + rank] = me;
         } else {
             long long gkey[L];
 #pragma unroll
@@ -434,29 +480,30 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
                     if (xc_better(og, oj, w.g, w.j)) { w.g = og; w.j = oj; wl = ol; }
                 }
                 if (lane == wl && c.pad >= 0) taken |= 1u << c.pad;
-                if (lane == 0) { Cand o; o.g = w.g; o.j = w.j; o.pad = 0; s_warp[warp * 32 + r] = o; }
+                if (lane == 0) { Cand o; o.g = w.g; o.j = w.j; o.pad = 0; s_tmp[warp * k + r] = o; }
             }
         }
-        __syncthreads();
+        __syncthreads();   // (1) warp candidates packed in s_tmp, s_blk emptied; every warp is past the previous re-add
         // ---- 2b. block top-k by ranking the NW * k warp candidates, then push to every CTA ----------------
         Cand *inbuf = s_in[s & 1];
         {
-            const int cnt = NW * k;
-            for (int q = threadIdx.x; q < cnt; q += THREADS) s_tmp[q] = s_warp[(q / k) * 32 + (q % k)];
-            __syncthreads();
-            rank_topk_smem(s_tmp, cnt, k, s_blk);
-            __syncthreads();
+            // s_fin was last read by the re-add of the previous instance, which every warp left before barrier (1)
+            if (threadIdx.x < k) s_fin[threadIdx.x] = c_empty;
+            rank_topk_smem(s_tmp, NW * k, k, s_blk);
+            __syncthreads();   // (2)
             // my block's k candidates go to slot `rank` of every CTA's input buffer (DSMEM stores)
-            for (int q = threadIdx.x; q < nc * k; q += THREADS) {
-                const int dst_rank = q / k, r = q % k;
+            int dst_rank = push_dst0, r = push_r0;
+            for (int q = threadIdx.x; q < nc * k;) {
                 Cand *remote = cluster.map_shared_rank(inbuf, dst_rank);
                 remote[rank * k + r] = s_blk[r];
+                q += THREADS;
+                if (q < nc * k) { dst_rank = q / k; r = q % k; }
             }
         }
-        cluster.sync();   // release/acquire: all pushes visible
+        cluster.sync();   // release/acquire: all pushes visible (and the s_fin fill above)
         // ---- 3. every CTA ranks the nc * k candidates (identical result everywhere) ---------------------
         rank_topk_smem(inbuf, nc * k, k, s_fin);
-        __syncthreads();
+        __syncthreads();   // (3)
         // ---- 4. re-add with the new selection (block_coordinate.py:203-209) --------------------------------
         const int fin = lane < k ? s_fin[lane].j : -1;
 #pragma unroll

@@ -19,6 +19,7 @@ one streaming pass); it exists so that every ``binary_metric_func`` the referenc
 """
 from __future__ import annotations
 
+import ctypes as C
 from time import time
 from typing import Any, Callable, Dict, List, Optional, Sequence, Union
 
@@ -237,11 +238,16 @@ def bca_generic_csr_core(data: torch.Tensor, indices: torch.Tensor, indptr: np.n
                          pred: torch.Tensor, metric: "_Metric", k: int, metric_aggregation: str,
                          normalize_conf_matrix: bool, maximize: bool, tolerance: float, greedy: bool, max_iters: int,
                          shuffle_order: bool, skip_tn: bool, seed, verbose: bool, mode: str, batch_size: Optional[int],
-                         meta: Dict[str, Any]) -> torch.Tensor:
+                         meta: Dict[str, Any], state_fn: Optional[Callable] = None) -> torch.Tensor:
     """The sweeps of predict_using_bc_with_0approx on CSR rows for a callable, on tensors of ANY device (the CPU tests
     drive it with CPU tensors).  ``data`` [nnz] float, ``indices`` [nnz] int64 ascending inside a row, ``indptr`` host
-    int64, ``pred`` [n, k] int64 label ids with -1 for unused slots.  Returns the final compact prediction."""
+    int64, ``pred`` [n, k] int64 label ids with -1 for unused slots.  ``state_fn(pred) -> [4, m]`` recomputes the
+    confusion sums at the sweep boundaries (default: ``csr_state_from_pred``; on the GPU the ordered C kernel, so that
+    the sums are added in the reference's row order instead of the order atomics happen to land in).  Returns the final
+    compact prediction."""
     dev_ = data.device
+    if state_fn is None:
+        state_fn = lambda pr: csr_state_from_pred(data, indices, row_of, pr, m, skip_tn, n)
     n_true = n
     n_div = n if normalize_conf_matrix else 1           # utilities (block_coordinate.py:403-405)
     n_order = n if normalize_conf_matrix else 1          # :403-414
@@ -263,7 +269,7 @@ def bca_generic_csr_core(data: torch.Tensor, indices: torch.Tensor, indptr: np.n
         if greedy:
             state = torch.zeros((4, m), dtype=torch.float64, device=dev_)
         elif new_u is None:
-            state = csr_state_from_pred(data, indices, row_of, pred, m, skip_tn, n_true)
+            state = state_fn(pred)
         old_u = _utility(metric, metric_aggregation, state, n_div) if (new_u is None or greedy) else new_u
         tp, fp, fn, tn = state[0], state[1], state[2], state[3]
         if mode == "exact":
@@ -377,7 +383,7 @@ def bca_generic_csr_core(data: torch.Tensor, indices: torch.Tensor, indptr: np.n
                         tn -= d_fp
                     pred[rows] = newp
             cnt_host = None   # not maintained in batched mode
-        state = csr_state_from_pred(data, indices, row_of, pred, m, skip_tn, n_true)   # :465-467
+        state = state_fn(pred)   # :465-467
         new_u = _utility(metric, metric_aggregation, state, n_div)
         greedy = False
         meta["iters"] = j
@@ -413,9 +419,25 @@ def _bca_generic_csr(y_proba: csr_matrix, binary_metric_func, k: int, metric_agg
     if greedy and mode != "exact":
         raise NotImplementedError("init_y_pred='greedy' needs the sequential mode (mode='exact')")
     meta["mode"] = mode
+    ctx = dev.ctx_for(device)
+
+    def state_fn(pr: torch.Tensor) -> torch.Tensor:
+        """confusion sums of the compact prediction with one running float64 sum per label in row order
+        (XC_SUM_ORDERED = 1: what numba's row loop does, numba_csr_functions.py:144-258)"""
+        st = torch.zeros((4, m), dtype=torch.float64, device=device)
+        p32 = pr.to(torch.int32).contiguous()
+        ctx.call("xc_confmat_csr_compact", dev.ptr(c.data), dev.ptr(c.indices), dev.ptr(c.indptr), c.code, dev.ptr(p32),
+                 k, n, m, 1, C.c_void_p(st[0].data_ptr()), C.c_void_p(st[1].data_ptr()), C.c_void_p(st[2].data_ptr()),
+                 dev.stream_ptr(device))
+        if skip_tn:
+            st[3].fill_(-1.0)
+        else:
+            st[3] = -st[0] - st[1] - st[2] + n
+        return st
+
     pred = bca_generic_csr_core(c.data, c.indices.long(), c.indptr.cpu().numpy().astype(np.int64), n, m, pred, metric, k,
                                 metric_aggregation, normalize_conf_matrix, maximize, tolerance, greedy, max_iters,
-                                shuffle_order, skip_tn, seed, verbose, mode, batch_size, meta)
+                                shuffle_order, skip_tn, seed, verbose, mode, batch_size, meta, state_fn=state_fn)
     y_pred = finish_pred_fn(y_proba, pred.to(torch.int32), m, y_pred_format, None)
     if return_meta:
         meta["time"] = time() - meta["time"]
