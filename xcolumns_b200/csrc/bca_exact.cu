@@ -260,6 +260,40 @@ bca_exact_dense_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld, const 
 //   into all peers' smem (DSMEM stores) -> barrier.cluster -> every CTA merges the <= 16*k candidates.
 constexpr int CL_MAX = 16;
 
+// ---- candidate exchange through asynchronous DSMEM stores that complete on the RECEIVER's mbarrier -----------------
+// (st.async ... mbarrier::complete_tx::bytes): the sender does not wait for its remote stores, the receiver waits for
+// the bytes it expects.  The first version used plain DSMEM stores + barrier.cluster: its release fence (ERRBAR in the
+// SASS) made every CTA wait for the round trip of its own remote stores before it could even arrive -- 8 % of all
+// warp samples of the sweep plus 5 % in the barrier itself (ncu, profiles/r02_notes.md section 7).
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_addr_of(uint32_t local_smem_addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_16(uint32_t remote_addr, long long a, long long b, uint32_t remote_mbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+                 :: "r"(remote_addr), "l"(a), "l"(b), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t mbar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    } while (!done);
+}
+
 // top-k of `cnt` candidates in smem by ranking: thread t < cnt counts the candidates that beat
 // candidate t (cnt broadcast-friendly smem reads, no shuffle chains, no serial rounds) and, if fewer
 // than k do, stores it at dst[rank].  All threads of the CTA call it; the caller synchronises.
@@ -312,6 +346,7 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
     __shared__ Cand s_fin[32];                // final top-k of the step
     __shared__ Cand s_tmp[NW * 32];           // per-warp top-k, densely packed: warp w owns [w * k, (w + 1) * k)
     __shared__ Cand s_keys[L == 1 ? NW * 32 : 1];   // per-warp key exchange (L == 1)
+    __shared__ alignas(8) unsigned long long s_mbar[2];   // one mbarrier per input buffer
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t stride = (int64_t)nc * THREADS;
     const int64_t j0 = (int64_t)rank * THREADS + threadIdx.x;
@@ -350,8 +385,9 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
     // The visiting order is read TWO steps ahead: an in-order warp stalls at the first consumer of a load, and with
     // one warp per scheduler nothing else can issue meanwhile (ncu, profiles/r02_exact_cluster_source.csv: 6 % of
     // all samples sat on `row = order[s]`, 2 % on the address arithmetic behind `order[s + 1]`).
+    // (kept as the raw 32-bit value: widening it right behind the load would make THAT the first consumer)
     int64_t row_cur = n_order > 0 ? (order ? (int64_t)order[0] : 0) : 0;
-    int64_t row_n1 = n_order > 1 ? (order ? (int64_t)order[1] : 1) : 0;
+    int row_n1 = n_order > 1 ? (order ? order[1] : 1) : 0;
     // the index arithmetic of the DSMEM push (q / k, q % k: ~25 instructions each with a run-time k) is loop
     // invariant for a thread's first -- and, unless nc * k > THREADS, only -- candidate
     const int push_dst0 = (int)threadIdx.x / k, push_r0 = (int)threadIdx.x % k;
@@ -360,20 +396,34 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
     double stn_n[L];   // used with skip_tn only: tn is never updated then, neither is its quotient
 #pragma unroll
     for (int l = 0; l < L; ++l) stn_n[l] = stn[l] / nd;
-    cluster.sync();
+    const uint32_t mbar0 = smem_addr_u32(&s_mbar[0]), mbar1 = smem_addr_u32(&s_mbar[1]);
+    const uint32_t in0 = smem_addr_u32(&s_in[0][0]), in1 = smem_addr_u32(&s_in[1][0]);
+    if (threadIdx.x == 0) {
+        mbar_init(mbar0, 1);
+        mbar_init(mbar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t push_bytes = (uint32_t)(nc * k) * (uint32_t)sizeof(Cand);
+    cluster.sync();   // every CTA's mbarriers are initialised before anybody pushes
 
     for (int64_t s = 0; s < n_order; ++s) {
         const int64_t row = row_cur;
         int32_t *prow = pred_idx + row * k;
         const int myp = myp_next;   // the row's current selection, one label per lane
-        // s_blk was last read by the push of the previous instance (a cluster barrier and a block barrier ago)
+        // s_blk was last read by the push of the previous instance (two block barriers ago)
         if (threadIdx.x < k) s_blk[threadIdx.x] = c_empty;
+        // Arm this instance's input buffer: nc * k candidates are expected.  Pushes of faster peers may already have
+        // landed -- the phase cannot complete before this arrival.  The buffer's previous use (instance s - 2) is over
+        // everywhere: a peer pushes instance s only after it has received every CTA's push of s - 1, which a CTA sends
+        // after its final ranking of s - 2.
+        const uint32_t mbar = (s & 1) ? mbar1 : mbar0;
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(mbar, push_bytes);
 #pragma unroll
         for (int l = 0; l < L; ++l) { pv[l] = pnext[l]; av[l] = anext[l]; }
         if (s + 1 < n_order) {
-            const int64_t rnext = row_n1;
+            const int64_t rnext = (int64_t)row_n1;
             row_cur = rnext;
-            if (s + 2 < n_order) row_n1 = order ? (int64_t)order[s + 2] : s + 2;
+            if (s + 2 < n_order) row_n1 = order ? order[s + 2] : (int)(s + 2);
             if (lane < k) myp_next = __ldg(pred_idx + rnext * k + lane);
 #pragma unroll
             for (int l = 0; l < L; ++l) {
@@ -491,16 +541,20 @@ bca_exact_dense_cluster_kernel(const TE *__restrict__ eta, int64_t m, int64_t ld
             if (threadIdx.x < k) s_fin[threadIdx.x] = c_empty;
             rank_topk_smem(s_tmp, NW * k, k, s_blk);
             __syncthreads();   // (2)
-            // my block's k candidates go to slot `rank` of every CTA's input buffer (DSMEM stores)
+            // my block's k candidates go to slot `rank` of every CTA's input buffer (asynchronous DSMEM stores that
+            // complete on the receiver's mbarrier; my own CTA is one of the receivers)
+            const uint32_t in_base = (s & 1) ? in1 : in0;
             int dst_rank = push_dst0, r = push_r0;
             for (int q = threadIdx.x; q < nc * k;) {
-                Cand *remote = cluster.map_shared_rank(inbuf, dst_rank);
-                remote[rank * k + r] = s_blk[r];
+                const Cand c = s_blk[r];
+                const long long w1 = (long long)(((unsigned long long)(unsigned)c.pad << 32) | (unsigned)c.j);
+                st_async_16(cluster_addr_of(in_base + (uint32_t)(rank * k + r) * (uint32_t)sizeof(Cand), (uint32_t)dst_rank),
+                            c.g, w1, cluster_addr_of(mbar, (uint32_t)dst_rank));
                 q += THREADS;
                 if (q < nc * k) { dst_rank = q / k; r = q % k; }
             }
         }
-        cluster.sync();   // release/acquire: all pushes visible (and the s_fin fill above)
+        mbar_wait_parity(mbar, (uint32_t)((s >> 1) & 1));   // all nc * k candidates of this instance have landed
         // ---- 3. every CTA ranks the nc * k candidates (identical result everywhere) ---------------------
         rank_topk_smem(inbuf, nc * k, k, s_fin);
         __syncthreads();   // (3)
