@@ -394,6 +394,44 @@ def bench_csr(args, device, what, n=153000, m=670000, nnz=100, cpu=True):
     return out
 
 
+def bench_exact_small(args, device, cpu=True):
+    """C1 / C2 (BASELINE.json configs[0] and the small-m case): the bit-exact sequential mode through the public API
+    on device-resident scores -- one launch per sweep, latency bound; the CPU port runs the same
+    call and must report the same utilities bit for bit."""
+    import torch
+    from xcolumns_b200 import predict_optimizing_macro_f1_score_using_bc
+    from xcolumns_b200.synth import dense_probs
+    out = {"metric": "BCA macro-F1@5 instances/sec per sweep (sequential-exact mode)", "unit": "instances/s",
+           "dtype": "f64 gains on f32 scores", "data": "synthetic", "configs": {}}
+    for name, n, m, seed in (("C1", 10000, 1000, 1001), ("C2", 3800, 4000, 1002)):
+        eta = dense_probs(n, m, seed=seed, tie_free=False)
+        eta_d = torch.from_numpy(eta).to(device)
+        best, meta = None, None
+        for _ in range(3):
+            torch.cuda.synchronize(device)
+            t0 = time.time()
+            _, meta = predict_optimizing_macro_f1_score_using_bc(eta_d, args.k, seed=0, mode="exact", return_meta=True,
+                                                                 y_pred_format="indices")
+            torch.cuda.synchronize(device)
+            dt = time.time() - t0
+            best = dt if best is None else min(best, dt)
+        cfg = {"workload": f"dense f32 n={n} m={m} k={args.k} macro-F1 BCA (sequential, bit-exact)", "sweeps": meta["iters"],
+               "value": n * meta["iters"] / best, "us_per_instance": 1e6 * best / (n * meta["iters"]),
+               "ms_per_call": 1e3 * best, "utility": meta["utilities"][-1]}
+        if cpu:
+            from oracle import oracle as orc
+            orc.build()
+            t0 = time.time()
+            _, ometa = orc.predict_using_bc_with_0approx(eta, "f1", args.k, seed=0, skip_tn=True)
+            dtc = time.time() - t0
+            cfg["cpu_baseline"] = {"value": n * ometa["iters"] / dtc, "unit": "instances/s", "cores": 1, "kind": "port",
+                                   "sample": f"the whole call ({ometa['iters']} sweeps in {dtc:.2f} s)"}
+            cfg["utilities_bit_equal_to_cpu_port"] = bool(list(meta["utilities"]) == list(ometa["utilities"]))
+        out["configs"][name] = cfg
+    out["value"] = out["configs"]["C1"]["value"]
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # multi-GPU parity: a small sharded problem against the single-GPU sequential (bit-pinned) mode
 # --------------------------------------------------------------------------------------------
@@ -676,7 +714,8 @@ def main():
         for name, fn in (("fw_dense", lambda: bench_fw(args, device, comm, cpu=not args.no_cpu)),
                          ("bca_csr_recall", lambda: bench_csr(args, device, "recall", cpu=not args.no_cpu)),
                          ("coverage_csr", lambda: bench_csr(args, device, "coverage", cpu=not args.no_cpu)),
-                         ("bca_csr_f1", lambda: bench_csr(args, device, "f1", cpu=False))):
+                         ("bca_csr_f1", lambda: bench_csr(args, device, "f1", cpu=False)),
+                         ("bca_exact_small", lambda: bench_exact_small(args, device, cpu=not args.no_cpu))):
             try:
                 sec[name] = fn()
             except Exception as e:  # a secondary line must never take the headline down
