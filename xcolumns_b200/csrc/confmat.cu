@@ -201,8 +201,33 @@ confmat_compact_ordered_kernel(const T *__restrict__ yt, int64_t ld, const int32
     double stp = 0.0, sfp = 0.0, sfn = 0.0;
     const T one = (T)1;
     const int jj = (int)j;
-#pragma unroll 2
-    for (int64_t i = 0; i < n; ++i) {
+    // The three running sums are chains of dependent float64 adds in row order (that order IS the contract), but the
+    // loads are not: U rows are fetched before their adds are issued, so the L2 latency of a row is paid once per U
+    // rows instead of once per two (a label's thread walks all n rows; with m = 1 000 only four CTAs exist and
+    // nothing else hides the latency -- this pass follows every sweep of the sequential mode).
+    constexpr int U = 8;
+    int64_t i = 0;
+    for (; i + U <= n; i += U) {
+        T y[U];
+        bool sel[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) y[u] = ldx(yt + (i + u) * ld + j);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sel[u] = false;
+            for (int t = 0; t < k; ++t) sel[u] |= (__ldg(pred + (i + u) * k + t) == jj);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (sel[u]) {
+                stp += (double)y[u];
+                sfp += (double)(T)(one - y[u]);
+            } else {
+                sfn += (double)y[u];
+            }
+        }
+    }
+    for (; i < n; ++i) {
         T y = ldx(yt + i * ld + j);
         bool sel = false;
         for (int t = 0; t < k; ++t) sel |= (__ldg(pred + i * k + t) == jj);
