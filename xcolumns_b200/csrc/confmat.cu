@@ -243,6 +243,65 @@ confmat_compact_ordered_kernel(const T *__restrict__ yt, int64_t ld, const int32
     fn[j] = sfn;
 }
 
+// Same sums, same order, with the prediction as a bitmap: word (i, j / 32) holds the "row i predicts label j" bits of
+// the 32 labels one warp owns, so a row costs a warp ONE broadcast load instead of k loads + k compares per lane.
+// Measured motive (ncu launch list of a C1 call, profiles/r02_launches_exact_c1.csv): the pass above took 3.3 ms for
+// 10 000 x 1 000 -- 650 cycles per row and thread, the k dependent load -> compare pairs of a run-time k serialise on
+// an in-order warp -- which is 8 % of a sequential sweep.
+__global__ void __launch_bounds__(kThreads)
+pred_bitmap_kernel(const int32_t *__restrict__ pred, int64_t total, int k, int64_t words_per_row, uint32_t *bitmap)
+{
+    const int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (q >= total) return;
+    const int j = pred[q];
+    if (j >= 0) atomicOr(bitmap + (q / k) * words_per_row + (j >> 5), 1u << (j & 31));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+confmat_bitmap_ordered_kernel(const T *__restrict__ yt, int64_t ld, const uint32_t *__restrict__ bitmap,
+                              int64_t words_per_row, int64_t n, int64_t m, double *tp, double *fp, double *fn)
+{
+    const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;   // kThreads is a multiple of 32: a warp's labels
+    if (j >= m) return;                                                // share the word j >> 5
+    double stp = 0.0, sfp = 0.0, sfn = 0.0;
+    const T one = (T)1;
+    const uint32_t *bw = bitmap + (j >> 5);
+    const int bit = (int)(j & 31);
+    constexpr int U = 8;
+    int64_t i = 0;
+    for (; i + U <= n; i += U) {
+        T y[U];
+        uint32_t w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            y[u] = ldx(yt + (i + u) * ld + j);
+            w[u] = __ldg(bw + (i + u) * words_per_row);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if ((w[u] >> bit) & 1u) {
+                stp += (double)y[u];
+                sfp += (double)(T)(one - y[u]);
+            } else {
+                sfn += (double)y[u];
+            }
+        }
+    }
+    for (; i < n; ++i) {
+        const T y = ldx(yt + i * ld + j);
+        if ((__ldg(bw + i * words_per_row) >> bit) & 1u) {
+            stp += (double)y;
+            sfp += (double)(T)(one - y);
+        } else {
+            sfn += (double)y;
+        }
+    }
+    tp[j] = stp;
+    fp[j] = sfp;
+    fn[j] = sfn;
+}
+
 // ---- CSR x CSR ------------------------------------------------------------------------------------
 // products exactly as numba forms them: a*b in T; a*(1.0-b) in float64 rounded once to T
 template <typename T> __device__ __forceinline__ T mul_round(T a, T b) { return (T)(a * b); }
@@ -568,6 +627,25 @@ extern "C" int xc_confmat_dense_compact(xc_ctx *ctx, const void *y_true, int dty
     cudaStream_t st = (cudaStream_t)stream;
     if (order == XC_SUM_ORDERED) {
         int grid = (int)((m + kThreads - 1) / kThreads);
+        const int64_t words_per_row = (m + 31) / 32;
+        const size_t bitmap_bytes = (size_t)n * (size_t)words_per_row * 4;
+        if (bitmap_bytes <= ((size_t)256 << 20)) {
+            void *scratch = nullptr;
+            int rc = xc_ctx_scratch(ctx, bitmap_bytes, &scratch);
+            if (rc) return rc;
+            uint32_t *bitmap = (uint32_t *)scratch;
+            XC_CUDA_TRY(ctx, cudaMemsetAsync(bitmap, 0, bitmap_bytes, st));
+            const int64_t total = n * (int64_t)k;
+            pred_bitmap_kernel<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, st>>>(pred_idx, total, k,
+                                                                                               words_per_row, bitmap);
+            XC_LAUNCHED(ctx);
+            if (dtype == XC_F32)
+                confmat_bitmap_ordered_kernel<float><<<grid, kThreads, 0, st>>>((const float *)y_true, ld, bitmap, words_per_row, n, m, tp, fp, fn);
+            else
+                confmat_bitmap_ordered_kernel<double><<<grid, kThreads, 0, st>>>((const double *)y_true, ld, bitmap, words_per_row, n, m, tp, fp, fn);
+            XC_LAUNCHED(ctx);
+            return XC_OK;
+        }
         if (dtype == XC_F32)
             confmat_compact_ordered_kernel<float><<<grid, kThreads, 0, st>>>((const float *)y_true, ld, pred_idx, k, n, m, tp, fp, fn);
         else
