@@ -237,8 +237,7 @@ def find_classifier_using_fw(
     is_csr = isinstance(y_proba, csr_matrix)
     if is_csr:
         pd_ = dev.csr_to_device(y_proba, device)
-        td_ = dev.csr_to_device(y_true, device, pd_.data.cpu().numpy().dtype if False else np.dtype(
-            np.float32 if pd_.code == 0 else np.float64))
+        td_ = dev.csr_to_device(y_true, device, np.dtype(np.float32 if pd_.code == 0 else np.float64))
         wdt = pd_.data.dtype
     else:
         pd_ = dev.dense_to_device(y_proba, device)
