@@ -146,7 +146,10 @@ XC_API int xc_confmat_dense(xc_ctx *ctx, const void *y_true, int64_t ldt, const 
                             int64_t ldp, int dtype, int64_t n, int64_t m, int axis, int order,
                             int acc_f32, double *tp, double *fp, double *fn, void *stream);
 /* same sums with a compact prediction (k ids per row); colsum (optional, fast order only) is
- * sum_i y_true[i][j] so that fn = colsum - tp without a second pass over y_true.            */
+ * sum_i y_true[i][j] so that fn = colsum - tp without a second pass over y_true.
+ * XC_SUM_ORDERED: one thread per label adds its column strictly in row order; the prediction is
+ * first expanded into a bitmap (n x ceil(m / 32) words in the context's scratch buffer, when that
+ * is <= 256 MB) so that a row costs a warp one broadcast load instead of k loads per lane.   */
 XC_API int xc_confmat_dense_compact(xc_ctx *ctx, const void *y_true, int dtype, int64_t ld,
                                     const int32_t *pred_idx, int k, int64_t n, int64_t m,
                                     int order, const double *colsum, double *tp, double *fp,
